@@ -1,0 +1,81 @@
+// fs2d_common.cuh -- shared device helpers for the sm_100a kernels of libfs2d.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fs2d.h"
+
+namespace fs2d {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+#define FS2D_CUDA_CHECK(expr)                                                              \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            fs2d::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return FS2D_E_CUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+#define FS2D_REQUIRE(cond, msg)                                   \
+    do {                                                          \
+        if (!(cond)) {                                            \
+            fs2d::set_error("bad argument: %s (%s)", msg, #cond); \
+            return FS2D_E_BADARG;                                 \
+        }                                                         \
+    } while (0)
+#define FS2D_LAUNCH_CHECK() FS2D_CUDA_CHECK(cudaGetLastError())
+
+int check_dom(const fs2d_dom &d);
+bool is_pow2(float x);
+
+// ---- indexing (clamp-to-edge sample(), fs/differentiation.py:4-9) -----------------------------
+__device__ __forceinline__ int CR(const fs2d_dom &d, int r) { return min(max(r, d.clo), d.chi); }
+__device__ __forceinline__ int CJ(const fs2d_dom &d, int j) { return min(max(j, 0), d.Y - 1); }
+__device__ __forceinline__ size_t IX(const fs2d_dom &d, int r, int j) { return (size_t)r * (size_t)d.Y + (size_t)j; }
+
+__device__ __forceinline__ float ld1(const float *f, const fs2d_dom &d, int r, int j) {
+    return __ldg(f + IX(d, CR(d, r), CJ(d, j)));
+}
+__device__ __forceinline__ float2 ld2(const float *f, const fs2d_dom &d, int r, int j) {
+    return __ldg(reinterpret_cast<const float2 *>(f) + IX(d, CR(d, r), CJ(d, j)));
+}
+
+// ---- float2 arithmetic with the reference's per-component order ----------------------------------
+__device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 operator-(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 operator-(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 operator*(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+__device__ __forceinline__ float2 operator*(float s, float2 a) { return make_float2(s * a.x, s * a.y); }
+__device__ __forceinline__ float2 operator*(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ float2 operator/(float2 a, float s) { return make_float2(a.x / s, a.y / s); }
+__device__ __forceinline__ float2 operator/(float2 a, float2 b) { return make_float2(a.x / b.x, a.y / b.y); }
+
+// Division by a grid constant c.  When c is a power of two, x / c == x * (1/c) bit-for-bit (exact
+// scaling), so the pow2 instantiation avoids the IEEE division sequence without changing results.
+template <bool P2>
+struct DivC {
+    float c, inv;
+    __host__ __device__ DivC(float c_) : c(c_), inv(1.0f / c_) {}
+    __device__ __forceinline__ float operator()(float x) const { return P2 ? x * inv : x / c; }
+    __device__ __forceinline__ float2 operator()(float2 x) const {
+        return P2 ? make_float2(x.x * inv, x.y * inv) : make_float2(x.x / c, x.y / c);
+    }
+};
+
+// fs/differentiation.py:12-14
+__device__ __forceinline__ float sign1(float x) { return x < 0.0f ? -1.0f : 1.0f; }
+
+// dense-kernel launch geometry: block = (TX, TY) threads, one cell per thread
+constexpr int TX = 64;
+constexpr int TY = 4;
+inline dim3 dense_block() { return dim3(TX, TY, 1); }
+inline dim3 dense_grid(const fs2d_dom &d) {
+    return dim3((unsigned)((d.r1 - d.r0 + TY - 1) / TY), (unsigned)((d.Y + TX - 1) / TX), 1);
+}
+#define FS2D_CELL(d, r, j)                                   \
+    const int j = blockIdx.y * blockDim.x + threadIdx.x;     \
+    const int r = (d).r0 + blockIdx.x * blockDim.y + threadIdx.y; \
+    if (j >= (d).Y || r >= (d).r1) return;
+
+}  // namespace fs2d

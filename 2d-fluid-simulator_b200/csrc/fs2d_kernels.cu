@@ -1,0 +1,647 @@
+// fs2d_kernels.cu -- dense stencil kernels + sparse BC kernels of libfs2d.so (sm_100a).
+//
+// One kernel per reference Taichi kernel (file:line cited at each).  All kernels are pure
+// 5-/9-/13-point fp32 stencils: HBM-bandwidth bound, no tensor cores.  Literal operation order of
+// the reference source, compiled with -fmad=false, so outputs are bit-identical to the oracle.
+#include <cstdarg>
+#include <cstdio>
+#include <cmath>
+
+#include "fs2d_common.cuh"
+
+namespace fs2d {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+bool is_pow2(float x) {
+    int e;
+    return x > 0.0f && std::isfinite(x) && std::frexp(x, &e) == 0.5f && (1.0f / x) * x == 1.0f;
+}
+int check_dom(const fs2d_dom &d) {
+    FS2D_REQUIRE(d.rows > 0 && d.Y > 0, "empty domain");
+    FS2D_REQUIRE(0 <= d.r0 && d.r0 <= d.r1 && d.r1 <= d.rows, "row range outside the local array");
+    FS2D_REQUIRE(0 <= d.clo && d.clo <= d.chi && d.chi < d.rows, "clamp range outside the local array");
+    return FS2D_OK;
+}
+
+// =============================================================================================
+// sparse boundary conditions
+// =============================================================================================
+// fs/boundary_condition.py:16-39 -- phase 1: evaluate every entry from the pre-kernel state
+__global__ void k_vel_bc_gather(const float2 *__restrict__ v, const float2 *__restrict__ bc_const,
+                                const int32_t *__restrict__ tgt, const int32_t *__restrict__ src,
+                                const uint8_t *__restrict__ kind, float2 *__restrict__ scratch, int n) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    uint8_t k = kind[e];
+    float2 out;
+    if (k == 0) {  // ghost cell two behind the face: v[tgt] = -v[src]  (:27-34)
+        out = -v[src[e]];
+    } else if (k == 1) {  // inflow: v = bc_const  (:35-36)
+        out = bc_const[tgt[e]];
+    } else {  // outflow: v.x = max(v(i-1,j).x, 0.05), y untouched  (:37-39)
+        out = v[tgt[e]];
+        out.x = fmaxf(v[src[e]].x, 0.05f);
+    }
+    scratch[e] = out;
+}
+__global__ void k_vel_bc_scatter(float2 *__restrict__ v, const int32_t *__restrict__ tgt,
+                                 const float2 *__restrict__ scratch, int n) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) v[tgt[e]] = scratch[e];
+}
+
+// fs/boundary_condition.py:41-65
+__global__ void k_p_bc_gather(const float *__restrict__ p, const int32_t *__restrict__ src0,
+                              const int32_t *__restrict__ src1, const uint8_t *__restrict__ kind,
+                              float *__restrict__ scratch, int n) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    uint8_t k = kind[e];
+    float out;
+    if (k == 0) out = p[src0[e]];
+    else if (k == 1) out = (p[src0[e]] + p[src1[e]]) / 2.0f;
+    else out = 0.0f;
+    scratch[e] = out;
+}
+__global__ void k_p_bc_scatter(float *__restrict__ p, const int32_t *__restrict__ tgt,
+                               const float *__restrict__ scratch, int n) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) p[tgt[e]] = scratch[e];
+}
+
+// =============================================================================================
+// stencil building blocks (fs/differentiation.py:41-60), per component of a float2 field
+// =============================================================================================
+template <bool P2>
+__device__ __forceinline__ float2 diff_x2(const float *f, const fs2d_dom &d, int r, int j, DivC<P2> ddx) {
+    return ddx(0.5f * (ld2(f, d, r + 1, j) - ld2(f, d, r - 1, j)));
+}
+template <bool P2>
+__device__ __forceinline__ float2 diff_y2(const float *f, const fs2d_dom &d, int r, int j, DivC<P2> ddx) {
+    return ddx(0.5f * (ld2(f, d, r, j + 1) - ld2(f, d, r, j - 1)));
+}
+template <bool P2>
+__device__ __forceinline__ float diff_x1(const float *f, const fs2d_dom &d, int r, int j, DivC<P2> ddx) {
+    return ddx(0.5f * (ld1(f, d, r + 1, j) - ld1(f, d, r - 1, j)));
+}
+template <bool P2>
+__device__ __forceinline__ float diff_y1(const float *f, const fs2d_dom &d, int r, int j, DivC<P2> ddx) {
+    return ddx(0.5f * (ld1(f, d, r, j + 1) - ld1(f, d, r, j - 1)));
+}
+// (diff2_x + diff2_y) of a float2 field; ddx2 divides by dx*dx
+template <bool P2>
+__device__ __forceinline__ float2 laplace2(const float *f, const fs2d_dom &d, int r, int j, float2 c, DivC<P2> ddx2) {
+    float2 d2x = ddx2(ld2(f, d, r + 1, j) - 2.0f * c + ld2(f, d, r - 1, j));
+    float2 d2y = ddx2(ld2(f, d, r, j + 1) - 2.0f * c + ld2(f, d, r, j - 1));
+    return d2x + d2y;
+}
+
+// fs/advection.py:12-24
+template <bool P2>
+__device__ __forceinline__ float2 advect_upwind(const float *vc, const fs2d_dom &d, int r, int j, float2 c,
+                                                DivC<P2> ddx) {
+    int k = c.x < 0.0f ? r : r - 1;
+    float2 a = c.x * ddx(ld2(vc, d, k + 1, j) - ld2(vc, d, k, j));
+    k = c.y < 0.0f ? j : j - 1;
+    float2 b = c.y * ddx(ld2(vc, d, r, k + 1) - ld2(vc, d, r, k));
+    return a + b;
+}
+// fs/advection.py:27-60
+__device__ __forceinline__ float2 advect_kk(const float *vc, const fs2d_dom &d, int r, int j, float2 c, float dx) {
+    const float six_dx = 6.0f * dx;
+    float k0, k1, k2, k3, k4;
+    if (c.x < 0.0f) { k0 = -2.0f; k1 = 10.0f; k2 = -9.0f; k3 = 2.0f; k4 = -1.0f; }
+    else { k0 = 1.0f; k1 = -2.0f; k2 = 9.0f; k3 = -10.0f; k4 = 2.0f; }
+    float2 acc = ld2(vc, d, r + 2, j) * k0;
+    acc = acc + ld2(vc, d, r + 1, j) * k1;
+    acc = acc + c * k2;
+    acc = acc + ld2(vc, d, r - 1, j) * k3;
+    acc = acc + ld2(vc, d, r - 2, j) * k4;
+    float2 a = acc / six_dx;
+    if (c.y < 0.0f) { k0 = -2.0f; k1 = 10.0f; k2 = -9.0f; k3 = 2.0f; k4 = -1.0f; }
+    else { k0 = 1.0f; k1 = -2.0f; k2 = 9.0f; k3 = -10.0f; k4 = 2.0f; }
+    acc = ld2(vc, d, r, j + 2) * k0;
+    acc = acc + ld2(vc, d, r, j + 1) * k1;
+    acc = acc + c * k2;
+    acc = acc + ld2(vc, d, r, j - 1) * k3;
+    acc = acc + ld2(vc, d, r, j - 2) * k4;
+    float2 b = acc / six_dx;
+    return c.x * a + c.y * b;
+}
+
+// =============================================================================================
+// fs/solver.py:94-107  MacSolver._update_velocities
+// =============================================================================================
+template <bool P2, int SCHEME>
+__global__ void __launch_bounds__(TX *TY)
+    k_mac_update(float *__restrict__ vn, const float *__restrict__ vc, const float *__restrict__ pc,
+                 const uint8_t *__restrict__ mask, fs2d_dom d, float dt, float dx, DivC<P2> ddx, DivC<P2> ddx2,
+                 float re) {
+    FS2D_CELL(d, r, j)
+    const size_t idx = IX(d, r, j);
+    if (mask[idx] != 0) return;
+    const float2 c = __ldg(reinterpret_cast<const float2 *>(vc) + idx);
+    float2 adv = SCHEME == FS2D_SCHEME_UPWIND ? advect_upwind<P2>(vc, d, r, j, c, ddx) : advect_kk(vc, d, r, j, c, dx);
+    float2 gp = make_float2(diff_x1<P2>(pc, d, r, j, ddx), diff_y1<P2>(pc, d, r, j, ddx));
+    float2 lap = laplace2<P2>(vc, d, r, j, c, ddx2) / re;
+    reinterpret_cast<float2 *>(vn)[idx] = c + dt * (-adv - gp + lap);
+}
+
+// =============================================================================================
+// fs/solver.py:229-240  CipMacSolver._non_advection_phase
+// =============================================================================================
+template <bool P2>
+__global__ void __launch_bounds__(TX *TY)
+    k_cip_nonadv(float *__restrict__ fn, const float *__restrict__ fc, const float *__restrict__ pc,
+                 const uint8_t *__restrict__ mask, fs2d_dom d, float dt, DivC<P2> ddx, DivC<P2> ddx2, float re) {
+    FS2D_CELL(d, r, j)
+    const size_t idx = IX(d, r, j);
+    if (mask[idx] == 1) return;
+    const float2 c = __ldg(reinterpret_cast<const float2 *>(fc) + idx);
+    float2 gp = make_float2(diff_x1<P2>(pc, d, r, j, ddx), diff_y1<P2>(pc, d, r, j, ddx));
+    float2 g = -gp + laplace2<P2>(fc, d, r, j, c, ddx2) / re;
+    reinterpret_cast<float2 *>(fn)[idx] = c + g * dt;
+}
+
+// fs/solver.py:242-261  _non_advection_phase_grad (raw indexing -> clamp)
+template <bool P2>
+__global__ void __launch_bounds__(TX *TY)
+    k_cip_nonadv_grad(float *__restrict__ fxn, float *__restrict__ fyn, const float *__restrict__ fxc,
+                      const float *__restrict__ fyc, const float *__restrict__ fc, const float *__restrict__ fn,
+                      const uint8_t *__restrict__ mask, fs2d_dom d, DivC<P2> d2dx) {
+    FS2D_CELL(d, r, j)
+    const size_t idx = IX(d, r, j);
+    if (mask[idx] == 1) return;
+    float2 gx = ld2(fn, d, r + 1, j) - ld2(fc, d, r + 1, j) - ld2(fn, d, r - 1, j) + ld2(fc, d, r - 1, j);
+    float2 gy = ld2(fn, d, r, j + 1) - ld2(fc, d, r, j + 1) - ld2(fn, d, r, j - 1) + ld2(fc, d, r, j - 1);
+    reinterpret_cast<float2 *>(fxn)[idx] = __ldg(reinterpret_cast<const float2 *>(fxc) + idx) + d2dx(gx);
+    reinterpret_cast<float2 *>(fyn)[idx] = __ldg(reinterpret_cast<const float2 *>(fyc) + idx) + d2dx(gy);
+}
+
+// =============================================================================================
+// fs/solver.py:267-332  _advection_phase / _cip_advect
+// =============================================================================================
+template <bool P2>
+__global__ void __launch_bounds__(TX *TY)
+    k_cip_advect(float *__restrict__ fn, float *__restrict__ fxn, float *__restrict__ fyn,
+                 const float *__restrict__ fc, const float *__restrict__ fxc, const float *__restrict__ fyc,
+                 const float *__restrict__ v, const uint8_t *__restrict__ mask, fs2d_dom d, float dt, float dx,
+                 DivC<P2> ddx, float dx2, float dx3) {
+    FS2D_CELL(d, r, j)
+    const size_t idx = IX(d, r, j);
+    if (mask[idx] != 0) return;
+    const float2 vel = __ldg(reinterpret_cast<const float2 *>(v) + idx);
+    const float i_s = sign1(vel.x), j_s = sign1(vel.y);
+    const int r_m = r - (int)i_s, j_m = j - (int)j_s;
+    // +-dx^3, +-dx are exact sign flips; divisions by them are exact scalings when dx is 2^k
+    const DivC<P2> disd(i_s * dx3), djsd(j_s * dx3), ddx2(dx2), disdx(i_s * dx);
+    const float Xd = -vel.x * dt, Yd = -vel.y * dt;
+    const float2 dxv = diff_x2<P2>(v, d, r, j, ddx);  // (d/dx u, d/dx v)
+    const float2 dyv = diff_y2<P2>(v, d, r, j, ddx);
+
+    const float2 f00 = ld2(fc, d, r, j), f0m = ld2(fc, d, r, j_m), fm0 = ld2(fc, d, r_m, j), fmm = ld2(fc, d, r_m, j_m);
+    const float2 x00 = ld2(fxc, d, r, j), x0m = ld2(fxc, d, r, j_m), xm0 = ld2(fxc, d, r_m, j);
+    const float2 y00 = ld2(fyc, d, r, j), y0m = ld2(fyc, d, r, j_m), ym0 = ld2(fyc, d, r_m, j);
+
+    const float2 tmp1 = f00 - f0m - fm0 + fmm;
+    const float2 tmp2 = fm0 - f00;
+    const float2 tmp3 = f0m - f00;
+
+    const float2 a = disd(i_s * (xm0 + x00) * dx - 2.0f * (-tmp2));
+    const float2 b = djsd(j_s * (y0m + y00) * dx - 2.0f * (-tmp3));
+    const float2 c = djsd(-tmp1 - i_s * (x0m - x00) * dx);
+    const float2 dd = disd(-tmp1 - j_s * (ym0 - y00) * dx);
+    const float2 e = ddx2(3.0f * tmp2 + i_s * (xm0 + 2.0f * x00) * dx);
+    const float2 f = ddx2(3.0f * tmp3 + j_s * (y0m + 2.0f * y00) * dx);
+    const float2 g = disdx(-(ym0 - y00) + c * dx2);
+
+    const float2 out = ((a * Xd + c * Yd + e) * Xd + g * Yd + x00) * Xd + ((b * Yd + dd * Xd + f) * Yd + y00) * Yd + f00;
+    const float2 Fx = (3.0f * a * Xd + 2.0f * c * Yd + 2.0f * e) * Xd + (dd * Yd + g) * Yd + x00;
+    const float2 Fy = (3.0f * b * Yd + 2.0f * dd * Xd + 2.0f * f) * Yd + (c * Xd + g) * Xd + y00;
+
+    reinterpret_cast<float2 *>(fn)[idx] = out;
+    reinterpret_cast<float2 *>(fxn)[idx] = Fx - dt * (Fx * dxv.x + Fy * dxv.y) / 2.0f;
+    reinterpret_cast<float2 *>(fyn)[idx] = Fy - dt * (Fx * dyv.x + Fy * dyv.y) / 2.0f;
+}
+
+// fs/solver.py:207-211  _set_grad
+template <bool P2>
+__global__ void __launch_bounds__(TX *TY)
+    k_set_grad(float *__restrict__ fx, float *__restrict__ fy, const float *__restrict__ f, fs2d_dom d, DivC<P2> ddx) {
+    FS2D_CELL(d, r, j)
+    const size_t idx = IX(d, r, j);
+    reinterpret_cast<float2 *>(fx)[idx] = diff_x2<P2>(f, d, r, j, ddx);
+    reinterpret_cast<float2 *>(fy)[idx] = diff_y2<P2>(f, d, r, j, ddx);
+}
+
+// =============================================================================================
+// fs/vorticity_confinement.py:27-32 / :34-55
+// =============================================================================================
+template <bool P2>
+__global__ void __launch_bounds__(TX *TY)
+    k_vort_calc(float *__restrict__ w, float *__restrict__ wabs, const float *__restrict__ vc,
+                const uint8_t *__restrict__ mask, fs2d_dom d, DivC<P2> ddx) {
+    FS2D_CELL(d, r, j)
+    const size_t idx = IX(d, r, j);
+    if (mask[idx] != 0) return;
+    float o = diff_x2<P2>(vc, d, r, j, ddx).y - diff_y2<P2>(vc, d, r, j, ddx).x;
+    w[idx] = o;
+    wabs[idx] = fabsf(o);
+}
+template <bool P2>
+__global__ void __launch_bounds__(TX *TY)
+    k_vort_add(float *__restrict__ vn, const float *__restrict__ vc, const float *__restrict__ w,
+               const float *__restrict__ wabs, const uint8_t *__restrict__ mask, fs2d_dom d, DivC<P2> ddx, float dtw) {
+    FS2D_CELL(d, r, j)
+    const size_t idx = IX(d, r, j);
+    if (mask[idx] != 0) return;
+    const float gx = diff_x1<P2>(wabs, d, r, j, ddx), gy = diff_y1<P2>(wabs, d, r, j, ddx);
+    const float nrm = sqrtf(gx * gx + gy * gy);
+    const float nx = gx / nrm, ny = gy / nrm;  // 0/0 = NaN on quiescent cells
+    const float o = __ldg(w + idx);
+    float fx = ny * o, fy = -nx * o;
+    fx = fmaxf(fminf(fx, 0.1f), -0.1f);  // NaN -> +0.1 by the fminf/fmaxf rule
+    fy = fmaxf(fminf(fy, 0.1f), -0.1f);
+    const float2 c = __ldg(reinterpret_cast<const float2 *>(vc) + idx);
+    reinterpret_cast<float2 *>(vn)[idx] = make_float2(c.x + dtw * fx, c.y + dtw * fy);
+}
+
+// =============================================================================================
+// pressure: predict_p (fs/pressure_updater.py:23-38)
+// =============================================================================================
+// velocity source terms of predict_p for cell (r, j): t2 = (sxx^2 + syy^2 + syx*sxy)/8, t3 = dx*(sxx+syy)/(8*dt)
+__device__ __forceinline__ void p_source(const float *vc, const fs2d_dom &d, int r, int j, float dt, float dx, float &t2,
+                                         float &t3) {
+    const float2 sx = ld2(vc, d, r + 1, j) - ld2(vc, d, r - 1, j);
+    const float2 sy = ld2(vc, d, r, j + 1) - ld2(vc, d, r, j - 1);
+    t2 = (sx.x * sx.x + sy.y * sy.y + (sy.x * sx.y)) / 8.0f;
+    t3 = dx * (sx.x + sy.y) / (8.0f * dt);
+}
+// post-BC pressure of cell (r, j) (already clamped) recomputed from the pre-BC field and pcode
+__device__ __forceinline__ float p_post(const float *pc, const uint8_t *pcode, const fs2d_dom &d, int r, int j) {
+    const size_t idx = IX(d, r, j);
+    const uint8_t c = __ldg(pcode + idx);
+    switch (c) {
+        case FS2D_PC_FLUID:
+        case FS2D_PC_W_NONE: return __ldg(pc + idx);
+        case FS2D_PC_W_IM: return ld1(pc, d, r - 1, j);
+        case FS2D_PC_W_IP: return ld1(pc, d, r + 1, j);
+        case FS2D_PC_W_JM: return ld1(pc, d, r, j - 1);
+        case FS2D_PC_W_JP: return ld1(pc, d, r, j + 1);
+        case FS2D_PC_W_IM_JP: return (ld1(pc, d, r - 1, j) + ld1(pc, d, r, j + 1)) / 2.0f;
+        case FS2D_PC_W_IP_JP: return (ld1(pc, d, r + 1, j) + ld1(pc, d, r, j + 1)) / 2.0f;
+        case FS2D_PC_W_IM_JM: return (ld1(pc, d, r - 1, j) + ld1(pc, d, r, j - 1)) / 2.0f;
+        case FS2D_PC_W_IP_JM: return (ld1(pc, d, r + 1, j) + ld1(pc, d, r, j - 1)) / 2.0f;
+        case FS2D_PC_INFLOW: return ld1(pc, d, r + 1, j);
+        default: return 0.0f;  // FS2D_PC_OUTFLOW
+    }
+}
+__device__ __forceinline__ bool pc_is_wall(uint8_t c) { return c >= FS2D_PC_W_IM && c <= FS2D_PC_W_NONE; }
+
+// scalar (any Y) Jacobi sweep: fs/pressure_updater.py:62-66
+template <bool INLINE_BC>
+__global__ void __launch_bounds__(TX *TY)
+    k_jacobi_scalar(float *__restrict__ pn, const float *__restrict__ pc, const float *__restrict__ vc,
+                    const uint8_t *__restrict__ pcode, fs2d_dom d, float dt, float dx) {
+    FS2D_CELL(d, r, j)
+    const size_t idx = IX(d, r, j);
+    if (pc_is_wall(__ldg(pcode + idx))) return;
+    float pe, pw, pn_, ps;
+    if (INLINE_BC) {
+        pe = p_post(pc, pcode, d, CR(d, r + 1), j);
+        pw = p_post(pc, pcode, d, CR(d, r - 1), j);
+        pn_ = p_post(pc, pcode, d, r, CJ(d, j + 1));
+        ps = p_post(pc, pcode, d, r, CJ(d, j - 1));
+    } else {
+        pe = ld1(pc, d, r + 1, j);
+        pw = ld1(pc, d, r - 1, j);
+        pn_ = ld1(pc, d, r, j + 1);
+        ps = ld1(pc, d, r, j - 1);
+    }
+    float t2, t3;
+    p_source(vc, d, r, j, dt, dx, t2, t3);
+    pn[idx] = 0.25f * (pe + pw + pn_ + ps) + t2 - t3;
+}
+
+// vectorised Jacobi sweep: 4 cells / thread along j (128-bit loads/stores), Y % 4 == 0.
+// block = (32 lanes x 4 cells = 128 columns) x 8 rows.
+constexpr int JV_ROWS = 8;
+template <bool INLINE_BC>
+__global__ void __launch_bounds__(32 * JV_ROWS)
+    k_jacobi_vec4(float *__restrict__ pn, const float *__restrict__ pc, const float *__restrict__ vc,
+                  const uint8_t *__restrict__ pcode, fs2d_dom d, float dt, float dx) {
+    const int j0 = 4 * (blockIdx.y * 32 + threadIdx.x);
+    const int r = d.r0 + blockIdx.x * JV_ROWS + threadIdx.y;
+    if (j0 >= d.Y || r >= d.r1) return;
+    const size_t idx = IX(d, r, j0);
+    const uchar4 cc = __ldg(reinterpret_cast<const uchar4 *>(pcode + idx));
+    const bool w0 = pc_is_wall(cc.x), w1 = pc_is_wall(cc.y), w2 = pc_is_wall(cc.z), w3 = pc_is_wall(cc.w);
+    if (w0 && w1 && w2 && w3) return;
+    const int ru = CR(d, r - 1), rd = CR(d, r + 1);
+    const int jl = CJ(d, j0 - 1), jr = CJ(d, j0 + 4);
+
+    float pw[4], pe[4], ps[4], pnn[4];  // (i-1), (i+1), (j-1), (j+1) neighbours per cell
+    bool fast = true;
+    if (INLINE_BC) {
+        const uchar4 cu = __ldg(reinterpret_cast<const uchar4 *>(pcode + IX(d, ru, j0)));
+        const uchar4 cd = __ldg(reinterpret_cast<const uchar4 *>(pcode + IX(d, rd, j0)));
+        const uint8_t cl = __ldg(pcode + IX(d, r, jl)), cr_ = __ldg(pcode + IX(d, r, jr));
+        auto plain = [](uint8_t c) { return c == FS2D_PC_FLUID || c == FS2D_PC_W_NONE; };
+        fast = plain(cu.x) && plain(cu.y) && plain(cu.z) && plain(cu.w) && plain(cd.x) && plain(cd.y) && plain(cd.z) &&
+               plain(cd.w) && plain(cc.x) && plain(cc.y) && plain(cc.z) && plain(cc.w) && plain(cl) && plain(cr_);
+    }
+    if (fast) {
+        const float4 c4 = __ldg(reinterpret_cast<const float4 *>(pc + idx));
+        const float4 u4 = __ldg(reinterpret_cast<const float4 *>(pc + IX(d, ru, j0)));
+        const float4 d4 = __ldg(reinterpret_cast<const float4 *>(pc + IX(d, rd, j0)));
+        const float pl = __ldg(pc + IX(d, r, jl)), pr = __ldg(pc + IX(d, r, jr));
+        pw[0] = u4.x; pw[1] = u4.y; pw[2] = u4.z; pw[3] = u4.w;
+        pe[0] = d4.x; pe[1] = d4.y; pe[2] = d4.z; pe[3] = d4.w;
+        ps[0] = pl; ps[1] = c4.x; ps[2] = c4.y; ps[3] = c4.z;
+        pnn[0] = c4.y; pnn[1] = c4.z; pnn[2] = c4.w; pnn[3] = pr;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            pw[k] = p_post(pc, pcode, d, ru, j0 + k);
+            pe[k] = p_post(pc, pcode, d, rd, j0 + k);
+            ps[k] = p_post(pc, pcode, d, r, CJ(d, j0 + k - 1));
+            pnn[k] = p_post(pc, pcode, d, r, CJ(d, j0 + k + 1));
+        }
+    }
+    // velocity differences: rows r+-1 (2 x float4 each), row r columns j0-1 .. j0+4
+    const float4 *vrow_d = reinterpret_cast<const float4 *>(vc + 2 * IX(d, rd, j0));
+    const float4 *vrow_u = reinterpret_cast<const float4 *>(vc + 2 * IX(d, ru, j0));
+    const float4 *vrow_c = reinterpret_cast<const float4 *>(vc + 2 * idx);
+    const float4 vd0 = __ldg(vrow_d), vd1 = __ldg(vrow_d + 1);
+    const float4 vu0 = __ldg(vrow_u), vu1 = __ldg(vrow_u + 1);
+    const float4 vc0 = __ldg(vrow_c), vc1 = __ldg(vrow_c + 1);
+    const float2 vl = __ldg(reinterpret_cast<const float2 *>(vc) + IX(d, r, jl));
+    const float2 vr = __ldg(reinterpret_cast<const float2 *>(vc) + IX(d, r, jr));
+    const float2 vdn[4] = {{vd0.x, vd0.y}, {vd0.z, vd0.w}, {vd1.x, vd1.y}, {vd1.z, vd1.w}};
+    const float2 vup[4] = {{vu0.x, vu0.y}, {vu0.z, vu0.w}, {vu1.x, vu1.y}, {vu1.z, vu1.w}};
+    const float2 vrow[6] = {vl, {vc0.x, vc0.y}, {vc0.z, vc0.w}, {vc1.x, vc1.y}, {vc1.z, vc1.w}, vr};
+    const float eight_dt = 8.0f * dt;
+    float out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 sx = vdn[k] - vup[k];
+        const float2 sy = vrow[k + 2] - vrow[k];
+        const float t2 = (sx.x * sx.x + sy.y * sy.y + (sy.x * sx.y)) / 8.0f;
+        const float t3 = dx * (sx.x + sy.y) / eight_dt;
+        out[k] = 0.25f * (pe[k] + pw[k] + pnn[k] + ps[k]) + t2 - t3;
+    }
+    if (!(w0 || w1 || w2 || w3)) {
+        *reinterpret_cast<float4 *>(pn + idx) = make_float4(out[0], out[1], out[2], out[3]);
+    } else {
+        if (!w0) pn[idx] = out[0];
+        if (!w1) pn[idx + 1] = out[1];
+        if (!w2) pn[idx + 2] = out[2];
+        if (!w3) pn[idx + 3] = out[3];
+    }
+}
+
+// fs/pressure_updater.py:98-114  one colour pass of red-black SOR (pc may alias pn)
+__global__ void __launch_bounds__(TX *TY)
+    k_rbsor_pass(float *pn, const float *pc, const float *__restrict__ vc, const uint8_t *__restrict__ mask, fs2d_dom d,
+                 float dt, float dx, float omega, float one_minus_omega, int parity) {
+    FS2D_CELL(d, r, j)
+    const size_t idx = IX(d, r, j);
+    if (((d.gi0 + r + j) & 1) != parity || mask[idx] != 0) return;
+    // plain loads: pc may alias pn (even pass) -- neighbours have the other colour, never written here
+    const float pe = pc[IX(d, CR(d, r + 1), j)], pw = pc[IX(d, CR(d, r - 1), j)];
+    const float pnn = pc[IX(d, r, CJ(d, j + 1))], ps = pc[IX(d, r, CJ(d, j - 1))];
+    float t2, t3;
+    p_source(vc, d, r, j, dt, dx, t2, t3);
+    const float pred = 0.25f * (pe + pw + pnn + ps) + t2 - t3;
+    pn[idx] = one_minus_omega * pc[idx] + omega * pred;
+}
+
+// fs/solver.py:38-43  limit_field
+__global__ void __launch_bounds__(TX *TY) k_limit(float *__restrict__ v, fs2d_dom d, float limit) {
+    FS2D_CELL(d, r, j)
+    float2 *p = reinterpret_cast<float2 *>(v) + IX(d, r, j);
+    const float2 c = *p;
+    const float nrm = sqrtf(c.x * c.x + c.y * c.y);
+    if (nrm > limit) *p = make_float2(limit * (c.x / nrm), limit * (c.y / nrm));
+}
+
+}  // namespace fs2d
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace fs2d;
+
+extern "C" {
+
+const char *fs2d_last_error(void) { return g_err; }
+int fs2d_version(void) { return 1; }
+int fs2d_device_ok(void) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+        set_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    }
+    if (prop.major != 10) {
+        set_error("libfs2d is built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
+        return 0;
+    }
+    return 1;
+}
+
+#define STREAM ((cudaStream_t)stream)
+static inline unsigned nblk(int n, int b) { return (unsigned)((n + b - 1) / b); }
+
+int fs2d_vel_bc(float *v, const float *bc_const, const int32_t *tgt, const int32_t *src, const uint8_t *kind,
+                float *scratch, int n, void *stream) {
+    if (n == 0) return FS2D_OK;
+    FS2D_REQUIRE(v && bc_const && tgt && src && kind && scratch && n > 0, "null table/field pointer");
+    k_vel_bc_gather<<<nblk(n, 256), 256, 0, STREAM>>>((const float2 *)v, (const float2 *)bc_const, tgt, src, kind,
+                                                       (float2 *)scratch, n);
+    k_vel_bc_scatter<<<nblk(n, 256), 256, 0, STREAM>>>((float2 *)v, tgt, (const float2 *)scratch, n);
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+int fs2d_pressure_bc(float *p, const int32_t *tgt, const int32_t *src0, const int32_t *src1, const uint8_t *kind,
+                     float *scratch, int n, void *stream) {
+    if (n == 0) return FS2D_OK;
+    FS2D_REQUIRE(p && tgt && src0 && src1 && kind && scratch && n > 0, "null table/field pointer");
+    k_p_bc_gather<<<nblk(n, 256), 256, 0, STREAM>>>(p, src0, src1, kind, scratch, n);
+    k_p_bc_scatter<<<nblk(n, 256), 256, 0, STREAM>>>(p, tgt, scratch, n);
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+#define DISPATCH_P2(p2, CALL_T, CALL_F) \
+    do {                                \
+        if (p2) { CALL_T; } else { CALL_F; } \
+    } while (0)
+
+int fs2d_mac_update(float *vn, const float *vc, const float *pc, const uint8_t *mask, fs2d_dom d, float dt, float dx,
+                    float re, int scheme, void *stream) {
+    FS2D_REQUIRE(vn && vc && pc && mask, "null field pointer");
+    FS2D_REQUIRE(scheme == FS2D_SCHEME_UPWIND || scheme == FS2D_SCHEME_KK, "unknown advection scheme");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+    const bool p2 = is_pow2(dx);
+    const float dx2 = dx * dx;
+#define MAC(P2, S) \
+    k_mac_update<P2, S><<<dense_grid(d), dense_block(), 0, STREAM>>>(vn, vc, pc, mask, d, dt, dx, DivC<P2>(dx), DivC<P2>(dx2), re)
+    if (scheme == FS2D_SCHEME_UPWIND) DISPATCH_P2(p2, MAC(true, FS2D_SCHEME_UPWIND), MAC(false, FS2D_SCHEME_UPWIND));
+    else DISPATCH_P2(p2, MAC(true, FS2D_SCHEME_KK), MAC(false, FS2D_SCHEME_KK));
+#undef MAC
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+int fs2d_cip_nonadv(float *fn, const float *fc, const float *pc, const uint8_t *mask, fs2d_dom d, float dt, float dx,
+                    float re, void *stream) {
+    FS2D_REQUIRE(fn && fc && pc && mask, "null field pointer");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+    const float dx2 = dx * dx;
+#define NA(P2) k_cip_nonadv<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(fn, fc, pc, mask, d, dt, DivC<P2>(dx), DivC<P2>(dx2), re)
+    DISPATCH_P2(is_pow2(dx), NA(true), NA(false));
+#undef NA
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+int fs2d_cip_nonadv_grad(float *fxn, float *fyn, const float *fxc, const float *fyc, const float *fc, const float *fn,
+                         const uint8_t *mask, fs2d_dom d, float two_dx, void *stream) {
+    FS2D_REQUIRE(fxn && fyn && fxc && fyc && fc && fn && mask, "null field pointer");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+#define NG(P2) k_cip_nonadv_grad<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(fxn, fyn, fxc, fyc, fc, fn, mask, d, DivC<P2>(two_dx))
+    DISPATCH_P2(is_pow2(two_dx), NG(true), NG(false));
+#undef NG
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+int fs2d_cip_advect(float *fn, float *fxn, float *fyn, const float *fc, const float *fxc, const float *fyc,
+                    const float *v, const uint8_t *mask, fs2d_dom d, float dt, float dx, float dx2, float dx3,
+                    void *stream) {
+    FS2D_REQUIRE(fn && fxn && fyn && fc && fxc && fyc && v && mask, "null field pointer");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+    const bool p2 = is_pow2(dx) && is_pow2(dx2) && is_pow2(dx3);
+#define CA(P2) k_cip_advect<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, DivC<P2>(dx), dx2, dx3)
+    DISPATCH_P2(p2, CA(true), CA(false));
+#undef CA
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+int fs2d_set_grad(float *fx, float *fy, const float *f, fs2d_dom d, float dx, void *stream) {
+    FS2D_REQUIRE(fx && fy && f, "null field pointer");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+#define SG(P2) k_set_grad<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(fx, fy, f, d, DivC<P2>(dx))
+    DISPATCH_P2(is_pow2(dx), SG(true), SG(false));
+#undef SG
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+int fs2d_vort_calc(float *w, float *wabs, const float *vc, const uint8_t *mask, fs2d_dom d, float dx, void *stream) {
+    FS2D_REQUIRE(w && wabs && vc && mask, "null field pointer");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+#define VC(P2) k_vort_calc<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(w, wabs, vc, mask, d, DivC<P2>(dx))
+    DISPATCH_P2(is_pow2(dx), VC(true), VC(false));
+#undef VC
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+int fs2d_vort_add(float *vn, const float *vc, const float *w, const float *wabs, const uint8_t *mask, fs2d_dom d,
+                  float dx, float dtw, void *stream) {
+    FS2D_REQUIRE(vn && vc && w && wabs && mask, "null field pointer");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+#define VA(P2) k_vort_add<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(vn, vc, w, wabs, mask, d, DivC<P2>(dx), dtw)
+    DISPATCH_P2(is_pow2(dx), VA(true), VA(false));
+#undef VA
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+static int launch_jacobi(float *pn, const float *pc, const float *vc, const uint8_t *pcode, const fs2d_dom &d, float dt,
+                         float dx, int inline_bc, cudaStream_t s) {
+    const bool vec = (d.Y % 4 == 0) && ((uintptr_t)pn % 16 == 0) && ((uintptr_t)pc % 16 == 0) &&
+                     ((uintptr_t)vc % 16 == 0) && ((uintptr_t)pcode % 4 == 0);
+    if (vec) {
+        dim3 blk(32, JV_ROWS, 1), grd(nblk(d.r1 - d.r0, JV_ROWS), nblk(d.Y, 128), 1);
+        if (inline_bc) k_jacobi_vec4<true><<<grd, blk, 0, s>>>(pn, pc, vc, pcode, d, dt, dx);
+        else k_jacobi_vec4<false><<<grd, blk, 0, s>>>(pn, pc, vc, pcode, d, dt, dx);
+    } else {
+        if (inline_bc) k_jacobi_scalar<true><<<dense_grid(d), dense_block(), 0, s>>>(pn, pc, vc, pcode, d, dt, dx);
+        else k_jacobi_scalar<false><<<dense_grid(d), dense_block(), 0, s>>>(pn, pc, vc, pcode, d, dt, dx);
+    }
+    return FS2D_OK;
+}
+
+int fs2d_jacobi_sweep(float *pn, const float *pc, const float *vc, const uint8_t *pcode, fs2d_dom d, float dt, float dx,
+                      int inline_bc, void *stream) {
+    FS2D_REQUIRE(pn && pc && vc && pcode, "null field pointer");
+    FS2D_REQUIRE(pn != pc, "Jacobi sweep cannot run in place");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+    launch_jacobi(pn, pc, vc, pcode, d, dt, dx, inline_bc, STREAM);
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+int fs2d_jacobi_update(float *pa, float *pb, const float *vc, const uint8_t *pcode, fs2d_dom d, float dt, float dx,
+                       int n_sweeps, const int32_t *tgt, const int32_t *src0, const int32_t *src1,
+                       const uint8_t *kind, float *scratch, int n_bc, int *final_in_b, void *stream) {
+    FS2D_REQUIRE(pa && pb && vc && pcode && pa != pb, "null/aliased field pointer");
+    FS2D_REQUIRE(n_sweeps >= 0, "negative sweep count");
+    FS2D_REQUIRE(n_bc == 0 || (tgt && src0 && src1 && kind && scratch), "null BC table");
+    if (int e = check_dom(d)) return e;
+    float *cur = pa, *nxt = pb;
+    for (int s = 0; s < n_sweeps; ++s) {
+        // The stored BC values of a buffer are only observable after its last in-place BC pass
+        // (SURVEY T1): materialise them for the final two sweeps, recompute inline before that.
+        if (s >= n_sweeps - 2 && n_bc > 0) {
+            k_p_bc_gather<<<nblk(n_bc, 256), 256, 0, STREAM>>>(cur, src0, src1, kind, scratch, n_bc);
+            k_p_bc_scatter<<<nblk(n_bc, 256), 256, 0, STREAM>>>(cur, tgt, scratch, n_bc);
+        }
+        if (d.r1 > d.r0) launch_jacobi(nxt, cur, vc, pcode, d, dt, dx, 1, STREAM);
+        float *t = cur; cur = nxt; nxt = t;
+    }
+    FS2D_LAUNCH_CHECK();
+    if (final_in_b) *final_in_b = (cur == pb);
+    return FS2D_OK;
+}
+
+int fs2d_rbsor_pass(float *pn, const float *pc, const float *vc, const uint8_t *mask, fs2d_dom d, float dt, float dx,
+                    float omega, float one_minus_omega, int parity, void *stream) {
+    FS2D_REQUIRE(pn && pc && vc && mask, "null field pointer");
+    FS2D_REQUIRE(parity == 0 || parity == 1, "parity must be 0 or 1");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+    k_rbsor_pass<<<dense_grid(d), dense_block(), 0, STREAM>>>(pn, pc, vc, mask, d, dt, dx, omega, one_minus_omega, parity);
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+int fs2d_limit(float *v, fs2d_dom d, float limit, void *stream) {
+    FS2D_REQUIRE(v, "null field pointer");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+    k_limit<<<dense_grid(d), dense_block(), 0, STREAM>>>(v, d, limit);
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,288 @@
+"""BoundaryCondition + scene builders, API of /root/reference/fs/boundary_condition.py.
+
+Device side: `set_velocity_boundary_condition` (:16-39) and `set_pressure_boundary_condition`
+(:41-65) run as sparse gather kernels of libfs2d.so over tables resolved once from the static mask
+(`fs/_bc_tables.py`).  Host side: the NumPy scene builders bc1..bc6 (:115-524) are restated as a
+small declarative scene description (same operations, same order, same rounding) and verified
+against masks produced by the reference's own builders (tests/golden/masks_*.{npz,json}).
+"""
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+import numpy.typing as npt
+import torch
+
+from fs import _bc_tables, _lib
+from fs.double_buffer import Field, default_device
+
+FLUID, WALL, INFLOW, OUTFLOW = 0, 1, 2, 3
+
+
+class BoundaryCondition:
+    """bc_const: (X, Y, 2) f32 inflow velocities; bc_mask: (X, Y) u8 cell types (:13, :78-85)."""
+
+    def __init__(self, bc_const: npt.NDArray, bc_mask: npt.NDArray, device=None, partition=None) -> None:
+        bc_const = np.ascontiguousarray(bc_const, dtype=np.float32)
+        bc_mask = np.ascontiguousarray(bc_mask, dtype=np.uint8)
+        if bc_const.shape[:2] != bc_mask.shape or bc_const.shape[2:] != (2,):
+            raise ValueError(f"bc_const {bc_const.shape} / bc_mask {bc_mask.shape} shape mismatch")
+        self.device = torch.device(device) if device is not None else default_device()
+        self._global_resolution = (int(bc_mask.shape[0]), int(bc_mask.shape[1]))
+        if partition is None:
+            from fs.distributed import Partition
+
+            partition = Partition.single(self._global_resolution[0])
+        self.partition = partition
+        X, Y = self._global_resolution
+        w0, w1 = partition.window()          # global rows held in the local array (owned + halo)
+        g0, g1 = partition.owned()           # global rows this rank updates
+        self._resolution = (g1 - g0, Y)
+        self.halo = partition.halo
+
+        gmask = torch.from_numpy(bc_mask).to(self.device)
+        pcode = _bc_tables.pressure_codes(gmask)
+        lo, hi = max(w0, 0), min(w1, X)      # part of the window that exists globally
+
+        def local(t_global: torch.Tensor, fill=0) -> torch.Tensor:
+            out = torch.full((w1 - w0,) + tuple(t_global.shape[1:]), fill, dtype=t_global.dtype, device=self.device)
+            out[lo - w0:hi - w0] = t_global[lo:hi]
+            return out.contiguous()
+
+        self._bc_mask = local(gmask, WALL)
+        self._pcode = local(pcode, _bc_tables.PC_W_NONE)
+        self._bc_const = local(torch.from_numpy(bc_const).to(self.device))
+        # BC targets: owned rows plus the halo rows whose sources are inside the window
+        tl, th = max(lo, g0 - max(self.halo - 2, 0)), min(hi, g1 + max(self.halo - 2, 0))
+        self._vel_table = _bc_tables.velocity_table(gmask, tl, th, w0, w1)
+        self._p_table = _bc_tables.pressure_table(pcode, max(lo, g0 - max(self.halo - 1, 0)),
+                                                  min(hi, g1 + max(self.halo - 1, 0)), w0, w1)
+        stale = _bc_tables.exposed_stale_cells(pcode)
+        if stale.numel():
+            si, sj = stale // Y, stale % Y
+            keep = (si >= lo) & (si < hi)
+            stale = (si[keep] - w0) * Y + sj[keep]
+        self._exposed_stale = stale
+        n = max(self._vel_table["n"], self._p_table["n"], 1)
+        self._scratch = torch.empty(2 * n, dtype=torch.float32, device=self.device)
+        self.dom = _lib.Dom(rows=w1 - w0, Y=Y, r0=g0 - w0, r1=g1 - w0, clo=lo - w0, chi=hi - 1 - w0, gi0=w0)
+        del gmask, pcode
+
+    # -- reference API ---------------------------------------------------------------------
+    def set_velocity_boundary_condition(self, vc: Field) -> None:
+        t = self._vel_table
+        _lib.call("fs2d_vel_bc", vc.ptr(), _lib.ptr(self._bc_const), _lib.ptr(t["tgt"]), _lib.ptr(t["src"]),
+                  _lib.ptr(t["kind"]), _lib.ptr(self._scratch), t["n"], _lib.stream())
+
+    def set_pressure_boundary_condition(self, pc: Field) -> None:
+        t = self._p_table
+        _lib.call("fs2d_pressure_bc", pc.ptr(), _lib.ptr(t["tgt"]), _lib.ptr(t["src0"]), _lib.ptr(t["src1"]),
+                  _lib.ptr(t["kind"]), _lib.ptr(self._scratch), t["n"], _lib.stream())
+
+    def is_wall(self, i: int, j: int) -> bool:
+        return int(self._bc_mask[i + self.halo, j]) == WALL
+
+    def is_fluid_domain(self, i: int, j: int) -> bool:
+        return int(self._bc_mask[i + self.halo, j]) == FLUID
+
+    def get_resolution(self) -> tuple[int, int]:
+        return self._resolution
+
+    def get_global_resolution(self) -> tuple[int, int]:
+        return self._global_resolution
+
+    @staticmethod
+    def to_field(bc: npt.NDArray, bc_mask: npt.NDArray, device=None) -> tuple[torch.Tensor, torch.Tensor]:
+        dev = torch.device(device) if device is not None else default_device()
+        return (torch.from_numpy(np.ascontiguousarray(bc, dtype=np.float32)).to(dev),
+                torch.from_numpy(np.ascontiguousarray(bc_mask, dtype=np.uint8)).to(dev))
+
+    # -- helpers for the other operators -----------------------------------------------------
+    def stale_cells_agree(self, a: Field, b: Field) -> bool:
+        """True if the never-written wall cells read by relaxed neighbours hold equal values in both
+        physical buffers (always the case for solver-owned buffers)."""
+        if self._exposed_stale.numel() == 0:
+            return True
+        fa, fb = a.tensor.flatten()[self._exposed_stale], b.tensor.flatten()[self._exposed_stale]
+        return bool(torch.equal(fa, fb))
+
+
+# =================================================================================================
+# scene builders (host, NumPy)
+# =================================================================================================
+def create_bc_array(x_resolution: int, y_resolution: int) -> tuple[npt.NDArray, npt.NDArray, npt.NDArray]:
+    return (np.zeros((x_resolution, y_resolution, 2), dtype=np.float32),
+            np.zeros((x_resolution, y_resolution), dtype=np.uint8),
+            np.zeros((x_resolution, y_resolution, 3), dtype=np.float32))
+
+
+def set_plane(bc, bc_mask, bc_dye, lower_left, upper_right) -> None:
+    """Axis-aligned wall slab (:157-168); NumPy slice semantics incl. negative corners."""
+    sl = (slice(int(lower_left[0]), int(upper_right[0])), slice(int(lower_left[1]), int(upper_right[1])))
+    bc[sl] = 0.0
+    bc_mask[sl] = WALL
+    if bc_dye is not None:
+        bc_dye[sl] = 0.0
+
+
+def set_circle(bc, bc_mask, bc_dye, center, radius: float) -> None:
+    """Wall disc (:137-154): cell (i, j) is wall iff |(i, j) + 0.5 - center| < radius, scanned over the
+    reference's rounded bounding box.  Vectorised; same float64 arithmetic per cell."""
+    c = np.asarray(center, dtype=np.float64)
+    lo = np.round(np.maximum(c - radius, 0)).astype(np.int32)
+    u0 = round(min(center[0] + radius, bc.shape[0]))
+    u1 = round(min(center[1] + radius, bc.shape[1]))
+    if u0 <= lo[0] or u1 <= lo[1]:
+        return
+    x = np.arange(lo[0], u0, dtype=np.float64)[:, None] + 0.5 - c[0]
+    y = np.arange(lo[1], u1, dtype=np.float64)[None, :] + 0.5 - c[1]
+    inside = np.sqrt(x * x + y * y) < radius
+    sub = (slice(int(lo[0]), int(u0)), slice(int(lo[1]), int(u1)))
+    bc[sub][inside] = 0.0
+    bc_mask[sub][inside] = WALL
+    if bc_dye is not None:
+        bc_dye[sub][inside] = 0.0
+
+
+def set_obstacle_fromfile(bc, bc_mask, bc_dye, filepath: Path) -> None:
+    """Dark pixels of an image become wall (:171-198)."""
+    from PIL import Image
+
+    image = Image.open(filepath).convert("L")
+    x_res, y_res = bc.shape[:2]
+    x_ratio, y_ratio = x_res / image.width, y_res / image.height
+    size = (x_res, round(image.height * x_ratio)) if x_ratio < y_ratio else (round(image.width * y_ratio), y_res)
+    image = image.resize(size)
+    canvas = Image.new(image.mode, (x_res, y_res), 255)
+    canvas.paste(image, ((x_res - image.width) // 2, 0))
+    dark = np.flip(np.array(canvas).T, axis=1) < 200
+    bc[dark] = 0.0
+    bc_mask[dark] = WALL
+    if bc_dye is not None:
+        bc_dye[dark] = 0.0
+
+
+def _inflow(bc, mask, rows, cols) -> None:
+    bc[rows, cols] = np.array([1.0, 0.0], dtype=np.float32)
+    mask[rows, cols] = INFLOW
+
+
+def _outflow(bc, mask, rows, cols) -> None:
+    bc[rows, cols] = 0.0
+    mask[rows, cols] = OUTFLOW
+
+
+def _floor_ceiling(bc, mask, X, Y) -> None:
+    set_plane(bc, mask, None, (0, 0), (X, 2))
+    set_plane(bc, mask, None, (0, Y - 2), (X, Y))
+
+
+ALL = slice(None)
+
+
+def build_scene(num: int, x_res: int, y_res: int, obstacle_image: Path | None = None):
+    """(bc_const, bc_mask) of scene `num` on an x_res x y_res grid.  `create_boundary_conditionN`
+    of the reference is build_scene(N, 2*res, res) (:226, 272, 326, 376, 425, 486); other aspect
+    ratios are used for the weak-scaling grids."""
+    X, Y = int(x_res), int(y_res)
+    bc, mask, _ = create_bc_array(X, Y)
+    if num == 1:                                                   # :222-265
+        _inflow(bc, mask, slice(0, 2), ALL)
+        _outflow(bc, mask, -1, ALL)
+        _floor_ceiling(bc, mask, X, Y)
+        set_circle(bc, mask, None, (X // 4, Y // 2), Y // 18)
+    elif num == 2:                                                 # :268-319
+        _inflow(bc, mask, slice(0, 2), ALL)
+        set_plane(bc, mask, None, (0, 0), (2, Y // 3))
+        set_plane(bc, mask, None, (0, 2 * Y // 3), (2, Y))
+        set_plane(bc, mask, None, (X - 2, 0), (X, Y))
+        _floor_ceiling(bc, mask, X, Y)
+        xp, yp, size = X // 5, Y // 2, Y // 32
+        set_plane(bc, mask, None, (xp - size, yp), (xp + size, Y))
+        set_plane(bc, mask, None, (2 * xp - size, 0), (2 * xp + size, yp))
+        set_plane(bc, mask, None, (3 * xp - size, yp), (3 * xp + size, Y))
+        set_plane(bc, mask, None, (4 * xp - size, 0), (4 * xp + size, yp))
+        yq = Y // 3
+        _outflow(bc, mask, slice(-2, None), slice(yq, 2 * yq))
+    elif num == 3:                                                 # :322-369
+        _inflow(bc, mask, slice(0, 2), ALL)
+        _outflow(bc, mask, -1, ALL)
+        _floor_ceiling(bc, mask, X, Y)
+        np.random.seed(123)  # noqa: NPY002  (legacy RNG on purpose: same stream as the reference)
+        points = np.random.uniform(0, X, (100, 2))  # noqa: NPY002
+        points = points[points[:, 1] < Y]
+        radius = 16 * (Y / 500)
+        for p in points:
+            set_circle(bc, mask, None, p, radius)
+    elif num == 4:                                                 # :372-418
+        set_plane(bc, mask, None, (0, 0), (2, Y))
+        set_plane(bc, mask, None, (X - 2, 0), (X, Y))
+        _floor_ceiling(bc, mask, X, Y)
+        _inflow(bc, mask, slice(0, 2), slice(3 * Y // 4, -2))
+        _inflow(bc, mask, slice(0, 2), slice(2, Y // 4))
+        _outflow(bc, mask, slice(-2, None), slice(3 * Y // 8, 5 * Y // 8))
+    elif num == 5:                                                 # :421-479
+        _inflow(bc, mask, slice(0, 2), slice(2, Y // 3))
+        _inflow(bc, mask, slice(0, 2), slice(2 * Y // 3, Y - 2))
+        _outflow(bc, mask, slice(-2, None), ALL)
+        _floor_ceiling(bc, mask, X, Y)
+        size = X // 64
+        set_plane(bc, mask, None, (0, Y // 5), (11 * X // 30, 4 * Y // 5))
+        set_plane(bc, mask, None, (X // 2 - size, 0), (X // 2 + size, 2 * Y // 5))
+        set_plane(bc, mask, None, (X // 2 - size, 3 * Y // 5), (X // 2 + size, Y))
+        yp, half = Y // 6, np.array([Y, Y]) // 25
+        for a, b in zip((7, 8, 9, 10, 11), (0, 1, 0, 1, 0), strict=True):
+            for i in range(1, 6 + b):
+                p = np.array([a * X // 12, i * yp - b * Y // 12])
+                set_plane(bc, mask, None, p - half, p + half)
+    elif num == 6:                                                 # :482-524
+        _inflow(bc, mask, slice(0, 2), ALL)
+        _outflow(bc, mask, -1, ALL)
+        _floor_ceiling(bc, mask, X, Y)
+        path = obstacle_image or Path(__file__).resolve().parents[1] / "images" / "bc_mask" / "dragon.png"
+        if not Path(path).exists():
+            raise FileNotFoundError(f"scene 6 needs the reference's obstacle image (images/bc_mask/dragon.png); "
+                                    f"not found at {path}")
+        set_obstacle_fromfile(bc, mask, None, Path(path))
+    else:
+        raise NotImplementedError
+    return bc, mask
+
+
+def _make(num: int, resolution: int, enable_dye: bool, **kw) -> BoundaryCondition:
+    if enable_dye:
+        raise NotImplementedError("dye transport is a later hot-path row (SURVEY 8f #2)")
+    bc, mask = build_scene(num, 2 * resolution, resolution)
+    return BoundaryCondition(bc, mask, **kw)
+
+
+def create_boundary_condition1(resolution: int, *, enable_dye: bool, **kw) -> BoundaryCondition:
+    return _make(1, resolution, enable_dye, **kw)
+
+
+def create_boundary_condition2(resolution: int, *, enable_dye: bool, **kw) -> BoundaryCondition:
+    return _make(2, resolution, enable_dye, **kw)
+
+
+def create_boundary_condition3(resolution: int, *, enable_dye: bool, **kw) -> BoundaryCondition:
+    return _make(3, resolution, enable_dye, **kw)
+
+
+def create_boundary_condition4(resolution: int, *, enable_dye: bool, **kw) -> BoundaryCondition:
+    return _make(4, resolution, enable_dye, **kw)
+
+
+def create_boundary_condition5(resolution: int, *, enable_dye: bool, **kw) -> BoundaryCondition:
+    return _make(5, resolution, enable_dye, **kw)
+
+
+def create_boundary_condition6(resolution: int, *, enable_dye: bool, **kw) -> BoundaryCondition:
+    return _make(6, resolution, enable_dye, **kw)
+
+
+def get_boundary_condition(num: int, resolution: int, *, enable_dye: bool, **kw) -> BoundaryCondition:
+    """(:201-219) NotImplementedError for unknown scene numbers, like the reference."""
+    if num not in (1, 2, 3, 4, 5, 6):
+        raise NotImplementedError
+    return _make(num, resolution, enable_dye, **kw)

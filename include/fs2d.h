@@ -1,0 +1,130 @@
+/*
+ * fs2d.h -- C ABI of libfs2d.so: the B200 (sm_100a) implementation of the per-step hot path of
+ * takah29/2d-fluid-simulator (reference commit ebd5d75).
+ *
+ * The reference has no native/FFI boundary (pure Python + Taichi JIT); each entry point below
+ * replaces one Taichi kernel and is what a ctypes/cffi binding of that kernel would bind.  All
+ * pointers are DEVICE pointers owned by the caller (PyTorch tensors in our host layer); the
+ * library never allocates or frees field memory.  `stream` is a cudaStream_t passed as void*.
+ * Every function returns 0 on success or a negative FS2D_E_* code; fs2d_last_error() returns a
+ * thread-local message for the last failure.  Not thread-safe per stream; one host thread per GPU.
+ *
+ * Grid: X rows (slow axis, index i) x Y columns (fast axis, index j), row-major, fp32.
+ * Vector fields are AoS float2 [i][j][2] exactly as Taichi's Vector.field / to_numpy()
+ * (fs/double_buffer.py:10-11).  Cell types (uint8): 0 fluid, 1 wall, 2 inflow, 3 outflow
+ * (fs/boundary_condition.py:82,225).
+ *
+ * Row-strip domains: every dense kernel takes an fs2d_dom describing the LOCAL array of one rank:
+ *   rows      allocated rows of the local array (owned rows + halo rows)
+ *   Y         columns
+ *   r0, r1    the kernel updates local rows [r0, r1)
+ *   clo, chi  clamp-to-edge bounds of sample() (fs/differentiation.py:4-9) in local row indices:
+ *             a read of row r uses row min(max(r, clo), chi).  Single GPU: clo=0, chi=rows-1.
+ *             Interior ranks: clo=0, chi=rows-1 as well (halo rows exist); edge ranks clamp to
+ *             their first/last owned row.
+ *   gi0       global row index of local row 0 (red/black parity)
+ *
+ * Floating point: kernels are compiled with -fmad=false and use IEEE div/sqrt, literal
+ * left-to-right operation order of the reference source, fminf/fmaxf NaN rule, so
+ * results are bit-identical to the CPU oracle (oracle/fs2d_oracle.c) -- except
+ * fs2d_jacobi_fused's rhs pre-pass variant where stated.
+ */
+#ifndef FS2D_H
+#define FS2D_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FS2D_OK 0
+#define FS2D_E_BADARG (-1)
+#define FS2D_E_CUDA (-2)
+#define FS2D_E_NCCL (-3)
+
+typedef struct {
+    int rows, Y, r0, r1, clo, chi, gi0;
+} fs2d_dom;
+
+/* advection scheme selector of fs2d_mac_update (fs/advection.py:12-24, :27-60) */
+#define FS2D_SCHEME_UPWIND 0
+#define FS2D_SCHEME_KK 1
+
+/* pressure-BC cell codes (derived from the mask by the host layer; see DESIGN.md "pcode") */
+#define FS2D_PC_FLUID 0   /* mask 0                                                          */
+#define FS2D_PC_W_IM 1    /* wall: p = p(i-1,j)          boundary_condition.py:46-47         */
+#define FS2D_PC_W_IP 2    /* wall: p = p(i+1,j)          :48-49                              */
+#define FS2D_PC_W_JM 3    /* wall: p = p(i,j-1)          :50-51                              */
+#define FS2D_PC_W_JP 4    /* wall: p = p(i,j+1)          :52-53                              */
+#define FS2D_PC_W_IM_JP 5 /* wall: (p(i-1,j)+p(i,j+1))/2 :54-55                              */
+#define FS2D_PC_W_IP_JP 6 /* wall: (p(i+1,j)+p(i,j+1))/2 :56-57                              */
+#define FS2D_PC_W_IM_JM 7 /* wall: (p(i-1,j)+p(i,j-1))/2 :58-59                              */
+#define FS2D_PC_W_IP_JM 8 /* wall: (p(i+1,j)+p(i,j-1))/2 :60-61                              */
+#define FS2D_PC_W_NONE 9  /* wall, no branch taken: value is never written ("stale", T1)     */
+#define FS2D_PC_INFLOW 10 /* mask 2: BC value p(i+1,j)   :62-63 ; cell is relaxed afterwards */
+#define FS2D_PC_OUTFLOW 11 /* mask 3: BC value 0         :64-65 ; cell is relaxed afterwards */
+
+const char *fs2d_last_error(void);
+int fs2d_version(void);
+/* 1 if the library was built for sm_100a and a device of compute capability 10.x is current */
+int fs2d_device_ok(void);
+
+/* ---- sparse in-place boundary conditions (tables built once from the static mask) ---------- */
+/* BoundaryCondition.set_velocity_boundary_condition, fs/boundary_condition.py:16-39 (gather form,
+ * SURVEY T4).  Entry e: kind 0: v[tgt] = -v[src]; kind 1: v[tgt] = bc_const[tgt];
+ * kind 2: v[tgt].x = max(v[src].x, 0.05).  tgt/src are linear cell indices into the local array.
+ * scratch: >= 2*n floats. */
+int fs2d_vel_bc(float *v, const float *bc_const, const int32_t *tgt, const int32_t *src, const uint8_t *kind,
+                float *scratch, int n, void *stream);
+/* BoundaryCondition.set_pressure_boundary_condition, fs/boundary_condition.py:41-65 (gather form).
+ * kind 0: p[tgt] = p[src0]; kind 1: p[tgt] = (p[src0] + p[src1]) / 2; kind 2: p[tgt] = 0.
+ * scratch: >= n floats. */
+int fs2d_pressure_bc(float *p, const int32_t *tgt, const int32_t *src0, const int32_t *src1, const uint8_t *kind,
+                     float *scratch, int n, void *stream);
+
+/* ---- dense stencil kernels ------------------------------------------------------------------ */
+/* MacSolver._update_velocities, fs/solver.py:94-107 (fluid cells) */
+int fs2d_mac_update(float *vn, const float *vc, const float *pc, const uint8_t *mask, fs2d_dom d, float dt, float dx,
+                    float re, int scheme, void *stream);
+/* CipMacSolver._non_advection_phase, fs/solver.py:229-240 (not-wall cells) */
+int fs2d_cip_nonadv(float *fn, const float *fc, const float *pc, const uint8_t *mask, fs2d_dom d, float dt, float dx,
+                    float re, void *stream);
+/* CipMacSolver._non_advection_phase_grad, fs/solver.py:242-261; two_dx = (float)(2.0*dx) */
+int fs2d_cip_nonadv_grad(float *fxn, float *fyn, const float *fxc, const float *fyc, const float *fc, const float *fn,
+                         const uint8_t *mask, fs2d_dom d, float two_dx, void *stream);
+/* CipMacSolver._advection_phase/_cip_advect, fs/solver.py:267-332 (fluid cells);
+ * dx2 = (float)(dx*dx), dx3 = (float)(dx*dx*dx) folded in double by the caller */
+int fs2d_cip_advect(float *fn, float *fxn, float *fyn, const float *fc, const float *fxc, const float *fyc,
+                    const float *v, const uint8_t *mask, fs2d_dom d, float dt, float dx, float dx2, float dx3,
+                    void *stream);
+/* CipMacSolver._set_grad, fs/solver.py:207-211 (all cells) */
+int fs2d_set_grad(float *fx, float *fy, const float *f, fs2d_dom d, float dx, void *stream);
+/* VorticityConfinement._calc_vorticity, fs/vorticity_confinement.py:27-32 (fluid cells) */
+int fs2d_vort_calc(float *w, float *wabs, const float *vc, const uint8_t *mask, fs2d_dom d, float dx, void *stream);
+/* VorticityConfinement._add_vorticity, fs/vorticity_confinement.py:34-55; dtw = (float)(dt*weight) */
+int fs2d_vort_add(float *vn, const float *vc, const float *w, const float *wabs, const uint8_t *mask, fs2d_dom d,
+                  float dx, float dtw, void *stream);
+/* JacobiPressureUpdater._update, fs/pressure_updater.py:62-66 + predict_p :23-38 (not-wall cells).
+ * inline_bc != 0: neighbour pressures are the post-BC values of `pc` recomputed from `pcode`
+ * (pc itself is not modified) == set_pressure_boundary_condition(pc) followed by _update;
+ * inline_bc == 0: pc is read as is (caller already applied the BC).  pcode: FS2D_PC_* per cell. */
+int fs2d_jacobi_sweep(float *pn, const float *pc, const float *vc, const uint8_t *pcode, fs2d_dom d, float dt, float dx,
+                      int inline_bc, void *stream);
+/* n_sweeps of {pressure BC, Jacobi} with ping-pong between pa (current) and pb (next); equal to
+ * n_sweeps reference iterations (fs/pressure_updater.py:56-60) INCLUDING the final contents of the
+ * BC cells of both buffers.  tables as in fs2d_pressure_bc.  Returns via *final_in_b whether the
+ * current buffer after the call is pb (n_sweeps odd). */
+int fs2d_jacobi_update(float *pa, float *pb, const float *vc, const uint8_t *pcode, fs2d_dom d, float dt, float dx,
+                       int n_sweeps, const int32_t *tgt, const int32_t *src0, const int32_t *src1,
+                       const uint8_t *kind, float *scratch, int n_bc, int *final_in_b, void *stream);
+/* One colour pass of RedBlackSorPressureUpdater, fs/pressure_updater.py:98-114 (fluid cells of
+ * colour `parity`, (i_global + j) % 2); pc may alias pn (even pass, :96) */
+int fs2d_rbsor_pass(float *pn, const float *pc, const float *vc, const uint8_t *mask, fs2d_dom d, float dt, float dx,
+                    float omega, float one_minus_omega, int parity, void *stream);
+/* limit_field, fs/solver.py:38-43 (all cells, in place) */
+int fs2d_limit(float *v, fs2d_dom d, float limit, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FS2D_H */
