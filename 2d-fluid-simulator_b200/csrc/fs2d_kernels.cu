@@ -12,6 +12,7 @@
 namespace fs2d {
 
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;  // kernels launched by this library (bench.py "gpu_launches")
 void set_error(const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -442,6 +443,7 @@ extern "C" {
 
 const char *fs2d_last_error(void) { return g_err; }
 int fs2d_version(void) { return 1; }
+unsigned long long fs2d_launch_count(void) { return g_launches; }
 int fs2d_device_ok(void) {
     int dev = 0;
     cudaDeviceProp prop;
@@ -463,9 +465,9 @@ int fs2d_vel_bc(float *v, const float *bc_const, const int32_t *tgt, const int32
                 float *scratch, int n, void *stream) {
     if (n == 0) return FS2D_OK;
     FS2D_REQUIRE(v && bc_const && tgt && src && kind && scratch && n > 0, "null table/field pointer");
-    k_vel_bc_gather<<<nblk(n, 256), 256, 0, STREAM>>>((const float2 *)v, (const float2 *)bc_const, tgt, src, kind,
+    ++g_launches; k_vel_bc_gather<<<nblk(n, 256), 256, 0, STREAM>>>((const float2 *)v, (const float2 *)bc_const, tgt, src, kind,
                                                        (float2 *)scratch, n);
-    k_vel_bc_scatter<<<nblk(n, 256), 256, 0, STREAM>>>((float2 *)v, tgt, (const float2 *)scratch, n);
+    ++g_launches; k_vel_bc_scatter<<<nblk(n, 256), 256, 0, STREAM>>>((float2 *)v, tgt, (const float2 *)scratch, n);
     FS2D_LAUNCH_CHECK();
     return FS2D_OK;
 }
@@ -474,8 +476,8 @@ int fs2d_pressure_bc(float *p, const int32_t *tgt, const int32_t *src0, const in
                      float *scratch, int n, void *stream) {
     if (n == 0) return FS2D_OK;
     FS2D_REQUIRE(p && tgt && src0 && src1 && kind && scratch && n > 0, "null table/field pointer");
-    k_p_bc_gather<<<nblk(n, 256), 256, 0, STREAM>>>(p, src0, src1, kind, scratch, n);
-    k_p_bc_scatter<<<nblk(n, 256), 256, 0, STREAM>>>(p, tgt, scratch, n);
+    ++g_launches; k_p_bc_gather<<<nblk(n, 256), 256, 0, STREAM>>>(p, src0, src1, kind, scratch, n);
+    ++g_launches; k_p_bc_scatter<<<nblk(n, 256), 256, 0, STREAM>>>(p, tgt, scratch, n);
     FS2D_LAUNCH_CHECK();
     return FS2D_OK;
 }
@@ -494,7 +496,7 @@ int fs2d_mac_update(float *vn, const float *vc, const float *pc, const uint8_t *
     const bool p2 = is_pow2(dx);
     const float dx2 = dx * dx;
 #define MAC(P2, S) \
-    k_mac_update<P2, S><<<dense_grid(d), dense_block(), 0, STREAM>>>(vn, vc, pc, mask, d, dt, dx, DivC<P2>(dx), DivC<P2>(dx2), re)
+    ++g_launches; k_mac_update<P2, S><<<dense_grid(d), dense_block(), 0, STREAM>>>(vn, vc, pc, mask, d, dt, dx, DivC<P2>(dx), DivC<P2>(dx2), re)
     if (scheme == FS2D_SCHEME_UPWIND) DISPATCH_P2(p2, MAC(true, FS2D_SCHEME_UPWIND), MAC(false, FS2D_SCHEME_UPWIND));
     else DISPATCH_P2(p2, MAC(true, FS2D_SCHEME_KK), MAC(false, FS2D_SCHEME_KK));
 #undef MAC
@@ -508,7 +510,7 @@ int fs2d_cip_nonadv(float *fn, const float *fc, const float *pc, const uint8_t *
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
     const float dx2 = dx * dx;
-#define NA(P2) k_cip_nonadv<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(fn, fc, pc, mask, d, dt, DivC<P2>(dx), DivC<P2>(dx2), re)
+#define NA(P2) ++g_launches, k_cip_nonadv<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(fn, fc, pc, mask, d, dt, DivC<P2>(dx), DivC<P2>(dx2), re)
     DISPATCH_P2(is_pow2(dx), NA(true), NA(false));
 #undef NA
     FS2D_LAUNCH_CHECK();
@@ -520,7 +522,7 @@ int fs2d_cip_nonadv_grad(float *fxn, float *fyn, const float *fxc, const float *
     FS2D_REQUIRE(fxn && fyn && fxc && fyc && fc && fn && mask, "null field pointer");
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
-#define NG(P2) k_cip_nonadv_grad<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(fxn, fyn, fxc, fyc, fc, fn, mask, d, DivC<P2>(two_dx))
+#define NG(P2) ++g_launches, k_cip_nonadv_grad<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(fxn, fyn, fxc, fyc, fc, fn, mask, d, DivC<P2>(two_dx))
     DISPATCH_P2(is_pow2(two_dx), NG(true), NG(false));
 #undef NG
     FS2D_LAUNCH_CHECK();
@@ -534,7 +536,7 @@ int fs2d_cip_advect(float *fn, float *fxn, float *fyn, const float *fc, const fl
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
     const bool p2 = is_pow2(dx) && is_pow2(dx2) && is_pow2(dx3);
-#define CA(P2) k_cip_advect<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, DivC<P2>(dx), dx2, dx3)
+#define CA(P2) ++g_launches, k_cip_advect<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, DivC<P2>(dx), dx2, dx3)
     DISPATCH_P2(p2, CA(true), CA(false));
 #undef CA
     FS2D_LAUNCH_CHECK();
@@ -545,7 +547,7 @@ int fs2d_set_grad(float *fx, float *fy, const float *f, fs2d_dom d, float dx, vo
     FS2D_REQUIRE(fx && fy && f, "null field pointer");
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
-#define SG(P2) k_set_grad<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(fx, fy, f, d, DivC<P2>(dx))
+#define SG(P2) ++g_launches, k_set_grad<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(fx, fy, f, d, DivC<P2>(dx))
     DISPATCH_P2(is_pow2(dx), SG(true), SG(false));
 #undef SG
     FS2D_LAUNCH_CHECK();
@@ -556,7 +558,7 @@ int fs2d_vort_calc(float *w, float *wabs, const float *vc, const uint8_t *mask, 
     FS2D_REQUIRE(w && wabs && vc && mask, "null field pointer");
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
-#define VC(P2) k_vort_calc<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(w, wabs, vc, mask, d, DivC<P2>(dx))
+#define VC(P2) ++g_launches, k_vort_calc<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(w, wabs, vc, mask, d, DivC<P2>(dx))
     DISPATCH_P2(is_pow2(dx), VC(true), VC(false));
 #undef VC
     FS2D_LAUNCH_CHECK();
@@ -568,7 +570,7 @@ int fs2d_vort_add(float *vn, const float *vc, const float *w, const float *wabs,
     FS2D_REQUIRE(vn && vc && w && wabs && mask, "null field pointer");
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
-#define VA(P2) k_vort_add<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(vn, vc, w, wabs, mask, d, DivC<P2>(dx), dtw)
+#define VA(P2) ++g_launches, k_vort_add<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(vn, vc, w, wabs, mask, d, DivC<P2>(dx), dtw)
     DISPATCH_P2(is_pow2(dx), VA(true), VA(false));
 #undef VA
     FS2D_LAUNCH_CHECK();
@@ -581,11 +583,11 @@ static int launch_jacobi(float *pn, const float *pc, const float *vc, const uint
                      ((uintptr_t)vc % 16 == 0) && ((uintptr_t)pcode % 4 == 0);
     if (vec) {
         dim3 blk(32, JV_ROWS, 1), grd(nblk(d.r1 - d.r0, JV_ROWS), nblk(d.Y, 128), 1);
-        if (inline_bc) k_jacobi_vec4<true><<<grd, blk, 0, s>>>(pn, pc, vc, pcode, d, dt, dx);
-        else k_jacobi_vec4<false><<<grd, blk, 0, s>>>(pn, pc, vc, pcode, d, dt, dx);
+        if (inline_bc) ++g_launches, k_jacobi_vec4<true><<<grd, blk, 0, s>>>(pn, pc, vc, pcode, d, dt, dx);
+        else ++g_launches, k_jacobi_vec4<false><<<grd, blk, 0, s>>>(pn, pc, vc, pcode, d, dt, dx);
     } else {
-        if (inline_bc) k_jacobi_scalar<true><<<dense_grid(d), dense_block(), 0, s>>>(pn, pc, vc, pcode, d, dt, dx);
-        else k_jacobi_scalar<false><<<dense_grid(d), dense_block(), 0, s>>>(pn, pc, vc, pcode, d, dt, dx);
+        if (inline_bc) ++g_launches, k_jacobi_scalar<true><<<dense_grid(d), dense_block(), 0, s>>>(pn, pc, vc, pcode, d, dt, dx);
+        else ++g_launches, k_jacobi_scalar<false><<<dense_grid(d), dense_block(), 0, s>>>(pn, pc, vc, pcode, d, dt, dx);
     }
     return FS2D_OK;
 }
@@ -603,20 +605,30 @@ int fs2d_jacobi_sweep(float *pn, const float *pc, const float *vc, const uint8_t
 
 int fs2d_jacobi_update(float *pa, float *pb, const float *vc, const uint8_t *pcode, fs2d_dom d, float dt, float dx,
                        int n_sweeps, const int32_t *tgt, const int32_t *src0, const int32_t *src1,
-                       const uint8_t *kind, float *scratch, int n_bc, int *final_in_b, void *stream) {
+                       const uint8_t *kind, float *scratch, int n_bc, const int32_t *f_tgt, const int32_t *f_src0,
+                       const int32_t *f_src1, const uint8_t *f_kind, int n_feed, int *final_in_b, void *stream) {
     FS2D_REQUIRE(pa && pb && vc && pcode && pa != pb, "null/aliased field pointer");
     FS2D_REQUIRE(n_sweeps >= 0, "negative sweep count");
     FS2D_REQUIRE(n_bc == 0 || (tgt && src0 && src1 && kind && scratch), "null BC table");
+    FS2D_REQUIRE(n_feed == 0 || (f_tgt && f_src0 && f_src1 && f_kind && scratch), "null feed table");
     if (int e = check_dom(d)) return e;
     float *cur = pa, *nxt = pb;
     for (int s = 0; s < n_sweeps; ++s) {
         // The stored BC values of a buffer are only observable after its last in-place BC pass
-        // (SURVEY T1): materialise them for the final two sweeps, recompute inline before that.
-        if (s >= n_sweeps - 2 && n_bc > 0) {
-            k_p_bc_gather<<<nblk(n_bc, 256), 256, 0, STREAM>>>(cur, src0, src1, kind, scratch, n_bc);
-            k_p_bc_scatter<<<nblk(n_bc, 256), 256, 0, STREAM>>>(cur, tgt, scratch, n_bc);
+        // (SURVEY T1): the final two sweeps run literally (in-place BC, then a plain sweep); before
+        // that the sweep recomputes post-BC neighbour values inline and leaves `cur` untouched.
+        const bool literal = s >= n_sweeps - 2;
+        if (literal && n_bc > 0) {
+            ++g_launches; k_p_bc_gather<<<nblk(n_bc, 256), 256, 0, STREAM>>>(cur, src0, src1, kind, scratch, n_bc);
+            ++g_launches; k_p_bc_scatter<<<nblk(n_bc, 256), 256, 0, STREAM>>>(cur, tgt, scratch, n_bc);
         }
-        if (d.r1 > d.r0) launch_jacobi(nxt, cur, vc, pcode, d, dt, dx, 1, STREAM);
+        if (d.r1 > d.r0) launch_jacobi(nxt, cur, vc, pcode, d, dt, dx, literal ? 0 : 1, STREAM);
+        if (!literal && n_feed > 0) {
+            // wall-BC cells whose STORED value is read raw by an inflow cell two sweeps later
+            // (p(i,j) = p(i+1,j), boundary_condition.py:62-63): keep exactly those materialised.
+            ++g_launches; k_p_bc_gather<<<nblk(n_feed, 256), 256, 0, STREAM>>>(cur, f_src0, f_src1, f_kind, scratch, n_feed);
+            ++g_launches; k_p_bc_scatter<<<nblk(n_feed, 256), 256, 0, STREAM>>>(cur, f_tgt, scratch, n_feed);
+        }
         float *t = cur; cur = nxt; nxt = t;
     }
     FS2D_LAUNCH_CHECK();
@@ -630,7 +642,7 @@ int fs2d_rbsor_pass(float *pn, const float *pc, const float *vc, const uint8_t *
     FS2D_REQUIRE(parity == 0 || parity == 1, "parity must be 0 or 1");
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
-    k_rbsor_pass<<<dense_grid(d), dense_block(), 0, STREAM>>>(pn, pc, vc, mask, d, dt, dx, omega, one_minus_omega, parity);
+    ++g_launches; k_rbsor_pass<<<dense_grid(d), dense_block(), 0, STREAM>>>(pn, pc, vc, mask, d, dt, dx, omega, one_minus_omega, parity);
     FS2D_LAUNCH_CHECK();
     return FS2D_OK;
 }
@@ -639,7 +651,7 @@ int fs2d_limit(float *v, fs2d_dom d, float limit, void *stream) {
     FS2D_REQUIRE(v, "null field pointer");
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
-    k_limit<<<dense_grid(d), dense_block(), 0, STREAM>>>(v, d, limit);
+    ++g_launches; k_limit<<<dense_grid(d), dense_block(), 0, STREAM>>>(v, d, limit);
     FS2D_LAUNCH_CHECK();
     return FS2D_OK;
 }

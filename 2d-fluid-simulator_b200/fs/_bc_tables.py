@@ -150,13 +150,19 @@ def pressure_table(pcode: torch.Tensor, t0: int | None = None, t1: int | None = 
     zero = kind == 2
     s0i, s0j = torch.where(zero, ti, s0i), torch.where(zero, tj, s0j)
     s1i, s1j = torch.where(kind != 1, s0i, s1i), torch.where(kind != 1, s0j, s1j)
-    # hazard for the inline-BC sweep: an inflow cell whose (i+1, j) source is itself a wall-BC cell
-    src_code = pcode[s0i, s0j]
-    inflow_reads_bc = bool(((c == PC_INFLOW) & (src_code >= PC_W_IM) & (src_code <= PC_W_IP_JM)).any()) \
-        if ti.numel() else False
-    return {"tgt": _window_index(ti, tj, w0, w1, Y, "p tgt"), "src0": _window_index(s0i, s0j, w0, w1, Y, "p src0"),
-            "src1": _window_index(s1i, s1j, w0, w1, Y, "p src1"), "kind": kind.contiguous(), "n": int(ti.numel()),
-            "inflow_reads_bc": inflow_reads_bc}
+    tgt = _window_index(ti, tj, w0, w1, Y, "p tgt")
+    src0 = _window_index(s0i, s0j, w0, w1, Y, "p src0")
+    src1 = _window_index(s1i, s1j, w0, w1, Y, "p src1")
+    kind = kind.contiguous()
+    # "feed" sub-table: wall-BC cells (codes 1..8) sitting at (i+1, j) of an inflow cell.  Their STORED
+    # value is read raw by that inflow cell's BC (p = p(i+1,j), :62-63), so the inline-BC sweep path must
+    # keep exactly these cells materialised (see fs2d_jacobi_update).
+    up = _shift(pcode, -1, 0)  # code of (i-1, j)
+    feeds = (c >= PC_W_IM) & (c <= PC_W_IP_JM) & (up[ti, tj] == PC_INFLOW) & (ti > 0)
+    sel = torch.nonzero(feeds, as_tuple=True)[0]
+    feed = {"tgt": tgt[sel].contiguous(), "src0": src0[sel].contiguous(), "src1": src1[sel].contiguous(),
+            "kind": kind[sel].contiguous(), "n": int(sel.numel())}
+    return {"tgt": tgt, "src0": src0, "src1": src1, "kind": kind, "n": int(ti.numel()), "feed": feed}
 
 
 def exposed_stale_cells(pcode: torch.Tensor) -> torch.Tensor:

@@ -35,6 +35,7 @@ _P = c_void_p
 _SIGNATURES = {
     "fs2d_last_error": (c_char_p, []),
     "fs2d_version": (c_int, []),
+    "fs2d_launch_count": (ctypes.c_ulonglong, []),
     "fs2d_device_ok": (c_int, []),
     "fs2d_vel_bc": (c_int, [_P, _P, _P, _P, _P, _P, c_int, _P]),
     "fs2d_pressure_bc": (c_int, [_P, _P, _P, _P, _P, _P, c_int, _P]),
@@ -47,7 +48,7 @@ _SIGNATURES = {
     "fs2d_vort_add": (c_int, [_P, _P, _P, _P, _P, Dom, c_float, c_float, _P]),
     "fs2d_jacobi_sweep": (c_int, [_P, _P, _P, _P, Dom, c_float, c_float, c_int, _P]),
     "fs2d_jacobi_update": (c_int, [_P, _P, _P, _P, Dom, c_float, c_float, c_int, _P, _P, _P, _P, _P, c_int,
-                                   POINTER(c_int), _P]),
+                                   _P, _P, _P, _P, c_int, POINTER(c_int), _P]),
     "fs2d_rbsor_pass": (c_int, [_P, _P, _P, _P, Dom, c_float, c_float, c_float, c_float, c_int, _P]),
     "fs2d_limit": (c_int, [_P, Dom, c_float, _P]),
 }

@@ -52,18 +52,13 @@ class JacobiPressureUpdater(PressureUpdater):
 
             jacobi_update_distributed(self, p, v_current)
             return
-        if bc._p_table["inflow_reads_bc"]:
-            # exotic masks (inflow cell fed by a wall-BC cell): literal per-sweep in-place BC
-            for _ in range(self._n_iter):
-                bc.set_pressure_boundary_condition(p.current)
-                self._update(p.next, p.current, v_current)
-                p.swap()
-            return
         t = bc._p_table
+        f = t["feed"]
         final_in_b = ctypes.c_int(0)
         _lib.call("fs2d_jacobi_update", p.current.ptr(), p.next.ptr(), v_current.ptr(), _lib.ptr(bc._pcode), bc.dom,
                   self.dt, self.dx, self._n_iter, _lib.ptr(t["tgt"]), _lib.ptr(t["src0"]), _lib.ptr(t["src1"]),
-                  _lib.ptr(t["kind"]), _lib.ptr(bc._scratch), t["n"], ctypes.byref(final_in_b), _lib.stream())
+                  _lib.ptr(t["kind"]), _lib.ptr(bc._scratch), t["n"], _lib.ptr(f["tgt"]), _lib.ptr(f["src0"]),
+                  _lib.ptr(f["src1"]), _lib.ptr(f["kind"]), f["n"], ctypes.byref(final_in_b), _lib.stream())
         if final_in_b.value:
             p.swap()  # n_iter odd: same net effect as the reference's n_iter swaps
 

@@ -40,6 +40,16 @@ class Solver(metaclass=ABCMeta):
     def _buffer(self, n_channel: int) -> DoubleBuffer:
         return DoubleBuffer(self.resolution, n_channel, self._bc.device, self._bc.halo)
 
+    timing_events = None  # optional (start, stop) torch.cuda.Event pair recorded around the pressure update
+
+    def _pressure_update(self) -> None:
+        ev = self.timing_events
+        if ev is not None:
+            ev[0].record()
+        self.pressure_updater.update(self.p, self.v.current)
+        if ev is not None:
+            ev[1].record()
+
     def _halo(self):
         if self._bc.partition.world == 1:
             return None
@@ -87,7 +97,7 @@ class MacSolver(Solver):
         if self.vorticity_confinement is not None:
             self.vorticity_confinement.apply(self.v)
             self.v.swap()
-        self.pressure_updater.update(self.p, self.v.current)
+        self._pressure_update()
         limit_field(self.v.current, VELOCITY_LIMIT, bc=self._bc)
 
     def get_fields(self) -> tuple[Field, Field]:
@@ -124,7 +134,7 @@ class CipMacSolver(Solver):
         if self.vorticity_confinement is not None:
             self.vorticity_confinement.apply(self.v)
             self.v.swap()
-        self.pressure_updater.update(self.p, self.v.current)
+        self._pressure_update()
         limit_field(self.v.current, VELOCITY_LIMIT, bc=self._bc)
 
     def get_fields(self) -> tuple[Field, Field]:

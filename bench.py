@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (one solver time step) on N B200s of one box.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle)
+
+Workload (`config.workload`): BASELINE config 4's per-GPU shard -- scene bc=2, CIP advection,
+Re=1e5, vorticity confinement 5.0 (main.py default), dt = 0.05/8192, dx = 1/8192, 80 Jacobi sweeps
+per step, fp32, quiescent start -- with 8192 x 8192 cells PER GPU (weak scaling): the global grid is
+(8192*N) x 8192 rows x columns, split into N row strips.  N=2 is exactly BASELINE config 4
+(res=8192, 16384 x 8192).  metric = cell-updates/s = cells * steps / time (all cells).
+
+One JSON line on rank 0.  `value`: device-resident stepping (state stays in HBM).  `e2e`: the same
+step through the public API with HOST buffers: every step uploads the state (v, vx, vy, p) from
+pinned host memory and downloads (v, p) (the `field_to_numpy()` payload) inside the timed region.
+`roofline`: the Jacobi sweep (12 algorithmic B/cell/sweep) timed with CUDA events around
+the pressure update inside the timed steps.  `cpu_baseline`: the CPU oracle (a C/OpenMP restatement
+of the reference's Taichi kernels -- real Taichi cannot be installed offline) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+for _p in (str(REPO), str(REPO / "2d-fluid-simulator_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+CELLS_PER_GPU_ROWS = 8192
+Y_COLS = 8192
+SCENE, SCHEME, RE, VC, N_JACOBI = 2, "cip", 1e5, 5.0, 80
+ALGO_BYTES_PER_CELL_SWEEP = 12.0       # p read + source read + p write; mask excluded
+ALGO_BYTES_PER_CELL_STEP = 139.0 + 12.0 * N_JACOBI
+
+
+def parse() -> argparse.Namespace:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--rows-per-gpu", type=int, default=CELLS_PER_GPU_ROWS, help="override for quick checks")
+    ap.add_argument("--cols", type=int, default=Y_COLS)
+    ap.add_argument("--jacobi", type=int, default=N_JACOBI)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-rows", type=int, default=1024, help="rows of the CPU-baseline sample grid")
+    return ap.parse_args()
+
+
+def peaks() -> tuple[float, str]:
+    f = REPO / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self) -> None:
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self) -> dict:
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline (the oracle; the only place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(rows: int, cols: int, n_jacobi: int, steps: int, warmup: int) -> dict:
+    from fs.boundary_condition import build_scene
+    from oracle import oracle as orc
+
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    const, mask = build_scene(SCENE, rows, cols)
+    dt, dx = 0.05 / Y_COLS, 1.0 / Y_COLS
+    s = orc.OracleSolver(mask, const, dt, dx, RE, SCHEME, VC, ("jacobi", n_jacobi))
+    for _ in range(warmup):
+        s.update()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        s.update()
+    t = time.perf_counter() - t0
+    cells = rows * cols
+    return {"value": cells * steps / t, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+            "sample": f"CPU oracle (C/OpenMP restatement of the reference's Taichi kernels; Taichi itself is not "
+                      f"installable offline), same scene/scheme/{n_jacobi} sweeps on a {rows}x{cols} grid, "
+                      f"{steps} steps after {warmup} warm-up, {t / steps * 1e3:.0f} ms/step",
+            "ms_per_step": t / steps * 1e3}
+
+
+def run_reference(a: argparse.Namespace) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows = min(a.cpu_sample_rows, a.rows_per_gpu * a.gpus)
+    r = cpu_reference(rows, a.cols, a.jacobi, a.steps, min(a.warmup, 1))
+    line = {"impl": "reference", "metric": "cell-updates/s", "value": r["value"], "unit": "cell-updates/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a, a.gpus), "gpu_launches": 0,
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a: argparse.Namespace, n: int) -> dict:
+    return {"workload": f"BASELINE config 4 shard: bc={SCENE} {SCHEME} Re={RE:g} vc={VC} dt=0.05/8192 dx=1/8192 "
+                        f"jacobi={a.jacobi}/step, grid {a.rows_per_gpu * n}x{a.cols} ({a.rows_per_gpu}x{a.cols} cells/GPU; "
+                        f"N=2 == res=8192), quiescent start, -no_dye",
+            "global_grid": [a.rows_per_gpu * n, a.cols], "cells_per_gpu": a.rows_per_gpu * a.cols,
+            "parallelism": f"row-strips x{n}", "l2_policy": "working set (>=5 GB/GPU) >> 126 MB L2, no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(a: argparse.Namespace) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from fs import _lib
+    from fs.boundary_condition import BoundaryCondition, build_scene
+    from fs.distributed import Partition
+    from fs.fluid_simulator import make_solver
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {a.gpus}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+    assert lib.fs2d_device_ok(), lib.fs2d_last_error().decode()
+
+    X, Y = a.rows_per_gpu * world, a.cols
+    dt, dx = 0.05 / Y_COLS, 1.0 / Y_COLS
+    const, mask = build_scene(SCENE, X, Y)
+    part = Partition(X, rank, world, 0 if world == 1 else 2)
+    bc = BoundaryCondition(const, mask, partition=part)
+    del const, mask
+    solver = make_solver(bc, dt, dx, RE, VC, SCHEME, pressure="jacobi", n_iter=a.jacobi)
+    cells_total = X * Y
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing -------------------------------------------------------------
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    solver.timing_events = None
+    for _ in range(a.warmup):
+        solver.update()
+    barrier()
+    n0 = lib.fs2d_launch_count()
+    t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        t_start.record()
+        for k in range(a.steps):
+            solver.timing_events = ev[k]      # the solver records these around pressure_updater.update()
+            solver.update()
+        t_stop.record()
+        barrier()
+    solver.timing_events = None
+    launches = lib.fs2d_launch_count() - n0
+    ms_total = max_over_ranks(t_start.elapsed_time(t_stop))
+    ms_step = ms_total / a.steps
+    value = cells_total * a.steps / (ms_total * 1e-3)
+    ms_poisson = max_over_ranks(sum(s.elapsed_time(e) for s, e in ev) / a.steps)
+    ms_sweep = ms_poisson / a.jacobi
+    peak, peak_src = peaks()
+    achieved = ALGO_BYTES_PER_CELL_SWEEP * (a.rows_per_gpu * Y) / (ms_sweep * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_jacobi_vec4 (Jacobi pressure sweep incl. its BC passes)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL_SWEEP * a.rows_per_gpu * Y,
+                "ms_per_sweep": ms_sweep, "poisson_share_of_step": ms_poisson / ms_step, "traffic": None,
+                "whole_step_algorithmic_gbs": ALGO_BYTES_PER_CELL_STEP * (a.rows_per_gpu * Y) / (ms_step * 1e-3) / 1e9}
+
+    # ---- end-to-end through the public API with host buffers ----------------------------------
+    e2e = None
+    if not a.no_e2e:
+        fields = {"v": solver.v, "vx": solver.vx, "vy": solver.vy, "p": solver.p}
+        host_in = {k: torch.empty_like(b.current.owned(), device="cpu").pin_memory() for k, b in fields.items()}
+        for k, b in fields.items():
+            host_in[k].copy_(b.current.owned())
+        host_out = {k: torch.empty_like(fields[k].current.owned(), device="cpu").pin_memory() for k in ("v", "p")}
+        h2d = sum(t.numel() * t.element_size() for t in host_in.values())
+        d2h = sum(t.numel() * t.element_size() for t in host_out.values())
+
+        def e2e_step():
+            for k, b in fields.items():
+                b.current.owned().copy_(host_in[k], non_blocking=True)
+            solver.update()
+            v, p = solver.get_fields()
+            host_out["v"].copy_(v.owned(), non_blocking=True)
+            host_out["p"].copy_(p.owned(), non_blocking=True)
+
+        e2e_steps = max(2, min(a.steps, 5))
+        e2e_step()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        s1.record()
+        barrier()
+        ms = max_over_ranks(s0.elapsed_time(s1))
+        e2e = {"value": cells_total * e2e_steps / (ms * 1e-3), "unit": "cell-updates/s", "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": d2h * world, "steps": e2e_steps, "ms_per_step": ms / e2e_steps,
+               "what": "per step: pinned-host state (v,vx,vy,p) -> device, step(), (v,p) -> pinned host"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        r = cpu_reference(min(a.cpu_sample_rows, a.rows_per_gpu), a.cols, a.jacobi, 2, 1)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": "cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, world),
+                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -66,6 +66,8 @@ typedef struct {
 
 const char *fs2d_last_error(void);
 int fs2d_version(void);
+/* number of kernels this library has launched in this process (bench.py gpu_launches) */
+unsigned long long fs2d_launch_count(void);
 /* 1 if the library was built for sm_100a and a device of compute capability 10.x is current */
 int fs2d_device_ok(void);
 
@@ -112,11 +114,14 @@ int fs2d_jacobi_sweep(float *pn, const float *pc, const float *vc, const uint8_t
                       int inline_bc, void *stream);
 /* n_sweeps of {pressure BC, Jacobi} with ping-pong between pa (current) and pb (next); equal to
  * n_sweeps reference iterations (fs/pressure_updater.py:56-60) INCLUDING the final contents of the
- * BC cells of both buffers.  tables as in fs2d_pressure_bc.  Returns via *final_in_b whether the
- * current buffer after the call is pb (n_sweeps odd). */
+ * BC cells of both buffers.  (tgt, src0, src1, kind, n_bc): table as in fs2d_pressure_bc.
+ * (f_*, n_feed): the sub-table of wall-BC cells whose stored value an inflow cell reads raw
+ * (usually empty).  scratch: >= max(n_bc, n_feed) floats.  *final_in_b = 1 if the current buffer
+ * after the call is pb (n_sweeps odd). */
 int fs2d_jacobi_update(float *pa, float *pb, const float *vc, const uint8_t *pcode, fs2d_dom d, float dt, float dx,
                        int n_sweeps, const int32_t *tgt, const int32_t *src0, const int32_t *src1,
-                       const uint8_t *kind, float *scratch, int n_bc, int *final_in_b, void *stream);
+                       const uint8_t *kind, float *scratch, int n_bc, const int32_t *f_tgt, const int32_t *f_src0,
+                       const int32_t *f_src1, const uint8_t *f_kind, int n_feed, int *final_in_b, void *stream);
 /* One colour pass of RedBlackSorPressureUpdater, fs/pressure_updater.py:98-114 (fluid cells of
  * colour `parity`, (i_global + j) % 2); pc may alias pn (even pass, :96) */
 int fs2d_rbsor_pass(float *pn, const float *pc, const float *vc, const uint8_t *mask, fs2d_dom d, float dt, float dx,

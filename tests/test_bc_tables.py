@@ -1,0 +1,106 @@
+"""Host-side BC tables (fs/_bc_tables.py) vs the oracle's BC kernels, on CPU tensors."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+from conftest import assert_bitexact
+
+from fs import _bc_tables as T
+from fs.boundary_condition import build_scene
+from fs.distributed import Partition
+from oracle import oracle as orc
+
+
+def apply_vel_table(v: np.ndarray, const: np.ndarray, t: dict) -> np.ndarray:
+    """numpy model of k_vel_bc_gather/k_vel_bc_scatter (test-only)."""
+    out = v.reshape(-1, 2).copy()
+    flat, c = v.reshape(-1, 2), const.reshape(-1, 2)
+    tgt, src, kind = t["tgt"].numpy().astype(np.int64), t["src"].numpy().astype(np.int64), t["kind"].numpy()
+    vals = np.where((kind == 0)[:, None], -flat[src], c[tgt])
+    of = np.stack([np.fmax(flat[src][:, 0], np.float32(0.05)), flat[tgt][:, 1]], axis=1)
+    vals = np.where((kind == 2)[:, None], of, vals)
+    out[tgt] = vals
+    return out.reshape(v.shape)
+
+
+def apply_p_table(p: np.ndarray, t: dict) -> np.ndarray:
+    flat = p.reshape(-1)
+    out = flat.copy()
+    tgt, s0, s1, kind = (t[k].numpy().astype(np.int64) for k in ("tgt", "src0", "src1", "kind"))
+    vals = np.where(kind == 0, flat[s0], np.where(kind == 1, (flat[s0] + flat[s1]) / np.float32(2.0), np.float32(0.0)))
+    out[tgt] = vals.astype(np.float32)
+    return out.reshape(p.shape)
+
+
+def scenes():
+    for num in (1, 2, 3, 4, 5):
+        for res in (16, 24, 40):
+            yield num, res
+
+
+@pytest.mark.parametrize("num,res", list(scenes()))
+def test_tables_equal_oracle_on_scenes(num, res):
+    const, mask = build_scene(num, 2 * res, res)
+    rng = np.random.default_rng(num * 100 + res)
+    v = rng.uniform(-1, 1, mask.shape + (2,)).astype(np.float32)
+    p = rng.uniform(-1, 1, mask.shape).astype(np.float32)
+    tm = torch.from_numpy(mask)
+    vt = T.velocity_table(tm)
+    assert num == 3 or not vt["thin_walls"]  # tiny bc3 discs are 1-cell walls
+    want = v.copy(); orc.vel_bc(want, mask, const)
+    assert_bitexact("vel table", apply_vel_table(v, const, vt), want)
+    pt = T.pressure_table(T.pressure_codes(tm))
+    want = p.copy(); orc.p_bc(want, mask)
+    assert_bitexact("p table", apply_p_table(p, pt), want)
+
+
+def test_tables_equal_oracle_on_random_masks():
+    rng = np.random.default_rng(11)
+    for trial in range(60):
+        X, Y = int(rng.integers(5, 28)), int(rng.integers(5, 28))
+        mask = rng.choice(np.array([0, 1, 2, 3], dtype=np.uint8), size=(X, Y), p=[0.45, 0.45, 0.05, 0.05])
+        const = rng.uniform(-1, 1, (X, Y, 2)).astype(np.float32)
+        v = rng.uniform(-1, 1, (X, Y, 2)).astype(np.float32)
+        p = rng.uniform(-1, 1, (X, Y)).astype(np.float32)
+        tm = torch.from_numpy(mask)
+        want = v.copy(); orc.vel_bc(want, mask, const)
+        assert_bitexact(f"vel {trial}", apply_vel_table(v, const, T.velocity_table(tm)), want)
+        want = p.copy(); orc.p_bc(want, mask)
+        assert_bitexact(f"p {trial}", apply_p_table(p, T.pressure_table(T.pressure_codes(tm))), want)
+
+
+def test_pcode_predicates():
+    _, mask = build_scene(2, 64, 32)
+    code = T.pressure_codes(torch.from_numpy(mask)).numpy()
+    assert ((code >= 1) & (code <= 9)).sum() == (mask == 1).sum()
+    assert ((code == T.PC_FLUID) == (mask == 0)).all()
+    assert ((code == T.PC_INFLOW) == (mask == 2)).all() and ((code == T.PC_OUTFLOW) == (mask == 3)).all()
+    # bc2 has never-written wall cells next to inflow/outflow cells (SURVEY T1 / DESIGN "stale")
+    assert T.exposed_stale_cells(torch.from_numpy(code)).numel() > 0
+
+
+def test_window_tables_are_local_and_checked():
+    _, mask = build_scene(2, 64, 32)
+    tm = torch.from_numpy(mask)
+    part = Partition(64, rank=1, world=2, halo=2)
+    g0, g1 = part.owned(); w0, w1 = part.window()
+    t = T.velocity_table(tm, g0, min(g1, 64), w0, w1)
+    assert t["n"] > 0 and int(t["tgt"].min()) >= 0 and int(t["src"].min()) >= 0
+    with pytest.raises(ValueError):
+        T.velocity_table(tm, 0, 64, 1, 64)  # source rows outside the window
+
+
+def test_partition_arithmetic():
+    for X, P in ((64, 1), (64, 2), (67, 4), (8192 * 8, 8)):
+        rows = []
+        for r in range(P):
+            p = Partition(X, r, P, 0 if P == 1 else 2)
+            g0, g1 = p.owned()
+            rows += list(range(g0, g1))
+            assert p.window() == (g0 - p.halo, g1 + p.halo)
+        assert rows == list(range(X))
+    with pytest.raises(ValueError):
+        Partition(64, 2, 2, 2)
+    with pytest.raises(ValueError):
+        Partition(64, 0, 2, 1)

@@ -1,0 +1,298 @@
+"""GPU parity tests proper: the CUDA path (through the fs API -> ctypes -> C ABI of libfs2d.so) vs
+the CPU oracle and vs the golden fixtures generated from the reference source.
+
+Bar: BIT-EXACT fp32 (the library is compiled with -fmad=false and keeps the reference's literal
+operation order), NaNs compare equal.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+from conftest import GOLDEN, assert_bitexact
+
+pytestmark = pytest.mark.gpu
+
+BCS = (1, 2, 3, 4, 5)
+
+
+@pytest.fixture(scope="module")
+def env():
+    from fs import _lib
+
+    lib = _lib.load()
+    assert lib.fs2d_device_ok(), lib.fs2d_last_error().decode()
+    return lib
+
+
+def fld(a: np.ndarray):
+    from fs.double_buffer import Field
+
+    f = Field(a.shape[:2], a.shape[2] if a.ndim == 3 else 1)
+    f.from_numpy(a)
+    return f
+
+
+def make_fs(mask, const, dt, dx, re, scheme, vc, pressure):
+    from fs.advection import advect_kk_scheme, advect_upwind
+    from fs.boundary_condition import BoundaryCondition
+    from fs.pressure_updater import JacobiPressureUpdater, RedBlackSorPressureUpdater
+    from fs.solver import CipMacSolver, MacSolver
+    from fs.vorticity_confinement import VorticityConfinement
+
+    bc = BoundaryCondition(const, mask)
+    vcf = VorticityConfinement(bc, dt, dx, vc) if vc is not None else None
+    pu = (JacobiPressureUpdater(bc, dt, dx, pressure[1]) if pressure[0] == "jacobi"
+          else RedBlackSorPressureUpdater(bc, dt, dx, pressure[1], pressure[2]))
+    if scheme == "cip":
+        return CipMacSolver(bc, pu, dt, dx, re, vcf)
+    return MacSolver(bc, pu, advect_upwind if scheme == "upwind" else advect_kk_scheme, dt, dx, re, vcf)
+
+
+def fs_state(s) -> dict:
+    d = {"v_cur": s.v.current, "v_nxt": s.v.next, "p_cur": s.p.current, "p_nxt": s.p.next}
+    if hasattr(s, "vx"):
+        d.update(vx_cur=s.vx.current, vx_nxt=s.vx.next, vy_cur=s.vy.current, vy_nxt=s.vy.next)
+    if s.vorticity_confinement is not None:
+        d.update(vort=s.vorticity_confinement.vorticity, vort_abs=s.vorticity_confinement.vorticity_abs)
+    return d
+
+
+def load_fs_state(s, st: dict) -> None:
+    for k, f in fs_state(s).items():
+        f.from_numpy(st[k])
+
+
+# ------------------------------------------------------------------------------------------------
+# 1. every kernel, one launch, on the reference-generated fixtures
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("num", BCS)
+def test_each_kernel_matches_reference_fixture(env, num, kernels_golden, masks_small):
+    from fs.solver import limit_field
+
+    g = kernels_golden
+    res, dt, dx, re, vcw = g["meta"]
+    res = int(res)
+    mask, const = masks_small[f"bc{num}_r{res}_mask"], masks_small[f"bc{num}_r{res}_const"]
+    G = lambda k: g[f"bc{num}/{k}"]  # noqa: E731
+    cip = make_fs(mask, const, dt, dx, re, "cip", vcw, ("jacobi", 1))
+    bc, vcf, jac = cip._bc, cip.vorticity_confinement, cip.pressure_updater
+    sor = make_fs(mask, const, dt, dx, re, "cip", None, ("rbsor", 1.3, 1)).pressure_updater
+
+    f = fld(G("v")); bc.set_velocity_boundary_condition(f); assert_bitexact("vel_bc", f.to_numpy(), G("vel_bc"))
+    f = fld(G("p")); bc.set_pressure_boundary_condition(f); assert_bitexact("p_bc", f.to_numpy(), G("p_bc"))
+    for name in ("upwind", "kk"):
+        s = make_fs(mask, const, dt, dx, re, name, None, ("jacobi", 1))
+        f = fld(G("vn0")); s._update_velocities(f, fld(G("v")), fld(G("p")))
+        assert_bitexact("mac_" + name, f.to_numpy(), G("mac_" + name))
+    fn = fld(G("vn0")); cip._non_advection_phase(fn, fld(G("v")), fld(G("p")))
+    assert_bitexact("nonadv", fn.to_numpy(), G("nonadv"))
+    fxn, fyn = fld(G("vxn0")), fld(G("vyn0"))
+    cip._non_advection_phase_grad(fxn, fyn, fld(G("vx")), fld(G("vy")), fld(G("v")), fn)
+    assert_bitexact("nonadv_gx", fxn.to_numpy(), G("nonadv_gx")); assert_bitexact("nonadv_gy", fyn.to_numpy(), G("nonadv_gy"))
+    a, b, c, fv = fld(G("vn0")), fld(G("vxn0")), fld(G("vyn0")), fld(G("v"))
+    cip._advection_phase(a, b, c, fv, fld(G("vx")), fld(G("vy")), fv)
+    assert_bitexact("cip_f", a.to_numpy(), G("cip_f")); assert_bitexact("cip_fx", b.to_numpy(), G("cip_fx"))
+    assert_bitexact("cip_fy", c.to_numpy(), G("cip_fy"))
+    a, b = fld(G("vxn0")), fld(G("vyn0")); cip._set_grad(a, b, fld(G("v")))
+    assert_bitexact("grad_x", a.to_numpy(), G("grad_x")); assert_bitexact("grad_y", b.to_numpy(), G("grad_y"))
+    vcf.vorticity.from_numpy(G("w0")); vcf.vorticity_abs.from_numpy(G("wa0"))
+    vcf._calc_vorticity(fld(G("v")))
+    assert_bitexact("vort", vcf.vorticity.to_numpy(), G("vort")); assert_bitexact("vort_abs", vcf.vorticity_abs.to_numpy(), G("vort_abs"))
+    f = fld(G("vn0")); vcf._add_vorticity(f, fld(G("v"))); assert_bitexact("vort_add", f.to_numpy(), G("vort_add"))
+    f = fld(G("pn0")); jac._update(f, fld(G("p")), fld(G("v"))); assert_bitexact("jacobi", f.to_numpy(), G("jacobi"))
+    f = fld(G("pn0")); sor._update(f, fld(G("p")), fld(G("v"))); assert_bitexact("rbsor", f.to_numpy(), G("rbsor"))
+    f = fld(G("v") * np.float32(12.0)); limit_field(f, 10.0); assert_bitexact("limit", f.to_numpy(), G("limit"))
+
+
+# ------------------------------------------------------------------------------------------------
+# 2. N-step trajectories through Solver.update(): every physical buffer, vs the reference fixtures
+# ------------------------------------------------------------------------------------------------
+TRAJ = sorted(p.name for p in GOLDEN.glob("traj_*.npz"))
+
+
+@pytest.mark.parametrize("name", TRAJ)
+def test_trajectory_matches_reference_fixture(env, name, masks_small):
+    g = np.load(GOLDEN / name)
+    num, res, vc = int(g["meta_num"]), int(g["meta_res"]), float(g["meta_vc"])
+    kind, n_iter = str(g["meta_pressure"]), int(g["meta_n_iter"])
+    pressure = ("jacobi", n_iter) if kind == "jacobi" else ("rbsor", 1.3, n_iter)
+    s = make_fs(masks_small[f"bc{num}_r{res}_mask"], masks_small[f"bc{num}_r{res}_const"], float(g["meta_dt"]),
+                float(g["meta_dx"]), float(g["meta_re"]), str(g["meta_scheme"]), None if vc < 0 else vc, pressure)
+    load_fs_state(s, {k[3:]: g[k] for k in g.files if k.startswith("s0_")})
+    for n in range(1, int(g["meta_steps"]) + 1):
+        s.update()
+        for k, f in fs_state(s).items():
+            assert_bitexact(f"{name} step {n} {k}", f.to_numpy(), g[f"s{n}_{k}"])
+
+
+# ------------------------------------------------------------------------------------------------
+# 3. BASELINE configs at sizes the oracle finishes in seconds, vs the oracle
+# ------------------------------------------------------------------------------------------------
+CONFIGS = [
+    # id, bc, res, dt, re, scheme, vc, pressure, steps
+    ("cfg1_as_given", 1, 128, 0.005, 100.0, "upwind", 5.0, ("jacobi", 40), 3),       # unstable beyond 3 steps
+    ("cfg1_stable", 1, 128, 0.0005, 100.0, "upwind", 5.0, ("jacobi", 40), 30),
+    ("cfg2_r256", 2, 256, None, 1e4, "cip", 5.0, ("jacobi", 80), 6),
+    ("cfg3_r256", 3, 256, None, 1e8, "cip", 10.0, ("jacobi", 100), 4),
+    ("cfg5_r192", 5, 192, None, 1e6, "cip", 5.0, ("jacobi", 21), 5),               # odd n_iter, Y % 64 != 0
+    ("kk_r100", 1, 100, None, 1000.0, "kk", 5.0, ("rbsor", 1.3, 2), 6),            # create() defaults, non-pow2 dx
+    ("cip_r50_y_not_mult4", 4, 50, None, 1e4, "cip", None, ("jacobi", 7), 4),      # scalar Jacobi path (Y % 4 != 0)
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=[c[0] for c in CONFIGS])
+def test_config_trajectory_vs_oracle(env, cfg):
+    from fs.boundary_condition import build_scene
+    from oracle import oracle as orc
+
+    _, num, res, dt, re, scheme, vc, pressure, steps = cfg
+    dt = dt if dt is not None else 0.05 / res
+    dx = 1.0 / res
+    const, mask = build_scene(num, 2 * res, res)
+    s = make_fs(mask, const, dt, dx, re, scheme, vc, pressure)
+    ref = orc.OracleSolver(mask, const, dt, dx, re, scheme, vc, pressure)
+    for n in range(1, steps + 1):
+        s.update()
+        ref.update()
+        if n in (1, steps):
+            got = fs_state(s)
+            for k, a in ref.state().items():
+                assert_bitexact(f"{cfg[0]} step {n} {k}", got[k].to_numpy(), a)
+
+
+def test_facade_matches_reference_defaults(env):
+    """FluidSimulator.create(...) == reference object graph (RB-SOR 1.3 x2) and the npz dump format."""
+    from fs.boundary_condition import build_scene
+    from fs.fluid_simulator import FluidSimulator
+    from oracle import oracle as orc
+
+    res = 64
+    sim = FluidSimulator.create(5, res, 0.05 / res, 1.0 / res, 1e6, 5.0, "cip")
+    const, mask = build_scene(5, 2 * res, res)
+    ref = orc.OracleSolver(mask, const, 0.05 / res, 1.0 / res, 1e6, "cip", 5.0, ("rbsor", 1.3, 2))
+    for _ in range(5):
+        sim.step(); ref.update()
+    out = sim.field_to_numpy()
+    assert set(out) == {"v", "p"} and out["v"].shape == (2 * res, res, 2) and out["p"].shape == (2 * res, res)
+    assert_bitexact("v", out["v"], ref.v.current); assert_bitexact("p", out["p"], ref.p.current)
+    with pytest.raises(ValueError, match="Unknown scheme"):
+        FluidSimulator.create(1, 32, 0.001, 1 / 32, 100.0, None, "weno")
+
+
+# ------------------------------------------------------------------------------------------------
+# 4. size-independent properties at BASELINE sizes + strip invariance of the dom row ranges
+# ------------------------------------------------------------------------------------------------
+def test_jacobi_row_range_invariance_and_literal_equivalence(env):
+    """(a) sweeping rows [0,h) then [h,X) == one full sweep; (b) inline-BC sweep == in-place BC then a
+    plain sweep; (c) fs2d_jacobi_update(n) == n literal reference iterations -- all bitwise, res=512."""
+    from fs import _lib
+    from fs.boundary_condition import BoundaryCondition, build_scene
+    from fs.pressure_updater import JacobiPressureUpdater
+
+    res = 512
+    const, mask = build_scene(3, 2 * res, res)
+    bc = BoundaryCondition(const, mask)
+    rng = np.random.default_rng(5)
+    p0 = rng.uniform(-1, 1, mask.shape).astype(np.float32)
+    v = fld(rng.uniform(-1, 1, mask.shape + (2,)).astype(np.float32))
+    dt, dx = 0.05 / res, 1.0 / res
+    jac = JacobiPressureUpdater(bc, dt, dx, 9)
+    full, halves = fld(p0 * 3), fld(p0 * 3)
+    pc = fld(p0)
+    jac._sweep(full, pc, v, inline_bc=True)
+    X = mask.shape[0]
+    for r0, r1 in ((0, X // 3), (X // 3, X)):
+        _lib.call("fs2d_jacobi_sweep", halves.ptr(), pc.ptr(), v.ptr(), _lib.ptr(bc._pcode), bc.dom.replace(r0=r0, r1=r1),
+                  dt, dx, 1, _lib.stream())
+    assert_bitexact("row ranges", halves.to_numpy(), full.to_numpy())
+    lit_in = fld(p0); bc.set_pressure_boundary_condition(lit_in)
+    lit = fld(p0 * 3); jac._update(lit, lit_in, v)
+    assert_bitexact("inline vs literal", full.to_numpy(), lit.to_numpy())
+    # n sweeps: C loop vs literal Python loop, both physical buffers
+    from fs.double_buffer import DoubleBuffer
+    a, b = DoubleBuffer(mask.shape, 1), DoubleBuffer(mask.shape, 1)
+    for db in (a, b):
+        db.current.from_numpy(p0); db.next.from_numpy(p0[::-1].copy())
+    jac.update(a, v)
+    for _ in range(9):
+        bc.set_pressure_boundary_condition(b.current); jac._update(b.next, b.current, v); b.swap()
+    assert_bitexact("update cur", a.current.to_numpy(), b.current.to_numpy())
+    assert_bitexact("update nxt", a.next.to_numpy(), b.next.to_numpy())
+
+
+@pytest.mark.parametrize("num,res", [(2, 2048), (3, 1024)])
+def test_full_size_step_vs_oracle(env, num, res):
+    """BASELINE config 2 at its full size (and config 3's scene at res 1024): 2 CIP+VC steps with a
+    reduced sweep count, every buffer bit-compared with the oracle (seconds of CPU time)."""
+    from fs.boundary_condition import build_scene
+    from oracle import oracle as orc
+
+    dt, dx, re, vc, pressure = 0.05 / res, 1.0 / res, 1e4, 5.0, ("jacobi", 6)
+    const, mask = build_scene(num, 2 * res, res)
+    s = make_fs(mask, const, dt, dx, re, "cip", vc, pressure)
+    ref = orc.OracleSolver(mask, const, dt, dx, re, "cip", vc, pressure)
+    for _ in range(2):
+        s.update(); ref.update()
+    got = fs_state(s)
+    for k, a in ref.state().items():
+        assert_bitexact(f"bc{num} res{res} {k}", got[k].to_numpy(), a)
+
+
+def test_properties_at_res_8192(env):
+    """Size-independent properties on the res=8192 grid (16384 x 8192, BASELINE config 4):
+    zero velocity => CIP advection is the identity; constant p & zero v is a Jacobi fixed point on
+    cells whose stencil sees no outflow BC; limiter bounds |v| and leaves slow cells untouched; checksum of a strip-wise run ==
+    checksum of the whole-grid run."""
+    from fs import _lib
+    from fs.boundary_condition import BoundaryCondition, build_scene
+    from fs.double_buffer import Field
+    from fs.pressure_updater import JacobiPressureUpdater
+    from fs.solver import limit_field
+
+    res = 8192
+    dt, dx = 0.05 / res, 1.0 / res
+    const, mask = build_scene(2, 2 * res, res)
+    bc = BoundaryCondition(const, mask)
+    X, Y = mask.shape
+    g = torch.Generator(device="cuda").manual_seed(1)
+
+    def rnd(ch):
+        f = Field((X, Y), ch)
+        f.tensor.copy_(torch.rand(f.tensor.shape, device="cuda", generator=g) * 2 - 1)
+        return f
+
+    # CIP identity at zero velocity
+    f, fx, fy = rnd(2), rnd(2), rnd(2)
+    fn, fxn, fyn, zero = Field((X, Y), 2), Field((X, Y), 2), Field((X, Y), 2), Field((X, Y), 2)
+    _lib.call("fs2d_cip_advect", fn.ptr(), fxn.ptr(), fyn.ptr(), f.ptr(), fx.ptr(), fy.ptr(), zero.ptr(),
+              _lib.ptr(bc._bc_mask), bc.dom, dt, dx, dx**2, dx**3, _lib.stream())
+    fluid = (bc._bc_mask == 0).unsqueeze(-1)
+    for out, src in ((fn, f), (fxn, fx), (fyn, fy)):
+        assert torch.equal(torch.where(fluid, out.tensor, 0), torch.where(fluid, src.tensor, 0))
+        assert torch.count_nonzero(torch.where(fluid, 0, out.tensor)) == 0  # non-fluid cells untouched
+    del fn, fxn, fyn, fx, fy
+    # limiter idempotence
+    f.tensor.mul_(30.0)
+    before = f.tensor.clone()
+    limit_field(f, 10.0)
+    nrm, nrm0 = f.tensor.norm(dim=-1), before.norm(dim=-1)
+    assert float(nrm.max()) <= 10.0 * (1 + 1e-6)
+    small = nrm0 <= 10.0 * (1 - 1e-6)
+    assert torch.equal(f.tensor[small], before[small])  # cells under the limit are untouched
+    del before, nrm, nrm0, small, f
+    # Jacobi: strip-wise == whole, and fixed point
+    jac = JacobiPressureUpdater(bc, dt, dx, 1)
+    pc, v = rnd(1), rnd(2)
+    whole, strips = Field((X, Y), 1), Field((X, Y), 1)
+    jac._sweep(whole, pc, v, inline_bc=True)
+    for k in range(8):
+        _lib.call("fs2d_jacobi_sweep", strips.ptr(), pc.ptr(), v.ptr(), _lib.ptr(bc._pcode),
+                  bc.dom.replace(r0=k * X // 8, r1=(k + 1) * X // 8), dt, dx, 1, _lib.stream())
+    assert torch.equal(whole.tensor, strips.tensor)
+    pc.tensor.fill_(0.75); v.tensor.zero_()
+    jac._sweep(whole, pc, v, inline_bc=True)
+    interior = torch.zeros_like(bc._bc_mask, dtype=torch.bool)
+    interior[4:X - 4] = True
+    ok = (bc._bc_mask == 0) & interior
+    assert torch.equal(whole.tensor[ok], torch.full_like(whole.tensor[ok], 0.75))
