@@ -26,7 +26,12 @@ void set_error(const char *fmt, ...);
     } while (0)
 #define FS2D_LAUNCH_CHECK() FS2D_CUDA_CHECK(cudaGetLastError())
 
+extern unsigned long long g_launches;  // every kernel launch of the library bumps this
 int check_dom(const fs2d_dom &d);
+// in-place sparse pressure BC (gather then scatter); no-op for n <= 0
+void launch_p_bc(float *p, const int32_t *tgt, const int32_t *src0, const int32_t *src1, const uint8_t *kind, float *scratch,
+                 int n, cudaStream_t s);
+inline unsigned nblk(int n, int b) { return (unsigned)((n + b - 1) / b); }
 bool is_pow2(float x);
 
 // ---- indexing (clamp-to-edge sample(), fs/differentiation.py:4-9) -----------------------------

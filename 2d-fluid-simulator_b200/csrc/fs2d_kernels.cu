@@ -12,7 +12,7 @@
 namespace fs2d {
 
 static thread_local char g_err[512] = "";
-static unsigned long long g_launches = 0;  // kernels launched by this library (bench.py "gpu_launches")
+unsigned long long g_launches = 0;  // kernels launched by this library (bench.py "gpu_launches")
 void set_error(const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -74,6 +74,14 @@ __global__ void k_p_bc_scatter(float *__restrict__ p, const int32_t *__restrict_
                                const float *__restrict__ scratch, int n) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e < n) p[tgt[e]] = scratch[e];
+}
+
+void launch_p_bc(float *p, const int32_t *tgt, const int32_t *src0, const int32_t *src1, const uint8_t *kind, float *scratch,
+                 int n, cudaStream_t s) {
+    if (n <= 0) return;
+    g_launches += 2;
+    k_p_bc_gather<<<nblk(n, 256), 256, 0, s>>>(p, src0, src1, kind, scratch, n);
+    k_p_bc_scatter<<<nblk(n, 256), 256, 0, s>>>(p, tgt, scratch, n);
 }
 
 // =============================================================================================
@@ -273,156 +281,6 @@ __global__ void __launch_bounds__(TX *TY)
     reinterpret_cast<float2 *>(vn)[idx] = make_float2(c.x + dtw * fx, c.y + dtw * fy);
 }
 
-// =============================================================================================
-// pressure: predict_p (fs/pressure_updater.py:23-38)
-// =============================================================================================
-// velocity source terms of predict_p for cell (r, j): t2 = (sxx^2 + syy^2 + syx*sxy)/8, t3 = dx*(sxx+syy)/(8*dt)
-__device__ __forceinline__ void p_source(const float *vc, const fs2d_dom &d, int r, int j, float dt, float dx, float &t2,
-                                         float &t3) {
-    const float2 sx = ld2(vc, d, r + 1, j) - ld2(vc, d, r - 1, j);
-    const float2 sy = ld2(vc, d, r, j + 1) - ld2(vc, d, r, j - 1);
-    t2 = (sx.x * sx.x + sy.y * sy.y + (sy.x * sx.y)) / 8.0f;
-    t3 = dx * (sx.x + sy.y) / (8.0f * dt);
-}
-// post-BC pressure of cell (r, j) (already clamped) recomputed from the pre-BC field and pcode
-__device__ __forceinline__ float p_post(const float *pc, const uint8_t *pcode, const fs2d_dom &d, int r, int j) {
-    const size_t idx = IX(d, r, j);
-    const uint8_t c = __ldg(pcode + idx);
-    switch (c) {
-        case FS2D_PC_FLUID:
-        case FS2D_PC_W_NONE: return __ldg(pc + idx);
-        case FS2D_PC_W_IM: return ld1(pc, d, r - 1, j);
-        case FS2D_PC_W_IP: return ld1(pc, d, r + 1, j);
-        case FS2D_PC_W_JM: return ld1(pc, d, r, j - 1);
-        case FS2D_PC_W_JP: return ld1(pc, d, r, j + 1);
-        case FS2D_PC_W_IM_JP: return (ld1(pc, d, r - 1, j) + ld1(pc, d, r, j + 1)) / 2.0f;
-        case FS2D_PC_W_IP_JP: return (ld1(pc, d, r + 1, j) + ld1(pc, d, r, j + 1)) / 2.0f;
-        case FS2D_PC_W_IM_JM: return (ld1(pc, d, r - 1, j) + ld1(pc, d, r, j - 1)) / 2.0f;
-        case FS2D_PC_W_IP_JM: return (ld1(pc, d, r + 1, j) + ld1(pc, d, r, j - 1)) / 2.0f;
-        case FS2D_PC_INFLOW: return ld1(pc, d, r + 1, j);
-        default: return 0.0f;  // FS2D_PC_OUTFLOW
-    }
-}
-__device__ __forceinline__ bool pc_is_wall(uint8_t c) { return c >= FS2D_PC_W_IM && c <= FS2D_PC_W_NONE; }
-
-// scalar (any Y) Jacobi sweep: fs/pressure_updater.py:62-66
-template <bool INLINE_BC>
-__global__ void __launch_bounds__(TX *TY)
-    k_jacobi_scalar(float *__restrict__ pn, const float *__restrict__ pc, const float *__restrict__ vc,
-                    const uint8_t *__restrict__ pcode, fs2d_dom d, float dt, float dx) {
-    FS2D_CELL(d, r, j)
-    const size_t idx = IX(d, r, j);
-    if (pc_is_wall(__ldg(pcode + idx))) return;
-    float pe, pw, pn_, ps;
-    if (INLINE_BC) {
-        pe = p_post(pc, pcode, d, CR(d, r + 1), j);
-        pw = p_post(pc, pcode, d, CR(d, r - 1), j);
-        pn_ = p_post(pc, pcode, d, r, CJ(d, j + 1));
-        ps = p_post(pc, pcode, d, r, CJ(d, j - 1));
-    } else {
-        pe = ld1(pc, d, r + 1, j);
-        pw = ld1(pc, d, r - 1, j);
-        pn_ = ld1(pc, d, r, j + 1);
-        ps = ld1(pc, d, r, j - 1);
-    }
-    float t2, t3;
-    p_source(vc, d, r, j, dt, dx, t2, t3);
-    pn[idx] = 0.25f * (pe + pw + pn_ + ps) + t2 - t3;
-}
-
-// vectorised Jacobi sweep: 4 cells / thread along j (128-bit loads/stores), Y % 4 == 0.
-// block = (32 lanes x 4 cells = 128 columns) x 8 rows.
-constexpr int JV_ROWS = 8;
-template <bool INLINE_BC>
-__global__ void __launch_bounds__(32 * JV_ROWS)
-    k_jacobi_vec4(float *__restrict__ pn, const float *__restrict__ pc, const float *__restrict__ vc,
-                  const uint8_t *__restrict__ pcode, fs2d_dom d, float dt, float dx) {
-    const int j0 = 4 * (blockIdx.y * 32 + threadIdx.x);
-    const int r = d.r0 + blockIdx.x * JV_ROWS + threadIdx.y;
-    if (j0 >= d.Y || r >= d.r1) return;
-    const size_t idx = IX(d, r, j0);
-    const uchar4 cc = __ldg(reinterpret_cast<const uchar4 *>(pcode + idx));
-    const bool w0 = pc_is_wall(cc.x), w1 = pc_is_wall(cc.y), w2 = pc_is_wall(cc.z), w3 = pc_is_wall(cc.w);
-    if (w0 && w1 && w2 && w3) return;
-    const int ru = CR(d, r - 1), rd = CR(d, r + 1);
-    const int jl = CJ(d, j0 - 1), jr = CJ(d, j0 + 4);
-
-    float pw[4], pe[4], ps[4], pnn[4];  // (i-1), (i+1), (j-1), (j+1) neighbours per cell
-    bool fast = true;
-    if (INLINE_BC) {
-        const uchar4 cu = __ldg(reinterpret_cast<const uchar4 *>(pcode + IX(d, ru, j0)));
-        const uchar4 cd = __ldg(reinterpret_cast<const uchar4 *>(pcode + IX(d, rd, j0)));
-        const uint8_t cl = __ldg(pcode + IX(d, r, jl)), cr_ = __ldg(pcode + IX(d, r, jr));
-        auto plain = [](uint8_t c) { return c == FS2D_PC_FLUID || c == FS2D_PC_W_NONE; };
-        fast = plain(cu.x) && plain(cu.y) && plain(cu.z) && plain(cu.w) && plain(cd.x) && plain(cd.y) && plain(cd.z) &&
-               plain(cd.w) && plain(cc.x) && plain(cc.y) && plain(cc.z) && plain(cc.w) && plain(cl) && plain(cr_);
-    }
-    if (fast) {
-        const float4 c4 = __ldg(reinterpret_cast<const float4 *>(pc + idx));
-        const float4 u4 = __ldg(reinterpret_cast<const float4 *>(pc + IX(d, ru, j0)));
-        const float4 d4 = __ldg(reinterpret_cast<const float4 *>(pc + IX(d, rd, j0)));
-        const float pl = __ldg(pc + IX(d, r, jl)), pr = __ldg(pc + IX(d, r, jr));
-        pw[0] = u4.x; pw[1] = u4.y; pw[2] = u4.z; pw[3] = u4.w;
-        pe[0] = d4.x; pe[1] = d4.y; pe[2] = d4.z; pe[3] = d4.w;
-        ps[0] = pl; ps[1] = c4.x; ps[2] = c4.y; ps[3] = c4.z;
-        pnn[0] = c4.y; pnn[1] = c4.z; pnn[2] = c4.w; pnn[3] = pr;
-    } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            pw[k] = p_post(pc, pcode, d, ru, j0 + k);
-            pe[k] = p_post(pc, pcode, d, rd, j0 + k);
-            ps[k] = p_post(pc, pcode, d, r, CJ(d, j0 + k - 1));
-            pnn[k] = p_post(pc, pcode, d, r, CJ(d, j0 + k + 1));
-        }
-    }
-    // velocity differences: rows r+-1 (2 x float4 each), row r columns j0-1 .. j0+4
-    const float4 *vrow_d = reinterpret_cast<const float4 *>(vc + 2 * IX(d, rd, j0));
-    const float4 *vrow_u = reinterpret_cast<const float4 *>(vc + 2 * IX(d, ru, j0));
-    const float4 *vrow_c = reinterpret_cast<const float4 *>(vc + 2 * idx);
-    const float4 vd0 = __ldg(vrow_d), vd1 = __ldg(vrow_d + 1);
-    const float4 vu0 = __ldg(vrow_u), vu1 = __ldg(vrow_u + 1);
-    const float4 vc0 = __ldg(vrow_c), vc1 = __ldg(vrow_c + 1);
-    const float2 vl = __ldg(reinterpret_cast<const float2 *>(vc) + IX(d, r, jl));
-    const float2 vr = __ldg(reinterpret_cast<const float2 *>(vc) + IX(d, r, jr));
-    const float2 vdn[4] = {{vd0.x, vd0.y}, {vd0.z, vd0.w}, {vd1.x, vd1.y}, {vd1.z, vd1.w}};
-    const float2 vup[4] = {{vu0.x, vu0.y}, {vu0.z, vu0.w}, {vu1.x, vu1.y}, {vu1.z, vu1.w}};
-    const float2 vrow[6] = {vl, {vc0.x, vc0.y}, {vc0.z, vc0.w}, {vc1.x, vc1.y}, {vc1.z, vc1.w}, vr};
-    const float eight_dt = 8.0f * dt;
-    float out[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float2 sx = vdn[k] - vup[k];
-        const float2 sy = vrow[k + 2] - vrow[k];
-        const float t2 = (sx.x * sx.x + sy.y * sy.y + (sy.x * sx.y)) / 8.0f;
-        const float t3 = dx * (sx.x + sy.y) / eight_dt;
-        out[k] = 0.25f * (pe[k] + pw[k] + pnn[k] + ps[k]) + t2 - t3;
-    }
-    if (!(w0 || w1 || w2 || w3)) {
-        *reinterpret_cast<float4 *>(pn + idx) = make_float4(out[0], out[1], out[2], out[3]);
-    } else {
-        if (!w0) pn[idx] = out[0];
-        if (!w1) pn[idx + 1] = out[1];
-        if (!w2) pn[idx + 2] = out[2];
-        if (!w3) pn[idx + 3] = out[3];
-    }
-}
-
-// fs/pressure_updater.py:98-114  one colour pass of red-black SOR (pc may alias pn)
-__global__ void __launch_bounds__(TX *TY)
-    k_rbsor_pass(float *pn, const float *pc, const float *__restrict__ vc, const uint8_t *__restrict__ mask, fs2d_dom d,
-                 float dt, float dx, float omega, float one_minus_omega, int parity) {
-    FS2D_CELL(d, r, j)
-    const size_t idx = IX(d, r, j);
-    if (((d.gi0 + r + j) & 1) != parity || mask[idx] != 0) return;
-    // plain loads: pc may alias pn (even pass) -- neighbours have the other colour, never written here
-    const float pe = pc[IX(d, CR(d, r + 1), j)], pw = pc[IX(d, CR(d, r - 1), j)];
-    const float pnn = pc[IX(d, r, CJ(d, j + 1))], ps = pc[IX(d, r, CJ(d, j - 1))];
-    float t2, t3;
-    p_source(vc, d, r, j, dt, dx, t2, t3);
-    const float pred = 0.25f * (pe + pw + pnn + ps) + t2 - t3;
-    pn[idx] = one_minus_omega * pc[idx] + omega * pred;
-}
-
 // fs/solver.py:38-43  limit_field
 __global__ void __launch_bounds__(TX *TY) k_limit(float *__restrict__ v, fs2d_dom d, float limit) {
     FS2D_CELL(d, r, j)
@@ -459,7 +317,6 @@ int fs2d_device_ok(void) {
 }
 
 #define STREAM ((cudaStream_t)stream)
-static inline unsigned nblk(int n, int b) { return (unsigned)((n + b - 1) / b); }
 
 int fs2d_vel_bc(float *v, const float *bc_const, const int32_t *tgt, const int32_t *src, const uint8_t *kind,
                 float *scratch, int n, void *stream) {
@@ -476,8 +333,7 @@ int fs2d_pressure_bc(float *p, const int32_t *tgt, const int32_t *src0, const in
                      float *scratch, int n, void *stream) {
     if (n == 0) return FS2D_OK;
     FS2D_REQUIRE(p && tgt && src0 && src1 && kind && scratch && n > 0, "null table/field pointer");
-    ++g_launches; k_p_bc_gather<<<nblk(n, 256), 256, 0, STREAM>>>(p, src0, src1, kind, scratch, n);
-    ++g_launches; k_p_bc_scatter<<<nblk(n, 256), 256, 0, STREAM>>>(p, tgt, scratch, n);
+    launch_p_bc(p, tgt, src0, src1, kind, scratch, n, STREAM);
     FS2D_LAUNCH_CHECK();
     return FS2D_OK;
 }
@@ -573,76 +429,6 @@ int fs2d_vort_add(float *vn, const float *vc, const float *w, const float *wabs,
 #define VA(P2) ++g_launches, k_vort_add<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(vn, vc, w, wabs, mask, d, DivC<P2>(dx), dtw)
     DISPATCH_P2(is_pow2(dx), VA(true), VA(false));
 #undef VA
-    FS2D_LAUNCH_CHECK();
-    return FS2D_OK;
-}
-
-static int launch_jacobi(float *pn, const float *pc, const float *vc, const uint8_t *pcode, const fs2d_dom &d, float dt,
-                         float dx, int inline_bc, cudaStream_t s) {
-    const bool vec = (d.Y % 4 == 0) && ((uintptr_t)pn % 16 == 0) && ((uintptr_t)pc % 16 == 0) &&
-                     ((uintptr_t)vc % 16 == 0) && ((uintptr_t)pcode % 4 == 0);
-    if (vec) {
-        dim3 blk(32, JV_ROWS, 1), grd(nblk(d.r1 - d.r0, JV_ROWS), nblk(d.Y, 128), 1);
-        if (inline_bc) ++g_launches, k_jacobi_vec4<true><<<grd, blk, 0, s>>>(pn, pc, vc, pcode, d, dt, dx);
-        else ++g_launches, k_jacobi_vec4<false><<<grd, blk, 0, s>>>(pn, pc, vc, pcode, d, dt, dx);
-    } else {
-        if (inline_bc) ++g_launches, k_jacobi_scalar<true><<<dense_grid(d), dense_block(), 0, s>>>(pn, pc, vc, pcode, d, dt, dx);
-        else ++g_launches, k_jacobi_scalar<false><<<dense_grid(d), dense_block(), 0, s>>>(pn, pc, vc, pcode, d, dt, dx);
-    }
-    return FS2D_OK;
-}
-
-int fs2d_jacobi_sweep(float *pn, const float *pc, const float *vc, const uint8_t *pcode, fs2d_dom d, float dt, float dx,
-                      int inline_bc, void *stream) {
-    FS2D_REQUIRE(pn && pc && vc && pcode, "null field pointer");
-    FS2D_REQUIRE(pn != pc, "Jacobi sweep cannot run in place");
-    if (int e = check_dom(d)) return e;
-    if (d.r1 == d.r0) return FS2D_OK;
-    launch_jacobi(pn, pc, vc, pcode, d, dt, dx, inline_bc, STREAM);
-    FS2D_LAUNCH_CHECK();
-    return FS2D_OK;
-}
-
-int fs2d_jacobi_update(float *pa, float *pb, const float *vc, const uint8_t *pcode, fs2d_dom d, float dt, float dx,
-                       int n_sweeps, const int32_t *tgt, const int32_t *src0, const int32_t *src1,
-                       const uint8_t *kind, float *scratch, int n_bc, const int32_t *f_tgt, const int32_t *f_src0,
-                       const int32_t *f_src1, const uint8_t *f_kind, int n_feed, int *final_in_b, void *stream) {
-    FS2D_REQUIRE(pa && pb && vc && pcode && pa != pb, "null/aliased field pointer");
-    FS2D_REQUIRE(n_sweeps >= 0, "negative sweep count");
-    FS2D_REQUIRE(n_bc == 0 || (tgt && src0 && src1 && kind && scratch), "null BC table");
-    FS2D_REQUIRE(n_feed == 0 || (f_tgt && f_src0 && f_src1 && f_kind && scratch), "null feed table");
-    if (int e = check_dom(d)) return e;
-    float *cur = pa, *nxt = pb;
-    for (int s = 0; s < n_sweeps; ++s) {
-        // The stored BC values of a buffer are only observable after its last in-place BC pass
-        // (SURVEY T1): the final two sweeps run literally (in-place BC, then a plain sweep); before
-        // that the sweep recomputes post-BC neighbour values inline and leaves `cur` untouched.
-        const bool literal = s >= n_sweeps - 2;
-        if (literal && n_bc > 0) {
-            ++g_launches; k_p_bc_gather<<<nblk(n_bc, 256), 256, 0, STREAM>>>(cur, src0, src1, kind, scratch, n_bc);
-            ++g_launches; k_p_bc_scatter<<<nblk(n_bc, 256), 256, 0, STREAM>>>(cur, tgt, scratch, n_bc);
-        }
-        if (d.r1 > d.r0) launch_jacobi(nxt, cur, vc, pcode, d, dt, dx, literal ? 0 : 1, STREAM);
-        if (!literal && n_feed > 0) {
-            // wall-BC cells whose STORED value is read raw by an inflow cell two sweeps later
-            // (p(i,j) = p(i+1,j), boundary_condition.py:62-63): keep exactly those materialised.
-            ++g_launches; k_p_bc_gather<<<nblk(n_feed, 256), 256, 0, STREAM>>>(cur, f_src0, f_src1, f_kind, scratch, n_feed);
-            ++g_launches; k_p_bc_scatter<<<nblk(n_feed, 256), 256, 0, STREAM>>>(cur, f_tgt, scratch, n_feed);
-        }
-        float *t = cur; cur = nxt; nxt = t;
-    }
-    FS2D_LAUNCH_CHECK();
-    if (final_in_b) *final_in_b = (cur == pb);
-    return FS2D_OK;
-}
-
-int fs2d_rbsor_pass(float *pn, const float *pc, const float *vc, const uint8_t *mask, fs2d_dom d, float dt, float dx,
-                    float omega, float one_minus_omega, int parity, void *stream) {
-    FS2D_REQUIRE(pn && pc && vc && mask, "null field pointer");
-    FS2D_REQUIRE(parity == 0 || parity == 1, "parity must be 0 or 1");
-    if (int e = check_dom(d)) return e;
-    if (d.r1 == d.r0) return FS2D_OK;
-    ++g_launches; k_rbsor_pass<<<dense_grid(d), dense_block(), 0, STREAM>>>(pn, pc, vc, mask, d, dt, dx, omega, one_minus_omega, parity);
     FS2D_LAUNCH_CHECK();
     return FS2D_OK;
 }

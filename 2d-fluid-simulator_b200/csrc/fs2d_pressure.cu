@@ -1,0 +1,241 @@
+// fs2d_pressure.cu -- pressure relaxation kernels of libfs2d.so (sm_100a).
+//
+// predict_p (fs/pressure_updater.py:23-38):
+//     p' = 0.25*(p(i+1,j) + p(i-1,j) + p(i,j+1) + p(i,j-1)) + t2 - t3
+//     t2 = (sx.x^2 + sy.y^2 + sy.x*sx.y)/8,  t3 = dx*(sx.x + sy.y)/(8*dt),  sx = v(i+1,j)-v(i-1,j), sy = v(i,j+1)-v(i,j-1)
+// The velocity does not change between the sweeps of one pressure update (:56-60), so (t2, t3) is
+// computed ONCE per update into a float2 "source" array by k_p_source and every sweep evaluates the
+// literal expression (t1 + t2) - t3 from it: bit-identical to recomputing it from v per sweep, but the
+// sweep itself shrinks to a 5-point stencil with no divisions.
+//
+// Bytes per cell per sweep: p 4 + src 8 + pcode 1 read, p 4 write = 17 (algorithmic figure used for the
+// roofline is 12).  The fused multi-sweep kernel (k_jacobi_fused) reads the same 17 B once
+// per T sweeps.
+#include "fs2d_common.cuh"
+
+namespace fs2d {
+
+// ---------------------------------------------------------------------------------------------
+// source terms
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TX *TY)
+    k_p_source(float *__restrict__ src, const float *__restrict__ vc, fs2d_dom d, float dt, float dx) {
+    FS2D_CELL(d, r, j)
+    const float2 sx = ld2(vc, d, r + 1, j) - ld2(vc, d, r - 1, j);
+    const float2 sy = ld2(vc, d, r, j + 1) - ld2(vc, d, r, j - 1);
+    const float t2 = (sx.x * sx.x + sy.y * sy.y + (sy.x * sx.y)) / 8.0f;
+    const float t3 = dx * (sx.x + sy.y) / (8.0f * dt);
+    reinterpret_cast<float2 *>(src)[IX(d, r, j)] = make_float2(t2, t3);
+}
+
+// ---------------------------------------------------------------------------------------------
+// inline pressure BC: post-BC value of cell (r, j) recomputed from the pre-BC field and pcode
+// (fs/boundary_condition.py:41-65); r, j already clamped
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool pc_is_wall(uint8_t c) { return c >= FS2D_PC_W_IM && c <= FS2D_PC_W_NONE; }
+__device__ __forceinline__ bool pc_plain(uint8_t c) { return c == FS2D_PC_FLUID || c == FS2D_PC_W_NONE; }
+
+__device__ __noinline__ float p_post(const float *pc, const uint8_t *pcode, const fs2d_dom &d, int r, int j) {
+    const size_t idx = IX(d, r, j);
+    const uint8_t c = __ldg(pcode + idx);
+    switch (c) {
+        case FS2D_PC_FLUID:
+        case FS2D_PC_W_NONE: return __ldg(pc + idx);
+        case FS2D_PC_W_IM: return ld1(pc, d, r - 1, j);
+        case FS2D_PC_W_IP: return ld1(pc, d, r + 1, j);
+        case FS2D_PC_W_JM: return ld1(pc, d, r, j - 1);
+        case FS2D_PC_W_JP: return ld1(pc, d, r, j + 1);
+        case FS2D_PC_W_IM_JP: return (ld1(pc, d, r - 1, j) + ld1(pc, d, r, j + 1)) / 2.0f;
+        case FS2D_PC_W_IP_JP: return (ld1(pc, d, r + 1, j) + ld1(pc, d, r, j + 1)) / 2.0f;
+        case FS2D_PC_W_IM_JM: return (ld1(pc, d, r - 1, j) + ld1(pc, d, r, j - 1)) / 2.0f;
+        case FS2D_PC_W_IP_JM: return (ld1(pc, d, r + 1, j) + ld1(pc, d, r, j - 1)) / 2.0f;
+        case FS2D_PC_INFLOW: return ld1(pc, d, r + 1, j);
+        default: return 0.0f;  // FS2D_PC_OUTFLOW
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// one Jacobi sweep (fs/pressure_updater.py:62-66), any Y
+// ---------------------------------------------------------------------------------------------
+template <bool INLINE_BC>
+__global__ void __launch_bounds__(TX *TY)
+    k_jacobi_scalar(float *__restrict__ pn, const float *__restrict__ pc, const float *__restrict__ src,
+                    const uint8_t *__restrict__ pcode, fs2d_dom d) {
+    FS2D_CELL(d, r, j)
+    const size_t idx = IX(d, r, j);
+    if (pc_is_wall(__ldg(pcode + idx))) return;
+    float pe, pw, pn_, ps;
+    if (INLINE_BC) {
+        pe = p_post(pc, pcode, d, CR(d, r + 1), j);
+        pw = p_post(pc, pcode, d, CR(d, r - 1), j);
+        pn_ = p_post(pc, pcode, d, r, CJ(d, j + 1));
+        ps = p_post(pc, pcode, d, r, CJ(d, j - 1));
+    } else {
+        pe = ld1(pc, d, r + 1, j);
+        pw = ld1(pc, d, r - 1, j);
+        pn_ = ld1(pc, d, r, j + 1);
+        ps = ld1(pc, d, r, j - 1);
+    }
+    const float2 s = __ldg(reinterpret_cast<const float2 *>(src) + idx);
+    pn[idx] = 0.25f * (pe + pw + pn_ + ps) + s.x - s.y;
+}
+
+// vectorised sweep: 4 cells / thread along j (128-bit loads/stores), Y % 4 == 0;
+// block = 32 lanes x 4 cells = 128 columns, JV_ROWS rows
+constexpr int JV_ROWS = 8;
+template <bool INLINE_BC>
+__global__ void __launch_bounds__(32 * JV_ROWS, 6)
+    k_jacobi_vec4(float *__restrict__ pn, const float *__restrict__ pc, const float *__restrict__ src,
+                  const uint8_t *__restrict__ pcode, fs2d_dom d) {
+    const int j0 = 4 * (blockIdx.y * 32 + threadIdx.x);
+    const int r = d.r0 + blockIdx.x * JV_ROWS + threadIdx.y;
+    if (j0 >= d.Y || r >= d.r1) return;
+    const size_t idx = IX(d, r, j0);
+    const uchar4 cc = __ldg(reinterpret_cast<const uchar4 *>(pcode + idx));
+    const bool w0 = pc_is_wall(cc.x), w1 = pc_is_wall(cc.y), w2 = pc_is_wall(cc.z), w3 = pc_is_wall(cc.w);
+    if (w0 && w1 && w2 && w3) return;  // wall interiors: nothing to read or write
+    const int ru = CR(d, r - 1), rd = CR(d, r + 1);
+    const int jl = CJ(d, j0 - 1), jr = CJ(d, j0 + 4);
+    const size_t iu = IX(d, ru, j0), id = IX(d, rd, j0), il = IX(d, r, jl), ir = IX(d, r, jr);
+    // issue every load before the first use
+    const float4 c4 = __ldg(reinterpret_cast<const float4 *>(pc + idx));
+    const float4 u4 = __ldg(reinterpret_cast<const float4 *>(pc + iu));
+    const float4 d4 = __ldg(reinterpret_cast<const float4 *>(pc + id));
+    const float pl = __ldg(pc + il), pr = __ldg(pc + ir);
+    const float4 s01 = __ldg(reinterpret_cast<const float4 *>(src + 2 * idx));
+    const float4 s23 = __ldg(reinterpret_cast<const float4 *>(src + 2 * idx) + 1);
+    float pw[4] = {u4.x, u4.y, u4.z, u4.w};    // (i-1, j)
+    float pe[4] = {d4.x, d4.y, d4.z, d4.w};    // (i+1, j)
+    float ps[4] = {pl, c4.x, c4.y, c4.z};      // (i, j-1)
+    float pq[4] = {c4.y, c4.z, c4.w, pr};      // (i, j+1)
+    if (INLINE_BC) {
+        const uchar4 cu = __ldg(reinterpret_cast<const uchar4 *>(pcode + iu));
+        const uchar4 cd = __ldg(reinterpret_cast<const uchar4 *>(pcode + id));
+        const uint8_t cl = __ldg(pcode + il), cr_ = __ldg(pcode + ir);
+        const uint8_t ku[4] = {cu.x, cu.y, cu.z, cu.w}, kd[4] = {cd.x, cd.y, cd.z, cd.w};
+        const uint8_t kc[6] = {cl, cc.x, cc.y, cc.z, cc.w, cr_};
+        bool all_plain = pc_plain(cl) && pc_plain(cr_);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) all_plain = all_plain && pc_plain(ku[k]) && pc_plain(kd[k]) && pc_plain(kc[k + 1]);
+        if (!all_plain) {  // rare: some neighbour is a BC cell -> recompute just those values
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!pc_plain(ku[k])) pw[k] = p_post(pc, pcode, d, ru, j0 + k);
+                if (!pc_plain(kd[k])) pe[k] = p_post(pc, pcode, d, rd, j0 + k);
+                if (!pc_plain(kc[k])) ps[k] = p_post(pc, pcode, d, r, CJ(d, j0 + k - 1));
+                if (!pc_plain(kc[k + 2])) pq[k] = p_post(pc, pcode, d, r, CJ(d, j0 + k + 1));
+            }
+        }
+    }
+    const float t2[4] = {s01.x, s01.z, s23.x, s23.z}, t3[4] = {s01.y, s01.w, s23.y, s23.w};
+    float out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[k] = 0.25f * (pe[k] + pw[k] + pq[k] + ps[k]) + t2[k] - t3[k];
+    if (!(w0 || w1 || w2 || w3)) {
+        *reinterpret_cast<float4 *>(pn + idx) = make_float4(out[0], out[1], out[2], out[3]);
+    } else {
+        if (!w0) pn[idx] = out[0];
+        if (!w1) pn[idx + 1] = out[1];
+        if (!w2) pn[idx + 2] = out[2];
+        if (!w3) pn[idx + 3] = out[3];
+    }
+}
+
+// fs/pressure_updater.py:98-114  one colour pass of red-black SOR (pc may alias pn)
+__global__ void __launch_bounds__(TX *TY)
+    k_rbsor_pass(float *pn, const float *pc, const float *__restrict__ src, const uint8_t *__restrict__ mask, fs2d_dom d,
+                 float omega, float one_minus_omega, int parity) {
+    FS2D_CELL(d, r, j)
+    const size_t idx = IX(d, r, j);
+    if (((d.gi0 + r + j) & 1) != parity || mask[idx] != 0) return;
+    // plain loads: pc may alias pn (even pass) -- neighbours have the other colour, never written here
+    const float pe = pc[IX(d, CR(d, r + 1), j)], pw = pc[IX(d, CR(d, r - 1), j)];
+    const float pq = pc[IX(d, r, CJ(d, j + 1))], ps = pc[IX(d, r, CJ(d, j - 1))];
+    const float2 s = __ldg(reinterpret_cast<const float2 *>(src) + idx);
+    const float pred = 0.25f * (pe + pw + pq + ps) + s.x - s.y;
+    pn[idx] = one_minus_omega * pc[idx] + omega * pred;
+}
+
+static void launch_jacobi(float *pn, const float *pc, const float *src, const uint8_t *pcode, const fs2d_dom &d,
+                          int inline_bc, cudaStream_t s) {
+    const bool vec = (d.Y % 4 == 0) && ((uintptr_t)pn % 16 == 0) && ((uintptr_t)pc % 16 == 0) &&
+                     ((uintptr_t)src % 16 == 0) && ((uintptr_t)pcode % 4 == 0);
+    ++g_launches;
+    if (vec) {
+        dim3 blk(32, JV_ROWS, 1), grd(nblk(d.r1 - d.r0, JV_ROWS), nblk(d.Y, 128), 1);
+        if (inline_bc) k_jacobi_vec4<true><<<grd, blk, 0, s>>>(pn, pc, src, pcode, d);
+        else k_jacobi_vec4<false><<<grd, blk, 0, s>>>(pn, pc, src, pcode, d);
+    } else {
+        if (inline_bc) k_jacobi_scalar<true><<<dense_grid(d), dense_block(), 0, s>>>(pn, pc, src, pcode, d);
+        else k_jacobi_scalar<false><<<dense_grid(d), dense_block(), 0, s>>>(pn, pc, src, pcode, d);
+    }
+}
+
+}  // namespace fs2d
+
+using namespace fs2d;
+#define STREAM ((cudaStream_t)stream)
+
+extern "C" {
+
+int fs2d_pressure_source(float *src, const float *vc, fs2d_dom d, float dt, float dx, void *stream) {
+    FS2D_REQUIRE(src && vc, "null field pointer");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+    ++g_launches;
+    k_p_source<<<dense_grid(d), dense_block(), 0, STREAM>>>(src, vc, d, dt, dx);
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+int fs2d_jacobi_sweep(float *pn, const float *pc, const float *src, const uint8_t *pcode, fs2d_dom d, int inline_bc,
+                      void *stream) {
+    FS2D_REQUIRE(pn && pc && src && pcode, "null field pointer");
+    FS2D_REQUIRE(pn != pc, "Jacobi sweep cannot run in place");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+    launch_jacobi(pn, pc, src, pcode, d, inline_bc, STREAM);
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+int fs2d_jacobi_update(float *pa, float *pb, const float *src, const uint8_t *pcode, fs2d_dom d, int n_sweeps,
+                       const int32_t *tgt, const int32_t *src0, const int32_t *src1, const uint8_t *kind, float *scratch,
+                       int n_bc, const int32_t *f_tgt, const int32_t *f_src0, const int32_t *f_src1,
+                       const uint8_t *f_kind, int n_feed, int *final_in_b, void *stream) {
+    FS2D_REQUIRE(pa && pb && src && pcode && pa != pb, "null/aliased field pointer");
+    FS2D_REQUIRE(n_sweeps >= 0, "negative sweep count");
+    FS2D_REQUIRE(n_bc == 0 || (tgt && src0 && src1 && kind && scratch), "null BC table");
+    FS2D_REQUIRE(n_feed == 0 || (f_tgt && f_src0 && f_src1 && f_kind && scratch), "null feed table");
+    if (int e = check_dom(d)) return e;
+    float *cur = pa, *nxt = pb;
+    for (int s = 0; s < n_sweeps; ++s) {
+        // The stored BC values of a buffer are only observable after its last in-place BC pass
+        // (SURVEY T1): the final two sweeps run literally (in-place BC, then a plain sweep); before
+        // that the sweep recomputes post-BC neighbour values inline and leaves `cur` untouched.
+        const bool literal = s >= n_sweeps - 2;
+        if (literal) launch_p_bc(cur, tgt, src0, src1, kind, scratch, n_bc, STREAM);
+        if (d.r1 > d.r0) launch_jacobi(nxt, cur, src, pcode, d, literal ? 0 : 1, STREAM);
+        // wall-BC cells whose STORED value is read raw by an inflow cell two sweeps later
+        // (p(i,j) = p(i+1,j), boundary_condition.py:62-63): keep exactly those materialised.
+        if (!literal) launch_p_bc(cur, f_tgt, f_src0, f_src1, f_kind, scratch, n_feed, STREAM);
+        float *t = cur; cur = nxt; nxt = t;
+    }
+    FS2D_LAUNCH_CHECK();
+    if (final_in_b) *final_in_b = (cur == pb);
+    return FS2D_OK;
+}
+
+int fs2d_rbsor_pass(float *pn, const float *pc, const float *src, const uint8_t *mask, fs2d_dom d, float omega,
+                    float one_minus_omega, int parity, void *stream) {
+    FS2D_REQUIRE(pn && pc && src && mask, "null field pointer");
+    FS2D_REQUIRE(parity == 0 || parity == 1, "parity must be 0 or 1");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+    ++g_launches;
+    k_rbsor_pass<<<dense_grid(d), dense_block(), 0, STREAM>>>(pn, pc, src, mask, d, omega, one_minus_omega, parity);
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+}  // extern "C"

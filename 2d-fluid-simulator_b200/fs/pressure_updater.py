@@ -22,10 +22,21 @@ class PressureUpdater(metaclass=ABCMeta):
         self._bc = boundary_condition
         self.dt = dt
         self.dx = dx
+        self._src: Field | None = None
 
     @abstractmethod
     def update(self, p: DoubleBuffer, v_current: Field) -> None:
         pass
+
+    def _source(self, v_current: Field, dom=None) -> Field:
+        """(t2, t3) velocity terms of predict_p (:23-38), one float2 per cell; v is constant during an
+        update (:56-60) so this runs once per update instead of once per sweep."""
+        bc = self._bc
+        if self._src is None:
+            self._src = Field(bc.get_resolution(), 2, bc.device, bc.halo)
+        _lib.call("fs2d_pressure_source", self._src.ptr(), v_current.ptr(), dom or bc.dom, self.dt, self.dx,
+                  _lib.stream())
+        return self._src
 
 
 class JacobiPressureUpdater(PressureUpdater):
@@ -34,16 +45,15 @@ class JacobiPressureUpdater(PressureUpdater):
     def __init__(self, boundary_condition: BoundaryCondition, dt: float, dx: float, n_iter: int) -> None:
         super().__init__(boundary_condition, dt, dx)
         self._n_iter = int(n_iter)
-        self._stale_ok: bool | None = None
 
-    def _sweep(self, p_next: Field, p_current: Field, v_current: Field, inline_bc: bool) -> None:
+    def _sweep(self, p_next: Field, p_current: Field, src: Field, inline_bc: bool, dom=None) -> None:
         bc = self._bc
-        _lib.call("fs2d_jacobi_sweep", p_next.ptr(), p_current.ptr(), v_current.ptr(), _lib.ptr(bc._pcode), bc.dom,
-                  self.dt, self.dx, int(inline_bc), _lib.stream())
+        _lib.call("fs2d_jacobi_sweep", p_next.ptr(), p_current.ptr(), src.ptr(), _lib.ptr(bc._pcode), dom or bc.dom,
+                  int(inline_bc), _lib.stream())
 
     # the reference's kernel of the same name (:62-66): one sweep, BC already applied by the caller
     def _update(self, p_next: Field, p_current: Field, v_current: Field) -> None:
-        self._sweep(p_next, p_current, v_current, inline_bc=False)
+        self._sweep(p_next, p_current, self._source(v_current), inline_bc=False)
 
     def update(self, p: DoubleBuffer, v_current: Field) -> None:
         bc = self._bc
@@ -52,13 +62,14 @@ class JacobiPressureUpdater(PressureUpdater):
 
             jacobi_update_distributed(self, p, v_current)
             return
+        src = self._source(v_current)
         t = bc._p_table
         f = t["feed"]
         final_in_b = ctypes.c_int(0)
-        _lib.call("fs2d_jacobi_update", p.current.ptr(), p.next.ptr(), v_current.ptr(), _lib.ptr(bc._pcode), bc.dom,
-                  self.dt, self.dx, self._n_iter, _lib.ptr(t["tgt"]), _lib.ptr(t["src0"]), _lib.ptr(t["src1"]),
-                  _lib.ptr(t["kind"]), _lib.ptr(bc._scratch), t["n"], _lib.ptr(f["tgt"]), _lib.ptr(f["src0"]),
-                  _lib.ptr(f["src1"]), _lib.ptr(f["kind"]), f["n"], ctypes.byref(final_in_b), _lib.stream())
+        _lib.call("fs2d_jacobi_update", p.current.ptr(), p.next.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom,
+                  self._n_iter, _lib.ptr(t["tgt"]), _lib.ptr(t["src0"]), _lib.ptr(t["src1"]), _lib.ptr(t["kind"]),
+                  _lib.ptr(bc._scratch), t["n"], _lib.ptr(f["tgt"]), _lib.ptr(f["src0"]), _lib.ptr(f["src1"]),
+                  _lib.ptr(f["kind"]), f["n"], ctypes.byref(final_in_b), _lib.stream())
         if final_in_b.value:
             p.swap()  # n_iter odd: same net effect as the reference's n_iter swaps
 
@@ -72,15 +83,16 @@ class RedBlackSorPressureUpdater(PressureUpdater):
         self._n_iter = int(n_iter)
         self._relaxation_factor = relaxation_factor
 
-    def _pass(self, pn: Field, pc: Field, vc: Field, parity: int) -> None:
+    def _pass(self, pn: Field, pc: Field, src: Field, parity: int, dom=None) -> None:
         bc = self._bc
         w = self._relaxation_factor
-        _lib.call("fs2d_rbsor_pass", pn.ptr(), pc.ptr(), vc.ptr(), _lib.ptr(bc._bc_mask), bc.dom, self.dt, self.dx,
-                  w, 1.0 - w, parity, _lib.stream())
+        _lib.call("fs2d_rbsor_pass", pn.ptr(), pc.ptr(), src.ptr(), _lib.ptr(bc._bc_mask), dom or bc.dom, w, 1.0 - w,
+                  parity, _lib.stream())
 
-    def _update(self, p_next: Field, p_current: Field, v_current: Field) -> None:
-        self._pass(p_next, p_current, v_current, 1)   # _update_pressures_odd  (:98-102)
-        self._pass(p_next, p_next, v_current, 0)      # _update_pressures_even (:104-108), pc = pn
+    def _update(self, p_next: Field, p_current: Field, v_current: Field, src: Field | None = None) -> None:
+        src = src if src is not None else self._source(v_current)
+        self._pass(p_next, p_current, src, 1)   # _update_pressures_odd  (:98-102)
+        self._pass(p_next, p_next, src, 0)      # _update_pressures_even (:104-108), pc = pn
 
     def update(self, p: DoubleBuffer, v_current: Field) -> None:
         if self._bc.partition.world > 1:
@@ -88,7 +100,8 @@ class RedBlackSorPressureUpdater(PressureUpdater):
 
             rbsor_update_distributed(self, p, v_current)
             return
+        src = self._source(v_current)
         for _ in range(self._n_iter):
             self._bc.set_pressure_boundary_condition(p.current)
-            self._update(p.next, p.current, v_current)
+            self._update(p.next, p.current, v_current, src)
             p.swap()

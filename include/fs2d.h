@@ -26,8 +26,7 @@
  *
  * Floating point: kernels are compiled with -fmad=false and use IEEE div/sqrt, literal
  * left-to-right operation order of the reference source, fminf/fmaxf NaN rule, so
- * results are bit-identical to the CPU oracle (oracle/fs2d_oracle.c) -- except
- * fs2d_jacobi_fused's rhs pre-pass variant where stated.
+ * results are bit-identical to the CPU oracle (oracle/fs2d_oracle.c).
  */
 #ifndef FS2D_H
 #define FS2D_H
@@ -106,26 +105,31 @@ int fs2d_vort_calc(float *w, float *wabs, const float *vc, const uint8_t *mask, 
 /* VorticityConfinement._add_vorticity, fs/vorticity_confinement.py:34-55; dtw = (float)(dt*weight) */
 int fs2d_vort_add(float *vn, const float *vc, const float *w, const float *wabs, const uint8_t *mask, fs2d_dom d,
                   float dx, float dtw, void *stream);
-/* JacobiPressureUpdater._update, fs/pressure_updater.py:62-66 + predict_p :23-38 (not-wall cells).
- * inline_bc != 0: neighbour pressures are the post-BC values of `pc` recomputed from `pcode`
- * (pc itself is not modified) == set_pressure_boundary_condition(pc) followed by _update;
- * inline_bc == 0: pc is read as is (caller already applied the BC).  pcode: FS2D_PC_* per cell. */
-int fs2d_jacobi_sweep(float *pn, const float *pc, const float *vc, const uint8_t *pcode, fs2d_dom d, float dt, float dx,
-                      int inline_bc, void *stream);
+/* Velocity source terms of predict_p (fs/pressure_updater.py:23-38) for every cell of rows [r0, r1):
+ * src[i][j] = (t2, t3), t2 = (sx.x^2 + sy.y^2 + sy.x*sx.y)/8, t3 = dx*(sx.x + sy.y)/(8*dt) with
+ * sx = v(i+1,j) - v(i-1,j), sy = v(i,j+1) - v(i,j-1).  v is constant during one pressure update, so the
+ * host computes this once per update; sweeps then evaluate the literal (t1 + t2) - t3. */
+int fs2d_pressure_source(float *src, const float *vc, fs2d_dom d, float dt, float dx, void *stream);
+/* JacobiPressureUpdater._update, fs/pressure_updater.py:62-66 (not-wall cells), src from
+ * fs2d_pressure_source.  inline_bc != 0: neighbour pressures are the post-BC values of `pc`
+ * recomputed from `pcode` (pc itself is not modified) == set_pressure_boundary_condition(pc)
+ * followed by _update; inline_bc == 0: pc is read as is (caller already applied the BC). */
+int fs2d_jacobi_sweep(float *pn, const float *pc, const float *src, const uint8_t *pcode, fs2d_dom d, int inline_bc,
+                      void *stream);
 /* n_sweeps of {pressure BC, Jacobi} with ping-pong between pa (current) and pb (next); equal to
  * n_sweeps reference iterations (fs/pressure_updater.py:56-60) INCLUDING the final contents of the
  * BC cells of both buffers.  (tgt, src0, src1, kind, n_bc): table as in fs2d_pressure_bc.
  * (f_*, n_feed): the sub-table of wall-BC cells whose stored value an inflow cell reads raw
  * (usually empty).  scratch: >= max(n_bc, n_feed) floats.  *final_in_b = 1 if the current buffer
  * after the call is pb (n_sweeps odd). */
-int fs2d_jacobi_update(float *pa, float *pb, const float *vc, const uint8_t *pcode, fs2d_dom d, float dt, float dx,
-                       int n_sweeps, const int32_t *tgt, const int32_t *src0, const int32_t *src1,
-                       const uint8_t *kind, float *scratch, int n_bc, const int32_t *f_tgt, const int32_t *f_src0,
-                       const int32_t *f_src1, const uint8_t *f_kind, int n_feed, int *final_in_b, void *stream);
+int fs2d_jacobi_update(float *pa, float *pb, const float *src, const uint8_t *pcode, fs2d_dom d, int n_sweeps,
+                       const int32_t *tgt, const int32_t *src0, const int32_t *src1, const uint8_t *kind, float *scratch,
+                       int n_bc, const int32_t *f_tgt, const int32_t *f_src0, const int32_t *f_src1,
+                       const uint8_t *f_kind, int n_feed, int *final_in_b, void *stream);
 /* One colour pass of RedBlackSorPressureUpdater, fs/pressure_updater.py:98-114 (fluid cells of
- * colour `parity`, (i_global + j) % 2); pc may alias pn (even pass, :96) */
-int fs2d_rbsor_pass(float *pn, const float *pc, const float *vc, const uint8_t *mask, fs2d_dom d, float dt, float dx,
-                    float omega, float one_minus_omega, int parity, void *stream);
+ * colour `parity`, (i_global + j) % 2); pc may alias pn (even pass, :96); src as above */
+int fs2d_rbsor_pass(float *pn, const float *pc, const float *src, const uint8_t *mask, fs2d_dom d, float omega,
+                    float one_minus_omega, int parity, void *stream);
 /* limit_field, fs/solver.py:38-43 (all cells, in place) */
 int fs2d_limit(float *v, fs2d_dom d, float limit, void *stream);
 

@@ -200,11 +200,11 @@ def test_jacobi_row_range_invariance_and_literal_equivalence(env):
     jac = JacobiPressureUpdater(bc, dt, dx, 9)
     full, halves = fld(p0 * 3), fld(p0 * 3)
     pc = fld(p0)
-    jac._sweep(full, pc, v, inline_bc=True)
+    src = jac._source(v)
+    jac._sweep(full, pc, src, inline_bc=True)
     X = mask.shape[0]
     for r0, r1 in ((0, X // 3), (X // 3, X)):
-        _lib.call("fs2d_jacobi_sweep", halves.ptr(), pc.ptr(), v.ptr(), _lib.ptr(bc._pcode), bc.dom.replace(r0=r0, r1=r1),
-                  dt, dx, 1, _lib.stream())
+        jac._sweep(halves, pc, src, inline_bc=True, dom=bc.dom.replace(r0=r0, r1=r1))
     assert_bitexact("row ranges", halves.to_numpy(), full.to_numpy())
     lit_in = fld(p0); bc.set_pressure_boundary_condition(lit_in)
     lit = fld(p0 * 3); jac._update(lit, lit_in, v)
@@ -285,13 +285,13 @@ def test_properties_at_res_8192(env):
     jac = JacobiPressureUpdater(bc, dt, dx, 1)
     pc, v = rnd(1), rnd(2)
     whole, strips = Field((X, Y), 1), Field((X, Y), 1)
-    jac._sweep(whole, pc, v, inline_bc=True)
+    src = jac._source(v)
+    jac._sweep(whole, pc, src, inline_bc=True)
     for k in range(8):
-        _lib.call("fs2d_jacobi_sweep", strips.ptr(), pc.ptr(), v.ptr(), _lib.ptr(bc._pcode),
-                  bc.dom.replace(r0=k * X // 8, r1=(k + 1) * X // 8), dt, dx, 1, _lib.stream())
+        jac._sweep(strips, pc, src, inline_bc=True, dom=bc.dom.replace(r0=k * X // 8, r1=(k + 1) * X // 8))
     assert torch.equal(whole.tensor, strips.tensor)
     pc.tensor.fill_(0.75); v.tensor.zero_()
-    jac._sweep(whole, pc, v, inline_bc=True)
+    jac._sweep(whole, pc, jac._source(v), inline_bc=True)
     interior = torch.zeros_like(bc._bc_mask, dtype=torch.bool)
     interior[4:X - 4] = True
     ok = (bc._bc_mask == 0) & interior
