@@ -37,7 +37,7 @@ __device__ __forceinline__ bool pc_plain(uint8_t c) { return c == FS2D_PC_FLUID 
 
 __device__ __noinline__ float p_post(const float *pc, const uint8_t *pcode, const fs2d_dom &d, int r, int j) {
     const size_t idx = IX(d, r, j);
-    const uint8_t c = __ldg(pcode + idx);
+    const uint8_t c = __ldg(pcode + idx) & 15;  // low nibble = FS2D_PC_* code
     switch (c) {
         case FS2D_PC_FLUID:
         case FS2D_PC_W_NONE: return __ldg(pc + idx);
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(TX *TY)
                     const uint8_t *__restrict__ pcode, fs2d_dom d) {
     FS2D_CELL(d, r, j)
     const size_t idx = IX(d, r, j);
-    if (pc_is_wall(__ldg(pcode + idx))) return;
+    if (pc_is_wall(__ldg(pcode + idx) & 15)) return;
     float pe, pw, pn_, ps;
     if (INLINE_BC) {
         pe = p_post(pc, pcode, d, CR(d, r + 1), j);
@@ -80,64 +80,70 @@ __global__ void __launch_bounds__(TX *TY)
     pn[idx] = 0.25f * (pe + pw + pn_ + ps) + s.x - s.y;
 }
 
-// vectorised sweep: 4 cells / thread along j (128-bit loads/stores), Y % 4 == 0;
-// block = 32 lanes x 4 cells = 128 columns, JV_ROWS rows
-constexpr int JV_ROWS = 8;
+// vectorised marching sweep: each warp owns a 128-column x JM_ROWS-row chunk, 4 cells / lane along j
+// (128-bit loads/stores), and walks down the rows keeping the (i-1, i, i+1) pressure rows in registers,
+// so every p row is fetched once per chunk (+2 halo rows); j-neighbours come from warp shuffles.
+// pcode byte = FS2D_PC_* code | (neighbour-is-a-BC-cell bits << 4), so no neighbour codes are loaded.
+// Requires Y % 4 == 0.
+constexpr int JM_ROWS = 16;   // rows marched by one warp
+constexpr int JM_WARPS = 8;   // warps per block (each on its own row chunk)
 template <bool INLINE_BC>
-__global__ void __launch_bounds__(32 * JV_ROWS, 6)
-    k_jacobi_vec4(float *__restrict__ pn, const float *__restrict__ pc, const float *__restrict__ src,
-                  const uint8_t *__restrict__ pcode, fs2d_dom d) {
-    const int j0 = 4 * (blockIdx.y * 32 + threadIdx.x);
-    const int r = d.r0 + blockIdx.x * JV_ROWS + threadIdx.y;
-    if (j0 >= d.Y || r >= d.r1) return;
-    const size_t idx = IX(d, r, j0);
-    const uchar4 cc = __ldg(reinterpret_cast<const uchar4 *>(pcode + idx));
-    const bool w0 = pc_is_wall(cc.x), w1 = pc_is_wall(cc.y), w2 = pc_is_wall(cc.z), w3 = pc_is_wall(cc.w);
-    if (w0 && w1 && w2 && w3) return;  // wall interiors: nothing to read or write
-    const int ru = CR(d, r - 1), rd = CR(d, r + 1);
-    const int jl = CJ(d, j0 - 1), jr = CJ(d, j0 + 4);
-    const size_t iu = IX(d, ru, j0), id = IX(d, rd, j0), il = IX(d, r, jl), ir = IX(d, r, jr);
-    // issue every load before the first use
-    const float4 c4 = __ldg(reinterpret_cast<const float4 *>(pc + idx));
-    const float4 u4 = __ldg(reinterpret_cast<const float4 *>(pc + iu));
-    const float4 d4 = __ldg(reinterpret_cast<const float4 *>(pc + id));
-    const float pl = __ldg(pc + il), pr = __ldg(pc + ir);
-    const float4 s01 = __ldg(reinterpret_cast<const float4 *>(src + 2 * idx));
-    const float4 s23 = __ldg(reinterpret_cast<const float4 *>(src + 2 * idx) + 1);
-    float pw[4] = {u4.x, u4.y, u4.z, u4.w};    // (i-1, j)
-    float pe[4] = {d4.x, d4.y, d4.z, d4.w};    // (i+1, j)
-    float ps[4] = {pl, c4.x, c4.y, c4.z};      // (i, j-1)
-    float pq[4] = {c4.y, c4.z, c4.w, pr};      // (i, j+1)
-    if (INLINE_BC) {
-        const uchar4 cu = __ldg(reinterpret_cast<const uchar4 *>(pcode + iu));
-        const uchar4 cd = __ldg(reinterpret_cast<const uchar4 *>(pcode + id));
-        const uint8_t cl = __ldg(pcode + il), cr_ = __ldg(pcode + ir);
-        const uint8_t ku[4] = {cu.x, cu.y, cu.z, cu.w}, kd[4] = {cd.x, cd.y, cd.z, cd.w};
-        const uint8_t kc[6] = {cl, cc.x, cc.y, cc.z, cc.w, cr_};
-        bool all_plain = pc_plain(cl) && pc_plain(cr_);
+__global__ void __launch_bounds__(32 * JM_WARPS, 6)
+    k_jacobi_march(float *__restrict__ pn, const float *__restrict__ pc, const float *__restrict__ src,
+                   const uint8_t *__restrict__ pcode, fs2d_dom d) {
+    const int lane = threadIdx.x;
+    const int j0 = 4 * (blockIdx.y * 32 + lane);
+    const bool active = j0 < d.Y;
+    const int jc = active ? j0 : 0;  // inactive lanes read column 0 (values unused) and never store
+    const int r_begin = d.r0 + (blockIdx.x * JM_WARPS + threadIdx.y) * JM_ROWS;
+    const int r_end = min(r_begin + JM_ROWS, d.r1);
+    if (r_begin >= r_end) return;  // warp-uniform
+    const int jl = CJ(d, jc - 1), jr = CJ(d, jc + 4);
+    float4 up = __ldg(reinterpret_cast<const float4 *>(pc + IX(d, CR(d, r_begin - 1), jc)));
+    float4 cen = __ldg(reinterpret_cast<const float4 *>(pc + IX(d, r_begin, jc)));
+    for (int r = r_begin; r < r_end; ++r) {
+        const size_t idx = IX(d, r, jc);
+        const float4 dn = __ldg(reinterpret_cast<const float4 *>(pc + IX(d, CR(d, r + 1), jc)));
+        const uchar4 cc = __ldg(reinterpret_cast<const uchar4 *>(pcode + idx));
+        // j-neighbours: lane l-1's .w / lane l+1's .x; the warp's edge lanes fetch them from memory
+        float pl = __shfl_up_sync(0xffffffffu, cen.w, 1), pr = __shfl_down_sync(0xffffffffu, cen.x, 1);
+        if (lane == 0) pl = __ldg(pc + IX(d, r, jl));
+        if (lane == 31 || jc + 4 >= d.Y) pr = __ldg(pc + IX(d, r, jr));
+        const uint8_t k0 = cc.x, k1 = cc.y, k2 = cc.z, k3 = cc.w;
+        const bool w0 = pc_is_wall(k0 & 15), w1 = pc_is_wall(k1 & 15), w2 = pc_is_wall(k2 & 15), w3 = pc_is_wall(k3 & 15);
+        if (active && !(w0 && w1 && w2 && w3)) {
+            const float4 s01 = __ldg(reinterpret_cast<const float4 *>(src + 2 * idx));
+            const float4 s23 = __ldg(reinterpret_cast<const float4 *>(src + 2 * idx) + 1);
+            float pw[4] = {up.x, up.y, up.z, up.w};        // (i-1, j)
+            float pe[4] = {dn.x, dn.y, dn.z, dn.w};        // (i+1, j)
+            float ps[4] = {pl, cen.x, cen.y, cen.z};       // (i, j-1)
+            float pq[4] = {cen.y, cen.z, cen.w, pr};       // (i, j+1)
+            if (INLINE_BC && ((k0 | k1 | k2 | k3) & 0xF0)) {  // rare: some neighbour is a BC cell
+                const uint8_t kk[4] = {k0, k1, k2, k3};
+                const int ru = CR(d, r - 1), rd = CR(d, r + 1);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) all_plain = all_plain && pc_plain(ku[k]) && pc_plain(kd[k]) && pc_plain(kc[k + 1]);
-        if (!all_plain) {  // rare: some neighbour is a BC cell -> recompute just those values
+                for (int k = 0; k < 4; ++k) {
+                    if (kk[k] & 0x10) pw[k] = p_post(pc, pcode, d, ru, jc + k);
+                    if (kk[k] & 0x20) pe[k] = p_post(pc, pcode, d, rd, jc + k);
+                    if (kk[k] & 0x40) ps[k] = p_post(pc, pcode, d, r, CJ(d, jc + k - 1));
+                    if (kk[k] & 0x80) pq[k] = p_post(pc, pcode, d, r, CJ(d, jc + k + 1));
+                }
+            }
+            const float t2[4] = {s01.x, s01.z, s23.x, s23.z}, t3[4] = {s01.y, s01.w, s23.y, s23.w};
+            float out[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (!pc_plain(ku[k])) pw[k] = p_post(pc, pcode, d, ru, j0 + k);
-                if (!pc_plain(kd[k])) pe[k] = p_post(pc, pcode, d, rd, j0 + k);
-                if (!pc_plain(kc[k])) ps[k] = p_post(pc, pcode, d, r, CJ(d, j0 + k - 1));
-                if (!pc_plain(kc[k + 2])) pq[k] = p_post(pc, pcode, d, r, CJ(d, j0 + k + 1));
+            for (int k = 0; k < 4; ++k) out[k] = 0.25f * (pe[k] + pw[k] + pq[k] + ps[k]) + t2[k] - t3[k];
+            if (!(w0 || w1 || w2 || w3)) {
+                *reinterpret_cast<float4 *>(pn + idx) = make_float4(out[0], out[1], out[2], out[3]);
+            } else {
+                if (!w0) pn[idx] = out[0];
+                if (!w1) pn[idx + 1] = out[1];
+                if (!w2) pn[idx + 2] = out[2];
+                if (!w3) pn[idx + 3] = out[3];
             }
         }
-    }
-    const float t2[4] = {s01.x, s01.z, s23.x, s23.z}, t3[4] = {s01.y, s01.w, s23.y, s23.w};
-    float out[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) out[k] = 0.25f * (pe[k] + pw[k] + pq[k] + ps[k]) + t2[k] - t3[k];
-    if (!(w0 || w1 || w2 || w3)) {
-        *reinterpret_cast<float4 *>(pn + idx) = make_float4(out[0], out[1], out[2], out[3]);
-    } else {
-        if (!w0) pn[idx] = out[0];
-        if (!w1) pn[idx + 1] = out[1];
-        if (!w2) pn[idx + 2] = out[2];
-        if (!w3) pn[idx + 3] = out[3];
+        up = cen;
+        cen = dn;
     }
 }
 
@@ -162,9 +168,9 @@ static void launch_jacobi(float *pn, const float *pc, const float *src, const ui
                      ((uintptr_t)src % 16 == 0) && ((uintptr_t)pcode % 4 == 0);
     ++g_launches;
     if (vec) {
-        dim3 blk(32, JV_ROWS, 1), grd(nblk(d.r1 - d.r0, JV_ROWS), nblk(d.Y, 128), 1);
-        if (inline_bc) k_jacobi_vec4<true><<<grd, blk, 0, s>>>(pn, pc, src, pcode, d);
-        else k_jacobi_vec4<false><<<grd, blk, 0, s>>>(pn, pc, src, pcode, d);
+        dim3 blk(32, JM_WARPS, 1), grd(nblk(d.r1 - d.r0, JM_ROWS * JM_WARPS), nblk(d.Y, 128), 1);
+        if (inline_bc) k_jacobi_march<true><<<grd, blk, 0, s>>>(pn, pc, src, pcode, d);
+        else k_jacobi_march<false><<<grd, blk, 0, s>>>(pn, pc, src, pcode, d);
     } else {
         if (inline_bc) k_jacobi_scalar<true><<<dense_grid(d), dense_block(), 0, s>>>(pn, pc, src, pcode, d);
         else k_jacobi_scalar<false><<<dense_grid(d), dense_block(), 0, s>>>(pn, pc, src, pcode, d);

@@ -61,6 +61,15 @@ def pressure_codes(mask: torch.Tensor) -> torch.Tensor:
     return code.contiguous()
 
 
+def pack_pcode(code: torch.Tensor) -> torch.Tensor:
+    """pcode byte of include/fs2d.h: code | (neighbour-is-a-BC-cell bits << 4), neighbours clamped."""
+    bc_cell = (code != PC_FLUID) & (code != PC_W_NONE)
+    out = code.clone()
+    for bit, (di, dj) in ((0x10, (-1, 0)), (0x20, (1, 0)), (0x40, (0, -1)), (0x80, (0, 1))):
+        out |= _shift(bc_cell, di, dj).to(torch.uint8) * bit
+    return out.contiguous()
+
+
 def velocity_writer_branch(mask: torch.Tensor) -> torch.Tensor:
     """Scatter branch 1..4 taken by each wall cell as a WRITER (boundary_condition.py:20-34), else 0."""
     m = mask

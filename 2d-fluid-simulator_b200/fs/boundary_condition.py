@@ -51,7 +51,7 @@ class BoundaryCondition:
             return out.contiguous()
 
         self._bc_mask = local(gmask, WALL)
-        self._pcode = local(pcode, _bc_tables.PC_W_NONE)
+        self._pcode = local(_bc_tables.pack_pcode(pcode), _bc_tables.PC_W_NONE)
         self._bc_const = local(torch.from_numpy(bc_const).to(self.device))
         # BC targets: owned rows plus the halo rows whose sources are inside the window
         tl, th = max(lo, g0 - max(self.halo - 2, 0)), min(hi, g1 + max(self.halo - 2, 0))
@@ -77,6 +77,13 @@ class BoundaryCondition:
 
     def set_pressure_boundary_condition(self, pc: Field) -> None:
         t = self._p_table
+        _lib.call("fs2d_pressure_bc", pc.ptr(), _lib.ptr(t["tgt"]), _lib.ptr(t["src0"]), _lib.ptr(t["src1"]),
+                  _lib.ptr(t["kind"]), _lib.ptr(self._scratch), t["n"], _lib.stream())
+
+    def apply_feed_bc(self, pc: Field) -> None:
+        """In-place BC of the few wall cells whose stored value an inflow cell reads raw (see
+        fs2d_jacobi_update in include/fs2d.h)."""
+        t = self._p_table["feed"]
         _lib.call("fs2d_pressure_bc", pc.ptr(), _lib.ptr(t["tgt"]), _lib.ptr(t["src0"]), _lib.ptr(t["src1"]),
                   _lib.ptr(t["kind"]), _lib.ptr(self._scratch), t["n"], _lib.stream())
 

@@ -1,0 +1,176 @@
+"""Halo exchange and the multi-rank versions of the operators.
+
+Row-strip decomposition: rank r owns global rows [g0, g1) and keeps `halo` extra rows of its
+neighbours on each side of every field (see fs/distributed.py).  The ONLY communication of the
+solver is a nearest-neighbour SendRecv of whole grid rows (NCCL over NVLink through
+torch.distributed; gloo in the CPU tests): no reductions, no global state.
+
+Invariant that makes P strips bit-identical to one GPU: a kernel that updates the owned rows reads
+rows up to its stencil radius away; those rows were copied from the owner's memory AFTER the owner's
+last write, so every load sees the same bits as in the single-GPU run.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from fs.double_buffer import DoubleBuffer, Field
+
+
+class HaloExchanger:
+    def __init__(self, partition, group=None) -> None:
+        self.part = partition
+        self.group = group
+        self.n_exchanges = 0
+        self.bytes_sent = 0
+
+    def exchange(self, field: Field | torch.Tensor, width: int) -> None:
+        """Fill the `width` halo rows adjacent to the owned rows on both sides from the neighbours."""
+        p = self.part
+        if p.world == 1 or width == 0:
+            return
+        t = field.tensor if isinstance(field, Field) else field
+        H, rows = p.halo, t.shape[0]
+        if width > H:
+            raise ValueError(f"halo exchange of {width} rows but the partition only has {H} halo rows")
+        ops, r = [], p.rank
+        if p.has_lower:
+            ops.append(dist.P2POp(dist.isend, t[H:H + width], r - 1, self.group))            # my first owned rows
+            ops.append(dist.P2POp(dist.irecv, t[H - width:H], r - 1, self.group))            # their last owned rows
+        if p.has_upper:
+            ops.append(dist.P2POp(dist.isend, t[rows - H - width:rows - H], r + 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, t[rows - H:rows - H + width], r + 1, self.group))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        self.n_exchanges += 1
+        self.bytes_sent += sum(op.tensor.numel() * op.tensor.element_size() for op in ops[::2])
+
+
+_EXCHANGERS: dict[int, HaloExchanger] = {}
+
+
+def exchanger_for(bc) -> HaloExchanger:
+    hx = _EXCHANGERS.get(id(bc))
+    if hx is None:
+        hx = _EXCHANGERS[id(bc)] = HaloExchanger(bc.partition)
+    return hx
+
+
+def _extended(bc, extra: int):
+    """dom covering the owned rows plus `extra` rows on each side that exist globally."""
+    d = bc.dom
+    return d.replace(r0=max(d.r0 - extra, d.clo), r1=min(d.r1 + extra, d.chi + 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-rank operator bodies (called from the single-rank classes when partition.world > 1)
+# ------------------------------------------------------------------------------------------------
+def vorticity_apply_distributed(vc, v: DoubleBuffer) -> None:
+    """fs/vorticity_confinement.py:57-59 on a strip: curl on owned+-1 rows (redundant row instead of
+    a second exchange), then the confinement force on the owned rows."""
+    bc = vc._bc
+    hx = exchanger_for(bc)
+    hx.exchange(v.current, 2)
+    vc._calc_vorticity(v.current, dom=_extended(bc, 1))
+    vc._add_vorticity(v.next, v.current)
+
+
+def jacobi_update_distributed(jac, p: DoubleBuffer, v_current: Field) -> None:
+    """fs/pressure_updater.py:56-60 on a strip: one 2-row SendRecv of p per sweep (row g0-1 is read by
+    the stencil, row g0-2 by the inline BC of row g0-1)."""
+    bc = jac._bc
+    hx = exchanger_for(bc)
+    hx.exchange(v_current, 1)
+    src = jac._source(v_current)
+    n = jac._n_iter
+    for s in range(n):
+        hx.exchange(p.current, 2)
+        literal = s >= n - 2
+        if literal:
+            bc.set_pressure_boundary_condition(p.current)   # owned rows and the first halo row
+        jac._sweep(p.next, p.current, src, inline_bc=not literal)
+        if not literal and bc._p_table["feed"]["n"]:
+            bc.apply_feed_bc(p.current)
+        p.swap()
+
+
+def rbsor_update_distributed(sor, p: DoubleBuffer, v_current: Field) -> None:
+    """fs/pressure_updater.py:86-96 on a strip: the even pass reads odd cells of p.next written in the
+    same iteration, so p.next's halo row is refreshed between the two colour passes."""
+    bc = sor._bc
+    hx = exchanger_for(bc)
+    hx.exchange(v_current, 1)
+    src = sor._source(v_current)
+    for _ in range(sor._n_iter):
+        hx.exchange(p.current, 2)
+        bc.set_pressure_boundary_condition(p.current)
+        sor._pass(p.next, p.current, src, 1)
+        hx.exchange(p.next, 1)
+        sor._pass(p.next, p.next, src, 0)
+        p.swap()
+
+
+def _velocity_bc(bc, hx: HaloExchanger, v: Field, reach: int) -> None:
+    """set_velocity_boundary_condition on a strip; afterwards v is post-BC on the owned rows +-reach."""
+    hx.exchange(v, bc.halo)                       # sources lie up to 2 rows away from a target
+    bc.set_velocity_boundary_condition(v)         # targets: owned rows +- (halo - 2)
+    if bc.halo - 2 < reach:
+        hx.exchange(v, reach)
+
+
+def cip_update_distributed(s) -> None:
+    """CipMacSolver.update() (fs/solver.py:192-227) on a strip."""
+    bc = s._bc
+    hx = exchanger_for(bc)
+    v, vx, vy, p = s.v, s.vx, s.vy, s.p
+    _velocity_bc(bc, hx, v.current, 1)
+    hx.exchange(p.current, 1)
+    s._non_advection_phase(v.next, v.current, p.current)
+    hx.exchange(v.next, 1)                        # fn(i+-1, j) of the grad kernel
+    s._non_advection_phase_grad(vx.next, vy.next, vx.current, vy.current, v.current, v.next)
+    v.swap(); vx.swap(); vy.swap()
+    hx.exchange(vx.current, 1)                    # CIP reads f, fx, fy at the upwind row i_m = i +- 1
+    hx.exchange(vy.current, 1)
+    s._advection_phase(v.next, vx.next, vy.next, v.current, vx.current, vy.current, v.current)
+    v.swap(); vx.swap(); vy.swap()
+    if s.vorticity_confinement is not None:
+        s.vorticity_confinement.apply(v)
+        v.swap()
+    s._pressure_update()
+    from fs.solver import VELOCITY_LIMIT, limit_field
+
+    limit_field(v.current, VELOCITY_LIMIT, bc=bc)
+
+
+def mac_update_distributed(s) -> None:
+    """MacSolver.update() (fs/solver.py:79-89) on a strip; KK reads +-2 rows."""
+    bc = s._bc
+    hx = exchanger_for(bc)
+    _velocity_bc(bc, hx, s.v.current, s._advect.radius)
+    hx.exchange(s.p.current, 1)
+    s._update_velocities(s.v.next, s.v.current, s.p.current)
+    s.v.swap()
+    if s.vorticity_confinement is not None:
+        s.vorticity_confinement.apply(s.v)
+        s.v.swap()
+    s._pressure_update()
+    from fs.solver import VELOCITY_LIMIT, limit_field
+
+    limit_field(s.v.current, VELOCITY_LIMIT, bc=bc)
+
+
+def gather_owned(field: Field, partition, dst: int = 0) -> torch.Tensor | None:
+    """Owned rows of every rank concatenated on rank `dst` (tests / field_to_numpy on strips)."""
+    own = field.owned().contiguous()
+    if partition.world == 1:
+        return own
+    sizes = [partition.owned(r)[1] - partition.owned(r)[0] for r in range(partition.world)]
+    if partition.rank == dst:
+        parts = [torch.empty((n,) + tuple(own.shape[1:]), dtype=own.dtype, device=own.device) for n in sizes]
+        parts[dst].copy_(own)
+        reqs = [dist.irecv(parts[r], r) for r in range(partition.world) if r != dst]
+        for q in reqs:
+            q.wait()
+        return torch.cat(parts, 0)
+    dist.send(own, dst)
+    return None

@@ -50,13 +50,6 @@ class Solver(metaclass=ABCMeta):
         if ev is not None:
             ev[1].record()
 
-    def _halo(self):
-        if self._bc.partition.world == 1:
-            return None
-        from fs.halo import exchanger_for
-
-        return exchanger_for(self._bc)
-
 
 def limit_field(field: Field, limit: float, dom=None, bc: BoundaryCondition | None = None) -> None:
     """:38-43 -- rescale |v| > limit to limit (all cells, in place)."""
@@ -87,10 +80,11 @@ class MacSolver(Solver):
         self.p = self._buffer(1)
 
     def update(self) -> None:
-        hx = self._halo()
-        if hx is not None:
-            hx.exchange(self.v.current, 2)
-            hx.exchange(self.p.current, 1)
+        if self._bc.partition.world > 1:
+            from fs.halo import mac_update_distributed
+
+            mac_update_distributed(self)
+            return
         self._bc.set_velocity_boundary_condition(self.v.current)
         self._update_velocities(self.v.next, self.v.current, self.p.current)
         self.v.swap()
@@ -122,13 +116,14 @@ class CipMacSolver(Solver):
         self.vx = self._buffer(2)
         self.vy = self._buffer(2)
         self.p = self._buffer(1)
-        self._set_grad(self.vx.current, self.vy.current, self.v.current)
+        self._set_grad(self.vx.current, self.vy.current, self.v.current)  # all-zero state: no halo needed
 
     def update(self) -> None:
-        hx = self._halo()
-        if hx is not None:
-            hx.exchange(self.v.current, 2)
-            hx.exchange(self.p.current, 1)
+        if self._bc.partition.world > 1:
+            from fs.halo import cip_update_distributed
+
+            cip_update_distributed(self)
+            return
         self._bc.set_velocity_boundary_condition(self.v.current)
         self._update_velocities(self.v, self.vx, self.vy, self.p)
         if self.vorticity_confinement is not None:
@@ -145,15 +140,9 @@ class CipMacSolver(Solver):
         _lib.call("fs2d_set_grad", fx.ptr(), fy.ptr(), f.ptr(), bc.dom, self.dx, _lib.stream())
 
     def _update_velocities(self, v: DoubleBuffer, vx: DoubleBuffer, vy: DoubleBuffer, p: DoubleBuffer) -> None:
-        hx = self._halo()
         self._non_advection_phase(v.next, v.current, p.current)
-        if hx is not None:
-            hx.exchange(v.next, 1)
         self._non_advection_phase_grad(vx.next, vy.next, vx.current, vy.current, v.current, v.next)
         v.swap(); vx.swap(); vy.swap()
-        if hx is not None:
-            hx.exchange(vx.current, 1)
-            hx.exchange(vy.current, 1)
         self._advection_phase(v.next, vx.next, vy.next, v.current, vx.current, vy.current, v.current)
         v.swap(); vx.swap(); vy.swap()
 

@@ -49,7 +49,10 @@ typedef struct {
 #define FS2D_SCHEME_UPWIND 0
 #define FS2D_SCHEME_KK 1
 
-/* pressure-BC cell codes (derived from the mask by the host layer; see DESIGN.md "pcode") */
+/* pressure-BC cell codes (derived from the mask by the host layer; see DESIGN.md "pcode").
+ * A pcode byte = code (low nibble) | neighbour bits (high nibble): 0x10/0x20/0x40/0x80 set when the
+ * clamped neighbour at (i-1,j)/(i+1,j)/(i,j-1)/(i,j+1) is a BC cell (code not FLUID / W_NONE), i.e. when
+ * its post-BC value differs from its stored value. */
 #define FS2D_PC_FLUID 0   /* mask 0                                                          */
 #define FS2D_PC_W_IM 1    /* wall: p = p(i-1,j)          boundary_condition.py:46-47         */
 #define FS2D_PC_W_IP 2    /* wall: p = p(i+1,j)          :48-49                              */

@@ -1,0 +1,92 @@
+"""Multi-rank strip check, launched by torchrun (NCCL, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/mp_strip_check.py
+
+Every case runs the same seeded problem (a) on P row strips with halo exchange and (b) on one GPU
+(rank 0), then compares every physical buffer BITWISE.  Prints "MP_CHECK OK <n cases>".
+"""
+from __future__ import annotations
+
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+REPO = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(REPO / "2d-fluid-simulator_b200"))
+
+from fs.boundary_condition import BoundaryCondition, build_scene  # noqa: E402
+from fs.distributed import Partition  # noqa: E402
+from fs.fluid_simulator import make_solver  # noqa: E402
+from fs.halo import gather_owned  # noqa: E402
+
+CASES = [
+    # bc, X, Y, scheme, vc, pressure kwargs, steps, halo
+    (2, 128, 64, "cip", 5.0, dict(pressure="jacobi", n_iter=6), 4, 2),
+    (3, 160, 80, "cip", 10.0, dict(pressure="jacobi", n_iter=5), 3, 2),
+    (5, 128, 64, "kk", 5.0, dict(pressure="rbsor", n_iter=2), 4, 2),
+    (1, 128, 64, "upwind", None, dict(pressure="jacobi", n_iter=3), 4, 3),
+    (4, 96, 48, "cip", 2.0, dict(pressure="rbsor", n_iter=3), 3, 4),
+    (2, 1024, 512, "cip", 5.0, dict(pressure="jacobi", n_iter=8), 2, 2),
+]
+
+
+def buffers(s) -> dict:
+    d = {"v_cur": s.v.current, "v_nxt": s.v.next, "p_cur": s.p.current, "p_nxt": s.p.next}
+    if hasattr(s, "vx"):
+        d.update(vx_cur=s.vx.current, vx_nxt=s.vx.next, vy_cur=s.vy.current, vy_nxt=s.vy.next)
+    if s.vorticity_confinement is not None:
+        d.update(vort=s.vorticity_confinement.vorticity, vort_abs=s.vorticity_confinement.vorticity_abs)
+    return d
+
+
+def main() -> None:
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_ok = 0
+    for num, X, Y, scheme, vc, pkw, steps, halo in CASES:
+        res = Y
+        dt, dx, re = 0.05 / res, 1.0 / res, 1e4
+        const, mask = build_scene(num, X, Y)
+        part = Partition(X, rank, world, halo)
+        strip = make_solver(BoundaryCondition(const, mask, partition=part), dt, dx, re, vc, scheme, **pkw)
+        single = make_solver(BoundaryCondition(const, mask), dt, dx, re, vc, scheme, **pkw) if rank == 0 else None
+        rng = np.random.default_rng(1234 + num)
+        g0, g1 = part.owned()
+        for k, f in buffers(strip).items():  # same seeded global state on every rank (incl. "next" buffers)
+            shape = (X, Y, 2) if f.n == 2 else (X, Y)
+            scale = 0.05 / dx if k[:2] in ("vx", "vy") else (0.5 if k[0] == "v" and k != "vort" else 1.0)
+            a = (rng.uniform(-1, 1, shape) * scale).astype(np.float32)
+            if k == "vort_abs":
+                a = np.abs(a)
+            f.from_numpy(a[g0:g1])
+            if single is not None:
+                buffers(single)[k].from_numpy(a)
+        for _ in range(steps):
+            strip.update()
+            if single is not None:
+                single.update()
+        for k, f in buffers(strip).items():
+            got = gather_owned(f, part)
+            if rank == 0:
+                want = buffers(single)[k].tensor
+                same = torch.equal(got, want) or bool(((got == want) | (got.isnan() & want.isnan())).all())
+                if not same:
+                    bad = ~((got == want) | (got.isnan() & want.isnan()))
+                    rows = torch.nonzero(bad.reshape(X, -1).any(1)).flatten()[:8].tolist()
+                    raise SystemExit(f"MP_CHECK FAIL case bc{num} {X}x{Y} {scheme} {pkw} buffer {k}: "
+                                     f"{int(bad.sum())} values differ, first rows {rows}")
+        n_ok += 1
+        dist.barrier()
+    if rank == 0:
+        print(f"MP_CHECK OK {n_ok} cases on {world} ranks", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
