@@ -37,6 +37,7 @@ _SIGNATURES = {
     "fs2d_version": (c_int, []),
     "fs2d_launch_count": (ctypes.c_ulonglong, []),
     "fs2d_device_ok": (c_int, []),
+    "fs2d_set_tuning": (c_int, [c_int, c_int]),
     "fs2d_vel_bc": (c_int, [_P, _P, _P, _P, _P, _P, c_int, _P]),
     "fs2d_pressure_bc": (c_int, [_P, _P, _P, _P, _P, _P, c_int, _P]),
     "fs2d_mac_update": (c_int, [_P, _P, _P, _P, Dom, c_float, c_float, c_float, c_int, _P]),

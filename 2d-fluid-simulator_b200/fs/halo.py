@@ -82,15 +82,10 @@ def jacobi_update_distributed(jac, p: DoubleBuffer, v_current: Field) -> None:
     hx = exchanger_for(bc)
     hx.exchange(v_current, 1)
     src = jac._source(v_current)
-    n = jac._n_iter
-    for s in range(n):
+    for _ in range(jac._n_iter):
         hx.exchange(p.current, 2)
-        literal = s >= n - 2
-        if literal:
-            bc.set_pressure_boundary_condition(p.current)   # owned rows and the first halo row
-        jac._sweep(p.next, p.current, src, inline_bc=not literal)
-        if not literal and bc._p_table["feed"]["n"]:
-            bc.apply_feed_bc(p.current)
+        bc.set_pressure_boundary_condition(p.current)       # owned rows and the first halo row
+        jac._sweep(p.next, p.current, src, inline_bc=False)
         p.swap()
 
 

@@ -223,7 +223,7 @@ def run_ours(a: argparse.Namespace) -> None:
     ms_sweep = ms_poisson / a.jacobi
     peak, peak_src = peaks()
     achieved = ALGO_BYTES_PER_CELL_SWEEP * (a.rows_per_gpu * Y) / (ms_sweep * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_jacobi_vec4 (Jacobi pressure sweep incl. its BC passes)",
+    roofline = {"bound": "hbm", "kernel": "k_jacobi_march<false,4> (one Jacobi pressure sweep incl. its sparse BC pass)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL_SWEEP * a.rows_per_gpu * Y,
                 "ms_per_sweep": ms_sweep, "poisson_share_of_step": ms_poisson / ms_step, "traffic": None,
