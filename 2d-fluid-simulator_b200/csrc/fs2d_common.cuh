@@ -33,6 +33,10 @@ void launch_p_bc(float *p, const int32_t *tgt, const int32_t *src0, const int32_
                  int n, cudaStream_t s);
 inline unsigned nblk(int n, int b) { return (unsigned)((n + b - 1) / b); }
 bool is_pow2(float x);
+// one fused pass of T Jacobi iterations p_in -> p_out (fs2d_fused.cu)
+int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t *pcode, const fs2d_dom &d, int T,
+               cudaStream_t s);
+bool fused_supported(const float *pa, const float *pb, const float *src, const uint8_t *pcode, const fs2d_dom &d);
 
 // ---- indexing (clamp-to-edge sample(), fs/differentiation.py:4-9) -----------------------------
 __device__ __forceinline__ int CR(const fs2d_dom &d, int r) { return min(max(r, d.clo), d.chi); }

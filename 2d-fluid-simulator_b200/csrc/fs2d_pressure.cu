@@ -224,23 +224,39 @@ int fs2d_jacobi_sweep(float *pn, const float *pc, const float *src, const uint8_
 
 int fs2d_jacobi_update(float *pa, float *pb, const float *src, const uint8_t *pcode, fs2d_dom d, int n_sweeps,
                        const int32_t *tgt, const int32_t *src0, const int32_t *src1, const uint8_t *kind, float *scratch,
-                       int n_bc, const int32_t *f_tgt, const int32_t *f_src0, const int32_t *f_src1,
-                       const uint8_t *f_kind, int n_feed, int *final_in_b, void *stream) {
+                       int n_bc, int fuse_t, int *final_in_b, void *stream) {
     FS2D_REQUIRE(pa && pb && src && pcode && pa != pb, "null/aliased field pointer");
-    FS2D_REQUIRE(n_sweeps >= 0, "negative sweep count");
+    FS2D_REQUIRE(n_sweeps >= 0 && fuse_t >= 0, "negative sweep count");
     FS2D_REQUIRE(n_bc == 0 || (tgt && src0 && src1 && kind && scratch), "null BC table");
-    FS2D_REQUIRE(n_feed == 0 || (f_tgt && f_src0 && f_src1 && f_kind && scratch), "null feed table");
     if (int e = check_dom(d)) return e;
     float *cur = pa, *nxt = pb;
-    (void)f_tgt; (void)f_src0; (void)f_src1; (void)f_kind; (void)n_feed;
-    for (int s = 0; s < n_sweeps; ++s) {
+    // Fused passes (temporal blocking, fs2d_fused.cu) for all but the last two iterations; the last two run
+    // literally so that the BC cells of BOTH buffers end up exactly as the reference leaves them.
+    int n_lit = n_sweeps < 2 ? n_sweeps : 2, n_f = n_sweeps - n_lit, passes = 0;
+    if (fuse_t > 0 && n_f > 0 && d.r1 > d.r0 && fused_supported(pa, pb, src, pcode, d)) {
+        passes = (n_f + fuse_t - 1) / fuse_t;
+        if ((passes & 1) != (n_f & 1)) {             // buffer parity must match n_f single sweeps
+            if (passes + 1 <= n_f) ++passes;
+            else { --n_f; ++n_lit; passes = n_f ? (n_f + fuse_t - 1) / fuse_t : 0; if (n_f && (passes & 1) != (n_f & 1)) ++passes; }
+        }
+    } else {
+        n_lit = n_sweeps;
+        n_f = 0;
+    }
+    for (int k = 0, left = n_f; k < passes; ++k) {
+        const int t = (left + (passes - k) - 1) / (passes - k);  // spread n_f over the passes
+        if (int e = fused_pass(cur, nxt, src, pcode, d, t, STREAM)) return e;
+        left -= t;
+        float *x = cur; cur = nxt; nxt = x;
+    }
+    for (int s = 0; s < n_lit; ++s) {
         // Literal reference iteration (fs/pressure_updater.py:57-60): in-place sparse BC (two tiny gather /
         // scatter launches over the ~0.1 % BC cells), then the plain 5-point sweep.  Measured on B200 at
         // 8192^2: plain sweep 187 us (6.1 TB/s of traffic) + 8 us of BC, vs 320 us for a sweep that
         // recomputes BC values inline (its divergent slow path hits every warp touching a wall face).
         launch_p_bc(cur, tgt, src0, src1, kind, scratch, n_bc, STREAM);
         if (d.r1 > d.r0) launch_jacobi(nxt, cur, src, pcode, d, 0, STREAM);
-        float *t = cur; cur = nxt; nxt = t;
+        float *x = cur; cur = nxt; nxt = x;
     }
     FS2D_LAUNCH_CHECK();
     if (final_in_b) *final_in_b = (cur == pb);

@@ -180,3 +180,66 @@ def exposed_stale_cells(pcode: torch.Tensor) -> torch.Tensor:
     notwall = (pcode == PC_FLUID) | (pcode == PC_INFLOW) | (pcode == PC_OUTFLOW)
     near = _shift(notwall, -1, 0) | _shift(notwall, 1, 0) | _shift(notwall, 0, -1) | _shift(notwall, 0, 1)
     return torch.nonzero(((pcode == PC_W_NONE) & near).flatten(), as_tuple=True)[0]
+
+
+# --------------------------------------------------------------------------------------------------
+# validity of the fused multi-iteration Jacobi kernel for a given mask (fs2d_jacobi_fused)
+# --------------------------------------------------------------------------------------------------
+_SRC_OFFSETS = {  # BC code of a neighbour -> offsets (relative to that neighbour) of the cells its value reads
+    PC_W_IM: ((-1, 0),), PC_W_IP: ((1, 0),), PC_W_JM: ((0, -1),), PC_W_JP: ((0, 1),),
+    PC_W_IM_JP: ((-1, 0), (0, 1)), PC_W_IP_JP: ((1, 0), (0, 1)), PC_W_IM_JM: ((-1, 0), (0, -1)),
+    PC_W_IP_JM: ((1, 0), (0, -1)), PC_INFLOW: ((1, 0),), PC_OUTFLOW: (),
+}
+
+
+def iteration_dependencies(code: torch.Tensor) -> dict:
+    """{(di, dj): bool mask}: relaxed cell c reads cell c + (di, dj) during one {BC, sweep} iteration."""
+    relaxed = (code == PC_FLUID) | (code == PC_INFLOW) | (code == PC_OUTFLOW)
+    deps: dict = {}
+
+    def add(off, m):
+        if off in deps:
+            deps[off] |= m
+        else:
+            deps[off] = m.clone()
+
+    for n in ((1, 0), (-1, 0), (0, 1), (0, -1)):
+        cn = _shift(code, *n)
+        add(n, relaxed & ((cn == PC_FLUID) | (cn == PC_W_NONE)))
+        for k, offs in _SRC_OFFSETS.items():
+            m = relaxed & (cn == k)
+            if bool(m.any()):
+                for o in offs:
+                    add((n[0] + o[0], n[1] + o[1]), m)
+    return deps
+
+
+def fused_reach_ok(code: torch.Tensor, T: int, tile_rows: int, tile_cols: int, row0: int = 0, row1: int | None = None) -> bool:
+    """True if, for the tiling used by fs2d_jacobi_fused (tiles of tile_rows x tile_cols loaded cells, halo T,
+    output tiles anchored at (row0, 0)), the value of every OUTPUT cell after T iterations depends only on cells
+    inside its tile.  Dynamic programme over the T iterations of how far up/down/left/right each cell's
+    dependency cone reaches (conservative at global edges)."""
+    X, Y = code.shape
+    row1 = X if row1 is None else row1
+    TI, TJ = tile_rows - 2 * T, tile_cols - 2 * T
+    if TI <= 0 or TJ <= 0:
+        return False
+    deps = iteration_dependencies(code)
+    dev = code.device
+    ii = torch.arange(X, device=dev)
+    lr = (T + ((ii - row0) % TI)).to(torch.int16)[:, None]          # tile row of each cell as an output cell
+    lc = (T + (torch.arange(Y, device=dev) % TJ)).to(torch.int16)[None, :]
+    owned = ((ii >= row0) & (ii < row1))[:, None]
+    weights = {"up": lambda o: -o[0], "down": lambda o: o[0], "left": lambda o: -o[1], "right": lambda o: o[1]}
+    room = {"up": lr, "down": (tile_rows - 1) - lr, "left": lc, "right": (tile_cols - 1) - lc}
+    for name, w in weights.items():
+        R = torch.zeros((X, Y), dtype=torch.int16, device=dev)
+        for _ in range(T):
+            new = torch.zeros_like(R)
+            for off, m in deps.items():
+                cand = _shift(R, *off) + w(off)
+                new = torch.maximum(new, torch.where(m, cand, torch.zeros_like(cand)))
+            R = new
+        if bool(((R > room[name]) & owned).any()):
+            return False
+    return True

@@ -52,6 +52,8 @@ class BoundaryCondition:
 
         self._bc_mask = local(gmask, WALL)
         self._pcode = local(_bc_tables.pack_pcode(pcode), _bc_tables.PC_W_NONE)
+        self._pcode_global = pcode           # unpacked codes of the whole grid (fused-kernel validity analysis)
+        self._fused_ok: dict[int, bool] = {}
         self._bc_const = local(torch.from_numpy(bc_const).to(self.device))
         # BC targets: owned rows plus the halo rows whose sources are inside the window
         tl, th = max(lo, g0 - max(self.halo - 2, 0)), min(hi, g1 + max(self.halo - 2, 0))
@@ -67,7 +69,7 @@ class BoundaryCondition:
         n = max(self._vel_table["n"], self._p_table["n"], 1)
         self._scratch = torch.empty(2 * n, dtype=torch.float32, device=self.device)
         self.dom = _lib.Dom(rows=w1 - w0, Y=Y, r0=g0 - w0, r1=g1 - w0, clo=lo - w0, chi=hi - 1 - w0, gi0=w0)
-        del gmask, pcode
+        del gmask
 
     # -- reference API ---------------------------------------------------------------------
     def set_velocity_boundary_condition(self, vc: Field) -> None:
@@ -106,6 +108,20 @@ class BoundaryCondition:
                 torch.from_numpy(np.ascontiguousarray(bc_mask, dtype=np.uint8)).to(dev))
 
     # -- helpers for the other operators -----------------------------------------------------
+    def fused_ok(self, T: int) -> bool:
+        """May fs2d_jacobi_fused run T iterations per pass on this mask?  (static analysis, cached)"""
+        if T not in self._fused_ok:
+            import ctypes
+
+            rows, cols, tmax = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+            _lib.call("fs2d_fused_tile", ctypes.byref(rows), ctypes.byref(cols), ctypes.byref(tmax))
+            g0, g1 = self.partition.owned()
+            ok = (1 <= T <= tmax.value and self._global_resolution[1] % 16 == 0 and self._p_table["feed"]["n"] == 0
+                  and (self.partition.world == 1 or self.halo >= T)
+                  and _bc_tables.fused_reach_ok(self._pcode_global, T, rows.value, cols.value, g0, g1))
+            self._fused_ok[T] = bool(ok)
+        return self._fused_ok[T]
+
     def stale_cells_agree(self, a: Field, b: Field) -> bool:
         """True if the never-written wall cells read by relaxed neighbours hold equal values in both
         physical buffers (always the case for solver-owned buffers)."""

@@ -40,11 +40,21 @@ class PressureUpdater(metaclass=ABCMeta):
 
 
 class JacobiPressureUpdater(PressureUpdater):
-    """Jacobi method (:41-66)."""
+    """Jacobi method (:41-66).
 
-    def __init__(self, boundary_condition: BoundaryCondition, dt: float, dx: float, n_iter: int) -> None:
+    `fuse` (not in the reference): number of iterations computed per pass over HBM by the fused
+    shared-memory kernel (fs2d_jacobi_fused); "auto" picks FUSE_DEFAULT when the mask qualifies, 0 disables.
+    Results are bit-identical either way."""
+
+    FUSE_DEFAULT = 5
+
+    def __init__(self, boundary_condition: BoundaryCondition, dt: float, dx: float, n_iter: int,
+                 fuse: int | str = "auto") -> None:
         super().__init__(boundary_condition, dt, dx)
         self._n_iter = int(n_iter)
+        self._fuse_request = fuse
+        self._fuse_t: int | None = None      # resolved lazily (needs the device tables)
+        self._stale_checked: tuple | None = None
 
     def _sweep(self, p_next: Field, p_current: Field, src: Field, inline_bc: bool, dom=None) -> None:
         bc = self._bc
@@ -55,6 +65,22 @@ class JacobiPressureUpdater(PressureUpdater):
     def _update(self, p_next: Field, p_current: Field, v_current: Field) -> None:
         self._sweep(p_next, p_current, self._source(v_current), inline_bc=False)
 
+    def fuse_t(self, p: DoubleBuffer) -> int:
+        """Iterations per fused pass for this mask and these buffers (0 = literal path only)."""
+        if self._fuse_t is None:
+            req = self._fuse_request
+            t = self.FUSE_DEFAULT if req == "auto" else int(req)
+            self._fuse_t = t if t > 0 and self._bc.fused_ok(t) else 0
+        if self._fuse_t == 0:
+            return 0
+        key = (id(p.current), id(p.next))
+        if self._stale_checked != key or p.current.dirty or p.next.dirty:
+            # never-written wall cells must agree between the two physical buffers (DESIGN.md "stale cells")
+            self._stale_ok = self._bc.stale_cells_agree(p.current, p.next)
+            self._stale_checked = key
+            p.current.dirty = p.next.dirty = False
+        return self._fuse_t if self._stale_ok else 0
+
     def update(self, p: DoubleBuffer, v_current: Field) -> None:
         bc = self._bc
         if bc.partition.world > 1:
@@ -64,12 +90,10 @@ class JacobiPressureUpdater(PressureUpdater):
             return
         src = self._source(v_current)
         t = bc._p_table
-        f = t["feed"]
         final_in_b = ctypes.c_int(0)
         _lib.call("fs2d_jacobi_update", p.current.ptr(), p.next.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom,
                   self._n_iter, _lib.ptr(t["tgt"]), _lib.ptr(t["src0"]), _lib.ptr(t["src1"]), _lib.ptr(t["kind"]),
-                  _lib.ptr(bc._scratch), t["n"], _lib.ptr(f["tgt"]), _lib.ptr(f["src0"]), _lib.ptr(f["src1"]),
-                  _lib.ptr(f["kind"]), f["n"], ctypes.byref(final_in_b), _lib.stream())
+                  _lib.ptr(bc._scratch), t["n"], self.fuse_t(p), ctypes.byref(final_in_b), _lib.stream())
         if final_in_b.value:
             p.swap()  # n_iter odd: same net effect as the reference's n_iter swaps
 

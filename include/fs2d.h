@@ -123,14 +123,24 @@ int fs2d_jacobi_sweep(float *pn, const float *pc, const float *src, const uint8_
                       void *stream);
 /* n_sweeps of {pressure BC, Jacobi} with ping-pong between pa (current) and pb (next); equal to
  * n_sweeps reference iterations (fs/pressure_updater.py:56-60) INCLUDING the final contents of the
- * BC cells of both buffers.  (tgt, src0, src1, kind, n_bc): table as in fs2d_pressure_bc.
- * (f_*, n_feed): the sub-table of wall-BC cells whose stored value an inflow cell reads raw
- * (usually empty).  scratch: >= max(n_bc, n_feed) floats.  *final_in_b = 1 if the current buffer
- * after the call is pb (n_sweeps odd). */
+ * BC cells of both buffers.  (tgt, src0, src1, kind, n_bc): table as in fs2d_pressure_bc; scratch:
+ * >= n_bc floats.  fuse_t > 0 allows the first n_sweeps-2 iterations to run as fused passes of up to
+ * fuse_t iterations each (fs2d_jacobi_fused); the caller must have verified the preconditions listed
+ * there.  *final_in_b = 1 if the current buffer after the call is pb (n_sweeps odd). */
 int fs2d_jacobi_update(float *pa, float *pb, const float *src, const uint8_t *pcode, fs2d_dom d, int n_sweeps,
                        const int32_t *tgt, const int32_t *src0, const int32_t *src1, const uint8_t *kind, float *scratch,
-                       int n_bc, const int32_t *f_tgt, const int32_t *f_src0, const int32_t *f_src1,
-                       const uint8_t *f_kind, int n_feed, int *final_in_b, void *stream);
+                       int n_bc, int fuse_t, int *final_in_b, void *stream);
+/* One fused pass: T reference iterations {BC, sweep} computed in shared memory, p_in -> relaxed cells of
+ * p_out (rows [r0, r1)); bit-identical to T calls of fs2d_pressure_bc + fs2d_jacobi_sweep on the relaxed
+ * cells.  BC cells of p_in/p_out are neither read nor written (their values are recomputed from pcode).
+ * Preconditions (checked by the host layer, fs/_bc_tables.py): Y % 16 == 0 and 16-byte aligned fields;
+ * T <= t_max of fs2d_fused_tile; the mask's dependency reach fits the tile halo (fused_reach_ok); no
+ * inflow cell reads a wall-BC cell; never-written wall cells hold equal values in p_in and p_out; in a
+ * row strip the halo rows [r0-T, r1+T) of p_in and src are up to date. */
+int fs2d_jacobi_fused(float *p_out, const float *p_in, const float *src, const uint8_t *pcode, fs2d_dom d, int T,
+                      void *stream);
+/* tile geometry of the fused kernel: loaded tile rows x cols and the largest T */
+int fs2d_fused_tile(int *rows, int *cols, int *t_max);
 /* One colour pass of RedBlackSorPressureUpdater, fs/pressure_updater.py:98-114 (fluid cells of
  * colour `parity`, (i_global + j) % 2); pc may alias pn (even pass, :96); src as above */
 int fs2d_rbsor_pass(float *pn, const float *pc, const float *src, const uint8_t *mask, fs2d_dom d, float omega,

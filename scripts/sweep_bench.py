@@ -29,3 +29,18 @@ for inline in (True, False):
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 20
         print(f"inline={inline} rows/warp={rows:2d}: {ms*1e3:7.1f} us/sweep  algorithmic {12*X*Y/ms/1e6:7.1f} GB/s  actual~{17*X*Y/ms/1e6:7.1f} GB/s", flush=True)
+
+print("fused passes (T iterations per pass), us per iteration:")
+for T in (1, 2, 3, 4, 5, 6, 8, 10, 12):
+    if not bc.fused_ok(T):
+        print("T", T, "not valid for this mask"); continue
+    for _ in range(2):
+        _lib.call("fs2d_jacobi_fused", b.ptr(), a.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom, T, _lib.stream())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        _lib.call("fs2d_jacobi_fused", b.ptr(), a.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom, T, _lib.stream())
+        _lib.call("fs2d_jacobi_fused", a.ptr(), b.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom, T, _lib.stream())
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"T={T:2d}: {ms*1e3:8.1f} us/pass  {ms*1e3/T:7.1f} us/iteration  algorithmic {12*X*Y*T/ms/1e6:8.1f} GB/s", flush=True)

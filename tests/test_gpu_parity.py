@@ -296,3 +296,71 @@ def test_properties_at_res_8192(env):
     interior[4:X - 4] = True
     ok = (bc._bc_mask == 0) & interior
     assert torch.equal(whole.tensor[ok], torch.full_like(whole.tensor[ok], 0.75))
+
+
+# ------------------------------------------------------------------------------------------------
+# 5. fused multi-iteration Jacobi (temporal blocking) == literal iterations, bitwise
+# ------------------------------------------------------------------------------------------------
+FUSED_CASES = [(1, 128, 64), (2, 256, 128), (3, 320, 160), (4, 200, 96), (5, 384, 192), (2, 1000, 512), (3, 2048, 1024)]
+
+
+@pytest.mark.parametrize("num,X,Y", FUSED_CASES)
+def test_fused_pass_equals_literal_iterations(env, num, X, Y):
+    from fs import _lib
+    from fs.boundary_condition import BoundaryCondition, build_scene
+    from fs.pressure_updater import JacobiPressureUpdater
+
+    const, mask = build_scene(num, X, Y)
+    bc = BoundaryCondition(const, mask)
+    rng = np.random.default_rng(X + num)
+    p0 = rng.uniform(-1, 1, mask.shape).astype(np.float32)
+    v = fld(rng.uniform(-1, 1, mask.shape + (2,)).astype(np.float32))
+    dt, dx = 0.05 / Y, 1.0 / Y
+    jac = JacobiPressureUpdater(bc, dt, dx, 1, fuse=0)
+    src = jac._source(v)
+    relaxed = torch.from_numpy((mask != 1)).cuda()
+    checked = 0
+    for T in (1, 2, 3, 5, 8, 12):
+        if not bc.fused_ok(T):
+            continue
+        a, b = fld(p0), fld(p0)
+        for _ in range(T):  # literal iterations
+            bc.set_pressure_boundary_condition(a); jac._sweep(b, a, src, inline_bc=False); a, b = b, a
+        fin, fout = fld(p0), fld(p0)
+        _lib.call("fs2d_jacobi_fused", fout.ptr(), fin.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom, T, _lib.stream())
+        got, want = fout.tensor, a.tensor
+        same = (got == want) | (got.isnan() & want.isnan())
+        bad = relaxed & ~same
+        assert not bool(bad.any()), f"bc{num} {X}x{Y} T={T}: {int(bad.sum())} relaxed cells differ, first {torch.nonzero(bad)[0].tolist()}"
+        assert torch.equal(fout.tensor[~relaxed], torch.from_numpy(p0).cuda()[~relaxed])  # walls untouched
+        checked += 1
+    assert checked >= 3
+
+
+@pytest.mark.parametrize("num,X,Y,n_iter", [(2, 256, 128, 80), (5, 384, 192, 21), (1, 128, 64, 7), (3, 320, 160, 13), (2, 96, 48, 3)])
+def test_fused_update_equals_literal_update(env, num, X, Y, n_iter):
+    """JacobiPressureUpdater.update with fused passes == without, both physical buffers, bitwise."""
+    from fs.boundary_condition import BoundaryCondition, build_scene
+    from fs.double_buffer import DoubleBuffer
+    from fs.pressure_updater import JacobiPressureUpdater
+
+    const, mask = build_scene(num, X, Y)
+    bc = BoundaryCondition(const, mask)
+    rng = np.random.default_rng(n_iter)
+    p0 = rng.uniform(-1, 1, mask.shape).astype(np.float32)
+    p1 = rng.uniform(-1, 1, mask.shape).astype(np.float32)
+    v = fld(rng.uniform(-1, 1, mask.shape + (2,)).astype(np.float32))
+    dt, dx = 0.05 / Y, 1.0 / Y
+    for other, expect_fused in ((p0, True), (p1, False)):   # equal / different never-written wall cells
+        res = []
+        for fuse in (5, 0):
+            jac = JacobiPressureUpdater(bc, dt, dx, n_iter, fuse=fuse)
+            db = DoubleBuffer(mask.shape, 1)
+            db.current.from_numpy(p0); db.next.from_numpy(other)
+            if fuse:
+                assert (jac.fuse_t(db) > 0) == (expect_fused and bc.fused_ok(5))
+            jac.update(db, v)
+            res.append((db.current.to_numpy(), db.next.to_numpy()))
+        assert_bitexact("cur", res[0][0], res[1][0])
+        if other is p0:
+            assert_bitexact("nxt", res[0][1], res[1][1])
