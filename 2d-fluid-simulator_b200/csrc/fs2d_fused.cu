@@ -18,7 +18,7 @@
 // update/slow bit masks live in registers for all T iterations; per iteration it writes its K values to a
 // ping-pong smem plane and reads only the j-neighbours (and the two i-neighbours outside its own rows) back.
 //
-// HBM bytes per cell per iteration: (4 + 8 + 1) * (SI*SJ)/((SI-2T)(SJ-2T)) / T + 4/T  (T=5: 4.2 B vs 17 B).
+// HBM bytes per cell per iteration: (4 + 8 + 1.1) * (SI*SJ)/((SI-2T)(SJ-2HJ)) / T + 4/T  (T=4: 5.0 B vs 17 B).
 #include <cuda.h>
 
 #include "fs2d_common.cuh"
@@ -31,7 +31,11 @@ constexpr int FSI = FK * FNTY;   // 64 tile rows
 constexpr int FSJ = 128;         // tile columns = threads per row block
 constexpr int F_THREADS = FSJ * FNTY;
 constexpr int F_TMAX = 12;
-constexpr size_t F_SMEM = (size_t)FSI * FSJ * (4 + 8 + 1 + 4 + 4 + 1) + 128;
+constexpr int FCW = FSJ + 16;   // columns of the staged pcode box (its start is rounded down to 16 bytes)
+constexpr size_t F_SMEM = (size_t)FSI * FSJ * (4 + 8 + 4 + 4 + 1) + (size_t)FSI * FCW + 128;
+// TMA (measured on B200, scripts/probes/tma_probe.cu): the box start must be 16-byte aligned in the innermost
+// dimension (an unaligned column coordinate raises "illegal instruction"), rows are free.  So the column halo
+// HJ is T rounded up to a multiple of 4 floats and the 1-byte pcode box starts at the previous multiple of 16.
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -62,8 +66,9 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
 }
 
 struct FusedGeom {
-    int T;        // iterations in this pass == halo width
-    int TI, TJ;   // output tile rows / cols = FSI - 2T, FSJ - 2T
+    int T;        // iterations in this pass == row halo
+    int HJ;       // column halo: T rounded up to a multiple of 4 (TMA alignment)
+    int TI, TJ;   // output tile rows / cols = FSI - 2T, FSJ - 2HJ
     int tiles_i, tiles_j;
 };
 
@@ -104,8 +109,8 @@ __global__ void __launch_bounds__(F_THREADS, 1)
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     float *stg_p = reinterpret_cast<float *>(smem);                          // FSI*FSJ floats   (TMA dst)
     float *stg_src = stg_p + FSI * FSJ;                                      // FSI*FSJ float2   (TMA dst)
-    uint8_t *stg_code = reinterpret_cast<uint8_t *>(stg_src + 2 * FSI * FSJ);  // FSI*FSJ bytes (TMA dst)
-    float *w0 = reinterpret_cast<float *>(stg_code + FSI * FSJ);
+    uint8_t *stg_code = reinterpret_cast<uint8_t *>(stg_src + 2 * FSI * FSJ);  // FSI*FCW bytes (TMA dst)
+    float *w0 = reinterpret_cast<float *>(stg_code + FSI * FCW);
     float *w1 = w0 + FSI * FSJ;
     uint8_t *wcode = reinterpret_cast<uint8_t *>(w1 + FSI * FSJ);
     __shared__ __align__(8) uint64_t bar;
@@ -114,27 +119,32 @@ __global__ void __launch_bounds__(F_THREADS, 1)
     const int lr0 = threadIdx.y * FK;      // first tile row of this thread
     const bool leader = (threadIdx.x == 0 && threadIdx.y == 0);
     const int n_tiles = g.tiles_i * g.tiles_j;
-    constexpr uint32_t TX_BYTES = FSI * FSJ * (4 + 8 + 1);
+    constexpr uint32_t TX_BYTES = FSI * FSJ * (4 + 8) + FSI * FCW;
 
-    auto issue = [&](int t) {
-        const int R0 = d.r0 + (t / g.tiles_j) * g.TI - g.T;
-        const int C0 = (t % g.tiles_j) * g.TJ - g.T;
-        mbar_expect_tx(&bar, TX_BYTES);
-        tma_load_2d(stg_p, &map_p, C0, R0, &bar);
-        tma_load_2d(stg_src, &map_src, 2 * C0, R0, &bar);
-        tma_load_2d(stg_code, &map_code, C0, R0, &bar);
-    };
+    // NOTE: the descriptors must be addressed in the kernel-parameter space (the TMA unit cannot read a copy
+    // that the compiler spilled to local memory), so take their addresses here, not through a lambda capture.
+    const CUtensorMap *mp = &map_p, *ms = &map_src, *mc = &map_code;
+#define FS2D_ISSUE(tile)                                                            \
+    do {                                                                            \
+        const int R0_ = d.r0 + ((tile) / g.tiles_j) * g.TI - g.T;                   \
+        const int C0_ = ((tile) % g.tiles_j) * g.TJ - g.HJ;                         \
+        mbar_expect_tx(&bar, TX_BYTES);                                             \
+        tma_load_2d(stg_p, mp, C0_, R0_, &bar);                                     \
+        tma_load_2d(stg_src, ms, 2 * C0_, R0_, &bar);                               \
+        tma_load_2d(stg_code, mc, C0_ & ~15, R0_, &bar);                            \
+    } while (0)
 
     if (leader) mbar_init(&bar, 1);
     __syncthreads();
     int t = blockIdx.x;
-    if (leader && t < n_tiles) issue(t);
+    if (leader && t < n_tiles) FS2D_ISSUE(t);
     uint32_t parity = 0;
     const int cl = max(c - 1, 0), cr = min(c + 1, FSJ - 1);
 
     for (; t < n_tiles; t += gridDim.x) {
         const int R0 = d.r0 + (t / g.tiles_j) * g.TI - g.T;   // local-array row of tile row 0
-        const int C0 = (t % g.tiles_j) * g.TJ - g.T;          // column of tile column 0
+        const int C0 = (t % g.tiles_j) * g.TJ - g.HJ;         // column of tile column 0
+        const int coff = C0 - (C0 & ~15);                     // where tile column 0 sits inside the staged pcode box
         // clamp bounds of sample() in tile coordinates (global edges only)
         const int rlo = max(0, d.clo - R0), rhi = min(FSI - 1, d.chi - R0);
         const int clo = max(0, -C0), chi = min(FSJ - 1, d.Y - 1 - C0);
@@ -152,7 +162,7 @@ __global__ void __launch_bounds__(F_THREADS, 1)
             const float2 s = reinterpret_cast<const float2 *>(stg_src)[o];
             t2[k] = s.x;
             t3[k] = s.y;
-            const uint8_t pc = stg_code[o];
+            const uint8_t pc = stg_code[lr * FCW + coff + c];
             wcode[o] = pc;
             const int code = pc & 15;
             const bool inside = lr >= rlo && lr <= rhi && c >= clo && c <= chi;
@@ -172,7 +182,7 @@ __global__ void __launch_bounds__(F_THREADS, 1)
         float *nxt = w0;
         for (int s = 0; s < g.T; ++s) {
             __syncthreads();  // plane `cur` (and wcode) complete; previous readers of `nxt` done
-            if (s == 1 && leader && t + (int)gridDim.x < n_tiles) issue(t + gridDim.x);  // staging is free now
+            if (s == 1 && leader && t + (int)gridDim.x < n_tiles) FS2D_ISSUE(t + (int)gridDim.x);  // staging is free now
             const float upx = cur[max(lr0 - 1, 0) * FSJ + c];
             const float dnx = cur[min(lr0 + FK, FSI - 1) * FSJ + c];
             float np[FK];
@@ -197,11 +207,11 @@ __global__ void __launch_bounds__(F_THREADS, 1)
         }
         if (g.T == 1) {  // staging was never released inside the loop
             __syncthreads();
-            if (leader && t + (int)gridDim.x < n_tiles) issue(t + gridDim.x);
+            if (leader && t + (int)gridDim.x < n_tiles) FS2D_ISSUE(t + (int)gridDim.x);
         }
 
         // ---- store the inner (TI x TJ) cells that were updated and belong to rows [r0, r1) ----------
-        if (c >= g.T && c < g.T + g.TJ && C0 + c < d.Y) {
+        if (c >= g.HJ && c < g.HJ + g.TJ && C0 + c < d.Y) {
 #pragma unroll
             for (int k = 0; k < FK; ++k) {
                 const int lr = lr0 + k, gr = R0 + lr;
@@ -273,11 +283,12 @@ int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t 
     CUtensorMap mp, ms, mc;
     if (int e = make_map(&mp, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p_in, d.Y, d.rows, FSJ, FSI)) return e;
     if (int e = make_map(&ms, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, src, 2ull * d.Y, d.rows, 2 * FSJ, FSI)) return e;
-    if (int e = make_map(&mc, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, pcode, d.Y, d.rows, FSJ, FSI)) return e;
+    if (int e = make_map(&mc, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, pcode, d.Y, d.rows, FCW, FSI)) return e;
     FusedGeom g;
     g.T = T;
+    g.HJ = (T + 3) & ~3;
     g.TI = FSI - 2 * T;
-    g.TJ = FSJ - 2 * T;
+    g.TJ = FSJ - 2 * g.HJ;
     g.tiles_i = (d.r1 - d.r0 + g.TI - 1) / g.TI;
     g.tiles_j = (d.Y + g.TJ - 1) / g.TJ;
     const int n_tiles = g.tiles_i * g.tiles_j;
@@ -293,9 +304,11 @@ using namespace fs2d;
 
 extern "C" {
 
-int fs2d_fused_tile(int *rows, int *cols, int *t_max) {
+int fs2d_fused_tile(int T, int *rows, int *cols, int *halo_rows, int *halo_cols, int *t_max) {
     if (rows) *rows = FSI;
     if (cols) *cols = FSJ;
+    if (halo_rows) *halo_rows = T;
+    if (halo_cols) *halo_cols = (T + 3) & ~3;
     if (t_max) *t_max = F_TMAX;
     return FS2D_OK;
 }

@@ -224,29 +224,31 @@ int fs2d_jacobi_sweep(float *pn, const float *pc, const float *src, const uint8_
 
 int fs2d_jacobi_update(float *pa, float *pb, const float *src, const uint8_t *pcode, fs2d_dom d, int n_sweeps,
                        const int32_t *tgt, const int32_t *src0, const int32_t *src1, const uint8_t *kind, float *scratch,
-                       int n_bc, int fuse_t, int *final_in_b, void *stream) {
+                       int n_bc, int fuse_mask, int *final_in_b, void *stream) {
     FS2D_REQUIRE(pa && pb && src && pcode && pa != pb, "null/aliased field pointer");
-    FS2D_REQUIRE(n_sweeps >= 0 && fuse_t >= 0, "negative sweep count");
+    FS2D_REQUIRE(n_sweeps >= 0 && fuse_mask >= 0, "negative sweep count");
     FS2D_REQUIRE(n_bc == 0 || (tgt && src0 && src1 && kind && scratch), "null BC table");
     if (int e = check_dom(d)) return e;
     float *cur = pa, *nxt = pb;
     // Fused passes (temporal blocking, fs2d_fused.cu) for all but the last two iterations; the last two run
     // literally so that the BC cells of BOTH buffers end up exactly as the reference leaves them.
-    int n_lit = n_sweeps < 2 ? n_sweeps : 2, n_f = n_sweeps - n_lit, passes = 0;
-    if (fuse_t > 0 && n_f > 0 && d.r1 > d.r0 && fused_supported(pa, pb, src, pcode, d)) {
-        passes = (n_f + fuse_t - 1) / fuse_t;
-        if ((passes & 1) != (n_f & 1)) {             // buffer parity must match n_f single sweeps
-            if (passes + 1 <= n_f) ++passes;
-            else { --n_f; ++n_lit; passes = n_f ? (n_f + fuse_t - 1) / fuse_t : 0; if (n_f && (passes & 1) != (n_f & 1)) ++passes; }
-        }
-    } else {
-        n_lit = n_sweeps;
-        n_f = 0;
+    // fuse_mask bit t (1 <= t <= 12) says the host validated a pass of t iterations for this mask.  The
+    // number of buffer flips must have the parity of n_sweeps so that the physical buffers end up as in the
+    // reference: q passes of t* + r single sweeps flip q + r times for q*t* + r iterations.
+    int n_lit = n_sweeps < 2 ? n_sweeps : 2, n_f = n_sweeps - n_lit, q = 0, tstar = 0;
+    if (fuse_mask > 0 && n_f > 0 && d.r1 > d.r0 && fused_supported(pa, pb, src, pcode, d)) {
+        for (int t = 12; t >= 1 && !tstar; --t)            // largest validated odd size (parity-neutral) ...
+            if ((fuse_mask >> t) & 1 && (t & 1) && t <= n_f) tstar = t;
+        for (int t = 12; t >= 1; --t)                      // ... unless an even one is at least 2 larger
+            if ((fuse_mask >> t) & 1 && !(t & 1) && t <= n_f && t > tstar + 1) { tstar = t; break; }
     }
-    for (int k = 0, left = n_f; k < passes; ++k) {
-        const int t = (left + (passes - k) - 1) / (passes - k);  // spread n_f over the passes
-        if (int e = fused_pass(cur, nxt, src, pcode, d, t, STREAM)) return e;
-        left -= t;
+    if (tstar) {
+        q = n_f / tstar;
+        if (!(tstar & 1) && (q & 1)) --q;                  // even pass size: keep the flip parity right
+    }
+    n_lit = n_sweeps - q * tstar;
+    for (int k = 0; k < q; ++k) {
+        if (int e = fused_pass(cur, nxt, src, pcode, d, tstar, STREAM)) return e;
         float *x = cur; cur = nxt; nxt = x;
     }
     for (int s = 0; s < n_lit; ++s) {

@@ -214,21 +214,24 @@ def iteration_dependencies(code: torch.Tensor) -> dict:
     return deps
 
 
-def fused_reach_ok(code: torch.Tensor, T: int, tile_rows: int, tile_cols: int, row0: int = 0, row1: int | None = None) -> bool:
-    """True if, for the tiling used by fs2d_jacobi_fused (tiles of tile_rows x tile_cols loaded cells, halo T,
-    output tiles anchored at (row0, 0)), the value of every OUTPUT cell after T iterations depends only on cells
-    inside its tile.  Dynamic programme over the T iterations of how far up/down/left/right each cell's
-    dependency cone reaches (conservative at global edges)."""
+def fused_reach_ok(code: torch.Tensor, T: int, tile_rows: int, tile_cols: int, halo_rows: int | None = None,
+                   halo_cols: int | None = None, row0: int = 0, row1: int | None = None) -> bool:
+    """True if, for the tiling used by fs2d_jacobi_fused (tiles of tile_rows x tile_cols loaded cells, of which
+    halo_rows / halo_cols are discarded on each side, output tiles anchored at (row0, 0)), the value of every
+    OUTPUT cell after T iterations depends only on cells inside its tile.  Dynamic programme over the T
+    iterations of how far up/down/left/right each cell's dependency cone reaches (conservative at global edges)."""
     X, Y = code.shape
     row1 = X if row1 is None else row1
-    TI, TJ = tile_rows - 2 * T, tile_cols - 2 * T
+    HI = T if halo_rows is None else halo_rows
+    HJ = T if halo_cols is None else halo_cols
+    TI, TJ = tile_rows - 2 * HI, tile_cols - 2 * HJ
     if TI <= 0 or TJ <= 0:
         return False
     deps = iteration_dependencies(code)
     dev = code.device
     ii = torch.arange(X, device=dev)
-    lr = (T + ((ii - row0) % TI)).to(torch.int16)[:, None]          # tile row of each cell as an output cell
-    lc = (T + (torch.arange(Y, device=dev) % TJ)).to(torch.int16)[None, :]
+    lr = (HI + ((ii - row0) % TI)).to(torch.int16)[:, None]         # tile row of each cell as an output cell
+    lc = (HJ + (torch.arange(Y, device=dev) % TJ)).to(torch.int16)[None, :]
     owned = ((ii >= row0) & (ii < row1))[:, None]
     weights = {"up": lambda o: -o[0], "down": lambda o: o[0], "left": lambda o: -o[1], "right": lambda o: o[1]}
     room = {"up": lr, "down": (tile_rows - 1) - lr, "left": lc, "right": (tile_cols - 1) - lc}

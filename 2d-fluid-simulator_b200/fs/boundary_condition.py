@@ -113,12 +113,13 @@ class BoundaryCondition:
         if T not in self._fused_ok:
             import ctypes
 
-            rows, cols, tmax = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
-            _lib.call("fs2d_fused_tile", ctypes.byref(rows), ctypes.byref(cols), ctypes.byref(tmax))
+            rows, cols, hr, hc, tmax = (ctypes.c_int() for _ in range(5))
+            _lib.call("fs2d_fused_tile", T, ctypes.byref(rows), ctypes.byref(cols), ctypes.byref(hr), ctypes.byref(hc),
+                      ctypes.byref(tmax))
             g0, g1 = self.partition.owned()
             ok = (1 <= T <= tmax.value and self._global_resolution[1] % 16 == 0 and self._p_table["feed"]["n"] == 0
                   and (self.partition.world == 1 or self.halo >= T)
-                  and _bc_tables.fused_reach_ok(self._pcode_global, T, rows.value, cols.value, g0, g1))
+                  and _bc_tables.fused_reach_ok(self._pcode_global, T, rows.value, cols.value, hr.value, hc.value, g0, g1))
             self._fused_ok[T] = bool(ok)
         return self._fused_ok[T]
 

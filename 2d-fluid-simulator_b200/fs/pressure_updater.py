@@ -65,12 +65,13 @@ class JacobiPressureUpdater(PressureUpdater):
     def _update(self, p_next: Field, p_current: Field, v_current: Field) -> None:
         self._sweep(p_next, p_current, self._source(v_current), inline_bc=False)
 
-    def fuse_t(self, p: DoubleBuffer) -> int:
-        """Iterations per fused pass for this mask and these buffers (0 = literal path only)."""
+    def fuse_mask(self, p: DoubleBuffer) -> int:
+        """Bit t set: a fused pass of t iterations is valid for this mask and these buffers (0 = literal only).
+        Every pass size has its own tiling, so each is validated separately (BoundaryCondition.fused_ok)."""
         if self._fuse_t is None:
             req = self._fuse_request
-            t = self.FUSE_DEFAULT if req == "auto" else int(req)
-            self._fuse_t = t if t > 0 and self._bc.fused_ok(t) else 0
+            t_max = self.FUSE_DEFAULT if req == "auto" else int(req)
+            self._fuse_t = sum(1 << t for t in range(1, t_max + 1) if self._bc.fused_ok(t)) if t_max > 0 else 0
         if self._fuse_t == 0:
             return 0
         key = (id(p.current), id(p.next))
@@ -93,7 +94,7 @@ class JacobiPressureUpdater(PressureUpdater):
         final_in_b = ctypes.c_int(0)
         _lib.call("fs2d_jacobi_update", p.current.ptr(), p.next.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom,
                   self._n_iter, _lib.ptr(t["tgt"]), _lib.ptr(t["src0"]), _lib.ptr(t["src1"]), _lib.ptr(t["kind"]),
-                  _lib.ptr(bc._scratch), t["n"], self.fuse_t(p), ctypes.byref(final_in_b), _lib.stream())
+                  _lib.ptr(bc._scratch), t["n"], self.fuse_mask(p), ctypes.byref(final_in_b), _lib.stream())
         if final_in_b.value:
             p.swap()  # n_iter odd: same net effect as the reference's n_iter swaps
 

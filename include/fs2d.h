@@ -124,12 +124,13 @@ int fs2d_jacobi_sweep(float *pn, const float *pc, const float *src, const uint8_
 /* n_sweeps of {pressure BC, Jacobi} with ping-pong between pa (current) and pb (next); equal to
  * n_sweeps reference iterations (fs/pressure_updater.py:56-60) INCLUDING the final contents of the
  * BC cells of both buffers.  (tgt, src0, src1, kind, n_bc): table as in fs2d_pressure_bc; scratch:
- * >= n_bc floats.  fuse_t > 0 allows the first n_sweeps-2 iterations to run as fused passes of up to
- * fuse_t iterations each (fs2d_jacobi_fused); the caller must have verified the preconditions listed
- * there.  *final_in_b = 1 if the current buffer after the call is pb (n_sweeps odd). */
+ * >= n_bc floats.  fuse_mask: bit t set (1 <= t <= 12) allows all but the last two iterations to run as
+ * fused passes of t iterations (fs2d_jacobi_fused) -- the caller must have verified that pass size against
+ * the preconditions listed there; 0 = literal iterations only.  *final_in_b = 1 if the current buffer after
+ * the call is pb (n_sweeps odd). */
 int fs2d_jacobi_update(float *pa, float *pb, const float *src, const uint8_t *pcode, fs2d_dom d, int n_sweeps,
                        const int32_t *tgt, const int32_t *src0, const int32_t *src1, const uint8_t *kind, float *scratch,
-                       int n_bc, int fuse_t, int *final_in_b, void *stream);
+                       int n_bc, int fuse_mask, int *final_in_b, void *stream);
 /* One fused pass: T reference iterations {BC, sweep} computed in shared memory, p_in -> relaxed cells of
  * p_out (rows [r0, r1)); bit-identical to T calls of fs2d_pressure_bc + fs2d_jacobi_sweep on the relaxed
  * cells.  BC cells of p_in/p_out are neither read nor written (their values are recomputed from pcode).
@@ -139,8 +140,9 @@ int fs2d_jacobi_update(float *pa, float *pb, const float *src, const uint8_t *pc
  * row strip the halo rows [r0-T, r1+T) of p_in and src are up to date. */
 int fs2d_jacobi_fused(float *p_out, const float *p_in, const float *src, const uint8_t *pcode, fs2d_dom d, int T,
                       void *stream);
-/* tile geometry of the fused kernel: loaded tile rows x cols and the largest T */
-int fs2d_fused_tile(int *rows, int *cols, int *t_max);
+/* tile geometry of the fused kernel for T iterations per pass: loaded tile rows x cols, the halo it discards on
+ * each side (rows: T; columns: T rounded up to 4 -- TMA box starts must be 16-byte aligned) and the largest T */
+int fs2d_fused_tile(int T, int *rows, int *cols, int *halo_rows, int *halo_cols, int *t_max);
 /* One colour pass of RedBlackSorPressureUpdater, fs/pressure_updater.py:98-114 (fluid cells of
  * colour `parity`, (i_global + j) % 2); pc may alias pn (even pass, :96); src as above */
 int fs2d_rbsor_pass(float *pn, const float *pc, const float *src, const uint8_t *mask, fs2d_dom d, float omega,

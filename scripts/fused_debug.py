@@ -1,0 +1,21 @@
+import sys
+from pathlib import Path
+REPO = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(REPO / "2d-fluid-simulator_b200"))
+import numpy as np, torch
+from fs import _lib
+from fs.boundary_condition import BoundaryCondition, build_scene
+from fs.double_buffer import Field
+from fs.pressure_updater import JacobiPressureUpdater
+X, Y, T = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+const, mask = build_scene(2, X, Y)
+bc = BoundaryCondition(const, mask)
+jac = JacobiPressureUpdater(bc, 0.05 / Y, 1.0 / Y, 1, fuse=0)
+a, b, v = Field((X, Y), 1), Field((X, Y), 1), Field((X, Y), 2)
+a.tensor.uniform_(-1, 1); b.tensor.copy_(a.tensor); v.tensor.uniform_(-1, 1)
+src = jac._source(v)
+torch.cuda.synchronize()
+print("fused_ok", bc.fused_ok(T), flush=True)
+_lib.call("fs2d_jacobi_fused", b.ptr(), a.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom, T, _lib.stream())
+torch.cuda.synchronize()
+print("ran", X, Y, T, float(b.tensor.abs().sum()), flush=True)

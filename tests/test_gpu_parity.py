@@ -320,7 +320,7 @@ def test_fused_pass_equals_literal_iterations(env, num, X, Y):
     src = jac._source(v)
     relaxed = torch.from_numpy((mask != 1)).cuda()
     checked = 0
-    for T in (1, 2, 3, 5, 8, 12):
+    for T in (1, 2, 3, 4, 5, 6, 8, 12):
         if not bc.fused_ok(T):
             continue
         a, b = fld(p0), fld(p0)
@@ -358,7 +358,7 @@ def test_fused_update_equals_literal_update(env, num, X, Y, n_iter):
             db = DoubleBuffer(mask.shape, 1)
             db.current.from_numpy(p0); db.next.from_numpy(other)
             if fuse:
-                assert (jac.fuse_t(db) > 0) == (expect_fused and bc.fused_ok(5))
+                assert (jac.fuse_mask(db) > 0) == (expect_fused and any(bc.fused_ok(t) for t in range(1, 6)))
             jac.update(db, v)
             res.append((db.current.to_numpy(), db.next.to_numpy()))
         assert_bitexact("cur", res[0][0], res[1][0])
