@@ -32,7 +32,6 @@ constexpr int FSJ = 128;         // tile columns = threads per row block
 constexpr int F_THREADS = FSJ * FNTY;
 constexpr int F_TMAX = 12;
 constexpr int FCW = FSJ + 16;   // columns of the staged pcode box (its start is rounded down to 16 bytes)
-constexpr size_t F_SMEM = (size_t)FSI * FSJ * (4 + 8 + 4 + 4 + 1) + (size_t)FSI * FCW + 128;
 // TMA (measured on B200, scripts/probes/tma_probe.cu): the box start must be 16-byte aligned in the innermost
 // dimension (an unaligned column coordinate raises "illegal instruction"), rows are free.  So the column halo
 // HJ is T rounded up to a multiple of 4 floats and the 1-byte pcode box starts at the previous multiple of 16.
@@ -72,54 +71,58 @@ struct FusedGeom {
     int tiles_i, tiles_j;
 };
 
-// post-BC pressure of tile cell (r, c) from plane `cur` (same rule as p_post in fs2d_pressure.cu);
-// rlo..rhi / clo..chi: tile coordinates of the clamp bounds
-__device__ __noinline__ float f_post(const float *cur, const uint8_t *code, int r, int c, int rlo, int rhi, int clo,
-                                     int chi) {
+// post-BC pressure of tile cell (r, c) read from plane `pl` (same rule as p_post in fs2d_pressure.cu);
+// rlo..rhi / clo..chi: tile coordinates of the clamp bounds of sample()
+__device__ __forceinline__ float f_post(const float *pl, const uint8_t *code, int r, int c, int rlo, int rhi, int clo,
+                                        int chi) {
     const int rm = max(r - 1, rlo), rp = min(r + 1, rhi), cm = max(c - 1, clo), cp = min(c + 1, chi);
+    int a = r * FSJ + c, b = a, mode = 0;  // mode 0: value of cell a; 1: (a + b) / 2; 2: zero
     switch (code[r * FSJ + c] & 15) {
-        case FS2D_PC_FLUID:
-        case FS2D_PC_W_NONE: return cur[r * FSJ + c];
-        case FS2D_PC_W_IM: return cur[rm * FSJ + c];
-        case FS2D_PC_W_IP: return cur[rp * FSJ + c];
-        case FS2D_PC_W_JM: return cur[r * FSJ + cm];
-        case FS2D_PC_W_JP: return cur[r * FSJ + cp];
-        case FS2D_PC_W_IM_JP: return (cur[rm * FSJ + c] + cur[r * FSJ + cp]) / 2.0f;
-        case FS2D_PC_W_IP_JP: return (cur[rp * FSJ + c] + cur[r * FSJ + cp]) / 2.0f;
-        case FS2D_PC_W_IM_JM: return (cur[rm * FSJ + c] + cur[r * FSJ + cm]) / 2.0f;
-        case FS2D_PC_W_IP_JM: return (cur[rp * FSJ + c] + cur[r * FSJ + cm]) / 2.0f;
-        case FS2D_PC_INFLOW: return cur[rp * FSJ + c];
-        default: return 0.0f;  // FS2D_PC_OUTFLOW
+        case FS2D_PC_W_IM: a = rm * FSJ + c; break;
+        case FS2D_PC_W_IP: a = rp * FSJ + c; break;
+        case FS2D_PC_W_JM: a = r * FSJ + cm; break;
+        case FS2D_PC_W_JP: a = r * FSJ + cp; break;
+        case FS2D_PC_W_IM_JP: a = rm * FSJ + c; b = r * FSJ + cp; mode = 1; break;
+        case FS2D_PC_W_IP_JP: a = rp * FSJ + c; b = r * FSJ + cp; mode = 1; break;
+        case FS2D_PC_W_IM_JM: a = rm * FSJ + c; b = r * FSJ + cm; mode = 1; break;
+        case FS2D_PC_W_IP_JM: a = rp * FSJ + c; b = r * FSJ + cm; mode = 1; break;
+        case FS2D_PC_INFLOW: a = rp * FSJ + c; break;
+        case FS2D_PC_OUTFLOW: mode = 2; break;
+        default: break;  // FLUID / W_NONE: the stored value
     }
+    const float va = pl[a], vb = pl[b];
+    return mode == 0 ? va : (mode == 1 ? (va + vb) / 2.0f : 0.0f);
 }
-// slow path of one cell: all four neighbours through f_post with clamping
-__device__ __noinline__ float f_slow_sum(const float *cur, const uint8_t *code, int r, int c, int rlo, int rhi, int clo,
-                                         int chi) {
-    const float pe = f_post(cur, code, min(r + 1, rhi), c, rlo, rhi, clo, chi);
-    const float pw = f_post(cur, code, max(r - 1, rlo), c, rlo, rhi, clo, chi);
-    const float pq = f_post(cur, code, r, min(c + 1, chi), rlo, rhi, clo, chi);
-    const float ps = f_post(cur, code, r, max(c - 1, clo), rlo, rhi, clo, chi);
-    return pe + pw + pq + ps;
-}
+
+// Shared-memory layout (float index unless noted).  All planes are addressed as offsets from ONE base pointer
+// so that the compiler keeps them in the shared address space (LDS/STS, not generic LD/ST).
+constexpr int FN = FSI * FSJ;          // cells per plane
+constexpr int OFF_P0 = 0;              // TMA destination of p, plane of iteration 0
+constexpr int OFF_SRC = FN;            // TMA destination of (t2, t3), 2*FN floats
+constexpr int OFF_W0 = 3 * FN;         // working plane
+constexpr int OFF_W1 = 4 * FN;         // working plane
+constexpr int OFF_BYTES = 5 * FN;      // byte area: staged pcode (FSI*FCW), tile pcode (FN), slow list (2*FN)
+constexpr size_t F_SMEM = (size_t)OFF_BYTES * 4 + (size_t)FSI * FCW + FN + 2 * FN;
 
 __global__ void __launch_bounds__(F_THREADS, 1)
     k_jacobi_fused(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_src,
-                   const __grid_constant__ CUtensorMap map_code, float *__restrict__ p_out, fs2d_dom d, FusedGeom g) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-    float *stg_p = reinterpret_cast<float *>(smem);                          // FSI*FSJ floats   (TMA dst)
-    float *stg_src = stg_p + FSI * FSJ;                                      // FSI*FSJ float2   (TMA dst)
-    uint8_t *stg_code = reinterpret_cast<uint8_t *>(stg_src + 2 * FSI * FSJ);  // FSI*FCW bytes (TMA dst)
-    float *w0 = reinterpret_cast<float *>(stg_code + FSI * FCW);
-    float *w1 = w0 + FSI * FSJ;
-    uint8_t *wcode = reinterpret_cast<uint8_t *>(w1 + FSI * FSJ);
+                   const __grid_constant__ CUtensorMap map_code, float *__restrict__ p_out, unsigned int *tile_ctr,
+                   fs2d_dom d, FusedGeom g) {
+    extern __shared__ __align__(1024) float sm[];
+    uint8_t *stg_code = reinterpret_cast<uint8_t *>(sm + OFF_BYTES);
+    uint8_t *wcode = stg_code + FSI * FCW;
+    uint16_t *slow_list = reinterpret_cast<uint16_t *>(wcode + FN);
     __shared__ __align__(8) uint64_t bar;
+    __shared__ int n_slow[2];   // slow cells of the current / next tile (ping-pong)
+    __shared__ int s_next;      // tile index fetched by the leader for the next round
 
+    const int tid = threadIdx.y * FSJ + threadIdx.x;
     const int c = threadIdx.x;             // tile column
     const int lr0 = threadIdx.y * FK;      // first tile row of this thread
-    const bool leader = (threadIdx.x == 0 && threadIdx.y == 0);
+    const int o0 = lr0 * FSJ + c;          // plane offset of this thread's first cell
+    const bool leader = tid == 0;
     const int n_tiles = g.tiles_i * g.tiles_j;
-    constexpr uint32_t TX_BYTES = FSI * FSJ * (4 + 8) + FSI * FCW;
+    constexpr uint32_t TX_BYTES = FN * (4 + 8) + FSI * FCW;
 
     // NOTE: the descriptors must be addressed in the kernel-parameter space (the TMA unit cannot read a copy
     // that the compiler spilled to local memory), so take their addresses here, not through a lambda capture.
@@ -129,25 +132,30 @@ __global__ void __launch_bounds__(F_THREADS, 1)
         const int R0_ = d.r0 + ((tile) / g.tiles_j) * g.TI - g.T;                   \
         const int C0_ = ((tile) % g.tiles_j) * g.TJ - g.HJ;                         \
         mbar_expect_tx(&bar, TX_BYTES);                                             \
-        tma_load_2d(stg_p, mp, C0_, R0_, &bar);                                     \
-        tma_load_2d(stg_src, ms, 2 * C0_, R0_, &bar);                               \
+        tma_load_2d(sm + OFF_P0, mp, C0_, R0_, &bar);                               \
+        tma_load_2d(sm + OFF_SRC, ms, 2 * C0_, R0_, &bar);                          \
         tma_load_2d(stg_code, mc, C0_ & ~15, R0_, &bar);                            \
     } while (0)
 
-    if (leader) mbar_init(&bar, 1);
+    if (leader) {
+        mbar_init(&bar, 1);
+        n_slow[0] = n_slow[1] = 0;
+    }
     __syncthreads();
     int t = blockIdx.x;
     if (leader && t < n_tiles) FS2D_ISSUE(t);
     uint32_t parity = 0;
-    const int cl = max(c - 1, 0), cr = min(c + 1, FSJ - 1);
+    const int dl = max(c - 1, 0) - c, dr = min(c + 1, FSJ - 1) - c;   // j-neighbour offsets, clamped inside the tile
+    const int o_up = max(lr0 - 1, 0) * FSJ + c, o_dn = min(lr0 + FK, FSI - 1) * FSJ + c;
 
-    for (; t < n_tiles; t += gridDim.x) {
+    while (t < n_tiles) {
         const int R0 = d.r0 + (t / g.tiles_j) * g.TI - g.T;   // local-array row of tile row 0
         const int C0 = (t % g.tiles_j) * g.TJ - g.HJ;         // column of tile column 0
         const int coff = C0 - (C0 & ~15);                     // where tile column 0 sits inside the staged pcode box
         // clamp bounds of sample() in tile coordinates (global edges only)
         const int rlo = max(0, d.clo - R0), rhi = min(FSI - 1, d.chi - R0);
         const int clo = max(0, -C0), chi = min(FSJ - 1, d.Y - 1 - C0);
+        const int par = parity;
 
         mbar_wait(&bar, parity);
         parity ^= 1;
@@ -157,57 +165,74 @@ __global__ void __launch_bounds__(F_THREADS, 1)
         uint32_t upd = 0, slow = 0;
 #pragma unroll
         for (int k = 0; k < FK; ++k) {
-            const int lr = lr0 + k, o = lr * FSJ + c;
-            p[k] = stg_p[o];
-            const float2 s = reinterpret_cast<const float2 *>(stg_src)[o];
-            t2[k] = s.x;
-            t3[k] = s.y;
+            const int lr = lr0 + k, o = o0 + k * FSJ;
+            p[k] = sm[OFF_P0 + o];
+            const float2 s2 = reinterpret_cast<const float2 *>(sm + OFF_SRC)[o];
+            t2[k] = s2.x;
+            t3[k] = s2.y;
             const uint8_t pc = stg_code[lr * FCW + coff + c];
             wcode[o] = pc;
             const int code = pc & 15;
             const bool inside = lr >= rlo && lr <= rhi && c >= clo && c <= chi;
             const bool relaxed = code == FS2D_PC_FLUID || code == FS2D_PC_INFLOW || code == FS2D_PC_OUTFLOW;
-            const bool e_rl = lr == rlo && R0 + lr == d.clo, e_rh = lr == rhi && R0 + lr == d.chi;
-            const bool e_cl = c == clo && C0 + c == 0, e_ch = c == chi && C0 + c == d.Y - 1;
+            const bool e_rl = R0 + lr == d.clo, e_rh = R0 + lr == d.chi;
+            const bool e_cl = C0 + c == 0, e_ch = C0 + c == d.Y - 1;
             // a cell on the tile rim whose missing neighbour is NOT a global edge cannot be updated
             const bool frozen = (lr == 0 && !e_rl) || (lr == FSI - 1 && !e_rh) || (c == 0 && !e_cl) || (c == FSJ - 1 && !e_ch);
             const bool u = inside && relaxed && !frozen;
             const bool sl = u && ((pc >> 4) != 0 || e_rl || e_rh || e_cl || e_ch);
             upd |= (uint32_t)u << k;
             slow |= (uint32_t)sl << k;
+            if (sl) slow_list[atomicAdd(&n_slow[par], 1)] = (uint16_t)o;   // cells that need post-BC neighbour values
         }
 
         // ---- T iterations --------------------------------------------------------------------------
-        const float *cur = stg_p;
-        float *nxt = w0;
+        int cur = OFF_P0, nxt = OFF_W0;
         for (int s = 0; s < g.T; ++s) {
-            __syncthreads();  // plane `cur` (and wcode) complete; previous readers of `nxt` done
-            if (s == 1 && leader && t + (int)gridDim.x < n_tiles) FS2D_ISSUE(t + (int)gridDim.x);  // staging is free now
-            const float upx = cur[max(lr0 - 1, 0) * FSJ + c];
-            const float dnx = cur[min(lr0 + FK, FSI - 1) * FSJ + c];
-            float np[FK];
+            __syncthreads();  // (A) plane `cur`, wcode and the slow list are complete; readers of `nxt` are done
+            if (leader && s == (g.T > 1 ? 1 : 0)) {
+                n_slow[par ^ 1] = 0;
+                if (g.T > 1) {  // staging is free: fetch the next tile index and start its loads
+                    const int tn = (int)atomicAdd(tile_ctr, 1u) + (int)gridDim.x;
+                    s_next = tn;
+                    if (tn < n_tiles) FS2D_ISSUE(tn);
+                }
+            }
+            const int ns = n_slow[par];
+            if (ns > 0) {  // block-uniform: the tile has cells next to BC cells / global edges
+                // Balanced fix-up: all threads share the slow cells and leave, in plane `nxt`, the SUM of the four
+                // post-BC neighbour values (the reference's order) for the owning thread to pick up.
+                for (int e = tid; e < ns; e += F_THREADS) {
+                    const int o = slow_list[e], r = o / FSJ, cc = o % FSJ;
+                    float sum = f_post(sm + cur, wcode, min(r + 1, rhi), cc, rlo, rhi, clo, chi);
+                    sum = sum + f_post(sm + cur, wcode, max(r - 1, rlo), cc, rlo, rhi, clo, chi);
+                    sum = sum + f_post(sm + cur, wcode, r, min(cc + 1, chi), rlo, rhi, clo, chi);
+                    sum = sum + f_post(sm + cur, wcode, r, max(cc - 1, clo), rlo, rhi, clo, chi);
+                    sm[nxt + o] = sum;
+                }
+                __syncthreads();  // (B)
+            }
+            const float upx = sm[cur + o_up], dnx = sm[cur + o_dn];
+            float prev_old = upx;
 #pragma unroll
             for (int k = 0; k < FK; ++k) {
-                const int lr = lr0 + k;
-                const float lf = cur[lr * FSJ + cl], rt = cur[lr * FSJ + cr];
-                const float upv = k > 0 ? p[k - 1] : upx;
+                const int o = o0 + k * FSJ;
+                const float lf = sm[cur + o + dl], rt = sm[cur + o + dr];
                 const float dnv = k < FK - 1 ? p[k + 1] : dnx;
-                float sum = dnv + upv + rt + lf;  // (i+1) + (i-1) + (j+1) + (j-1), the reference's order
-                if ((slow >> k) & 1u) sum = f_slow_sum(cur, wcode, lr, c, rlo, rhi, clo, chi);
+                const float sum = dnv + prev_old + rt + lf;  // (i+1) + (i-1) + (j+1) + (j-1), the reference's order
                 const float v = 0.25f * sum + t2[k] - t3[k];
-                np[k] = ((upd >> k) & 1u) ? v : p[k];
+                prev_old = p[k];
+                p[k] = ((upd >> k) & 1u) ? v : p[k];
+            }
+            if (slow) {
+#pragma unroll
+                for (int k = 0; k < FK; ++k)
+                    if ((slow >> k) & 1u) p[k] = 0.25f * sm[nxt + o0 + k * FSJ] + t2[k] - t3[k];
             }
 #pragma unroll
-            for (int k = 0; k < FK; ++k) {
-                p[k] = np[k];
-                nxt[(lr0 + k) * FSJ + c] = np[k];
-            }
+            for (int k = 0; k < FK; ++k) sm[nxt + o0 + k * FSJ] = p[k];
             cur = nxt;
-            nxt = (nxt == w0) ? w1 : w0;
-        }
-        if (g.T == 1) {  // staging was never released inside the loop
-            __syncthreads();
-            if (leader && t + (int)gridDim.x < n_tiles) FS2D_ISSUE(t + (int)gridDim.x);
+            nxt = (nxt == OFF_W0) ? OFF_W1 : OFF_W0;
         }
 
         // ---- store the inner (TI x TJ) cells that were updated and belong to rows [r0, r1) ----------
@@ -218,8 +243,18 @@ __global__ void __launch_bounds__(F_THREADS, 1)
                 if (lr >= g.T && lr < g.T + g.TI && gr < d.r1 && ((upd >> k) & 1u)) p_out[(size_t)gr * d.Y + (C0 + c)] = p[k];
             }
         }
-        __syncthreads();  // all reads of the working planes done before the next tile overwrites them
+        __syncthreads();  // all reads of the working planes are done before the next tile overwrites them
+        if (g.T == 1) {   // the staging plane doubled as the only `cur` plane: release it only now
+            if (leader) {
+                const int tn = (int)atomicAdd(tile_ctr, 1u) + (int)gridDim.x;
+                s_next = tn;
+                if (tn < n_tiles) FS2D_ISSUE(tn);
+            }
+            __syncthreads();
+        }
+        t = s_next;
     }
+#undef FS2D_ISSUE
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -293,8 +328,11 @@ int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t 
     g.tiles_j = (d.Y + g.TJ - 1) / g.TJ;
     const int n_tiles = g.tiles_i * g.tiles_j;
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
+    static unsigned int *ctr = nullptr;   // dynamic tile scheduler: tiles next to walls cost more than open-fluid tiles
+    if (!ctr) FS2D_CUDA_CHECK(cudaMalloc(&ctr, sizeof(unsigned int)));
+    FS2D_CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), s));
     ++g_launches;
-    k_jacobi_fused<<<grid, dim3(FSJ, FNTY, 1), F_SMEM, s>>>(mp, ms, mc, p_out, d, g);
+    k_jacobi_fused<<<grid, dim3(FSJ, FNTY, 1), F_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);
     return FS2D_OK;
 }
 
