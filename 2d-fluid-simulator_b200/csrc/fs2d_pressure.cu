@@ -222,6 +222,58 @@ int fs2d_jacobi_sweep(float *pn, const float *pc, const float *src, const uint8_
     return FS2D_OK;
 }
 
+// Decompose n_sweeps reference iterations into fused passes (size t >= 1, only sizes whose bit is set in
+// fuse_mask) and literal single iterations (size 0), cheapest first by a cost table measured on B200 at
+// 8192^2 cells (scripts/sweep_bench.py, us): the last two iterations are always literal and the
+// number of buffer flips (= number of entries) must have the parity of n_sweeps so that the two PHYSICAL
+// buffers end up exactly as in the reference.
+static int plan_jacobi(int n_sweeps, int fuse_mask, int *out, int cap) {
+    static const float pass_cost[13] = {0, 362, 371, 393, 457, 550, 633, 718, 803, 945, 1087, 1212, 1336};
+    const float lit_cost = 195.0f;
+    const int n_lit = n_sweeps < 2 ? n_sweeps : 2, n_f = n_sweeps - n_lit;
+    int n = 0;
+    if (n_f > 0 && (fuse_mask & 0x1FFE) && n_f < 4096) {
+        // dp[i][par]: cheapest way to do i iterations with an entry count of parity par
+        static thread_local float dp[4097][2];
+        static thread_local short choice[4097][2];
+        const float INF = 1e30f;
+        dp[0][0] = 0; dp[0][1] = INF;
+        for (int i = 1; i <= n_f; ++i)
+            for (int par = 0; par < 2; ++par) {
+                float best = dp[i - 1][par ^ 1] + lit_cost;   // one literal iteration
+                short ch = 0;
+                for (int t = 1; t <= 12 && t <= i; ++t)
+                    if ((fuse_mask >> t) & 1) {
+                        const float cst = dp[i - t][par ^ 1] + pass_cost[t];
+                        if (cst < best) { best = cst; ch = (short)t; }
+                    }
+                dp[i][par] = best;
+                choice[i][par] = ch;
+            }
+        int par = n_f & 1, i = n_f;
+        if (dp[i][par] >= INF) return -1;
+        while (i > 0) {
+            const int t = choice[i][par];
+            if (n >= cap) return -1;
+            out[n++] = t;
+            i -= t ? t : 1;
+            par ^= 1;
+        }
+    } else {
+        for (int i = 0; i < n_f; ++i) { if (n >= cap) return -1; out[n++] = 0; }
+    }
+    for (int i = 0; i < n_lit; ++i) { if (n >= cap) return -1; out[n++] = 0; }
+    return n;
+}
+
+int fs2d_jacobi_plan(int n_sweeps, int fuse_mask, int *sizes, int cap, int *n_entries) {
+    FS2D_REQUIRE(n_sweeps >= 0 && fuse_mask >= 0 && sizes && n_entries && cap > 0, "bad plan arguments");
+    const int n = plan_jacobi(n_sweeps, fuse_mask, sizes, cap);
+    FS2D_REQUIRE(n >= 0, "plan does not fit the output array");
+    *n_entries = n;
+    return FS2D_OK;
+}
+
 int fs2d_jacobi_update(float *pa, float *pb, const float *src, const uint8_t *pcode, fs2d_dom d, int n_sweeps,
                        const int32_t *tgt, const int32_t *src0, const int32_t *src1, const uint8_t *kind, float *scratch,
                        int n_bc, int fuse_mask, int *final_in_b, void *stream) {
@@ -230,34 +282,19 @@ int fs2d_jacobi_update(float *pa, float *pb, const float *src, const uint8_t *pc
     FS2D_REQUIRE(n_bc == 0 || (tgt && src0 && src1 && kind && scratch), "null BC table");
     if (int e = check_dom(d)) return e;
     float *cur = pa, *nxt = pb;
-    // Fused passes (temporal blocking, fs2d_fused.cu) for all but the last two iterations; the last two run
-    // literally so that the BC cells of BOTH buffers end up exactly as the reference leaves them.
-    // fuse_mask bit t (1 <= t <= 12) says the host validated a pass of t iterations for this mask.  The
-    // number of buffer flips must have the parity of n_sweeps so that the physical buffers end up as in the
-    // reference: q passes of t* + r single sweeps flip q + r times for q*t* + r iterations.
-    int n_lit = n_sweeps < 2 ? n_sweeps : 2, n_f = n_sweeps - n_lit, q = 0, tstar = 0;
-    if (fuse_mask > 0 && n_f > 0 && d.r1 > d.r0 && fused_supported(pa, pb, src, pcode, d)) {
-        for (int t = 12; t >= 1 && !tstar; --t)            // largest validated odd size (parity-neutral) ...
-            if ((fuse_mask >> t) & 1 && (t & 1) && t <= n_f) tstar = t;
-        for (int t = 12; t >= 1; --t)                      // ... unless an even one is at least 2 larger
-            if ((fuse_mask >> t) & 1 && !(t & 1) && t <= n_f && t > tstar + 1) { tstar = t; break; }
-    }
-    if (tstar) {
-        q = n_f / tstar;
-        if (!(tstar & 1) && (q & 1)) --q;                  // even pass size: keep the flip parity right
-    }
-    n_lit = n_sweeps - q * tstar;
-    for (int k = 0; k < q; ++k) {
-        if (int e = fused_pass(cur, nxt, src, pcode, d, tstar, STREAM)) return e;
-        float *x = cur; cur = nxt; nxt = x;
-    }
-    for (int s = 0; s < n_lit; ++s) {
-        // Literal reference iteration (fs/pressure_updater.py:57-60): in-place sparse BC (two tiny gather /
-        // scatter launches over the ~0.1 % BC cells), then the plain 5-point sweep.  Measured on B200 at
-        // 8192^2: plain sweep 187 us (6.1 TB/s of traffic) + 8 us of BC, vs 320 us for a sweep that
-        // recomputes BC values inline (its divergent slow path hits every warp touching a wall face).
-        launch_p_bc(cur, tgt, src0, src1, kind, scratch, n_bc, STREAM);
-        if (d.r1 > d.r0) launch_jacobi(nxt, cur, src, pcode, d, 0, STREAM);
+    if (d.r1 == d.r0 || !fused_supported(pa, pb, src, pcode, d)) fuse_mask = 0;
+    static thread_local int plan[4200];
+    const int n = plan_jacobi(n_sweeps, fuse_mask, plan, 4200);
+    FS2D_REQUIRE(n >= 0, "iteration count too large");
+    for (int k = 0; k < n; ++k) {
+        if (plan[k] > 0) {
+            // fused pass: plan[k] iterations in shared memory (fs2d_fused.cu)
+            if (int e = fused_pass(cur, nxt, src, pcode, d, plan[k], STREAM)) return e;
+        } else {
+            // literal reference iteration (fs/pressure_updater.py:57-60): in-place sparse BC, then the plain sweep
+            launch_p_bc(cur, tgt, src0, src1, kind, scratch, n_bc, STREAM);
+            if (d.r1 > d.r0) launch_jacobi(nxt, cur, src, pcode, d, 0, STREAM);
+        }
         float *x = cur; cur = nxt; nxt = x;
     }
     FS2D_LAUNCH_CHECK();

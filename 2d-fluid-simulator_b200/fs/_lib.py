@@ -50,6 +50,7 @@ _SIGNATURES = {
     "fs2d_pressure_source": (c_int, [_P, _P, Dom, c_float, c_float, _P]),
     "fs2d_jacobi_sweep": (c_int, [_P, _P, _P, _P, Dom, c_int, _P]),
     "fs2d_jacobi_update": (c_int, [_P, _P, _P, _P, Dom, c_int, _P, _P, _P, _P, _P, c_int, c_int, POINTER(c_int), _P]),
+    "fs2d_jacobi_plan": (c_int, [c_int, c_int, POINTER(c_int), c_int, POINTER(c_int)]),
     "fs2d_jacobi_fused": (c_int, [_P, _P, _P, _P, Dom, c_int, _P]),
     "fs2d_fused_tile": (c_int, [c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "fs2d_rbsor_pass": (c_int, [_P, _P, _P, _P, Dom, c_float, c_float, c_int, _P]),

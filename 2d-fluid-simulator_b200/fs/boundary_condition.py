@@ -118,7 +118,7 @@ class BoundaryCondition:
                       ctypes.byref(tmax))
             g0, g1 = self.partition.owned()
             ok = (1 <= T <= tmax.value and self._global_resolution[1] % 16 == 0 and self._p_table["feed"]["n"] == 0
-                  and (self.partition.world == 1 or self.halo >= T)
+                  and (self.partition.world == 1 or self.halo >= T + 1)
                   and _bc_tables.fused_reach_ok(self._pcode_global, T, rows.value, cols.value, hr.value, hc.value, g0, g1))
             self._fused_ok[T] = bool(ok)
         return self._fused_ok[T]

@@ -76,16 +76,23 @@ def vorticity_apply_distributed(vc, v: DoubleBuffer) -> None:
 
 
 def jacobi_update_distributed(jac, p: DoubleBuffer, v_current: Field) -> None:
-    """fs/pressure_updater.py:56-60 on a strip: one 2-row SendRecv of p per sweep (row g0-1 is read by
-    the stencil, row g0-2 by the inline BC of row g0-1)."""
+    """fs/pressure_updater.py:56-60 on a strip.  Same schedule as fs2d_jacobi_update: a fused pass of t
+    iterations needs t fresh halo rows of p (one SendRecv per PASS instead of per iteration) and the source
+    terms on those rows; a literal iteration needs 2 (row g0-1 for the stencil, g0-2 for the BC of row g0-1)."""
     bc = jac._bc
     hx = exchanger_for(bc)
-    hx.exchange(v_current, 1)
-    src = jac._source(v_current)
-    for _ in range(jac._n_iter):
-        hx.exchange(p.current, 2)
-        bc.set_pressure_boundary_condition(p.current)       # owned rows and the first halo row
-        jac._sweep(p.next, p.current, src, inline_bc=False)
+    plan = jac.plan(p)
+    reach = max([t for t in plan if t > 0], default=0)
+    hx.exchange(v_current, min(bc.halo, reach + 1))
+    src = jac._source(v_current, dom=_extended(bc, reach))        # source terms also on the halo rows a pass reads
+    for t in plan:
+        if t > 0:
+            hx.exchange(p.current, t)
+            jac._fused(p.next, p.current, src, t)
+        else:
+            hx.exchange(p.current, 2)
+            bc.set_pressure_boundary_condition(p.current)       # owned rows and the first halo row
+            jac._sweep(p.next, p.current, src, inline_bc=False)
         p.swap()
 
 

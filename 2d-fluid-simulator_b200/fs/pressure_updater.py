@@ -46,7 +46,7 @@ class JacobiPressureUpdater(PressureUpdater):
     shared-memory kernel (fs2d_jacobi_fused); "auto" picks FUSE_DEFAULT when the mask qualifies, 0 disables.
     Results are bit-identical either way."""
 
-    FUSE_DEFAULT = 5
+    FUSE_DEFAULT = 8
 
     def __init__(self, boundary_condition: BoundaryCondition, dt: float, dx: float, n_iter: int,
                  fuse: int | str = "auto") -> None:
@@ -72,15 +72,38 @@ class JacobiPressureUpdater(PressureUpdater):
             req = self._fuse_request
             t_max = self.FUSE_DEFAULT if req == "auto" else int(req)
             self._fuse_t = sum(1 << t for t in range(1, t_max + 1) if self._bc.fused_ok(t)) if t_max > 0 else 0
-        if self._fuse_t == 0:
+        if self._fuse_t == 0 and self._bc.partition.world == 1:
             return 0
         key = (id(p.current), id(p.next))
         if self._stale_checked != key or p.current.dirty or p.next.dirty:
             # never-written wall cells must agree between the two physical buffers (DESIGN.md "stale cells")
-            self._stale_ok = self._bc.stale_cells_agree(p.current, p.next)
+            ok = self._bc.stale_cells_agree(p.current, p.next)
+            if self._bc.partition.world > 1:
+                # every rank must follow the same schedule (its halo exchanges pair up): agree on the verdict.
+                # Setup-time only -- runs again only after user code rewrites a pressure buffer from the host.
+                import torch
+                import torch.distributed as dist
+
+                verdict = torch.tensor([self._fuse_t if ok else 0], dtype=torch.int32, device=p.current.tensor.device)
+                dist.all_reduce(verdict, op=dist.ReduceOp.BAND)
+                self._agreed_mask = int(verdict.item())
+            else:
+                self._agreed_mask = self._fuse_t if ok else 0
             self._stale_checked = key
             p.current.dirty = p.next.dirty = False
-        return self._fuse_t if self._stale_ok else 0
+        return self._agreed_mask
+
+    def plan(self, p: DoubleBuffer) -> list[int]:
+        """Schedule of one update: fused pass sizes (> 0) and literal iterations (0), fs2d_jacobi_plan."""
+        cap = self._n_iter + 4
+        sizes, n = (ctypes.c_int * cap)(), ctypes.c_int(0)
+        _lib.call("fs2d_jacobi_plan", self._n_iter, self.fuse_mask(p), sizes, cap, ctypes.byref(n))
+        return list(sizes[:n.value])
+
+    def _fused(self, p_next: Field, p_current: Field, src: Field, t: int) -> None:
+        bc = self._bc
+        _lib.call("fs2d_jacobi_fused", p_next.ptr(), p_current.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom, t,
+                  _lib.stream())
 
     def update(self, p: DoubleBuffer, v_current: Field) -> None:
         bc = self._bc

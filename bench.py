@@ -181,7 +181,7 @@ def run_ours(a: argparse.Namespace) -> None:
     X, Y = a.rows_per_gpu * world, a.cols
     dt, dx = 0.05 / Y_COLS, 1.0 / Y_COLS
     const, mask = build_scene(SCENE, X, Y)
-    part = Partition(X, rank, world, 0 if world == 1 else 2)
+    part = Partition(X, rank, world, 0 if world == 1 else 9)   # halo 9: fused Jacobi passes of up to 8 iterations
     bc = BoundaryCondition(const, mask, partition=part)
     del const, mask
     solver = make_solver(bc, dt, dx, RE, VC, SCHEME, pressure="jacobi", n_iter=a.jacobi)

@@ -131,6 +131,10 @@ int fs2d_jacobi_sweep(float *pn, const float *pc, const float *src, const uint8_
 int fs2d_jacobi_update(float *pa, float *pb, const float *src, const uint8_t *pcode, fs2d_dom d, int n_sweeps,
                        const int32_t *tgt, const int32_t *src0, const int32_t *src1, const uint8_t *kind, float *scratch,
                        int n_bc, int fuse_mask, int *final_in_b, void *stream);
+/* The schedule fs2d_jacobi_update uses: sizes[k] > 0 = one fused pass of that many iterations, 0 = one literal
+ * iteration {fs2d_pressure_bc, fs2d_jacobi_sweep}; every entry flips the buffers once.  (A multi-rank host runs
+ * the same schedule with a halo exchange in front of every entry.) */
+int fs2d_jacobi_plan(int n_sweeps, int fuse_mask, int *sizes, int cap, int *n_entries);
 /* One fused pass: T reference iterations {BC, sweep} computed in shared memory, p_in -> relaxed cells of
  * p_out (rows [r0, r1)); bit-identical to T calls of fs2d_pressure_bc + fs2d_jacobi_sweep on the relaxed
  * cells.  BC cells of p_in/p_out are neither read nor written (their values are recomputed from pcode).

@@ -32,6 +32,9 @@ CASES = [
     (1, 128, 64, "upwind", None, dict(pressure="jacobi", n_iter=3), 4, 3),
     (4, 96, 48, "cip", 2.0, dict(pressure="rbsor", n_iter=3), 3, 4),
     (2, 1024, 512, "cip", 5.0, dict(pressure="jacobi", n_iter=8), 2, 2),
+    (2, 1024, 512, "cip", 5.0, dict(pressure="jacobi", n_iter=40), 2, 9),      # fused passes of 8 across the strip edge
+    (5, 384, 192, "cip", 5.0, dict(pressure="jacobi", n_iter=21), 3, 6),       # odd count, passes of <= 5
+    (3, 640, 320, "upwind", None, dict(pressure="jacobi", n_iter=30), 2, 9),
 ]
 
 
