@@ -84,9 +84,10 @@ class JacobiPressureUpdater(PressureUpdater):
                 import torch
                 import torch.distributed as dist
 
-                verdict = torch.tensor([self._fuse_t if ok else 0], dtype=torch.int32, device=p.current.tensor.device)
-                dist.all_reduce(verdict, op=dist.ReduceOp.BAND)
-                self._agreed_mask = int(verdict.item())
+                mine = self._fuse_t if ok else 0
+                bits = torch.tensor([(mine >> t) & 1 for t in range(13)], dtype=torch.int32, device=p.current.tensor.device)
+                dist.all_reduce(bits, op=dist.ReduceOp.MIN)     # bitwise AND across ranks (NCCL has no BAND)
+                self._agreed_mask = sum(int(b) << t for t, b in enumerate(bits.tolist()))
             else:
                 self._agreed_mask = self._fuse_t if ok else 0
             self._stale_checked = key
