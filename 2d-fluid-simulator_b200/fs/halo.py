@@ -46,13 +46,11 @@ class HaloExchanger:
         self.bytes_sent += sum(op.tensor.numel() * op.tensor.element_size() for op in ops[::2])
 
 
-_EXCHANGERS: dict[int, HaloExchanger] = {}
-
-
 def exchanger_for(bc) -> HaloExchanger:
-    hx = _EXCHANGERS.get(id(bc))
+    """The (single) exchanger of a BoundaryCondition; kept on the object so its lifetime follows the partition."""
+    hx = getattr(bc, "_halo_exchanger", None)
     if hx is None:
-        hx = _EXCHANGERS[id(bc)] = HaloExchanger(bc.partition)
+        hx = bc._halo_exchanger = HaloExchanger(bc.partition)
     return hx
 
 
