@@ -12,7 +12,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k
     python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 tail -3 gpurun_out/ncu_bench.log
 echo "== ncu full (jacobi)"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_jacobi_march -s 20 -c 2 -f -o gpurun_out/jacobi_full \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_jacobi_fused -s 4 -c 2 -f -o gpurun_out/jacobi_full \
     python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
 ls -la gpurun_out
