@@ -1,0 +1,257 @@
+// fs2d_dye.cu -- dye transport: the reference's Dye solvers run the same stencils on
+// 3-channel AoS fields (fs/solver.py:110-161, :335-401).  Kernels here are generic in the channel count C
+// (scalar loads per component, same per-component operation order as the float2 kernels in
+// fs2d_kernels.cu), instantiated for C = 3.  Dye is off the benchmark path (`-no_dye`), so these favour
+// clarity over vectorisation; they are still bit-identical to the oracle.
+#include "fs2d_common.cuh"
+
+namespace fs2d {
+
+template <int C>
+__device__ __forceinline__ float ldc(const float *f, const fs2d_dom &d, int r, int j, int c) {
+    return __ldg(f + (size_t)C * IX(d, CR(d, r), CJ(d, j)) + c);
+}
+
+// fs/boundary_condition.py:94-99  set_dye_boundary_condition: dye = bc_dye on inflow cells (sparse list)
+__global__ void k_dye_bc(float *__restrict__ dye, const float *__restrict__ bc_dye, const int32_t *__restrict__ tgt, int n) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const size_t o = 3 * (size_t)tgt[e];
+    dye[o] = bc_dye[o];
+    dye[o + 1] = bc_dye[o + 1];
+    dye[o + 2] = bc_dye[o + 2];
+}
+
+// fs/solver.py:46-49  clamp_field (all cells, all components)
+__global__ void __launch_bounds__(256) k_clamp(float *__restrict__ f, size_t begin, size_t end, float low, float high) {
+    const size_t k = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < end) f[k] = fminf(fmaxf(f[k], low), high);
+}
+
+// fs/solver.py:157-161  DyeMacSolver._update_dye: dn = dc - dt * advect(vc, dc)   (fluid cells)
+template <bool P2, int SCHEME, int C>
+__global__ void __launch_bounds__(TX *TY)
+    k_dye_mac(float *__restrict__ dn, const float *__restrict__ dc, const float *__restrict__ vc,
+              const uint8_t *__restrict__ mask, fs2d_dom d, float dt, float dx, DivC<P2> ddx) {
+    FS2D_CELL(d, r, j)
+    const size_t idx = IX(d, r, j);
+    if (mask[idx] != 0) return;
+    const float2 vel = __ldg(reinterpret_cast<const float2 *>(vc) + idx);
+    const float six_dx = 6.0f * dx;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        float adv;
+        if (SCHEME == FS2D_SCHEME_UPWIND) {  // fs/advection.py:12-24
+            int k = vel.x < 0.0f ? r : r - 1;
+            const float a = vel.x * ddx(ldc<C>(dc, d, k + 1, j, c) - ldc<C>(dc, d, k, j, c));
+            k = vel.y < 0.0f ? j : j - 1;
+            const float b = vel.y * ddx(ldc<C>(dc, d, r, k + 1, c) - ldc<C>(dc, d, r, k, c));
+            adv = a + b;
+        } else {  // fs/advection.py:27-60
+            float k0, k1, k2, k3, k4;
+            if (vel.x < 0.0f) { k0 = -2.0f; k1 = 10.0f; k2 = -9.0f; k3 = 2.0f; k4 = -1.0f; }
+            else { k0 = 1.0f; k1 = -2.0f; k2 = 9.0f; k3 = -10.0f; k4 = 2.0f; }
+            float acc = ldc<C>(dc, d, r + 2, j, c) * k0;
+            acc = acc + ldc<C>(dc, d, r + 1, j, c) * k1;
+            acc = acc + ldc<C>(dc, d, r, j, c) * k2;
+            acc = acc + ldc<C>(dc, d, r - 1, j, c) * k3;
+            acc = acc + ldc<C>(dc, d, r - 2, j, c) * k4;
+            const float a = acc / six_dx;
+            if (vel.y < 0.0f) { k0 = -2.0f; k1 = 10.0f; k2 = -9.0f; k3 = 2.0f; k4 = -1.0f; }
+            else { k0 = 1.0f; k1 = -2.0f; k2 = 9.0f; k3 = -10.0f; k4 = 2.0f; }
+            acc = ldc<C>(dc, d, r, j + 2, c) * k0;
+            acc = acc + ldc<C>(dc, d, r, j + 1, c) * k1;
+            acc = acc + ldc<C>(dc, d, r, j, c) * k2;
+            acc = acc + ldc<C>(dc, d, r, j - 1, c) * k3;
+            acc = acc + ldc<C>(dc, d, r, j - 2, c) * k4;
+            const float b = acc / six_dx;
+            adv = vel.x * a + vel.y * b;
+        }
+        dn[C * idx + c] = __ldg(dc + C * idx + c) - dt * adv;
+    }
+}
+
+// fs/solver.py:378-383  _non_advection_phase_dye: dn = dc + diffusion(dc) * dt   (not-wall cells)
+template <bool P2, int C>
+__global__ void __launch_bounds__(TX *TY)
+    k_dye_nonadv(float *__restrict__ dn, const float *__restrict__ dc, const uint8_t *__restrict__ mask, fs2d_dom d,
+                 float dt, DivC<P2> ddx2, float re) {
+    FS2D_CELL(d, r, j)
+    const size_t idx = IX(d, r, j);
+    if (mask[idx] == 1) return;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const float cc = __ldg(dc + C * idx + c);
+        const float d2x = ddx2(ldc<C>(dc, d, r + 1, j, c) - 2.0f * cc + ldc<C>(dc, d, r - 1, j, c));
+        const float d2y = ddx2(ldc<C>(dc, d, r, j + 1, c) - 2.0f * cc + ldc<C>(dc, d, r, j - 1, c));
+        dn[C * idx + c] = cc + (d2x + d2y) / re * dt;
+    }
+}
+
+// fs/solver.py:242-261  _non_advection_phase_grad on C channels
+template <bool P2, int C>
+__global__ void __launch_bounds__(TX *TY)
+    k_nonadv_grad_n(float *__restrict__ fxn, float *__restrict__ fyn, const float *__restrict__ fxc,
+                    const float *__restrict__ fyc, const float *__restrict__ fc, const float *__restrict__ fn,
+                    const uint8_t *__restrict__ mask, fs2d_dom d, DivC<P2> d2dx) {
+    FS2D_CELL(d, r, j)
+    const size_t idx = IX(d, r, j);
+    if (mask[idx] == 1) return;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const float gx = ldc<C>(fn, d, r + 1, j, c) - ldc<C>(fc, d, r + 1, j, c) - ldc<C>(fn, d, r - 1, j, c) + ldc<C>(fc, d, r - 1, j, c);
+        const float gy = ldc<C>(fn, d, r, j + 1, c) - ldc<C>(fc, d, r, j + 1, c) - ldc<C>(fn, d, r, j - 1, c) + ldc<C>(fc, d, r, j - 1, c);
+        fxn[C * idx + c] = __ldg(fxc + C * idx + c) + d2dx(gx);
+        fyn[C * idx + c] = __ldg(fyc + C * idx + c) + d2dx(gy);
+    }
+}
+
+// fs/solver.py:267-332  _advection_phase/_cip_advect on C channels, advecting velocity v (float2)
+template <bool P2, int C>
+__global__ void __launch_bounds__(TX *TY)
+    k_cip_advect_n(float *__restrict__ fn, float *__restrict__ fxn, float *__restrict__ fyn,
+                   const float *__restrict__ fc, const float *__restrict__ fxc, const float *__restrict__ fyc,
+                   const float *__restrict__ v, const uint8_t *__restrict__ mask, fs2d_dom d, float dt, float dx,
+                   DivC<P2> ddx, float dx2, float dx3) {
+    FS2D_CELL(d, r, j)
+    const size_t idx = IX(d, r, j);
+    if (mask[idx] != 0) return;
+    const float2 vel = __ldg(reinterpret_cast<const float2 *>(v) + idx);
+    const float i_s = sign1(vel.x), j_s = sign1(vel.y);
+    const int r_m = r - (int)i_s, j_m = j - (int)j_s;
+    const DivC<P2> disd(i_s * dx3), djsd(j_s * dx3), ddx2(dx2), disdx(i_s * dx);
+    const float Xd = -vel.x * dt, Yd = -vel.y * dt;
+    const float2 dxv = ddx(0.5f * (ld2(v, d, r + 1, j) - ld2(v, d, r - 1, j)));
+    const float2 dyv = ddx(0.5f * (ld2(v, d, r, j + 1) - ld2(v, d, r, j - 1)));
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const float f00 = ldc<C>(fc, d, r, j, c), f0m = ldc<C>(fc, d, r, j_m, c), fm0 = ldc<C>(fc, d, r_m, j, c), fmm = ldc<C>(fc, d, r_m, j_m, c);
+        const float x00 = ldc<C>(fxc, d, r, j, c), x0m = ldc<C>(fxc, d, r, j_m, c), xm0 = ldc<C>(fxc, d, r_m, j, c);
+        const float y00 = ldc<C>(fyc, d, r, j, c), y0m = ldc<C>(fyc, d, r, j_m, c), ym0 = ldc<C>(fyc, d, r_m, j, c);
+        const float tmp1 = f00 - f0m - fm0 + fmm;
+        const float tmp2 = fm0 - f00;
+        const float tmp3 = f0m - f00;
+        const float a = disd(i_s * (xm0 + x00) * dx - 2.0f * (-tmp2));
+        const float b = djsd(j_s * (y0m + y00) * dx - 2.0f * (-tmp3));
+        const float cc = djsd(-tmp1 - i_s * (x0m - x00) * dx);
+        const float dd = disd(-tmp1 - j_s * (ym0 - y00) * dx);
+        const float e = ddx2(3.0f * tmp2 + i_s * (xm0 + 2.0f * x00) * dx);
+        const float f = ddx2(3.0f * tmp3 + j_s * (y0m + 2.0f * y00) * dx);
+        const float g = disdx(-(ym0 - y00) + cc * dx2);
+        fn[C * idx + c] = ((a * Xd + cc * Yd + e) * Xd + g * Yd + x00) * Xd + ((b * Yd + dd * Xd + f) * Yd + y00) * Yd + f00;
+        const float Fx = (3.0f * a * Xd + 2.0f * cc * Yd + 2.0f * e) * Xd + (dd * Yd + g) * Yd + x00;
+        const float Fy = (3.0f * b * Yd + 2.0f * dd * Xd + 2.0f * f) * Yd + (cc * Xd + g) * Xd + y00;
+        fxn[C * idx + c] = Fx - dt * (Fx * dxv.x + Fy * dxv.y) / 2.0f;
+        fyn[C * idx + c] = Fy - dt * (Fx * dyv.x + Fy * dyv.y) / 2.0f;
+    }
+}
+
+// fs/solver.py:207-211  _set_grad on C channels
+template <bool P2, int C>
+__global__ void __launch_bounds__(TX *TY)
+    k_set_grad_n(float *__restrict__ fx, float *__restrict__ fy, const float *__restrict__ f, fs2d_dom d, DivC<P2> ddx) {
+    FS2D_CELL(d, r, j)
+    const size_t idx = IX(d, r, j);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        fx[C * idx + c] = ddx(0.5f * (ldc<C>(f, d, r + 1, j, c) - ldc<C>(f, d, r - 1, j, c)));
+        fy[C * idx + c] = ddx(0.5f * (ldc<C>(f, d, r, j + 1, c) - ldc<C>(f, d, r, j - 1, c)));
+    }
+}
+
+}  // namespace fs2d
+
+using namespace fs2d;
+#define STREAM ((cudaStream_t)stream)
+#define P2_DISPATCH(p2, T, F) \
+    do {                      \
+        ++g_launches;         \
+        if (p2) { T; } else { F; } \
+    } while (0)
+
+extern "C" {
+
+int fs2d_dye_bc(float *dye, const float *bc_dye, const int32_t *tgt, int n, void *stream) {
+    if (n == 0) return FS2D_OK;
+    FS2D_REQUIRE(dye && bc_dye && tgt && n > 0, "null table/field pointer");
+    ++g_launches;
+    k_dye_bc<<<nblk(n, 256), 256, 0, STREAM>>>(dye, bc_dye, tgt, n);
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+int fs2d_clamp(float *f, fs2d_dom d, int channels, float low, float high, void *stream) {
+    FS2D_REQUIRE(f && channels >= 1, "null field pointer");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+    const size_t begin = (size_t)d.r0 * d.Y * channels, end = (size_t)d.r1 * d.Y * channels;
+    ++g_launches;
+    k_clamp<<<(unsigned)((end - begin + 255) / 256), 256, 0, STREAM>>>(f, begin, end, low, high);
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+int fs2d_dye_mac(float *dn, const float *dc, const float *vc, const uint8_t *mask, fs2d_dom d, float dt, float dx, int scheme,
+                 void *stream) {
+    FS2D_REQUIRE(dn && dc && vc && mask, "null field pointer");
+    FS2D_REQUIRE(scheme == FS2D_SCHEME_UPWIND || scheme == FS2D_SCHEME_KK, "unknown advection scheme");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+#define DM(P2, S) k_dye_mac<P2, S, 3><<<dense_grid(d), dense_block(), 0, STREAM>>>(dn, dc, vc, mask, d, dt, dx, DivC<P2>(dx))
+    if (scheme == FS2D_SCHEME_UPWIND) P2_DISPATCH(is_pow2(dx), DM(true, FS2D_SCHEME_UPWIND), DM(false, FS2D_SCHEME_UPWIND));
+    else P2_DISPATCH(is_pow2(dx), DM(true, FS2D_SCHEME_KK), DM(false, FS2D_SCHEME_KK));
+#undef DM
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+int fs2d_dye_nonadv(float *dn, const float *dc, const uint8_t *mask, fs2d_dom d, float dt, float dx, float re, void *stream) {
+    FS2D_REQUIRE(dn && dc && mask, "null field pointer");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+    const float dx2 = dx * dx;
+#define DN(P2) k_dye_nonadv<P2, 3><<<dense_grid(d), dense_block(), 0, STREAM>>>(dn, dc, mask, d, dt, DivC<P2>(dx2), re)
+    P2_DISPATCH(is_pow2(dx), DN(true), DN(false));
+#undef DN
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+int fs2d_dye_nonadv_grad(float *fxn, float *fyn, const float *fxc, const float *fyc, const float *fc, const float *fn,
+                         const uint8_t *mask, fs2d_dom d, float two_dx, void *stream) {
+    FS2D_REQUIRE(fxn && fyn && fxc && fyc && fc && fn && mask, "null field pointer");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+#define NG(P2) k_nonadv_grad_n<P2, 3><<<dense_grid(d), dense_block(), 0, STREAM>>>(fxn, fyn, fxc, fyc, fc, fn, mask, d, DivC<P2>(two_dx))
+    P2_DISPATCH(is_pow2(two_dx), NG(true), NG(false));
+#undef NG
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+int fs2d_dye_cip_advect(float *fn, float *fxn, float *fyn, const float *fc, const float *fxc, const float *fyc,
+                        const float *v, const uint8_t *mask, fs2d_dom d, float dt, float dx, float dx2, float dx3,
+                        void *stream) {
+    FS2D_REQUIRE(fn && fxn && fyn && fc && fxc && fyc && v && mask, "null field pointer");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+    const bool p2 = is_pow2(dx) && is_pow2(dx2) && is_pow2(dx3);
+#define CA(P2) k_cip_advect_n<P2, 3><<<dense_grid(d), dense_block(), 0, STREAM>>>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, DivC<P2>(dx), dx2, dx3)
+    P2_DISPATCH(p2, CA(true), CA(false));
+#undef CA
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+int fs2d_dye_set_grad(float *fx, float *fy, const float *f, fs2d_dom d, float dx, void *stream) {
+    FS2D_REQUIRE(fx && fy && f, "null field pointer");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+#define SG(P2) k_set_grad_n<P2, 3><<<dense_grid(d), dense_block(), 0, STREAM>>>(fx, fy, f, d, DivC<P2>(dx))
+    P2_DISPATCH(is_pow2(dx), SG(true), SG(false));
+#undef SG
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+}  // extern "C"

@@ -132,6 +132,27 @@ class BoundaryCondition:
         return bool(torch.equal(fa, fb))
 
 
+class DyeBoundaryCondition(BoundaryCondition):
+    """(:88-112) adds the inflow dye colours bc_dye (X, Y, 3) f32 and set_dye_boundary_condition."""
+
+    def __init__(self, bc_const: npt.NDArray, bc_dye: npt.NDArray, bc_mask: npt.NDArray, device=None, partition=None) -> None:
+        super().__init__(bc_const, bc_mask, device=device, partition=partition)
+        bc_dye = np.ascontiguousarray(bc_dye, dtype=np.float32)
+        if bc_dye.shape != tuple(self._global_resolution) + (3,):
+            raise ValueError(f"bc_dye {bc_dye.shape} does not match the mask {self._global_resolution}")
+        X, Y = self._global_resolution
+        w0, w1 = self.partition.window()
+        lo, hi = max(w0, 0), min(w1, X)
+        loc = torch.zeros((w1 - w0, Y, 3), dtype=torch.float32, device=self.device)
+        loc[lo - w0:hi - w0] = torch.from_numpy(bc_dye[lo:hi]).to(self.device)
+        self._bc_dye = loc.contiguous()
+        self._dye_tgt = torch.nonzero((self._bc_mask == INFLOW).flatten(), as_tuple=True)[0].to(torch.int32).contiguous()
+
+    def set_dye_boundary_condition(self, dye: Field) -> None:
+        _lib.call("fs2d_dye_bc", dye.ptr(), _lib.ptr(self._bc_dye), _lib.ptr(self._dye_tgt), int(self._dye_tgt.numel()),
+                  _lib.stream())
+
+
 # =================================================================================================
 # scene builders (host, NumPy)
 # =================================================================================================
@@ -187,6 +208,18 @@ def set_obstacle_fromfile(bc, bc_mask, bc_dye, filepath: Path) -> None:
         bc_dye[dark] = 0.0
 
 
+def create_color_map(color_list: list[npt.NDArray], n_samples: int) -> npt.NDArray:
+    """(:125-134) piecewise-linear colour ramp through `color_list`, n_samples x 3 (float64)."""
+    color_arr = np.vstack(color_list)
+    x = np.linspace(0.0, 1.0, color_arr.shape[0], endpoint=True)
+    x_ = np.linspace(0.0, 1.0, n_samples, endpoint=True)
+    return np.vstack([np.interp(x_, x, color_arr[:, k]) for k in range(3)]).T
+
+
+_YEL, _BLU, _RED, _CYA = (np.array(c) for c in ([1.1, 1.1, 0.2], [0.2, 0.2, 1.1], [1.1, 0.2, 0.2], [0.2, 1.1, 1.1]))
+_RAMP = [_CYA, _RED, _BLU, _YEL]
+
+
 def _inflow(bc, mask, rows, cols) -> None:
     bc[rows, cols] = np.array([1.0, 0.0], dtype=np.float32)
     mask[rows, cols] = INFLOW
@@ -197,86 +230,111 @@ def _outflow(bc, mask, rows, cols) -> None:
     mask[rows, cols] = OUTFLOW
 
 
-def _floor_ceiling(bc, mask, X, Y) -> None:
-    set_plane(bc, mask, None, (0, 0), (X, 2))
-    set_plane(bc, mask, None, (0, Y - 2), (X, Y))
+def _floor_ceiling(bc, mask, X, Y, dye=None) -> None:
+    set_plane(bc, mask, dye, (0, 0), (X, 2))
+    set_plane(bc, mask, dye, (0, Y - 2), (X, Y))
 
 
 ALL = slice(None)
 
 
-def build_scene(num: int, x_res: int, y_res: int, obstacle_image: Path | None = None):
+def build_scene(num: int, x_res: int, y_res: int, obstacle_image: Path | None = None, with_dye: bool = False):
     """(bc_const, bc_mask) of scene `num` on an x_res x y_res grid.  `create_boundary_conditionN`
     of the reference is build_scene(N, 2*res, res) (:226, 272, 326, 376, 425, 486); other aspect
     ratios are used for the weak-scaling grids."""
     X, Y = int(x_res), int(y_res)
-    bc, mask, _ = create_bc_array(X, Y)
+    bc, mask, dye = create_bc_array(X, Y)
+    if not with_dye:
+        dye = None
+
+    def two_rows(ramp):  # the same colour ramp on both inflow rows (:239, :339, :393-394, :499)
+        return np.stack((ramp, ramp), axis=0)
+
     if num == 1:                                                   # :222-265
         _inflow(bc, mask, slice(0, 2), ALL)
+        if with_dye:
+            dye[:2, :] = two_rows(create_color_map(_RAMP * 3, Y))
         _outflow(bc, mask, -1, ALL)
-        _floor_ceiling(bc, mask, X, Y)
-        set_circle(bc, mask, None, (X // 4, Y // 2), Y // 18)
+        _floor_ceiling(bc, mask, X, Y, dye)
+        set_circle(bc, mask, dye, (X // 4, Y // 2), Y // 18)
     elif num == 2:                                                 # :268-319
         _inflow(bc, mask, slice(0, 2), ALL)
-        set_plane(bc, mask, None, (0, 0), (2, Y // 3))
-        set_plane(bc, mask, None, (0, 2 * Y // 3), (2, Y))
-        set_plane(bc, mask, None, (X - 2, 0), (X, Y))
-        _floor_ceiling(bc, mask, X, Y)
+        if with_dye:
+            dye[:2, :] = np.array([0.2, 0.2, 1.2])
+            width = Y // 10
+            for i in range(0, Y, width):
+                dye[:2, i:i + width // 2] = np.array([1.2, 1.2, 0.2])
+        set_plane(bc, mask, dye, (0, 0), (2, Y // 3))
+        set_plane(bc, mask, dye, (0, 2 * Y // 3), (2, Y))
+        set_plane(bc, mask, dye, (X - 2, 0), (X, Y))
+        _floor_ceiling(bc, mask, X, Y, dye)
         xp, yp, size = X // 5, Y // 2, Y // 32
-        set_plane(bc, mask, None, (xp - size, yp), (xp + size, Y))
-        set_plane(bc, mask, None, (2 * xp - size, 0), (2 * xp + size, yp))
-        set_plane(bc, mask, None, (3 * xp - size, yp), (3 * xp + size, Y))
-        set_plane(bc, mask, None, (4 * xp - size, 0), (4 * xp + size, yp))
+        set_plane(bc, mask, dye, (xp - size, yp), (xp + size, Y))
+        set_plane(bc, mask, dye, (2 * xp - size, 0), (2 * xp + size, yp))
+        set_plane(bc, mask, dye, (3 * xp - size, yp), (3 * xp + size, Y))
+        set_plane(bc, mask, dye, (4 * xp - size, 0), (4 * xp + size, yp))
         yq = Y // 3
         _outflow(bc, mask, slice(-2, None), slice(yq, 2 * yq))
     elif num == 3:                                                 # :322-369
         _inflow(bc, mask, slice(0, 2), ALL)
+        if with_dye:
+            dye[:2, :] = two_rows(create_color_map(_RAMP, Y))
         _outflow(bc, mask, -1, ALL)
-        _floor_ceiling(bc, mask, X, Y)
+        _floor_ceiling(bc, mask, X, Y, dye)
         np.random.seed(123)  # noqa: NPY002  (legacy RNG on purpose: same stream as the reference)
         points = np.random.uniform(0, X, (100, 2))  # noqa: NPY002
         points = points[points[:, 1] < Y]
         radius = 16 * (Y / 500)
         for p in points:
-            set_circle(bc, mask, None, p, radius)
+            set_circle(bc, mask, dye, p, radius)
     elif num == 4:                                                 # :372-418
-        set_plane(bc, mask, None, (0, 0), (2, Y))
-        set_plane(bc, mask, None, (X - 2, 0), (X, Y))
-        _floor_ceiling(bc, mask, X, Y)
+        set_plane(bc, mask, dye, (0, 0), (2, Y))
+        set_plane(bc, mask, dye, (X - 2, 0), (X, Y))
+        _floor_ceiling(bc, mask, X, Y, dye)
+        if with_dye:
+            ramp = two_rows(create_color_map(_RAMP, Y // 4 - 2))
+            dye[:2, 3 * Y // 4:-2] = ramp
+            dye[:2, 2:Y // 4] = ramp
         _inflow(bc, mask, slice(0, 2), slice(3 * Y // 4, -2))
         _inflow(bc, mask, slice(0, 2), slice(2, Y // 4))
         _outflow(bc, mask, slice(-2, None), slice(3 * Y // 8, 5 * Y // 8))
     elif num == 5:                                                 # :421-479
         _inflow(bc, mask, slice(0, 2), slice(2, Y // 3))
         _inflow(bc, mask, slice(0, 2), slice(2 * Y // 3, Y - 2))
+        if with_dye:
+            dye[:2, 2:Y // 3] = np.array([1.2, 0.2, 0.2])
+            dye[:2, 2 * Y // 3:Y - 2] = np.array([0.2, 1.2, 1.2])
         _outflow(bc, mask, slice(-2, None), ALL)
-        _floor_ceiling(bc, mask, X, Y)
+        _floor_ceiling(bc, mask, X, Y, dye)
         size = X // 64
-        set_plane(bc, mask, None, (0, Y // 5), (11 * X // 30, 4 * Y // 5))
-        set_plane(bc, mask, None, (X // 2 - size, 0), (X // 2 + size, 2 * Y // 5))
-        set_plane(bc, mask, None, (X // 2 - size, 3 * Y // 5), (X // 2 + size, Y))
+        set_plane(bc, mask, dye, (0, Y // 5), (11 * X // 30, 4 * Y // 5))
+        set_plane(bc, mask, dye, (X // 2 - size, 0), (X // 2 + size, 2 * Y // 5))
+        set_plane(bc, mask, dye, (X // 2 - size, 3 * Y // 5), (X // 2 + size, Y))
         yp, half = Y // 6, np.array([Y, Y]) // 25
         for a, b in zip((7, 8, 9, 10, 11), (0, 1, 0, 1, 0), strict=True):
             for i in range(1, 6 + b):
                 p = np.array([a * X // 12, i * yp - b * Y // 12])
-                set_plane(bc, mask, None, p - half, p + half)
+                set_plane(bc, mask, dye, p - half, p + half)
     elif num == 6:                                                 # :482-524
         _inflow(bc, mask, slice(0, 2), ALL)
+        if with_dye:
+            dye[:2, :] = two_rows(create_color_map(_RAMP, Y))
         _outflow(bc, mask, -1, ALL)
-        _floor_ceiling(bc, mask, X, Y)
+        _floor_ceiling(bc, mask, X, Y, dye)
         path = obstacle_image or Path(__file__).resolve().parents[1] / "images" / "bc_mask" / "dragon.png"
         if not Path(path).exists():
             raise FileNotFoundError(f"scene 6 needs the reference's obstacle image (images/bc_mask/dragon.png); "
                                     f"not found at {path}")
-        set_obstacle_fromfile(bc, mask, None, Path(path))
+        set_obstacle_fromfile(bc, mask, dye, Path(path))
     else:
         raise NotImplementedError
-    return bc, mask
+    return (bc, mask, dye) if with_dye else (bc, mask)
 
 
 def _make(num: int, resolution: int, enable_dye: bool, **kw) -> BoundaryCondition:
     if enable_dye:
-        raise NotImplementedError("dye transport is a later hot-path row (SURVEY 8f #2)")
+        bc, mask, dye = build_scene(num, 2 * resolution, resolution, with_dye=True)
+        return DyeBoundaryCondition(bc, dye, mask, **kw)
     bc, mask = build_scene(num, 2 * resolution, resolution)
     return BoundaryCondition(bc, mask, **kw)
 

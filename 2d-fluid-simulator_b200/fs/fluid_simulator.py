@@ -14,13 +14,13 @@ import numpy.typing as npt
 from fs.advection import advect_kk_scheme, advect_upwind
 from fs.boundary_condition import BoundaryCondition, get_boundary_condition
 from fs.pressure_updater import JacobiPressureUpdater, PressureUpdater, RedBlackSorPressureUpdater
-from fs.solver import CipMacSolver, MacSolver
+from fs.solver import CipMacSolver, DyeCipMacSolver, DyeMacSolver, MacSolver
 from fs.vorticity_confinement import VorticityConfinement
 
 
 def make_solver(boundary_condition: BoundaryCondition, dt: float, dx: float, re: float, vor_eps: float | None,
                 scheme: str, pressure_updater: PressureUpdater | None = None, pressure: str = "rbsor",
-                n_iter: int = 2, relaxation_factor: float = 1.3):
+                n_iter: int = 2, relaxation_factor: float = 1.3, dye: bool = False):
     vorticity_confinement = (VorticityConfinement(boundary_condition, dt, dx, vor_eps) if vor_eps is not None else None)
     if pressure_updater is None:
         if pressure == "rbsor":
@@ -30,12 +30,13 @@ def make_solver(boundary_condition: BoundaryCondition, dt: float, dx: float, re:
             pressure_updater = JacobiPressureUpdater(boundary_condition, dt, dx, n_iter=n_iter)
         else:
             raise ValueError(f"Unknown pressure updater: {pressure}")
+    cip, mac = (DyeCipMacSolver, DyeMacSolver) if dye else (CipMacSolver, MacSolver)
     if scheme == "cip":
-        return CipMacSolver(boundary_condition, pressure_updater, dt, dx, re, vorticity_confinement)
+        return cip(boundary_condition, pressure_updater, dt, dx, re, vorticity_confinement)
     if scheme == "upwind":
-        return MacSolver(boundary_condition, pressure_updater, advect_upwind, dt, dx, re, vorticity_confinement)
+        return mac(boundary_condition, pressure_updater, advect_upwind, dt, dx, re, vorticity_confinement)
     if scheme == "kk":
-        return MacSolver(boundary_condition, pressure_updater, advect_kk_scheme, dt, dx, re, vorticity_confinement)
+        return mac(boundary_condition, pressure_updater, advect_kk_scheme, dt, dx, re, vorticity_confinement)
     msg = f"Unknown scheme: {scheme}"
     raise ValueError(msg)
 
@@ -65,3 +66,21 @@ class FluidSimulator:
             raise ValueError(msg)
         boundary_condition = get_boundary_condition(num, resolution, enable_dye=False, **bc_kw)
         return FluidSimulator(make_solver(boundary_condition, dt, dx, re, vor_eps, scheme, **kwargs))
+
+
+class DyeFluidSimulator(FluidSimulator):
+    """(:111-176) the default simulator of main.py: velocity/pressure + three dye channels."""
+
+    def field_to_numpy(self) -> dict[str, npt.NDArray]:
+        fields = self._solver.get_fields()
+        return {"v": fields[0].to_numpy(), "p": fields[1].to_numpy(), "dye": fields[2].to_numpy()}
+
+    @staticmethod
+    def create(num: int, resolution: int, dt: float, dx: float, re: float, vor_eps: float | None, scheme: str,
+               **kwargs) -> "DyeFluidSimulator":
+        bc_kw = {k: kwargs.pop(k) for k in ("device", "partition") if k in kwargs}
+        if scheme not in ("cip", "upwind", "kk"):
+            msg = f"Unknown scheme: {scheme}"
+            raise ValueError(msg)
+        boundary_condition = get_boundary_condition(num, resolution, enable_dye=True, **bc_kw)
+        return DyeFluidSimulator(make_solver(boundary_condition, dt, dx, re, vor_eps, scheme, dye=True, **kwargs))

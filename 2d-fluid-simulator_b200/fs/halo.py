@@ -159,6 +159,34 @@ def mac_update_distributed(s) -> None:
     limit_field(s.v.current, VELOCITY_LIMIT, bc=bc)
 
 
+def dye_update_distributed(s) -> None:
+    """Dye part of DyeMacSolver.update (fs/solver.py:149-152) / DyeCipMacSolver.update (:366-373) on a strip."""
+    from fs.solver import clamp_field
+
+    bc = s._bc
+    hx = exchanger_for(bc)
+    dye = s.dye
+    if hasattr(s, "dyex"):
+        dx_, dy_ = s.dyex, s.dyey
+        hx.exchange(dye.current, 1)
+        bc.set_dye_boundary_condition(dye.current)            # every local inflow cell, halo rows included
+        s._non_advection_phase_dye(dye.next, dye.current)
+        hx.exchange(dye.next, 1)
+        s._dye_grad(dx_.next, dy_.next, dx_.current, dy_.current, dye.current, dye.next)
+        dye.swap(); dx_.swap(); dy_.swap()
+        hx.exchange(dx_.current, 1)
+        hx.exchange(dy_.current, 1)
+        hx.exchange(s.v.current, 1)                           # d/dx, d/dy of the (limited) advecting velocity
+        s._dye_advect(dye.next, dx_.next, dy_.next, dye.current, dx_.current, dy_.current, s.v.current)
+        dye.swap(); dx_.swap(); dy_.swap()
+    else:
+        hx.exchange(dye.current, s._advect.radius)
+        bc.set_dye_boundary_condition(dye.current)
+        s._update_dye(dye.next, dye.current, s.v.current)
+        dye.swap()
+    clamp_field(dye.current, 0.0, 1.0, bc=bc)
+
+
 def gather_owned(field: Field, partition, dst: int = 0) -> torch.Tensor | None:
     """Owned rows of every rank concatenated on rank `dst` (tests / field_to_numpy on strips)."""
     own = field.owned().contiguous()

@@ -10,7 +10,7 @@ from abc import ABCMeta, abstractmethod
 
 from fs import _lib
 from fs.advection import AdvectionScheme
-from fs.boundary_condition import BoundaryCondition
+from fs.boundary_condition import BoundaryCondition, DyeBoundaryCondition
 from fs.double_buffer import DoubleBuffer, Field
 from fs.pressure_updater import PressureUpdater
 from fs.vorticity_confinement import VorticityConfinement
@@ -61,6 +61,16 @@ def limit_field(field: Field, limit: float, dom=None, bc: BoundaryCondition | No
             dom = _lib.Dom(rows=X + 2 * field.halo, Y=Y, r0=field.halo, r1=field.halo + X, clo=0,
                            chi=X + 2 * field.halo - 1, gi0=0)
     _lib.call("fs2d_limit", field.ptr(), dom, limit, _lib.stream())
+
+
+def clamp_field(field: Field, low: float, high: float, bc: BoundaryCondition | None = None) -> None:
+    """:46-49 -- clamp every component to [low, high] (all cells, in place)."""
+    if bc is not None:
+        dom = bc.dom
+    else:
+        X, Y = field.resolution
+        dom = _lib.Dom(rows=X + 2 * field.halo, Y=Y, r0=field.halo, r1=field.halo + X, clo=0, chi=X + 2 * field.halo - 1, gi0=0)
+    _lib.call("fs2d_clamp", field.ptr(), dom, max(field.n, 1), low, high, _lib.stream())
 
 
 class MacSolver(Solver):
@@ -160,3 +170,83 @@ class CipMacSolver(Solver):
         bc = self._bc
         _lib.call("fs2d_cip_advect", fn.ptr(), fxn.ptr(), fyn.ptr(), fc.ptr(), fxc.ptr(), fyc.ptr(), v.ptr(),
                   _lib.ptr(bc._bc_mask), bc.dom, self.dt, self.dx, self.dx**2, self.dx**3, _lib.stream())
+
+
+class DyeMacSolver(MacSolver):
+    """MacSolver + passive dye advected with the same scheme (:110-161)."""
+
+    def __init__(self, boundary_condition: DyeBoundaryCondition, pressure_updater: PressureUpdater,
+                 advect_function: AdvectionScheme, dt: float, dx: float, re: float,
+                 vorticity_confinement: VorticityConfinement | None = None) -> None:
+        super().__init__(boundary_condition, pressure_updater, advect_function, dt, dx, re, vorticity_confinement)
+        self.dye = self._buffer(3)
+
+    def update(self) -> None:
+        super().update()
+        if self._bc.partition.world > 1:
+            from fs.halo import dye_update_distributed
+
+            dye_update_distributed(self)
+            return
+        self._bc.set_dye_boundary_condition(self.dye.current)
+        self._update_dye(self.dye.next, self.dye.current, self.v.current)
+        self.dye.swap()
+        clamp_field(self.dye.current, 0.0, 1.0, bc=self._bc)
+
+    def get_fields(self) -> tuple[Field, Field, Field]:
+        return self.v.current, self.p.current, self.dye.current
+
+    def _update_dye(self, dn: Field, dc: Field, vc: Field) -> None:
+        bc = self._bc
+        _lib.call("fs2d_dye_mac", dn.ptr(), dc.ptr(), vc.ptr(), _lib.ptr(bc._bc_mask), bc.dom, self.dt, self.dx,
+                  self._advect.code, _lib.stream())
+
+
+class DyeCipMacSolver(CipMacSolver):
+    """CipMacSolver + dye carried with CIP (dye and its two derivative fields, :335-401)."""
+
+    def __init__(self, boundary_condition: DyeBoundaryCondition, pressure_updater: PressureUpdater, dt: float, dx: float,
+                 re: float, vorticity_confinement: VorticityConfinement | None = None) -> None:
+        super().__init__(boundary_condition, pressure_updater, dt, dx, re, vorticity_confinement)
+        self.dye = self._buffer(3)
+        self.dyex = self._buffer(3)
+        self.dyey = self._buffer(3)
+        bc = self._bc
+        _lib.call("fs2d_dye_set_grad", self.dyex.current.ptr(), self.dyey.current.ptr(), self.dye.current.ptr(), bc.dom,
+                  self.dx, _lib.stream())
+
+    def update(self) -> None:
+        super().update()
+        if self._bc.partition.world > 1:
+            from fs.halo import dye_update_distributed
+
+            dye_update_distributed(self)
+            return
+        self._bc.set_dye_boundary_condition(self.dye.current)
+        self._update_dye(self.dye, self.dyex, self.dyey, self.v)
+        clamp_field(self.dye.current, 0.0, 1.0, bc=self._bc)
+
+    def get_fields(self) -> tuple[Field, Field, Field]:
+        return self.v.current, self.p.current, self.dye.current
+
+    def _non_advection_phase_dye(self, dn: Field, dc: Field) -> None:
+        bc = self._bc
+        _lib.call("fs2d_dye_nonadv", dn.ptr(), dc.ptr(), _lib.ptr(bc._bc_mask), bc.dom, self.dt, self.dx, self.re,
+                  _lib.stream())
+
+    def _dye_grad(self, dxn: Field, dyn: Field, dxc: Field, dyc: Field, dc: Field, dn: Field) -> None:
+        bc = self._bc
+        _lib.call("fs2d_dye_nonadv_grad", dxn.ptr(), dyn.ptr(), dxc.ptr(), dyc.ptr(), dc.ptr(), dn.ptr(),
+                  _lib.ptr(bc._bc_mask), bc.dom, 2.0 * self.dx, _lib.stream())
+
+    def _dye_advect(self, dn: Field, dxn: Field, dyn: Field, dc: Field, dxc: Field, dyc: Field, v: Field) -> None:
+        bc = self._bc
+        _lib.call("fs2d_dye_cip_advect", dn.ptr(), dxn.ptr(), dyn.ptr(), dc.ptr(), dxc.ptr(), dyc.ptr(), v.ptr(),
+                  _lib.ptr(bc._bc_mask), bc.dom, self.dt, self.dx, self.dx**2, self.dx**3, _lib.stream())
+
+    def _update_dye(self, dye: DoubleBuffer, dyex: DoubleBuffer, dyey: DoubleBuffer, v: DoubleBuffer) -> None:
+        self._non_advection_phase_dye(dye.next, dye.current)
+        self._dye_grad(dyex.next, dyey.next, dyex.current, dyey.current, dye.current, dye.next)
+        dye.swap(); dyex.swap(); dyey.swap()
+        self._dye_advect(dye.next, dyex.next, dyey.next, dye.current, dyex.current, dyey.current, v.current)
+        dye.swap(); dyex.swap(); dyey.swap()

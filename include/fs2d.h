@@ -151,6 +151,25 @@ int fs2d_fused_tile(int T, int *rows, int *cols, int *halo_rows, int *halo_cols,
  * colour `parity`, (i_global + j) % 2); pc may alias pn (even pass, :96); src as above */
 int fs2d_rbsor_pass(float *pn, const float *pc, const float *src, const uint8_t *mask, fs2d_dom d, float omega,
                     float one_minus_omega, int parity, void *stream);
+/* ---- dye transport (3-channel AoS fields; DyeMacSolver / DyeCipMacSolver, fs/solver.py:110-161, :335-401) ---- */
+/* DyeBoundaryCondition.set_dye_boundary_condition, fs/boundary_condition.py:94-99: dye[tgt] = bc_dye[tgt] for
+ * the inflow cells listed in tgt (linear cell indices into the local array) */
+int fs2d_dye_bc(float *dye, const float *bc_dye, const int32_t *tgt, int n, void *stream);
+/* clamp_field, fs/solver.py:46-49 (all cells of rows [r0, r1), all `channels` components) */
+int fs2d_clamp(float *f, fs2d_dom d, int channels, float low, float high, void *stream);
+/* DyeMacSolver._update_dye, fs/solver.py:157-161: dn = dc - dt * advect(vc, dc) (fluid cells) */
+int fs2d_dye_mac(float *dn, const float *dc, const float *vc, const uint8_t *mask, fs2d_dom d, float dt, float dx, int scheme,
+                 void *stream);
+/* DyeCipMacSolver._non_advection_phase_dye, fs/solver.py:378-383 (not-wall cells) */
+int fs2d_dye_nonadv(float *dn, const float *dc, const uint8_t *mask, fs2d_dom d, float dt, float dx, float re, void *stream);
+/* _non_advection_phase_grad / _advection_phase / _set_grad on the 3-channel dye fields (fs/solver.py:242-332, :207-211);
+ * v is the 2-channel advecting velocity */
+int fs2d_dye_nonadv_grad(float *fxn, float *fyn, const float *fxc, const float *fyc, const float *fc, const float *fn,
+                         const uint8_t *mask, fs2d_dom d, float two_dx, void *stream);
+int fs2d_dye_cip_advect(float *fn, float *fxn, float *fyn, const float *fc, const float *fxc, const float *fyc,
+                        const float *v, const uint8_t *mask, fs2d_dom d, float dt, float dx, float dx2, float dx3,
+                        void *stream);
+int fs2d_dye_set_grad(float *fx, float *fy, const float *f, fs2d_dom d, float dx, void *stream);
 /* limit_field, fs/solver.py:38-43 (all cells, in place) */
 int fs2d_limit(float *v, fs2d_dom d, float limit, void *stream);
 

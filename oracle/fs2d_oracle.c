@@ -367,4 +367,146 @@ void orc_limit(float *v, int X, int Y, float limit) {
         }
 }
 
-int orc_abi_version(void) { return 1; }
+/* ==========================================================================================
+ * Dye transport: the same kernels on C-channel fields (C = 3 for dye).
+ * SC(f, i, j, c): clamped sample of component c of a C-channel AoS field.
+ * ======================================================================================== */
+#define SC(f, i, j, c) ((f)[(size_t)C * IDX(CI(i), CJ(j)) + (c)])
+
+/* fs/boundary_condition.py:94-99 DyeBoundaryCondition.set_dye_boundary_condition */
+void orc_dye_bc(float *dye, const float *bc_dye, const uint8_t *mask, int X, int Y) {
+    const int C = 3;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < X; ++i)
+        for (int j = 0; j < Y; ++j)
+            if (mask[IDX(i, j)] == 2)
+                for (int c = 0; c < C; ++c) dye[C * IDX(i, j) + c] = bc_dye[C * IDX(i, j) + c];
+}
+
+/* fs/solver.py:46-49 clamp_field (all cells, all components) */
+void orc_clamp(float *f, int X, int Y, int C, float low, float high) {
+    size_t n = (size_t)X * Y * C;
+#pragma omp parallel for schedule(static)
+    for (size_t k = 0; k < n; ++k) f[k] = fminf(fmaxf(f[k], low), high);
+}
+
+/* fs/solver.py:157-161 DyeMacSolver._update_dye: dn = dc - dt * advect(vc, dc); scheme 0 upwind, 1 kk */
+void orc_dye_mac(float *dn, const float *dc, const float *vc, const uint8_t *mask, int X, int Y, int C, float dt,
+                 float dx, int scheme) {
+    static const float cneg[5] = {-2.0f, 10.0f, -9.0f, 2.0f, -1.0f};
+    static const float cpos[5] = {1.0f, -2.0f, 9.0f, -10.0f, 2.0f};
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < X; ++i)
+        for (int j = 0; j < Y; ++j) {
+            if (mask[IDX(i, j)] != 0) continue;
+            float u = vc[2 * IDX(i, j)], w = vc[2 * IDX(i, j) + 1];
+            for (int c = 0; c < C; ++c) {
+                float adv;
+                if (scheme == 0) { /* fs/advection.py:12-24 */
+                    int k = u < 0.0f ? i : i - 1;
+                    float a = u * ((SC(dc, k + 1, j, c) - SC(dc, k, j, c)) / dx);
+                    k = w < 0.0f ? j : j - 1;
+                    float b = w * ((SC(dc, i, k + 1, c) - SC(dc, i, k, c)) / dx);
+                    adv = a + b;
+                } else { /* fs/advection.py:27-60 */
+                    const float *k = u < 0.0f ? cneg : cpos;
+                    float acc = SC(dc, i + 2, j, c) * k[0];
+                    acc = acc + SC(dc, i + 1, j, c) * k[1];
+                    acc = acc + SC(dc, i, j, c) * k[2];
+                    acc = acc + SC(dc, i - 1, j, c) * k[3];
+                    acc = acc + SC(dc, i - 2, j, c) * k[4];
+                    float a = acc / (6.0f * dx);
+                    k = w < 0.0f ? cneg : cpos;
+                    acc = SC(dc, i, j + 2, c) * k[0];
+                    acc = acc + SC(dc, i, j + 1, c) * k[1];
+                    acc = acc + SC(dc, i, j, c) * k[2];
+                    acc = acc + SC(dc, i, j - 1, c) * k[3];
+                    acc = acc + SC(dc, i, j - 2, c) * k[4];
+                    float b = acc / (6.0f * dx);
+                    adv = u * a + w * b;
+                }
+                dn[C * IDX(i, j) + c] = dc[C * IDX(i, j) + c] - dt * adv;
+            }
+        }
+}
+
+/* fs/solver.py:378-383 DyeCipMacSolver._non_advection_phase_dye: dn = dc + diffusion(dc) * dt (not-wall) */
+void orc_dye_nonadv(float *dn, const float *dc, const uint8_t *mask, int X, int Y, int C, float dt, float dx, float re) {
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < X; ++i)
+        for (int j = 0; j < Y; ++j) {
+            if (mask[IDX(i, j)] == 1) continue;
+            for (int c = 0; c < C; ++c) {
+                float d2x = (SC(dc, i + 1, j, c) - 2.0f * SC(dc, i, j, c) + SC(dc, i - 1, j, c)) / (dx * dx);
+                float d2y = (SC(dc, i, j + 1, c) - 2.0f * SC(dc, i, j, c) + SC(dc, i, j - 1, c)) / (dx * dx);
+                dn[C * IDX(i, j) + c] = dc[C * IDX(i, j) + c] + (d2x + d2y) / re * dt;
+            }
+        }
+}
+
+/* fs/solver.py:242-261 on C channels */
+void orc_cip_nonadv_grad_n(float *fxn, float *fyn, const float *fxc, const float *fyc, const float *fc, const float *fn,
+                           const uint8_t *mask, int X, int Y, int C, float two_dx) {
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < X; ++i)
+        for (int j = 0; j < Y; ++j) {
+            if (mask[IDX(i, j)] == 1) continue;
+            for (int c = 0; c < C; ++c) {
+                fxn[C * IDX(i, j) + c] = fxc[C * IDX(i, j) + c] +
+                    (SC(fn, i + 1, j, c) - SC(fc, i + 1, j, c) - SC(fn, i - 1, j, c) + SC(fc, i - 1, j, c)) / two_dx;
+                fyn[C * IDX(i, j) + c] = fyc[C * IDX(i, j) + c] +
+                    (SC(fn, i, j + 1, c) - SC(fc, i, j + 1, c) - SC(fn, i, j - 1, c) + SC(fc, i, j - 1, c)) / two_dx;
+            }
+        }
+}
+
+/* fs/solver.py:267-332 on C channels, advecting velocity v (2 channels) */
+void orc_cip_advect_n(float *fn, float *fxn, float *fyn, const float *fc, const float *fxc, const float *fyc,
+                      const float *v, const uint8_t *mask, int X, int Y, int C, float dt, float dx, float dx2, float dx3) {
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < X; ++i)
+        for (int j = 0; j < Y; ++j) {
+            if (mask[IDX(i, j)] != 0) continue;
+            float u = v[2 * IDX(i, j)], w = v[2 * IDX(i, j) + 1];
+            float i_s = signf_(u), j_s = signf_(w);
+            int i_m = i - (int)i_s, j_m = j - (int)j_s;
+            float isd = i_s * dx3, jsd = j_s * dx3, isdx = i_s * dx;
+            float Xd = -u * dt, Yd = -w * dt;
+            float dxu = DIFFX2(v, i, j, 0), dxv = DIFFX2(v, i, j, 1);
+            float dyu = DIFFY2(v, i, j, 0), dyv = DIFFY2(v, i, j, 1);
+            for (int c = 0; c < C; ++c) {
+                float f00 = SC(fc, i, j, c), f0m = SC(fc, i, j_m, c), fm0 = SC(fc, i_m, j, c), fmm = SC(fc, i_m, j_m, c);
+                float x00 = SC(fxc, i, j, c), x0m = SC(fxc, i, j_m, c), xm0 = SC(fxc, i_m, j, c);
+                float y00 = SC(fyc, i, j, c), y0m = SC(fyc, i, j_m, c), ym0 = SC(fyc, i_m, j, c);
+                float tmp1 = f00 - f0m - fm0 + fmm;
+                float tmp2 = fm0 - f00;
+                float tmp3 = f0m - f00;
+                float a = (i_s * (xm0 + x00) * dx - 2.0f * (-tmp2)) / isd;
+                float b = (j_s * (y0m + y00) * dx - 2.0f * (-tmp3)) / jsd;
+                float cc = (-tmp1 - i_s * (x0m - x00) * dx) / jsd;
+                float d = (-tmp1 - j_s * (ym0 - y00) * dx) / isd;
+                float e = (3.0f * tmp2 + i_s * (xm0 + 2.0f * x00) * dx) / dx2;
+                float f = (3.0f * tmp3 + j_s * (y0m + 2.0f * y00) * dx) / dx2;
+                float g = (-(ym0 - y00) + cc * dx2) / isdx;
+                fn[C * IDX(i, j) + c] = ((a * Xd + cc * Yd + e) * Xd + g * Yd + x00) * Xd +
+                                        ((b * Yd + d * Xd + f) * Yd + y00) * Yd + f00;
+                float Fx = (3.0f * a * Xd + 2.0f * cc * Yd + 2.0f * e) * Xd + (d * Yd + g) * Yd + x00;
+                float Fy = (3.0f * b * Yd + 2.0f * d * Xd + 2.0f * f) * Yd + (cc * Xd + g) * Xd + y00;
+                fxn[C * IDX(i, j) + c] = Fx - dt * (Fx * dxu + Fy * dxv) / 2.0f;
+                fyn[C * IDX(i, j) + c] = Fy - dt * (Fx * dyu + Fy * dyv) / 2.0f;
+            }
+        }
+}
+
+/* fs/solver.py:207-211 on C channels */
+void orc_set_grad_n(float *fx, float *fy, const float *f, int X, int Y, int C, float dx) {
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < X; ++i)
+        for (int j = 0; j < Y; ++j)
+            for (int c = 0; c < C; ++c) {
+                fx[C * IDX(i, j) + c] = 0.5f * (SC(f, i + 1, j, c) - SC(f, i - 1, j, c)) / dx;
+                fy[C * IDX(i, j) + c] = 0.5f * (SC(f, i, j + 1, c) - SC(f, i, j - 1, c)) / dx;
+            }
+}
+
+int orc_abi_version(void) { return 2; }

@@ -124,6 +124,45 @@ def limit(v, lim=VELOCITY_LIMIT) -> None:
     lib().orc_limit(_p(v), _i(X), _i(Y), _f(f32(lim)))
 
 
+# ----------------------------------------------------------------------------- dye kernels (C = 3)
+def dye_bc(dye, bc_dye, mask) -> None:
+    X, Y = mask.shape
+    lib().orc_dye_bc(_p(dye), _p(bc_dye), _p(mask), _i(X), _i(Y))
+
+
+def clamp(f, low=0.0, high=1.0) -> None:
+    X, Y, C = f.shape
+    lib().orc_clamp(_p(f), _i(X), _i(Y), _i(C), _f(f32(low)), _f(f32(high)))
+
+
+def dye_mac(dn, dc, vc, mask, dt, dx, scheme: str) -> None:
+    X, Y = mask.shape
+    lib().orc_dye_mac(_p(dn), _p(dc), _p(vc), _p(mask), _i(X), _i(Y), _i(dn.shape[2]), _f(f32(dt)), _f(f32(dx)),
+                      _i({"upwind": 0, "kk": 1}[scheme]))
+
+
+def dye_nonadv(dn, dc, mask, dt, dx, re) -> None:
+    X, Y = mask.shape
+    lib().orc_dye_nonadv(_p(dn), _p(dc), _p(mask), _i(X), _i(Y), _i(dn.shape[2]), _f(f32(dt)), _f(f32(dx)), _f(f32(re)))
+
+
+def cip_nonadv_grad_n(fxn, fyn, fxc, fyc, fc, fn, mask, dx) -> None:
+    X, Y = mask.shape
+    lib().orc_cip_nonadv_grad_n(_p(fxn), _p(fyn), _p(fxc), _p(fyc), _p(fc), _p(fn), _p(mask), _i(X), _i(Y),
+                                _i(fc.shape[2]), _f(f32(2.0 * dx)))
+
+
+def cip_advect_n(fn, fxn, fyn, fc, fxc, fyc, v, mask, dt, dx) -> None:
+    X, Y = mask.shape
+    lib().orc_cip_advect_n(_p(fn), _p(fxn), _p(fyn), _p(fc), _p(fxc), _p(fyc), _p(v), _p(mask), _i(X), _i(Y),
+                           _i(fc.shape[2]), _f(f32(dt)), _f(f32(dx)), _f(f32(dx**2)), _f(f32(dx**3)))
+
+
+def set_grad_n(fx, fy, f, dx) -> None:
+    X, Y, C = f.shape
+    lib().orc_set_grad_n(_p(fx), _p(fy), _p(f), _i(X), _i(Y), _i(C), _f(f32(dx)))
+
+
 def set_threads(n: int) -> None:
     os.environ["OMP_NUM_THREADS"] = str(n)
 
@@ -141,7 +180,7 @@ class Buf:
 
 
 class OracleSolver:
-    def __init__(self, mask, bc_const, dt, dx, re, scheme="cip", vc=None, pressure=("jacobi", 2)):
+    def __init__(self, mask, bc_const, dt, dx, re, scheme="cip", vc=None, pressure=("jacobi", 2), bc_dye=None):
         self.mask = np.ascontiguousarray(mask, dtype=np.uint8)
         self.bc_const = np.ascontiguousarray(bc_const, dtype=np.float32)
         self.dt, self.dx, self.re, self.scheme, self.vc, self.pressure = dt, dx, re, scheme, vc, pressure
@@ -156,6 +195,13 @@ class OracleSolver:
         if vc is not None:
             self.vort = np.zeros((X, Y), dtype=np.float32)
             self.vort_abs = np.zeros((X, Y), dtype=np.float32)
+        # dye variants: DyeMacSolver (fs/solver.py:110-161), DyeCipMacSolver (:335-401)
+        self.bc_dye = None if bc_dye is None else np.ascontiguousarray(bc_dye, dtype=np.float32)
+        if self.bc_dye is not None:
+            self.dye = Buf((X, Y, 3))
+            if scheme == "cip":
+                self.dyex, self.dyey = Buf((X, Y, 3)), Buf((X, Y, 3))
+                set_grad_n(self.dyex.current, self.dyey.current, self.dye.current, dx)  # solver.py:351
 
     # fs/pressure_updater.py:56-60 / :86-96
     def _pressure_update(self) -> None:
@@ -196,6 +242,24 @@ class OracleSolver:
             self._vc_apply()
         self._pressure_update()
         limit(self.v.current)
+        if self.bc_dye is not None:
+            self._update_dye()
+
+    def _update_dye(self) -> None:
+        m, dye = self.mask, self.dye
+        dye_bc(dye.current, self.bc_dye, m)                                   # solver.py:149 / :366
+        if self.scheme == "cip":                                              # solver.py:385-401
+            dx_, dy_ = self.dyex, self.dyey
+            dye_nonadv(dye.next, dye.current, m, self.dt, self.dx, self.re)
+            cip_nonadv_grad_n(dx_.next, dy_.next, dx_.current, dy_.current, dye.current, dye.next, m, self.dx)
+            dye.swap(); dx_.swap(); dy_.swap()
+            cip_advect_n(dye.next, dx_.next, dy_.next, dye.current, dx_.current, dy_.current, self.v.current, m,
+                         self.dt, self.dx)
+            dye.swap(); dx_.swap(); dy_.swap()
+        else:                                                                 # solver.py:150-151
+            dye_mac(dye.next, dye.current, self.v.current, m, self.dt, self.dx, self.scheme)
+            dye.swap()
+        clamp(dye.current, 0.0, 1.0)                                          # solver.py:152 / :373
 
     def state(self) -> dict:
         d = {"v_cur": self.v.current, "v_nxt": self.v.next, "p_cur": self.p.current, "p_nxt": self.p.next}
@@ -203,6 +267,11 @@ class OracleSolver:
             d.update(vx_cur=self.vx.current, vx_nxt=self.vx.next, vy_cur=self.vy.current, vy_nxt=self.vy.next)
         if self.vc is not None:
             d.update(vort=self.vort, vort_abs=self.vort_abs)
+        if self.bc_dye is not None:
+            d.update(dye_cur=self.dye.current, dye_nxt=self.dye.next)
+            if self.scheme == "cip":
+                d.update(dyex_cur=self.dyex.current, dyex_nxt=self.dyex.next, dyey_cur=self.dyey.current,
+                         dyey_nxt=self.dyey.next)
         return d
 
     def load_state(self, st: dict) -> None:

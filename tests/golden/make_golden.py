@@ -43,7 +43,7 @@ from fs.boundary_condition import (  # noqa: E402
     get_boundary_condition,
 )
 from fs.pressure_updater import JacobiPressureUpdater, RedBlackSorPressureUpdater  # noqa: E402
-from fs.solver import CipMacSolver, MacSolver, limit_field  # noqa: E402
+from fs.solver import CipMacSolver, DyeCipMacSolver, DyeMacSolver, MacSolver, clamp_field, limit_field  # noqa: E402
 from fs.vorticity_confinement import VorticityConfinement  # noqa: E402
 
 
@@ -238,6 +238,79 @@ def gen_traj(only: str | None = None) -> None:
         print(f"traj {name}: {time.time() - t0:.1f}s", flush=True)
 
 
+# --------------------------------------------------------------------------- dye
+DYE_TRAJ = [
+    ("dyeA_cip_bc1_r24_sor2_vc5", 1, 24, None, 1e4, 5.0, "cip", ("rbsor", 2), 3, "zero"),
+    ("dyeB_cip_bc2_r16_jac3_novc_rand", 2, 16, None, 300.0, None, "cip", ("jacobi", 3), 3, "rand"),
+    ("dyeC_upwind_bc4_r24_jac2_vc5_rand", 4, 24, None, 500.0, 5.0, "upwind", ("jacobi", 2), 3, "rand"),
+    ("dyeD_kk_bc5_r16_sor2_novc_rand", 5, 16, None, 1000.0, None, "kk", ("rbsor", 2), 3, "rand"),
+    ("dyeE_cip_bc3_r20_jac4_vc5", 3, 20, None, 1e6, 5.0, "cip", ("jacobi", 4), 3, "zero"),
+]
+
+
+def dye_state_of(s) -> dict:
+    d = state_of(s)
+    d.update(dye_cur=s.dye.current.to_numpy(), dye_nxt=s.dye.next.to_numpy())
+    if hasattr(s, "dyex"):
+        d.update(dyex_cur=s.dyex.current.to_numpy(), dyex_nxt=s.dyex.next.to_numpy(),
+                 dyey_cur=s.dyey.current.to_numpy(), dyey_nxt=s.dyey.next.to_numpy())
+    return d
+
+
+def gen_dye() -> None:
+    # scene dye arrays
+    out = {}
+    for num in (1, 2, 3, 4, 5):
+        for res in (16, 20, 24, 40):
+            bc = get_boundary_condition(num, res, enable_dye=True)
+            out[f"bc{num}_r{res}_dye"] = bc._bc_dye.to_numpy()
+            out[f"bc{num}_r{res}_mask"] = bc._bc_mask.to_numpy()
+            out[f"bc{num}_r{res}_const"] = bc._bc_const.to_numpy()
+    np.savez_compressed(HERE / "dye_scenes.npz", **out)
+    for name, num, res, dt, re, vc, scheme, pressure, steps, init in DYE_TRAJ:
+        t0 = time.time()
+        dt_ = dt if dt is not None else 0.05 / res
+        dx_ = 1.0 / res
+        bc = get_boundary_condition(num, res, enable_dye=True)
+        vcf = VorticityConfinement(bc, dt_, dx_, vc) if vc is not None else None
+        pu = (JacobiPressureUpdater(bc, dt_, dx_, pressure[1]) if pressure[0] == "jacobi"
+              else RedBlackSorPressureUpdater(bc, dt_, dx_, 1.3, pressure[1]))
+        if scheme == "cip":
+            s = DyeCipMacSolver(bc, pu, dt_, dx_, re, vcf)
+        else:
+            s = DyeMacSolver(bc, pu, advect_upwind if scheme == "upwind" else advect_kk_scheme, dt_, dx_, re, vcf)
+        X, Y = s.resolution
+        out = {"meta_num": num, "meta_res": res, "meta_dt": dt_, "meta_dx": dx_, "meta_re": re,
+               "meta_vc": -1.0 if vc is None else vc, "meta_scheme": scheme, "meta_pressure": pressure[0],
+               "meta_n_iter": pressure[1], "meta_steps": steps}
+        if init == "rand":
+            rng = np.random.default_rng(sum(map(ord, name)))
+
+            def rv(scale, ch):
+                shp = (X, Y, ch) if ch else (X, Y)
+                return (rng.uniform(-1, 1, shp) * scale).astype(np.float32)
+
+            s.v.current.from_numpy(rv(0.5, 2)); s.v.next.from_numpy(rv(0.5, 2))
+            s.p.current.from_numpy(rv(1.0, 0)); s.p.next.from_numpy(rv(1.0, 0))
+            s.dye.current.from_numpy(np.abs(rv(1.0, 3))); s.dye.next.from_numpy(np.abs(rv(1.0, 3)))
+            if hasattr(s, "vx"):
+                for b in (s.vx, s.vy):
+                    b.current.from_numpy(rv(0.05 / dx_, 2)); b.next.from_numpy(rv(0.05 / dx_, 2))
+                for b in (s.dyex, s.dyey):
+                    b.current.from_numpy(rv(0.05 / dx_, 3)); b.next.from_numpy(rv(0.05 / dx_, 3))
+            if s.vorticity_confinement is not None:
+                s.vorticity_confinement.vorticity.from_numpy(rv(1.0, 0))
+                s.vorticity_confinement.vorticity_abs.from_numpy(np.abs(rv(1.0, 0)))
+        for k, a in dye_state_of(s).items():
+            out[f"s0_{k}"] = a
+        for n in range(1, steps + 1):
+            s.update()
+            for k, a in dye_state_of(s).items():
+                out[f"s{n}_{k}"] = a
+        np.savez_compressed(HERE / f"traj_{name}.npz", **out)
+        print(f"dye traj {name}: {time.time() - t0:.1f}s", flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -249,3 +322,5 @@ if __name__ == "__main__":
         gen_kernels()
     if a.only in (None, "traj"):
         gen_traj(a.traj)
+    if a.only in (None, "dye"):
+        gen_dye()

@@ -108,7 +108,7 @@ def test_each_kernel_matches_reference_fixture(env, num, kernels_golden, masks_s
 # ------------------------------------------------------------------------------------------------
 # 2. N-step trajectories through Solver.update(): every physical buffer, vs the reference fixtures
 # ------------------------------------------------------------------------------------------------
-TRAJ = sorted(p.name for p in GOLDEN.glob("traj_*.npz"))
+TRAJ = sorted(p.name for p in GOLDEN.glob("traj_[A-Z]_*.npz"))
 
 
 @pytest.mark.parametrize("name", TRAJ)
@@ -364,3 +364,57 @@ def test_fused_update_equals_literal_update(env, num, X, Y, n_iter):
         assert_bitexact("cur", res[0][0], res[1][0])
         if other is p0:
             assert_bitexact("nxt", res[0][1], res[1][1])
+
+
+# ------------------------------------------------------------------------------------------------
+# 6. dye transport (DyeMacSolver / DyeCipMacSolver) vs the reference fixtures and the oracle
+# ------------------------------------------------------------------------------------------------
+DYE_TRAJ = sorted(p.name for p in GOLDEN.glob("traj_dye*.npz"))
+
+
+def dye_state(s) -> dict:
+    d = fs_state(s)
+    d.update(dye_cur=s.dye.current, dye_nxt=s.dye.next)
+    if hasattr(s, "dyex"):
+        d.update(dyex_cur=s.dyex.current, dyex_nxt=s.dyex.next, dyey_cur=s.dyey.current, dyey_nxt=s.dyey.next)
+    return d
+
+
+@pytest.mark.parametrize("name", DYE_TRAJ)
+def test_dye_trajectory_matches_reference_fixture(env, name):
+    from fs.boundary_condition import DyeBoundaryCondition
+    from fs.fluid_simulator import make_solver
+
+    g = np.load(GOLDEN / name)
+    sc = np.load(GOLDEN / "dye_scenes.npz")
+    num, res, vc = int(g["meta_num"]), int(g["meta_res"]), float(g["meta_vc"])
+    kind, n_iter = str(g["meta_pressure"]), int(g["meta_n_iter"])
+    bc = DyeBoundaryCondition(sc[f"bc{num}_r{res}_const"], sc[f"bc{num}_r{res}_dye"], sc[f"bc{num}_r{res}_mask"])
+    s = make_solver(bc, float(g["meta_dt"]), float(g["meta_dx"]), float(g["meta_re"]), None if vc < 0 else vc,
+                    str(g["meta_scheme"]), pressure=kind, n_iter=n_iter, dye=True)
+    for k, f in dye_state(s).items():
+        f.from_numpy(g[f"s0_{k}"])
+    for n in range(1, int(g["meta_steps"]) + 1):
+        s.update()
+        for k, f in dye_state(s).items():
+            assert_bitexact(f"{name} step {n} {k}", f.to_numpy(), g[f"s{n}_{k}"])
+
+
+@pytest.mark.parametrize("num,res,scheme", [(1, 128, "cip"), (2, 96, "kk"), (5, 100, "upwind")])
+def test_dye_simulator_vs_oracle(env, num, res, scheme):
+    """DyeFluidSimulator.create (main.py's default object graph) for a few steps vs the oracle."""
+    from fs.boundary_condition import build_scene
+    from fs.fluid_simulator import DyeFluidSimulator
+    from oracle import oracle as orc
+
+    dt, dx, re, vc = 0.05 / res, 1.0 / res, 1e4, 5.0
+    sim = DyeFluidSimulator.create(num, res, dt, dx, re, vc, scheme)
+    const, mask, dye = build_scene(num, 2 * res, res, with_dye=True)
+    ref = orc.OracleSolver(mask, const, dt, dx, re, scheme, vc, ("rbsor", 1.3, 2), bc_dye=dye)
+    for _ in range(6):
+        sim.step(); ref.update()
+    out = sim.field_to_numpy()
+    assert set(out) == {"v", "p", "dye"} and out["dye"].shape == (2 * res, res, 3)
+    assert_bitexact("v", out["v"], ref.v.current); assert_bitexact("p", out["p"], ref.p.current)
+    assert_bitexact("dye", out["dye"], ref.dye.current)
+    assert float(out["dye"].max()) > 0.5   # dye actually entered the domain

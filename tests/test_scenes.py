@@ -36,6 +36,16 @@ def test_large_scenes_hash_equal_reference(key):
     assert int((mask == 0).sum()) == SHAS[key]["fluid"]
 
 
+def test_dye_scenes_equal_reference():
+    sc = np.load(GOLDEN / "dye_scenes.npz")
+    for num in (1, 2, 3, 4, 5):
+        for res in (16, 20, 24, 40):
+            const, mask, dye = build_scene(num, 2 * res, res, with_dye=True)
+            np.testing.assert_array_equal(mask, sc[f"bc{num}_r{res}_mask"])
+            np.testing.assert_array_equal(const, sc[f"bc{num}_r{res}_const"])
+            np.testing.assert_array_equal(dye, sc[f"bc{num}_r{res}_dye"])
+
+
 def test_unknown_scene_and_dye():
     with pytest.raises(NotImplementedError):
         get_boundary_condition(7, 16, enable_dye=False, device="cpu")
