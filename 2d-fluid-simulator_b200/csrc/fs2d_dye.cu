@@ -159,6 +159,33 @@ __global__ void __launch_bounds__(TX *TY)
     }
 }
 
+// fs/fluid_simulator.py:38-58, :121-126 + fs/visualization.py:8-22: field -> RGB image, wall colour override
+template <bool P2, int MODE>
+__global__ void __launch_bounds__(TX *TY)
+    k_render(float *__restrict__ rgb, const float *__restrict__ v, const float *__restrict__ p, const float *__restrict__ dye,
+             const uint8_t *__restrict__ mask, fs2d_dom d, DivC<P2> ddx) {
+    FS2D_CELL(d, r, j)
+    const size_t idx = IX(d, r, j);
+    float o0, o1, o2;
+    if (MODE == 0) {
+        const float2 c = __ldg(reinterpret_cast<const float2 *>(v) + idx);
+        const float n = sqrtf(c.x * c.x + c.y * c.y), pv = __ldg(p + idx);
+        o0 = 0.2f * n + 0.002f * fmaxf(pv, 0.0f);
+        o1 = 0.2f * n + 0.002f * 0.0f;
+        o2 = 0.2f * n + 0.002f * fmaxf(-pv, 0.0f);
+    } else if (MODE == 1) {
+        const float pv = __ldg(p + idx);
+        o0 = 0.04f * fmaxf(pv, 0.0f); o1 = 0.04f * 0.0f; o2 = 0.04f * fmaxf(-pv, 0.0f);
+    } else if (MODE == 2) {
+        const float val = ddx(0.5f * (ld2(v, d, r + 1, j) - ld2(v, d, r - 1, j))).y - ddx(0.5f * (ld2(v, d, r, j + 1) - ld2(v, d, r, j - 1))).x;
+        o0 = 0.005f * fmaxf(val, 0.0f); o1 = 0.005f * 0.0f; o2 = 0.005f * fmaxf(-val, 0.0f);
+    } else {
+        o0 = __ldg(dye + 3 * idx); o1 = __ldg(dye + 3 * idx + 1); o2 = __ldg(dye + 3 * idx + 2);
+    }
+    if (mask[idx] == 1) { o0 = 0.5f; o1 = 0.7f; o2 = 0.5f; }
+    rgb[3 * idx] = o0; rgb[3 * idx + 1] = o1; rgb[3 * idx + 2] = o2;
+}
+
 }  // namespace fs2d
 
 using namespace fs2d;
@@ -250,6 +277,25 @@ int fs2d_dye_set_grad(float *fx, float *fy, const float *f, fs2d_dom d, float dx
 #define SG(P2) k_set_grad_n<P2, 3><<<dense_grid(d), dense_block(), 0, STREAM>>>(fx, fy, f, d, DivC<P2>(dx))
     P2_DISPATCH(is_pow2(dx), SG(true), SG(false));
 #undef SG
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+int fs2d_render(float *rgb, const float *v, const float *p, const float *dye, const uint8_t *mask, fs2d_dom d, float dx,
+                int mode, void *stream) {
+    FS2D_REQUIRE(rgb && mask && mode >= 0 && mode <= 3, "bad render arguments");
+    FS2D_REQUIRE((mode == 0 && v && p) || (mode == 1 && p) || (mode == 2 && v) || (mode == 3 && dye), "missing input field");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+#define RD(P2, M) k_render<P2, M><<<dense_grid(d), dense_block(), 0, STREAM>>>(rgb, v, p, dye, mask, d, DivC<P2>(dx))
+    const bool p2 = is_pow2(dx);
+    switch (mode) {
+        case 0: P2_DISPATCH(p2, RD(true, 0), RD(false, 0)); break;
+        case 1: P2_DISPATCH(p2, RD(true, 1), RD(false, 1)); break;
+        case 2: P2_DISPATCH(p2, RD(true, 2), RD(false, 2)); break;
+        default: P2_DISPATCH(p2, RD(true, 3), RD(false, 3)); break;
+    }
+#undef RD
     FS2D_LAUNCH_CHECK();
     return FS2D_OK;
 }

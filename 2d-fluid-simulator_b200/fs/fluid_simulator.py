@@ -11,6 +11,9 @@ from __future__ import annotations
 import numpy as np
 import numpy.typing as npt
 
+from fs import _lib
+from fs.double_buffer import Field
+
 from fs.advection import advect_kk_scheme, advect_upwind
 from fs.boundary_condition import BoundaryCondition, get_boundary_condition
 from fs.pressure_updater import JacobiPressureUpdater, PressureUpdater, RedBlackSorPressureUpdater
@@ -44,9 +47,60 @@ def make_solver(boundary_condition: BoundaryCondition, dt: float, dx: float, re:
 class FluidSimulator:
     def __init__(self, solver: MacSolver | CipMacSolver) -> None:
         self._solver = solver
+        self._rgb: Field | None = None   # image buffer (:16), allocated on first use: 12 B/cell
 
     def step(self) -> None:
         self._solver.update()
+
+    # -- render getters (:22-32): (X, Y, 3) f32 images, wall cells in the wall colour -------------------
+    @property
+    def rgb_buf(self) -> Field:
+        if self._rgb is None:
+            bc = self._solver._bc
+            self._rgb = Field(self._solver.resolution, 3, bc.device, bc.halo)
+        return self._rgb
+
+    def _render(self, mode: int) -> Field:
+        s, bc = self._solver, self._solver._bc
+        fields = s.get_fields()
+        dye = fields[2].ptr() if len(fields) > 2 else None
+        _lib.call("fs2d_render", self.rgb_buf.ptr(), fields[0].ptr(), fields[1].ptr(), dye, _lib.ptr(bc._bc_mask), bc.dom,
+                  s.dx, mode, _lib.stream())
+        return self.rgb_buf
+
+    def get_norm_field(self) -> Field:
+        return self._render(0)
+
+    def get_pressure_field(self) -> Field:
+        return self._render(1)
+
+    def get_vorticity_field(self) -> Field:
+        if self._solver._bc.partition.world > 1:
+            from fs.halo import exchanger_for
+
+            exchanger_for(self._solver._bc).exchange(self._solver.get_fields()[0], 1)
+        return self._render(2)
+
+    # -- full-state dump / restore: the `d`-key dump (main.py:129-132) cannot resume a CIP run
+    #    because vx/vy are not in it; these carry every physical buffer.
+    def state_dict(self) -> dict[str, npt.NDArray]:
+        out = {}
+        for name in ("v", "vx", "vy", "p", "dye", "dyex", "dyey"):
+            buf = getattr(self._solver, name, None)
+            if buf is not None:
+                out[name + "_cur"], out[name + "_nxt"] = buf.current.to_numpy(), buf.next.to_numpy()
+        vc = self._solver.vorticity_confinement
+        if vc is not None:
+            out["vort"], out["vort_abs"] = vc.vorticity.to_numpy(), vc.vorticity_abs.to_numpy()
+        return out
+
+    def load_state_dict(self, state: dict) -> None:
+        for key, a in state.items():
+            if key in ("vort", "vort_abs"):
+                getattr(self._solver.vorticity_confinement, "vorticity" if key == "vort" else "vorticity_abs").from_numpy(a)
+            else:
+                name, which = key.rsplit("_", 1)
+                getattr(getattr(self._solver, name), "current" if which == "cur" else "next").from_numpy(a)
 
     def field_to_numpy(self) -> dict[str, npt.NDArray]:
         """{"v": (X, Y, 2) f32, "p": (X, Y) f32} -- the `d`-key dump format (main.py:129-132)."""
@@ -70,6 +124,9 @@ class FluidSimulator:
 
 class DyeFluidSimulator(FluidSimulator):
     """(:111-176) the default simulator of main.py: velocity/pressure + three dye channels."""
+
+    def get_dye_field(self) -> Field:
+        return self._render(3)
 
     def field_to_numpy(self) -> dict[str, npt.NDArray]:
         fields = self._solver.get_fields()

@@ -170,6 +170,11 @@ int fs2d_dye_cip_advect(float *fn, float *fxn, float *fyn, const float *fc, cons
                         const float *v, const uint8_t *mask, fs2d_dom d, float dt, float dx, float dx2, float dx3,
                         void *stream);
 int fs2d_dye_set_grad(float *fx, float *fy, const float *f, fs2d_dom d, float dx, void *stream);
+/* FluidSimulator._to_norm/_to_pressure/_to_vorticity, DyeFluidSimulator._to_dye (fs/fluid_simulator.py:38-58,
+ * :121-126; fs/visualization.py:8-22): rgb (rows, Y, 3) <- mode 0 norm + pressure tint, 1 pressure, 2 vorticity,
+ * 3 dye; wall cells get the wall colour (0.5, 0.7, 0.5).  Unused inputs may be NULL. */
+int fs2d_render(float *rgb, const float *v, const float *p, const float *dye, const uint8_t *mask, fs2d_dom d, float dx,
+                int mode, void *stream);
 /* limit_field, fs/solver.py:38-43 (all cells, in place) */
 int fs2d_limit(float *v, fs2d_dom d, float limit, void *stream);
 

@@ -509,4 +509,34 @@ void orc_set_grad_n(float *fx, float *fy, const float *f, int X, int Y, int C, f
             }
 }
 
-int orc_abi_version(void) { return 2; }
+/* ==========================================================================================
+ * Render kernels: fs/fluid_simulator.py:38-58, :121-126 + fs/visualization.py:8-22.
+ * mode 0 norm (+pressure tint), 1 pressure, 2 vorticity, 3 dye.  rgb: (X, Y, 3).
+ * ======================================================================================== */
+void orc_render(float *rgb, const float *v, const float *p, const float *dye, const uint8_t *mask, int X, int Y,
+                float dx, int mode) {
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < X; ++i)
+        for (int j = 0; j < Y; ++j) {
+            float *o = rgb + 3 * IDX(i, j);
+            if (mode == 0) {          /* _to_norm :38-44 */
+                float x = v[2 * IDX(i, j)], y = v[2 * IDX(i, j) + 1];
+                float c = sqrtf(x * x + y * y);
+                float pv = p[IDX(i, j)];
+                o[0] = 0.2f * c + 0.002f * fmaxf(pv, 0.0f);
+                o[1] = 0.2f * c + 0.002f * 0.0f;
+                o[2] = 0.2f * c + 0.002f * fmaxf(-pv, 0.0f);
+            } else if (mode == 1) {   /* _to_pressure :46-51 */
+                float pv = p[IDX(i, j)];
+                o[0] = 0.04f * fmaxf(pv, 0.0f); o[1] = 0.04f * 0.0f; o[2] = 0.04f * fmaxf(-pv, 0.0f);
+            } else if (mode == 2) {   /* _to_vorticity :53-58, visualization.py:19-22 */
+                float val = DIFFX2(v, i, j, 1) - DIFFY2(v, i, j, 0);
+                o[0] = 0.005f * fmaxf(val, 0.0f); o[1] = 0.005f * 0.0f; o[2] = 0.005f * fmaxf(-val, 0.0f);
+            } else {                  /* _to_dye :121-126 */
+                for (int c = 0; c < 3; ++c) o[c] = dye[3 * IDX(i, j) + c];
+            }
+            if (mask[IDX(i, j)] == 1) { o[0] = 0.5f; o[1] = 0.7f; o[2] = 0.5f; }   /* wall colour :17 */
+        }
+}
+
+int orc_abi_version(void) { return 3; }

@@ -163,6 +163,14 @@ def set_grad_n(fx, fy, f, dx) -> None:
     lib().orc_set_grad_n(_p(fx), _p(fy), _p(f), _i(X), _i(Y), _i(C), _f(f32(dx)))
 
 
+def render(v, p, dye, mask, dx, mode: str) -> np.ndarray:
+    X, Y = mask.shape
+    rgb = np.zeros((X, Y, 3), dtype=np.float32)
+    lib().orc_render(_p(rgb), _p(v), _p(p), _p(dye) if dye is not None else None, _p(mask), _i(X), _i(Y), _f(f32(dx)),
+                     _i({"norm": 0, "pressure": 1, "vorticity": 2, "dye": 3}[mode]))
+    return rgb
+
+
 def set_threads(n: int) -> None:
     os.environ["OMP_NUM_THREADS"] = str(n)
 

@@ -311,6 +311,33 @@ def gen_dye() -> None:
         print(f"dye traj {name}: {time.time() - t0:.1f}s", flush=True)
 
 
+# --------------------------------------------------------------------------- render kernels
+def gen_render() -> None:
+    from fs.fluid_simulator import DyeFluidSimulator
+
+    rng = np.random.default_rng(77)
+    out = {}
+    for num, res in ((2, 16), (3, 20)):
+        dt, dx = 0.05 / res, 1.0 / res
+        bc = get_boundary_condition(num, res, enable_dye=True)
+        pu = JacobiPressureUpdater(bc, dt, dx, 1)
+        sim = DyeFluidSimulator(DyeCipMacSolver(bc, pu, dt, dx, 1e4, None))
+        s = sim._solver
+        X, Y = s.resolution
+        v = (rng.uniform(-1, 1, (X, Y, 2)) * 3).astype(np.float32)
+        p = (rng.uniform(-1, 1, (X, Y)) * 40).astype(np.float32)
+        dye = rng.uniform(0, 1, (X, Y, 3)).astype(np.float32)
+        s.v.current.from_numpy(v); s.p.current.from_numpy(p); s.dye.current.from_numpy(dye)
+        pre = f"bc{num}_r{res}/"
+        out[pre + "v"], out[pre + "p"], out[pre + "dye"] = v, p, dye
+        out[pre + "norm"] = sim.get_norm_field().to_numpy()
+        out[pre + "pressure"] = sim.get_pressure_field().to_numpy()
+        out[pre + "vorticity"] = sim.get_vorticity_field().to_numpy()
+        out[pre + "dye_img"] = sim.get_dye_field().to_numpy()
+    np.savez_compressed(HERE / "render.npz", **out)
+    print("render done", flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -324,3 +351,5 @@ if __name__ == "__main__":
         gen_traj(a.traj)
     if a.only in (None, "dye"):
         gen_dye()
+    if a.only in (None, "render"):
+        gen_render()

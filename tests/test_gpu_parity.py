@@ -418,3 +418,45 @@ def test_dye_simulator_vs_oracle(env, num, res, scheme):
     assert_bitexact("v", out["v"], ref.v.current); assert_bitexact("p", out["p"], ref.p.current)
     assert_bitexact("dye", out["dye"], ref.dye.current)
     assert float(out["dye"].max()) > 0.5   # dye actually entered the domain
+
+
+# ------------------------------------------------------------------------------------------------
+# 7. render getters and full-state dump / restore
+# ------------------------------------------------------------------------------------------------
+def test_render_matches_reference_fixture(env):
+    from fs.boundary_condition import DyeBoundaryCondition
+    from fs.fluid_simulator import DyeFluidSimulator, make_solver
+
+    g = np.load(GOLDEN / "render.npz")
+    sc = np.load(GOLDEN / "dye_scenes.npz")
+    for num, res in ((2, 16), (3, 20)):
+        pre = f"bc{num}_r{res}/"
+        bc = DyeBoundaryCondition(sc[f"bc{num}_r{res}_const"], sc[f"bc{num}_r{res}_dye"], sc[f"bc{num}_r{res}_mask"])
+        sim = DyeFluidSimulator(make_solver(bc, 0.05 / res, 1.0 / res, 1e4, None, "cip", pressure="jacobi", n_iter=1, dye=True))
+        s = sim.solver
+        s.v.current.from_numpy(g[pre + "v"]); s.p.current.from_numpy(g[pre + "p"]); s.dye.current.from_numpy(g[pre + "dye"])
+        assert_bitexact("norm", sim.get_norm_field().to_numpy(), g[pre + "norm"])
+        assert_bitexact("pressure", sim.get_pressure_field().to_numpy(), g[pre + "pressure"])
+        assert_bitexact("vorticity", sim.get_vorticity_field().to_numpy(), g[pre + "vorticity"])
+        assert_bitexact("dye", sim.get_dye_field().to_numpy(), g[pre + "dye_img"])
+        assert sim.rgb_buf.to_numpy().shape == (2 * res, res, 3)
+
+
+def test_state_dict_roundtrip_resumes_bitwise(env):
+    """A run restored from state_dict() continues bit-identically (the reference's npz dump cannot: no vx/vy)."""
+    from fs.fluid_simulator import DyeFluidSimulator
+
+    res = 64
+    args = (2, res, 0.05 / res, 1.0 / res, 1e4, 5.0, "cip")
+    a = DyeFluidSimulator.create(*args, pressure="jacobi", n_iter=9)
+    for _ in range(4):
+        a.step()
+    saved = a.state_dict()
+    for _ in range(3):
+        a.step()
+    b = DyeFluidSimulator.create(*args, pressure="jacobi", n_iter=9)
+    b.load_state_dict(saved)
+    for _ in range(3):
+        b.step()
+    for k, v in a.state_dict().items():
+        assert_bitexact(k, b.state_dict()[k], v)
