@@ -50,7 +50,59 @@ class FluidSimulator:
         self._rgb: Field | None = None   # image buffer (:16), allocated on first use: 12 B/cell
 
     def step(self) -> None:
-        self._solver.update()
+        if self._graphs is not None:
+            self._replay()
+        else:
+            self._solver.update()
+
+    # -- CUDA-graph stepping (not in the reference): one graph launch per time step -------------------
+    _graphs = None
+
+    def _buffers(self) -> list:
+        s = self._solver
+        return [b for b in (getattr(s, n, None) for n in ("v", "vx", "vy", "p", "dye", "dyex", "dyey")) if b is not None]
+
+    def enable_cuda_graph(self) -> None:
+        """Capture the ~100-200 kernel launches of `solver.update()` into CUDA graphs and replay them in step().
+
+        Small grids are launch-bound (a res=512 step is 150 launches of a few microseconds each).  The double
+        buffers swap roles inside a step, so a step's kernel arguments repeat with period 1 or 2; one graph is
+        captured per phase and step() replays them in turn, mirroring the swaps on the Python side so that
+        `.current` / `.next` stay truthful.  Single-rank only; results are bit-identical (same kernels)."""
+        import torch
+
+        if self._solver._bc.partition.world > 1:
+            raise NotImplementedError("CUDA-graph stepping is single-rank (NCCL exchanges are issued from the host)")
+        if self._graphs is not None:
+            return
+        self._solver.update()               # warm-up outside capture: lazy allocations, one-time validity checks
+        torch.cuda.synchronize()
+        start = [id(b.current) for b in self._buffers()]
+        graphs = []
+        for _ in range(2):                  # period <= 2: every buffer swaps a fixed number of times per step
+            before = [id(b.current) for b in self._buffers()]
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._solver.update()
+            flips = [k for k, b in enumerate(self._buffers()) if id(b.current) != before[k]]
+            graphs.append((g, flips))
+            if [id(b.current) for b in self._buffers()] == start:
+                break
+        else:
+            raise RuntimeError("buffer roles did not return to the start after two steps")
+        # the captures executed the Python-side swaps without running any kernel: roll them back, then replay
+        for g, flips in reversed(graphs):
+            for k in flips:
+                self._buffers()[k].swap()
+        self._graphs, self._phase = graphs, 0
+
+    def _replay(self) -> None:
+        g, flips = self._graphs[self._phase]
+        g.replay()
+        bufs = self._buffers()
+        for k in flips:
+            bufs[k].swap()
+        self._phase = (self._phase + 1) % len(self._graphs)
 
     # -- render getters (:22-32): (X, Y, 3) f32 images, wall cells in the wall colour -------------------
     @property

@@ -38,6 +38,7 @@ def main() -> None:
     parser.add_argument("--dump-every", type=int, default=0, help="write output/step_%%06d.npz every N steps")
     parser.add_argument("--output", type=str, default=str(Path(__file__).parent.resolve() / "output"))
     parser.add_argument("--jacobi", type=int, default=0, help="use JacobiPressureUpdater with N sweeps/step")
+    parser.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
     args = parser.parse_args()
 
     if args.cpu:
@@ -59,6 +60,8 @@ def main() -> None:
     cls = FluidSimulator if args.no_dye else DyeFluidSimulator
     fluid_sim = cls.create(n_bc, resolution, dt, dx, re, vor_eps, scheme, **kw)
 
+    if not args.no_graph:
+        fluid_sim.enable_cuda_graph()
     out = Path(args.output)
     torch.cuda.synchronize()
     t0 = time.perf_counter()

@@ -460,3 +460,22 @@ def test_state_dict_roundtrip_resumes_bitwise(env):
         b.step()
     for k, v in a.state_dict().items():
         assert_bitexact(k, b.state_dict()[k], v)
+
+
+@pytest.mark.parametrize("scheme,vc,n_iter,dye", [("cip", 5.0, 12, False), ("cip", None, 7, True), ("upwind", 5.0, 4, False)])
+def test_cuda_graph_stepping_is_bitwise_identical(env, scheme, vc, n_iter, dye):
+    """FluidSimulator.enable_cuda_graph(): graph replay == eager stepping, every physical buffer, odd/even swaps."""
+    from fs.fluid_simulator import DyeFluidSimulator, FluidSimulator
+
+    res = 96
+    cls = DyeFluidSimulator if dye else FluidSimulator
+    args = (2, res, 0.05 / res, 1.0 / res, 1e4, vc, scheme)
+    eager = cls.create(*args, pressure="jacobi", n_iter=n_iter)
+    graph = cls.create(*args, pressure="jacobi", n_iter=n_iter)
+    graph.enable_cuda_graph()
+    eager.step()                                  # enable_cuda_graph() ran one warm-up step
+    for n in range(5):
+        eager.step(); graph.step()
+        se, sg = eager.state_dict(), graph.state_dict()
+        for k in se:
+            assert_bitexact(f"step {n} {k}", sg[k], se[k])
