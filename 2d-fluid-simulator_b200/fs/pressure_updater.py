@@ -74,7 +74,7 @@ class JacobiPressureUpdater(PressureUpdater):
             self._fuse_t = sum(1 << t for t in range(1, t_max + 1) if self._bc.fused_ok(t)) if t_max > 0 else 0
         if self._fuse_t == 0 and self._bc.partition.world == 1:
             return 0
-        key = (id(p.current), id(p.next))
+        key = frozenset((id(p.current), id(p.next)))   # the pair of physical buffers, whichever is current
         if self._stale_checked != key or p.current.dirty or p.next.dirty:
             # never-written wall cells must agree between the two physical buffers (DESIGN.md "stale cells")
             ok = self._bc.stale_cells_agree(p.current, p.next)
