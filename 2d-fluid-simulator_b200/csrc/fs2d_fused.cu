@@ -177,14 +177,18 @@ __global__ void __launch_bounds__(F_THREADS, 1)
             const bool relaxed = code == FS2D_PC_FLUID || code == FS2D_PC_INFLOW || code == FS2D_PC_OUTFLOW;
             const bool e_rl = R0 + lr == d.clo, e_rh = R0 + lr == d.chi;
             const bool e_cl = C0 + c == 0, e_ch = C0 + c == d.Y - 1;
-            // a cell on the tile rim whose missing neighbour is NOT a global edge cannot be updated
-            const bool frozen = (lr == 0 && !e_rl) || (lr == FSI - 1 && !e_rh) || (c == 0 && !e_cl) || (c == FSJ - 1 && !e_ch);
-            const bool u = inside && relaxed && !frozen;
+            // Cells on the tile rim lack a neighbour, so what they compute is garbage -- harmlessly: a rim value is
+            // consumed by its inner neighbour only in the iteration in which it still holds the loaded state, and
+            // that neighbour is outside the valid region from then on anyway.  Not freezing them lets tiles
+            // without walls skip the per-cell update predicate altogether (all_upd below).
+            const bool u = inside && relaxed;
             const bool sl = u && ((pc >> 4) != 0 || e_rl || e_rh || e_cl || e_ch);
             upd |= (uint32_t)u << k;
             slow |= (uint32_t)sl << k;
             if (sl) slow_list[atomicAdd(&n_slow[par], 1)] = (uint16_t)o;   // cells that need post-BC neighbour values
         }
+
+        const bool all_upd = __syncthreads_and(upd == (1u << FK) - 1u) != 0;   // block-uniform: open-fluid tile
 
         // ---- T iterations --------------------------------------------------------------------------
         int cur = OFF_P0, nxt = OFF_W0;
@@ -214,15 +218,27 @@ __global__ void __launch_bounds__(F_THREADS, 1)
             }
             const float upx = sm[cur + o_up], dnx = sm[cur + o_dn];
             float prev_old = upx;
+            if (all_upd) {
 #pragma unroll
-            for (int k = 0; k < FK; ++k) {
-                const int o = o0 + k * FSJ;
-                const float lf = sm[cur + o + dl], rt = sm[cur + o + dr];
-                const float dnv = k < FK - 1 ? p[k + 1] : dnx;
-                const float sum = dnv + prev_old + rt + lf;  // (i+1) + (i-1) + (j+1) + (j-1), the reference's order
-                const float v = 0.25f * sum + t2[k] - t3[k];
-                prev_old = p[k];
-                p[k] = ((upd >> k) & 1u) ? v : p[k];
+                for (int k = 0; k < FK; ++k) {
+                    const int o = o0 + k * FSJ;
+                    const float lf = sm[cur + o + dl], rt = sm[cur + o + dr];
+                    const float dnv = k < FK - 1 ? p[k + 1] : dnx;
+                    const float sum = dnv + prev_old + rt + lf;  // (i+1) + (i-1) + (j+1) + (j-1), the reference's order
+                    prev_old = p[k];
+                    p[k] = 0.25f * sum + t2[k] - t3[k];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < FK; ++k) {
+                    const int o = o0 + k * FSJ;
+                    const float lf = sm[cur + o + dl], rt = sm[cur + o + dr];
+                    const float dnv = k < FK - 1 ? p[k + 1] : dnx;
+                    const float sum = dnv + prev_old + rt + lf;
+                    const float v = 0.25f * sum + t2[k] - t3[k];
+                    prev_old = p[k];
+                    p[k] = ((upd >> k) & 1u) ? v : p[k];
+                }
             }
             if (slow) {
 #pragma unroll

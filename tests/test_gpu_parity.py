@@ -479,3 +479,54 @@ def test_cuda_graph_stepping_is_bitwise_identical(env, scheme, vc, n_iter, dye):
         se, sg = eager.state_dict(), graph.state_dict()
         for k in se:
             assert_bitexact(f"step {n} {k}", sg[k], se[k])
+
+
+# ------------------------------------------------------------------------------------------------
+# 8. BASELINE full sizes
+# ------------------------------------------------------------------------------------------------
+def test_config3_full_size_step_vs_oracle(env):
+    """BASELINE config 3 exactly (bc=3 res=4096 CIP Re=1e8 vc=10, 100 Jacobi sweeps): one step, every buffer
+    bit-compared with the oracle."""
+    from fs.boundary_condition import build_scene
+    from oracle import oracle as orc
+
+    res = 4096
+    dt, dx, re, vc, pressure = 0.05 / res, 1.0 / res, 1e8, 10.0, ("jacobi", 100)
+    const, mask = build_scene(3, 2 * res, res)
+    s = make_fs(mask, const, dt, dx, re, "cip", vc, pressure)
+    ref = orc.OracleSolver(mask, const, dt, dx, re, "cip", vc, pressure)
+    s.update(); ref.update()
+    got = fs_state(s)
+    for k, a in ref.state().items():
+        assert_bitexact(f"config3 {k}", got[k].to_numpy(), a)
+
+
+def test_config5_grid_fused_equals_literal(env):
+    """BASELINE config 5's grid on ONE GPU (bc=5 res=16384: 32768 x 16384 = 537 M cells): the fused Jacobi update
+    (200 sweeps) equals 200 literal iterations bitwise -- size-independent property, no oracle needed."""
+    from fs.boundary_condition import BoundaryCondition, build_scene
+    from fs.double_buffer import DoubleBuffer, Field
+    from fs.pressure_updater import JacobiPressureUpdater
+
+    res = 16384
+    const, mask = build_scene(5, 2 * res, res)
+    bc = BoundaryCondition(const, mask)
+    del const, mask
+    X, Y = 2 * res, res
+    g = torch.Generator(device="cuda").manual_seed(3)
+    v = Field((X, Y), 2)
+    v.tensor.copy_(torch.rand(v.tensor.shape, device="cuda", generator=g) * 2 - 1)
+    p0 = torch.rand((X, Y), device="cuda", generator=g) * 2 - 1
+    res_cur = []
+    for fuse in (8, 0):
+        jac = JacobiPressureUpdater(bc, 0.05 / res, 1.0 / res, 200 if fuse else 200, fuse=fuse)
+        db = DoubleBuffer((X, Y), 1)
+        db.current.tensor.copy_(p0); db.next.tensor.copy_(p0)
+        db.current.dirty = db.next.dirty = True
+        if fuse:
+            assert jac.fuse_mask(db) != 0
+        jac.update(db, v)
+        res_cur.append(db.current.tensor.clone())
+        del db, jac
+    same = (res_cur[0] == res_cur[1]) | (res_cur[0].isnan() & res_cur[1].isnan())
+    assert bool(same.all()), f"{int((~same).sum())} cells differ"
