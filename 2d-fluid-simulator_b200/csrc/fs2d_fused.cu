@@ -274,6 +274,220 @@ __global__ void __launch_bounds__(F_THREADS, 1)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Variant 2: packed fp32x2 arithmetic (Blackwell FADD2 / FFMA2).  Thread (tx, ty) owns the column PAIR
+// (2tx, 2tx+1) and 4 consecutive rows: a row of its state is one 64-bit register pair, the i-neighbours
+// are whole pairs (own registers or one LDS.64), only the two j-neighbours outside the pair are scalar
+// LDS, and each iteration costs 3 FADD2 + 1 FFMA2 + 1 FADD2 per TWO cells.  add/sub/mul.rn.f32x2 round
+// each lane exactly like the scalar instructions (ptxas folds the *0.25 into FFMA2 only because that
+// product is exact), so results stay bit-identical.  Same tile, staging, scheduler and slow-cell fix-up as
+// variant 1.
+// ---------------------------------------------------------------------------------------------
+constexpr int GK = 4;             // rows per thread
+constexpr int GNTX = FSJ / 2;     // 64 column pairs
+constexpr int GNTY = FSI / GK;    // 16 row blocks
+
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+__global__ void __launch_bounds__(F_THREADS, 1)
+    k_jacobi_fused2(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_src,
+                    const __grid_constant__ CUtensorMap map_code, float *__restrict__ p_out, unsigned int *tile_ctr,
+                    fs2d_dom d, FusedGeom g) {
+    extern __shared__ __align__(1024) float sm[];
+    uint8_t *stg_code = reinterpret_cast<uint8_t *>(sm + OFF_BYTES);
+    uint8_t *wcode = stg_code + FSI * FCW;
+    uint16_t *slow_list = reinterpret_cast<uint16_t *>(wcode + FN);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int n_slow[2];
+    __shared__ int s_next;
+
+    const int tid = threadIdx.y * GNTX + threadIdx.x;
+    const int c = 2 * threadIdx.x;          // first tile column of the pair
+    const int lr0 = threadIdx.y * GK;       // first tile row of this thread
+    const int o0 = lr0 * FSJ + c;
+    const bool leader = tid == 0;
+    const int n_tiles = g.tiles_i * g.tiles_j;
+    constexpr uint32_t TX_BYTES = FN * (4 + 8) + FSI * FCW;
+    const CUtensorMap *mp = &map_p, *ms = &map_src, *mc = &map_code;
+#define FS2D_ISSUE(tile)                                                            \
+    do {                                                                            \
+        const int R0_ = d.r0 + ((tile) / g.tiles_j) * g.TI - g.T;                   \
+        const int C0_ = ((tile) % g.tiles_j) * g.TJ - g.HJ;                         \
+        mbar_expect_tx(&bar, TX_BYTES);                                             \
+        tma_load_2d(sm + OFF_P0, mp, C0_, R0_, &bar);                               \
+        tma_load_2d(sm + OFF_SRC, ms, 2 * C0_, R0_, &bar);                          \
+        tma_load_2d(stg_code, mc, C0_ & ~15, R0_, &bar);                            \
+    } while (0)
+
+    if (leader) {
+        mbar_init(&bar, 1);
+        n_slow[0] = n_slow[1] = 0;
+    }
+    __syncthreads();
+    int t = blockIdx.x;
+    if (leader && t < n_tiles) FS2D_ISSUE(t);
+    uint32_t parity = 0;
+    const int o_l = (c > 0 ? -1 : 0), o_r = (c + 2 < FSJ ? 2 : 1);            // j-neighbours outside the pair (clamped)
+    const int o_up = max(lr0 - 1, 0) * FSJ + c, o_dn = min(lr0 + GK, FSI - 1) * FSJ + c;
+    const uint64_t quarter = pk2(0.25f, 0.25f);
+
+    while (t < n_tiles) {
+        const int R0 = d.r0 + (t / g.tiles_j) * g.TI - g.T;
+        const int C0 = (t % g.tiles_j) * g.TJ - g.HJ;
+        const int coff = C0 - (C0 & ~15);
+        const int rlo = max(0, d.clo - R0), rhi = min(FSI - 1, d.chi - R0);
+        const int clo = max(0, -C0), chi = min(FSJ - 1, d.Y - 1 - C0);
+        const int par = parity;
+
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+
+        // ---- per-thread state: GK rows x 2 columns ------------------------------------------------
+        uint64_t p2[GK], t2p[GK], t3p[GK];   // (col c, col c+1) pairs of p, t2, t3
+        uint32_t upd = 0, slow = 0;          // bit 2k + h: row k, column c + h
+#pragma unroll
+        for (int k = 0; k < GK; ++k) {
+            const int lr = lr0 + k, o = o0 + k * FSJ;
+            p2[k] = *reinterpret_cast<const uint64_t *>(sm + OFF_P0 + o);
+            const float4 s4 = *reinterpret_cast<const float4 *>(sm + OFF_SRC + 2 * o);   // (t2, t3) of both columns
+            t2p[k] = pk2(s4.x, s4.z);
+            t3p[k] = pk2(s4.y, s4.w);
+            const uint16_t pc2 = *reinterpret_cast<const uint16_t *>(stg_code + lr * FCW + coff + c);
+            *reinterpret_cast<uint16_t *>(wcode + o) = pc2;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint8_t pc = (uint8_t)(pc2 >> (8 * h));
+                const int code = pc & 15, cc = c + h;
+                const bool inside = lr >= rlo && lr <= rhi && cc >= clo && cc <= chi;
+                const bool relaxed = code == FS2D_PC_FLUID || code == FS2D_PC_INFLOW || code == FS2D_PC_OUTFLOW;
+                const bool edge = R0 + lr == d.clo || R0 + lr == d.chi || C0 + cc == 0 || C0 + cc == d.Y - 1;
+                const bool u = inside && relaxed;   // rim cells may compute garbage, see variant 1
+                const bool sl = u && ((pc >> 4) != 0 || edge);
+                upd |= (uint32_t)u << (2 * k + h);
+                slow |= (uint32_t)sl << (2 * k + h);
+                if (sl) slow_list[atomicAdd(&n_slow[par], 1)] = (uint16_t)(o + h);
+            }
+        }
+        const bool all_upd = __syncthreads_and(upd == (1u << (2 * GK)) - 1u) != 0;
+
+        int cur = OFF_P0, nxt = OFF_W0;
+        for (int s = 0; s < g.T; ++s) {
+            __syncthreads();  // (A)
+            if (leader && s == (g.T > 1 ? 1 : 0)) {
+                n_slow[par ^ 1] = 0;
+                if (g.T > 1) {
+                    const int tn = (int)atomicAdd(tile_ctr, 1u) + (int)gridDim.x;
+                    s_next = tn;
+                    if (tn < n_tiles) FS2D_ISSUE(tn);
+                }
+            }
+            const int ns = n_slow[par];
+            if (ns > 0) {
+                for (int e = tid; e < ns; e += F_THREADS) {
+                    const int o = slow_list[e], r = o / FSJ, cc = o % FSJ;
+                    float sum = f_post(sm + cur, wcode, min(r + 1, rhi), cc, rlo, rhi, clo, chi);
+                    sum = sum + f_post(sm + cur, wcode, max(r - 1, rlo), cc, rlo, rhi, clo, chi);
+                    sum = sum + f_post(sm + cur, wcode, r, min(cc + 1, chi), rlo, rhi, clo, chi);
+                    sum = sum + f_post(sm + cur, wcode, r, max(cc - 1, clo), rlo, rhi, clo, chi);
+                    sm[nxt + o] = sum;
+                }
+                __syncthreads();  // (B)
+            }
+            const uint64_t upx = *reinterpret_cast<const uint64_t *>(sm + cur + o_up);
+            const uint64_t dnx = *reinterpret_cast<const uint64_t *>(sm + cur + o_dn);
+            uint64_t prev_old = upx;
+#pragma unroll
+            for (int k = 0; k < GK; ++k) {
+                const int o = o0 + k * FSJ;
+                const float lf = sm[cur + o + o_l], rt = sm[cur + o + o_r];
+                float own_x, own_y;
+                upk2(p2[k], own_x, own_y);
+                const uint64_t dn2 = k < GK - 1 ? p2[k + 1] : dnx;
+                // per lane: (i+1) + (i-1) + (j+1) + (j-1), the reference's order
+                const uint64_t sum2 = add2(add2(add2(dn2, prev_old), pk2(own_y, rt)), pk2(lf, own_x));
+                const uint64_t v2 = sub2(add2(mul2(quarter, sum2), t2p[k]), t3p[k]);
+                prev_old = p2[k];
+                if (all_upd) {
+                    p2[k] = v2;
+                } else {
+                    float vx, vy;
+                    upk2(v2, vx, vy);
+                    p2[k] = pk2(((upd >> (2 * k)) & 1u) ? vx : own_x, ((upd >> (2 * k + 1)) & 1u) ? vy : own_y);
+                }
+            }
+            if (slow) {
+#pragma unroll
+                for (int k = 0; k < GK; ++k) {
+                    if ((slow >> (2 * k)) & 3u) {
+                        float a, b, ta, tb, ua, ub;
+                        upk2(p2[k], a, b);
+                        upk2(t2p[k], ta, tb);
+                        upk2(t3p[k], ua, ub);
+                        if ((slow >> (2 * k)) & 1u) a = 0.25f * sm[nxt + o0 + k * FSJ] + ta - ua;
+                        if ((slow >> (2 * k + 1)) & 1u) b = 0.25f * sm[nxt + o0 + k * FSJ + 1] + tb - ub;
+                        p2[k] = pk2(a, b);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < GK; ++k) *reinterpret_cast<uint64_t *>(sm + nxt + o0 + k * FSJ) = p2[k];
+            cur = nxt;
+            nxt = (nxt == OFF_W0) ? OFF_W1 : OFF_W0;
+        }
+
+        // ---- store ---------------------------------------------------------------------------------
+#pragma unroll
+        for (int k = 0; k < GK; ++k) {
+            const int lr = lr0 + k, gr = R0 + lr;
+            if (lr >= g.T && lr < g.T + g.TI && gr < d.r1) {
+                float a, b;
+                upk2(p2[k], a, b);
+                float *dst = p_out + (size_t)gr * d.Y + (C0 + c);
+                const bool in0 = c >= g.HJ && c < g.HJ + g.TJ && C0 + c < d.Y && ((upd >> (2 * k)) & 1u);
+                const bool in1 = c + 1 >= g.HJ && c + 1 < g.HJ + g.TJ && C0 + c + 1 < d.Y && ((upd >> (2 * k + 1)) & 1u);
+                if (in0 && in1) *reinterpret_cast<float2 *>(dst) = make_float2(a, b);   // C0 + c is even: 8-byte aligned
+                else {
+                    if (in0) dst[0] = a;
+                    if (in1) dst[1] = b;
+                }
+            }
+        }
+        __syncthreads();
+        if (g.T == 1) {
+            if (leader) {
+                const int tn = (int)atomicAdd(tile_ctr, 1u) + (int)gridDim.x;
+                s_next = tn;
+                if (tn < n_tiles) FS2D_ISSUE(tn);
+            }
+            __syncthreads();
+        }
+        t = s_next;
+    }
+#undef FS2D_ISSUE
+}
+
+int g_fused_variant = 2;   // fs2d_set_tuning(1, v): 1 = scalar arithmetic, 2 = packed fp32x2
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -329,6 +543,7 @@ int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t 
     }
     if (!attr_set) {
         FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
+        FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
         attr_set = true;
     }
     CUtensorMap mp, ms, mc;
@@ -348,7 +563,8 @@ int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t 
     if (!ctr) FS2D_CUDA_CHECK(cudaMalloc(&ctr, sizeof(unsigned int)));
     FS2D_CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), s));
     ++g_launches;
-    k_jacobi_fused<<<grid, dim3(FSJ, FNTY, 1), F_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);
+    if (g_fused_variant == 2) k_jacobi_fused2<<<grid, dim3(GNTX, GNTY, 1), F_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);
+    else k_jacobi_fused<<<grid, dim3(FSJ, FNTY, 1), F_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);
     return FS2D_OK;
 }
 

@@ -197,6 +197,7 @@ extern "C" {
 
 int fs2d_set_tuning(int key, int value) {
     if (key == 0) { g_jm_rows = value; return FS2D_OK; }
+    if (key == 1 && (value == 1 || value == 2)) { fs2d::g_fused_variant = value; return FS2D_OK; }
     set_error("unknown tuning key %d", key);
     return FS2D_E_BADARG;
 }
