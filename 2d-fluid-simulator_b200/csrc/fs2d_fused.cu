@@ -485,7 +485,10 @@ __global__ void __launch_bounds__(F_THREADS, 1)
 #undef FS2D_ISSUE
 }
 
-int g_fused_variant = 2;   // fs2d_set_tuning(1, v): 1 = scalar arithmetic, 2 = packed fp32x2
+// Measured on B200 at 8192^2, T=8: variant 1 795 us/pass, variant 2 915 us/pass -- the packed variant halves the FP
+// instructions but its scalar j-neighbour LDS have a 2-way bank conflict (lane stride 2 words) and the pack/unpack
+// moves eat the rest, so the scalar variant stays the default.
+int g_fused_variant = 1;   // fs2d_set_tuning(1, v): 1 = scalar arithmetic, 2 = packed fp32x2
 
 // ---------------------------------------------------------------------------------------------
 // host side

@@ -80,31 +80,40 @@ def traffic_from_profile():
 # clocks sampling during the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms DURING the timed region (one long-lived process)."""
+
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int) -> None:
-        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self.samples, self._proc, self._t = index, [], None, None
 
-    def _run(self) -> None:
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:  # noqa: BLE001
-                pass
-            self._stop.wait(0.2)
+    def _read(self) -> None:
+        for line in self._proc.stdout:
+            parts = [x.strip() for x in line.strip().split(",")]
+            if len(parts) == 6:
+                self.samples.append(parts)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        try:
+            self._proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._read, daemon=True)
+            self._t.start()
+            time.sleep(0.25)     # first sample lands before the timed region starts; the rest fall inside it
+        except Exception:  # noqa: BLE001
+            self._proc = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self._proc is not None:
+            time.sleep(0.12)
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=3)
+            except Exception:  # noqa: BLE001
+                self._proc.kill()
+            self._t.join(timeout=3)
 
     def summary(self) -> dict:
         if not self.samples:
