@@ -163,19 +163,47 @@ __global__ void __launch_bounds__(TX *TY)
 }
 
 // =============================================================================================
-// fs/solver.py:229-240  CipMacSolver._non_advection_phase
+// The per-step CIP-path kernels below process FS2D_NU rows per thread (rows r, r+TY, ...): each row's
+// value is computed by a side-effect-free function (clamped loads are safe for any cell, wall cells just
+// compute an unused value) and stored under the kernel's write predicate afterwards, so the loads of all
+// rows are in flight together.  One row per thread left these streaming kernels latency-bound
+// (8 B in flight per thread: 2.8-3.5 TB/s).
 // =============================================================================================
+#define FS2D_ROWS(d, j, r, ok)                                                       \
+    const int j = blockIdx.y * blockDim.x + threadIdx.x;                              \
+    if (j >= (d).Y) return;                                                           \
+    int r[FS2D_NU];                                                                   \
+    bool ok[FS2D_NU];                                                                 \
+    _Pragma("unroll") for (int u = 0; u < FS2D_NU; ++u) {                             \
+        const int rr = (d).r0 + (blockIdx.x * FS2D_NU + u) * blockDim.y + threadIdx.y; \
+        ok[u] = rr < (d).r1;                                                          \
+        r[u] = ok[u] ? rr : (d).r1 - 1;                                               \
+    }
+
+// fs/solver.py:229-240  CipMacSolver._non_advection_phase
+template <bool P2>
+__device__ __forceinline__ float2 c_cip_nonadv(const float *fc, const float *pc, const fs2d_dom &d, int r, int j, float dt,
+                                               DivC<P2> ddx, DivC<P2> ddx2, float re) {
+    const float2 c = ld2(fc, d, r, j);
+    float2 gp = make_float2(diff_x1<P2>(pc, d, r, j, ddx), diff_y1<P2>(pc, d, r, j, ddx));
+    float2 g = -gp + laplace2<P2>(fc, d, r, j, c, ddx2) / re;
+    return c + g * dt;
+}
 template <bool P2>
 __global__ void __launch_bounds__(TX *TY)
     k_cip_nonadv(float *__restrict__ fn, const float *__restrict__ fc, const float *__restrict__ pc,
                  const uint8_t *__restrict__ mask, fs2d_dom d, float dt, DivC<P2> ddx, DivC<P2> ddx2, float re) {
-    FS2D_CELL(d, r, j)
-    const size_t idx = IX(d, r, j);
-    if (mask[idx] == 1) return;
-    const float2 c = __ldg(reinterpret_cast<const float2 *>(fc) + idx);
-    float2 gp = make_float2(diff_x1<P2>(pc, d, r, j, ddx), diff_y1<P2>(pc, d, r, j, ddx));
-    float2 g = -gp + laplace2<P2>(fc, d, r, j, c, ddx2) / re;
-    reinterpret_cast<float2 *>(fn)[idx] = c + g * dt;
+    FS2D_ROWS(d, j, r, ok)
+    float2 out[FS2D_NU];
+    uint8_t m[FS2D_NU];
+#pragma unroll
+    for (int u = 0; u < FS2D_NU; ++u) {
+        m[u] = __ldg(mask + IX(d, r[u], j));
+        out[u] = c_cip_nonadv<P2>(fc, pc, d, r[u], j, dt, ddx, ddx2, re);
+    }
+#pragma unroll
+    for (int u = 0; u < FS2D_NU; ++u)
+        if (ok[u] && m[u] != 1) reinterpret_cast<float2 *>(fn)[IX(d, r[u], j)] = out[u];
 }
 
 // fs/solver.py:242-261  _non_advection_phase_grad (raw indexing -> clamp)
@@ -184,28 +212,35 @@ __global__ void __launch_bounds__(TX *TY)
     k_cip_nonadv_grad(float *__restrict__ fxn, float *__restrict__ fyn, const float *__restrict__ fxc,
                       const float *__restrict__ fyc, const float *__restrict__ fc, const float *__restrict__ fn,
                       const uint8_t *__restrict__ mask, fs2d_dom d, DivC<P2> d2dx) {
-    FS2D_CELL(d, r, j)
-    const size_t idx = IX(d, r, j);
-    if (mask[idx] == 1) return;
-    float2 gx = ld2(fn, d, r + 1, j) - ld2(fc, d, r + 1, j) - ld2(fn, d, r - 1, j) + ld2(fc, d, r - 1, j);
-    float2 gy = ld2(fn, d, r, j + 1) - ld2(fc, d, r, j + 1) - ld2(fn, d, r, j - 1) + ld2(fc, d, r, j - 1);
-    reinterpret_cast<float2 *>(fxn)[idx] = __ldg(reinterpret_cast<const float2 *>(fxc) + idx) + d2dx(gx);
-    reinterpret_cast<float2 *>(fyn)[idx] = __ldg(reinterpret_cast<const float2 *>(fyc) + idx) + d2dx(gy);
+    FS2D_ROWS(d, j, r, ok)
+    float2 ox[FS2D_NU], oy[FS2D_NU];
+    uint8_t m[FS2D_NU];
+#pragma unroll
+    for (int u = 0; u < FS2D_NU; ++u) {
+        const int rr = r[u];
+        m[u] = __ldg(mask + IX(d, rr, j));
+        float2 gx = ld2(fn, d, rr + 1, j) - ld2(fc, d, rr + 1, j) - ld2(fn, d, rr - 1, j) + ld2(fc, d, rr - 1, j);
+        float2 gy = ld2(fn, d, rr, j + 1) - ld2(fc, d, rr, j + 1) - ld2(fn, d, rr, j - 1) + ld2(fc, d, rr, j - 1);
+        ox[u] = ld2(fxc, d, rr, j) + d2dx(gx);
+        oy[u] = ld2(fyc, d, rr, j) + d2dx(gy);
+    }
+#pragma unroll
+    for (int u = 0; u < FS2D_NU; ++u)
+        if (ok[u] && m[u] != 1) {
+            reinterpret_cast<float2 *>(fxn)[IX(d, r[u], j)] = ox[u];
+            reinterpret_cast<float2 *>(fyn)[IX(d, r[u], j)] = oy[u];
+        }
 }
 
 // =============================================================================================
 // fs/solver.py:267-332  _advection_phase / _cip_advect
 // =============================================================================================
+struct CipOut { float2 f, fx, fy; };
 template <bool P2>
-__global__ void __launch_bounds__(TX *TY)
-    k_cip_advect(float *__restrict__ fn, float *__restrict__ fxn, float *__restrict__ fyn,
-                 const float *__restrict__ fc, const float *__restrict__ fxc, const float *__restrict__ fyc,
-                 const float *__restrict__ v, const uint8_t *__restrict__ mask, fs2d_dom d, float dt, float dx,
-                 DivC<P2> ddx, float dx2, float dx3) {
-    FS2D_CELL(d, r, j)
-    const size_t idx = IX(d, r, j);
-    if (mask[idx] != 0) return;
-    const float2 vel = __ldg(reinterpret_cast<const float2 *>(v) + idx);
+__device__ __forceinline__ CipOut c_cip_advect(const float *fc, const float *fxc, const float *fyc, const float *v,
+                                               const fs2d_dom &d, int r, int j, float dt, float dx, DivC<P2> ddx,
+                                               float dx2, float dx3) {
+    const float2 vel = ld2(v, d, r, j);
     const float i_s = sign1(vel.x), j_s = sign1(vel.y);
     const int r_m = r - (int)i_s, j_m = j - (int)j_s;
     // +-dx^3, +-dx are exact sign flips; divisions by them are exact scalings when dx is 2^k
@@ -230,13 +265,36 @@ __global__ void __launch_bounds__(TX *TY)
     const float2 f = ddx2(3.0f * tmp3 + j_s * (y0m + 2.0f * y00) * dx);
     const float2 g = disdx(-(ym0 - y00) + c * dx2);
 
-    const float2 out = ((a * Xd + c * Yd + e) * Xd + g * Yd + x00) * Xd + ((b * Yd + dd * Xd + f) * Yd + y00) * Yd + f00;
+    CipOut o;
+    o.f = ((a * Xd + c * Yd + e) * Xd + g * Yd + x00) * Xd + ((b * Yd + dd * Xd + f) * Yd + y00) * Yd + f00;
     const float2 Fx = (3.0f * a * Xd + 2.0f * c * Yd + 2.0f * e) * Xd + (dd * Yd + g) * Yd + x00;
     const float2 Fy = (3.0f * b * Yd + 2.0f * dd * Xd + 2.0f * f) * Yd + (c * Xd + g) * Xd + y00;
-
-    reinterpret_cast<float2 *>(fn)[idx] = out;
-    reinterpret_cast<float2 *>(fxn)[idx] = Fx - dt * (Fx * dxv.x + Fy * dxv.y) / 2.0f;
-    reinterpret_cast<float2 *>(fyn)[idx] = Fy - dt * (Fx * dyv.x + Fy * dyv.y) / 2.0f;
+    o.fx = Fx - dt * (Fx * dxv.x + Fy * dxv.y) / 2.0f;
+    o.fy = Fy - dt * (Fx * dyv.x + Fy * dyv.y) / 2.0f;
+    return o;
+}
+template <bool P2>
+__global__ void __launch_bounds__(TX *TY)
+    k_cip_advect(float *__restrict__ fn, float *__restrict__ fxn, float *__restrict__ fyn,
+                 const float *__restrict__ fc, const float *__restrict__ fxc, const float *__restrict__ fyc,
+                 const float *__restrict__ v, const uint8_t *__restrict__ mask, fs2d_dom d, float dt, float dx,
+                 DivC<P2> ddx, float dx2, float dx3) {
+    FS2D_ROWS(d, j, r, ok)
+    CipOut o[FS2D_NU];
+    uint8_t m[FS2D_NU];
+#pragma unroll
+    for (int u = 0; u < FS2D_NU; ++u) {
+        m[u] = __ldg(mask + IX(d, r[u], j));
+        o[u] = c_cip_advect<P2>(fc, fxc, fyc, v, d, r[u], j, dt, dx, ddx, dx2, dx3);
+    }
+#pragma unroll
+    for (int u = 0; u < FS2D_NU; ++u)
+        if (ok[u] && m[u] == 0) {
+            const size_t idx = IX(d, r[u], j);
+            reinterpret_cast<float2 *>(fn)[idx] = o[u].f;
+            reinterpret_cast<float2 *>(fxn)[idx] = o[u].fx;
+            reinterpret_cast<float2 *>(fyn)[idx] = o[u].fy;
+        }
 }
 
 // fs/solver.py:207-211  _set_grad
@@ -256,38 +314,63 @@ template <bool P2>
 __global__ void __launch_bounds__(TX *TY)
     k_vort_calc(float *__restrict__ w, float *__restrict__ wabs, const float *__restrict__ vc,
                 const uint8_t *__restrict__ mask, fs2d_dom d, DivC<P2> ddx) {
-    FS2D_CELL(d, r, j)
-    const size_t idx = IX(d, r, j);
-    if (mask[idx] != 0) return;
-    float o = diff_x2<P2>(vc, d, r, j, ddx).y - diff_y2<P2>(vc, d, r, j, ddx).x;
-    w[idx] = o;
-    wabs[idx] = fabsf(o);
+    FS2D_ROWS(d, j, r, ok)
+    float o[FS2D_NU];
+    uint8_t m[FS2D_NU];
+#pragma unroll
+    for (int u = 0; u < FS2D_NU; ++u) {
+        m[u] = __ldg(mask + IX(d, r[u], j));
+        o[u] = diff_x2<P2>(vc, d, r[u], j, ddx).y - diff_y2<P2>(vc, d, r[u], j, ddx).x;
+    }
+#pragma unroll
+    for (int u = 0; u < FS2D_NU; ++u)
+        if (ok[u] && m[u] == 0) {
+            w[IX(d, r[u], j)] = o[u];
+            wabs[IX(d, r[u], j)] = fabsf(o[u]);
+        }
+}
+template <bool P2>
+__device__ __forceinline__ float2 c_vort_add(const float *vc, const float *w, const float *wabs, const fs2d_dom &d, int r,
+                                             int j, DivC<P2> ddx, float dtw) {
+    const float gx = diff_x1<P2>(wabs, d, r, j, ddx), gy = diff_y1<P2>(wabs, d, r, j, ddx);
+    const float nrm = sqrtf(gx * gx + gy * gy);
+    const float nx = gx / nrm, ny = gy / nrm;  // 0/0 = NaN on quiescent cells (SURVEY T2)
+    const float o = ld1(w, d, r, j);
+    float fx = ny * o, fy = -nx * o;
+    fx = fmaxf(fminf(fx, 0.1f), -0.1f);  // NaN -> +0.1 by the fminf/fmaxf rule
+    fy = fmaxf(fminf(fy, 0.1f), -0.1f);
+    const float2 c = ld2(vc, d, r, j);
+    return make_float2(c.x + dtw * fx, c.y + dtw * fy);
 }
 template <bool P2>
 __global__ void __launch_bounds__(TX *TY)
     k_vort_add(float *__restrict__ vn, const float *__restrict__ vc, const float *__restrict__ w,
                const float *__restrict__ wabs, const uint8_t *__restrict__ mask, fs2d_dom d, DivC<P2> ddx, float dtw) {
-    FS2D_CELL(d, r, j)
-    const size_t idx = IX(d, r, j);
-    if (mask[idx] != 0) return;
-    const float gx = diff_x1<P2>(wabs, d, r, j, ddx), gy = diff_y1<P2>(wabs, d, r, j, ddx);
-    const float nrm = sqrtf(gx * gx + gy * gy);
-    const float nx = gx / nrm, ny = gy / nrm;  // 0/0 = NaN on quiescent cells (SURVEY T2)
-    const float o = __ldg(w + idx);
-    float fx = ny * o, fy = -nx * o;
-    fx = fmaxf(fminf(fx, 0.1f), -0.1f);  // NaN -> +0.1 by the fminf/fmaxf rule
-    fy = fmaxf(fminf(fy, 0.1f), -0.1f);
-    const float2 c = __ldg(reinterpret_cast<const float2 *>(vc) + idx);
-    reinterpret_cast<float2 *>(vn)[idx] = make_float2(c.x + dtw * fx, c.y + dtw * fy);
+    FS2D_ROWS(d, j, r, ok)
+    float2 o[FS2D_NU];
+    uint8_t m[FS2D_NU];
+#pragma unroll
+    for (int u = 0; u < FS2D_NU; ++u) {
+        m[u] = __ldg(mask + IX(d, r[u], j));
+        o[u] = c_vort_add<P2>(vc, w, wabs, d, r[u], j, ddx, dtw);
+    }
+#pragma unroll
+    for (int u = 0; u < FS2D_NU; ++u)
+        if (ok[u] && m[u] == 0) reinterpret_cast<float2 *>(vn)[IX(d, r[u], j)] = o[u];
 }
 
 // fs/solver.py:38-43  limit_field
 __global__ void __launch_bounds__(TX *TY) k_limit(float *__restrict__ v, fs2d_dom d, float limit) {
-    FS2D_CELL(d, r, j)
-    float2 *p = reinterpret_cast<float2 *>(v) + IX(d, r, j);
-    const float2 c = *p;
-    const float nrm = sqrtf(c.x * c.x + c.y * c.y);
-    if (nrm > limit) *p = make_float2(limit * (c.x / nrm), limit * (c.y / nrm));
+    FS2D_ROWS(d, j, r, ok)
+    float2 c[FS2D_NU];
+#pragma unroll
+    for (int u = 0; u < FS2D_NU; ++u) c[u] = reinterpret_cast<const float2 *>(v)[IX(d, r[u], j)];
+#pragma unroll
+    for (int u = 0; u < FS2D_NU; ++u) {
+        const float nrm = sqrtf(c[u].x * c[u].x + c[u].y * c[u].y);
+        if (ok[u] && nrm > limit)
+            reinterpret_cast<float2 *>(v)[IX(d, r[u], j)] = make_float2(limit * (c[u].x / nrm), limit * (c[u].y / nrm));
+    }
 }
 
 }  // namespace fs2d
@@ -366,7 +449,7 @@ int fs2d_cip_nonadv(float *fn, const float *fc, const float *pc, const uint8_t *
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
     const float dx2 = dx * dx;
-#define NA(P2) ++g_launches, k_cip_nonadv<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(fn, fc, pc, mask, d, dt, DivC<P2>(dx), DivC<P2>(dx2), re)
+#define NA(P2) ++g_launches, k_cip_nonadv<P2><<<dense_grid_nu(d), dense_block(), 0, STREAM>>>(fn, fc, pc, mask, d, dt, DivC<P2>(dx), DivC<P2>(dx2), re)
     DISPATCH_P2(is_pow2(dx), NA(true), NA(false));
 #undef NA
     FS2D_LAUNCH_CHECK();
@@ -378,7 +461,7 @@ int fs2d_cip_nonadv_grad(float *fxn, float *fyn, const float *fxc, const float *
     FS2D_REQUIRE(fxn && fyn && fxc && fyc && fc && fn && mask, "null field pointer");
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
-#define NG(P2) ++g_launches, k_cip_nonadv_grad<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(fxn, fyn, fxc, fyc, fc, fn, mask, d, DivC<P2>(two_dx))
+#define NG(P2) ++g_launches, k_cip_nonadv_grad<P2><<<dense_grid_nu(d), dense_block(), 0, STREAM>>>(fxn, fyn, fxc, fyc, fc, fn, mask, d, DivC<P2>(two_dx))
     DISPATCH_P2(is_pow2(two_dx), NG(true), NG(false));
 #undef NG
     FS2D_LAUNCH_CHECK();
@@ -392,7 +475,7 @@ int fs2d_cip_advect(float *fn, float *fxn, float *fyn, const float *fc, const fl
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
     const bool p2 = is_pow2(dx) && is_pow2(dx2) && is_pow2(dx3);
-#define CA(P2) ++g_launches, k_cip_advect<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, DivC<P2>(dx), dx2, dx3)
+#define CA(P2) ++g_launches, k_cip_advect<P2><<<dense_grid_nu(d), dense_block(), 0, STREAM>>>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, DivC<P2>(dx), dx2, dx3)
     DISPATCH_P2(p2, CA(true), CA(false));
 #undef CA
     FS2D_LAUNCH_CHECK();
@@ -414,7 +497,7 @@ int fs2d_vort_calc(float *w, float *wabs, const float *vc, const uint8_t *mask, 
     FS2D_REQUIRE(w && wabs && vc && mask, "null field pointer");
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
-#define VC(P2) ++g_launches, k_vort_calc<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(w, wabs, vc, mask, d, DivC<P2>(dx))
+#define VC(P2) ++g_launches, k_vort_calc<P2><<<dense_grid_nu(d), dense_block(), 0, STREAM>>>(w, wabs, vc, mask, d, DivC<P2>(dx))
     DISPATCH_P2(is_pow2(dx), VC(true), VC(false));
 #undef VC
     FS2D_LAUNCH_CHECK();
@@ -426,7 +509,7 @@ int fs2d_vort_add(float *vn, const float *vc, const float *w, const float *wabs,
     FS2D_REQUIRE(vn && vc && w && wabs && mask, "null field pointer");
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
-#define VA(P2) ++g_launches, k_vort_add<P2><<<dense_grid(d), dense_block(), 0, STREAM>>>(vn, vc, w, wabs, mask, d, DivC<P2>(dx), dtw)
+#define VA(P2) ++g_launches, k_vort_add<P2><<<dense_grid_nu(d), dense_block(), 0, STREAM>>>(vn, vc, w, wabs, mask, d, DivC<P2>(dx), dtw)
     DISPATCH_P2(is_pow2(dx), VA(true), VA(false));
 #undef VA
     FS2D_LAUNCH_CHECK();
@@ -437,7 +520,7 @@ int fs2d_limit(float *v, fs2d_dom d, float limit, void *stream) {
     FS2D_REQUIRE(v, "null field pointer");
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
-    ++g_launches; k_limit<<<dense_grid(d), dense_block(), 0, STREAM>>>(v, d, limit);
+    ++g_launches; k_limit<<<dense_grid_nu(d), dense_block(), 0, STREAM>>>(v, d, limit);
     FS2D_LAUNCH_CHECK();
     return FS2D_OK;
 }

@@ -20,12 +20,25 @@ namespace fs2d {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TX *TY)
     k_p_source(float *__restrict__ src, const float *__restrict__ vc, fs2d_dom d, float dt, float dx) {
-    FS2D_CELL(d, r, j)
-    const float2 sx = ld2(vc, d, r + 1, j) - ld2(vc, d, r - 1, j);
-    const float2 sy = ld2(vc, d, r, j + 1) - ld2(vc, d, r, j - 1);
-    const float t2 = (sx.x * sx.x + sy.y * sy.y + (sy.x * sx.y)) / 8.0f;
-    const float t3 = dx * (sx.x + sy.y) / (8.0f * dt);
-    reinterpret_cast<float2 *>(src)[IX(d, r, j)] = make_float2(t2, t3);
+    const int j = blockIdx.y * blockDim.x + threadIdx.x;
+    if (j >= d.Y) return;
+    float2 sx[FS2D_NU], sy[FS2D_NU];
+    int r[FS2D_NU];
+    bool ok[FS2D_NU];
+#pragma unroll
+    for (int u = 0; u < FS2D_NU; ++u) {   // all loads of the thread's rows first (memory-level parallelism)
+        const int rr = d.r0 + (blockIdx.x * FS2D_NU + u) * blockDim.y + threadIdx.y;
+        ok[u] = rr < d.r1;
+        r[u] = ok[u] ? rr : d.r1 - 1;
+        sx[u] = ld2(vc, d, r[u] + 1, j) - ld2(vc, d, r[u] - 1, j);
+        sy[u] = ld2(vc, d, r[u], j + 1) - ld2(vc, d, r[u], j - 1);
+    }
+#pragma unroll
+    for (int u = 0; u < FS2D_NU; ++u) {
+        const float t2 = (sx[u].x * sx[u].x + sy[u].y * sy[u].y + (sy[u].x * sx[u].y)) / 8.0f;
+        const float t3 = dx * (sx[u].x + sy[u].y) / (8.0f * dt);
+        if (ok[u]) reinterpret_cast<float2 *>(src)[IX(d, r[u], j)] = make_float2(t2, t3);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -207,7 +220,7 @@ int fs2d_pressure_source(float *src, const float *vc, fs2d_dom d, float dt, floa
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
     ++g_launches;
-    k_p_source<<<dense_grid(d), dense_block(), 0, STREAM>>>(src, vc, d, dt, dx);
+    k_p_source<<<dense_grid_nu(d), dense_block(), 0, STREAM>>>(src, vc, d, dt, dx);
     FS2D_LAUNCH_CHECK();
     return FS2D_OK;
 }
