@@ -83,12 +83,9 @@ inline dim3 dense_block() { return dim3(TX, TY, 1); }
 inline dim3 dense_grid(const fs2d_dom &d) {
     return dim3((unsigned)((d.r1 - d.r0 + TY - 1) / TY), (unsigned)((d.Y + TX - 1) / TX), 1);
 }
-// rows per thread of the multi-row streaming kernels (fs2d_kernels.cu)
-#ifndef FS2D_NU
-#define FS2D_NU 2
-#endif
-inline dim3 dense_grid_nu(const fs2d_dom &d) {
-    return dim3((unsigned)((d.r1 - d.r0 + TY * FS2D_NU - 1) / (TY * FS2D_NU)), (unsigned)((d.Y + TX - 1) / TX), 1);
+// launch grid of the streaming kernels that process `nu` rows per thread (fs2d_kernels.cu)
+inline dim3 dense_grid_nu(const fs2d_dom &d, int nu) {
+    return dim3((unsigned)((d.r1 - d.r0 + TY * nu - 1) / (TY * nu)), (unsigned)((d.Y + TX - 1) / TX), 1);
 }
 #define FS2D_CELL(d, r, j)                                   \
     const int j = blockIdx.y * blockDim.x + threadIdx.x;     \

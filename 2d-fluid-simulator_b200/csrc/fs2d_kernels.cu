@@ -163,19 +163,25 @@ __global__ void __launch_bounds__(TX *TY)
 }
 
 // =============================================================================================
-// The per-step CIP-path kernels below process FS2D_NU rows per thread (rows r, r+TY, ...): each row's
+// The per-step CIP-path kernels below process NU rows per thread (rows r, r+TY, ...): each row's
 // value is computed by a side-effect-free function (clamped loads are safe for any cell, wall cells just
 // compute an unused value) and stored under the kernel's write predicate afterwards, so the loads of all
 // rows are in flight together.  One row per thread left these streaming kernels latency-bound
 // (8 B in flight per thread: 2.8-3.5 TB/s).
 // =============================================================================================
+constexpr int NU_CIP_NONADV = 2;
+constexpr int NU_CIP_NONADV_GRAD = 1;
+constexpr int NU_CIP_ADVECT = 1;
+constexpr int NU_VORT_CALC = 4;
+constexpr int NU_VORT_ADD = 2;
+constexpr int NU_LIMIT = 4;
 #define FS2D_ROWS(d, j, r, ok)                                                       \
     const int j = blockIdx.y * blockDim.x + threadIdx.x;                              \
     if (j >= (d).Y) return;                                                           \
-    int r[FS2D_NU];                                                                   \
-    bool ok[FS2D_NU];                                                                 \
-    _Pragma("unroll") for (int u = 0; u < FS2D_NU; ++u) {                             \
-        const int rr = (d).r0 + (blockIdx.x * FS2D_NU + u) * blockDim.y + threadIdx.y; \
+    int r[NU];                                                                        \
+    bool ok[NU];                                                                      \
+    _Pragma("unroll") for (int u = 0; u < NU; ++u) {                                  \
+        const int rr = (d).r0 + (blockIdx.x * NU + u) * blockDim.y + threadIdx.y;     \
         ok[u] = rr < (d).r1;                                                          \
         r[u] = ok[u] ? rr : (d).r1 - 1;                                               \
     }
@@ -193,16 +199,17 @@ template <bool P2>
 __global__ void __launch_bounds__(TX *TY)
     k_cip_nonadv(float *__restrict__ fn, const float *__restrict__ fc, const float *__restrict__ pc,
                  const uint8_t *__restrict__ mask, fs2d_dom d, float dt, DivC<P2> ddx, DivC<P2> ddx2, float re) {
+    constexpr int NU = NU_CIP_NONADV;
     FS2D_ROWS(d, j, r, ok)
-    float2 out[FS2D_NU];
-    uint8_t m[FS2D_NU];
+    float2 out[NU];
+    uint8_t m[NU];
 #pragma unroll
-    for (int u = 0; u < FS2D_NU; ++u) {
+    for (int u = 0; u < NU; ++u) {
         m[u] = __ldg(mask + IX(d, r[u], j));
         out[u] = c_cip_nonadv<P2>(fc, pc, d, r[u], j, dt, ddx, ddx2, re);
     }
 #pragma unroll
-    for (int u = 0; u < FS2D_NU; ++u)
+    for (int u = 0; u < NU; ++u)
         if (ok[u] && m[u] != 1) reinterpret_cast<float2 *>(fn)[IX(d, r[u], j)] = out[u];
 }
 
@@ -212,11 +219,12 @@ __global__ void __launch_bounds__(TX *TY)
     k_cip_nonadv_grad(float *__restrict__ fxn, float *__restrict__ fyn, const float *__restrict__ fxc,
                       const float *__restrict__ fyc, const float *__restrict__ fc, const float *__restrict__ fn,
                       const uint8_t *__restrict__ mask, fs2d_dom d, DivC<P2> d2dx) {
+    constexpr int NU = NU_CIP_NONADV_GRAD;
     FS2D_ROWS(d, j, r, ok)
-    float2 ox[FS2D_NU], oy[FS2D_NU];
-    uint8_t m[FS2D_NU];
+    float2 ox[NU], oy[NU];
+    uint8_t m[NU];
 #pragma unroll
-    for (int u = 0; u < FS2D_NU; ++u) {
+    for (int u = 0; u < NU; ++u) {
         const int rr = r[u];
         m[u] = __ldg(mask + IX(d, rr, j));
         float2 gx = ld2(fn, d, rr + 1, j) - ld2(fc, d, rr + 1, j) - ld2(fn, d, rr - 1, j) + ld2(fc, d, rr - 1, j);
@@ -225,7 +233,7 @@ __global__ void __launch_bounds__(TX *TY)
         oy[u] = ld2(fyc, d, rr, j) + d2dx(gy);
     }
 #pragma unroll
-    for (int u = 0; u < FS2D_NU; ++u)
+    for (int u = 0; u < NU; ++u)
         if (ok[u] && m[u] != 1) {
             reinterpret_cast<float2 *>(fxn)[IX(d, r[u], j)] = ox[u];
             reinterpret_cast<float2 *>(fyn)[IX(d, r[u], j)] = oy[u];
@@ -279,16 +287,17 @@ __global__ void __launch_bounds__(TX *TY)
                  const float *__restrict__ fc, const float *__restrict__ fxc, const float *__restrict__ fyc,
                  const float *__restrict__ v, const uint8_t *__restrict__ mask, fs2d_dom d, float dt, float dx,
                  DivC<P2> ddx, float dx2, float dx3) {
+    constexpr int NU = NU_CIP_ADVECT;
     FS2D_ROWS(d, j, r, ok)
-    CipOut o[FS2D_NU];
-    uint8_t m[FS2D_NU];
+    CipOut o[NU];
+    uint8_t m[NU];
 #pragma unroll
-    for (int u = 0; u < FS2D_NU; ++u) {
+    for (int u = 0; u < NU; ++u) {
         m[u] = __ldg(mask + IX(d, r[u], j));
         o[u] = c_cip_advect<P2>(fc, fxc, fyc, v, d, r[u], j, dt, dx, ddx, dx2, dx3);
     }
 #pragma unroll
-    for (int u = 0; u < FS2D_NU; ++u)
+    for (int u = 0; u < NU; ++u)
         if (ok[u] && m[u] == 0) {
             const size_t idx = IX(d, r[u], j);
             reinterpret_cast<float2 *>(fn)[idx] = o[u].f;
@@ -314,16 +323,17 @@ template <bool P2>
 __global__ void __launch_bounds__(TX *TY)
     k_vort_calc(float *__restrict__ w, float *__restrict__ wabs, const float *__restrict__ vc,
                 const uint8_t *__restrict__ mask, fs2d_dom d, DivC<P2> ddx) {
+    constexpr int NU = NU_VORT_CALC;
     FS2D_ROWS(d, j, r, ok)
-    float o[FS2D_NU];
-    uint8_t m[FS2D_NU];
+    float o[NU];
+    uint8_t m[NU];
 #pragma unroll
-    for (int u = 0; u < FS2D_NU; ++u) {
+    for (int u = 0; u < NU; ++u) {
         m[u] = __ldg(mask + IX(d, r[u], j));
         o[u] = diff_x2<P2>(vc, d, r[u], j, ddx).y - diff_y2<P2>(vc, d, r[u], j, ddx).x;
     }
 #pragma unroll
-    for (int u = 0; u < FS2D_NU; ++u)
+    for (int u = 0; u < NU; ++u)
         if (ok[u] && m[u] == 0) {
             w[IX(d, r[u], j)] = o[u];
             wabs[IX(d, r[u], j)] = fabsf(o[u]);
@@ -346,27 +356,29 @@ template <bool P2>
 __global__ void __launch_bounds__(TX *TY)
     k_vort_add(float *__restrict__ vn, const float *__restrict__ vc, const float *__restrict__ w,
                const float *__restrict__ wabs, const uint8_t *__restrict__ mask, fs2d_dom d, DivC<P2> ddx, float dtw) {
+    constexpr int NU = NU_VORT_ADD;
     FS2D_ROWS(d, j, r, ok)
-    float2 o[FS2D_NU];
-    uint8_t m[FS2D_NU];
+    float2 o[NU];
+    uint8_t m[NU];
 #pragma unroll
-    for (int u = 0; u < FS2D_NU; ++u) {
+    for (int u = 0; u < NU; ++u) {
         m[u] = __ldg(mask + IX(d, r[u], j));
         o[u] = c_vort_add<P2>(vc, w, wabs, d, r[u], j, ddx, dtw);
     }
 #pragma unroll
-    for (int u = 0; u < FS2D_NU; ++u)
+    for (int u = 0; u < NU; ++u)
         if (ok[u] && m[u] == 0) reinterpret_cast<float2 *>(vn)[IX(d, r[u], j)] = o[u];
 }
 
 // fs/solver.py:38-43  limit_field
 __global__ void __launch_bounds__(TX *TY) k_limit(float *__restrict__ v, fs2d_dom d, float limit) {
+    constexpr int NU = NU_LIMIT;
     FS2D_ROWS(d, j, r, ok)
-    float2 c[FS2D_NU];
+    float2 c[NU];
 #pragma unroll
-    for (int u = 0; u < FS2D_NU; ++u) c[u] = reinterpret_cast<const float2 *>(v)[IX(d, r[u], j)];
+    for (int u = 0; u < NU; ++u) c[u] = reinterpret_cast<const float2 *>(v)[IX(d, r[u], j)];
 #pragma unroll
-    for (int u = 0; u < FS2D_NU; ++u) {
+    for (int u = 0; u < NU; ++u) {
         const float nrm = sqrtf(c[u].x * c[u].x + c[u].y * c[u].y);
         if (ok[u] && nrm > limit)
             reinterpret_cast<float2 *>(v)[IX(d, r[u], j)] = make_float2(limit * (c[u].x / nrm), limit * (c[u].y / nrm));
@@ -449,7 +461,7 @@ int fs2d_cip_nonadv(float *fn, const float *fc, const float *pc, const uint8_t *
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
     const float dx2 = dx * dx;
-#define NA(P2) ++g_launches, k_cip_nonadv<P2><<<dense_grid_nu(d), dense_block(), 0, STREAM>>>(fn, fc, pc, mask, d, dt, DivC<P2>(dx), DivC<P2>(dx2), re)
+#define NA(P2) ++g_launches, k_cip_nonadv<P2><<<dense_grid_nu(d, NU_CIP_NONADV), dense_block(), 0, STREAM>>>(fn, fc, pc, mask, d, dt, DivC<P2>(dx), DivC<P2>(dx2), re)
     DISPATCH_P2(is_pow2(dx), NA(true), NA(false));
 #undef NA
     FS2D_LAUNCH_CHECK();
@@ -461,7 +473,7 @@ int fs2d_cip_nonadv_grad(float *fxn, float *fyn, const float *fxc, const float *
     FS2D_REQUIRE(fxn && fyn && fxc && fyc && fc && fn && mask, "null field pointer");
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
-#define NG(P2) ++g_launches, k_cip_nonadv_grad<P2><<<dense_grid_nu(d), dense_block(), 0, STREAM>>>(fxn, fyn, fxc, fyc, fc, fn, mask, d, DivC<P2>(two_dx))
+#define NG(P2) ++g_launches, k_cip_nonadv_grad<P2><<<dense_grid_nu(d, NU_CIP_NONADV_GRAD), dense_block(), 0, STREAM>>>(fxn, fyn, fxc, fyc, fc, fn, mask, d, DivC<P2>(two_dx))
     DISPATCH_P2(is_pow2(two_dx), NG(true), NG(false));
 #undef NG
     FS2D_LAUNCH_CHECK();
@@ -475,7 +487,7 @@ int fs2d_cip_advect(float *fn, float *fxn, float *fyn, const float *fc, const fl
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
     const bool p2 = is_pow2(dx) && is_pow2(dx2) && is_pow2(dx3);
-#define CA(P2) ++g_launches, k_cip_advect<P2><<<dense_grid_nu(d), dense_block(), 0, STREAM>>>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, DivC<P2>(dx), dx2, dx3)
+#define CA(P2) ++g_launches, k_cip_advect<P2><<<dense_grid_nu(d, NU_CIP_ADVECT), dense_block(), 0, STREAM>>>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, DivC<P2>(dx), dx2, dx3)
     DISPATCH_P2(p2, CA(true), CA(false));
 #undef CA
     FS2D_LAUNCH_CHECK();
@@ -497,7 +509,7 @@ int fs2d_vort_calc(float *w, float *wabs, const float *vc, const uint8_t *mask, 
     FS2D_REQUIRE(w && wabs && vc && mask, "null field pointer");
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
-#define VC(P2) ++g_launches, k_vort_calc<P2><<<dense_grid_nu(d), dense_block(), 0, STREAM>>>(w, wabs, vc, mask, d, DivC<P2>(dx))
+#define VC(P2) ++g_launches, k_vort_calc<P2><<<dense_grid_nu(d, NU_VORT_CALC), dense_block(), 0, STREAM>>>(w, wabs, vc, mask, d, DivC<P2>(dx))
     DISPATCH_P2(is_pow2(dx), VC(true), VC(false));
 #undef VC
     FS2D_LAUNCH_CHECK();
@@ -509,7 +521,7 @@ int fs2d_vort_add(float *vn, const float *vc, const float *w, const float *wabs,
     FS2D_REQUIRE(vn && vc && w && wabs && mask, "null field pointer");
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
-#define VA(P2) ++g_launches, k_vort_add<P2><<<dense_grid_nu(d), dense_block(), 0, STREAM>>>(vn, vc, w, wabs, mask, d, DivC<P2>(dx), dtw)
+#define VA(P2) ++g_launches, k_vort_add<P2><<<dense_grid_nu(d, NU_VORT_ADD), dense_block(), 0, STREAM>>>(vn, vc, w, wabs, mask, d, DivC<P2>(dx), dtw)
     DISPATCH_P2(is_pow2(dx), VA(true), VA(false));
 #undef VA
     FS2D_LAUNCH_CHECK();
@@ -520,7 +532,7 @@ int fs2d_limit(float *v, fs2d_dom d, float limit, void *stream) {
     FS2D_REQUIRE(v, "null field pointer");
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
-    ++g_launches; k_limit<<<dense_grid_nu(d), dense_block(), 0, STREAM>>>(v, d, limit);
+    ++g_launches; k_limit<<<dense_grid_nu(d, NU_LIMIT), dense_block(), 0, STREAM>>>(v, d, limit);
     FS2D_LAUNCH_CHECK();
     return FS2D_OK;
 }

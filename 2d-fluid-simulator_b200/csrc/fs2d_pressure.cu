@@ -18,23 +18,24 @@ namespace fs2d {
 // ---------------------------------------------------------------------------------------------
 // source terms
 // ---------------------------------------------------------------------------------------------
+constexpr int NU_P_SOURCE = 4;   // rows per thread
 __global__ void __launch_bounds__(TX *TY)
     k_p_source(float *__restrict__ src, const float *__restrict__ vc, fs2d_dom d, float dt, float dx) {
     const int j = blockIdx.y * blockDim.x + threadIdx.x;
     if (j >= d.Y) return;
-    float2 sx[FS2D_NU], sy[FS2D_NU];
-    int r[FS2D_NU];
-    bool ok[FS2D_NU];
+    float2 sx[NU_P_SOURCE], sy[NU_P_SOURCE];
+    int r[NU_P_SOURCE];
+    bool ok[NU_P_SOURCE];
 #pragma unroll
-    for (int u = 0; u < FS2D_NU; ++u) {   // all loads of the thread's rows first (memory-level parallelism)
-        const int rr = d.r0 + (blockIdx.x * FS2D_NU + u) * blockDim.y + threadIdx.y;
+    for (int u = 0; u < NU_P_SOURCE; ++u) {   // all loads of the thread's rows first (memory-level parallelism)
+        const int rr = d.r0 + (blockIdx.x * NU_P_SOURCE + u) * blockDim.y + threadIdx.y;
         ok[u] = rr < d.r1;
         r[u] = ok[u] ? rr : d.r1 - 1;
         sx[u] = ld2(vc, d, r[u] + 1, j) - ld2(vc, d, r[u] - 1, j);
         sy[u] = ld2(vc, d, r[u], j + 1) - ld2(vc, d, r[u], j - 1);
     }
 #pragma unroll
-    for (int u = 0; u < FS2D_NU; ++u) {
+    for (int u = 0; u < NU_P_SOURCE; ++u) {
         const float t2 = (sx[u].x * sx[u].x + sy[u].y * sy[u].y + (sy[u].x * sx[u].y)) / 8.0f;
         const float t3 = dx * (sx[u].x + sy[u].y) / (8.0f * dt);
         if (ok[u]) reinterpret_cast<float2 *>(src)[IX(d, r[u], j)] = make_float2(t2, t3);
@@ -220,7 +221,7 @@ int fs2d_pressure_source(float *src, const float *vc, fs2d_dom d, float dt, floa
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
     ++g_launches;
-    k_p_source<<<dense_grid_nu(d), dense_block(), 0, STREAM>>>(src, vc, d, dt, dx);
+    k_p_source<<<dense_grid_nu(d, NU_P_SOURCE), dense_block(), 0, STREAM>>>(src, vc, d, dt, dx);
     FS2D_LAUNCH_CHECK();
     return FS2D_OK;
 }
