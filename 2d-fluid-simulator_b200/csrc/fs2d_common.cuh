@@ -33,7 +33,7 @@ void launch_p_bc(float *p, const int32_t *tgt, const int32_t *src0, const int32_
                  int n, cudaStream_t s);
 inline unsigned nblk(int n, int b) { return (unsigned)((n + b - 1) / b); }
 bool is_pow2(float x);
-extern int g_fused_variant;  // fused Jacobi kernel variant (1 scalar, 2 packed fp32x2), fs2d_set_tuning(1, v)
+extern int g_fused_variant;  // fused Jacobi kernel variant (1 smem planes, 3 register tile), fs2d_set_tuning(1, v)
 // one fused pass of T Jacobi iterations p_in -> p_out (fs2d_fused.cu)
 int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t *pcode, const fs2d_dom &d, int T,
                cudaStream_t s);

@@ -274,44 +274,73 @@ __global__ void __launch_bounds__(F_THREADS, 1)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Variant 2: packed fp32x2 arithmetic (Blackwell FADD2 / FFMA2).  Thread (tx, ty) owns the column PAIR
-// (2tx, 2tx+1) and 4 consecutive rows: a row of its state is one 64-bit register pair, the i-neighbours
-// are whole pairs (own registers or one LDS.64), only the two j-neighbours outside the pair are scalar
-// LDS, and each iteration costs 3 FADD2 + 1 FFMA2 + 1 FADD2 per TWO cells.  add/sub/mul.rn.f32x2 round
-// each lane exactly like the scalar instructions (ptxas folds the *0.25 into FFMA2 only because that
-// product is exact), so results stay bit-identical.  Same tile, staging, scheduler and slow-cell fix-up as
-// variant 1.
+// Variant 3: register tile + warp shuffles.  A warp owns HK consecutive tile rows and ALL 128 tile columns;
+// lane l owns columns 4l..4l+3 of those rows, i.e. a thread keeps a 8 x 4 block of p, t2 and t3 in registers
+// for the whole pass.  Per iteration the j-neighbours outside the thread's block come from the adjacent
+// lanes by two shuffles per row (a warp spans the tile width, so no other warp is involved) and the
+// i-neighbours outside the block are the adjacent warps' edge rows, exchanged through the ping-pong planes
+// with one LDS.128 + one STS.128 per edge row.  Open-fluid tiles therefore cost ~6 FP32 + 0.7 other
+// instructions per cell-iteration (variant 1: 13) and touch shared memory only for the two edge rows of each
+// warp; tiles with cells next to BC cells / global edges additionally mirror all rows into the plane every
+// iteration so that the cooperative slow-cell fix-up of variant 1 (f_post) works unchanged.  Same tile,
+// TMA staging, tile scheduler, validity rules and arithmetic (literal order) as variant 1.
 // ---------------------------------------------------------------------------------------------
-constexpr int GK = 4;             // rows per thread
-constexpr int GNTX = FSJ / 2;     // 64 column pairs
-constexpr int GNTY = FSI / GK;    // 16 row blocks
+static_assert(FSJ == 128, "a warp (32 lanes x 4 columns) must span the tile width");
 
-__device__ __forceinline__ uint64_t pk2(float a, float b) {
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-    return r;
-}
-__device__ __forceinline__ void upk2(uint64_t v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
-    uint64_t r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
-    uint64_t r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
-    uint64_t r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
+__device__ __forceinline__ float4 lds4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void sts4(float *p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
 }
 
-__global__ void __launch_bounds__(F_THREADS, 1)
-    k_jacobi_fused2(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_src,
+// One Jacobi iteration on a thread's HK x 4 register block, in place.  up/dn: old values of the rows above / below
+// the block.  The rows are software-pipelined so that row k-1 is overwritten only after row k has consumed its old
+// values: no second register copy of the block and no end-of-iteration moves.  ALL: every cell is relaxed (no
+// per-cell select).  Every cell evaluates 0.25*((p(i+1,j)+p(i-1,j))+p(i,j+1))+p(i,j-1)) + t2 - t3, the reference's order.
+template <int HK, bool ALL>
+__device__ __forceinline__ void jacobi_rows(float (&p)[HK][4], const float (&t2)[HK][4], const float (&t3)[HK][4],
+                                            uint32_t upd, const float4 up, const float4 dn) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    float lf[HK], rt[HK];
+#pragma unroll
+    for (int k = 0; k < HK; ++k) {   // all shuffles first: their latency is paid once per iteration
+        lf[k] = __shfl_up_sync(FULL, p[k][3], 1);
+        rt[k] = __shfl_down_sync(FULL, p[k][0], 1);
+    }
+    float S[4], A[4];
+    S[0] = p[1][0] + up.x + p[0][1] + lf[0];
+    S[1] = p[1][1] + up.y + p[0][2] + p[0][0];
+    S[2] = p[1][2] + up.z + p[0][3] + p[0][1];
+    S[3] = p[1][3] + up.w + rt[0] + p[0][2];
+#pragma unroll
+    for (int k = 1; k <= HK; ++k) {
+        if (k < HK) {   // last use of the old row k-1
+            A[0] = (k < HK - 1 ? p[k + 1][0] : dn.x) + p[k - 1][0];
+            A[1] = (k < HK - 1 ? p[k + 1][1] : dn.y) + p[k - 1][1];
+            A[2] = (k < HK - 1 ? p[k + 1][2] : dn.z) + p[k - 1][2];
+            A[3] = (k < HK - 1 ? p[k + 1][3] : dn.w) + p[k - 1][3];
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {   // finish row k-1
+            const float v = 0.25f * S[h] + t2[k - 1][h] - t3[k - 1][h];
+            if (ALL) p[k - 1][h] = v;
+            else p[k - 1][h] = ((upd >> (4 * (k - 1) + h)) & 1u) ? v : p[k - 1][h];
+        }
+        if (k < HK) {
+            S[0] = A[0] + p[k][1] + lf[k];
+            S[1] = A[1] + p[k][2] + p[k][0];
+            S[2] = A[2] + p[k][3] + p[k][1];
+            S[3] = A[3] + rt[k] + p[k][2];
+        }
+    }
+}
+
+template <int HK>
+__global__ void __launch_bounds__(32 * (FSI / HK), 1)
+    k_jacobi_fused3(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_src,
                     const __grid_constant__ CUtensorMap map_code, float *__restrict__ p_out, unsigned int *tile_ctr,
                     fs2d_dom d, FusedGeom g) {
+    constexpr int H_THREADS = 32 * (FSI / HK);
+    static_assert(HK >= 2 && FSI % HK == 0 && 4 * HK <= 32, "rows per thread");
     extern __shared__ __align__(1024) float sm[];
     uint8_t *stg_code = reinterpret_cast<uint8_t *>(sm + OFF_BYTES);
     uint8_t *wcode = stg_code + FSI * FCW;
@@ -320,13 +349,15 @@ __global__ void __launch_bounds__(F_THREADS, 1)
     __shared__ int n_slow[2];
     __shared__ int s_next;
 
-    const int tid = threadIdx.y * GNTX + threadIdx.x;
-    const int c = 2 * threadIdx.x;          // first tile column of the pair
-    const int lr0 = threadIdx.y * GK;       // first tile row of this thread
-    const int o0 = lr0 * FSJ + c;
+    const int lane = threadIdx.x;
+    const int tid = threadIdx.y * 32 + lane;
+    const int c = 4 * lane;                 // first tile column of this thread
+    const int lr0 = threadIdx.y * HK;       // first tile row of this thread
+    const int o0 = lr0 * FSJ + c;           // plane offset of the thread's first cell
     const bool leader = tid == 0;
     const int n_tiles = g.tiles_i * g.tiles_j;
     constexpr uint32_t TX_BYTES = FN * (4 + 8) + FSI * FCW;
+    constexpr uint32_t BLOCK_BITS = HK == 8 ? 0xffffffffu : (1u << (4 * HK)) - 1u;   // one bit per cell of the block
     const CUtensorMap *mp = &map_p, *ms = &map_src, *mc = &map_code;
 #define FS2D_ISSUE(tile)                                                            \
     do {                                                                            \
@@ -346,63 +377,77 @@ __global__ void __launch_bounds__(F_THREADS, 1)
     int t = blockIdx.x;
     if (leader && t < n_tiles) FS2D_ISSUE(t);
     uint32_t parity = 0;
-    const int o_l = (c > 0 ? -1 : 0), o_r = (c + 2 < FSJ ? 2 : 1);            // j-neighbours outside the pair (clamped)
-    const int o_up = max(lr0 - 1, 0) * FSJ + c, o_dn = min(lr0 + GK, FSI - 1) * FSJ + c;
-    const uint64_t quarter = pk2(0.25f, 0.25f);
+    // edge rows of the adjacent warps (clamped inside the tile: rim rows compute harmless garbage, see variant 1)
+    const int o_up = max(lr0 - 1, 0) * FSJ + c, o_dn = min(lr0 + HK, FSI - 1) * FSJ + c;
+    constexpr uint32_t FULL = 0xffffffffu;
 
     while (t < n_tiles) {
         const int R0 = d.r0 + (t / g.tiles_j) * g.TI - g.T;
         const int C0 = (t % g.tiles_j) * g.TJ - g.HJ;
-        const int coff = C0 - (C0 & ~15);
+        const int coff = C0 - (C0 & ~15);   // multiple of 4: C0 is a multiple of 4
         const int rlo = max(0, d.clo - R0), rhi = min(FSI - 1, d.chi - R0);
         const int clo = max(0, -C0), chi = min(FSJ - 1, d.Y - 1 - C0);
         const int par = parity;
+        // per-thread column flags: inside the grid / on a global edge column
+        uint32_t col_in = 0, col_edge = 0;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            col_in |= (uint32_t)(c + h >= clo && c + h <= chi) << h;
+            col_edge |= (uint32_t)(C0 + c + h == 0 || C0 + c + h == d.Y - 1) << h;
+        }
 
         mbar_wait(&bar, parity);
         parity ^= 1;
 
-        // ---- per-thread state: GK rows x 2 columns ------------------------------------------------
-        uint64_t p2[GK], t2p[GK], t3p[GK];   // (col c, col c+1) pairs of p, t2, t3
-        uint32_t upd = 0, slow = 0;          // bit 2k + h: row k, column c + h
+        // ---- per-thread state from the staging buffer: HK rows x 4 columns --------------------------
+        float p[HK][4], t2[HK][4], t3[HK][4];
+        uint32_t upd = 0, slow = 0;   // bit 4k + h: row k, column c + h
 #pragma unroll
-        for (int k = 0; k < GK; ++k) {
+        for (int k = 0; k < HK; ++k) {
             const int lr = lr0 + k, o = o0 + k * FSJ;
-            p2[k] = *reinterpret_cast<const uint64_t *>(sm + OFF_P0 + o);
-            const float4 s4 = *reinterpret_cast<const float4 *>(sm + OFF_SRC + 2 * o);   // (t2, t3) of both columns
-            t2p[k] = pk2(s4.x, s4.z);
-            t3p[k] = pk2(s4.y, s4.w);
-            const uint16_t pc2 = *reinterpret_cast<const uint16_t *>(stg_code + lr * FCW + coff + c);
-            *reinterpret_cast<uint16_t *>(wcode + o) = pc2;
+            const float4 pv = lds4(sm + OFF_P0 + o);
+            const float4 s01 = lds4(sm + OFF_SRC + 2 * o), s23 = lds4(sm + OFF_SRC + 2 * o + 4);
+            p[k][0] = pv.x; p[k][1] = pv.y; p[k][2] = pv.z; p[k][3] = pv.w;
+            t2[k][0] = s01.x; t3[k][0] = s01.y; t2[k][1] = s01.z; t3[k][1] = s01.w;
+            t2[k][2] = s23.x; t3[k][2] = s23.y; t2[k][3] = s23.z; t3[k][3] = s23.w;
+            const uint32_t cw = *reinterpret_cast<const uint32_t *>(stg_code + lr * FCW + coff + c);   // 4 pcode bytes
+            *reinterpret_cast<uint32_t *>(wcode + o) = cw;
+            const bool row_in = lr >= rlo && lr <= rhi;
+            const bool row_edge = R0 + lr == d.clo || R0 + lr == d.chi;
+            if (cw == 0u && !row_edge && col_edge == 0u) {   // four open-fluid cells without BC neighbours (the common case)
+                if (row_in) upd |= col_in << (4 * k);
+            } else {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint8_t pc = (uint8_t)(pc2 >> (8 * h));
-                const int code = pc & 15, cc = c + h;
-                const bool inside = lr >= rlo && lr <= rhi && cc >= clo && cc <= chi;
-                const bool relaxed = code == FS2D_PC_FLUID || code == FS2D_PC_INFLOW || code == FS2D_PC_OUTFLOW;
-                const bool edge = R0 + lr == d.clo || R0 + lr == d.chi || C0 + cc == 0 || C0 + cc == d.Y - 1;
-                const bool u = inside && relaxed;   // rim cells may compute garbage, see variant 1
-                const bool sl = u && ((pc >> 4) != 0 || edge);
-                upd |= (uint32_t)u << (2 * k + h);
-                slow |= (uint32_t)sl << (2 * k + h);
-                if (sl) slow_list[atomicAdd(&n_slow[par], 1)] = (uint16_t)(o + h);
+                for (int h = 0; h < 4; ++h) {
+                    const uint32_t pc = (cw >> (8 * h)) & 0xffu, code = pc & 15u;
+                    const bool relaxed = code == FS2D_PC_FLUID || code == FS2D_PC_INFLOW || code == FS2D_PC_OUTFLOW;
+                    const bool u = row_in && ((col_in >> h) & 1u) && relaxed;   // rim cells may compute garbage, see variant 1
+                    const bool sl = u && ((pc >> 4) != 0u || row_edge || ((col_edge >> h) & 1u));
+                    upd |= (uint32_t)u << (4 * k + h);
+                    slow |= (uint32_t)sl << (4 * k + h);
+                    if (sl) slow_list[atomicAdd(&n_slow[par], 1)] = (uint16_t)(o + h);
+                }
             }
         }
-        const bool all_upd = __syncthreads_and(upd == (1u << (2 * GK)) - 1u) != 0;
+        const bool all_upd = __all_sync(FULL, upd == BLOCK_BITS) != 0;   // warp-uniform: open fluid in all of this warp's rows
+        __syncthreads();  // (A) wcode and the slow list are complete
+        const int ns = n_slow[par];   // block-uniform; > 0: the tile has cells next to BC cells / global edges
 
+        // ---- T iterations --------------------------------------------------------------------------
         int cur = OFF_P0, nxt = OFF_W0;
         for (int s = 0; s < g.T; ++s) {
-            __syncthreads();  // (A)
             if (leader && s == (g.T > 1 ? 1 : 0)) {
                 n_slow[par ^ 1] = 0;
-                if (g.T > 1) {
+                if (g.T > 1) {  // staging is free: fetch the next tile index and start its loads
                     const int tn = (int)atomicAdd(tile_ctr, 1u) + (int)gridDim.x;
                     s_next = tn;
                     if (tn < n_tiles) FS2D_ISSUE(tn);
                 }
             }
-            const int ns = n_slow[par];
             if (ns > 0) {
-                for (int e = tid; e < ns; e += F_THREADS) {
+                // Balanced fix-up: all threads share the slow cells and leave, in plane `nxt`, the SUM of the four
+                // post-BC neighbour values (the reference's order) for the owning thread to pick up.
+                for (int e = tid; e < ns; e += H_THREADS) {
                     const int o = slow_list[e], r = o / FSJ, cc = o % FSJ;
                     float sum = f_post(sm + cur, wcode, min(r + 1, rhi), cc, rlo, rhi, clo, chi);
                     sum = sum + f_post(sm + cur, wcode, max(r - 1, rlo), cc, rlo, rhi, clo, chi);
@@ -412,67 +457,51 @@ __global__ void __launch_bounds__(F_THREADS, 1)
                 }
                 __syncthreads();  // (B)
             }
-            const uint64_t upx = *reinterpret_cast<const uint64_t *>(sm + cur + o_up);
-            const uint64_t dnx = *reinterpret_cast<const uint64_t *>(sm + cur + o_dn);
-            uint64_t prev_old = upx;
+            const float4 upv = lds4(sm + cur + o_up), dnv = lds4(sm + cur + o_dn);
+            if (all_upd) jacobi_rows<HK, true>(p, t2, t3, upd, upv, dnv);
+            else jacobi_rows<HK, false>(p, t2, t3, upd, upv, dnv);
+            if (slow) {   // pick up the post-BC neighbour sums left in plane `nxt` by the fix-up
 #pragma unroll
-            for (int k = 0; k < GK; ++k) {
-                const int o = o0 + k * FSJ;
-                const float lf = sm[cur + o + o_l], rt = sm[cur + o + o_r];
-                float own_x, own_y;
-                upk2(p2[k], own_x, own_y);
-                const uint64_t dn2 = k < GK - 1 ? p2[k + 1] : dnx;
-                // per lane: (i+1) + (i-1) + (j+1) + (j-1), the reference's order
-                const uint64_t sum2 = add2(add2(add2(dn2, prev_old), pk2(own_y, rt)), pk2(lf, own_x));
-                const uint64_t v2 = sub2(add2(mul2(quarter, sum2), t2p[k]), t3p[k]);
-                prev_old = p2[k];
-                if (all_upd) {
-                    p2[k] = v2;
-                } else {
-                    float vx, vy;
-                    upk2(v2, vx, vy);
-                    p2[k] = pk2(((upd >> (2 * k)) & 1u) ? vx : own_x, ((upd >> (2 * k + 1)) & 1u) ? vy : own_y);
-                }
-            }
-            if (slow) {
+                for (int k = 0; k < HK; ++k) {
+                    if ((slow >> (4 * k)) & 15u) {
 #pragma unroll
-                for (int k = 0; k < GK; ++k) {
-                    if ((slow >> (2 * k)) & 3u) {
-                        float a, b, ta, tb, ua, ub;
-                        upk2(p2[k], a, b);
-                        upk2(t2p[k], ta, tb);
-                        upk2(t3p[k], ua, ub);
-                        if ((slow >> (2 * k)) & 1u) a = 0.25f * sm[nxt + o0 + k * FSJ] + ta - ua;
-                        if ((slow >> (2 * k + 1)) & 1u) b = 0.25f * sm[nxt + o0 + k * FSJ + 1] + tb - ub;
-                        p2[k] = pk2(a, b);
+                        for (int h = 0; h < 4; ++h)
+                            if ((slow >> (4 * k + h)) & 1u) p[k][h] = 0.25f * sm[nxt + o0 + k * FSJ + h] + t2[k][h] - t3[k][h];
                     }
                 }
             }
+            if (ns > 0) {   // slow tile: mirror the whole block so that f_post can read any cell
 #pragma unroll
-            for (int k = 0; k < GK; ++k) *reinterpret_cast<uint64_t *>(sm + nxt + o0 + k * FSJ) = p2[k];
+                for (int k = 0; k < HK; ++k) sts4(sm + nxt + o0 + k * FSJ, p[k][0], p[k][1], p[k][2], p[k][3]);
+            } else {        // only the block's edge rows are read by other warps
+                sts4(sm + nxt + o0, p[0][0], p[0][1], p[0][2], p[0][3]);
+                sts4(sm + nxt + o0 + (HK - 1) * FSJ, p[HK - 1][0], p[HK - 1][1], p[HK - 1][2], p[HK - 1][3]);
+            }
+            __syncthreads();  // plane `nxt` is complete; after the last iteration: all plane/list reads of this tile are done
             cur = nxt;
             nxt = (nxt == OFF_W0) ? OFF_W1 : OFF_W0;
         }
 
-        // ---- store ---------------------------------------------------------------------------------
+        // ---- store the inner (TI x TJ) cells that were updated and belong to rows [r0, r1) ----------
+        // HJ, TJ, C0 and Y are multiples of 4, so a thread's four columns are inside or outside together
+        if (c >= g.HJ && c < g.HJ + g.TJ && C0 + c < d.Y) {
 #pragma unroll
-        for (int k = 0; k < GK; ++k) {
-            const int lr = lr0 + k, gr = R0 + lr;
-            if (lr >= g.T && lr < g.T + g.TI && gr < d.r1) {
-                float a, b;
-                upk2(p2[k], a, b);
-                float *dst = p_out + (size_t)gr * d.Y + (C0 + c);
-                const bool in0 = c >= g.HJ && c < g.HJ + g.TJ && C0 + c < d.Y && ((upd >> (2 * k)) & 1u);
-                const bool in1 = c + 1 >= g.HJ && c + 1 < g.HJ + g.TJ && C0 + c + 1 < d.Y && ((upd >> (2 * k + 1)) & 1u);
-                if (in0 && in1) *reinterpret_cast<float2 *>(dst) = make_float2(a, b);   // C0 + c is even: 8-byte aligned
-                else {
-                    if (in0) dst[0] = a;
-                    if (in1) dst[1] = b;
+            for (int k = 0; k < HK; ++k) {
+                const int lr = lr0 + k, gr = R0 + lr;
+                const uint32_t m = (upd >> (4 * k)) & 15u;
+                if (lr >= g.T && lr < g.T + g.TI && gr < d.r1 && m) {
+                    float *dst = p_out + (size_t)gr * d.Y + (C0 + c);
+                    if (m == 15u) {
+                        *reinterpret_cast<float4 *>(dst) = make_float4(p[k][0], p[k][1], p[k][2], p[k][3]);
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < 4; ++h)
+                            if ((m >> h) & 1u) dst[h] = p[k][h];
+                    }
                 }
             }
         }
-        __syncthreads();
-        if (g.T == 1) {
+        if (g.T == 1) {   // the staging plane doubled as the only `cur` plane: release it only now
             if (leader) {
                 const int tn = (int)atomicAdd(tile_ctr, 1u) + (int)gridDim.x;
                 s_next = tn;
@@ -485,10 +514,10 @@ __global__ void __launch_bounds__(F_THREADS, 1)
 #undef FS2D_ISSUE
 }
 
-// Measured on B200 at 8192^2, T=8: variant 1 795 us/pass, variant 2 915 us/pass -- the packed variant halves the FP
-// instructions but its scalar j-neighbour LDS have a 2-way bank conflict (lane stride 2 words) and the pack/unpack
-// moves eat the rest, so the scalar variant stays the default.
-int g_fused_variant = 1;   // fs2d_set_tuning(1, v): 1 = scalar arithmetic, 2 = packed fp32x2
+// (A packed fp32x2 variant -- FADD2/FFMA2, column-pair ownership -- was measured at 915 us/pass vs 795 us for
+// variant 1 at 8192^2, T=8: bank-conflicted scalar j-neighbour loads and pack/unpack moves; removed.)
+int g_fused_variant = 3;   // fs2d_set_tuning(1, v): 1 = one column per thread (smem planes), 3 / 4 = register tile + shuffles
+                           // with 8 / 4 rows per thread (256 / 512 threads per CTA)
 
 // ---------------------------------------------------------------------------------------------
 // host side
@@ -546,7 +575,8 @@ int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t 
     }
     if (!attr_set) {
         FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
-        FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
+        FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
+        FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused3<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
         attr_set = true;
     }
     CUtensorMap mp, ms, mc;
@@ -566,7 +596,8 @@ int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t 
     if (!ctr) FS2D_CUDA_CHECK(cudaMalloc(&ctr, sizeof(unsigned int)));
     FS2D_CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), s));
     ++g_launches;
-    if (g_fused_variant == 2) k_jacobi_fused2<<<grid, dim3(GNTX, GNTY, 1), F_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);
+    if (g_fused_variant == 3) k_jacobi_fused3<8><<<grid, dim3(32, FSI / 8, 1), F_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);
+    else if (g_fused_variant == 4) k_jacobi_fused3<4><<<grid, dim3(32, FSI / 4, 1), F_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);
     else k_jacobi_fused<<<grid, dim3(FSJ, FNTY, 1), F_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);
     return FS2D_OK;
 }
@@ -590,7 +621,8 @@ int fs2d_jacobi_fused(float *p_out, const float *p_in, const float *src, const u
                       void *stream) {
     FS2D_REQUIRE(p_out && p_in && src && pcode && p_out != p_in, "null/aliased field pointer");
     FS2D_REQUIRE(T >= 1 && T <= F_TMAX, "fused iteration count out of range");
-    FS2D_REQUIRE(d.Y % 16 == 0 && ((uintptr_t)p_in % 16 == 0) && ((uintptr_t)src % 16 == 0) && ((uintptr_t)pcode % 16 == 0),
+    FS2D_REQUIRE(d.Y % 16 == 0 && ((uintptr_t)p_in % 16 == 0) && ((uintptr_t)p_out % 16 == 0) && ((uintptr_t)src % 16 == 0) &&
+                     ((uintptr_t)pcode % 16 == 0),
                  "fused Jacobi needs Y % 16 == 0 and 16-byte aligned fields (TMA row pitch / base alignment)");
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;

@@ -211,7 +211,7 @@ extern "C" {
 
 int fs2d_set_tuning(int key, int value) {
     if (key == 0) { g_jm_rows = value; return FS2D_OK; }
-    if (key == 1 && (value == 1 || value == 2)) { fs2d::g_fused_variant = value; return FS2D_OK; }
+    if (key == 1 && (value == 1 || value == 3 || value == 4)) { fs2d::g_fused_variant = value; return FS2D_OK; }
     set_error("unknown tuning key %d", key);
     return FS2D_E_BADARG;
 }
@@ -243,7 +243,7 @@ int fs2d_jacobi_sweep(float *pn, const float *pc, const float *src, const uint8_
 // number of buffer flips (= number of entries) must have the parity of n_sweeps so that the two PHYSICAL
 // buffers end up exactly as in the reference.
 static int plan_jacobi(int n_sweeps, int fuse_mask, int *out, int cap) {
-    static const float pass_cost[13] = {0, 362, 371, 393, 457, 550, 633, 718, 803, 945, 1087, 1212, 1336};
+    static const float pass_cost[13] = {0, 262, 269, 260, 287, 348, 398, 450, 511, 612, 683, 775, 842};   // variant 3
     const float lit_cost = 195.0f;
     const int n_lit = n_sweeps < 2 ? n_sweeps : 2, n_f = n_sweeps - n_lit;
     int n = 0;

@@ -71,7 +71,7 @@ int fs2d_version(void);
 /* number of kernels this library has launched in this process (bench.py gpu_launches) */
 unsigned long long fs2d_launch_count(void);
 /* performance knobs (never change results): key 0 = rows marched per warp by the Jacobi sweep {1,2,4,8,16};
- * key 1 = fused Jacobi kernel variant {1: scalar arithmetic (default), 2: packed fp32x2} */
+ * key 1 = fused Jacobi kernel variant {1: one column per thread, shared-memory planes; 3: register tile + warp shuffles (default)} */
 int fs2d_set_tuning(int key, int value);
 /* 1 if the library was built for sm_100a and a device of compute capability 10.x is current */
 int fs2d_device_ok(void);

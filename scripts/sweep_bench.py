@@ -31,10 +31,11 @@ for inline in (False,):
         print(f"inline={inline} rows/warp={rows:2d}: {ms*1e3:7.1f} us/sweep  algorithmic {12*X*Y/ms/1e6:7.1f} GB/s  actual~{17*X*Y/ms/1e6:7.1f} GB/s", flush=True)
 
 import os
-variant = int(os.environ.get("FUSED_VARIANT", "2"))
+variant = int(os.environ.get("FUSED_VARIANT", "3"))
 lib.fs2d_set_tuning(1, variant)
 print(f"fused passes, variant {variant} (T iterations per pass), us per iteration:")
-for T in (1, 2, 4, 6, 8, 10, 12):
+costs = {}
+for T in range(1, 13):
     if not bc.fused_ok(T):
         print("T", T, "not valid for this mask"); continue
     for _ in range(2):
@@ -46,4 +47,6 @@ for T in (1, 2, 4, 6, 8, 10, 12):
         _lib.call("fs2d_jacobi_fused", a.ptr(), b.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom, T, _lib.stream())
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
+    costs[T] = ms * 1e3
     print(f"T={T:2d}: {ms*1e3:8.1f} us/pass  {ms*1e3/T:7.1f} us/iteration  algorithmic {12*X*Y*T/ms/1e6:8.1f} GB/s", flush=True)
+print("pass_cost table:", "{0, " + ", ".join(f"{costs.get(T, 1e9):.0f}" for T in range(1, 13)) + "}")
