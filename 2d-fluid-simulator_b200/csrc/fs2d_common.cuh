@@ -51,6 +51,28 @@ __device__ __forceinline__ float2 ld2(const float *f, const fs2d_dom &d, int r, 
     return __ldg(reinterpret_cast<const float2 *>(f) + IX(d, CR(d, r), CJ(d, j)));
 }
 
+// Templated variants.  CL = true: clamp-to-edge as above.  CL = false: the caller guarantees that the access lies
+// inside the clamp window (see block_interior), so the neighbour is a plain offset from the cell -- no min/max and
+// one address computation shared by all fields.  The streaming kernels were issue-bound on this index arithmetic.
+template <bool CL>
+__device__ __forceinline__ float ld1(const float *f, const fs2d_dom &d, int r, int j) {
+    if (CL) return ld1(f, d, r, j);
+    return __ldg(f + ((ptrdiff_t)r * d.Y + j));
+}
+template <bool CL>
+__device__ __forceinline__ float2 ld2(const float *f, const fs2d_dom &d, int r, int j) {
+    if (CL) return ld2(f, d, r, j);
+    return __ldg(reinterpret_cast<const float2 *>(f) + ((ptrdiff_t)r * d.Y + j));
+}
+// True if every cell of this thread block (block_rows rows from the block's first row, blockDim.x columns) and every
+// neighbour within `halo` cells of it lies inside the clamp window [clo, chi] x [0, Y-1], and all its rows are
+// updated rows (< r1).  Block-uniform.
+__device__ __forceinline__ bool block_interior(const fs2d_dom &d, int block_rows, int halo) {
+    const int rb = d.r0 + blockIdx.x * block_rows, jb = blockIdx.y * blockDim.x;
+    return rb - halo >= d.clo && rb + block_rows - 1 + halo <= d.chi && rb + block_rows <= d.r1 && jb - halo >= 0 &&
+           jb + (int)blockDim.x - 1 + halo <= d.Y - 1;
+}
+
 // ---- float2 arithmetic with the reference's per-component order ----------------------------------
 __device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 operator-(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }

@@ -514,10 +514,250 @@ __global__ void __launch_bounds__(32 * (FSI / HK), 1)
 #undef FS2D_ISSUE
 }
 
+// ---------------------------------------------------------------------------------------------
+// Variant 5: the register-tile kernel on a TALLER tile (96 x 128 cells, 12 warps x 8 rows, 3 warps per scheduler).
+// 96 rows raise the useful fraction of a tile (T = 8: 0.73 vs 0.66), amortise the per-tile load/store phases over
+// 1.5x more cells and give the schedulers a third warp to hide shuffle / LDS latencies.  The shared memory no longer
+// holds two full working planes next to the staging buffers (that would need 246 KB), so
+//   * open-fluid tiles exchange only the edge rows of each warp through a small ping-pong buffer (EX), and
+//   * tiles with cells next to BC cells / global edges ("slow" tiles, 8 % of bc2 at 8192^2) re-use the (t2, t3)
+//     staging area -- free once every thread has its source terms in registers -- as the second working plane and the
+//     slow-cell list, read pcode straight from its staging buffer, and therefore start the next tile's TMA loads
+//     only when they are done (no overlap for these tiles).
+// ---------------------------------------------------------------------------------------------
+constexpr int VSI = 96;                       // tile rows
+constexpr int VN = VSI * FSJ;                 // cells per plane
+constexpr int V_WARPS = VSI / 8;              // 12
+constexpr int V_THREADS = 32 * V_WARPS;       // 384
+constexpr int VOFF_P0 = 0;                    // TMA destination of p; slow tiles: working plane A
+constexpr int VOFF_SRC = VN;                  // TMA destination of (t2, t3), 2*VN floats; slow tiles: working plane B (VN floats) ...
+constexpr int VOFF_LIST = 2 * VN;             // ... and the slow-cell list (VN uint16)
+constexpr int VOFF_EX = 3 * VN;               // edge-row exchange: [2][V_WARPS][2 rows][FSJ] floats
+constexpr int VEX_PLANE = V_WARPS * 2 * FSJ;
+constexpr int VOFF_BYTES = VOFF_EX + 2 * VEX_PLANE;   // staged pcode, VSI x FCW bytes
+constexpr size_t V_SMEM = (size_t)VOFF_BYTES * 4 + (size_t)VSI * FCW;
+static_assert((VOFF_BYTES * 4) % 128 == 0 && (VOFF_SRC * 4) % 128 == 0, "TMA destinations must be 128-byte aligned");
+
+// f_post for a code array with its own row pitch (the staged pcode box)
+__device__ __forceinline__ float f_post_p(const float *pl, const uint8_t *code, int cpitch, int r, int c, int rlo, int rhi,
+                                          int clo, int chi) {
+    const int rm = max(r - 1, rlo), rp = min(r + 1, rhi), cm = max(c - 1, clo), cp = min(c + 1, chi);
+    int a = r * FSJ + c, b = a, mode = 0;  // mode 0: value of cell a; 1: (a + b) / 2; 2: zero
+    switch (code[r * cpitch + c] & 15) {
+        case FS2D_PC_W_IM: a = rm * FSJ + c; break;
+        case FS2D_PC_W_IP: a = rp * FSJ + c; break;
+        case FS2D_PC_W_JM: a = r * FSJ + cm; break;
+        case FS2D_PC_W_JP: a = r * FSJ + cp; break;
+        case FS2D_PC_W_IM_JP: a = rm * FSJ + c; b = r * FSJ + cp; mode = 1; break;
+        case FS2D_PC_W_IP_JP: a = rp * FSJ + c; b = r * FSJ + cp; mode = 1; break;
+        case FS2D_PC_W_IM_JM: a = rm * FSJ + c; b = r * FSJ + cm; mode = 1; break;
+        case FS2D_PC_W_IP_JM: a = rp * FSJ + c; b = r * FSJ + cm; mode = 1; break;
+        case FS2D_PC_INFLOW: a = rp * FSJ + c; break;
+        case FS2D_PC_OUTFLOW: mode = 2; break;
+        default: break;  // FLUID / W_NONE: the stored value
+    }
+    const float va = pl[a], vb = pl[b];
+    return mode == 0 ? va : (mode == 1 ? (va + vb) / 2.0f : 0.0f);
+}
+
+__global__ void __launch_bounds__(V_THREADS, 1)
+    k_jacobi_fused5(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_src,
+                    const __grid_constant__ CUtensorMap map_code, float *__restrict__ p_out, unsigned int *tile_ctr,
+                    fs2d_dom d, FusedGeom g) {
+    constexpr int HK = 8;
+    extern __shared__ __align__(1024) float sm[];
+    uint8_t *stg_code = reinterpret_cast<uint8_t *>(sm + VOFF_BYTES);
+    uint16_t *slow_list = reinterpret_cast<uint16_t *>(sm + VOFF_LIST);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int n_slow;
+    __shared__ int s_next;
+
+    const int lane = threadIdx.x, w = threadIdx.y;
+    const int tid = w * 32 + lane;
+    const int c = 4 * lane;                 // first tile column of this thread
+    const int lr0 = w * HK;                 // first tile row of this thread
+    const int o0 = lr0 * FSJ + c;           // plane offset of the thread's first cell
+    const bool leader = tid == 0;
+    const int n_tiles = g.tiles_i * g.tiles_j;
+    constexpr uint32_t TX_BYTES = VN * (4 + 8) + VSI * FCW;
+    const CUtensorMap *mp = &map_p, *ms = &map_src, *mc = &map_code;
+#define FS2D_ISSUE(tile)                                                            \
+    do {                                                                            \
+        const int R0_ = d.r0 + ((tile) / g.tiles_j) * g.TI - g.T;                   \
+        const int C0_ = ((tile) % g.tiles_j) * g.TJ - g.HJ;                         \
+        mbar_expect_tx(&bar, TX_BYTES);                                             \
+        tma_load_2d(sm + VOFF_P0, mp, C0_, R0_, &bar);                              \
+        tma_load_2d(sm + VOFF_SRC, ms, 2 * C0_, R0_, &bar);                         \
+        tma_load_2d(stg_code, mc, C0_ & ~15, R0_, &bar);                            \
+    } while (0)
+#define FS2D_NEXT_TILE()                                                            \
+    do {                                                                            \
+        const int tn = (int)atomicAdd(tile_ctr, 1u) + (int)gridDim.x;               \
+        s_next = tn;                                                                \
+        if (tn < n_tiles) FS2D_ISSUE(tn);                                           \
+    } while (0)
+
+    if (leader) mbar_init(&bar, 1);
+    __syncthreads();
+    int t = blockIdx.x;
+    if (leader && t < n_tiles) FS2D_ISSUE(t);
+    uint32_t parity = 0;
+    // rows adjacent to the thread's block inside a full plane (clamped inside the tile: rim rows compute harmless
+    // garbage, see variant 1) and inside the exchange buffer (edge rows of the adjacent warps)
+    const int o_up = max(lr0 - 1, 0) * FSJ + c, o_dn = min(lr0 + HK, VSI - 1) * FSJ + c;
+    const int x_own = VOFF_EX + (w * 2) * FSJ + c;                                  // this warp's top row; + FSJ: bottom row
+    const int x_up = w > 0 ? VOFF_EX + ((w - 1) * 2 + 1) * FSJ + c : x_own;         // bottom row of the warp above
+    const int x_dn = w < V_WARPS - 1 ? VOFF_EX + ((w + 1) * 2) * FSJ + c : x_own + FSJ;
+    constexpr uint32_t FULL = 0xffffffffu;
+
+    while (t < n_tiles) {
+        const int R0 = d.r0 + (t / g.tiles_j) * g.TI - g.T;
+        const int C0 = (t % g.tiles_j) * g.TJ - g.HJ;
+        const int coff = C0 - (C0 & ~15);   // multiple of 4: C0 is a multiple of 4
+        const int rlo = max(0, d.clo - R0), rhi = min(VSI - 1, d.chi - R0);
+        const int clo = max(0, -C0), chi = min(FSJ - 1, d.Y - 1 - C0);
+        uint32_t col_in = 0, col_edge = 0;   // per-thread column flags: inside the grid / on a global edge column
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            col_in |= (uint32_t)(c + h >= clo && c + h <= chi) << h;
+            col_edge |= (uint32_t)(C0 + c + h == 0 || C0 + c + h == d.Y - 1) << h;
+        }
+        if (leader) n_slow = 0;   // ordered before the list is built by the barrier below
+
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+
+        // ---- per-thread state from the staging buffer: HK rows x 4 columns --------------------------
+        float p[HK][4], t2[HK][4], t3[HK][4];
+        uint32_t upd = 0, slow = 0;   // bit 4k + h: row k, column c + h
+#pragma unroll
+        for (int k = 0; k < HK; ++k) {
+            const int lr = lr0 + k, o = o0 + k * FSJ;
+            const float4 pv = lds4(sm + VOFF_P0 + o);
+            const float4 s01 = lds4(sm + VOFF_SRC + 2 * o), s23 = lds4(sm + VOFF_SRC + 2 * o + 4);
+            p[k][0] = pv.x; p[k][1] = pv.y; p[k][2] = pv.z; p[k][3] = pv.w;
+            t2[k][0] = s01.x; t3[k][0] = s01.y; t2[k][1] = s01.z; t3[k][1] = s01.w;
+            t2[k][2] = s23.x; t3[k][2] = s23.y; t2[k][3] = s23.z; t3[k][3] = s23.w;
+            const uint32_t cw = *reinterpret_cast<const uint32_t *>(stg_code + lr * FCW + coff + c);   // 4 pcode bytes
+            const bool row_in = lr >= rlo && lr <= rhi;
+            const bool row_edge = R0 + lr == d.clo || R0 + lr == d.chi;
+            if (cw == 0u && !row_edge && col_edge == 0u) {   // four open-fluid cells without BC neighbours (the common case)
+                if (row_in) upd |= col_in << (4 * k);
+            } else {
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const uint32_t pc = (cw >> (8 * h)) & 0xffu, code = pc & 15u;
+                    const bool relaxed = code == FS2D_PC_FLUID || code == FS2D_PC_INFLOW || code == FS2D_PC_OUTFLOW;
+                    const bool u = row_in && ((col_in >> h) & 1u) && relaxed;   // rim cells may compute garbage, see variant 1
+                    const bool sl = u && ((pc >> 4) != 0u || row_edge || ((col_edge >> h) & 1u));
+                    upd |= (uint32_t)u << (4 * k + h);
+                    slow |= (uint32_t)sl << (4 * k + h);
+                }
+            }
+        }
+        const bool all_upd = __all_sync(FULL, upd == FULL) != 0;   // warp-uniform: open fluid in all of this warp's rows
+        // every thread has left the staging buffers; block-uniform verdict: does the tile have slow cells?
+        const bool tile_slow = __syncthreads_or(slow != 0u) != 0;
+
+        if (!tile_slow) {
+            // ---- open-fluid tile: T iterations, only the warps' edge rows go through shared memory ---------------
+            for (int s = 0; s < g.T; ++s) {
+                if (leader && s == 1) FS2D_NEXT_TILE();   // staging is free (T > 1): start the next tile's loads
+                const int xs = ((s + 1) & 1) * VEX_PLANE;   // exchange plane written by iteration s - 1
+                const float4 upv = lds4(sm + (s == 0 ? VOFF_P0 + o_up : x_up + xs));
+                const float4 dnv = lds4(sm + (s == 0 ? VOFF_P0 + o_dn : x_dn + xs));
+                if (all_upd) jacobi_rows<HK, true>(p, t2, t3, upd, upv, dnv);
+                else jacobi_rows<HK, false>(p, t2, t3, upd, upv, dnv);
+                if (s + 1 < g.T) {
+                    const int xw = (s & 1) * VEX_PLANE;
+                    sts4(sm + x_own + xw, p[0][0], p[0][1], p[0][2], p[0][3]);
+                    sts4(sm + x_own + xw + FSJ, p[HK - 1][0], p[HK - 1][1], p[HK - 1][2], p[HK - 1][3]);
+                    __syncthreads();   // edge rows of iteration s are complete (and s_next is visible after s == 1)
+                }
+            }
+        } else {
+            // ---- slow tile: full working planes in P0 / the (t2, t3) staging area, cooperative fix-up ------------
+#pragma unroll
+            for (int k = 0; k < HK; ++k) {
+                if ((slow >> (4 * k)) & 15u) {
+#pragma unroll
+                    for (int h = 0; h < 4; ++h)
+                        if ((slow >> (4 * k + h)) & 1u) slow_list[atomicAdd(&n_slow, 1)] = (uint16_t)(o0 + k * FSJ + h);
+                }
+            }
+            __syncthreads();
+            const int ns = n_slow;
+            const uint8_t *code = stg_code + coff;   // tile pcode, row pitch FCW (the staging buffer stays intact)
+            int cur = VOFF_P0, nxt = VOFF_SRC;
+            for (int s = 0; s < g.T; ++s) {
+                // all threads share the slow cells and leave, in plane `nxt`, the SUM of the four post-BC neighbour
+                // values (the reference's order) for the owning thread to pick up
+                for (int e = tid; e < ns; e += V_THREADS) {
+                    const int o = slow_list[e], r = o / FSJ, cc = o % FSJ;
+                    float sum = f_post_p(sm + cur, code, FCW, min(r + 1, rhi), cc, rlo, rhi, clo, chi);
+                    sum = sum + f_post_p(sm + cur, code, FCW, max(r - 1, rlo), cc, rlo, rhi, clo, chi);
+                    sum = sum + f_post_p(sm + cur, code, FCW, r, min(cc + 1, chi), rlo, rhi, clo, chi);
+                    sum = sum + f_post_p(sm + cur, code, FCW, r, max(cc - 1, clo), rlo, rhi, clo, chi);
+                    sm[nxt + o] = sum;
+                }
+                __syncthreads();
+                const float4 upv = lds4(sm + cur + o_up), dnv = lds4(sm + cur + o_dn);
+                if (all_upd) jacobi_rows<HK, true>(p, t2, t3, upd, upv, dnv);
+                else jacobi_rows<HK, false>(p, t2, t3, upd, upv, dnv);
+                if (slow) {
+#pragma unroll
+                    for (int k = 0; k < HK; ++k) {
+                        if ((slow >> (4 * k)) & 15u) {
+#pragma unroll
+                            for (int h = 0; h < 4; ++h)
+                                if ((slow >> (4 * k + h)) & 1u) p[k][h] = 0.25f * sm[nxt + o0 + k * FSJ + h] + t2[k][h] - t3[k][h];
+                        }
+                    }
+                }
+                if (s + 1 < g.T) {   // mirror the whole block so that f_post can read any cell
+#pragma unroll
+                    for (int k = 0; k < HK; ++k) sts4(sm + nxt + o0 + k * FSJ, p[k][0], p[k][1], p[k][2], p[k][3]);
+                }
+                __syncthreads();   // plane `nxt` complete; after the last iteration: all plane / list / pcode reads are done
+                const int x = cur; cur = nxt; nxt = x;
+            }
+        }
+        const bool deferred = tile_slow || g.T == 1;   // the next tile's loads could not be started during the iterations
+        if (deferred) {
+            if (!tile_slow) __syncthreads();           // T == 1: the halo rows of iteration 0 were read from the staged plane
+            if (leader) FS2D_NEXT_TILE();
+        }
+
+        // ---- store the inner (TI x TJ) cells that were updated and belong to rows [r0, r1) ----------
+        // HJ, TJ, C0 and Y are multiples of 4, so a thread's four columns are inside or outside together
+        if (c >= g.HJ && c < g.HJ + g.TJ && C0 + c < d.Y) {
+#pragma unroll
+            for (int k = 0; k < HK; ++k) {
+                const int lr = lr0 + k, gr = R0 + lr;
+                const uint32_t m = (upd >> (4 * k)) & 15u;
+                if (lr >= g.T && lr < g.T + g.TI && gr < d.r1 && m) {
+                    float *dst = p_out + (size_t)gr * d.Y + (C0 + c);
+                    if (m == 15u) {
+                        *reinterpret_cast<float4 *>(dst) = make_float4(p[k][0], p[k][1], p[k][2], p[k][3]);
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < 4; ++h)
+                            if ((m >> h) & 1u) dst[h] = p[k][h];
+                    }
+                }
+            }
+        }
+        if (deferred || g.T == 2) __syncthreads();   // s_next visible to all (T >= 3: a barrier followed the s == 1 write)
+        t = s_next;
+    }
+#undef FS2D_ISSUE
+#undef FS2D_NEXT_TILE
+}
+
 // (A packed fp32x2 variant -- FADD2/FFMA2, column-pair ownership -- was measured at 915 us/pass vs 795 us for
 // variant 1 at 8192^2, T=8: bank-conflicted scalar j-neighbour loads and pack/unpack moves; removed.)
-int g_fused_variant = 3;   // fs2d_set_tuning(1, v): 1 = one column per thread (smem planes), 3 / 4 = register tile + shuffles
-                           // with 8 / 4 rows per thread (256 / 512 threads per CTA)
+int g_fused_variant = 5;   // fs2d_set_tuning(1, v): 1 = one column per thread (64 x 128 tile, smem planes); 3 = register tile +
+                           // shuffles (64 x 128 tile); 5 = register tile on a 96 x 128 tile
 
 // ---------------------------------------------------------------------------------------------
 // host side
@@ -559,6 +799,8 @@ static int make_map(CUtensorMap *m, CUtensorMapDataType dt, size_t esz, const vo
     return FS2D_OK;
 }
 
+int fused_tile_rows() { return g_fused_variant == 5 ? VSI : FSI; }
+
 bool fused_supported(const float *pa, const float *pb, const float *src, const uint8_t *pcode, const fs2d_dom &d) {
     return d.Y % 16 == 0 && ((uintptr_t)pa % 16 == 0) && ((uintptr_t)pb % 16 == 0) && ((uintptr_t)src % 16 == 0) &&
            ((uintptr_t)pcode % 16 == 0);
@@ -576,17 +818,18 @@ int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t 
     if (!attr_set) {
         FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
         FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
-        FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused3<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
+        FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM));
         attr_set = true;
     }
     CUtensorMap mp, ms, mc;
-    if (int e = make_map(&mp, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p_in, d.Y, d.rows, FSJ, FSI)) return e;
-    if (int e = make_map(&ms, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, src, 2ull * d.Y, d.rows, 2 * FSJ, FSI)) return e;
-    if (int e = make_map(&mc, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, pcode, d.Y, d.rows, FCW, FSI)) return e;
+    const int tile_rows = fused_tile_rows();
+    if (int e = make_map(&mp, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p_in, d.Y, d.rows, FSJ, tile_rows)) return e;
+    if (int e = make_map(&ms, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, src, 2ull * d.Y, d.rows, 2 * FSJ, tile_rows)) return e;
+    if (int e = make_map(&mc, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, pcode, d.Y, d.rows, FCW, tile_rows)) return e;
     FusedGeom g;
     g.T = T;
     g.HJ = (T + 3) & ~3;
-    g.TI = FSI - 2 * T;
+    g.TI = tile_rows - 2 * T;
     g.TJ = FSJ - 2 * g.HJ;
     g.tiles_i = (d.r1 - d.r0 + g.TI - 1) / g.TI;
     g.tiles_j = (d.Y + g.TJ - 1) / g.TJ;
@@ -597,7 +840,7 @@ int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t 
     FS2D_CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), s));
     ++g_launches;
     if (g_fused_variant == 3) k_jacobi_fused3<8><<<grid, dim3(32, FSI / 8, 1), F_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);
-    else if (g_fused_variant == 4) k_jacobi_fused3<4><<<grid, dim3(32, FSI / 4, 1), F_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);
+    else if (g_fused_variant == 5) k_jacobi_fused5<<<grid, dim3(32, V_WARPS, 1), V_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);
     else k_jacobi_fused<<<grid, dim3(FSJ, FNTY, 1), F_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);
     return FS2D_OK;
 }
@@ -609,7 +852,7 @@ using namespace fs2d;
 extern "C" {
 
 int fs2d_fused_tile(int T, int *rows, int *cols, int *halo_rows, int *halo_cols, int *t_max) {
-    if (rows) *rows = FSI;
+    if (rows) *rows = fused_tile_rows();
     if (cols) *cols = FSJ;
     if (halo_rows) *halo_rows = T;
     if (halo_cols) *halo_cols = (T + 3) & ~3;

@@ -87,27 +87,28 @@ void launch_p_bc(float *p, const int32_t *tgt, const int32_t *src0, const int32_
 // =============================================================================================
 // stencil building blocks (fs/differentiation.py:41-60), per component of a float2 field
 // =============================================================================================
-template <bool P2>
+// CL: clamp-to-edge loads (true, any cell) or plain neighbour offsets (false, interior blocks; fs2d_common.cuh)
+template <bool P2, bool CL = true>
 __device__ __forceinline__ float2 diff_x2(const float *f, const fs2d_dom &d, int r, int j, DivC<P2> ddx) {
-    return ddx(0.5f * (ld2(f, d, r + 1, j) - ld2(f, d, r - 1, j)));
+    return ddx(0.5f * (ld2<CL>(f, d, r + 1, j) - ld2<CL>(f, d, r - 1, j)));
 }
-template <bool P2>
+template <bool P2, bool CL = true>
 __device__ __forceinline__ float2 diff_y2(const float *f, const fs2d_dom &d, int r, int j, DivC<P2> ddx) {
-    return ddx(0.5f * (ld2(f, d, r, j + 1) - ld2(f, d, r, j - 1)));
+    return ddx(0.5f * (ld2<CL>(f, d, r, j + 1) - ld2<CL>(f, d, r, j - 1)));
 }
-template <bool P2>
+template <bool P2, bool CL = true>
 __device__ __forceinline__ float diff_x1(const float *f, const fs2d_dom &d, int r, int j, DivC<P2> ddx) {
-    return ddx(0.5f * (ld1(f, d, r + 1, j) - ld1(f, d, r - 1, j)));
+    return ddx(0.5f * (ld1<CL>(f, d, r + 1, j) - ld1<CL>(f, d, r - 1, j)));
 }
-template <bool P2>
+template <bool P2, bool CL = true>
 __device__ __forceinline__ float diff_y1(const float *f, const fs2d_dom &d, int r, int j, DivC<P2> ddx) {
-    return ddx(0.5f * (ld1(f, d, r, j + 1) - ld1(f, d, r, j - 1)));
+    return ddx(0.5f * (ld1<CL>(f, d, r, j + 1) - ld1<CL>(f, d, r, j - 1)));
 }
 // (diff2_x + diff2_y) of a float2 field; ddx2 divides by dx*dx
-template <bool P2>
+template <bool P2, bool CL = true>
 __device__ __forceinline__ float2 laplace2(const float *f, const fs2d_dom &d, int r, int j, float2 c, DivC<P2> ddx2) {
-    float2 d2x = ddx2(ld2(f, d, r + 1, j) - 2.0f * c + ld2(f, d, r - 1, j));
-    float2 d2y = ddx2(ld2(f, d, r, j + 1) - 2.0f * c + ld2(f, d, r, j - 1));
+    float2 d2x = ddx2(ld2<CL>(f, d, r + 1, j) - 2.0f * c + ld2<CL>(f, d, r - 1, j));
+    float2 d2y = ddx2(ld2<CL>(f, d, r, j + 1) - 2.0f * c + ld2<CL>(f, d, r, j - 1));
     return d2x + d2y;
 }
 
@@ -187,18 +188,18 @@ constexpr int NU_LIMIT = 4;
     }
 
 // fs/solver.py:229-240  CipMacSolver._non_advection_phase
-template <bool P2>
+template <bool P2, bool CL>
 __device__ __forceinline__ float2 c_cip_nonadv(const float *fc, const float *pc, const fs2d_dom &d, int r, int j, float dt,
                                                DivC<P2> ddx, DivC<P2> ddx2, float re) {
-    const float2 c = ld2(fc, d, r, j);
-    float2 gp = make_float2(diff_x1<P2>(pc, d, r, j, ddx), diff_y1<P2>(pc, d, r, j, ddx));
-    float2 g = -gp + laplace2<P2>(fc, d, r, j, c, ddx2) / re;
+    const float2 c = ld2<CL>(fc, d, r, j);
+    float2 gp = make_float2(diff_x1<P2, CL>(pc, d, r, j, ddx), diff_y1<P2, CL>(pc, d, r, j, ddx));
+    float2 g = -gp + laplace2<P2, CL>(fc, d, r, j, c, ddx2) / re;
     return c + g * dt;
 }
-template <bool P2>
-__global__ void __launch_bounds__(TX *TY)
-    k_cip_nonadv(float *__restrict__ fn, const float *__restrict__ fc, const float *__restrict__ pc,
-                 const uint8_t *__restrict__ mask, fs2d_dom d, float dt, DivC<P2> ddx, DivC<P2> ddx2, float re) {
+template <bool P2, bool CL>
+__device__ __forceinline__ void b_cip_nonadv(float *__restrict__ fn, const float *__restrict__ fc, const float *__restrict__ pc,
+                                             const uint8_t *__restrict__ mask, const fs2d_dom &d, float dt, DivC<P2> ddx,
+                                             DivC<P2> ddx2, float re) {
     constexpr int NU = NU_CIP_NONADV;
     FS2D_ROWS(d, j, r, ok)
     float2 out[NU];
@@ -206,19 +207,26 @@ __global__ void __launch_bounds__(TX *TY)
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
         m[u] = __ldg(mask + IX(d, r[u], j));
-        out[u] = c_cip_nonadv<P2>(fc, pc, d, r[u], j, dt, ddx, ddx2, re);
+        out[u] = c_cip_nonadv<P2, CL>(fc, pc, d, r[u], j, dt, ddx, ddx2, re);
     }
 #pragma unroll
     for (int u = 0; u < NU; ++u)
         if (ok[u] && m[u] != 1) reinterpret_cast<float2 *>(fn)[IX(d, r[u], j)] = out[u];
 }
-
-// fs/solver.py:242-261  _non_advection_phase_grad (raw indexing -> clamp, SURVEY T3)
 template <bool P2>
 __global__ void __launch_bounds__(TX *TY)
-    k_cip_nonadv_grad(float *__restrict__ fxn, float *__restrict__ fyn, const float *__restrict__ fxc,
-                      const float *__restrict__ fyc, const float *__restrict__ fc, const float *__restrict__ fn,
-                      const uint8_t *__restrict__ mask, fs2d_dom d, DivC<P2> d2dx) {
+    k_cip_nonadv(float *__restrict__ fn, const float *__restrict__ fc, const float *__restrict__ pc,
+                 const uint8_t *__restrict__ mask, fs2d_dom d, float dt, DivC<P2> ddx, DivC<P2> ddx2, float re) {
+    if (block_interior(d, TY * NU_CIP_NONADV, 1)) b_cip_nonadv<P2, false>(fn, fc, pc, mask, d, dt, ddx, ddx2, re);
+    else b_cip_nonadv<P2, true>(fn, fc, pc, mask, d, dt, ddx, ddx2, re);
+}
+
+// fs/solver.py:242-261  _non_advection_phase_grad (raw indexing -> clamp, SURVEY T3)
+template <bool P2, bool CL>
+__device__ __forceinline__ void b_cip_nonadv_grad(float *__restrict__ fxn, float *__restrict__ fyn, const float *__restrict__ fxc,
+                                                  const float *__restrict__ fyc, const float *__restrict__ fc,
+                                                  const float *__restrict__ fn, const uint8_t *__restrict__ mask,
+                                                  const fs2d_dom &d, DivC<P2> d2dx) {
     constexpr int NU = NU_CIP_NONADV_GRAD;
     FS2D_ROWS(d, j, r, ok)
     float2 ox[NU], oy[NU];
@@ -227,10 +235,10 @@ __global__ void __launch_bounds__(TX *TY)
     for (int u = 0; u < NU; ++u) {
         const int rr = r[u];
         m[u] = __ldg(mask + IX(d, rr, j));
-        float2 gx = ld2(fn, d, rr + 1, j) - ld2(fc, d, rr + 1, j) - ld2(fn, d, rr - 1, j) + ld2(fc, d, rr - 1, j);
-        float2 gy = ld2(fn, d, rr, j + 1) - ld2(fc, d, rr, j + 1) - ld2(fn, d, rr, j - 1) + ld2(fc, d, rr, j - 1);
-        ox[u] = ld2(fxc, d, rr, j) + d2dx(gx);
-        oy[u] = ld2(fyc, d, rr, j) + d2dx(gy);
+        float2 gx = ld2<CL>(fn, d, rr + 1, j) - ld2<CL>(fc, d, rr + 1, j) - ld2<CL>(fn, d, rr - 1, j) + ld2<CL>(fc, d, rr - 1, j);
+        float2 gy = ld2<CL>(fn, d, rr, j + 1) - ld2<CL>(fc, d, rr, j + 1) - ld2<CL>(fn, d, rr, j - 1) + ld2<CL>(fc, d, rr, j - 1);
+        ox[u] = ld2<CL>(fxc, d, rr, j) + d2dx(gx);
+        oy[u] = ld2<CL>(fyc, d, rr, j) + d2dx(gy);
     }
 #pragma unroll
     for (int u = 0; u < NU; ++u)
@@ -239,27 +247,35 @@ __global__ void __launch_bounds__(TX *TY)
             reinterpret_cast<float2 *>(fyn)[IX(d, r[u], j)] = oy[u];
         }
 }
+template <bool P2>
+__global__ void __launch_bounds__(TX *TY)
+    k_cip_nonadv_grad(float *__restrict__ fxn, float *__restrict__ fyn, const float *__restrict__ fxc,
+                      const float *__restrict__ fyc, const float *__restrict__ fc, const float *__restrict__ fn,
+                      const uint8_t *__restrict__ mask, fs2d_dom d, DivC<P2> d2dx) {
+    if (block_interior(d, TY * NU_CIP_NONADV_GRAD, 1)) b_cip_nonadv_grad<P2, false>(fxn, fyn, fxc, fyc, fc, fn, mask, d, d2dx);
+    else b_cip_nonadv_grad<P2, true>(fxn, fyn, fxc, fyc, fc, fn, mask, d, d2dx);
+}
 
 // =============================================================================================
 // fs/solver.py:267-332  _advection_phase / _cip_advect
 // =============================================================================================
 struct CipOut { float2 f, fx, fy; };
-template <bool P2>
+template <bool P2, bool CL>
 __device__ __forceinline__ CipOut c_cip_advect(const float *fc, const float *fxc, const float *fyc, const float *v,
                                                const fs2d_dom &d, int r, int j, float dt, float dx, DivC<P2> ddx,
                                                float dx2, float dx3) {
-    const float2 vel = ld2(v, d, r, j);
+    const float2 vel = ld2<CL>(v, d, r, j);
     const float i_s = sign1(vel.x), j_s = sign1(vel.y);
     const int r_m = r - (int)i_s, j_m = j - (int)j_s;
     // +-dx^3, +-dx are exact sign flips; divisions by them are exact scalings when dx is 2^k
     const DivC<P2> disd(i_s * dx3), djsd(j_s * dx3), ddx2(dx2), disdx(i_s * dx);
     const float Xd = -vel.x * dt, Yd = -vel.y * dt;
-    const float2 dxv = diff_x2<P2>(v, d, r, j, ddx);  // (d/dx u, d/dx v)
-    const float2 dyv = diff_y2<P2>(v, d, r, j, ddx);
+    const float2 dxv = diff_x2<P2, CL>(v, d, r, j, ddx);  // (d/dx u, d/dx v)
+    const float2 dyv = diff_y2<P2, CL>(v, d, r, j, ddx);
 
-    const float2 f00 = ld2(fc, d, r, j), f0m = ld2(fc, d, r, j_m), fm0 = ld2(fc, d, r_m, j), fmm = ld2(fc, d, r_m, j_m);
-    const float2 x00 = ld2(fxc, d, r, j), x0m = ld2(fxc, d, r, j_m), xm0 = ld2(fxc, d, r_m, j);
-    const float2 y00 = ld2(fyc, d, r, j), y0m = ld2(fyc, d, r, j_m), ym0 = ld2(fyc, d, r_m, j);
+    const float2 f00 = ld2<CL>(fc, d, r, j), f0m = ld2<CL>(fc, d, r, j_m), fm0 = ld2<CL>(fc, d, r_m, j), fmm = ld2<CL>(fc, d, r_m, j_m);
+    const float2 x00 = ld2<CL>(fxc, d, r, j), x0m = ld2<CL>(fxc, d, r, j_m), xm0 = ld2<CL>(fxc, d, r_m, j);
+    const float2 y00 = ld2<CL>(fyc, d, r, j), y0m = ld2<CL>(fyc, d, r, j_m), ym0 = ld2<CL>(fyc, d, r_m, j);
 
     const float2 tmp1 = f00 - f0m - fm0 + fmm;
     const float2 tmp2 = fm0 - f00;
@@ -281,12 +297,12 @@ __device__ __forceinline__ CipOut c_cip_advect(const float *fc, const float *fxc
     o.fy = Fy - dt * (Fx * dyv.x + Fy * dyv.y) / 2.0f;
     return o;
 }
-template <bool P2>
-__global__ void __launch_bounds__(TX *TY)
-    k_cip_advect(float *__restrict__ fn, float *__restrict__ fxn, float *__restrict__ fyn,
-                 const float *__restrict__ fc, const float *__restrict__ fxc, const float *__restrict__ fyc,
-                 const float *__restrict__ v, const uint8_t *__restrict__ mask, fs2d_dom d, float dt, float dx,
-                 DivC<P2> ddx, float dx2, float dx3) {
+template <bool P2, bool CL>
+__device__ __forceinline__ void b_cip_advect(float *__restrict__ fn, float *__restrict__ fxn, float *__restrict__ fyn,
+                                             const float *__restrict__ fc, const float *__restrict__ fxc,
+                                             const float *__restrict__ fyc, const float *__restrict__ v,
+                                             const uint8_t *__restrict__ mask, const fs2d_dom &d, float dt, float dx,
+                                             DivC<P2> ddx, float dx2, float dx3) {
     constexpr int NU = NU_CIP_ADVECT;
     FS2D_ROWS(d, j, r, ok)
     CipOut o[NU];
@@ -294,7 +310,7 @@ __global__ void __launch_bounds__(TX *TY)
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
         m[u] = __ldg(mask + IX(d, r[u], j));
-        o[u] = c_cip_advect<P2>(fc, fxc, fyc, v, d, r[u], j, dt, dx, ddx, dx2, dx3);
+        o[u] = c_cip_advect<P2, CL>(fc, fxc, fyc, v, d, r[u], j, dt, dx, ddx, dx2, dx3);
     }
 #pragma unroll
     for (int u = 0; u < NU; ++u)
@@ -304,6 +320,15 @@ __global__ void __launch_bounds__(TX *TY)
             reinterpret_cast<float2 *>(fxn)[idx] = o[u].fx;
             reinterpret_cast<float2 *>(fyn)[idx] = o[u].fy;
         }
+}
+template <bool P2>
+__global__ void __launch_bounds__(TX *TY)
+    k_cip_advect(float *__restrict__ fn, float *__restrict__ fxn, float *__restrict__ fyn,
+                 const float *__restrict__ fc, const float *__restrict__ fxc, const float *__restrict__ fyc,
+                 const float *__restrict__ v, const uint8_t *__restrict__ mask, fs2d_dom d, float dt, float dx,
+                 DivC<P2> ddx, float dx2, float dx3) {
+    if (block_interior(d, TY * NU_CIP_ADVECT, 1)) b_cip_advect<P2, false>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, ddx, dx2, dx3);
+    else b_cip_advect<P2, true>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, ddx, dx2, dx3);
 }
 
 // fs/solver.py:207-211  _set_grad
@@ -319,10 +344,9 @@ __global__ void __launch_bounds__(TX *TY)
 // =============================================================================================
 // fs/vorticity_confinement.py:27-32 / :34-55
 // =============================================================================================
-template <bool P2>
-__global__ void __launch_bounds__(TX *TY)
-    k_vort_calc(float *__restrict__ w, float *__restrict__ wabs, const float *__restrict__ vc,
-                const uint8_t *__restrict__ mask, fs2d_dom d, DivC<P2> ddx) {
+template <bool P2, bool CL>
+__device__ __forceinline__ void b_vort_calc(float *__restrict__ w, float *__restrict__ wabs, const float *__restrict__ vc,
+                                            const uint8_t *__restrict__ mask, const fs2d_dom &d, DivC<P2> ddx) {
     constexpr int NU = NU_VORT_CALC;
     FS2D_ROWS(d, j, r, ok)
     float o[NU];
@@ -330,7 +354,7 @@ __global__ void __launch_bounds__(TX *TY)
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
         m[u] = __ldg(mask + IX(d, r[u], j));
-        o[u] = diff_x2<P2>(vc, d, r[u], j, ddx).y - diff_y2<P2>(vc, d, r[u], j, ddx).x;
+        o[u] = diff_x2<P2, CL>(vc, d, r[u], j, ddx).y - diff_y2<P2, CL>(vc, d, r[u], j, ddx).x;
     }
 #pragma unroll
     for (int u = 0; u < NU; ++u)
@@ -340,22 +364,29 @@ __global__ void __launch_bounds__(TX *TY)
         }
 }
 template <bool P2>
+__global__ void __launch_bounds__(TX *TY)
+    k_vort_calc(float *__restrict__ w, float *__restrict__ wabs, const float *__restrict__ vc,
+                const uint8_t *__restrict__ mask, fs2d_dom d, DivC<P2> ddx) {
+    if (block_interior(d, TY * NU_VORT_CALC, 1)) b_vort_calc<P2, false>(w, wabs, vc, mask, d, ddx);
+    else b_vort_calc<P2, true>(w, wabs, vc, mask, d, ddx);
+}
+template <bool P2, bool CL>
 __device__ __forceinline__ float2 c_vort_add(const float *vc, const float *w, const float *wabs, const fs2d_dom &d, int r,
                                              int j, DivC<P2> ddx, float dtw) {
-    const float gx = diff_x1<P2>(wabs, d, r, j, ddx), gy = diff_y1<P2>(wabs, d, r, j, ddx);
+    const float gx = diff_x1<P2, CL>(wabs, d, r, j, ddx), gy = diff_y1<P2, CL>(wabs, d, r, j, ddx);
     const float nrm = sqrtf(gx * gx + gy * gy);
     const float nx = gx / nrm, ny = gy / nrm;  // 0/0 = NaN on quiescent cells
-    const float o = ld1(w, d, r, j);
+    const float o = ld1<CL>(w, d, r, j);
     float fx = ny * o, fy = -nx * o;
     fx = fmaxf(fminf(fx, 0.1f), -0.1f);  // NaN -> +0.1 by the fminf/fmaxf rule
     fy = fmaxf(fminf(fy, 0.1f), -0.1f);
-    const float2 c = ld2(vc, d, r, j);
+    const float2 c = ld2<CL>(vc, d, r, j);
     return make_float2(c.x + dtw * fx, c.y + dtw * fy);
 }
-template <bool P2>
-__global__ void __launch_bounds__(TX *TY)
-    k_vort_add(float *__restrict__ vn, const float *__restrict__ vc, const float *__restrict__ w,
-               const float *__restrict__ wabs, const uint8_t *__restrict__ mask, fs2d_dom d, DivC<P2> ddx, float dtw) {
+template <bool P2, bool CL>
+__device__ __forceinline__ void b_vort_add(float *__restrict__ vn, const float *__restrict__ vc, const float *__restrict__ w,
+                                           const float *__restrict__ wabs, const uint8_t *__restrict__ mask, const fs2d_dom &d,
+                                           DivC<P2> ddx, float dtw) {
     constexpr int NU = NU_VORT_ADD;
     FS2D_ROWS(d, j, r, ok)
     float2 o[NU];
@@ -363,11 +394,18 @@ __global__ void __launch_bounds__(TX *TY)
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
         m[u] = __ldg(mask + IX(d, r[u], j));
-        o[u] = c_vort_add<P2>(vc, w, wabs, d, r[u], j, ddx, dtw);
+        o[u] = c_vort_add<P2, CL>(vc, w, wabs, d, r[u], j, ddx, dtw);
     }
 #pragma unroll
     for (int u = 0; u < NU; ++u)
         if (ok[u] && m[u] == 0) reinterpret_cast<float2 *>(vn)[IX(d, r[u], j)] = o[u];
+}
+template <bool P2>
+__global__ void __launch_bounds__(TX *TY)
+    k_vort_add(float *__restrict__ vn, const float *__restrict__ vc, const float *__restrict__ w,
+               const float *__restrict__ wabs, const uint8_t *__restrict__ mask, fs2d_dom d, DivC<P2> ddx, float dtw) {
+    if (block_interior(d, TY * NU_VORT_ADD, 1)) b_vort_add<P2, false>(vn, vc, w, wabs, mask, d, ddx, dtw);
+    else b_vort_add<P2, true>(vn, vc, w, wabs, mask, d, ddx, dtw);
 }
 
 // fs/solver.py:38-43  limit_field

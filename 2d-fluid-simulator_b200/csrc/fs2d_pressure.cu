@@ -19,8 +19,9 @@ namespace fs2d {
 // source terms
 // ---------------------------------------------------------------------------------------------
 constexpr int NU_P_SOURCE = 4;   // rows per thread
-__global__ void __launch_bounds__(TX *TY)
-    k_p_source(float *__restrict__ src, const float *__restrict__ vc, fs2d_dom d, float dt, float dx) {
+template <bool CL>
+__device__ __forceinline__ void b_p_source(float *__restrict__ src, const float *__restrict__ vc, const fs2d_dom &d, float dt,
+                                           float dx) {
     const int j = blockIdx.y * blockDim.x + threadIdx.x;
     if (j >= d.Y) return;
     float2 sx[NU_P_SOURCE], sy[NU_P_SOURCE];
@@ -31,8 +32,8 @@ __global__ void __launch_bounds__(TX *TY)
         const int rr = d.r0 + (blockIdx.x * NU_P_SOURCE + u) * blockDim.y + threadIdx.y;
         ok[u] = rr < d.r1;
         r[u] = ok[u] ? rr : d.r1 - 1;
-        sx[u] = ld2(vc, d, r[u] + 1, j) - ld2(vc, d, r[u] - 1, j);
-        sy[u] = ld2(vc, d, r[u], j + 1) - ld2(vc, d, r[u], j - 1);
+        sx[u] = ld2<CL>(vc, d, r[u] + 1, j) - ld2<CL>(vc, d, r[u] - 1, j);
+        sy[u] = ld2<CL>(vc, d, r[u], j + 1) - ld2<CL>(vc, d, r[u], j - 1);
     }
 #pragma unroll
     for (int u = 0; u < NU_P_SOURCE; ++u) {
@@ -40,6 +41,11 @@ __global__ void __launch_bounds__(TX *TY)
         const float t3 = dx * (sx[u].x + sy[u].y) / (8.0f * dt);
         if (ok[u]) reinterpret_cast<float2 *>(src)[IX(d, r[u], j)] = make_float2(t2, t3);
     }
+}
+__global__ void __launch_bounds__(TX *TY)
+    k_p_source(float *__restrict__ src, const float *__restrict__ vc, fs2d_dom d, float dt, float dx) {
+    if (block_interior(d, TY * NU_P_SOURCE, 1)) b_p_source<false>(src, vc, d, dt, dx);
+    else b_p_source<true>(src, vc, d, dt, dx);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -211,7 +217,7 @@ extern "C" {
 
 int fs2d_set_tuning(int key, int value) {
     if (key == 0) { g_jm_rows = value; return FS2D_OK; }
-    if (key == 1 && (value == 1 || value == 3 || value == 4)) { fs2d::g_fused_variant = value; return FS2D_OK; }
+    if (key == 1 && (value == 1 || value == 3 || value == 5)) { fs2d::g_fused_variant = value; return FS2D_OK; }
     set_error("unknown tuning key %d", key);
     return FS2D_E_BADARG;
 }
@@ -243,7 +249,7 @@ int fs2d_jacobi_sweep(float *pn, const float *pc, const float *src, const uint8_
 // number of buffer flips (= number of entries) must have the parity of n_sweeps so that the two PHYSICAL
 // buffers end up exactly as in the reference.
 static int plan_jacobi(int n_sweeps, int fuse_mask, int *out, int cap) {
-    static const float pass_cost[13] = {0, 262, 269, 260, 287, 348, 398, 450, 511, 612, 683, 775, 842};   // variant 3
+    static const float pass_cost[13] = {0, 224, 247, 236, 256, 305, 349, 390, 428, 512, 559, 617, 666};   // variant 5
     const float lit_cost = 195.0f;
     const int n_lit = n_sweeps < 2 ? n_sweeps : 2, n_f = n_sweeps - n_lit;
     int n = 0;

@@ -110,18 +110,19 @@ class BoundaryCondition:
     # -- helpers for the other operators -----------------------------------------------------
     def fused_ok(self, T: int) -> bool:
         """May fs2d_jacobi_fused run T iterations per pass on this mask?  (static analysis, cached)"""
-        if T not in self._fused_ok:
-            import ctypes
+        import ctypes
 
-            rows, cols, hr, hc, tmax = (ctypes.c_int() for _ in range(5))
-            _lib.call("fs2d_fused_tile", T, ctypes.byref(rows), ctypes.byref(cols), ctypes.byref(hr), ctypes.byref(hc),
-                      ctypes.byref(tmax))
+        rows, cols, hr, hc, tmax = (ctypes.c_int() for _ in range(5))
+        _lib.call("fs2d_fused_tile", T, ctypes.byref(rows), ctypes.byref(cols), ctypes.byref(hr), ctypes.byref(hc),
+                  ctypes.byref(tmax))
+        key = (T, rows.value, cols.value)   # the tile depends on the kernel variant (fs2d_set_tuning)
+        if key not in self._fused_ok:
             g0, g1 = self.partition.owned()
             ok = (1 <= T <= tmax.value and self._global_resolution[1] % 16 == 0 and self._p_table["feed"]["n"] == 0
                   and (self.partition.world == 1 or self.halo >= T + 1)
                   and _bc_tables.fused_reach_ok(self._pcode_global, T, rows.value, cols.value, hr.value, hc.value, g0, g1))
-            self._fused_ok[T] = bool(ok)
-        return self._fused_ok[T]
+            self._fused_ok[key] = bool(ok)
+        return self._fused_ok[key]
 
     def stale_cells_agree(self, a: Field, b: Field) -> bool:
         """True if the never-written wall cells read by relaxed neighbours hold equal values in both
