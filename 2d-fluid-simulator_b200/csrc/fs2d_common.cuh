@@ -64,22 +64,52 @@ __device__ __forceinline__ float2 ld2(const float *f, const fs2d_dom &d, int r, 
     if (CL) return ld2(f, d, r, j);
     return __ldg(reinterpret_cast<const float2 *>(f) + ((ptrdiff_t)r * d.Y + j));
 }
+// Dense-kernel grids put the COLUMN blocks on blockIdx.x (fastest-varying in the block scheduler): the blocks resident
+// at any time then cover a few complete rows (64 KB contiguous each at Y = 8192) instead of a 512-byte wide column
+// of thousands of rows (64 KB stride: one DRAM page activation per 512 bytes).
+#define FS2D_COLBLK ((int)blockIdx.x)
+#define FS2D_ROWBLK ((int)blockIdx.y)
 // True if every cell of this thread block (block_rows rows from the block's first row, blockDim.x columns) and every
 // neighbour within `halo` cells of it lies inside the clamp window [clo, chi] x [0, Y-1], and all its rows are
 // updated rows (< r1).  Block-uniform.
 __device__ __forceinline__ bool block_interior(const fs2d_dom &d, int block_rows, int halo) {
-    const int rb = d.r0 + blockIdx.x * block_rows, jb = blockIdx.y * blockDim.x;
+    const int rb = d.r0 + FS2D_ROWBLK * block_rows, jb = FS2D_COLBLK * blockDim.x;
     return rb - halo >= d.clo && rb + block_rows - 1 + halo <= d.chi && rb + block_rows <= d.r1 && jb - halo >= 0 &&
            jb + (int)blockDim.x - 1 + halo <= d.Y - 1;
 }
 
 // ---- float2 arithmetic with the reference's per-component order ----------------------------------
-__device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 operator-(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 operator-(float2 a) { return make_float2(-a.x, -a.y); }
+// Multiplications use the Blackwell packed instruction (mul.rn.f32x2 -> FMUL2: both components in one issue slot;
+// each lane rounds exactly like mul.rn.f32).  Additions stay scalar on purpose: ptxas 12.9 contracts a
+// mul.rn.f32x2 feeding an add/sub.rn.f32x2 into FFMA2 even under --fmad false (measured, scripts/probes/README),
+// which would change the rounding; it does not contract FMUL2 with a scalar FADD.  The vector kernels (CIP advection:
+// ~210 fp32 operations per cell) are issue-bound, so this removes ~30 % of their FP instructions.
+#ifndef FS2D_NO_F32X2
+__device__ __forceinline__ uint64_t f2_pack(float2 a) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ float2 f2_unpack(uint64_t v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ float2 operator*(float2 a, float2 b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+    return f2_unpack(r);
+}
+__device__ __forceinline__ float2 operator*(float2 a, float s) { return a * make_float2(s, s); }
+__device__ __forceinline__ float2 operator*(float s, float2 a) { return make_float2(s, s) * a; }
+#else
 __device__ __forceinline__ float2 operator*(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
 __device__ __forceinline__ float2 operator*(float s, float2 a) { return make_float2(s * a.x, s * a.y); }
 __device__ __forceinline__ float2 operator*(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+#endif
+__device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 operator-(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 operator-(float2 a) { return make_float2(-a.x, -a.y); }
 __device__ __forceinline__ float2 operator/(float2 a, float s) { return make_float2(a.x / s, a.y / s); }
 __device__ __forceinline__ float2 operator/(float2 a, float2 b) { return make_float2(a.x / b.x, a.y / b.y); }
 
@@ -89,9 +119,16 @@ template <bool P2>
 struct DivC {
     float c, inv;
     __host__ __device__ DivC(float c_) : c(c_), inv(1.0f / c_) {}
+    // division by s*c for s = +-1: both the divisor and its reciprocal just change sign (no device-side division)
+    __device__ __forceinline__ DivC signed_by(float s) const {
+        DivC r(*this);
+        r.c = c * s;
+        r.inv = inv * s;
+        return r;
+    }
     __device__ __forceinline__ float operator()(float x) const { return P2 ? x * inv : x / c; }
     __device__ __forceinline__ float2 operator()(float2 x) const {
-        return P2 ? make_float2(x.x * inv, x.y * inv) : make_float2(x.x / c, x.y / c);
+        return P2 ? x * inv : make_float2(x.x / c, x.y / c);
     }
 };
 
@@ -103,15 +140,15 @@ constexpr int TX = 64;
 constexpr int TY = 4;
 inline dim3 dense_block() { return dim3(TX, TY, 1); }
 inline dim3 dense_grid(const fs2d_dom &d) {
-    return dim3((unsigned)((d.r1 - d.r0 + TY - 1) / TY), (unsigned)((d.Y + TX - 1) / TX), 1);
+    return dim3((unsigned)((d.Y + TX - 1) / TX), (unsigned)((d.r1 - d.r0 + TY - 1) / TY), 1);
 }
 // launch grid of the streaming kernels that process `nu` rows per thread (fs2d_kernels.cu)
 inline dim3 dense_grid_nu(const fs2d_dom &d, int nu) {
-    return dim3((unsigned)((d.r1 - d.r0 + TY * nu - 1) / (TY * nu)), (unsigned)((d.Y + TX - 1) / TX), 1);
+    return dim3((unsigned)((d.Y + TX - 1) / TX), (unsigned)((d.r1 - d.r0 + TY * nu - 1) / (TY * nu)), 1);
 }
 #define FS2D_CELL(d, r, j)                                   \
-    const int j = blockIdx.y * blockDim.x + threadIdx.x;     \
-    const int r = (d).r0 + blockIdx.x * blockDim.y + threadIdx.y; \
+    const int j = FS2D_COLBLK * blockDim.x + threadIdx.x;     \
+    const int r = (d).r0 + FS2D_ROWBLK * blockDim.y + threadIdx.y; \
     if (j >= (d).Y || r >= (d).r1) return;
 
 }  // namespace fs2d

@@ -174,27 +174,39 @@ constexpr int NU_CIP_NONADV = 2;
 constexpr int NU_CIP_NONADV_GRAD = 1;
 constexpr int NU_CIP_ADVECT = 1;
 constexpr int NU_VORT_CALC = 4;
-constexpr int NU_VORT_ADD = 2;
+constexpr int NU_VORT_ADD = 4;
 constexpr int NU_LIMIT = 4;
 #define FS2D_ROWS(d, j, r, ok)                                                       \
-    const int j = blockIdx.y * blockDim.x + threadIdx.x;                              \
+    const int j = FS2D_COLBLK * blockDim.x + threadIdx.x;                             \
     if (j >= (d).Y) return;                                                           \
     int r[NU];                                                                        \
     bool ok[NU];                                                                      \
     _Pragma("unroll") for (int u = 0; u < NU; ++u) {                                  \
-        const int rr = (d).r0 + (blockIdx.x * NU + u) * blockDim.y + threadIdx.y;     \
+        const int rr = (d).r0 + (FS2D_ROWBLK * NU + u) * blockDim.y + threadIdx.y;    \
         ok[u] = rr < (d).r1;                                                          \
         r[u] = ok[u] ? rr : (d).r1 - 1;                                               \
     }
 
 // fs/solver.py:229-240  CipMacSolver._non_advection_phase
-template <bool P2, bool CL>
-__device__ __forceinline__ float2 c_cip_nonadv(const float *fc, const float *pc, const fs2d_dom &d, int r, int j, float dt,
-                                               DivC<P2> ddx, DivC<P2> ddx2, float re) {
-    const float2 c = ld2<CL>(fc, d, r, j);
-    float2 gp = make_float2(diff_x1<P2, CL>(pc, d, r, j, ddx), diff_y1<P2, CL>(pc, d, r, j, ddx));
-    float2 g = -gp + laplace2<P2, CL>(fc, d, r, j, c, ddx2) / re;
-    return c + g * dt;
+// loads of one cell of _non_advection_phase (all issued before any arithmetic: the IEEE divisions below contain
+// branches the compiler does not hoist loads across)
+struct NonadvIn { float2 c, ip, im, jp, jm; float pip, pim, pjp, pjm; };
+template <bool CL>
+__device__ __forceinline__ NonadvIn l_cip_nonadv(const float *fc, const float *pc, const fs2d_dom &d, int r, int j) {
+    NonadvIn x;
+    x.c = ld2<CL>(fc, d, r, j);
+    x.ip = ld2<CL>(fc, d, r + 1, j); x.im = ld2<CL>(fc, d, r - 1, j);
+    x.jp = ld2<CL>(fc, d, r, j + 1); x.jm = ld2<CL>(fc, d, r, j - 1);
+    x.pip = ld1<CL>(pc, d, r + 1, j); x.pim = ld1<CL>(pc, d, r - 1, j);
+    x.pjp = ld1<CL>(pc, d, r, j + 1); x.pjm = ld1<CL>(pc, d, r, j - 1);
+    return x;
+}
+template <bool P2>
+__device__ __forceinline__ float2 c_cip_nonadv(const NonadvIn &x, float dt, DivC<P2> ddx, DivC<P2> ddx2, float re) {
+    const float2 gp = make_float2(ddx(0.5f * (x.pip - x.pim)), ddx(0.5f * (x.pjp - x.pjm)));   // (diff_x p, diff_y p)
+    const float2 d2x = ddx2(x.ip - 2.0f * x.c + x.im), d2y = ddx2(x.jp - 2.0f * x.c + x.jm);
+    const float2 g = -gp + (d2x + d2y) / re;
+    return x.c + g * dt;
 }
 template <bool P2, bool CL>
 __device__ __forceinline__ void b_cip_nonadv(float *__restrict__ fn, const float *__restrict__ fc, const float *__restrict__ pc,
@@ -202,16 +214,18 @@ __device__ __forceinline__ void b_cip_nonadv(float *__restrict__ fn, const float
                                              DivC<P2> ddx2, float re) {
     constexpr int NU = NU_CIP_NONADV;
     FS2D_ROWS(d, j, r, ok)
-    float2 out[NU];
+    NonadvIn in[NU];
     uint8_t m[NU];
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
         m[u] = __ldg(mask + IX(d, r[u], j));
-        out[u] = c_cip_nonadv<P2, CL>(fc, pc, d, r[u], j, dt, ddx, ddx2, re);
+        in[u] = l_cip_nonadv<CL>(fc, pc, d, r[u], j);
     }
 #pragma unroll
-    for (int u = 0; u < NU; ++u)
-        if (ok[u] && m[u] != 1) reinterpret_cast<float2 *>(fn)[IX(d, r[u], j)] = out[u];
+    for (int u = 0; u < NU; ++u) {
+        const float2 out = c_cip_nonadv<P2>(in[u], dt, ddx, ddx2, re);
+        if (ok[u] && m[u] != 1) reinterpret_cast<float2 *>(fn)[IX(d, r[u], j)] = out;
+    }
 }
 template <bool P2>
 __global__ void __launch_bounds__(TX *TY)
@@ -263,19 +277,38 @@ struct CipOut { float2 f, fx, fy; };
 template <bool P2, bool CL>
 __device__ __forceinline__ CipOut c_cip_advect(const float *fc, const float *fxc, const float *fyc, const float *v,
                                                const fs2d_dom &d, int r, int j, float dt, float dx, DivC<P2> ddx,
-                                               float dx2, float dx3) {
-    const float2 vel = ld2<CL>(v, d, r, j);
-    const float i_s = sign1(vel.x), j_s = sign1(vel.y);
-    const int r_m = r - (int)i_s, j_m = j - (int)j_s;
-    // +-dx^3, +-dx are exact sign flips; divisions by them are exact scalings when dx is 2^k
-    const DivC<P2> disd(i_s * dx3), djsd(j_s * dx3), ddx2(dx2), disdx(i_s * dx);
-    const float Xd = -vel.x * dt, Yd = -vel.y * dt;
-    const float2 dxv = diff_x2<P2, CL>(v, d, r, j, ddx);  // (d/dx u, d/dx v)
-    const float2 dyv = diff_y2<P2, CL>(v, d, r, j, ddx);
+                                               DivC<P2> ddx2, DivC<P2> ddx3) {
+    const float dx2 = ddx2.c;
+    // One round of independent loads: both candidates of every upwind neighbour are fetched (they are neighbours of
+    // the cell, so L1/L2 hits) and the upwind one is selected afterwards -- loading only (r_m, j_m) makes ten loads
+    // depend on the velocity load, i.e. two DRAM latencies per cell, and left the kernel latency-bound.
+    const float2 f00 = ld2<CL>(fc, d, r, j);
+    const float2 f0a = ld2<CL>(fc, d, r, j - 1), f0b = ld2<CL>(fc, d, r, j + 1);
+    const float2 fa0 = ld2<CL>(fc, d, r - 1, j), fb0 = ld2<CL>(fc, d, r + 1, j);
+    const float2 faa = ld2<CL>(fc, d, r - 1, j - 1), fab = ld2<CL>(fc, d, r - 1, j + 1);
+    const float2 fba = ld2<CL>(fc, d, r + 1, j - 1), fbb = ld2<CL>(fc, d, r + 1, j + 1);
+    const float2 x00 = ld2<CL>(fxc, d, r, j), x0a = ld2<CL>(fxc, d, r, j - 1), x0b = ld2<CL>(fxc, d, r, j + 1);
+    const float2 xa0 = ld2<CL>(fxc, d, r - 1, j), xb0 = ld2<CL>(fxc, d, r + 1, j);
+    const float2 y00 = ld2<CL>(fyc, d, r, j), y0a = ld2<CL>(fyc, d, r, j - 1), y0b = ld2<CL>(fyc, d, r, j + 1);
+    const float2 ya0 = ld2<CL>(fyc, d, r - 1, j), yb0 = ld2<CL>(fyc, d, r + 1, j);
+    const bool same = v == fc;   // the advecting velocity is the advected field itself in CipMacSolver (block-uniform)
+    const float2 vel = same ? f00 : ld2<CL>(v, d, r, j);
+    const float2 vb0 = same ? fb0 : ld2<CL>(v, d, r + 1, j), va0 = same ? fa0 : ld2<CL>(v, d, r - 1, j);
+    const float2 v0b = same ? f0b : ld2<CL>(v, d, r, j + 1), v0a = same ? f0a : ld2<CL>(v, d, r, j - 1);
 
-    const float2 f00 = ld2<CL>(fc, d, r, j), f0m = ld2<CL>(fc, d, r, j_m), fm0 = ld2<CL>(fc, d, r_m, j), fmm = ld2<CL>(fc, d, r_m, j_m);
-    const float2 x00 = ld2<CL>(fxc, d, r, j), x0m = ld2<CL>(fxc, d, r, j_m), xm0 = ld2<CL>(fxc, d, r_m, j);
-    const float2 y00 = ld2<CL>(fyc, d, r, j), y0m = ld2<CL>(fyc, d, r, j_m), ym0 = ld2<CL>(fyc, d, r_m, j);
+    const float i_s = sign1(vel.x), j_s = sign1(vel.y);
+    const bool im = !(vel.x < 0.0f), jm = !(vel.y < 0.0f);   // upwind cell (r_m, j_m) = (r - i_s, j - j_s)
+    // +-dx^3, +-dx are exact sign flips; divisions by them are exact scalings when dx is 2^k
+    const DivC<P2> disd = ddx3.signed_by(i_s), djsd = ddx3.signed_by(j_s), disdx = ddx.signed_by(i_s);
+    const float Xd = -vel.x * dt, Yd = -vel.y * dt;
+    const float2 dxv = ddx(0.5f * (vb0 - va0));  // diff_x(v) = (d/dx u, d/dx v)
+    const float2 dyv = ddx(0.5f * (v0b - v0a));  // diff_y(v)
+
+    const float2 f0m = jm ? f0a : f0b, fm0 = im ? fa0 : fb0;
+    const float2 fma = im ? faa : fba, fmb = im ? fab : fbb;
+    const float2 fmm = jm ? fma : fmb;
+    const float2 x0m = jm ? x0a : x0b, xm0 = im ? xa0 : xb0;
+    const float2 y0m = jm ? y0a : y0b, ym0 = im ? ya0 : yb0;
 
     const float2 tmp1 = f00 - f0m - fm0 + fmm;
     const float2 tmp2 = fm0 - f00;
@@ -302,7 +335,7 @@ __device__ __forceinline__ void b_cip_advect(float *__restrict__ fn, float *__re
                                              const float *__restrict__ fc, const float *__restrict__ fxc,
                                              const float *__restrict__ fyc, const float *__restrict__ v,
                                              const uint8_t *__restrict__ mask, const fs2d_dom &d, float dt, float dx,
-                                             DivC<P2> ddx, float dx2, float dx3) {
+                                             DivC<P2> ddx, DivC<P2> ddx2, DivC<P2> ddx3) {
     constexpr int NU = NU_CIP_ADVECT;
     FS2D_ROWS(d, j, r, ok)
     CipOut o[NU];
@@ -310,7 +343,7 @@ __device__ __forceinline__ void b_cip_advect(float *__restrict__ fn, float *__re
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
         m[u] = __ldg(mask + IX(d, r[u], j));
-        o[u] = c_cip_advect<P2, CL>(fc, fxc, fyc, v, d, r[u], j, dt, dx, ddx, dx2, dx3);
+        o[u] = c_cip_advect<P2, CL>(fc, fxc, fyc, v, d, r[u], j, dt, dx, ddx, ddx2, ddx3);
     }
 #pragma unroll
     for (int u = 0; u < NU; ++u)
@@ -326,9 +359,9 @@ __global__ void __launch_bounds__(TX *TY)
     k_cip_advect(float *__restrict__ fn, float *__restrict__ fxn, float *__restrict__ fyn,
                  const float *__restrict__ fc, const float *__restrict__ fxc, const float *__restrict__ fyc,
                  const float *__restrict__ v, const uint8_t *__restrict__ mask, fs2d_dom d, float dt, float dx,
-                 DivC<P2> ddx, float dx2, float dx3) {
-    if (block_interior(d, TY * NU_CIP_ADVECT, 1)) b_cip_advect<P2, false>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, ddx, dx2, dx3);
-    else b_cip_advect<P2, true>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, ddx, dx2, dx3);
+                 DivC<P2> ddx, DivC<P2> ddx2, DivC<P2> ddx3) {
+    if (block_interior(d, TY * NU_CIP_ADVECT, 1)) b_cip_advect<P2, false>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, ddx, ddx2, ddx3);
+    else b_cip_advect<P2, true>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, ddx, ddx2, ddx3);
 }
 
 // fs/solver.py:207-211  _set_grad
@@ -370,18 +403,25 @@ __global__ void __launch_bounds__(TX *TY)
     if (block_interior(d, TY * NU_VORT_CALC, 1)) b_vort_calc<P2, false>(w, wabs, vc, mask, d, ddx);
     else b_vort_calc<P2, true>(w, wabs, vc, mask, d, ddx);
 }
-template <bool P2, bool CL>
-__device__ __forceinline__ float2 c_vort_add(const float *vc, const float *w, const float *wabs, const fs2d_dom &d, int r,
-                                             int j, DivC<P2> ddx, float dtw) {
-    const float gx = diff_x1<P2, CL>(wabs, d, r, j, ddx), gy = diff_y1<P2, CL>(wabs, d, r, j, ddx);
+struct VortIn { float aip, aim, ajp, ajm, o; float2 c; };
+template <bool CL>
+__device__ __forceinline__ VortIn l_vort_add(const float *vc, const float *w, const float *wabs, const fs2d_dom &d, int r, int j) {
+    VortIn x;
+    x.aip = ld1<CL>(wabs, d, r + 1, j); x.aim = ld1<CL>(wabs, d, r - 1, j);
+    x.ajp = ld1<CL>(wabs, d, r, j + 1); x.ajm = ld1<CL>(wabs, d, r, j - 1);
+    x.o = ld1<CL>(w, d, r, j);
+    x.c = ld2<CL>(vc, d, r, j);
+    return x;
+}
+template <bool P2>
+__device__ __forceinline__ float2 c_vort_add(const VortIn &x, DivC<P2> ddx, float dtw) {
+    const float gx = ddx(0.5f * (x.aip - x.aim)), gy = ddx(0.5f * (x.ajp - x.ajm));
     const float nrm = sqrtf(gx * gx + gy * gy);
     const float nx = gx / nrm, ny = gy / nrm;  // 0/0 = NaN on quiescent cells
-    const float o = ld1<CL>(w, d, r, j);
-    float fx = ny * o, fy = -nx * o;
+    float fx = ny * x.o, fy = -nx * x.o;
     fx = fmaxf(fminf(fx, 0.1f), -0.1f);  // NaN -> +0.1 by the fminf/fmaxf rule
     fy = fmaxf(fminf(fy, 0.1f), -0.1f);
-    const float2 c = ld2<CL>(vc, d, r, j);
-    return make_float2(c.x + dtw * fx, c.y + dtw * fy);
+    return make_float2(x.c.x + dtw * fx, x.c.y + dtw * fy);
 }
 template <bool P2, bool CL>
 __device__ __forceinline__ void b_vort_add(float *__restrict__ vn, const float *__restrict__ vc, const float *__restrict__ w,
@@ -389,16 +429,18 @@ __device__ __forceinline__ void b_vort_add(float *__restrict__ vn, const float *
                                            DivC<P2> ddx, float dtw) {
     constexpr int NU = NU_VORT_ADD;
     FS2D_ROWS(d, j, r, ok)
-    float2 o[NU];
+    VortIn in[NU];
     uint8_t m[NU];
 #pragma unroll
-    for (int u = 0; u < NU; ++u) {
+    for (int u = 0; u < NU; ++u) {   // all loads of the thread's rows first (the divisions below contain branches)
         m[u] = __ldg(mask + IX(d, r[u], j));
-        o[u] = c_vort_add<P2, CL>(vc, w, wabs, d, r[u], j, ddx, dtw);
+        in[u] = l_vort_add<CL>(vc, w, wabs, d, r[u], j);
     }
 #pragma unroll
-    for (int u = 0; u < NU; ++u)
-        if (ok[u] && m[u] == 0) reinterpret_cast<float2 *>(vn)[IX(d, r[u], j)] = o[u];
+    for (int u = 0; u < NU; ++u) {
+        const float2 o = c_vort_add<P2>(in[u], ddx, dtw);
+        if (ok[u] && m[u] == 0) reinterpret_cast<float2 *>(vn)[IX(d, r[u], j)] = o;
+    }
 }
 template <bool P2>
 __global__ void __launch_bounds__(TX *TY)
@@ -525,7 +567,7 @@ int fs2d_cip_advect(float *fn, float *fxn, float *fyn, const float *fc, const fl
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
     const bool p2 = is_pow2(dx) && is_pow2(dx2) && is_pow2(dx3);
-#define CA(P2) ++g_launches, k_cip_advect<P2><<<dense_grid_nu(d, NU_CIP_ADVECT), dense_block(), 0, STREAM>>>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, DivC<P2>(dx), dx2, dx3)
+#define CA(P2) ++g_launches, k_cip_advect<P2><<<dense_grid_nu(d, NU_CIP_ADVECT), dense_block(), 0, STREAM>>>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, DivC<P2>(dx), DivC<P2>(dx2), DivC<P2>(dx3))
     DISPATCH_P2(p2, CA(true), CA(false));
 #undef CA
     FS2D_LAUNCH_CHECK();

@@ -22,14 +22,14 @@ constexpr int NU_P_SOURCE = 4;   // rows per thread
 template <bool CL>
 __device__ __forceinline__ void b_p_source(float *__restrict__ src, const float *__restrict__ vc, const fs2d_dom &d, float dt,
                                            float dx) {
-    const int j = blockIdx.y * blockDim.x + threadIdx.x;
+    const int j = FS2D_COLBLK * blockDim.x + threadIdx.x;
     if (j >= d.Y) return;
     float2 sx[NU_P_SOURCE], sy[NU_P_SOURCE];
     int r[NU_P_SOURCE];
     bool ok[NU_P_SOURCE];
 #pragma unroll
     for (int u = 0; u < NU_P_SOURCE; ++u) {   // all loads of the thread's rows first (memory-level parallelism)
-        const int rr = d.r0 + (blockIdx.x * NU_P_SOURCE + u) * blockDim.y + threadIdx.y;
+        const int rr = d.r0 + (FS2D_ROWBLK * NU_P_SOURCE + u) * blockDim.y + threadIdx.y;
         ok[u] = rr < d.r1;
         r[u] = ok[u] ? rr : d.r1 - 1;
         sx[u] = ld2<CL>(vc, d, r[u] + 1, j) - ld2<CL>(vc, d, r[u] - 1, j);
@@ -112,10 +112,10 @@ __global__ void __launch_bounds__(32 * JM_WARPS, 6)
     k_jacobi_march(float *__restrict__ pn, const float *__restrict__ pc, const float *__restrict__ src,
                    const uint8_t *__restrict__ pcode, fs2d_dom d) {
     const int lane = threadIdx.x;
-    const int j0 = 4 * (blockIdx.y * 32 + lane);
+    const int j0 = 4 * (FS2D_COLBLK * 32 + lane);
     const bool active = j0 < d.Y;
     const int jc = active ? j0 : 0;  // inactive lanes read column 0 (values unused) and never store
-    const int r_begin = d.r0 + (blockIdx.x * JM_WARPS + threadIdx.y) * JM_ROWS;
+    const int r_begin = d.r0 + (FS2D_ROWBLK * JM_WARPS + threadIdx.y) * JM_ROWS;
     const int r_end = min(r_begin + JM_ROWS, d.r1);
     if (r_begin >= r_end) return;  // warp-uniform
     const int jl = CJ(d, jc - 1), jr = CJ(d, jc + 4);
@@ -190,7 +190,7 @@ static void launch_jacobi(float *pn, const float *pc, const float *src, const ui
     if (vec) {
 #define JM_LAUNCH(R)                                                                          \
     do {                                                                                      \
-        dim3 blk(32, JM_WARPS, 1), grd(nblk(d.r1 - d.r0, R * JM_WARPS), nblk(d.Y, 128), 1);    \
+        dim3 blk(32, JM_WARPS, 1), grd(nblk(d.Y, 128), nblk(d.r1 - d.r0, R * JM_WARPS), 1);    \
         if (inline_bc) k_jacobi_march<true, R><<<grd, blk, 0, s>>>(pn, pc, src, pcode, d);    \
         else k_jacobi_march<false, R><<<grd, blk, 0, s>>>(pn, pc, src, pcode, d);             \
     } while (0)

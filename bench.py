@@ -192,8 +192,11 @@ def run_ours(a: argparse.Namespace) -> None:
     if world != a.gpus:
         raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {a.gpus}")
     torch.cuda.set_device(local)
+    # stdout carries exactly ONE JSON line: whatever libraries print there (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
     assert lib.fs2d_device_ok(), lib.fs2d_last_error().decode()
@@ -327,7 +330,8 @@ def run_ours(a: argparse.Namespace) -> None:
                 "stepping": "cuda-graph replay (1 launch/step)" if use_graph else "eager launches",
                 "ms_per_step_eager": ms_step_eager, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
