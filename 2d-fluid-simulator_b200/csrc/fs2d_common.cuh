@@ -110,8 +110,20 @@ __device__ __forceinline__ float2 operator*(float2 a, float2 b) { return make_fl
 __device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 operator-(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 operator-(float2 a) { return make_float2(-a.x, -a.y); }
-__device__ __forceinline__ float2 operator/(float2 a, float s) { return make_float2(a.x / s, a.y / s); }
-__device__ __forceinline__ float2 operator/(float2 a, float2 b) { return make_float2(a.x / b.x, a.y / b.y); }
+// x / y, IEEE-exact (div.rn.f32 semantics), that never sends a ZERO DIVIDEND into the division: the correctly
+// rounded fp32 division is a reciprocal + Newton sequence with a range check (FCHK) that diverts zero / denormal
+// operands to a ~100-instruction slow path.  Exactly uniform regions (free stream, quiescent start: Laplacians and
+// vorticity gradients are exactly 0 there) made that slow path the common case.  0 / y = +-0 (sign = XOR of the
+// signs) for every y but 0 and NaN, where it is NaN.
+__device__ __forceinline__ float fdiv_z(float x, float y) {
+    const bool z = x == 0.0f;
+    const bool ybad = !(fabsf(y) > 0.0f);   // y is 0 or NaN
+    const float q = (z ? 1.0f : x) / ((z && ybad) ? 1.0f : y);
+    const float sz = __int_as_float((__float_as_int(x) ^ __float_as_int(y)) & (int)0x80000000);
+    return z ? (ybad ? __int_as_float(0x7fffffff) : sz) : q;
+}
+__device__ __forceinline__ float2 operator/(float2 a, float s) { return make_float2(fdiv_z(a.x, s), fdiv_z(a.y, s)); }
+__device__ __forceinline__ float2 operator/(float2 a, float2 b) { return make_float2(fdiv_z(a.x, b.x), fdiv_z(a.y, b.y)); }
 
 // Division by a grid constant c.  When c is a power of two, x / c == x * (1/c) bit-for-bit (exact
 // scaling), so the pow2 instantiation avoids the IEEE division sequence without changing results.
@@ -126,9 +138,9 @@ struct DivC {
         r.inv = inv * s;
         return r;
     }
-    __device__ __forceinline__ float operator()(float x) const { return P2 ? x * inv : x / c; }
+    __device__ __forceinline__ float operator()(float x) const { return P2 ? x * inv : fdiv_z(x, c); }
     __device__ __forceinline__ float2 operator()(float2 x) const {
-        return P2 ? x * inv : make_float2(x.x / c, x.y / c);
+        return P2 ? x * inv : make_float2(fdiv_z(x.x, c), fdiv_z(x.y, c));
     }
 };
 

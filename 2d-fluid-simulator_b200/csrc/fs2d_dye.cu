@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(TX *TY)
         const float cc = __ldg(dc + C * idx + c);
         const float d2x = ddx2(ldc<C>(dc, d, r + 1, j, c) - 2.0f * cc + ldc<C>(dc, d, r - 1, j, c));
         const float d2y = ddx2(ldc<C>(dc, d, r, j + 1, c) - 2.0f * cc + ldc<C>(dc, d, r, j - 1, c));
-        dn[C * idx + c] = cc + (d2x + d2y) / re * dt;
+        dn[C * idx + c] = cc + fdiv_z(d2x + d2y, re) * dt;
     }
 }
 

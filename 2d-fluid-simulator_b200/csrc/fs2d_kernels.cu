@@ -416,8 +416,9 @@ __device__ __forceinline__ VortIn l_vort_add(const float *vc, const float *w, co
 template <bool P2>
 __device__ __forceinline__ float2 c_vort_add(const VortIn &x, DivC<P2> ddx, float dtw) {
     const float gx = ddx(0.5f * (x.aip - x.aim)), gy = ddx(0.5f * (x.ajp - x.ajm));
-    const float nrm = sqrtf(gx * gx + gy * gy);
-    const float nx = gx / nrm, ny = gy / nrm;  // 0/0 = NaN on quiescent cells
+    const float n2 = gx * gx + gy * gy;
+    const float nrm = n2 == 0.0f ? n2 : sqrtf(n2);                  // sqrt(+0) = +0 without the zero-operand slow path
+    const float nx = fdiv_z(gx, nrm), ny = fdiv_z(gy, nrm);         // 0/0 = NaN on quiescent cells
     float fx = ny * x.o, fy = -nx * x.o;
     fx = fmaxf(fminf(fx, 0.1f), -0.1f);  // NaN -> +0.1 by the fminf/fmaxf rule
     fy = fmaxf(fminf(fy, 0.1f), -0.1f);

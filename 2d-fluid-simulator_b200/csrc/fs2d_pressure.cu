@@ -38,7 +38,7 @@ __device__ __forceinline__ void b_p_source(float *__restrict__ src, const float 
 #pragma unroll
     for (int u = 0; u < NU_P_SOURCE; ++u) {
         const float t2 = (sx[u].x * sx[u].x + sy[u].y * sy[u].y + (sy[u].x * sx[u].y)) / 8.0f;
-        const float t3 = dx * (sx[u].x + sy[u].y) / (8.0f * dt);
+        const float t3 = fdiv_z(dx * (sx[u].x + sy[u].y), 8.0f * dt);
         if (ok[u]) reinterpret_cast<float2 *>(src)[IX(d, r[u], j)] = make_float2(t2, t3);
     }
 }

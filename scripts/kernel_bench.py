@@ -12,8 +12,14 @@ X = Y = 8192
 const, mask = build_scene(2, X, Y)
 bc = BoundaryCondition(const, mask)
 s = make_solver(bc, 0.05 / Y, 1.0 / Y, 1e5, 5.0, "cip", pressure="jacobi", n_iter=80)
+import os
+MODE = os.environ.get("FIELDS", "random")   # random | uniform (v = const: Laplacians / vorticity exactly 0, like a quiescent start)
 for f in (s.v, s.vx, s.vy, s.p):
-    f.current.tensor.uniform_(-1, 1); f.next.tensor.uniform_(-1, 1)
+    if MODE == "random":
+        f.current.tensor.uniform_(-1, 1); f.next.tensor.uniform_(-1, 1)
+    else:
+        f.current.tensor.fill_(0.25 if f is s.v else 0.0); f.next.tensor.zero_()
+print("fields:", MODE)
 vc = s.vorticity_confinement
 cases = {
     "cip_nonadv (21 B)": (lambda: s._non_advection_phase(s.v.next, s.v.current, s.p.current), 21),
