@@ -37,6 +37,16 @@ extern int g_fused_variant;  // fused Jacobi kernel variant (1 smem planes, 3 re
 // one fused pass of T Jacobi iterations p_in -> p_out (fs2d_fused.cu)
 int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t *pcode, const fs2d_dom &d, int T,
                cudaStream_t s);
+// TMA-fed streaming versions of the stencil kernels (fs2d_stream.cu); g_stream: fs2d_set_tuning(2, 0/1)
+extern int g_stream, g_stream_cfg;
+bool stream_ok(const fs2d_dom &d, const void *const *ptrs, int n);
+int stream_cip_advect(float *fn, float *fxn, float *fyn, const float *fc, const float *fxc, const float *fyc,
+                      const uint8_t *mask, const fs2d_dom &d, float dt, float dx, float dx2, float dx3, bool p2,
+                      cudaStream_t s);
+int stream_cip_nonadv(float *fn, const float *fc, const float *pc, const uint8_t *mask, const fs2d_dom &d, float dt, float dx,
+                      float re, bool p2, cudaStream_t s);
+int stream_vort_apply(float *vn, float *w, float *wabs, const float *vc, const uint8_t *mask, const fs2d_dom &d, float dx,
+                      float dtw, bool p2, cudaStream_t s);
 bool fused_supported(const float *pa, const float *pb, const float *src, const uint8_t *pcode, const fs2d_dom &d);
 
 // ---- indexing (clamp-to-edge sample(), fs/differentiation.py:4-9) -----------------------------

@@ -778,7 +778,7 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-static int make_map(CUtensorMap *m, CUtensorMapDataType dt, size_t esz, const void *base, uint64_t cols, uint64_t rows,
+int make_map(CUtensorMap *m, CUtensorMapDataType dt, size_t esz, const void *base, uint64_t cols, uint64_t rows,
                     uint32_t box_cols, uint32_t box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {

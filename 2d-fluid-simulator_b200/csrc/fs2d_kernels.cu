@@ -7,7 +7,7 @@
 #include <cstdio>
 #include <cmath>
 
-#include "fs2d_common.cuh"
+#include "fs2d_ops.cuh"
 
 namespace fs2d {
 
@@ -188,26 +188,6 @@ constexpr int NU_LIMIT = 4;
     }
 
 // fs/solver.py:229-240  CipMacSolver._non_advection_phase
-// loads of one cell of _non_advection_phase (all issued before any arithmetic: the IEEE divisions below contain
-// branches the compiler does not hoist loads across)
-struct NonadvIn { float2 c, ip, im, jp, jm; float pip, pim, pjp, pjm; };
-template <bool CL>
-__device__ __forceinline__ NonadvIn l_cip_nonadv(const float *fc, const float *pc, const fs2d_dom &d, int r, int j) {
-    NonadvIn x;
-    x.c = ld2<CL>(fc, d, r, j);
-    x.ip = ld2<CL>(fc, d, r + 1, j); x.im = ld2<CL>(fc, d, r - 1, j);
-    x.jp = ld2<CL>(fc, d, r, j + 1); x.jm = ld2<CL>(fc, d, r, j - 1);
-    x.pip = ld1<CL>(pc, d, r + 1, j); x.pim = ld1<CL>(pc, d, r - 1, j);
-    x.pjp = ld1<CL>(pc, d, r, j + 1); x.pjm = ld1<CL>(pc, d, r, j - 1);
-    return x;
-}
-template <bool P2>
-__device__ __forceinline__ float2 c_cip_nonadv(const NonadvIn &x, float dt, DivC<P2> ddx, DivC<P2> ddx2, float re) {
-    const float2 gp = make_float2(ddx(0.5f * (x.pip - x.pim)), ddx(0.5f * (x.pjp - x.pjm)));   // (diff_x p, diff_y p)
-    const float2 d2x = ddx2(x.ip - 2.0f * x.c + x.im), d2y = ddx2(x.jp - 2.0f * x.c + x.jm);
-    const float2 g = -gp + (d2x + d2y) / re;
-    return x.c + g * dt;
-}
 template <bool P2, bool CL>
 __device__ __forceinline__ void b_cip_nonadv(float *__restrict__ fn, const float *__restrict__ fc, const float *__restrict__ pc,
                                              const uint8_t *__restrict__ mask, const fs2d_dom &d, float dt, DivC<P2> ddx,
@@ -219,7 +199,7 @@ __device__ __forceinline__ void b_cip_nonadv(float *__restrict__ fn, const float
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
         m[u] = __ldg(mask + IX(d, r[u], j));
-        in[u] = l_cip_nonadv<CL>(fc, pc, d, r[u], j);
+        in[u] = l_cip_nonadv(GAt<CL>{d, r[u], j}, fc, pc);
     }
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
@@ -273,63 +253,6 @@ __global__ void __launch_bounds__(TX *TY)
 // =============================================================================================
 // fs/solver.py:267-332  _advection_phase / _cip_advect
 // =============================================================================================
-struct CipOut { float2 f, fx, fy; };
-template <bool P2, bool CL>
-__device__ __forceinline__ CipOut c_cip_advect(const float *fc, const float *fxc, const float *fyc, const float *v,
-                                               const fs2d_dom &d, int r, int j, float dt, float dx, DivC<P2> ddx,
-                                               DivC<P2> ddx2, DivC<P2> ddx3) {
-    const float dx2 = ddx2.c;
-    // One round of independent loads: both candidates of every upwind neighbour are fetched (they are neighbours of
-    // the cell, so L1/L2 hits) and the upwind one is selected afterwards -- loading only (r_m, j_m) makes ten loads
-    // depend on the velocity load, i.e. two DRAM latencies per cell, and left the kernel latency-bound.
-    const float2 f00 = ld2<CL>(fc, d, r, j);
-    const float2 f0a = ld2<CL>(fc, d, r, j - 1), f0b = ld2<CL>(fc, d, r, j + 1);
-    const float2 fa0 = ld2<CL>(fc, d, r - 1, j), fb0 = ld2<CL>(fc, d, r + 1, j);
-    const float2 faa = ld2<CL>(fc, d, r - 1, j - 1), fab = ld2<CL>(fc, d, r - 1, j + 1);
-    const float2 fba = ld2<CL>(fc, d, r + 1, j - 1), fbb = ld2<CL>(fc, d, r + 1, j + 1);
-    const float2 x00 = ld2<CL>(fxc, d, r, j), x0a = ld2<CL>(fxc, d, r, j - 1), x0b = ld2<CL>(fxc, d, r, j + 1);
-    const float2 xa0 = ld2<CL>(fxc, d, r - 1, j), xb0 = ld2<CL>(fxc, d, r + 1, j);
-    const float2 y00 = ld2<CL>(fyc, d, r, j), y0a = ld2<CL>(fyc, d, r, j - 1), y0b = ld2<CL>(fyc, d, r, j + 1);
-    const float2 ya0 = ld2<CL>(fyc, d, r - 1, j), yb0 = ld2<CL>(fyc, d, r + 1, j);
-    const bool same = v == fc;   // the advecting velocity is the advected field itself in CipMacSolver (block-uniform)
-    const float2 vel = same ? f00 : ld2<CL>(v, d, r, j);
-    const float2 vb0 = same ? fb0 : ld2<CL>(v, d, r + 1, j), va0 = same ? fa0 : ld2<CL>(v, d, r - 1, j);
-    const float2 v0b = same ? f0b : ld2<CL>(v, d, r, j + 1), v0a = same ? f0a : ld2<CL>(v, d, r, j - 1);
-
-    const float i_s = sign1(vel.x), j_s = sign1(vel.y);
-    const bool im = !(vel.x < 0.0f), jm = !(vel.y < 0.0f);   // upwind cell (r_m, j_m) = (r - i_s, j - j_s)
-    // +-dx^3, +-dx are exact sign flips; divisions by them are exact scalings when dx is 2^k
-    const DivC<P2> disd = ddx3.signed_by(i_s), djsd = ddx3.signed_by(j_s), disdx = ddx.signed_by(i_s);
-    const float Xd = -vel.x * dt, Yd = -vel.y * dt;
-    const float2 dxv = ddx(0.5f * (vb0 - va0));  // diff_x(v) = (d/dx u, d/dx v)
-    const float2 dyv = ddx(0.5f * (v0b - v0a));  // diff_y(v)
-
-    const float2 f0m = jm ? f0a : f0b, fm0 = im ? fa0 : fb0;
-    const float2 fma = im ? faa : fba, fmb = im ? fab : fbb;
-    const float2 fmm = jm ? fma : fmb;
-    const float2 x0m = jm ? x0a : x0b, xm0 = im ? xa0 : xb0;
-    const float2 y0m = jm ? y0a : y0b, ym0 = im ? ya0 : yb0;
-
-    const float2 tmp1 = f00 - f0m - fm0 + fmm;
-    const float2 tmp2 = fm0 - f00;
-    const float2 tmp3 = f0m - f00;
-
-    const float2 a = disd(i_s * (xm0 + x00) * dx - 2.0f * (-tmp2));
-    const float2 b = djsd(j_s * (y0m + y00) * dx - 2.0f * (-tmp3));
-    const float2 c = djsd(-tmp1 - i_s * (x0m - x00) * dx);
-    const float2 dd = disd(-tmp1 - j_s * (ym0 - y00) * dx);
-    const float2 e = ddx2(3.0f * tmp2 + i_s * (xm0 + 2.0f * x00) * dx);
-    const float2 f = ddx2(3.0f * tmp3 + j_s * (y0m + 2.0f * y00) * dx);
-    const float2 g = disdx(-(ym0 - y00) + c * dx2);
-
-    CipOut o;
-    o.f = ((a * Xd + c * Yd + e) * Xd + g * Yd + x00) * Xd + ((b * Yd + dd * Xd + f) * Yd + y00) * Yd + f00;
-    const float2 Fx = (3.0f * a * Xd + 2.0f * c * Yd + 2.0f * e) * Xd + (dd * Yd + g) * Yd + x00;
-    const float2 Fy = (3.0f * b * Yd + 2.0f * dd * Xd + 2.0f * f) * Yd + (c * Xd + g) * Xd + y00;
-    o.fx = Fx - dt * (Fx * dxv.x + Fy * dxv.y) / 2.0f;
-    o.fy = Fy - dt * (Fx * dyv.x + Fy * dyv.y) / 2.0f;
-    return o;
-}
 template <bool P2, bool CL>
 __device__ __forceinline__ void b_cip_advect(float *__restrict__ fn, float *__restrict__ fxn, float *__restrict__ fyn,
                                              const float *__restrict__ fc, const float *__restrict__ fxc,
@@ -343,7 +266,7 @@ __device__ __forceinline__ void b_cip_advect(float *__restrict__ fn, float *__re
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
         m[u] = __ldg(mask + IX(d, r[u], j));
-        o[u] = c_cip_advect<P2, CL>(fc, fxc, fyc, v, d, r[u], j, dt, dx, ddx, ddx2, ddx3);
+        o[u] = c_cip_advect<P2>(GAt<CL>{d, r[u], j}, fc, fxc, fyc, v, dt, dx, ddx, ddx2, ddx3);
     }
 #pragma unroll
     for (int u = 0; u < NU; ++u)
@@ -403,27 +326,6 @@ __global__ void __launch_bounds__(TX *TY)
     if (block_interior(d, TY * NU_VORT_CALC, 1)) b_vort_calc<P2, false>(w, wabs, vc, mask, d, ddx);
     else b_vort_calc<P2, true>(w, wabs, vc, mask, d, ddx);
 }
-struct VortIn { float aip, aim, ajp, ajm, o; float2 c; };
-template <bool CL>
-__device__ __forceinline__ VortIn l_vort_add(const float *vc, const float *w, const float *wabs, const fs2d_dom &d, int r, int j) {
-    VortIn x;
-    x.aip = ld1<CL>(wabs, d, r + 1, j); x.aim = ld1<CL>(wabs, d, r - 1, j);
-    x.ajp = ld1<CL>(wabs, d, r, j + 1); x.ajm = ld1<CL>(wabs, d, r, j - 1);
-    x.o = ld1<CL>(w, d, r, j);
-    x.c = ld2<CL>(vc, d, r, j);
-    return x;
-}
-template <bool P2>
-__device__ __forceinline__ float2 c_vort_add(const VortIn &x, DivC<P2> ddx, float dtw) {
-    const float gx = ddx(0.5f * (x.aip - x.aim)), gy = ddx(0.5f * (x.ajp - x.ajm));
-    const float n2 = gx * gx + gy * gy;
-    const float nrm = n2 == 0.0f ? n2 : sqrtf(n2);                  // sqrt(+0) = +0 without the zero-operand slow path
-    const float nx = fdiv_z(gx, nrm), ny = fdiv_z(gy, nrm);         // 0/0 = NaN on quiescent cells
-    float fx = ny * x.o, fy = -nx * x.o;
-    fx = fmaxf(fminf(fx, 0.1f), -0.1f);  // NaN -> +0.1 by the fminf/fmaxf rule
-    fy = fmaxf(fminf(fy, 0.1f), -0.1f);
-    return make_float2(x.c.x + dtw * fx, x.c.y + dtw * fy);
-}
 template <bool P2, bool CL>
 __device__ __forceinline__ void b_vort_add(float *__restrict__ vn, const float *__restrict__ vc, const float *__restrict__ w,
                                            const float *__restrict__ wabs, const uint8_t *__restrict__ mask, const fs2d_dom &d,
@@ -435,7 +337,7 @@ __device__ __forceinline__ void b_vort_add(float *__restrict__ vn, const float *
 #pragma unroll
     for (int u = 0; u < NU; ++u) {   // all loads of the thread's rows first (the divisions below contain branches)
         m[u] = __ldg(mask + IX(d, r[u], j));
-        in[u] = l_vort_add<CL>(vc, w, wabs, d, r[u], j);
+        in[u] = l_vort_add(GAt<CL>{d, r[u], j}, vc, w, wabs);
     }
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
@@ -449,6 +351,73 @@ __global__ void __launch_bounds__(TX *TY)
                const float *__restrict__ wabs, const uint8_t *__restrict__ mask, fs2d_dom d, DivC<P2> ddx, float dtw) {
     if (block_interior(d, TY * NU_VORT_ADD, 1)) b_vort_add<P2, false>(vn, vc, w, wabs, mask, d, ddx, dtw);
     else b_vort_add<P2, true>(vn, vc, w, wabs, mask, d, ddx, dtw);
+}
+
+// fs/vorticity_confinement.py:57-59  apply() = _calc_vorticity + _add_vorticity in ONE pass over HBM.
+// The force at a fluid cell reads |curl v| at its four (clamped) neighbours; for a fluid neighbour that is the value
+// _calc_vorticity is about to store there, so it is recomputed from v (same expression, same inputs: bit-identical);
+// a non-fluid neighbour keeps its stored value (never written by _calc_vorticity), which is loaded.
+// Traffic: v 8 + mask 1 read, vorticity 4 + |vorticity| 4 + v.next 8 written = 25 B/cell instead of 17 + 25.
+// Shared-memory tiling: a block first evaluates the curl once for every cell of its (VA_ROWS + 2) x (TX + 2) tile
+// (clamped coordinates, so the ring repeats the edge cells exactly like sample()), then the force from the tile.
+constexpr int VA_ROWS = 16;               // tile rows per block (TY threads x 4 rows each)
+constexpr int VA_PITCH = TX + 2 + 1;      // odd pitch: the column walk of phase 1 stays conflict-free
+template <bool P2, bool CL>
+__device__ __forceinline__ float c_curl(const float *vc, const fs2d_dom &d, int r, int j, DivC<P2> ddx) {
+    return diff_x2<P2, CL>(vc, d, r, j, ddx).y - diff_y2<P2, CL>(vc, d, r, j, ddx).x;
+}
+template <bool P2, bool CL>
+__device__ __forceinline__ void b_vort_apply(float *__restrict__ vn, float *__restrict__ w, float *__restrict__ wabs,
+                                             const float *__restrict__ vc, const uint8_t *__restrict__ mask,
+                                             const fs2d_dom &d, DivC<P2> ddx, float dtw, float (*s_w)[VA_PITCH],
+                                             float (*s_a)[VA_PITCH]) {
+    const int rb = d.r0 + FS2D_ROWBLK * VA_ROWS, jb = FS2D_COLBLK * TX;
+    const int tid = threadIdx.y * TX + threadIdx.x;
+    // phase 1: signed curl and effective |curl| (stored value at non-fluid cells) of the tile and its ring
+    for (int e = tid; e < (VA_ROWS + 2) * (TX + 2); e += TX * TY) {
+        const int lr = e / (TX + 2), lc = e - lr * (TX + 2);
+        const int r = CL ? CR(d, rb - 1 + lr) : rb - 1 + lr, j = CL ? CJ(d, jb - 1 + lc) : jb - 1 + lc;
+        const size_t idx = IX(d, r, j);
+        float cw = 0.0f, ca;
+        if (__ldg(mask + idx) == 0) {
+            cw = c_curl<P2, CL>(vc, d, r, j, ddx);
+            ca = fabsf(cw);
+        } else {
+            ca = wabs[idx];   // never written by _calc_vorticity
+        }
+        s_w[lr][lc] = cw;
+        s_a[lr][lc] = ca;
+    }
+    __syncthreads();
+    // phase 2: the confinement force on the block's cells
+    const int j = jb + threadIdx.x, lc = threadIdx.x + 1;
+    if (j >= d.Y) return;
+#pragma unroll
+    for (int u = 0; u < VA_ROWS / TY; ++u) {
+        const int lr = threadIdx.y + u * TY + 1, r = rb + lr - 1;
+        if (r >= d.r1) break;
+        const size_t idx = IX(d, r, j);
+        if (__ldg(mask + idx) != 0) continue;
+        VortIn x;
+        x.aip = s_a[lr + 1][lc]; x.aim = s_a[lr - 1][lc]; x.ajp = s_a[lr][lc + 1]; x.ajm = s_a[lr][lc - 1];
+        x.o = s_w[lr][lc];
+        x.c = __ldg(reinterpret_cast<const float2 *>(vc) + idx);
+        const float2 out = c_vort_add<P2>(x, ddx, dtw);
+        w[idx] = x.o;
+        wabs[idx] = fabsf(x.o);
+        reinterpret_cast<float2 *>(vn)[idx] = out;
+    }
+}
+template <bool P2>
+__global__ void __launch_bounds__(TX *TY)
+    k_vort_apply(float *__restrict__ vn, float *__restrict__ w, float *__restrict__ wabs, const float *__restrict__ vc,
+                 const uint8_t *__restrict__ mask, fs2d_dom d, DivC<P2> ddx, float dtw) {
+    __shared__ float s_w[VA_ROWS + 2][VA_PITCH], s_a[VA_ROWS + 2][VA_PITCH];
+    // interior: the ring (1 cell) and the curl stencil of the ring (1 more) stay inside the clamp window
+    const int rb = d.r0 + FS2D_ROWBLK * VA_ROWS, jb = FS2D_COLBLK * TX;
+    const bool interior = rb - 2 >= d.clo && rb + VA_ROWS + 1 <= d.chi && jb - 2 >= 0 && jb + TX + 1 <= d.Y - 1;
+    if (interior) b_vort_apply<P2, false>(vn, w, wabs, vc, mask, d, ddx, dtw, s_w, s_a);
+    else b_vort_apply<P2, true>(vn, w, wabs, vc, mask, d, ddx, dtw, s_w, s_a);
 }
 
 // fs/solver.py:38-43  limit_field
@@ -541,6 +510,14 @@ int fs2d_cip_nonadv(float *fn, const float *fc, const float *pc, const uint8_t *
     FS2D_REQUIRE(fn && fc && pc && mask, "null field pointer");
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
+    {
+        const void *ptrs[] = {fn, fc, pc, mask};
+        if (g_stream == 2 && stream_ok(d, ptrs, 4)) {   // measured no faster than the direct kernel (330 us): off by default
+            if (int e = stream_cip_nonadv(fn, fc, pc, mask, d, dt, dx, re, is_pow2(dx), STREAM)) return e;
+            FS2D_LAUNCH_CHECK();
+            return FS2D_OK;
+        }
+    }
     const float dx2 = dx * dx;
 #define NA(P2) ++g_launches, k_cip_nonadv<P2><<<dense_grid_nu(d, NU_CIP_NONADV), dense_block(), 0, STREAM>>>(fn, fc, pc, mask, d, dt, DivC<P2>(dx), DivC<P2>(dx2), re)
     DISPATCH_P2(is_pow2(dx), NA(true), NA(false));
@@ -568,6 +545,14 @@ int fs2d_cip_advect(float *fn, float *fxn, float *fyn, const float *fc, const fl
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
     const bool p2 = is_pow2(dx) && is_pow2(dx2) && is_pow2(dx3);
+    {
+        const void *ptrs[] = {fn, fxn, fyn, fc, fxc, fyc, mask};
+        if (v == fc && stream_ok(d, ptrs, 7)) {
+            if (int e = stream_cip_advect(fn, fxn, fyn, fc, fxc, fyc, mask, d, dt, dx, dx2, dx3, p2, STREAM)) return e;
+            FS2D_LAUNCH_CHECK();
+            return FS2D_OK;
+        }
+    }
 #define CA(P2) ++g_launches, k_cip_advect<P2><<<dense_grid_nu(d, NU_CIP_ADVECT), dense_block(), 0, STREAM>>>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, DivC<P2>(dx), DivC<P2>(dx2), DivC<P2>(dx3))
     DISPATCH_P2(p2, CA(true), CA(false));
 #undef CA
@@ -605,6 +590,27 @@ int fs2d_vort_add(float *vn, const float *vc, const float *w, const float *wabs,
 #define VA(P2) ++g_launches, k_vort_add<P2><<<dense_grid_nu(d, NU_VORT_ADD), dense_block(), 0, STREAM>>>(vn, vc, w, wabs, mask, d, DivC<P2>(dx), dtw)
     DISPATCH_P2(is_pow2(dx), VA(true), VA(false));
 #undef VA
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+int fs2d_vort_apply(float *vn, float *w, float *wabs, const float *vc, const uint8_t *mask, fs2d_dom d, float dx, float dtw,
+                    void *stream) {
+    FS2D_REQUIRE(vn && w && wabs && vc && mask, "null field pointer");
+    FS2D_REQUIRE(vn != vc, "the confinement force cannot be added in place");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+    {
+        const void *ptrs[] = {vn, w, wabs, vc, mask};
+        if (g_stream == 2 && stream_ok(d, ptrs, 5)) {   // measured slower (534 us) than the tiled kernel below (465 us): opt-in
+            if (int e = stream_vort_apply(vn, w, wabs, vc, mask, d, dx, dtw, is_pow2(dx), STREAM)) return e;
+            FS2D_LAUNCH_CHECK();
+            return FS2D_OK;
+        }
+    }
+#define VP(P2) ++g_launches, k_vort_apply<P2><<<dense_grid_nu(d, VA_ROWS / TY), dense_block(), 0, STREAM>>>(vn, w, wabs, vc, mask, d, DivC<P2>(dx), dtw)
+    DISPATCH_P2(is_pow2(dx), VP(true), VP(false));
+#undef VP
     FS2D_LAUNCH_CHECK();
     return FS2D_OK;
 }

@@ -64,13 +64,12 @@ def _extended(bc, extra: int):
 # multi-rank operator bodies (called from the single-rank classes when partition.world > 1)
 # ------------------------------------------------------------------------------------------------
 def vorticity_apply_distributed(vc, v: DoubleBuffer) -> None:
-    """fs/vorticity_confinement.py:57-59 on a strip: curl on owned+-1 rows (redundant row instead of
-    a second exchange), then the confinement force on the owned rows."""
+    """fs/vorticity_confinement.py:57-59 on a strip: the fused kernel recomputes the neighbours' curl from v, so two
+    fresh halo rows of v are all it needs (no exchange of the vorticity fields)."""
     bc = vc._bc
     hx = exchanger_for(bc)
     hx.exchange(v.current, 2)
-    vc._calc_vorticity(v.current, dom=_extended(bc, 1))
-    vc._add_vorticity(v.next, v.current)
+    vc._apply_fused(v.next, v.current)
 
 
 def jacobi_update_distributed(jac, p: DoubleBuffer, v_current: Field) -> None:

@@ -32,11 +32,17 @@ class VorticityConfinement:
         _lib.call("fs2d_vort_add", vn.ptr(), vc.ptr(), self.vorticity.ptr(), self.vorticity_abs.ptr(),
                   _lib.ptr(bc._bc_mask), bc.dom, self.dx, self.dt * self.weight, _lib.stream())
 
+    def _apply_fused(self, vn: Field, vc: Field) -> None:
+        """_calc_vorticity + _add_vorticity in one pass over HBM (fs2d_vort_apply): same vorticity, vorticity_abs
+        and vn, 25 instead of 42 bytes per cell."""
+        bc = self._bc
+        _lib.call("fs2d_vort_apply", vn.ptr(), self.vorticity.ptr(), self.vorticity_abs.ptr(), vc.ptr(),
+                  _lib.ptr(bc._bc_mask), bc.dom, self.dx, self.dt * self.weight, _lib.stream())
+
     def apply(self, v: DoubleBuffer) -> None:
         if self._bc.partition.world > 1:
             from fs.halo import vorticity_apply_distributed
 
             vorticity_apply_distributed(self, v)
             return
-        self._calc_vorticity(v.current)
-        self._add_vorticity(v.next, v.current)  # v.next only; the solver swaps
+        self._apply_fused(v.next, v.current)  # v.next only; the solver swaps

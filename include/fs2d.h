@@ -71,6 +71,7 @@ int fs2d_version(void);
 /* number of kernels this library has launched in this process (bench.py gpu_launches) */
 unsigned long long fs2d_launch_count(void);
 /* performance knobs (never change results): key 0 = rows marched per warp by the Jacobi sweep {1,2,4,8,16};
+ * key 2 = TMA-fed streaming versions of the CIP-path stencil kernels {0: off, 1: CIP advection (default), 2: also the non-advection phase and the vorticity confinement};
  * key 1 = fused Jacobi kernel variant {1: one column per thread, shared-memory planes; 3: register tile + warp shuffles (default)} */
 int fs2d_set_tuning(int key, int value);
 /* 1 if the library was built for sm_100a and a device of compute capability 10.x is current */
@@ -111,6 +112,11 @@ int fs2d_vort_calc(float *w, float *wabs, const float *vc, const uint8_t *mask, 
 /* VorticityConfinement._add_vorticity, fs/vorticity_confinement.py:34-55; dtw = (float)(dt*weight) */
 int fs2d_vort_add(float *vn, const float *vc, const float *w, const float *wabs, const uint8_t *mask, fs2d_dom d,
                   float dx, float dtw, void *stream);
+/* VorticityConfinement.apply, fs/vorticity_confinement.py:57-59: fs2d_vort_calc followed by fs2d_vort_add in one pass
+ * (the |vorticity| of a fluid neighbour is recomputed from vc instead of being read back; non-fluid neighbours keep
+ * their stored value).  Same results in w, wabs and vn as the two calls; vn must not alias vc. */
+int fs2d_vort_apply(float *vn, float *w, float *wabs, const float *vc, const uint8_t *mask, fs2d_dom d, float dx, float dtw,
+                    void *stream);
 /* Velocity source terms of predict_p (fs/pressure_updater.py:23-38) for every cell of rows [r0, r1):
  * src[i][j] = (t2, t3), t2 = (sx.x^2 + sy.y^2 + sy.x*sx.y)/8, t3 = dx*(sx.x + sy.y)/(8*dt) with
  * sx = v(i+1,j) - v(i-1,j), sy = v(i,j+1) - v(i,j-1).  v is constant during one pressure update, so the

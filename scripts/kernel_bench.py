@@ -19,7 +19,9 @@ for f in (s.v, s.vx, s.vy, s.p):
         f.current.tensor.uniform_(-1, 1); f.next.tensor.uniform_(-1, 1)
     else:
         f.current.tensor.fill_(0.25 if f is s.v else 0.0); f.next.tensor.zero_()
-print("fields:", MODE)
+from fs import _lib
+_lib.load().fs2d_set_tuning(3, int(os.environ.get("STREAM_CFG", "0")))
+print("fields:", MODE, "stream cfg", os.environ.get("STREAM_CFG", "0"))
 vc = s.vorticity_confinement
 cases = {
     "cip_nonadv (21 B)": (lambda: s._non_advection_phase(s.v.next, s.v.current, s.p.current), 21),
@@ -27,6 +29,7 @@ cases = {
     "cip_advect (49 B)": (lambda: s._advection_phase(s.v.next, s.vx.next, s.vy.next, s.v.current, s.vx.current, s.vy.current, s.v.current), 49),
     "vort_calc (17 B)": (lambda: vc._calc_vorticity(s.v.current), 17),
     "vort_add (25 B)": (lambda: vc._add_vorticity(s.v.next, s.v.current), 25),
+    "vort_apply fused (25 B)": (lambda: vc._apply_fused(s.v.next, s.v.current), 25),
     "p_source (16 B)": (lambda: s.pressure_updater._source(s.v.current), 16),
     "limit (8 B)": (lambda: limit_field(s.v.current, VELOCITY_LIMIT, bc=bc), 8),
 }

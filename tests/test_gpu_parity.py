@@ -100,6 +100,11 @@ def test_each_kernel_matches_reference_fixture(env, num, kernels_golden, masks_s
     vcf._calc_vorticity(fld(G("v")))
     assert_bitexact("vort", vcf.vorticity.to_numpy(), G("vort")); assert_bitexact("vort_abs", vcf.vorticity_abs.to_numpy(), G("vort_abs"))
     f = fld(G("vn0")); vcf._add_vorticity(f, fld(G("v"))); assert_bitexact("vort_add", f.to_numpy(), G("vort_add"))
+    # the fused apply() kernel (calc + add in one pass) must leave the same three fields
+    vcf.vorticity.from_numpy(G("w0")); vcf.vorticity_abs.from_numpy(G("wa0"))
+    f = fld(G("vn0")); vcf._apply_fused(f, fld(G("v")))
+    assert_bitexact("fused vort", vcf.vorticity.to_numpy(), G("vort")); assert_bitexact("fused vort_abs", vcf.vorticity_abs.to_numpy(), G("vort_abs"))
+    assert_bitexact("fused vort_add", f.to_numpy(), G("vort_add"))
     f = fld(G("pn0")); jac._update(f, fld(G("p")), fld(G("v"))); assert_bitexact("jacobi", f.to_numpy(), G("jacobi"))
     f = fld(G("pn0")); sor._update(f, fld(G("p")), fld(G("v"))); assert_bitexact("rbsor", f.to_numpy(), G("rbsor"))
     f = fld(G("v") * np.float32(12.0)); limit_field(f, 10.0); assert_bitexact("limit", f.to_numpy(), G("limit"))
@@ -606,3 +611,45 @@ def test_random_mask_trajectory_vs_oracle(env, seed):
             got = fs_state(s)
             for k, a in ref.state().items():
                 assert_bitexact(f"seed {seed} {scheme} step {n} {k}", got[k].to_numpy(), a)
+
+
+# ------------------------------------------------------------------------------------------------
+# 9. TMA-fed streaming stencil kernels (fs2d_stream.cu) == direct kernels, bitwise
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("num,X,Y", [(2, 256, 128), (3, 200, 176), (5, 333, 208), (1, 64, 48)])
+def test_stream_kernels_equal_direct_kernels(env, num, X, Y):
+    """cip_nonadv / cip_advect through the TMA tile pipeline vs the one-cell-per-thread kernels: whole grid and a row
+    window with clamp bounds inside the array (what an edge rank of a strip decomposition passes)."""
+    from fs.boundary_condition import BoundaryCondition, build_scene
+    from fs.fluid_simulator import make_solver
+
+    const, mask = build_scene(num, X, Y)
+    bc = BoundaryCondition(const, mask)
+    dt, dx = 0.05 / Y, 1.0 / 128      # power-of-two dx; Y is not (exercises partial tiles)
+    rng = np.random.default_rng(X * Y)
+    doms = [bc.dom, bc.dom.replace(r0=7, r1=X - 9, clo=3, chi=X - 4)]
+    for dxv in (dx, 0.01):             # exact-reciprocal and true-division instantiations
+        s = make_solver(bc, dt, dxv, 1e3, 5.0, "cip", pressure="jacobi", n_iter=1)
+        vcf = s.vorticity_confinement
+        init = {k: rng.uniform(-1, 1, getattr(s, k).current.tensor.shape).astype(np.float32) for k in ("v", "vx", "vy", "p")}
+        for dom in doms:
+            out = []
+            for stream in (2, 0):
+                env.fs2d_set_tuning(2, stream)
+                try:
+                    for k, a in init.items():
+                        getattr(s, k).current.from_numpy(a); getattr(s, k).next.from_numpy(a[::-1].copy())
+                    old = bc.dom
+                    bc.dom = dom
+                    s._non_advection_phase(s.v.next, s.v.current, s.p.current)
+                    r1 = s.v.next.to_numpy()
+                    s._advection_phase(s.v.next, s.vx.next, s.vy.next, s.v.current, s.vx.current, s.vy.current, s.v.current)
+                    adv = (s.v.next.to_numpy(), s.vx.next.to_numpy(), s.vy.next.to_numpy())
+                    vcf.vorticity.from_numpy(init["p"]); vcf.vorticity_abs.from_numpy(np.abs(init["p"][:, ::-1]).copy())
+                    vcf._apply_fused(s.v.next, s.v.current)
+                    out.append((r1,) + adv + (s.v.next.to_numpy(), vcf.vorticity.to_numpy(), vcf.vorticity_abs.to_numpy()))
+                finally:
+                    bc.dom = old
+                    env.fs2d_set_tuning(2, 1)
+            for name, a, b in zip(("nonadv", "adv f", "adv fx", "adv fy", "vort vn", "vort w", "vort |w|"), out[0], out[1]):
+                assert_bitexact(f"{name} bc{num} dx={dxv} dom={dom.r0}:{dom.r1}", a, b)
