@@ -42,6 +42,7 @@ ALGO_BYTES_PER_CELL_STEP = 139.0 + 12.0 * N_JACOBI
 
 
 def parse() -> argparse.Namespace:
+    global SCENE, RE, VC, N_JACOBI, Y_COLS, ALGO_BYTES_PER_CELL_STEP
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -54,7 +55,16 @@ def parse() -> argparse.Namespace:
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=1024, help="rows of the CPU-baseline sample grid")
-    return ap.parse_args()
+    ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3, 5],
+                    help="run a BASELINE.json config on its own grid instead of the headline workload: 2 = bc2 res=2048 Re=1e4 "
+                         "80 sweeps, 3 = bc3 res=4096 Re=1e8 vc=10 100 sweeps, 5 = bc5 res=16384 Re=1e6 200 sweeps (rows split over --gpus)")
+    a = ap.parse_args()
+    if a.config:
+        SCENE, res, RE, VC, N_JACOBI = {2: (2, 2048, 1e4, 5.0, 80), 3: (3, 4096, 1e8, 10.0, 100), 5: (5, 16384, 1e6, 5.0, 200)}[a.config]
+        Y_COLS = a.cols = res
+        a.rows_per_gpu, a.jacobi = 2 * res // a.gpus, N_JACOBI
+        ALGO_BYTES_PER_CELL_STEP = 139.0 + 12.0 * N_JACOBI
+    return a
 
 
 def peaks() -> tuple[float, str]:
@@ -167,11 +177,12 @@ def run_reference(a: argparse.Namespace) -> None:
 
 
 def workload_config(a: argparse.Namespace, n: int) -> dict:
-    return {"workload": f"BASELINE config 4 shard: bc={SCENE} {SCHEME} Re={RE:g} vc={VC} dt=0.05/8192 dx=1/8192 "
-                        f"jacobi={a.jacobi}/step, grid {a.rows_per_gpu * n}x{a.cols} ({a.rows_per_gpu}x{a.cols} cells/GPU; "
-                        f"N=2 == res=8192), quiescent start, -no_dye",
+    what = f"BASELINE config {a.config}" if a.config else "BASELINE config 4 shard"
+    return {"workload": f"{what}: bc={SCENE} {SCHEME} Re={RE:g} vc={VC} dt=0.05/{Y_COLS} dx=1/{Y_COLS} "
+                        f"jacobi={a.jacobi}/step, grid {a.rows_per_gpu * n}x{a.cols} ({a.rows_per_gpu}x{a.cols} cells/GPU"
+                        + ("" if a.config else "; N=2 == res=8192") + "), quiescent start, -no_dye",
             "global_grid": [a.rows_per_gpu * n, a.cols], "cells_per_gpu": a.rows_per_gpu * a.cols,
-            "parallelism": f"row-strips x{n}", "l2_policy": "working set (>=5 GB/GPU) >> 126 MB L2, no flush needed"}
+            "parallelism": f"row-strips x{n}", "l2_policy": f"working set {a.rows_per_gpu * a.cols * 82 / 1e9:.1f} GB/GPU (82 B/cell) >> 126 MB L2, no flush needed"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -271,11 +282,11 @@ def run_ours(a: argparse.Namespace) -> None:
     ms_sweep = ms_poisson / a.jacobi
     peak, peak_src = peaks()
     achieved = ALGO_BYTES_PER_CELL_SWEEP * (a.rows_per_gpu * Y) / (ms_sweep * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_jacobi_fused (T Jacobi iterations per pass in shared memory; update = fused passes + 2 literal sweeps)",
+    roofline = {"bound": "hbm", "kernel": "k_jacobi_fused5 (T Jacobi iterations per pass on a 96x128 register tile; update = fused passes + 2 literal sweeps)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL_SWEEP * a.rows_per_gpu * Y,
                 "ms_per_sweep": ms_sweep, "poisson_share_of_step": ms_poisson / ms_step_eager, "traffic": traffic_from_profile(),
-                "note": "frac > 1 is expected: the fused kernel keeps tiles in shared memory for T iterations, so the DRAM "
+                "note": "frac > 1 is expected: the fused kernel keeps tiles in registers / shared memory for T iterations, so the DRAM "
                         "traffic per iteration (see traffic, per fused launch of T=8 iterations) is far below the 12 B/cell "
                         "algorithmic figure the fraction is defined on",
                 "whole_step_algorithmic_gbs": ALGO_BYTES_PER_CELL_STEP * (a.rows_per_gpu * Y) / (ms_step * 1e-3) / 1e9}
