@@ -91,7 +91,7 @@ __device__ __forceinline__ bool block_interior(const fs2d_dom &d, int block_rows
 // ---- float2 arithmetic with the reference's per-component order ----------------------------------
 // Multiplications use the Blackwell packed instruction (mul.rn.f32x2 -> FMUL2: both components in one issue slot;
 // each lane rounds exactly like mul.rn.f32).  Additions stay scalar on purpose: ptxas 12.9 contracts a
-// mul.rn.f32x2 feeding an add/sub.rn.f32x2 into FFMA2 even under --fmad false (measured, scripts/probes/README),
+// mul.rn.f32x2 feeding an add/sub.rn.f32x2 into FFMA2 even under --fmad false (measured, scripts/probes/README.md),
 // which would change the rounding; it does not contract FMUL2 with a scalar FADD.  The vector kernels (CIP advection:
 // ~210 fp32 operations per cell) are issue-bound, so this removes ~30 % of their FP instructions.
 #ifndef FS2D_NO_F32X2
