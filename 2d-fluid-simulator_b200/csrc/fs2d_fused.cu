@@ -352,6 +352,7 @@ __global__ void __launch_bounds__(32 * (FSI / HK), 1)
     const int lane = threadIdx.x;
     const int tid = threadIdx.y * 32 + lane;
     const int c = 4 * lane;                 // first tile column of this thread
+    const int swz = (lane >> 2) & 1;        // order in which the two (t2, t3) chunks of a row are read
     const int lr0 = threadIdx.y * HK;       // first tile row of this thread
     const int o0 = lr0 * FSJ + c;           // plane offset of the thread's first cell
     const bool leader = tid == 0;
@@ -406,7 +407,11 @@ __global__ void __launch_bounds__(32 * (FSI / HK), 1)
         for (int k = 0; k < HK; ++k) {
             const int lr = lr0 + k, o = o0 + k * FSJ;
             const float4 pv = lds4(sm + OFF_P0 + o);
-            const float4 s01 = lds4(sm + OFF_SRC + 2 * o), s23 = lds4(sm + OFF_SRC + 2 * o + 4);
+            // (t2, t3) of the thread's 4 columns = two 16-byte chunks at a 32-byte lane stride: read in the order
+            // (even, odd) by lanes 0-3 of every 8 and (odd, even) by lanes 4-7, so each quarter-warp wavefront touches
+            // all 8 bank groups once (a plain read is 2-way bank conflicted), then put them back in order
+            const float4 sa = lds4(sm + OFF_SRC + 2 * o + 4 * swz), sb = lds4(sm + OFF_SRC + 2 * o + 4 * (1 - swz));
+            const float4 s01 = swz ? sb : sa, s23 = swz ? sa : sb;
             p[k][0] = pv.x; p[k][1] = pv.y; p[k][2] = pv.z; p[k][3] = pv.w;
             t2[k][0] = s01.x; t3[k][0] = s01.y; t2[k][1] = s01.z; t3[k][1] = s01.w;
             t2[k][2] = s23.x; t3[k][2] = s23.y; t2[k][3] = s23.z; t3[k][3] = s23.w;
@@ -575,6 +580,7 @@ __global__ void __launch_bounds__(V_THREADS, 1)
     const int lane = threadIdx.x, w = threadIdx.y;
     const int tid = w * 32 + lane;
     const int c = 4 * lane;                 // first tile column of this thread
+    const int swz = (lane >> 2) & 1;        // order in which the two (t2, t3) chunks of a row are read
     const int lr0 = w * HK;                 // first tile row of this thread
     const int o0 = lr0 * FSJ + c;           // plane offset of the thread's first cell
     const bool leader = tid == 0;
@@ -634,7 +640,9 @@ __global__ void __launch_bounds__(V_THREADS, 1)
         for (int k = 0; k < HK; ++k) {
             const int lr = lr0 + k, o = o0 + k * FSJ;
             const float4 pv = lds4(sm + VOFF_P0 + o);
-            const float4 s01 = lds4(sm + VOFF_SRC + 2 * o), s23 = lds4(sm + VOFF_SRC + 2 * o + 4);
+            // two 16-byte chunks at a 32-byte lane stride, read in swizzled order (conflict-free, see variant 3)
+            const float4 sa = lds4(sm + VOFF_SRC + 2 * o + 4 * swz), sb = lds4(sm + VOFF_SRC + 2 * o + 4 * (1 - swz));
+            const float4 s01 = swz ? sb : sa, s23 = swz ? sa : sb;
             p[k][0] = pv.x; p[k][1] = pv.y; p[k][2] = pv.z; p[k][3] = pv.w;
             t2[k][0] = s01.x; t3[k][0] = s01.y; t2[k][1] = s01.z; t3[k][1] = s01.w;
             t2[k][2] = s23.x; t3[k][2] = s23.y; t2[k][3] = s23.z; t3[k][3] = s23.w;

@@ -251,7 +251,7 @@ int fs2d_jacobi_sweep(float *pn, const float *pc, const float *src, const uint8_
 // number of buffer flips (= number of entries) must have the parity of n_sweeps so that the two PHYSICAL
 // buffers end up exactly as in the reference.
 static int plan_jacobi(int n_sweeps, int fuse_mask, int *out, int cap) {
-    static const float pass_cost[13] = {0, 224, 247, 236, 256, 305, 349, 390, 428, 512, 559, 617, 666};   // variant 5
+    static const float pass_cost[13] = {0, 214, 237, 226, 245, 295, 340, 381, 420, 501, 547, 607, 655};   // variant 5
     const float lit_cost = 195.0f;
     const int n_lit = n_sweeps < 2 ? n_sweeps : 2, n_f = n_sweeps - n_lit;
     int n = 0;

@@ -1,0 +1,27 @@
+"""Small launches of every shared-memory / TMA kernel for compute-sanitizer (memcheck, racecheck, synccheck):
+    compute-sanitizer --tool racecheck python scripts/sanitize_small.py"""
+import sys
+from pathlib import Path
+REPO = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(REPO / "2d-fluid-simulator_b200"))
+import numpy as np
+import torch
+from fs import _lib
+from fs.boundary_condition import BoundaryCondition, build_scene
+from fs.fluid_simulator import make_solver
+
+lib = _lib.load()
+for num, X, Y in ((2, 256, 128), (3, 200, 176)):
+    const, mask = build_scene(num, X, Y)
+    bc = BoundaryCondition(const, mask)
+    s = make_solver(bc, 0.05 / Y, 1.0 / 128, 1e3, 5.0, "cip", pressure="jacobi", n_iter=12)
+    rng = np.random.default_rng(1)
+    for k in ("v", "vx", "vy", "p"):
+        getattr(s, k).current.from_numpy(rng.uniform(-1, 1, getattr(s, k).current.tensor.shape).astype(np.float32))
+    for variant in (5, 3, 1):
+        lib.fs2d_set_tuning(1, variant)
+        for stream in (2, 0):
+            lib.fs2d_set_tuning(2, stream)
+            s.update()
+    torch.cuda.synchronize()
+    print("ok", num, X, Y, float(s.p.current.tensor.abs().sum()))
