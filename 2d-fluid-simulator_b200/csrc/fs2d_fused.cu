@@ -69,7 +69,10 @@ struct FusedGeom {
     int HJ;       // column halo: T rounded up to a multiple of 4 (TMA alignment)
     int TI, TJ;   // output tile rows / cols = FSI - 2T, FSJ - 2HJ
     int tiles_i, tiles_j;
+    int skip_from, skip_n;   // tile rows [skip_from, skip_from + skip_n) of the tiling are left to another launch
 };
+// tile row of the tiling for the launch's `row`-th tile row
+__device__ __forceinline__ int f_tile_row(const FusedGeom &g, int row) { return row < g.skip_from ? row : row + g.skip_n; }
 
 // post-BC pressure of tile cell (r, c) read from plane `pl` (same rule as p_post in fs2d_pressure.cu);
 // rlo..rhi / clo..chi: tile coordinates of the clamp bounds of sample()
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(F_THREADS, 1)
     const CUtensorMap *mp = &map_p, *ms = &map_src, *mc = &map_code;
 #define FS2D_ISSUE(tile)                                                            \
     do {                                                                            \
-        const int R0_ = d.r0 + ((tile) / g.tiles_j) * g.TI - g.T;                   \
+        const int R0_ = d.r0 + f_tile_row(g, (tile) / g.tiles_j) * g.TI - g.T;                   \
         const int C0_ = ((tile) % g.tiles_j) * g.TJ - g.HJ;                         \
         mbar_expect_tx(&bar, TX_BYTES);                                             \
         tma_load_2d(sm + OFF_P0, mp, C0_, R0_, &bar);                               \
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__(F_THREADS, 1)
     const int o_up = max(lr0 - 1, 0) * FSJ + c, o_dn = min(lr0 + FK, FSI - 1) * FSJ + c;
 
     while (t < n_tiles) {
-        const int R0 = d.r0 + (t / g.tiles_j) * g.TI - g.T;   // local-array row of tile row 0
+        const int R0 = d.r0 + f_tile_row(g, t / g.tiles_j) * g.TI - g.T;   // local-array row of tile row 0
         const int C0 = (t % g.tiles_j) * g.TJ - g.HJ;         // column of tile column 0
         const int coff = C0 - (C0 & ~15);                     // where tile column 0 sits inside the staged pcode box
         // clamp bounds of sample() in tile coordinates (global edges only)
@@ -362,7 +365,7 @@ __global__ void __launch_bounds__(32 * (FSI / HK), 1)
     const CUtensorMap *mp = &map_p, *ms = &map_src, *mc = &map_code;
 #define FS2D_ISSUE(tile)                                                            \
     do {                                                                            \
-        const int R0_ = d.r0 + ((tile) / g.tiles_j) * g.TI - g.T;                   \
+        const int R0_ = d.r0 + f_tile_row(g, (tile) / g.tiles_j) * g.TI - g.T;                   \
         const int C0_ = ((tile) % g.tiles_j) * g.TJ - g.HJ;                         \
         mbar_expect_tx(&bar, TX_BYTES);                                             \
         tma_load_2d(sm + OFF_P0, mp, C0_, R0_, &bar);                               \
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(32 * (FSI / HK), 1)
     constexpr uint32_t FULL = 0xffffffffu;
 
     while (t < n_tiles) {
-        const int R0 = d.r0 + (t / g.tiles_j) * g.TI - g.T;
+        const int R0 = d.r0 + f_tile_row(g, t / g.tiles_j) * g.TI - g.T;
         const int C0 = (t % g.tiles_j) * g.TJ - g.HJ;
         const int coff = C0 - (C0 & ~15);   // multiple of 4: C0 is a multiple of 4
         const int rlo = max(0, d.clo - R0), rhi = min(FSI - 1, d.chi - R0);
@@ -589,7 +592,7 @@ __global__ void __launch_bounds__(V_THREADS, 1)
     const CUtensorMap *mp = &map_p, *ms = &map_src, *mc = &map_code;
 #define FS2D_ISSUE(tile)                                                            \
     do {                                                                            \
-        const int R0_ = d.r0 + ((tile) / g.tiles_j) * g.TI - g.T;                   \
+        const int R0_ = d.r0 + f_tile_row(g, (tile) / g.tiles_j) * g.TI - g.T;                   \
         const int C0_ = ((tile) % g.tiles_j) * g.TJ - g.HJ;                         \
         mbar_expect_tx(&bar, TX_BYTES);                                             \
         tma_load_2d(sm + VOFF_P0, mp, C0_, R0_, &bar);                              \
@@ -617,7 +620,7 @@ __global__ void __launch_bounds__(V_THREADS, 1)
     constexpr uint32_t FULL = 0xffffffffu;
 
     while (t < n_tiles) {
-        const int R0 = d.r0 + (t / g.tiles_j) * g.TI - g.T;
+        const int R0 = d.r0 + f_tile_row(g, t / g.tiles_j) * g.TI - g.T;
         const int C0 = (t % g.tiles_j) * g.TJ - g.HJ;
         const int coff = C0 - (C0 & ~15);   // multiple of 4: C0 is a multiple of 4
         const int rlo = max(0, d.clo - R0), rhi = min(VSI - 1, d.chi - R0);
@@ -815,7 +818,7 @@ bool fused_supported(const float *pa, const float *pb, const float *src, const u
 }
 
 int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t *pcode, const fs2d_dom &d, int T,
-               cudaStream_t s) {
+               cudaStream_t s, int skip_from, int skip_n) {
     static int n_sm = 0;
     static bool attr_set = false;
     if (!n_sm) {
@@ -839,8 +842,17 @@ int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t 
     g.HJ = (T + 3) & ~3;
     g.TI = tile_rows - 2 * T;
     g.TJ = FSJ - 2 * g.HJ;
-    g.tiles_i = (d.r1 - d.r0 + g.TI - 1) / g.TI;
+    const int all_rows = (d.r1 - d.r0 + g.TI - 1) / g.TI;
+    if (skip_n < 0 || skip_from < 0 || skip_from + skip_n > all_rows) {
+        set_error("bad argument: skipped tile rows [%d, %d) outside the %d tile rows of the pass", skip_from, skip_from + skip_n,
+                  all_rows);
+        return FS2D_E_BADARG;
+    }
+    g.skip_from = skip_from;
+    g.skip_n = skip_n;
+    g.tiles_i = all_rows - skip_n;
     g.tiles_j = (d.Y + g.TJ - 1) / g.TJ;
+    if (g.tiles_i == 0) return FS2D_OK;
     const int n_tiles = g.tiles_i * g.tiles_j;
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
     static unsigned int *ctr = nullptr;   // dynamic tile scheduler: tiles next to walls cost more than open-fluid tiles
@@ -877,7 +889,21 @@ int fs2d_jacobi_fused(float *p_out, const float *p_in, const float *src, const u
                  "fused Jacobi needs Y % 16 == 0 and 16-byte aligned fields (TMA row pitch / base alignment)");
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
-    if (int e = fused_pass(p_in, p_out, src, pcode, d, T, (cudaStream_t)stream)) return e;
+    if (int e = fused_pass(p_in, p_out, src, pcode, d, T, (cudaStream_t)stream, 0, 0)) return e;
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
+int fs2d_jacobi_fused_part(float *p_out, const float *p_in, const float *src, const uint8_t *pcode, fs2d_dom d, int T,
+                           int skip_from, int skip_n, void *stream) {
+    FS2D_REQUIRE(p_out && p_in && src && pcode && p_out != p_in, "null/aliased field pointer");
+    FS2D_REQUIRE(T >= 1 && T <= F_TMAX, "fused iteration count out of range");
+    FS2D_REQUIRE(d.Y % 16 == 0 && ((uintptr_t)p_in % 16 == 0) && ((uintptr_t)p_out % 16 == 0) && ((uintptr_t)src % 16 == 0) &&
+                     ((uintptr_t)pcode % 16 == 0),
+                 "fused Jacobi needs Y % 16 == 0 and 16-byte aligned fields (TMA row pitch / base alignment)");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+    if (int e = fused_pass(p_in, p_out, src, pcode, d, T, (cudaStream_t)stream, skip_from, skip_n)) return e;
     FS2D_LAUNCH_CHECK();
     return FS2D_OK;
 }

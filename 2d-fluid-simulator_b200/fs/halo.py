@@ -11,6 +11,8 @@ last write, so every load sees the same bits as in the single-GPU run.
 """
 from __future__ import annotations
 
+from contextlib import contextmanager
+
 import torch
 import torch.distributed as dist
 
@@ -24,26 +26,41 @@ class HaloExchanger:
         self.n_exchanges = 0
         self.bytes_sent = 0
 
-    def exchange(self, field: Field | torch.Tensor, width: int) -> None:
-        """Fill the `width` halo rows adjacent to the owned rows on both sides from the neighbours."""
+    def start(self, field: Field | torch.Tensor | list, width: int = 0) -> list:
+        """Post the SendRecv that fills the `width` halo rows on both sides; returns the requests for finish().
+        `field` may be a list of (field, width) pairs: all of them go into ONE batch (one NCCL group).
+        Kernels launched between start() and finish() run concurrently with the transfer (the communication stream only
+        waits for work enqueued before start()): they must neither write the rows being sent nor touch the halo rows."""
         p = self.part
-        if p.world == 1 or width == 0:
-            return
-        t = field.tensor if isinstance(field, Field) else field
-        H, rows = p.halo, t.shape[0]
-        if width > H:
-            raise ValueError(f"halo exchange of {width} rows but the partition only has {H} halo rows")
+        pairs = field if isinstance(field, list) else [(field, width)]
+        pairs = [(f, w) for f, w in pairs if w > 0]
+        if p.world == 1 or not pairs:
+            return []
         ops, r = [], p.rank
-        if p.has_lower:
-            ops.append(dist.P2POp(dist.isend, t[H:H + width], r - 1, self.group))            # my first owned rows
-            ops.append(dist.P2POp(dist.irecv, t[H - width:H], r - 1, self.group))            # their last owned rows
-        if p.has_upper:
-            ops.append(dist.P2POp(dist.isend, t[rows - H - width:rows - H], r + 1, self.group))
-            ops.append(dist.P2POp(dist.irecv, t[rows - H:rows - H + width], r + 1, self.group))
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
+        for f, w in pairs:
+            t = f.tensor if isinstance(f, Field) else f
+            H, rows = p.halo, t.shape[0]
+            if w > H:
+                raise ValueError(f"halo exchange of {w} rows but the partition only has {H} halo rows")
+            if p.has_lower:
+                ops.append(dist.P2POp(dist.isend, t[H:H + w], r - 1, self.group))            # my first owned rows
+                ops.append(dist.P2POp(dist.irecv, t[H - w:H], r - 1, self.group))            # their last owned rows
+            if p.has_upper:
+                ops.append(dist.P2POp(dist.isend, t[rows - H - w:rows - H], r + 1, self.group))
+                ops.append(dist.P2POp(dist.irecv, t[rows - H:rows - H + w], r + 1, self.group))
         self.n_exchanges += 1
         self.bytes_sent += sum(op.tensor.numel() * op.tensor.element_size() for op in ops[::2])
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    @staticmethod
+    def finish(reqs: list) -> None:
+        """Make the current stream (the host, for gloo) wait for the transfer posted by start()."""
+        for req in reqs:
+            req.wait()
+
+    def exchange(self, field: Field | torch.Tensor, width: int) -> None:
+        """Fill the `width` halo rows adjacent to the owned rows on both sides from the neighbours."""
+        self.finish(self.start(field, width))
 
 
 def exchanger_for(bc) -> HaloExchanger:
@@ -68,8 +85,63 @@ def vorticity_apply_distributed(vc, v: DoubleBuffer) -> None:
     fresh halo rows of v are all it needs (no exchange of the vorticity fields)."""
     bc = vc._bc
     hx = exchanger_for(bc)
-    hx.exchange(v.current, 2)
-    vc._apply_fused(v.next, v.current)
+    _overlapped(bc, hx, [(v.current, 2)], lambda: vc._apply_fused(v.next, v.current), 2)
+
+
+@contextmanager
+def _rows(bc, r0: int, r1: int):
+    """Temporarily restrict the rows the kernels of `bc` update (they all take bc.dom)."""
+    old = bc.dom
+    bc.dom = old.replace(r0=r0, r1=r1)
+    try:
+        yield
+    finally:
+        bc.dom = old
+
+
+def _overlapped(bc, hx: HaloExchanger, exchanges: list, launch, reach: int) -> None:
+    """exchange(...) followed by launch(), with the transfer hidden behind the kernel: post the SendRecv, run `launch`
+    on the owned rows that read no halo row ([r0 + reach, r1 - reach)), wait, then run it on the `reach` edge rows of
+    each side.  `launch` must write neither the exchanged fields nor anything it reads from other rows."""
+    d = bc.dom
+    if d.r1 - d.r0 < 4 * reach + 16:
+        hx.finish(hx.start(exchanges))
+        launch()
+        return
+    reqs = hx.start(exchanges)
+    with _rows(bc, d.r0 + reach, d.r1 - reach):
+        launch()
+    hx.finish(reqs)
+    with _rows(bc, d.r0, d.r0 + reach):
+        launch()
+    with _rows(bc, d.r1 - reach, d.r1):
+        launch()
+
+
+def _pass_windows(bc, t: int):
+    """Interior row window of a fused pass of t iterations on this strip and the number m of tile rows before its end
+    (tile rows [1, m) are interior), or (None, 0) if the strip has too few tile rows to split."""
+    import ctypes
+
+    from fs import _lib
+
+    rows, cols, hr, hc, tmax = (ctypes.c_int() for _ in range(5))
+    _lib.call("fs2d_fused_tile", t, ctypes.byref(rows), ctypes.byref(cols), ctypes.byref(hr), ctypes.byref(hc), ctypes.byref(tmax))
+    return split_windows(bc.dom, rows.value - 2 * hr.value, t)
+
+
+def split_windows(d, ti: int, t: int):
+    """(mid, m): `mid` = copy of dom `d` covering the tile rows [1, m) of the tiling of [r0, r1) by tiles of ti output
+    rows, i.e. rows [r0 + ti, r0 + m*ti), chosen such that a pass of t iterations over it (reading t rows beyond its
+    tiles) touches owned rows only: r0 + ti - t >= r0 and r0 + m*ti + t <= r1.  (None, 0) when no such non-empty window
+    exists.  The remaining tile rows {0} U [m, k) read the halo rows."""
+    n = d.r1 - d.r0
+    if ti < t or ti <= 0:
+        return None, 0
+    m = min((n + ti - 1) // ti - 1, (n - t) // ti)
+    if m < 2:
+        return None, 0
+    return d.replace(r0=d.r0 + ti, r1=d.r0 + m * ti), m
 
 
 def jacobi_update_distributed(jac, p: DoubleBuffer, v_current: Field) -> None:
@@ -84,8 +156,18 @@ def jacobi_update_distributed(jac, p: DoubleBuffer, v_current: Field) -> None:
     src = jac._source(v_current, dom=_extended(bc, reach))        # source terms also on the halo rows a pass reads
     for t in plan:
         if t > 0:
-            hx.exchange(p.current, t)
-            jac._fused(p.next, p.current, src, t)
+            # Overlap: the pass reads the fresh halo rows only in its first and last TILE ROW, so the tile rows in
+            # between run while the SendRecv is in flight.  The interior window starts at a multiple of the tile height
+            # from r0, so both launches use exactly the tiles of a single launch (the validated tiling, fused_reach_ok).
+            mid, m = _pass_windows(bc, t)
+            if mid is None:
+                hx.exchange(p.current, t)
+                jac._fused(p.next, p.current, src, t)
+            else:
+                reqs = hx.start(p.current, t)
+                jac._fused(p.next, p.current, src, t, dom=mid)              # tile rows [1, m): owned rows only
+                hx.finish(reqs)
+                jac._fused(p.next, p.current, src, t, skip=(1, m - 1))      # tile rows {0} U [m, k) in one launch
         else:
             hx.exchange(p.current, 2)
             bc.set_pressure_boundary_condition(p.current)       # owned rows and the first halo row
@@ -123,14 +205,13 @@ def cip_update_distributed(s) -> None:
     hx = exchanger_for(bc)
     v, vx, vy, p = s.v, s.vx, s.vy, s.p
     _velocity_bc(bc, hx, v.current, 1)
-    hx.exchange(p.current, 1)
-    s._non_advection_phase(v.next, v.current, p.current)
-    hx.exchange(v.next, 1)                        # fn(i+-1, j) of the grad kernel
-    s._non_advection_phase_grad(vx.next, vy.next, vx.current, vy.current, v.current, v.next)
+    # every exchange below is hidden behind the interior rows of the kernel that needs it (_overlapped)
+    _overlapped(bc, hx, [(p.current, 1)], lambda: s._non_advection_phase(v.next, v.current, p.current), 1)
+    _overlapped(bc, hx, [(v.next, 1)],            # fn(i+-1, j) of the grad kernel
+                lambda: s._non_advection_phase_grad(vx.next, vy.next, vx.current, vy.current, v.current, v.next), 1)
     v.swap(); vx.swap(); vy.swap()
-    hx.exchange(vx.current, 1)                    # CIP reads f, fx, fy at the upwind row i_m = i +- 1
-    hx.exchange(vy.current, 1)
-    s._advection_phase(v.next, vx.next, vy.next, v.current, vx.current, vy.current, v.current)
+    _overlapped(bc, hx, [(vx.current, 1), (vy.current, 1)],   # CIP reads f, fx, fy at the upwind row i_m = i +- 1
+                lambda: s._advection_phase(v.next, vx.next, vy.next, v.current, vx.current, vy.current, v.current), 1)
     v.swap(); vx.swap(); vy.swap()
     if s.vorticity_confinement is not None:
         s.vorticity_confinement.apply(v)

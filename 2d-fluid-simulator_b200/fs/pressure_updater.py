@@ -101,10 +101,16 @@ class JacobiPressureUpdater(PressureUpdater):
         _lib.call("fs2d_jacobi_plan", self._n_iter, self.fuse_mask(p), sizes, cap, ctypes.byref(n))
         return list(sizes[:n.value])
 
-    def _fused(self, p_next: Field, p_current: Field, src: Field, t: int) -> None:
+    def _fused(self, p_next: Field, p_current: Field, src: Field, t: int, dom=None, skip=None) -> None:
+        """One fused pass; dom: row window (default: the owned rows); skip = (first, n): leave these tile rows of the
+        window's tiling to another launch (fs2d_jacobi_fused_part)."""
         bc = self._bc
-        _lib.call("fs2d_jacobi_fused", p_next.ptr(), p_current.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom, t,
-                  _lib.stream())
+        if skip is None:
+            _lib.call("fs2d_jacobi_fused", p_next.ptr(), p_current.ptr(), src.ptr(), _lib.ptr(bc._pcode), dom or bc.dom, t,
+                      _lib.stream())
+        else:
+            _lib.call("fs2d_jacobi_fused_part", p_next.ptr(), p_current.ptr(), src.ptr(), _lib.ptr(bc._pcode), dom or bc.dom,
+                      t, skip[0], skip[1], _lib.stream())
 
     def update(self, p: DoubleBuffer, v_current: Field) -> None:
         bc = self._bc

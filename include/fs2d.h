@@ -151,6 +151,12 @@ int fs2d_jacobi_plan(int n_sweeps, int fuse_mask, int *sizes, int cap, int *n_en
  * row strip the halo rows [r0-T, r1+T) of p_in and src are up to date. */
 int fs2d_jacobi_fused(float *p_out, const float *p_in, const float *src, const uint8_t *pcode, fs2d_dom d, int T,
                       void *stream);
+/* The same pass restricted to part of its tile rows: the tiling of rows [r0, r1) (tile rows of fs2d_fused_tile rows -
+ * 2 * halo_rows output rows, anchored at r0) minus the tile rows [skip_from, skip_from + skip_n).  A multi-rank host
+ * runs the interior tile rows (a row window through fs2d_jacobi_fused) while the halo SendRecv is in flight and then the
+ * first and last tile rows, which read the fresh halo, in ONE launch through this entry point. */
+int fs2d_jacobi_fused_part(float *p_out, const float *p_in, const float *src, const uint8_t *pcode, fs2d_dom d, int T,
+                           int skip_from, int skip_n, void *stream);
 /* tile geometry of the fused kernel for T iterations per pass: loaded tile rows x cols, the halo it discards on
  * each side (rows: T; columns: T rounded up to 4 -- TMA box starts must be 16-byte aligned) and the largest T */
 int fs2d_fused_tile(int T, int *rows, int *cols, int *halo_rows, int *halo_cols, int *t_max);

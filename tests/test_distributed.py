@@ -42,6 +42,15 @@ def _worker(rank: int, world: int, port: int, X: int, Y: int, halo: int, iters: 
         if part.has_upper:
             assert torch.equal(t[halo + g1 - g0:halo + g1 - g0 + w], full[g1:g1 + w]), (rank, w)
         assert torch.equal(t[halo:halo + g1 - g0], full[g0:g1])
+    # 1b. split-phase exchange: work between start() and finish() on other rows does not disturb it
+    t = loc.clone()
+    reqs = hx.start(t, halo)
+    t[2 * halo:g1 - g0] += 1.0                     # "interior kernel": owned rows that are neither sent nor received
+    hx.finish(reqs)
+    if part.has_lower:
+        assert torch.equal(t[:halo], full[g0 - halo:g0])
+    if part.has_upper:
+        assert torch.equal(t[halo + g1 - g0:], full[g1:g1 + halo])
     with np.testing.assert_raises(ValueError):
         hx.exchange(loc, halo + 1)
     ok = True
@@ -62,7 +71,7 @@ def test_halo_exchange_gloo_world2(halo):
         p.join(120)
         assert p.exitcode == 0
     res = sorted(q.get(timeout=5) for _ in range(2))
-    assert all(ok for _, ok, _ in res) and all(n == halo for _, _, n in res)
+    assert all(ok for _, ok, _ in res) and all(n == halo + 1 for _, _, n in res)
 
 
 def _strip_worker(rank: int, world: int, port: int, q) -> None:
@@ -127,3 +136,21 @@ def test_strips_bitwise_equal_single_gpu_nccl():
            "--master-addr", "127.0.0.1", "--master-port", str(free_port()), str(REPO / "tests" / "mp_strip_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "MP_CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_split_windows_cover_the_strip_and_keep_the_interior_off_the_halo():
+    """fs.halo.split_windows: the interior window is a whole number of tile rows starting one tile row into the strip,
+    and its reads (t rows beyond it) stay inside the owned rows."""
+    sys.path.insert(0, str(REPO / "2d-fluid-simulator_b200"))
+    from fs._lib import Dom
+    from fs.halo import split_windows
+
+    for rows, halo, ti, t in [(8192, 9, 80, 8), (500, 9, 80, 8), (250, 13, 72, 12), (4096, 9, 84, 6), (200, 9, 80, 8), (96, 4, 90, 3)]:
+        d = Dom(rows + 2 * halo, 64, halo, halo + rows, 0, rows + 2 * halo - 1, 0)
+        mid, m = split_windows(d, ti, t)
+        k = (rows + ti - 1) // ti
+        if mid is None:
+            assert (rows - t) // ti < 2 or k < 3
+            continue
+        assert mid.r0 == d.r0 + ti and mid.r1 == d.r0 + m * ti and 2 <= m <= k - 1
+        assert mid.r0 - t >= d.r0 and mid.r1 + t <= d.r1

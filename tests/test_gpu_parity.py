@@ -653,3 +653,40 @@ def test_stream_kernels_equal_direct_kernels(env, num, X, Y):
                     env.fs2d_set_tuning(2, 1)
             for name, a, b in zip(("nonadv", "adv f", "adv fx", "adv fy", "vort vn", "vort w", "vort |w|"), out[0], out[1]):
                 assert_bitexact(f"{name} bc{num} dx={dxv} dom={dom.r0}:{dom.r1}", a, b)
+
+
+@pytest.mark.parametrize("variant", [3, 5])
+def test_fused_pass_split_into_interior_and_edge_launches(env, variant):
+    """fs2d_jacobi_fused on an interior row window + fs2d_jacobi_fused_part on the remaining tile rows == one launch
+    (what the multi-rank host does to hide the halo exchange)."""
+    from fs import _lib
+    from fs.boundary_condition import BoundaryCondition, build_scene
+    from fs.halo import split_windows
+    from fs.pressure_updater import JacobiPressureUpdater
+    import ctypes
+
+    env.fs2d_set_tuning(1, variant)
+    try:
+        X, Y = 1000, 512
+        const, mask = build_scene(2, X, Y)
+        bc = BoundaryCondition(const, mask)
+        rng = np.random.default_rng(7)
+        p0 = rng.uniform(-1, 1, mask.shape).astype(np.float32)
+        v = fld(rng.uniform(-1, 1, mask.shape + (2,)).astype(np.float32))
+        jac = JacobiPressureUpdater(bc, 0.05 / Y, 1.0 / Y, 1, fuse=0)
+        src = jac._source(v)
+        for T in (4, 8):
+            assert bc.fused_ok(T)
+            rows, cols, hr, hc, tmax = (ctypes.c_int() for _ in range(5))
+            _lib.call("fs2d_fused_tile", T, ctypes.byref(rows), ctypes.byref(cols), ctypes.byref(hr), ctypes.byref(hc), ctypes.byref(tmax))
+            mid, m = split_windows(bc.dom, rows.value - 2 * hr.value, T)
+            assert mid is not None
+            whole, parts, fin = fld(p0), fld(p0), fld(p0)
+            jac._fused(whole, fin, src, T)
+            jac._fused(parts, fin, src, T, dom=mid)
+            jac._fused(parts, fin, src, T, skip=(1, m - 1))
+            assert torch.equal(whole.tensor, parts.tensor), f"T={T}: split launches differ from the single launch"
+            with pytest.raises((ValueError, RuntimeError)):
+                jac._fused(parts, fin, src, T, skip=(1, 10 ** 6))
+    finally:
+        env.fs2d_set_tuning(1, 5)
