@@ -690,3 +690,46 @@ def test_fused_pass_split_into_interior_and_edge_launches(env, variant):
                 jac._fused(parts, fin, src, T, skip=(1, 10 ** 6))
     finally:
         env.fs2d_set_tuning(1, 5)
+
+
+# ------------------------------------------------------------------------------------------------
+# 10. IEEE special cases of the guarded divisions / square root (fdiv_z) vs the oracle's plain C arithmetic
+# ------------------------------------------------------------------------------------------------
+def test_division_special_cases_match_the_oracle(env):
+    """Zero, denormal, infinite and NaN operands in the vorticity-confinement normalisation (0/0, x/0 by underflow of
+    the norm, 0/x, inf/inf), the viscous term (0/Re, denormal/Re) and the pressure source: the kernels that keep zero
+    dividends out of div.rn.f32 must still produce the oracle's IEEE results (NaN == NaN)."""
+    from fs.boundary_condition import BoundaryCondition, build_scene
+    from fs.fluid_simulator import make_solver
+    from oracle import oracle as orc
+
+    X, Y = 64, 48
+    const, mask = build_scene(1, X, Y)
+    bc = BoundaryCondition(const, mask)
+    dt, dx, re, vcw = 0.05 / Y, 1.0 / 64, 1e4, 5.0
+    s = make_solver(bc, dt, dx, re, vcw, "cip", pressure="jacobi", n_iter=1)
+    vcf = s.vorticity_confinement
+    rng = np.random.default_rng(3)
+    special = np.array([0.0, -0.0, 1e-32, -1e-32, 1e-42, -3e-45, 1.0, -2.5, 3e38, -3e38, np.inf, -np.inf, np.nan, 1e-20, 7e-39],
+                       dtype=np.float32)
+    pick = lambda shape: special[rng.integers(0, len(special), shape)]  # noqa: E731
+    for trial in range(6):
+        v = pick(mask.shape + (2,)); p = pick(mask.shape); w = pick(mask.shape); wa = np.abs(pick(mask.shape))
+        if trial % 2:   # smooth background with sparse special values: neighbours differ by tiny amounts
+            v = np.where(rng.random(v.shape) < 0.2, v, np.float32(0.25)); wa = np.where(rng.random(wa.shape) < 0.3, wa, np.float32(0.5))
+        v, p, w, wa = (np.ascontiguousarray(a, dtype=np.float32) for a in (v, p, w, wa))
+        with np.errstate(all="ignore"):
+            # vorticity force
+            want = v[..., ::-1].copy(); orc.vort_add(want, v, w, wa, mask, dx, dt, vcw)
+            vcf.vorticity.from_numpy(w); vcf.vorticity_abs.from_numpy(wa)
+            got = fld(v[..., ::-1].copy()); vcf._add_vorticity(got, fld(v))
+            assert_bitexact(f"vort_add special {trial}", got.to_numpy(), want)
+            # non-advection phase (division by Re)
+            want = v[..., ::-1].copy(); orc.cip_nonadv(want, v, p, mask, dt, dx, re)
+            got = fld(v[..., ::-1].copy()); s._non_advection_phase(got, fld(v), fld(p))
+            assert_bitexact(f"nonadv special {trial}", got.to_numpy(), want)
+            # one Jacobi sweep from the source terms (division by 8 dt)
+            pn_want = p[::-1].copy(); orc.jacobi_sweep(pn_want, p, v, mask, dt, dx)
+            jac = s.pressure_updater
+            pn = fld(p[::-1].copy()); jac._sweep(pn, fld(p), jac._source(fld(v)), inline_bc=False)
+            assert_bitexact(f"jacobi special {trial}", pn.to_numpy(), pn_want)
