@@ -70,9 +70,14 @@ const char *fs2d_last_error(void);
 int fs2d_version(void);
 /* number of kernels this library has launched in this process (bench.py gpu_launches) */
 unsigned long long fs2d_launch_count(void);
-/* performance knobs (never change results): key 0 = rows marched per warp by the Jacobi sweep {1,2,4,8,16};
- * key 2 = TMA-fed streaming versions of the CIP-path stencil kernels {0: off, 1: CIP advection (default), 2: also the non-advection phase and the vorticity confinement};
- * key 1 = fused Jacobi kernel variant {1: one column per thread, shared-memory planes; 3: register tile + warp shuffles (default)} */
+/* performance knobs (never change results):
+ * key 0 = rows marched per warp by the single-iteration Jacobi sweep {1, 2, 4 (default), 8, 16};
+ * key 1 = fused Jacobi kernel variant {1: one column per thread, shared-memory planes (64 x 128 tile); 3: register tile +
+ *         warp shuffles (64 x 128 tile); 5: register tile on a 96 x 128 tile (default)};
+ * key 2 = TMA-fed streaming versions of the CIP-path stencil kernels {0: off, 1: CIP advection (default), 2: also the
+ *         non-advection phase and the vorticity confinement};
+ * key 3 = streaming-kernel shape {stages x CTAs/SM x threads}: {0: 3x2x256, 1: 2x3x256 (default), 2: 3x2x512, 3: 2x2x512}.
+ * Unknown keys / values return FS2D_E_BADARG and change nothing. */
 int fs2d_set_tuning(int key, int value);
 /* 1 if the library was built for sm_100a and a device of compute capability 10.x is current */
 int fs2d_device_ok(void);

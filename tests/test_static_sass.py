@@ -1,0 +1,66 @@
+"""Static checks on the built sm_100a library (no GPU): the code ptxas generated is the code DESIGN.md describes.
+
+* the Jacobi kernels contain no fused multiply-add: the literal `0.25*(sum) + t2 - t3` order of
+  fs/pressure_updater.py:23-38 survived compilation (bit-exact parity rests on it);
+* the TMA kernels really contain UTMALDG (cp.async.bulk.tensor) and SYNCS (mbarrier) instructions;
+* the hot kernels do not spill to local memory.
+"""
+from __future__ import annotations
+
+import shutil
+import sys
+
+import pytest
+from conftest import REPO
+
+sys.path.insert(0, str(REPO / "scripts"))
+
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+
+
+@pytest.fixture(scope="module")
+def sass():
+    import static_sass_report as ssr
+
+    assert ssr.LIB.exists(), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    counts, usage = ssr.sass_counts(), ssr.res_usage()
+    short = ssr.demangle(sorted(counts))
+    return {short[m]: (counts[m], usage.get(m, {})) for m in counts}
+
+
+def _kernels(sass, prefix):
+    ks = {k: v for k, v in sass.items() if k.startswith(prefix)}
+    assert ks, f"no kernel named {prefix}* in libfs2d.so"
+    return ks
+
+
+def test_jacobi_kernels_have_no_fma(sass):
+    for prefix in ("k_jacobi_fused", "k_jacobi_march", "k_jacobi_scalar", "k_rbsor_pass"):
+        for name, (c, _) in _kernels(sass, prefix).items():
+            assert c["FFMA"] == 0 and c["FFMA2"] == 0, f"{name}: ptxas contracted a mul+add ({c['FFMA']} FFMA)"
+            assert c["FADD"] > 0 and c["FMUL"] > 0, name
+
+
+def test_pow2_stencil_kernels_have_no_fma(sass):
+    """With dx = 2^k (every BASELINE config) the gradient kernel is division-free, so any FFMA would be a contraction."""
+    c, _ = sass["k_cip_nonadv_grad<true>"]
+    assert c["FFMA"] == 0 and c["FFMA2"] == 0
+    c, _ = sass["k_cip_advect<true>"]
+    assert c["FFMA"] == 0 and c["FFMA2"] == 0 and c["FMUL2"] > 0      # packed multiplies, scalar adds (fs2d_common.cuh)
+
+
+def test_tma_kernels_use_tma_and_mbarriers(sass):
+    for prefix in ("k_jacobi_fused", "k_stream<"):
+        for name, (c, _) in _kernels(sass, prefix).items():
+            assert c["UTMALDG"] >= 3, f"{name}: no TMA tensor loads"
+            assert c["SYNCS"] >= 2, f"{name}: no mbarrier instructions"
+
+
+def test_hot_kernels_do_not_spill(sass):
+    hot = ["k_jacobi_fused5", "k_jacobi_fused3<8>", "k_jacobi_march<false, 4>", "k_p_source", "k_cip_nonadv<true>",
+           "k_cip_nonadv_grad<true>", "k_stream<OpAdvect<true>, 2, 3, 256>", "k_vort_apply<true>", "k_limit"]
+    for name in hot:
+        _, u = sass[name]
+        assert u.get("LOCAL", 0) == 0 and u.get("STACK", 0) == 0, f"{name}: spills ({u})"
+    # the 96 x 128 register tile needs <= 168 registers to keep 384 threads (12 warps) resident on one SM
+    assert sass["k_jacobi_fused5"][1]["REG"] <= 168
