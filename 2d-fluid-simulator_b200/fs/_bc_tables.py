@@ -215,11 +215,20 @@ def iteration_dependencies(code: torch.Tensor) -> dict:
 
 
 def fused_reach_ok(code: torch.Tensor, T: int, tile_rows: int, tile_cols: int, halo_rows: int | None = None,
-                   halo_cols: int | None = None, row0: int = 0, row1: int | None = None) -> bool:
+                   halo_cols: int | None = None, row0: int = 0, row1: int | None = None,
+                   fresh_below: int | None = None) -> bool:
     """True if, for the tiling used by fs2d_jacobi_fused (tiles of tile_rows x tile_cols loaded cells, of which
     halo_rows / halo_cols are discarded on each side, output tiles anchored at (row0, 0)), the value of every
     OUTPUT cell after T iterations depends only on cells inside its tile.  Dynamic programme over the T
-    iterations of how far up/down/left/right each cell's dependency cone reaches (conservative at global edges)."""
+    iterations of how far up/down/left/right each cell's dependency cone reaches (conservative at global edges).
+
+    fresh_below (row strips with a neighbour below row1): only that many rows beyond row1 - 1 hold current data (the
+    halo rows exchanged before the pass).  The tiles are anchored at row0, so the LAST tile row of a strip generally
+    extends further down than that; its extra rows are stale, and a cone that grows by more than one row per iteration
+    (a relaxed cell above an inflow cell reads, through that cell's BC value p(i+1, j), two rows down) must not reach
+    them.  The upward side needs no such bound: the first tile starts exactly halo_rows above row0, so the tile bound
+    is the fresh-row bound there.  The reference's scenes keep inflow cells in the first rows of the grid and never
+    trip this; adversarial masks do (tests/test_host_logic.py, tests/test_bc_tables.py)."""
     X, Y = code.shape
     row1 = X if row1 is None else row1
     HI = T if halo_rows is None else halo_rows
@@ -235,6 +244,8 @@ def fused_reach_ok(code: torch.Tensor, T: int, tile_rows: int, tile_cols: int, h
     owned = ((ii >= row0) & (ii < row1))[:, None]
     weights = {"up": lambda o: -o[0], "down": lambda o: o[0], "left": lambda o: -o[1], "right": lambda o: o[1]}
     room = {"up": lr, "down": (tile_rows - 1) - lr, "left": lc, "right": (tile_cols - 1) - lc}
+    if fresh_below is not None:
+        room["down"] = torch.minimum(room["down"], ((row1 - 1 - ii) + fresh_below).clamp(min=0).to(torch.int16)[:, None])
     for name, w in weights.items():
         R = torch.zeros((X, Y), dtype=torch.int16, device=dev)
         for _ in range(T):

@@ -120,7 +120,8 @@ class BoundaryCondition:
             g0, g1 = self.partition.owned()
             ok = (1 <= T <= tmax.value and self._global_resolution[1] % 16 == 0 and self._p_table["feed"]["n"] == 0
                   and (self.partition.world == 1 or self.halo >= T + 1)
-                  and _bc_tables.fused_reach_ok(self._pcode_global, T, rows.value, cols.value, hr.value, hc.value, g0, g1))
+                  and _bc_tables.fused_reach_ok(self._pcode_global, T, rows.value, cols.value, hr.value, hc.value, g0, g1,
+                                                fresh_below=T if self.partition.has_upper else None))
             self._fused_ok[key] = bool(ok)
         return self._fused_ok[key]
 

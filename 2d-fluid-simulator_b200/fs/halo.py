@@ -82,9 +82,15 @@ def _extended(bc, extra: int):
 # ------------------------------------------------------------------------------------------------
 def vorticity_apply_distributed(vc, v: DoubleBuffer) -> None:
     """fs/vorticity_confinement.py:57-59 on a strip: the fused kernel recomputes the neighbours' curl from v, so two
-    fresh halo rows of v are all it needs (no exchange of the vorticity fields)."""
+    fresh halo rows of v are all it needs per step (no per-step exchange of the vorticity fields)."""
     bc = vc._bc
     hx = exchanger_for(bc)
+    if vc.vorticity_abs.dirty:
+        # The stored |vorticity| of a NON-fluid cell is read by its fluid neighbours and never written by any kernel
+        # (SURVEY T1), so a halo row only has to receive it once after the field was written from the host
+        # (construction: zeros; load_state_dict / from_numpy -- which every rank must call alike, like any collective).
+        hx.exchange(vc.vorticity_abs, 1)
+        vc.vorticity_abs.dirty = False
     _overlapped(bc, hx, [(v.current, 2)], lambda: vc._apply_fused(v.next, v.current), 2)
 
 

@@ -104,3 +104,38 @@ def test_partition_arithmetic():
         Partition(64, 2, 2, 2)
     with pytest.raises(ValueError):
         Partition(64, 0, 2, 1)
+
+
+def test_fused_reach_bounds_the_stale_rows_below_a_strip():
+    """fused_reach_ok(fresh_below=T): an inflow cell right below a strip's last row doubles the downward dependency reach
+    (its BC value is p(i+1, j), fs/boundary_condition.py:62-63, so the relaxed cell above it reads two rows down), and
+    after T iterations the cone touches row row1 + T -- beyond the T halo rows exchanged before the pass.  The tile
+    (anchored at row0) extends further down, so only the strip-aware bound catches it."""
+    X, Y, tile_rows, tile_cols = 96, 128, 64, 128
+    for stray_inflow, expect_strip_ok in ((True, False), (False, True)):
+        mask = np.zeros((X, Y), dtype=np.uint8)
+        mask[:, :2] = 1; mask[:, -2:] = 1
+        mask[60:64, 40:60] = 1                          # an ordinary thick obstacle: reach stays one row per iteration
+        if stray_inflow:
+            mask[48, 50] = 2                            # first row below the strip [0, 48)
+        code = T.pressure_codes(torch.from_numpy(mask))
+        for t in (1, 2, 3, 4):
+            hj = (t + 3) & ~3
+            assert T.fused_reach_ok(code, t, tile_rows, tile_cols, t, hj, 0, X)                     # single domain: fine
+            assert T.fused_reach_ok(code, t, tile_rows, tile_cols, t, hj, 0, 48)                    # tile-only bound: blind to it
+            assert T.fused_reach_ok(code, t, tile_rows, tile_cols, t, hj, 0, 48, fresh_below=t) == expect_strip_ok
+        # brute force: poison everything below the fresh rows and compare T literal iterations, strip vs full domain
+        rng = np.random.default_rng(int(stray_inflow))
+        p0 = rng.uniform(-1, 1, (X, Y)).astype(np.float32)
+        v0 = np.zeros((X, Y, 2), np.float32)
+        t = 3
+        full, part = p0.copy(), p0.copy()
+        part[48 + t:] = np.nan
+        for a in (full, part):
+            for _ in range(t):
+                orc.p_bc(a, mask)
+                b = a.copy()
+                orc.jacobi_sweep(b, a, v0, mask, 0.01, 1.0 / 64)
+                a[...] = b
+        same = np.array_equal(full[:48][mask[:48] != 1], part[:48][mask[:48] != 1], equal_nan=False)
+        assert same == expect_strip_ok

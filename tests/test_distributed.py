@@ -138,6 +138,16 @@ def test_strips_bitwise_equal_single_gpu_nccl():
     assert out.returncode == 0 and "MP_CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_strip_check_script_dry_run_on_cpu(world):
+    """The NCCL strip check (tests/mp_strip_check.py) run on CPU: gloo + the oracle-backed stand-in for libfs2d.so
+    (tests/fake_fs2d.py).  Exercises the script itself and the whole multi-rank host layer under torchrun, small cases."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()), str(REPO / "tests" / "mp_strip_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, FS2D_FAKE_LIB="1"))
+    assert out.returncode == 0 and f"MP_CHECK OK 7 cases on {world} ranks" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_split_windows_cover_the_strip_and_keep_the_interior_off_the_halo():
     """fs.halo.split_windows: the interior window is a whole number of tile rows starting one tile row into the strip,
     and its reads (t rows beyond it) stay inside the owned rows."""
