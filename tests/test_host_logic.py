@@ -303,3 +303,95 @@ def test_strips_equal_single_domain_under_gloo(world):
     info = res[0][2]
     assert all(n_ex > 0 for _, _, n_ex, _ in info)                 # every case really exchanged halos
     assert info[4][3] > 0                                           # the 13-iteration case ran fused passes on the strips
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# facade (fs/fluid_simulator.py): the reference's create()/step()/field_to_numpy() contract and the state dump
+# ---------------------------------------------------------------------------------------------------------------------
+def test_facade_create_step_dump_and_resume(monkeypatch):
+    """FluidSimulator.create(num, resolution, dt, dx, re, vor_eps, scheme) builds the reference's default object graph
+    (RB-SOR omega=1.3 x2, fs/fluid_simulator.py:76-78); field_to_numpy() is the `d`-key dump (main.py:129-132);
+    state_dict()/load_state_dict() resume a CIP run bit-identically (every physical buffer)."""
+    from fake_fs2d import FakeFs2d
+    from fs import _lib
+    from fs.boundary_condition import build_scene
+    from fs.fluid_simulator import DyeFluidSimulator, FluidSimulator
+    from fs.pressure_updater import RedBlackSorPressureUpdater
+    from fs.solver import CipMacSolver, DyeMacSolver
+
+    FakeFs2d(_lib.load()).install(monkeypatch)
+    res = 24
+    dt, dx, re = 0.05 / res, 1.0 / res, 1e4
+    sim = FluidSimulator.create(1, res, dt, dx, re, 5.0, "cip", device="cpu")
+    assert isinstance(sim.solver, CipMacSolver) and isinstance(sim.solver.pressure_updater, RedBlackSorPressureUpdater)
+    assert sim.solver.pressure_updater._n_iter == 2 and sim.solver.pressure_updater._relaxation_factor == 1.3
+    assert sim.solver.resolution == (2 * res, res)
+    const, mask = build_scene(1, 2 * res, res)
+    ref = orc.OracleSolver(mask, const, dt, dx, re, "cip", 5.0, ("rbsor", 1.3, 2))
+    for _ in range(3):
+        sim.step()
+        ref.update()
+    out = sim.field_to_numpy()
+    assert sorted(out) == ["p", "v"] and out["v"].shape == (2 * res, res, 2) and out["p"].dtype == np.float32
+    assert_bitexact("v", out["v"], ref.v.current)
+    assert_bitexact("p", out["p"], ref.p.current)
+    # dump, continue, restore into a fresh simulator, continue: identical
+    saved = {k: a.copy() for k, a in sim.state_dict().items()}
+    for _ in range(2):
+        sim.step()
+    want = sim.state_dict()
+    sim2 = FluidSimulator.create(1, res, dt, dx, re, 5.0, "cip", device="cpu")
+    sim2.load_state_dict(saved)
+    for _ in range(2):
+        sim2.step()
+    got = sim2.state_dict()
+    assert sorted(got) == sorted(want)
+    for k in want:
+        assert_bitexact(f"resumed {k}", got[k], want[k])
+    # dye facade: three fields in the dump, MAC solver for the non-CIP schemes
+    dsim = DyeFluidSimulator.create(2, res, dt, dx, re, None, "upwind", device="cpu")
+    assert isinstance(dsim.solver, DyeMacSolver) and dsim.solver.vorticity_confinement is None
+    dsim.step()
+    d = dsim.field_to_numpy()
+    assert sorted(d) == ["dye", "p", "v"] and d["dye"].shape == (2 * res, res, 3)
+    # error behaviour of the reference (fs/fluid_simulator.py:104-106, fs/boundary_condition.py:216-217)
+    with pytest.raises(ValueError, match="Unknown scheme: bogus"):
+        FluidSimulator.create(1, res, dt, dx, re, None, "bogus", device="cpu")
+    with pytest.raises(NotImplementedError):
+        FluidSimulator.create(9, res, dt, dx, re, None, "cip", device="cpu")
+
+
+def test_constructor_injection_like_the_reference(monkeypatch):
+    """The reference's plugin API is constructor injection: MacSolver(bc, pressure_updater, advect_function,
+    dt, dx, re, vorticity_confinement) with fs.advection.advect_kk_scheme etc.; a user-defined PressureUpdater works too."""
+    from fake_fs2d import FakeFs2d
+    from fs import _lib
+    from fs.advection import advect_kk_scheme, advect_upwind
+    from fs.boundary_condition import get_boundary_condition
+    from fs.pressure_updater import JacobiPressureUpdater, PressureUpdater
+    from fs.solver import MacSolver
+    from fs.vorticity_confinement import VorticityConfinement
+
+    FakeFs2d(_lib.load()).install(monkeypatch)
+    res = 16
+    dt, dx, re = 0.05 / res, 1.0 / res, 100.0
+    bc = get_boundary_condition(1, res, enable_dye=False, device="cpu")
+    assert bc.get_resolution() == (2 * res, res)
+    vc = VorticityConfinement(bc, dt, dx, 2.5)
+    solver = MacSolver(bc, JacobiPressureUpdater(bc, dt, dx, n_iter=3), advect_kk_scheme, dt, dx, re, vc)
+    solver.update()
+    v, p = solver.get_fields()
+    assert v.to_numpy().shape == (2 * res, res, 2) and p.to_numpy().shape == (2 * res, res)
+    assert solver.is_wall(0, 0) and not solver.is_fluid_domain(0, 0) and solver.is_fluid_domain(res, res // 4)
+
+    calls = []
+
+    class CountingUpdater(PressureUpdater):        # a user plugin: called once per step with (p: DoubleBuffer, v_current)
+        def update(self, p, v_current) -> None:
+            calls.append((p, v_current))
+
+    s2 = MacSolver(bc, CountingUpdater(bc, dt, dx), advect_upwind, dt, dx, re)
+    s2.update(); s2.update()
+    assert len(calls) == 2 and calls[0][0] is s2.p and calls[1][1] is s2.v.current
+    with pytest.raises(TypeError):
+        MacSolver(bc, CountingUpdater(bc, dt, dx), lambda *a: None, dt, dx, re)
