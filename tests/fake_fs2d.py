@@ -188,6 +188,12 @@ class FakeFs2d:
         self._windowed(d, [self.a(f, d, channels)], lambda w, o: orc.lib().orc_clamp(
             _p(o), _i(o.shape[0]), _i(d.Y), _i(channels), _f(low), _f(high)))
 
+    def fs2d_render(self, rgb, v, p, dye, mask, d, dx, mode, stream) -> None:
+        V, P, M = self.a(v, d, 2), self.a(p, d, 1), self.a(mask, d)
+        D = self.a(dye, d, 3) if dye is not None else None
+        self._windowed(d, [self.a(rgb, d, 3)], lambda w, o: orc.lib().orc_render(
+            _p(o), _p(V[w]), _p(P[w]), _p(D[w]) if D is not None else None, _p(M[w]), _i(o.shape[0]), _i(d.Y), _f(dx), _i(mode)))
+
     # ---- pressure ----------------------------------------------------------------------------------------------------
     def fs2d_pressure_source(self, src, vc, d, dt, dx, stream) -> None:
         """The fake source array just carries the velocity rows the real kernel reads ([r0-1, r1+1) clamped); the sweeps

@@ -354,6 +354,15 @@ def test_facade_create_step_dump_and_resume(monkeypatch):
     dsim.step()
     d = dsim.field_to_numpy()
     assert sorted(d) == ["dye", "p", "v"] and d["dye"].shape == (2 * res, res, 3)
+    # render getters (fs/fluid_simulator.py:22-32, :111-119): (X, Y, 3) f32 images in rgb_buf, wall cells in the wall colour
+    mask2 = build_scene(2, 2 * res, res)[1]
+    v2, p2, dye2 = (f.to_numpy() for f in dsim.solver.get_fields())
+    for getter, mode in ((dsim.get_norm_field, "norm"), (dsim.get_pressure_field, "pressure"),
+                         (dsim.get_vorticity_field, "vorticity"), (dsim.get_dye_field, "dye")):
+        img = getter()
+        assert img is dsim.rgb_buf and img.to_numpy().shape == (2 * res, res, 3)
+        assert_bitexact(f"render {mode}", img.to_numpy(), orc.render(v2, p2, dye2, mask2, dx, mode))
+        assert np.array_equal(img.to_numpy()[mask2 == 1], np.broadcast_to(np.float32([0.5, 0.7, 0.5]), ((mask2 == 1).sum(), 3)))
     # error behaviour of the reference (fs/fluid_simulator.py:104-106, fs/boundary_condition.py:216-217)
     with pytest.raises(ValueError, match="Unknown scheme: bogus"):
         FluidSimulator.create(1, res, dt, dx, re, None, "bogus", device="cpu")
