@@ -38,7 +38,9 @@ class Field:
         return self.tensor[h:self.tensor.shape[0] - h] if h else self.tensor
 
     def to_numpy(self) -> np.ndarray:
-        return self.owned().detach().cpu().numpy()
+        """A host COPY of the owned rows (like Taichi's to_numpy()); never a view of live memory."""
+        t = self.owned().detach()
+        return t.cpu().numpy() if t.is_cuda else t.numpy().copy()   # CPU tensors only occur in the host-logic tests
 
     def from_numpy(self, a: np.ndarray) -> None:
         src = torch.from_numpy(np.ascontiguousarray(a)).to(self.tensor.dtype)

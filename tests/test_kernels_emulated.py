@@ -1,0 +1,116 @@
+"""The CUDA kernel SOURCES executed on the CPU (tests/cuda_emu: a fiber-based emulation of the CUDA slice they use, with
+mbarrier / TMA box-load semantics) and put through the GPU parity tests' own bodies -- bit-exact against the reference
+fixtures and the oracle.
+
+What this covers that nothing else can without a GPU: the kernels' indexing and tiling logic -- clamp windows and row
+windows, interior fast paths, the TMA tile pipeline with clamp repair in shared memory, the fused Jacobi kernels' tile
+scheduler / slow-cell lists / edge-row exchange / shrinking valid region (all three variants), barrier placement (a
+missing __syncthreads deadlocks or corrupts here too), TMA box geometry and alignment rules.
+What it does not cover: anything about the hardware -- memory ordering, async-proxy fences, occupancy, performance.  The
+`-m gpu` tests on a B200 remain the parity gate; this module exists so that kernel logic is exercised on every CPU run.
+The emulated library is tests/cuda_emu/_build/libfs2d_emu.so; the product never loads it (fs/_lib.py opens lib/libfs2d.so only).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import sys
+
+import pytest
+import torch
+from conftest import REPO
+
+sys.path.insert(0, str(REPO / "tests" / "cuda_emu"))
+
+import test_gpu_parity as G  # noqa: E402  (its module-level `gpu` mark does not apply to the functions re-exported here)
+
+
+@pytest.fixture(scope="module")
+def env():
+    """Swap libfs2d.so for the emulated build and CUDA tensors for CPU tensors, for this module only."""
+    import build_emu
+    from fs import _lib, boundary_condition, double_buffer
+
+    lib = ctypes.CDLL(os.environ.get("FS2D_EMU_LIB") or str(build_emu.build()))   # override: mutation testing of this harness
+    for name, (res, args) in _lib._SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    saved = (_lib._lib, _lib.ptr, _lib.stream, double_buffer.default_device, boundary_condition.default_device)
+    _lib._lib = lib
+    _lib.ptr = lambda t: None if t is None else t.data_ptr()
+    _lib.stream = lambda: 0
+    double_buffer.default_device = boundary_condition.default_device = lambda: torch.device("cpu")
+    try:
+        assert _lib.load() is lib and lib.fs2d_device_ok()
+        yield lib
+    finally:
+        _lib._lib, _lib.ptr, _lib.stream, double_buffer.default_device, boundary_condition.default_device = saved
+
+
+# ---- the GPU parity tests, unchanged -------------------------------------------------------------------------------------
+test_emu_each_kernel_matches_reference_fixture = G.test_each_kernel_matches_reference_fixture
+test_emu_trajectory_matches_reference_fixture = G.test_trajectory_matches_reference_fixture
+test_emu_dye_trajectory_matches_reference_fixture = G.test_dye_trajectory_matches_reference_fixture
+test_emu_render_matches_reference_fixture = G.test_render_matches_reference_fixture
+test_emu_state_dict_roundtrip_resumes_bitwise = G.test_state_dict_roundtrip_resumes_bitwise
+test_emu_random_mask_trajectory_vs_oracle = G.test_random_mask_trajectory_vs_oracle
+test_emu_division_special_cases_match_the_oracle = G.test_division_special_cases_match_the_oracle
+test_emu_facade_matches_reference_defaults = G.test_facade_matches_reference_defaults
+
+
+# ---- the same bodies on the parameter sets an emulator finishes in seconds -----------------------------------------------
+_SMALL_CONFIGS = [c for c in G.CONFIGS if c[0] in ("cfg1_as_given", "kk_r100", "cip_r50_y_not_mult4")]
+
+
+@pytest.mark.parametrize("cfg", _SMALL_CONFIGS, ids=[c[0] for c in _SMALL_CONFIGS])
+def test_emu_config_trajectory_vs_oracle(env, cfg):
+    G.test_config_trajectory_vs_oracle(env, cfg)
+
+
+def test_emu_jacobi_row_range_invariance_and_literal_equivalence(env):
+    G.test_jacobi_row_range_invariance_and_literal_equivalence(env, res=128)
+
+
+@pytest.mark.parametrize("variant", [1, 3, 5])
+@pytest.mark.parametrize("num,X,Y", [(1, 128, 64), (2, 256, 128), (4, 200, 96), (5, 384, 192), (1, 288, 352)])
+def test_emu_fused_pass_equals_literal_iterations(env, num, X, Y, variant):
+    # (1, 288, 352) is wide and tall enough to contain OPEN-FLUID tiles (no wall, BC cell or grid edge in the tile): the
+    # register-tile kernels' fast path with the early prefetch of the next tile; every tile of the smaller grids is "slow"
+    big = X * Y > 40000
+    G.test_fused_pass_equals_literal_iterations(env, num, X, Y, variant, t_list=(3, 8) if big else (1, 2, 4, 6, 8, 11, 12),
+                                                need=2 if big else 3)
+
+
+@pytest.mark.parametrize("variant", [1, 3, 5])
+def test_emu_fused_pass_random_obstacles(env, variant):
+    G.test_fused_pass_random_obstacles(env, 0, variant, size=(320, 160), t_list=(4, 8))
+
+
+@pytest.mark.parametrize("num,X,Y,n_iter", [(1, 128, 64, 7), (3, 320, 160, 13), (2, 96, 48, 3)])
+def test_emu_fused_update_equals_literal_update(env, num, X, Y, n_iter):
+    G.test_fused_update_equals_literal_update(env, num, X, Y, n_iter)
+
+
+@pytest.mark.parametrize("num,X,Y", [(2, 256, 128), (3, 200, 176), (5, 333, 208), (1, 64, 48)])
+def test_emu_stream_kernels_equal_direct_kernels(env, num, X, Y):
+    G.test_stream_kernels_equal_direct_kernels(env, num, X, Y)
+
+
+@pytest.mark.parametrize("cfg", [0, 2, 3])
+def test_emu_stream_kernel_shapes(env, cfg):
+    """every {stages x CTAs/SM x threads} shape of the TMA streaming kernel (fs2d_set_tuning(3, cfg)) == direct kernels"""
+    env.fs2d_set_tuning(3, cfg)
+    try:
+        G.test_stream_kernels_equal_direct_kernels(env, 3, 200, 176)
+    finally:
+        env.fs2d_set_tuning(3, 1)
+
+
+@pytest.mark.parametrize("variant", [3, 5])
+def test_emu_fused_pass_split_into_interior_and_edge_launches(env, variant):
+    G.test_fused_pass_split_into_interior_and_edge_launches(env, variant, X=420, Y=160)
+
+
+@pytest.mark.parametrize("num,res,scheme", [(2, 96, "kk"), (5, 100, "upwind")])
+def test_emu_dye_simulator_vs_oracle(env, num, res, scheme):
+    G.test_dye_simulator_vs_oracle(env, num, res, scheme)
