@@ -538,6 +538,22 @@ int fs2d_cip_nonadv_grad(float *fxn, float *fyn, const float *fxc, const float *
     return FS2D_OK;
 }
 
+int fs2d_cip_nonadv_fused(float *fn, float *fxn, float *fyn, const float *fc, const float *fxc, const float *fyc, const float *pc,
+                          const uint8_t *mask, fs2d_dom d, float dt, float dx, float re, float two_dx, void *stream) {
+    FS2D_REQUIRE(fn && fxn && fyn && fc && fxc && fyc && pc && mask, "null field pointer");
+    FS2D_REQUIRE(fn != fc && fxn != fxc && fyn != fyc, "the fused non-advection phase cannot run in place");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+    const void *ptrs[] = {fn, fxn, fyn, fc, fxc, fyc, pc, mask};
+    if (!stream_ok(d, ptrs, 8)) {   // TMA needs Y % 16 == 0 and 16-byte aligned fields: the two reference kernels instead
+        if (int e = fs2d_cip_nonadv(fn, fc, pc, mask, d, dt, dx, re, stream)) return e;
+        return fs2d_cip_nonadv_grad(fxn, fyn, fxc, fyc, fc, fn, mask, d, two_dx, stream);
+    }
+    if (int e = stream_cip_nonadv_fused(fn, fxn, fyn, fc, fxc, fyc, pc, mask, d, dt, dx, re, two_dx, STREAM)) return e;
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
 int fs2d_cip_advect(float *fn, float *fxn, float *fyn, const float *fc, const float *fxc, const float *fyc,
                     const float *v, const uint8_t *mask, fs2d_dom d, float dt, float dx, float dx2, float dx3,
                     void *stream) {

@@ -149,9 +149,20 @@ class CipMacSolver(Solver):
         bc = self._bc
         _lib.call("fs2d_set_grad", fx.ptr(), fy.ptr(), f.ptr(), bc.dom, self.dx, _lib.stream())
 
+    #: EXPERIMENTAL, off by default: run the two non-advection kernels as ONE pass over HBM (fs2d_cip_nonadv_fused; same
+    #: results bit for bit, 53 instead of 70 B/cell).  Single rank only.  Verified on the CPU emulation of the kernel
+    #: sources (tests/test_kernels_emulated.py); not yet measured on a B200.
+    fused_non_advection = False
+
     def _update_velocities(self, v: DoubleBuffer, vx: DoubleBuffer, vy: DoubleBuffer, p: DoubleBuffer) -> None:
-        self._non_advection_phase(v.next, v.current, p.current)
-        self._non_advection_phase_grad(vx.next, vy.next, vx.current, vy.current, v.current, v.next)
+        if self.fused_non_advection and self._bc.partition.world == 1:
+            bc = self._bc
+            _lib.call("fs2d_cip_nonadv_fused", v.next.ptr(), vx.next.ptr(), vy.next.ptr(), v.current.ptr(), vx.current.ptr(),
+                      vy.current.ptr(), p.current.ptr(), _lib.ptr(bc._bc_mask), bc.dom, self.dt, self.dx, self.re, 2.0 * self.dx,
+                      _lib.stream())
+        else:
+            self._non_advection_phase(v.next, v.current, p.current)
+            self._non_advection_phase_grad(vx.next, vy.next, vx.current, vy.current, v.current, v.next)
         v.swap(); vx.swap(); vy.swap()
         self._advection_phase(v.next, vx.next, vy.next, v.current, vx.current, vy.current, v.current)
         v.swap(); vx.swap(); vy.swap()

@@ -732,3 +732,94 @@ def test_division_special_cases_match_the_oracle(env):
             jac = s.pressure_updater
             pn = fld(p[::-1].copy()); jac._sweep(pn, fld(p), jac._source(fld(v)), inline_bc=False)
             assert_bitexact(f"jacobi special {trial}", pn.to_numpy(), pn_want)
+
+
+# ------------------------------------------------------------------------------------------------
+# 11. EXPERIMENTAL kernels (off by default).  On a GPU they run only with FS2D_EXPERIMENTAL=1 (not yet measured there);
+#     tests/test_kernels_emulated.py always runs the same bodies on the CPU emulation of the kernel sources.
+# ------------------------------------------------------------------------------------------------
+import os  # noqa: E402
+
+experimental = pytest.mark.skipif(os.environ.get("FS2D_EXPERIMENTAL") != "1", reason="experimental kernel: set FS2D_EXPERIMENTAL=1")
+
+
+def _nonadv_fused_check(num, X, Y, mask_override=None):
+    """fs2d_cip_nonadv_fused == fs2d_cip_nonadv + fs2d_cip_nonadv_grad, all three output fields, whole grid and a row
+    window with clamp bounds inside the array, power-of-two and general dx; never-written cells keep their values."""
+    from fs import _lib
+    from fs.boundary_condition import BoundaryCondition, build_scene
+    from fs.fluid_simulator import make_solver
+
+    const, mask = build_scene(num, X, Y)
+    if mask_override is not None:
+        mask = mask_override
+    bc = BoundaryCondition(const, mask)
+    rng = np.random.default_rng(X * Y + 1)
+    doms = [bc.dom, bc.dom.replace(r0=5, r1=X - 11, clo=2, chi=X - 3)]
+    for dxv in (1.0 / 128, 0.013):
+        s = make_solver(bc, 0.05 / Y, dxv, 1e3, None, "cip", pressure="jacobi", n_iter=1)
+        init = {k: rng.uniform(-1, 1, getattr(s, k).current.tensor.shape).astype(np.float32) for k in ("v", "vx", "vy", "p")}
+        stale = {k: rng.uniform(-1, 1, getattr(s, k).current.tensor.shape).astype(np.float32) for k in ("v", "vx", "vy")}
+        for dom in doms:
+            out = []
+            for fused in (True, False):
+                for k, a in init.items():
+                    getattr(s, k).current.from_numpy(a)
+                for k, a in stale.items():
+                    getattr(s, k).next.from_numpy(a)
+                old = bc.dom
+                bc.dom = dom
+                try:
+                    if fused:
+                        _lib.call("fs2d_cip_nonadv_fused", s.v.next.ptr(), s.vx.next.ptr(), s.vy.next.ptr(), s.v.current.ptr(),
+                                  s.vx.current.ptr(), s.vy.current.ptr(), s.p.current.ptr(), _lib.ptr(bc._bc_mask), bc.dom, s.dt,
+                                  s.dx, s.re, 2.0 * s.dx, _lib.stream())
+                    else:
+                        s._non_advection_phase(s.v.next, s.v.current, s.p.current)
+                        s._non_advection_phase_grad(s.vx.next, s.vy.next, s.vx.current, s.vy.current, s.v.current, s.v.next)
+                finally:
+                    bc.dom = old
+                out.append((s.v.next.to_numpy(), s.vx.next.to_numpy(), s.vy.next.to_numpy()))
+            for name, a, b in zip(("fn", "fxn", "fyn"), out[0], out[1]):
+                assert_bitexact(f"{name} bc{num} {X}x{Y} dx={dxv} rows {dom.r0}:{dom.r1}", a, b)
+
+
+@pytest.mark.parametrize("num,X,Y", [(2, 256, 128), (3, 200, 176), (5, 333, 208), (1, 64, 48), (4, 97, 80)])
+def test_nonadv_fused_equals_two_kernels(env, num, X, Y):
+    _nonadv_fused_check(num, X, Y)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_nonadv_fused_random_masks(env, seed):
+    rng = np.random.default_rng(500 + seed)
+    X, Y = 150 + 16 * seed, 96
+    mask = np.zeros((X, Y), dtype=np.uint8)
+    mask[:, :2] = 1; mask[:, -2:] = 1
+    for _ in range(25):
+        i, j = int(rng.integers(0, X - 6)), int(rng.integers(0, Y - 6))
+        mask[i:i + int(rng.integers(1, 7)), j:j + int(rng.integers(1, 7))] = 1
+    mask[:2, 2:-2] = np.where(rng.random((2, Y - 4)) < 0.8, 2, mask[:2, 2:-2])
+    mask[-2:, 2:-2] = np.where(rng.random((2, Y - 4)) < 0.7, 3, mask[-2:, 2:-2])
+    _nonadv_fused_check(1, X, Y, mask_override=mask)
+
+
+def test_fused_non_advection_trajectory_vs_oracle(env):
+    """CipMacSolver.fused_non_advection = True: a whole trajectory through the experimental kernel vs the oracle."""
+    from fs.boundary_condition import build_scene
+    from oracle import oracle as orc
+
+    X, Y = 160, 80
+    dt, dx, re, vc, pressure = 0.05 / Y, 1.0 / Y, 1e4, 5.0, ("jacobi", 6)
+    const, mask = build_scene(3, X, Y)
+    s = make_fs(mask, const, dt, dx, re, "cip", vc, pressure)
+    s.fused_non_advection = True
+    ref = orc.OracleSolver(mask, const, dt, dx, re, "cip", vc, pressure)
+    for n in range(4):
+        s.update(); ref.update()
+        got = fs_state(s)
+        for k, a in ref.state().items():
+            assert_bitexact(f"step {n} {k}", got[k].to_numpy(), a)
+
+
+for _t in (test_nonadv_fused_equals_two_kernels, test_nonadv_fused_random_masks, test_fused_non_advection_trajectory_vs_oracle):
+    globals()[_t.__name__] = experimental(_t)

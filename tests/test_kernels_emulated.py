@@ -114,3 +114,19 @@ def test_emu_fused_pass_split_into_interior_and_edge_launches(env, variant):
 @pytest.mark.parametrize("num,res,scheme", [(2, 96, "kk"), (5, 100, "upwind")])
 def test_emu_dye_simulator_vs_oracle(env, num, res, scheme):
     G.test_dye_simulator_vs_oracle(env, num, res, scheme)
+
+
+# ---- experimental kernels (off by default in the product; gated on the GPU until measured there) ---------------------------
+@pytest.mark.parametrize("num,X,Y", [(2, 256, 128), (3, 200, 176), (5, 333, 208), (1, 64, 48), (4, 97, 80)])
+def test_emu_nonadv_fused_equals_two_kernels(env, num, X, Y):
+    G._nonadv_fused_check(num, X, Y)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_emu_nonadv_fused_random_masks(env, seed):
+    G.test_nonadv_fused_random_masks.__wrapped__(env, seed) if hasattr(G.test_nonadv_fused_random_masks, "__wrapped__") else \
+        G.test_nonadv_fused_random_masks(env, seed)
+
+
+def test_emu_fused_non_advection_trajectory_vs_oracle(env):
+    G.test_fused_non_advection_trajectory_vs_oracle(env)
