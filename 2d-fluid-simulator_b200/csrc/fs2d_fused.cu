@@ -568,10 +568,21 @@ __device__ __forceinline__ float f_post_p(const float *pl, const uint8_t *code, 
     return mode == 0 ? va : (mode == 1 ? (va + vb) / 2.0f : 0.0f);
 }
 
-__global__ void __launch_bounds__(V_THREADS, 1)
-    k_jacobi_fused5(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_src,
-                    const __grid_constant__ CUtensorMap map_code, float *__restrict__ p_out, unsigned int *tile_ctr,
-                    fs2d_dom d, FusedGeom g) {
+// bar.sync on a named barrier shared by `count` threads (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+// Variant 6 (EXPERIMENTAL, PAIR = true): in open-fluid tiles a warp's iteration depends only on the edge rows of the warps
+// directly above and below it, so after iteration 0 the CTA-wide barrier per iteration is replaced by two 64-thread named
+// barriers (with the upper and with the lower neighbour; even-indexed pairs first, so the waits cannot form a cycle).
+// Warps may then drift by an iteration against their neighbours: one warp's shuffle / LDS phase overlaps another's FP32
+// phase instead of all twelve stalling together.  The ping-pong exchange buffer is deep enough: warp w reads the rows
+// its neighbours wrote for iteration s at the start of iteration s + 1 and meets them at the pair barrier after its own
+// write, before they can write iteration s + 2.  Slow tiles keep the CTA barriers.  Same arithmetic: bit-identical.
+template <bool PAIR>
+__device__ __forceinline__ void jacobi_fused5_body(const CUtensorMap *mp, const CUtensorMap *ms, const CUtensorMap *mc,
+                                                   float *__restrict__ p_out, unsigned int *tile_ctr, const fs2d_dom &d,
+                                                   const FusedGeom &g) {
     constexpr int HK = 8;
     extern __shared__ __align__(1024) float sm[];
     uint8_t *stg_code = reinterpret_cast<uint8_t *>(sm + VOFF_BYTES);
@@ -589,7 +600,6 @@ __global__ void __launch_bounds__(V_THREADS, 1)
     const bool leader = tid == 0;
     const int n_tiles = g.tiles_i * g.tiles_j;
     constexpr uint32_t TX_BYTES = VN * (4 + 8) + VSI * FCW;
-    const CUtensorMap *mp = &map_p, *ms = &map_src, *mc = &map_code;
 #define FS2D_ISSUE(tile)                                                            \
     do {                                                                            \
         const int R0_ = d.r0 + f_tile_row(g, (tile) / g.tiles_j) * g.TI - g.T;                   \
@@ -683,9 +693,21 @@ __global__ void __launch_bounds__(V_THREADS, 1)
                     const int xw = (s & 1) * VEX_PLANE;
                     sts4(sm + x_own + xw, p[0][0], p[0][1], p[0][2], p[0][3]);
                     sts4(sm + x_own + xw + FSJ, p[HK - 1][0], p[HK - 1][1], p[HK - 1][2], p[HK - 1][3]);
-                    __syncthreads();   // edge rows of iteration s are complete (and s_next is visible after s == 1)
+                    if (!PAIR || s == 0) {
+                        __syncthreads();   // edge rows of iteration s are complete (and s_next is visible after s == 1)
+                    } else {               // (after s == 0 the CTA barrier also frees the staged plane for the prefetch)
+                        // pair barrier id 1 + (index of the pair's upper warp); even-indexed pairs first
+                        if ((w & 1) == 0) {
+                            if (w < V_WARPS - 1) named_bar_sync(1 + w, 64);
+                            if (w > 0) named_bar_sync(w, 64);
+                        } else {
+                            named_bar_sync(w, 64);
+                            if (w < V_WARPS - 1) named_bar_sync(1 + w, 64);
+                        }
+                    }
                 }
             }
+            if (PAIR && g.T > 2) __syncthreads();   // s_next (written at s == 1) becomes visible to every warp
         } else {
             // ---- slow tile: full working planes in P0 / the (t2, t3) staging area, cooperative fix-up ------------
 #pragma unroll
@@ -765,10 +787,24 @@ __global__ void __launch_bounds__(V_THREADS, 1)
 #undef FS2D_NEXT_TILE
 }
 
+__global__ void __launch_bounds__(V_THREADS, 1)
+    k_jacobi_fused5(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_src,
+                    const __grid_constant__ CUtensorMap map_code, float *__restrict__ p_out, unsigned int *tile_ctr,
+                    fs2d_dom d, FusedGeom g) {
+    // the descriptors must be addressed in the kernel-parameter space: take their addresses here
+    jacobi_fused5_body<false>(&map_p, &map_src, &map_code, p_out, tile_ctr, d, g);
+}
+__global__ void __launch_bounds__(V_THREADS, 1)
+    k_jacobi_fused6(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_src,
+                    const __grid_constant__ CUtensorMap map_code, float *__restrict__ p_out, unsigned int *tile_ctr,
+                    fs2d_dom d, FusedGeom g) {
+    jacobi_fused5_body<true>(&map_p, &map_src, &map_code, p_out, tile_ctr, d, g);
+}
+
 // (A packed fp32x2 variant -- FADD2/FFMA2, column-pair ownership -- was measured at 915 us/pass vs 795 us for
 // variant 1 at 8192^2, T=8: bank-conflicted scalar j-neighbour loads and pack/unpack moves; removed.)
 int g_fused_variant = 5;   // fs2d_set_tuning(1, v): 1 = one column per thread (64 x 128 tile, smem planes); 3 = register tile +
-                           // shuffles (64 x 128 tile); 5 = register tile on a 96 x 128 tile
+                           // shuffles (64 x 128 tile); 5 = register tile on a 96 x 128 tile; 6 = 5 with pair barriers (experimental)
 
 // ---------------------------------------------------------------------------------------------
 // host side
@@ -810,7 +846,7 @@ int make_map(CUtensorMap *m, CUtensorMapDataType dt, size_t esz, const void *bas
     return FS2D_OK;
 }
 
-int fused_tile_rows() { return g_fused_variant == 5 ? VSI : FSI; }
+int fused_tile_rows() { return g_fused_variant >= 5 ? VSI : FSI; }
 
 bool fused_supported(const float *pa, const float *pb, const float *src, const uint8_t *pcode, const fs2d_dom &d) {
     return d.Y % 16 == 0 && ((uintptr_t)pa % 16 == 0) && ((uintptr_t)pb % 16 == 0) && ((uintptr_t)src % 16 == 0) &&
@@ -830,6 +866,7 @@ int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t 
         FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
         FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
         FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM));
+        FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM));
         attr_set = true;
     }
     CUtensorMap mp, ms, mc;
@@ -861,6 +898,7 @@ int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t 
     ++g_launches;
     if (g_fused_variant == 3) k_jacobi_fused3<8><<<grid, dim3(32, FSI / 8, 1), F_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);
     else if (g_fused_variant == 5) k_jacobi_fused5<<<grid, dim3(32, V_WARPS, 1), V_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);
+    else if (g_fused_variant == 6) k_jacobi_fused6<<<grid, dim3(32, V_WARPS, 1), V_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);
     else k_jacobi_fused<<<grid, dim3(FSJ, FNTY, 1), F_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);
     return FS2D_OK;
 }

@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <functional>
 #include <vector>
 
@@ -131,6 +132,23 @@ inline void barrier(int pred, int *r_and, int *r_or) {
     if (r_and) *r_and = c.res_and[g];
     if (r_or) *r_or = c.res_or[g];
 }
+// bar.sync id, count: a named barrier shared by exactly `count` threads (ids 1..15)
+struct NamedBar { int arrived = 0, gen = 0; };
+inline NamedBar *named_bars() {
+    static NamedBar nb[16];
+    return nb;
+}
+inline void named_barrier(int id, int count) {
+    if (id < 1 || id > 15 || count % 32 != 0) { fprintf(stderr, "cuda_emu: bad named barrier (%d, %d)\n", id, count); abort(); }
+    NamedBar &b = named_bars()[id];
+    const int my = b.gen;
+    ++M().progress;
+    if (++b.arrived == count) {
+        b.arrived = 0;
+        ++b.gen;
+    }
+    while (b.gen == my) yield();
+}
 inline Warp &my_warp() { return M().cta.warps[M().cur->lin / 32]; }
 inline void warp_release(Warp &w) {
     w.arrived = 0;
@@ -190,6 +208,7 @@ void launch(dim3 grid, dim3 block, size_t smem, F f) {
                 c.bdim = block;
                 c.gdim = grid;
                 c.warps.assign((n + 31) / 32, Warp());
+                for (int q = 0; q < 16; ++q) named_bars()[q] = NamedBar();
                 memset(dyn, 0xCD, smem ? smem : 1024);     // shared memory starts as garbage
                 for (int t = 0; t < n; ++t) {
                     Fiber &fb = m.fibers[t];
@@ -203,18 +222,42 @@ void launch(dim3 grid, dim3 block, size_t smem, F f) {
                     fb.ctx.uc_link = nullptr;
                     makecontext(&fb.ctx, (void (*)())trampoline, 0);
                 }
-                int live = n;
-                while (live > 0) {
-                    const unsigned long before = m.progress;
-                    live = 0;
-                    for (int t = 0; t < n; ++t) {
+                // Schedule.  Default: round-robin over all fibers (deterministic, warps advance in lock step).
+                // FS2D_EMU_SCHED=<seed>: adversarial starvation -- one randomly chosen "victim" warp is not run at all while
+                // any other warp can still make progress, then it runs one slice and a new victim is drawn.  Warps thereby
+                // drift apart as far as the kernel's own synchronisation allows, so a missing barrier shows up as a wrong
+                // result or a deadlock (tests/test_kernels_emulated.py runs the synchronisation-heavy kernels under several seeds).
+                static const char *sched_env = getenv("FS2D_EMU_SCHED");
+                static unsigned long long rng = sched_env ? 0x9E3779B97F4A7C15ull * (unsigned long long)(atoll(sched_env) + 1) : 0;
+                auto next_rand = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
+                const int n_warps = (n + 31) / 32;
+                std::vector<int> order(n_warps);
+                for (int q = 0; q < n_warps; ++q) order[q] = q;
+                auto run_warp = [&](int wq) {
+                    for (int t = wq * 32; t < n && t < wq * 32 + 32; ++t) {
                         Fiber &fb = m.fibers[t];
                         if (fb.done) continue;
                         m.cur = &fb;
                         swapcontext(&m.sched, &fb.ctx);
-                        if (!fb.done) ++live;
                     }
-                    if (live > 0 && m.progress == before) {
+                };
+                // the leader warp (tile scheduler, TMA issue) is the most interesting victim: starve it half of the time
+                auto draw_victim = [&]() { return (next_rand() & 1) ? 0 : (int)(next_rand() % n_warps); };
+                int live = n, stalled = 0, victim = sched_env ? draw_victim() : -1;
+                while (live > 0) {
+                    const unsigned long before = m.progress;
+                    if (sched_env)
+                        for (int q = n_warps - 1; q > 0; --q) std::swap(order[q], order[next_rand() % (q + 1)]);
+                    for (int q = 0; q < n_warps; ++q)
+                        if (order[q] != victim) run_warp(order[q]);
+                    if (sched_env && m.progress == before) {     // everybody else is blocked: let the victim move, redraw
+                        run_warp(victim);
+                        victim = draw_victim();
+                    }
+                    live = 0;
+                    for (int t = 0; t < n; ++t) live += !m.fibers[t].done;
+                    stalled = m.progress == before ? stalled + 1 : 0;
+                    if (live > 0 && stalled > (sched_env ? 2 * n_warps : 0)) {
                         fprintf(stderr, "cuda_emu: deadlock in block (%u,%u,%u): %d threads blocked (barrier %d/%d arrived)\n", bx, by,
                                 bz, live, c.arrived, c.n - c.exited);
                         abort();

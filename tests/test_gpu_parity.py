@@ -821,5 +821,12 @@ def test_fused_non_advection_trajectory_vs_oracle(env):
             assert_bitexact(f"step {n} {k}", got[k].to_numpy(), a)
 
 
-for _t in (test_nonadv_fused_equals_two_kernels, test_nonadv_fused_random_masks, test_fused_non_advection_trajectory_vs_oracle):
+@pytest.mark.parametrize("num,X,Y", [(2, 256, 128), (5, 384, 192), (2, 1000, 512), (3, 2048, 1024)])
+def test_pair_barrier_variant_equals_literal_iterations(env, num, X, Y):
+    """fused Jacobi variant 6 (pairwise named barriers between neighbouring warps in open-fluid tiles)"""
+    test_fused_pass_equals_literal_iterations(env, num, X, Y, 6)
+
+
+for _t in (test_nonadv_fused_equals_two_kernels, test_nonadv_fused_random_masks, test_fused_non_advection_trajectory_vs_oracle,
+           test_pair_barrier_variant_equals_literal_iterations):
     globals()[_t.__name__] = experimental(_t)

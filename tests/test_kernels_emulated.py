@@ -71,7 +71,7 @@ def test_emu_jacobi_row_range_invariance_and_literal_equivalence(env):
     G.test_jacobi_row_range_invariance_and_literal_equivalence(env, res=128)
 
 
-@pytest.mark.parametrize("variant", [1, 3, 5])
+@pytest.mark.parametrize("variant", [1, 3, 5, 6])       # 6: experimental pair-barrier variant (off by default)
 @pytest.mark.parametrize("num,X,Y", [(1, 128, 64), (2, 256, 128), (4, 200, 96), (5, 384, 192), (1, 288, 352)])
 def test_emu_fused_pass_equals_literal_iterations(env, num, X, Y, variant):
     # (1, 288, 352) is wide and tall enough to contain OPEN-FLUID tiles (no wall, BC cell or grid edge in the tile): the
@@ -81,7 +81,7 @@ def test_emu_fused_pass_equals_literal_iterations(env, num, X, Y, variant):
                                                 need=2 if big else 3)
 
 
-@pytest.mark.parametrize("variant", [1, 3, 5])
+@pytest.mark.parametrize("variant", [1, 3, 5, 6])
 def test_emu_fused_pass_random_obstacles(env, variant):
     G.test_fused_pass_random_obstacles(env, 0, variant, size=(320, 160), t_list=(4, 8))
 
@@ -106,7 +106,7 @@ def test_emu_stream_kernel_shapes(env, cfg):
         env.fs2d_set_tuning(3, 1)
 
 
-@pytest.mark.parametrize("variant", [3, 5])
+@pytest.mark.parametrize("variant", [3, 5, 6])
 def test_emu_fused_pass_split_into_interior_and_edge_launches(env, variant):
     G.test_fused_pass_split_into_interior_and_edge_launches(env, variant, X=420, Y=160)
 
@@ -130,3 +130,26 @@ def test_emu_nonadv_fused_random_masks(env, seed):
 
 def test_emu_fused_non_advection_trajectory_vs_oracle(env):
     G.test_fused_non_advection_trajectory_vs_oracle(env)
+
+
+def test_emu_pair_barrier_variant_on_a_wide_open_grid(env):
+    """variant 6 where it differs from variant 5: many OPEN-FLUID tiles (pair barriers instead of CTA barriers), every
+    pass size, against literal iterations"""
+    G.test_fused_pass_equals_literal_iterations(env, 1, 300, 480, 6, t_list=(2, 3, 5, 8, 12), need=5)
+
+
+# ---- adversarial schedules ---------------------------------------------------------------------------------------------------
+@pytest.mark.skipif(os.environ.get("FS2D_EMU_SCHED") is not None, reason="already inside an adversarial-schedule run")
+@pytest.mark.parametrize("seed", [1, 2])
+def test_emu_synchronisation_under_adversarial_warp_schedules(seed):
+    """The kernels with hand-written synchronisation (fused Jacobi variants incl. the open-fluid fast path and the
+    pair-barrier variant, the TMA streaming kernels, the fused non-advection kernel) once more under the emulator's
+    starvation scheduler (FS2D_EMU_SCHED=<seed>): a victim warp -- the leader half of the time -- only runs when every
+    other warp is blocked, so warps drift as far apart as the barriers allow.  Seeded mutants with a missing barrier or
+    an early TMA refill pass the round-robin schedule but fail here."""
+    import subprocess
+
+    sel = "352 or pair_barrier or stream_kernel_shapes or (nonadv_fused_equals and 256) or random_obstacles"
+    out = subprocess.run([sys.executable, "-m", "pytest", __file__, "-x", "-q", "-p", "no:cacheprovider", "-k", sel],
+                         capture_output=True, text=True, timeout=1200, env=dict(os.environ, FS2D_EMU_SCHED=str(seed)))
+    assert out.returncode == 0 and " passed" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
