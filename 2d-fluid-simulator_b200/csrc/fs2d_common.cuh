@@ -36,7 +36,8 @@ bool is_pow2(float x);
 extern int g_fused_variant;  // fused Jacobi kernel variant (1 smem planes, 3 register tile), fs2d_set_tuning(1, v)
 // one fused pass of T Jacobi iterations p_in -> p_out (fs2d_fused.cu)
 int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t *pcode, const fs2d_dom &d, int T,
-               cudaStream_t s, int skip_from = 0, int skip_n = 0);
+               cudaStream_t s, int skip_from = 0, int skip_n = 0, bool emit = false);
+extern int g_tail_emit;      // fs2d_set_tuning(4, v), see fs2d_fused.cu
 // TMA-fed streaming versions of the stencil kernels (fs2d_stream.cu); g_stream: fs2d_set_tuning(2, 0/1)
 extern int g_stream, g_stream_cfg;
 bool stream_ok(const fs2d_dom &d, const void *const *ptrs, int n);

@@ -579,10 +579,18 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
 // phase instead of all twelve stalling together.  The ping-pong exchange buffer is deep enough: warp w reads the rows
 // its neighbours wrote for iteration s at the start of iteration s + 1 and meets them at the pair barrier after its own
 // write, before they can write iteration s + 2.  Slow tiles keep the CTA barriers.  Same arithmetic: bit-identical.
-template <bool PAIR>
+//
+// EMIT (EXPERIMENTAL, the "tail" pass of fs2d_jacobi_update when fs2d_set_tuning(4, 1)): besides its output the pass
+// stores, into the wall-BC cells of its INPUT array `emit` (= p_in; those cells are never read, their values are
+// recomputed from pcode), the BC values of its PENULTIMATE state.  The reference leaves exactly these values in the
+// wall cells of the buffer its last sweep writes (fs/pressure_updater.py:56-60: BC'd in place one iteration earlier,
+// SURVEY T1), so a pass of T iterations ending at iteration n - 1, followed by ONE literal iteration, reproduces both
+// physical buffers -- instead of ending every update with two literal iterations.  A wall-BC cell has a fluid
+// neighbour, which is a slow cell of the same loaded tile, so only slow tiles emit.
+template <bool PAIR, bool EMIT>
 __device__ __forceinline__ void jacobi_fused5_body(const CUtensorMap *mp, const CUtensorMap *ms, const CUtensorMap *mc,
                                                    float *__restrict__ p_out, unsigned int *tile_ctr, const fs2d_dom &d,
-                                                   const FusedGeom &g) {
+                                                   const FusedGeom &g, float *emit) {
     constexpr int HK = 8;
     extern __shared__ __align__(1024) float sm[];
     uint8_t *stg_code = reinterpret_cast<uint8_t *>(sm + VOFF_BYTES);
@@ -723,6 +731,17 @@ __device__ __forceinline__ void jacobi_fused5_body(const CUtensorMap *mp, const 
             const uint8_t *code = stg_code + coff;   // tile pcode, row pitch FCW (the staging buffer stays intact)
             int cur = VOFF_P0, nxt = VOFF_SRC;
             for (int s = 0; s < g.T; ++s) {
+                if (EMIT && s == g.T - 1) {
+                    // plane `cur` holds the state after T - 1 iterations: its BC values go to the wall-BC cells of the
+                    // tile's output region in the input array
+                    for (int e = tid; e < g.TI * g.TJ; e += V_THREADS) {
+                        const int r = g.T + e / g.TJ, cc = g.HJ + e % g.TJ, gr = R0 + r, gc = C0 + cc;
+                        if (gr >= d.r1 || gc >= d.Y) continue;
+                        const int cd = code[r * FCW + cc] & 15;
+                        if (cd >= FS2D_PC_W_IM && cd <= FS2D_PC_W_IP_JM)
+                            emit[(size_t)gr * d.Y + gc] = f_post_p(sm + cur, code, FCW, r, cc, rlo, rhi, clo, chi);
+                    }
+                }
                 // all threads share the slow cells and leave, in plane `nxt`, the SUM of the four post-BC neighbour
                 // values (the reference's order) for the owning thread to pick up
                 for (int e = tid; e < ns; e += V_THREADS) {
@@ -792,17 +811,24 @@ __global__ void __launch_bounds__(V_THREADS, 1)
                     const __grid_constant__ CUtensorMap map_code, float *__restrict__ p_out, unsigned int *tile_ctr,
                     fs2d_dom d, FusedGeom g) {
     // the descriptors must be addressed in the kernel-parameter space: take their addresses here
-    jacobi_fused5_body<false>(&map_p, &map_src, &map_code, p_out, tile_ctr, d, g);
+    jacobi_fused5_body<false, false>(&map_p, &map_src, &map_code, p_out, tile_ctr, d, g, nullptr);
+}
+__global__ void __launch_bounds__(V_THREADS, 1)
+    k_jacobi_fused5e(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_src,
+                     const __grid_constant__ CUtensorMap map_code, float *__restrict__ p_out, unsigned int *tile_ctr,
+                     fs2d_dom d, FusedGeom g, float *emit) {
+    jacobi_fused5_body<false, true>(&map_p, &map_src, &map_code, p_out, tile_ctr, d, g, emit);
 }
 __global__ void __launch_bounds__(V_THREADS, 1)
     k_jacobi_fused6(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_src,
                     const __grid_constant__ CUtensorMap map_code, float *__restrict__ p_out, unsigned int *tile_ctr,
                     fs2d_dom d, FusedGeom g) {
-    jacobi_fused5_body<true>(&map_p, &map_src, &map_code, p_out, tile_ctr, d, g);
+    jacobi_fused5_body<true, false>(&map_p, &map_src, &map_code, p_out, tile_ctr, d, g, nullptr);
 }
 
 // (A packed fp32x2 variant -- FADD2/FFMA2, column-pair ownership -- was measured at 915 us/pass vs 795 us for
 // variant 1 at 8192^2, T=8: bank-conflicted scalar j-neighbour loads and pack/unpack moves; removed.)
+int g_tail_emit = 0;       // fs2d_set_tuning(4, v): 1 = end fs2d_jacobi_update with {emitting pass, ONE literal iteration} (experimental)
 int g_fused_variant = 5;   // fs2d_set_tuning(1, v): 1 = one column per thread (64 x 128 tile, smem planes); 3 = register tile +
                            // shuffles (64 x 128 tile); 5 = register tile on a 96 x 128 tile; 6 = 5 with pair barriers (experimental)
 
@@ -854,7 +880,7 @@ bool fused_supported(const float *pa, const float *pb, const float *src, const u
 }
 
 int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t *pcode, const fs2d_dom &d, int T,
-               cudaStream_t s, int skip_from, int skip_n) {
+               cudaStream_t s, int skip_from, int skip_n, bool emit) {
     static int n_sm = 0;
     static bool attr_set = false;
     if (!n_sm) {
@@ -867,6 +893,7 @@ int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t 
         FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
         FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM));
         FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM));
+        FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused5e, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM));
         attr_set = true;
     }
     CUtensorMap mp, ms, mc;
@@ -896,6 +923,14 @@ int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t 
     if (!ctr) FS2D_CUDA_CHECK(cudaMalloc(&ctr, sizeof(unsigned int)));
     FS2D_CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), s));
     ++g_launches;
+    if (emit) {
+        if (g_fused_variant != 5) {
+            set_error("the emitting tail pass exists for fused variant 5 only");
+            return FS2D_E_BADARG;
+        }
+        k_jacobi_fused5e<<<grid, dim3(32, V_WARPS, 1), V_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g, const_cast<float *>(p_in));
+        return FS2D_OK;
+    }
     if (g_fused_variant == 3) k_jacobi_fused3<8><<<grid, dim3(32, FSI / 8, 1), F_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);
     else if (g_fused_variant == 5) k_jacobi_fused5<<<grid, dim3(32, V_WARPS, 1), V_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);
     else if (g_fused_variant == 6) k_jacobi_fused6<<<grid, dim3(32, V_WARPS, 1), V_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);

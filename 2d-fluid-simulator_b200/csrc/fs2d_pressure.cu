@@ -220,6 +220,7 @@ int fs2d_set_tuning(int key, int value) {
     if (key == 1 && (value == 1 || value == 3 || value == 5 || value == 6)) { fs2d::g_fused_variant = value; return FS2D_OK; }
     if (key == 2 && value >= 0 && value <= 2) { fs2d::g_stream = value; return FS2D_OK; }
     if (key == 3 && value >= 0 && value <= 3) { fs2d::g_stream_cfg = value; return FS2D_OK; }
+    if (key == 4 && (value == 0 || value == 1)) { fs2d::g_tail_emit = value; return FS2D_OK; }
     set_error("unknown tuning key %d / value %d", key, value);
     return FS2D_E_BADARG;
 }
@@ -250,10 +251,10 @@ int fs2d_jacobi_sweep(float *pn, const float *pc, const float *src, const uint8_
 // 8192^2 cells (scripts/sweep_bench.py, us): the last two iterations are always literal and the
 // number of buffer flips (= number of entries) must have the parity of n_sweeps so that the two PHYSICAL
 // buffers end up exactly as in the reference.
-static int plan_jacobi(int n_sweeps, int fuse_mask, int *out, int cap) {
+static int plan_jacobi(int n_sweeps, int fuse_mask, int *out, int cap, int tail_literal = 2) {
     static const float pass_cost[13] = {0, 214, 237, 226, 245, 295, 340, 381, 420, 501, 547, 607, 655};   // variant 5
     const float lit_cost = 195.0f;
-    const int n_lit = n_sweeps < 2 ? n_sweeps : 2, n_f = n_sweeps - n_lit;
+    const int n_lit = n_sweeps < tail_literal ? n_sweeps : tail_literal, n_f = n_sweeps - n_lit;
     int n = 0;
     if (n_f > 0 && (fuse_mask & 0x1FFE) && n_f < 4096) {
         // dp[i][par]: cheapest way to do i iterations with an entry count of parity par
@@ -307,12 +308,21 @@ int fs2d_jacobi_update(float *pa, float *pb, const float *src, const uint8_t *pc
     float *cur = pa, *nxt = pb;
     if (d.r1 == d.r0 || !fused_supported(pa, pb, src, pcode, d)) fuse_mask = 0;
     static thread_local int plan[4200];
-    const int n = plan_jacobi(n_sweeps, fuse_mask, plan, 4200);
+    // Experimental tail (fs2d_set_tuning(4, 1), variant 5): {..., fused pass that also emits the BC values of its
+    // penultimate state, ONE literal iteration} instead of {..., two literal iterations}; see jacobi_fused5_body<.., EMIT>.
+    // If the schedule's entry before the last one is itself a literal iteration the old reasoning applies unchanged.
+    int n = -1;
+    bool tail = fs2d::g_tail_emit && fs2d::g_fused_variant == 5 && fuse_mask != 0 && n_sweeps >= 3;
+    if (tail) n = plan_jacobi(n_sweeps, fuse_mask, plan, 4200, 1);
+    if (n < 0) {
+        tail = false;
+        n = plan_jacobi(n_sweeps, fuse_mask, plan, 4200);
+    }
     FS2D_REQUIRE(n >= 0, "iteration count too large");
     for (int k = 0; k < n; ++k) {
         if (plan[k] > 0) {
             // fused pass: plan[k] iterations in shared memory (fs2d_fused.cu)
-            if (int e = fused_pass(cur, nxt, src, pcode, d, plan[k], STREAM)) return e;
+            if (int e = fused_pass(cur, nxt, src, pcode, d, plan[k], STREAM, 0, 0, tail && k == n - 2)) return e;
         } else {
             // literal reference iteration (fs/pressure_updater.py:57-60): in-place sparse BC, then the plain sweep
             launch_p_bc(cur, tgt, src0, src1, kind, scratch, n_bc, STREAM);

@@ -12,3 +12,28 @@ FIELDS=uniform timeout 240 python scripts/kernel_bench.py 2>&1 | tee -a gpurun_o
 echo "== fused Jacobi: variant 6 (pair barriers, experimental) vs variant 5 (default)"
 FS2D_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "pair_barrier" 2>&1 | tail -4
 for v in 5 6; do FUSED_VARIANT=$v timeout 200 python scripts/sweep_bench.py 2>&1 | tee -a gpurun_out/sweep_bench_variants.txt | grep -E "variant|T= ?(4|8|12):"; done
+echo "== emitting tail pass (fs2d_set_tuning(4, 1)): parity, then the update with and without it"
+FS2D_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "emitting_tail" 2>&1 | tail -4
+timeout 200 python - <<'PY' 2>&1 | tee gpurun_out/tail_emit_timing.txt
+import sys; sys.path.insert(0, "2d-fluid-simulator_b200")
+import torch
+from fs import _lib
+from fs.boundary_condition import BoundaryCondition, build_scene
+from fs.double_buffer import DoubleBuffer, Field
+from fs.pressure_updater import JacobiPressureUpdater
+X = Y = 8192
+const, mask = build_scene(2, X, Y)
+bc = BoundaryCondition(const, mask)
+jac = JacobiPressureUpdater(bc, 0.05 / Y, 1.0 / Y, 80)
+p, v = DoubleBuffer((X, Y), 1), Field((X, Y), 2)
+for tail in (0, 1, 0, 1):
+    _lib.load().fs2d_set_tuning(4, tail)
+    for _ in range(2):
+        jac.update(p, v)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        jac.update(p, v)
+    e1.record(); torch.cuda.synchronize()
+    print(f"tail={tail}: {e0.elapsed_time(e1) / 5:.3f} ms per 80-iteration update", flush=True)
+PY

@@ -827,6 +827,18 @@ def test_pair_barrier_variant_equals_literal_iterations(env, num, X, Y):
     test_fused_pass_equals_literal_iterations(env, num, X, Y, 6)
 
 
-for _t in (test_nonadv_fused_equals_two_kernels, test_nonadv_fused_random_masks, test_fused_non_advection_trajectory_vs_oracle,
+@pytest.mark.parametrize("num,X,Y,n_iter", [(2, 256, 128, 80), (5, 384, 192, 21), (1, 128, 64, 7), (3, 320, 160, 13), (2, 96, 48, 3),
+                                            (4, 200, 96, 4), (1, 288, 352, 10)])
+def test_emitting_tail_pass_equals_literal_update(env, num, X, Y, n_iter):
+    """fs2d_set_tuning(4, 1): the update ends with {fused pass emitting the BC values of its penultimate state, ONE literal
+    iteration}; both physical buffers -- wall-BC cells included -- must still equal n literal iterations."""
+    env.fs2d_set_tuning(4, 1)
+    try:
+        test_fused_update_equals_literal_update(env, num, X, Y, n_iter)
+    finally:
+        env.fs2d_set_tuning(4, 0)
+
+
+for _t in (test_emitting_tail_pass_equals_literal_update, test_nonadv_fused_equals_two_kernels, test_nonadv_fused_random_masks, test_fused_non_advection_trajectory_vs_oracle,
            test_pair_barrier_variant_equals_literal_iterations):
     globals()[_t.__name__] = experimental(_t)

@@ -138,6 +138,24 @@ def test_emu_pair_barrier_variant_on_a_wide_open_grid(env):
     G.test_fused_pass_equals_literal_iterations(env, 1, 300, 480, 6, t_list=(2, 3, 5, 8, 12), need=5)
 
 
+@pytest.mark.parametrize("num,X,Y,n_iter", [(5, 384, 192, 21), (1, 128, 64, 7), (3, 320, 160, 13), (2, 96, 48, 3), (4, 200, 96, 4),
+                                            (1, 288, 352, 10)])
+def test_emu_emitting_tail_pass_equals_literal_update(env, num, X, Y, n_iter):
+    G.test_emitting_tail_pass_equals_literal_update.__wrapped__(env, num, X, Y, n_iter) if hasattr(
+        G.test_emitting_tail_pass_equals_literal_update, "__wrapped__") else G.test_emitting_tail_pass_equals_literal_update(env, num, X, Y, n_iter)
+
+
+def test_emu_emitting_tail_trajectory_vs_oracle(env):
+    """whole trajectories with the experimental tail: every physical buffer (p.next's wall cells included) vs the oracle"""
+    env.fs2d_set_tuning(4, 1)
+    try:
+        for seed in (0, 3):
+            G.test_random_mask_trajectory_vs_oracle(env, seed)
+        G.test_config_trajectory_vs_oracle(env, [c for c in G.CONFIGS if c[0] == "cfg1_as_given"][0])
+    finally:
+        env.fs2d_set_tuning(4, 0)
+
+
 # ---- adversarial schedules ---------------------------------------------------------------------------------------------------
 @pytest.mark.skipif(os.environ.get("FS2D_EMU_SCHED") is not None, reason="already inside an adversarial-schedule run")
 @pytest.mark.parametrize("seed", [1, 2])
