@@ -35,6 +35,7 @@ CASES = [
     (2, 1024, 512, "cip", 5.0, dict(pressure="jacobi", n_iter=40), 2, 9),      # fused passes of 8 across the strip edge
     (5, 384, 192, "cip", 5.0, dict(pressure="jacobi", n_iter=21), 3, 6),       # odd count, passes of <= 5
     (3, 640, 320, "upwind", None, dict(pressure="jacobi", n_iter=30), 2, 9),
+    (2, 640, 64, "cip", 5.0, dict(pressure="jacobi", n_iter=13), 2, 9),       # tall narrow strips: fused passes split into interior + edge launches
     ("rand1", 192, 64, "cip", 5.0, dict(pressure="jacobi", n_iter=11), 2, 5),  # thin walls on / next to the strip edges
     ("rand3", 192, 64, "kk", None, dict(pressure="jacobi", n_iter=14), 2, 6),
 ]
@@ -69,17 +70,32 @@ def buffers(s) -> dict:
 
 def main() -> None:
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    if os.environ.get("FS2D_FAKE_LIB") == "1":
-        # CPU dry run of THIS script's logic (gloo + tests/fake_fs2d.py, the oracle-backed stand-in for libfs2d.so):
-        # checks the host layer and the script, says nothing about the CUDA kernels.  Small cases only.
-        sys.path[:0] = [str(REPO), str(REPO / "tests")]
-        from fake_fs2d import FakeFs2d
+    if os.environ.get("FS2D_FAKE_LIB") in ("1", "emu"):
+        # CPU dry run of THIS script (gloo).  "1": tests/fake_fs2d.py, the oracle-backed stand-in for libfs2d.so (host layer
+        # and script logic only).  "emu": the kernel SOURCES compiled against the CUDA emulation of tests/cuda_emu -- the real
+        # kernels' row-window / clamp-window handling on strips, split fused passes, 1-2 row edge windows.  Small cases only.
+        sys.path[:0] = [str(REPO), str(REPO / "tests"), str(REPO / "tests" / "cuda_emu")]
         from fs import _lib
 
-        FakeFs2d(_lib.load()).install_plain()
+        if os.environ["FS2D_FAKE_LIB"] == "1":
+            from fake_fs2d import FakeFs2d
+
+            FakeFs2d(_lib.load()).install_plain()
+        else:
+            import ctypes
+
+            import build_emu
+
+            emu = ctypes.CDLL(str(build_emu.LIB))      # built by the test that launches this script
+            for name, (res, args) in _lib._SIGNATURES.items():
+                fn = getattr(emu, name)
+                fn.restype, fn.argtypes = res, args
+            _lib._lib = emu
+            _lib.ptr = lambda t: None if t is None else t.data_ptr()
+            _lib.stream = lambda: 0
         dev = torch.device("cpu")
         dist.init_process_group("gloo")
-        cases = [c for c in CASES if c[1] * c[2] <= 160 * 80]
+        cases = [c for c in CASES if c[1] * c[2] <= 640 * 64]
     else:
         torch.cuda.set_device(local)
         dev = torch.device("cuda", local)
