@@ -158,8 +158,17 @@ def jacobi_update_distributed(jac, p: DoubleBuffer, v_current: Field) -> None:
     hx = exchanger_for(bc)
     plan = jac.plan(p)
     reach = max([t for t in plan if t > 0], default=0)
-    hx.exchange(v_current, min(bc.halo, reach + 1))
-    src = jac._source(v_current, dom=_extended(bc, reach))        # source terms also on the halo rows a pass reads
+    # source terms also on the halo rows a pass reads; the rows that need no halo row of v run during the exchange
+    d, ext = bc.dom, _extended(bc, reach)
+    if d.r1 - d.r0 >= 16:
+        reqs = hx.start(v_current, min(bc.halo, reach + 1))
+        jac._source(v_current, dom=d.replace(r0=d.r0 + 1, r1=d.r1 - 1))
+        hx.finish(reqs)
+        jac._source(v_current, dom=ext.replace(r1=d.r0 + 1))
+        src = jac._source(v_current, dom=ext.replace(r0=d.r1 - 1))
+    else:
+        hx.exchange(v_current, min(bc.halo, reach + 1))
+        src = jac._source(v_current, dom=ext)
     for t in plan:
         if t > 0:
             # Overlap: the pass reads the fresh halo rows only in its first and last TILE ROW, so the tile rows in
