@@ -3,7 +3,7 @@
     python scripts/summarize_profiles.py r01_v7 [gpurun_out/step_full.ncu-rep]
 
 profiles/<tag>_launches_summary.csv   per-kernel launch counts / times / SHARE of the step (ncu launch list of
-                                      `python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline`)
+                                      `python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-extra-config`)
 profiles/<tag>_kernels_ncu_full.csv   one row per distinct kernel from the `ncu --set full` capture of the same command
 profiles/dominant_kernel_traffic.json DRAM bytes per launch of the dominant kernel (read by bench.py -> roofline.traffic)
 """
@@ -22,7 +22,7 @@ for r in data:
     a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += float(r[mi].replace(",", ""))
 tot = sum(a[1] for a in agg.values())
 out = [f"# {tag}: ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 200, python bench.py --steps 1 --warmup 1 "
-       "--no-e2e --no-cpu-baseline (8192x8192 cells/GPU, 80 Jacobi sweeps/step); ns; cold-cache serialised replays: compare SHARES",
+       "--no-e2e --no-cpu-baseline --no-extra-config (8192x8192 cells/GPU, 80 Jacobi sweeps/step); ns; cold-cache serialised replays: compare SHARES",
        "kernel,launches,total_ns,avg_ns,share"]
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f"{k},{n},{t:.0f},{t / n:.0f},{t / tot:.4f}")
@@ -45,7 +45,7 @@ if rep:
             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
     idx = [hd.index(k) for k in keep if k in hd]
     lines = [f"# {tag}: ncu --set full --clock-control none --import-source on --kernel-id ::regex:k_:3 (3rd invocation of each kernel), "
-             "python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline; units row, then one row per kernel",
+             "python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-extra-config; units row, then one row per kernel",
              ",".join(hd[i] for i in idx)]
     for r in rr[1:]:
         lines.append(",".join('"' + r[i] + '"' if "," in r[i] else r[i] for i in idx))
