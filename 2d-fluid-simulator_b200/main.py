@@ -1,7 +1,7 @@
 """Headless driver with the reference's command line (/root/reference/main.py:10-51).
 
 Same flags and defaults (-bc, -re, -res, -dt, -vis, -vc, -scheme, -no_dye); the GGUI window, key
-handling and PNG screenshots are out of scope (DESIGN.md §7), so instead of an event loop this runs
+handling and PNG screenshots are out of scope (DESIGN.md §9), so instead of an event loop this runs
 `--steps` time steps on the GPU and can dump `{"v", "p"[, "dye"]}` to `output/step_%06d.npz`
 (the `d`-key format, main.py:129-132).  Extras: `--jacobi N` selects the Jacobi updater used by the
 BASELINE configs (the reference hard-codes RB-SOR 1.3 x2, fs/fluid_simulator.py:76-78).
