@@ -194,7 +194,8 @@ def test_emu_synchronisation_under_adversarial_warp_schedules(seed):
     an early TMA refill pass the round-robin schedule but fail here."""
     import subprocess
 
-    sel = "352 or pair_barrier or stream_kernel_shapes or (nonadv_fused_equals and 256) or random_obstacles"
+    sel = ("352 or pair_barrier or stream_kernel_shapes or (nonadv_fused_equals and 256) or random_obstacles or "
+           "(emitting_tail_pass and 128-64) or fused_non_advection_trajectory")
     out = subprocess.run([sys.executable, "-m", "pytest", __file__, "-x", "-q", "-p", "no:cacheprovider", "-k", sel],
                          capture_output=True, text=True, timeout=1200, env=dict(os.environ, FS2D_EMU_SCHED=str(seed)))
     assert out.returncode == 0 and " passed" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
