@@ -149,6 +149,11 @@ class FakeFs2d:
         self._windowed(d, [self.a(fxn, d, 2), self.a(fyn, d, 2)], lambda w, ox, oy: orc.lib().orc_cip_nonadv_grad(
             _p(ox), _p(oy), _p(XC[w]), _p(YC[w]), _p(FC[w]), _p(FN[w]), _p(M[w]), _i(ox.shape[0]), _i(d.Y), _f(two_dx)))
 
+    def fs2d_cip_nonadv_fused(self, fn, fxn, fyn, fc, fxc, fyc, pc, mask, d, dt, dx, re, two_dx, stream) -> None:
+        """by definition the two reference kernels one after the other (include/fs2d.h)"""
+        self.fs2d_cip_nonadv(fn, fc, pc, mask, d, dt, dx, re, stream)
+        self.fs2d_cip_nonadv_grad(fxn, fyn, fxc, fyc, fc, fn, mask, d, two_dx, stream)
+
     def fs2d_cip_advect(self, fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, dx2, dx3, stream) -> None:
         FC, XC, YC, V, M = self.a(fc, d, 2), self.a(fxc, d, 2), self.a(fyc, d, 2), self.a(v, d, 2), self.a(mask, d)
         self._windowed(d, [self.a(fn, d, 2), self.a(fxn, d, 2), self.a(fyn, d, 2)], lambda w, o, ox, oy: orc.lib().orc_cip_advect(
