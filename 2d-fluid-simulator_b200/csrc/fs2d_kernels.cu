@@ -624,6 +624,11 @@ int fs2d_vort_apply(float *vn, float *w, float *wabs, const float *vc, const uin
             return FS2D_OK;
         }
     }
+    if (g_vort_march) {   // experimental marching kernel (fs2d_vort_march.cu), off by default
+        if (int e = vort_march(vn, w, wabs, vc, mask, d, dx, dtw, STREAM)) return e;
+        FS2D_LAUNCH_CHECK();
+        return FS2D_OK;
+    }
 #define VP(P2) ++g_launches, k_vort_apply<P2><<<dense_grid_nu(d, VA_ROWS / TY), dense_block(), 0, STREAM>>>(vn, w, wabs, vc, mask, d, DivC<P2>(dx), dtw)
     DISPATCH_P2(is_pow2(dx), VP(true), VP(false));
 #undef VP

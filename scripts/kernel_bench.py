@@ -33,6 +33,8 @@ cases = {
     "vort_calc (17 B)": (lambda: vc._calc_vorticity(s.v.current), 17),
     "vort_add (25 B)": (lambda: vc._add_vorticity(s.v.next, s.v.current), 25),
     "vort_apply fused (25 B)": (lambda: vc._apply_fused(s.v.next, s.v.current), 25),
+    "vort_apply MARCHING, EXPERIMENTAL (25 B)": (lambda: (_lib.load().fs2d_set_tuning(5, 1), vc._apply_fused(s.v.next, s.v.current),
+                                                          _lib.load().fs2d_set_tuning(5, 0)), 25),
     "p_source (16 B)": (lambda: s.pressure_updater._source(s.v.current), 16),
     "limit (8 B)": (lambda: limit_field(s.v.current, VELOCITY_LIMIT, bc=bc), 8),
 }

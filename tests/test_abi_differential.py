@@ -127,6 +127,12 @@ def test_dense_entry_points_against_the_window_model(libs, seed):
           lambda q: (q["vn"], q["vc"], q["w"], q["wabs"], q["mask"], d, dx, dt * 5.0, None))
     c.run("fs2d_vort_apply", dict(vn=o2a, w=o1a, wabs=o1b, vc=v, mask=m), ("vn", "w", "wabs"),
           lambda q: (q["vn"], q["w"], q["wabs"], q["vc"], q["mask"], d, dx, dt * 5.0, None))
+    c.emu.fs2d_set_tuning(5, 1)     # the experimental marching kernel behind the same entry point
+    try:
+        c.run("fs2d_vort_apply", dict(vn=o2a, w=o1a, wabs=o1b, vc=v, mask=m), ("vn", "w", "wabs"),
+              lambda q: (q["vn"], q["w"], q["wabs"], q["vc"], q["mask"], d, dx, dt * 5.0, None))
+    finally:
+        c.emu.fs2d_set_tuning(5, 0)
     c.run("fs2d_limit", dict(v=v * np.float32(14.0)), ("v",), lambda q: (q["v"], d, 10.0, None))
     c.run("fs2d_clamp", dict(f=c.f(X, Y, 3, scale=2.0)), ("f",), lambda q: (q["f"], d, 3, 0.0, 1.0, None))
     c.run("fs2d_dye_nonadv", dict(dn=o3a, dc=dye, mask=m), ("dn",), lambda q: (q["dn"], q["dc"], q["mask"], d, dt, dx, re, None))

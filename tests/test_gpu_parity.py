@@ -839,6 +839,24 @@ def test_emitting_tail_pass_equals_literal_update(env, num, X, Y, n_iter):
         env.fs2d_set_tuning(4, 0)
 
 
-for _t in (test_emitting_tail_pass_equals_literal_update, test_nonadv_fused_equals_two_kernels, test_nonadv_fused_random_masks, test_fused_non_advection_trajectory_vs_oracle,
+def test_marching_vorticity_kernel(env, kernels_golden, masks_small):
+    """fs2d_set_tuning(5, 1): the marching version of VorticityConfinement.apply() behind fs2d_vort_apply"""
+    env.fs2d_set_tuning(5, 1)
+    try:
+        for num in BCS:
+            test_each_kernel_matches_reference_fixture(env, num, kernels_golden, masks_small)
+        for name in TRAJ:
+            if "novc" not in name:
+                test_trajectory_matches_reference_fixture(env, name, masks_small)
+        for seed in range(6):
+            test_random_mask_trajectory_vs_oracle(env, seed)
+        for cfg in CONFIGS:
+            if cfg[6] is not None:
+                test_config_trajectory_vs_oracle(env, cfg)
+    finally:
+        env.fs2d_set_tuning(5, 0)
+
+
+for _t in (test_marching_vorticity_kernel, test_emitting_tail_pass_equals_literal_update, test_nonadv_fused_equals_two_kernels, test_nonadv_fused_random_masks, test_fused_non_advection_trajectory_vs_oracle,
            test_pair_barrier_variant_equals_literal_iterations):
     globals()[_t.__name__] = experimental(_t)

@@ -183,6 +183,23 @@ def test_emu_fused_pass_fuzz(env, seed):
             env.fs2d_set_tuning(1, 5)
 
 
+def test_emu_marching_vorticity_kernel(env, kernels_golden, masks_small):
+    """fs2d_set_tuning(5, 1): the experimental marching version of VorticityConfinement.apply() behind the same entry point --
+    reference fixtures (all scenes), trajectories with confinement, random masks, IEEE special cases"""
+    env.fs2d_set_tuning(5, 1)
+    try:
+        for num in G.BCS:
+            G.test_each_kernel_matches_reference_fixture(env, num, kernels_golden, masks_small)
+        for name in G.TRAJ:
+            if "novc" not in name:
+                G.test_trajectory_matches_reference_fixture(env, name, masks_small)
+        for seed in (1, 4):
+            G.test_random_mask_trajectory_vs_oracle(env, seed)
+        G.test_config_trajectory_vs_oracle(env, [c for c in G.CONFIGS if c[0] == "kk_r100"][0])
+    finally:
+        env.fs2d_set_tuning(5, 0)
+
+
 # ---- adversarial schedules ---------------------------------------------------------------------------------------------------
 @pytest.mark.skipif(os.environ.get("FS2D_EMU_SCHED") is not None, reason="already inside an adversarial-schedule run")
 @pytest.mark.parametrize("seed", [1])
