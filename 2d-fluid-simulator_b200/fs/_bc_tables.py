@@ -245,7 +245,8 @@ def fused_reach_ok(code: torch.Tensor, T: int, tile_rows: int, tile_cols: int, h
     weights = {"up": lambda o: -o[0], "down": lambda o: o[0], "left": lambda o: -o[1], "right": lambda o: o[1]}
     room = {"up": lr, "down": (tile_rows - 1) - lr, "left": lc, "right": (tile_cols - 1) - lc}
     if fresh_below is not None:
-        room["down"] = torch.minimum(room["down"], ((row1 - 1 - ii) + fresh_below).clamp(min=0).to(torch.int16)[:, None])
+        fresh = ((row1 - 1 - ii) + fresh_below).clamp(min=0, max=32767)      # int16 like the other bounds; only the small values matter
+        room["down"] = torch.minimum(room["down"], fresh.to(torch.int16)[:, None])
     for name, w in weights.items():
         R = torch.zeros((X, Y), dtype=torch.int16, device=dev)
         for _ in range(T):
