@@ -820,6 +820,12 @@ __global__ void __launch_bounds__(V_THREADS, 1)
     jacobi_fused5_body<false, true>(&map_p, &map_src, &map_code, p_out, tile_ctr, d, g, emit);
 }
 __global__ void __launch_bounds__(V_THREADS, 1)
+    k_jacobi_fused6e(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_src,
+                     const __grid_constant__ CUtensorMap map_code, float *__restrict__ p_out, unsigned int *tile_ctr,
+                     fs2d_dom d, FusedGeom g, float *emit) {
+    jacobi_fused5_body<true, true>(&map_p, &map_src, &map_code, p_out, tile_ctr, d, g, emit);
+}
+__global__ void __launch_bounds__(V_THREADS, 1)
     k_jacobi_fused6(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_src,
                     const __grid_constant__ CUtensorMap map_code, float *__restrict__ p_out, unsigned int *tile_ctr,
                     fs2d_dom d, FusedGeom g) {
@@ -894,6 +900,7 @@ int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t 
         FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM));
         FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM));
         FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused5e, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM));
+        FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused6e, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM));
         attr_set = true;
     }
     CUtensorMap mp, ms, mc;
@@ -924,11 +931,12 @@ int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t 
     FS2D_CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), s));
     ++g_launches;
     if (emit) {
-        if (g_fused_variant != 5) {
-            set_error("the emitting tail pass exists for fused variant 5 only");
+        if (g_fused_variant < 5) {
+            set_error("the emitting tail pass exists for the fused variants 5 and 6 only");
             return FS2D_E_BADARG;
         }
-        k_jacobi_fused5e<<<grid, dim3(32, V_WARPS, 1), V_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g, const_cast<float *>(p_in));
+        if (g_fused_variant == 6) k_jacobi_fused6e<<<grid, dim3(32, V_WARPS, 1), V_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g, const_cast<float *>(p_in));
+        else k_jacobi_fused5e<<<grid, dim3(32, V_WARPS, 1), V_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g, const_cast<float *>(p_in));
         return FS2D_OK;
     }
     if (g_fused_variant == 3) k_jacobi_fused3<8><<<grid, dim3(32, FSI / 8, 1), F_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);

@@ -313,7 +313,7 @@ int fs2d_jacobi_update(float *pa, float *pb, const float *src, const uint8_t *pc
     // penultimate state, ONE literal iteration} instead of {..., two literal iterations}; see jacobi_fused5_body<.., EMIT>.
     // If the schedule's entry before the last one is itself a literal iteration the old reasoning applies unchanged.
     int n = -1;
-    bool tail = fs2d::g_tail_emit && fs2d::g_fused_variant == 5 && fuse_mask != 0 && n_sweeps >= 3;
+    bool tail = fs2d::g_tail_emit && fs2d::g_fused_variant >= 5 && fuse_mask != 0 && n_sweeps >= 3;
     if (tail) n = plan_jacobi(n_sweeps, fuse_mask, plan, 4200, 1);
     if (n < 0) {
         tail = false;

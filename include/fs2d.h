@@ -79,7 +79,7 @@ unsigned long long fs2d_launch_count(void);
  *         non-advection phase and the vorticity confinement};
  * key 3 = streaming-kernel shape {stages x CTAs/SM x threads}: {0: 3x2x256, 1: 2x3x256 (default), 2: 3x2x512, 3: 2x2x512}.
  * key 4 = EXPERIMENTAL tail of fs2d_jacobi_update {0: two literal iterations (default); 1: the last fused pass also emits the
- *         BC values of its penultimate state, so ONE literal iteration ends the update (variant 5 only)}.
+ *         BC values of its penultimate state, so ONE literal iteration ends the update (variants 5 and 6)}.
  * key 5 = EXPERIMENTAL fs2d_vort_apply kernel {0: shared-memory tile (default); 1: marching kernel, one curl evaluation per cell,
  *         j-neighbours by warp shuffles, no shared memory}.
  * Unknown keys / values return FS2D_E_BADARG and change nothing. */

@@ -144,6 +144,15 @@ def test_emu_emitting_tail_pass_equals_literal_update(env, num, X, Y, n_iter):
         G.test_emitting_tail_pass_equals_literal_update, "__wrapped__") else G.test_emitting_tail_pass_equals_literal_update(env, num, X, Y, n_iter)
 
 
+def test_emu_emitting_tail_with_the_pair_barrier_variant(env):
+    env.fs2d_set_tuning(1, 6)
+    try:
+        for num, X, Y, n_iter in ((1, 128, 64, 7), (1, 288, 352, 6)):
+            G.test_emitting_tail_pass_equals_literal_update(env, num, X, Y, n_iter)
+    finally:
+        env.fs2d_set_tuning(1, 5)
+
+
 def test_emu_emitting_tail_trajectory_vs_oracle(env):
     """whole trajectories with the experimental tail: every physical buffer (p.next's wall cells included) vs the oracle"""
     env.fs2d_set_tuning(4, 1)
