@@ -37,3 +37,7 @@ for tail in (0, 1, 0, 1):
     e1.record(); torch.cuda.synchronize()
     print(f"tail={tail}: {e0.elapsed_time(e1) / 5:.3f} ms per 80-iteration update", flush=True)
 PY
+echo "== compute-sanitizer on the experimental kernels"
+for tool in memcheck racecheck synccheck; do
+  echo "-- $tool"; FS2D_EXPERIMENTAL=1 timeout 280 compute-sanitizer --tool $tool --print-limit 5 python scripts/sanitize_small.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|^ok|=========.*(Error|hazard|Invalid)" | head -8
+done

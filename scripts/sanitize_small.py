@@ -23,5 +23,16 @@ for num, X, Y in ((2, 256, 128), (3, 200, 176)):
         for stream in (2, 0):
             lib.fs2d_set_tuning(2, stream)
             s.update()
+    # the experimental kernels (off by default): pair-barrier Jacobi variant, emitting tail, marching vorticity kernel,
+    # fused non-advection phase
+    import os
+    if os.environ.get("FS2D_EXPERIMENTAL") == "1":
+        lib.fs2d_set_tuning(2, 1)
+        for variant, tail, march, fused in ((6, 0, 0, False), (5, 1, 1, True), (6, 1, 1, True)):
+            lib.fs2d_set_tuning(1, variant); lib.fs2d_set_tuning(4, tail); lib.fs2d_set_tuning(5, march)
+            s.fused_non_advection = fused
+            s.update(); s.update()
+        lib.fs2d_set_tuning(1, 5); lib.fs2d_set_tuning(4, 0); lib.fs2d_set_tuning(5, 0)
+        s.fused_non_advection = False
     torch.cuda.synchronize()
     print("ok", num, X, Y, float(s.p.current.tensor.abs().sum()))
