@@ -568,6 +568,35 @@ __device__ __forceinline__ float f_post_p(const float *pl, const uint8_t *code, 
     return mode == 0 ? va : (mode == 1 ? (va + vb) / 2.0f : 0.0f);
 }
 
+// f_post_p split into its index part and its value part.  FASTSLOW tiles resolve, ONCE per tile, which plane cells
+// the post-BC value of each neighbour of a slow cell reads (two 14-bit plane offsets + a 2-bit mode in one word); the
+// fix-up of every iteration is then four table look-ups instead of four walks through the pcode switch.
+__device__ __forceinline__ uint32_t f_resolve_p(const uint8_t *code, int cpitch, int r, int c, int rlo, int rhi, int clo, int chi) {
+    const int rm = max(r - 1, rlo), rp = min(r + 1, rhi), cm = max(c - 1, clo), cp = min(c + 1, chi);
+    int a = r * FSJ + c, b = a, mode = 0;  // mode 0: value of cell a; 1: (a + b) / 2; 2: zero
+    switch (code[r * cpitch + c] & 15) {
+        case FS2D_PC_W_IM: a = rm * FSJ + c; break;
+        case FS2D_PC_W_IP: a = rp * FSJ + c; break;
+        case FS2D_PC_W_JM: a = r * FSJ + cm; break;
+        case FS2D_PC_W_JP: a = r * FSJ + cp; break;
+        case FS2D_PC_W_IM_JP: a = rm * FSJ + c; b = r * FSJ + cp; mode = 1; break;
+        case FS2D_PC_W_IP_JP: a = rp * FSJ + c; b = r * FSJ + cp; mode = 1; break;
+        case FS2D_PC_W_IM_JM: a = rm * FSJ + c; b = r * FSJ + cm; mode = 1; break;
+        case FS2D_PC_W_IP_JM: a = rp * FSJ + c; b = r * FSJ + cm; mode = 1; break;
+        case FS2D_PC_INFLOW: a = rp * FSJ + c; break;
+        case FS2D_PC_OUTFLOW: mode = 2; break;
+        default: break;  // FLUID / W_NONE: the stored value
+    }
+    return (uint32_t)a | ((uint32_t)b << 14) | ((uint32_t)mode << 28);
+}
+__device__ __forceinline__ float f_resolved_value(const float *pl, uint32_t x) {
+    const float va = pl[x & 0x3fffu], vb = pl[(x >> 14) & 0x3fffu];
+    const uint32_t mode = x >> 28;
+    return mode == 0u ? va : (mode == 1u ? (va + vb) / 2.0f : 0.0f);   // the expression of f_post_p
+}
+constexpr int FS_CAP = VN / 8;   // slow cells per tile the resolved table has room for (behind the slow-cell list): 1536
+static_assert(VN <= (1 << 14), "plane offsets must fit 14 bits");
+
 // bar.sync on a named barrier shared by `count` threads (ids 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -587,7 +616,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
 // SURVEY T1), so a pass of T iterations ending at iteration n - 1, followed by ONE literal iteration, reproduces both
 // physical buffers -- instead of ending every update with two literal iterations.  A wall-BC cell has a fluid
 // neighbour, which is a slow cell of the same loaded tile, so only slow tiles emit.
-template <bool PAIR, bool EMIT>
+//
+// FASTSLOW (EXPERIMENTAL, variants 7 / 8): slow tiles with at most FS_CAP slow cells use the resolved table above.
+template <bool PAIR, bool EMIT, bool FASTSLOW>
 __device__ __forceinline__ void jacobi_fused5_body(const CUtensorMap *mp, const CUtensorMap *ms, const CUtensorMap *mc,
                                                    float *__restrict__ p_out, unsigned int *tile_ctr, const fs2d_dom &d,
                                                    const FusedGeom &g, float *emit) {
@@ -729,6 +760,19 @@ __device__ __forceinline__ void jacobi_fused5_body(const CUtensorMap *mp, const 
             __syncthreads();
             const int ns = n_slow;
             const uint8_t *code = stg_code + coff;   // tile pcode, row pitch FCW (the staging buffer stays intact)
+            // resolved neighbour table: 4 words per slow cell, behind the list (VN uint16 = VN / 2 floats); each thread reads
+            // back only the entries it wrote (same e -> thread mapping), so no barrier is needed
+            uint32_t *res = reinterpret_cast<uint32_t *>(sm + VOFF_LIST + VN / 2);
+            const bool fast = FASTSLOW && ns <= FS_CAP;   // block-uniform
+            if (fast) {
+                for (int e = tid; e < ns; e += V_THREADS) {
+                    const int o = slow_list[e], r = o / FSJ, cc = o % FSJ;
+                    res[4 * e + 0] = f_resolve_p(code, FCW, min(r + 1, rhi), cc, rlo, rhi, clo, chi);
+                    res[4 * e + 1] = f_resolve_p(code, FCW, max(r - 1, rlo), cc, rlo, rhi, clo, chi);
+                    res[4 * e + 2] = f_resolve_p(code, FCW, r, min(cc + 1, chi), rlo, rhi, clo, chi);
+                    res[4 * e + 3] = f_resolve_p(code, FCW, r, max(cc - 1, clo), rlo, rhi, clo, chi);
+                }
+            }
             int cur = VOFF_P0, nxt = VOFF_SRC;
             for (int s = 0; s < g.T; ++s) {
                 if (EMIT && s == g.T - 1) {
@@ -744,13 +788,24 @@ __device__ __forceinline__ void jacobi_fused5_body(const CUtensorMap *mp, const 
                 }
                 // all threads share the slow cells and leave, in plane `nxt`, the SUM of the four post-BC neighbour
                 // values (the reference's order) for the owning thread to pick up
-                for (int e = tid; e < ns; e += V_THREADS) {
-                    const int o = slow_list[e], r = o / FSJ, cc = o % FSJ;
-                    float sum = f_post_p(sm + cur, code, FCW, min(r + 1, rhi), cc, rlo, rhi, clo, chi);
-                    sum = sum + f_post_p(sm + cur, code, FCW, max(r - 1, rlo), cc, rlo, rhi, clo, chi);
-                    sum = sum + f_post_p(sm + cur, code, FCW, r, min(cc + 1, chi), rlo, rhi, clo, chi);
-                    sum = sum + f_post_p(sm + cur, code, FCW, r, max(cc - 1, clo), rlo, rhi, clo, chi);
-                    sm[nxt + o] = sum;
+                if (fast) {
+                    for (int e = tid; e < ns; e += V_THREADS) {
+                        const uint4 q = *reinterpret_cast<const uint4 *>(res + 4 * e);
+                        float sum = f_resolved_value(sm + cur, q.x);
+                        sum = sum + f_resolved_value(sm + cur, q.y);
+                        sum = sum + f_resolved_value(sm + cur, q.z);
+                        sum = sum + f_resolved_value(sm + cur, q.w);
+                        sm[nxt + slow_list[e]] = sum;
+                    }
+                } else {
+                    for (int e = tid; e < ns; e += V_THREADS) {
+                        const int o = slow_list[e], r = o / FSJ, cc = o % FSJ;
+                        float sum = f_post_p(sm + cur, code, FCW, min(r + 1, rhi), cc, rlo, rhi, clo, chi);
+                        sum = sum + f_post_p(sm + cur, code, FCW, max(r - 1, rlo), cc, rlo, rhi, clo, chi);
+                        sum = sum + f_post_p(sm + cur, code, FCW, r, min(cc + 1, chi), rlo, rhi, clo, chi);
+                        sum = sum + f_post_p(sm + cur, code, FCW, r, max(cc - 1, clo), rlo, rhi, clo, chi);
+                        sm[nxt + o] = sum;
+                    }
                 }
                 __syncthreads();
                 const float4 upv = lds4(sm + cur + o_up), dnv = lds4(sm + cur + o_dn);
@@ -811,26 +866,40 @@ __global__ void __launch_bounds__(V_THREADS, 1)
                     const __grid_constant__ CUtensorMap map_code, float *__restrict__ p_out, unsigned int *tile_ctr,
                     fs2d_dom d, FusedGeom g) {
     // the descriptors must be addressed in the kernel-parameter space: take their addresses here
-    jacobi_fused5_body<false, false>(&map_p, &map_src, &map_code, p_out, tile_ctr, d, g, nullptr);
+    jacobi_fused5_body<false, false, false>(&map_p, &map_src, &map_code, p_out, tile_ctr, d, g, nullptr);
 }
 __global__ void __launch_bounds__(V_THREADS, 1)
     k_jacobi_fused5e(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_src,
                      const __grid_constant__ CUtensorMap map_code, float *__restrict__ p_out, unsigned int *tile_ctr,
                      fs2d_dom d, FusedGeom g, float *emit) {
-    jacobi_fused5_body<false, true>(&map_p, &map_src, &map_code, p_out, tile_ctr, d, g, emit);
+    jacobi_fused5_body<false, true, false>(&map_p, &map_src, &map_code, p_out, tile_ctr, d, g, emit);
 }
 __global__ void __launch_bounds__(V_THREADS, 1)
     k_jacobi_fused6e(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_src,
                      const __grid_constant__ CUtensorMap map_code, float *__restrict__ p_out, unsigned int *tile_ctr,
                      fs2d_dom d, FusedGeom g, float *emit) {
-    jacobi_fused5_body<true, true>(&map_p, &map_src, &map_code, p_out, tile_ctr, d, g, emit);
+    jacobi_fused5_body<true, true, false>(&map_p, &map_src, &map_code, p_out, tile_ctr, d, g, emit);
 }
 __global__ void __launch_bounds__(V_THREADS, 1)
     k_jacobi_fused6(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_src,
                     const __grid_constant__ CUtensorMap map_code, float *__restrict__ p_out, unsigned int *tile_ctr,
                     fs2d_dom d, FusedGeom g) {
-    jacobi_fused5_body<true, false>(&map_p, &map_src, &map_code, p_out, tile_ctr, d, g, nullptr);
+    jacobi_fused5_body<true, false, false>(&map_p, &map_src, &map_code, p_out, tile_ctr, d, g, nullptr);
 }
+
+// variants 7 / 8 (EXPERIMENTAL): variants 5 / 6 with the resolved slow-cell table; *e: with the emitting tail
+#define FS2D_FUSED_KERNEL(NAME, PAIR, EMIT)                                                                                     \
+    __global__ void __launch_bounds__(V_THREADS, 1)                                                                             \
+        NAME(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_src,                            \
+             const __grid_constant__ CUtensorMap map_code, float *__restrict__ p_out, unsigned int *tile_ctr, fs2d_dom d,       \
+             FusedGeom g, float *emit) {                                                                                        \
+        jacobi_fused5_body<PAIR, EMIT, true>(&map_p, &map_src, &map_code, p_out, tile_ctr, d, g, emit);                         \
+    }
+FS2D_FUSED_KERNEL(k_jacobi_fused7, false, false)
+FS2D_FUSED_KERNEL(k_jacobi_fused7e, false, true)
+FS2D_FUSED_KERNEL(k_jacobi_fused8, true, false)
+FS2D_FUSED_KERNEL(k_jacobi_fused8e, true, true)
+#undef FS2D_FUSED_KERNEL
 
 // (A packed fp32x2 variant -- FADD2/FFMA2, column-pair ownership -- was measured at 915 us/pass vs 795 us for
 // variant 1 at 8192^2, T=8: bank-conflicted scalar j-neighbour loads and pack/unpack moves; removed.)
@@ -901,6 +970,10 @@ int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t 
         FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM));
         FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused5e, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM));
         FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused6e, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM));
+        FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM));
+        FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused7e, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM));
+        FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM));
+        FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_jacobi_fused8e, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM));
         attr_set = true;
     }
     CUtensorMap mp, ms, mc;
@@ -935,13 +1008,19 @@ int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t 
             set_error("the emitting tail pass exists for the fused variants 5 and 6 only");
             return FS2D_E_BADARG;
         }
-        if (g_fused_variant == 6) k_jacobi_fused6e<<<grid, dim3(32, V_WARPS, 1), V_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g, const_cast<float *>(p_in));
-        else k_jacobi_fused5e<<<grid, dim3(32, V_WARPS, 1), V_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g, const_cast<float *>(p_in));
+        float *em = const_cast<float *>(p_in);
+        const dim3 blk(32, V_WARPS, 1);
+        if (g_fused_variant == 6) k_jacobi_fused6e<<<grid, blk, V_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g, em);
+        else if (g_fused_variant == 7) k_jacobi_fused7e<<<grid, blk, V_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g, em);
+        else if (g_fused_variant == 8) k_jacobi_fused8e<<<grid, blk, V_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g, em);
+        else k_jacobi_fused5e<<<grid, blk, V_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g, em);
         return FS2D_OK;
     }
     if (g_fused_variant == 3) k_jacobi_fused3<8><<<grid, dim3(32, FSI / 8, 1), F_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);
     else if (g_fused_variant == 5) k_jacobi_fused5<<<grid, dim3(32, V_WARPS, 1), V_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);
     else if (g_fused_variant == 6) k_jacobi_fused6<<<grid, dim3(32, V_WARPS, 1), V_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);
+    else if (g_fused_variant == 7) k_jacobi_fused7<<<grid, dim3(32, V_WARPS, 1), V_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g, nullptr);
+    else if (g_fused_variant == 8) k_jacobi_fused8<<<grid, dim3(32, V_WARPS, 1), V_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g, nullptr);
     else k_jacobi_fused<<<grid, dim3(FSJ, FNTY, 1), F_SMEM, s>>>(mp, ms, mc, p_out, ctr, d, g);
     return FS2D_OK;
 }

@@ -217,7 +217,7 @@ extern "C" {
 
 int fs2d_set_tuning(int key, int value) {
     if (key == 0 && (value == 1 || value == 2 || value == 4 || value == 8 || value == 16)) { g_jm_rows = value; return FS2D_OK; }
-    if (key == 1 && (value == 1 || value == 3 || value == 5 || value == 6)) { fs2d::g_fused_variant = value; return FS2D_OK; }
+    if (key == 1 && (value == 1 || value == 3 || (value >= 5 && value <= 8))) { fs2d::g_fused_variant = value; return FS2D_OK; }
     if (key == 2 && value >= 0 && value <= 2) { fs2d::g_stream = value; return FS2D_OK; }
     if (key == 3 && value >= 0 && value <= 3) { fs2d::g_stream_cfg = value; return FS2D_OK; }
     if (key == 4 && (value == 0 || value == 1)) { fs2d::g_tail_emit = value; return FS2D_OK; }

@@ -74,7 +74,8 @@ unsigned long long fs2d_launch_count(void);
  * key 0 = rows marched per warp by the single-iteration Jacobi sweep {1, 2, 4 (default), 8, 16};
  * key 1 = fused Jacobi kernel variant {1: one column per thread, shared-memory planes (64 x 128 tile); 3: register tile +
  *         warp shuffles (64 x 128 tile); 5: register tile on a 96 x 128 tile (default); 6: EXPERIMENTAL, variant 5 with
- *         pairwise named barriers between neighbouring warps instead of a CTA barrier per iteration};
+ *         pairwise named barriers between neighbouring warps instead of a CTA barrier per iteration; 7 / 8: EXPERIMENTAL,
+ *         variants 5 / 6 whose slow tiles resolve the BC source cells of their slow cells once per tile};
  * key 2 = TMA-fed streaming versions of the CIP-path stencil kernels {0: off, 1: CIP advection (default), 2: also the
  *         non-advection phase and the vorticity confinement};
  * key 3 = streaming-kernel shape {stages x CTAs/SM x threads}: {0: 3x2x256, 1: 2x3x256 (default), 2: 3x2x512, 3: 2x2x512}.

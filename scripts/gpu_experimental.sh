@@ -9,9 +9,9 @@ echo "== kernel bench, random fields"
 timeout 240 python scripts/kernel_bench.py 2>&1 | tee gpurun_out/kernel_bench_experimental.txt | tail -14
 echo "== kernel bench, uniform fields (quiescent-like)"
 FIELDS=uniform timeout 240 python scripts/kernel_bench.py 2>&1 | tee -a gpurun_out/kernel_bench_experimental.txt | tail -14
-echo "== fused Jacobi: variant 6 (pair barriers, experimental) vs variant 5 (default)"
+echo "== fused Jacobi: variants 6 (pair barriers), 7 (resolved slow-cell table), 8 (both) vs variant 5 (default)"
 FS2D_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "pair_barrier" 2>&1 | tail -4
-for v in 5 6; do FUSED_VARIANT=$v timeout 200 python scripts/sweep_bench.py 2>&1 | tee -a gpurun_out/sweep_bench_variants.txt | grep -E "variant|T= ?(4|8|12):"; done
+for v in 5 6 7 8; do FUSED_VARIANT=$v timeout 200 python scripts/sweep_bench.py 2>&1 | tee -a gpurun_out/sweep_bench_variants.txt | grep -E "variant|T= ?(4|8|12):"; done
 echo "== emitting tail pass (fs2d_set_tuning(4, 1)): parity, then the update with and without it"
 FS2D_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "emitting_tail" 2>&1 | tail -4
 timeout 200 python - <<'PY' 2>&1 | tee gpurun_out/tail_emit_timing.txt

@@ -28,7 +28,7 @@ for num, X, Y in ((2, 256, 128), (3, 200, 176)):
     import os
     if os.environ.get("FS2D_EXPERIMENTAL") == "1":
         lib.fs2d_set_tuning(2, 1)
-        for variant, tail, march, fused in ((6, 0, 0, False), (5, 1, 1, True), (6, 1, 1, True)):
+        for variant, tail, march, fused in ((6, 0, 0, False), (5, 1, 1, True), (7, 0, 0, False), (8, 1, 1, True)):
             lib.fs2d_set_tuning(1, variant); lib.fs2d_set_tuning(4, tail); lib.fs2d_set_tuning(5, march)
             s.fused_non_advection = fused
             s.update(); s.update()

@@ -823,8 +823,10 @@ def test_fused_non_advection_trajectory_vs_oracle(env):
 
 @pytest.mark.parametrize("num,X,Y", [(2, 256, 128), (5, 384, 192), (2, 1000, 512), (3, 2048, 1024)])
 def test_pair_barrier_variant_equals_literal_iterations(env, num, X, Y):
-    """fused Jacobi variant 6 (pairwise named barriers between neighbouring warps in open-fluid tiles)"""
-    test_fused_pass_equals_literal_iterations(env, num, X, Y, 6)
+    """fused Jacobi variants 6 (pairwise named barriers between neighbouring warps in open-fluid tiles), 7 (resolved
+    slow-cell table) and 8 (both)"""
+    for variant in (6, 7, 8):
+        test_fused_pass_equals_literal_iterations(env, num, X, Y, variant)
 
 
 @pytest.mark.parametrize("num,X,Y,n_iter", [(2, 256, 128, 80), (5, 384, 192, 21), (1, 128, 64, 7), (3, 320, 160, 13), (2, 96, 48, 3),

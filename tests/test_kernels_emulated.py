@@ -71,7 +71,7 @@ def test_emu_jacobi_row_range_invariance_and_literal_equivalence(env):
     G.test_jacobi_row_range_invariance_and_literal_equivalence(env, res=128)
 
 
-@pytest.mark.parametrize("variant", [1, 3, 5, 6])       # 6: experimental pair-barrier variant (off by default)
+@pytest.mark.parametrize("variant", [1, 3, 5, 6, 7, 8])       # 6, 7, 8: experimental variants (off by default)
 @pytest.mark.parametrize("num,X,Y", [(1, 128, 64), (2, 256, 128), (4, 200, 96), (5, 384, 192), (1, 288, 352)])
 def test_emu_fused_pass_equals_literal_iterations(env, num, X, Y, variant):
     # (1, 288, 352) is wide and tall enough to contain OPEN-FLUID tiles (no wall, BC cell or grid edge in the tile): the
@@ -81,7 +81,7 @@ def test_emu_fused_pass_equals_literal_iterations(env, num, X, Y, variant):
                                                 need=2 if big else 3)
 
 
-@pytest.mark.parametrize("variant", [1, 3, 5, 6])
+@pytest.mark.parametrize("variant", [1, 3, 5, 6, 7, 8])
 def test_emu_fused_pass_random_obstacles(env, variant):
     G.test_fused_pass_random_obstacles(env, 0, variant, size=(320, 160), t_list=(4, 8))
 
@@ -106,7 +106,7 @@ def test_emu_stream_kernel_shapes(env, cfg):
         env.fs2d_set_tuning(3, 1)
 
 
-@pytest.mark.parametrize("variant", [3, 5, 6])
+@pytest.mark.parametrize("variant", [3, 5, 6, 7])
 def test_emu_fused_pass_split_into_interior_and_edge_launches(env, variant):
     G.test_fused_pass_split_into_interior_and_edge_launches(env, variant, X=420, Y=160)
 
@@ -144,10 +144,11 @@ def test_emu_emitting_tail_pass_equals_literal_update(env, num, X, Y, n_iter):
         G.test_emitting_tail_pass_equals_literal_update, "__wrapped__") else G.test_emitting_tail_pass_equals_literal_update(env, num, X, Y, n_iter)
 
 
-def test_emu_emitting_tail_with_the_pair_barrier_variant(env):
-    env.fs2d_set_tuning(1, 6)
+@pytest.mark.parametrize("variant", [6, 7, 8])
+def test_emu_emitting_tail_with_the_other_experimental_variants(env, variant):
+    env.fs2d_set_tuning(1, variant)
     try:
-        for num, X, Y, n_iter in ((1, 128, 64, 7), (1, 288, 352, 6)):
+        for num, X, Y, n_iter in ((1, 128, 64, 7), (1, 288, 352, 6), (3, 200, 96, 5)):
             G.test_emitting_tail_pass_equals_literal_update(env, num, X, Y, n_iter)
     finally:
         env.fs2d_set_tuning(1, 5)
@@ -184,7 +185,7 @@ def test_emu_fused_pass_fuzz(env, seed):
     if kind == 2:
         for _ in range(6):
             mask[int(rng.integers(3, X - 3)), int(rng.integers(3, Y - 3))] = int(rng.integers(2, 4))
-    for variant in (3, 5, 6):
+    for variant in (3, 5, 6, 7, 8):
         env.fs2d_set_tuning(1, variant)
         try:
             G._fused_pass_check(1, X, Y, mask_override=mask, t_list=(1, 3, 8), need=0)
