@@ -148,7 +148,7 @@ def test_strip_check_script_dry_run_on_cpu(world):
     assert out.returncode == 0 and f"MP_CHECK OK 8 cases on {world} ranks" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [3])
 def test_strip_check_script_with_emulated_kernels(world):
     """The same script with the KERNEL SOURCES running on the CUDA emulation (tests/cuda_emu) instead of the oracle stand-in:
     the real kernels on strips -- row windows with clamp bounds inside the local array, 1-2 row edge windows of the overlap
