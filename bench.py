@@ -239,6 +239,18 @@ def run_ours(a: argparse.Namespace) -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
     assert lib.fs2d_device_ok(), lib.fs2d_last_error().decode()
+    # experimental kernel selection for A/B runs (default: none): FS2D_TUNING="1=8,4=1,5=1,nonadv=1" -> fs2d_set_tuning(key, value)
+    # pairs and CipMacSolver.fused_non_advection; recorded in the JSON line as "tuning"
+    tuning = {}
+    for item in filter(None, os.environ.get("FS2D_TUNING", "").split(",")):
+        k, v = item.split("=")
+        tuning[k] = int(v)
+        if k == "nonadv":
+            from fs.solver import CipMacSolver
+
+            CipMacSolver.fused_non_advection = bool(int(v))
+        else:
+            _lib.call("fs2d_set_tuning", int(k), int(v))
 
     X, Y = a.rows_per_gpu * world, a.cols
     dt, dx = 0.05 / Y_COLS, 1.0 / Y_COLS
@@ -383,7 +395,7 @@ def run_ours(a: argparse.Namespace) -> None:
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, world),
                 "stepping": "cuda-graph replay (1 launch/step)" if use_graph else "eager launches",
                 "ms_per_step_eager": ms_step_eager, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu, "baseline_config_2": extra}
+                "cpu_baseline": cpu, "baseline_config_2": extra, "tuning": tuning or None}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
