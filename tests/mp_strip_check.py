@@ -95,7 +95,7 @@ def main() -> None:
             _lib.stream = lambda: 0
         dev = torch.device("cpu")
         dist.init_process_group("gloo")
-        cases = [c for c in CASES if c[1] * c[2] <= 640 * 64]
+        cases = [c for c in CASES if c[1] * c[2] <= int(os.environ.get("FS2D_DRY_MAX_CELLS", 640 * 64))]
     else:
         torch.cuda.set_device(local)
         dev = torch.device("cuda", local)
