@@ -49,7 +49,8 @@ int stream_cip_nonadv(float *fn, const float *fc, const float *pc, const uint8_t
 int stream_vort_apply(float *vn, float *w, float *wabs, const float *vc, const uint8_t *mask, const fs2d_dom &d, float dx,
                       float dtw, bool p2, cudaStream_t s);
 int stream_cip_nonadv_fused(float *fn, float *fxn, float *fyn, const float *fc, const float *fxc, const float *fyc, const float *pc,
-                            const uint8_t *mask, const fs2d_dom &d, float dt, float dx, float re, float two_dx, cudaStream_t s);
+                            const uint8_t *mask, const fs2d_dom &d, float dt, float dx, float re, float two_dx, int ring_lo,
+                            int ring_hi, cudaStream_t s);
 // EXPERIMENTAL marching version of VorticityConfinement.apply() (fs2d_vort_march.cu); g_vort_march: fs2d_set_tuning(5, 0/1)
 extern int g_vort_march;
 int vort_march(float *vn, float *w, float *wabs, const float *vc, const uint8_t *mask, const fs2d_dom &d, float dx, float dtw,

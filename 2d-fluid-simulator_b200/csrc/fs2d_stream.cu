@@ -344,8 +344,8 @@ int stream_vort_apply(float *vn, float *w, float *wabs, const float *vc, const u
 //
 // Per tile (16 x 64 cells, TMA-fed stages like k_stream): phase 1 evaluates fn on the tile + ring (18 x 66 cells; a wall
 // cell keeps the value stored in the fn array -- never written by the reference kernel, SURVEY T1 -- which is read from
-// global memory) into a shared scratch tile and stores the tile's own not-wall cells; phase 2 forms the two gradients
-// from the scratch tile.  Same per-cell functions and operation order as the two kernels: bit-identical results.
+// global memory) into a shared scratch tile and stores the tile's own not-wall cells (and those of the ring rows outside
+// [r0, r1) that the caller allows it to recompute: [ring_lo, ring_hi)); phase 2 forms the two gradients from the scratch tile.  Same per-cell functions and operation order as the two kernels: bit-identical results.
 // Reads outside the clamp window [clo, chi] x [0, Y-1] are clamped by index, so no halo repair is needed.
 // =============================================================================================
 constexpr int NFU_HR = 2;                                   // row halo of the fc / p boxes (ring 1 + its stencil)
@@ -380,7 +380,8 @@ struct NfuAt {
 template <bool P2, int STAGES, int MIN_CTAS>
 __global__ void __launch_bounds__(256, MIN_CTAS)
     k_nonadv_fused(const __grid_constant__ NfuMaps maps, float *__restrict__ fn, float *__restrict__ fxn, float *__restrict__ fyn,
-                   const fs2d_dom d, const StreamGeom g, float dt, float re, DivC<P2> ddx, DivC<P2> ddx2, DivC<P2> d2dx) {
+                   const fs2d_dom d, const StreamGeom g, float dt, float re, DivC<P2> ddx, DivC<P2> ddx2, DivC<P2> d2dx,
+                   int ring_lo, int ring_hi) {
     extern __shared__ __align__(1024) uint8_t nf_sm[];
     __shared__ __align__(8) uint64_t full[STAGES];
     float2 *scratch = reinterpret_cast<float2 *>(nf_sm + (size_t)STAGES * NFU_STAGE);
@@ -435,14 +436,16 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
             if (r < d.clo || r > d.chi || j < 0 || j >= d.Y) continue;   // never read: neighbour reads are clamped
             const size_t idx = (size_t)r * d.Y + j;
             float2 val;
-            if (s_mk[lr * NFU_MK_COLS + lc + 15] == 1 || r < d.r0 || r >= d.r1) {
-                // a wall cell, or a row this launch does not update: the value stored in fn (never written here) -- exactly
-                // what the separate gradient kernel would read
+            if (s_mk[lr * NFU_MK_COLS + lc + 15] == 1 || r < ring_lo || r >= ring_hi) {
+                // a wall cell, or a row outside [ring_lo, ring_hi) -- the rows whose fn this call may recompute: the value
+                // stored in fn (never written here), exactly what the separate gradient kernel would read
                 val = reinterpret_cast<const float2 *>(fn)[idx];
             } else {
                 const NfuAt at{r, j, R0 - NFU_HR, C0 - ST_HC, d.clo, d.chi, d.Y - 1};
                 val = c_cip_nonadv<P2>(l_cip_nonadv(at, s_fc, s_pc), dt, ddx, ddx2, re);
-                if (lr >= 1 && lr <= ST_TR && lc >= 1 && lc <= ST_TC) reinterpret_cast<float2 *>(fn)[idx] = val;
+                // stored by the tile that owns the cell's column: its own rows inside [r0, r1), and the ring rows outside it
+                const bool own_row = lr >= 1 && lr <= ST_TR && r < d.r1;
+                if (lc >= 1 && lc <= ST_TC && (own_row || r < d.r0 || r >= d.r1)) reinterpret_cast<float2 *>(fn)[idx] = val;
             }
             scratch[lr * NFU_SC_COLS + lc] = val;
         }
@@ -474,7 +477,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
 template <bool P2>
 static int launch_nonadv_fused(float *fn, float *fxn, float *fyn, const float *fc, const float *fxc, const float *fyc,
                                const float *pc, const uint8_t *mask, const fs2d_dom &d, float dt, float dx, float re, float two_dx,
-                               cudaStream_t s) {
+                               int ring_lo, int ring_hi, cudaStream_t s) {
     constexpr int STAGES = 2, MIN_CTAS = 2;
     constexpr int SMEM = STAGES * NFU_STAGE + NFU_SC_ROWS * NFU_SC_COLS * 8;
     static int n_sm = 0;
@@ -500,14 +503,16 @@ static int launch_nonadv_fused(float *fn, float *fxn, float *fyn, const float *f
     const int grid = g.n_tiles < MIN_CTAS * n_sm ? g.n_tiles : MIN_CTAS * n_sm;
     ++g_launches;
     k_nonadv_fused<P2, STAGES, MIN_CTAS><<<grid, 256, SMEM, s>>>(maps, fn, fxn, fyn, d, g, dt, re, DivC<P2>(dx), DivC<P2>(dx * dx),
-                                                                DivC<P2>(two_dx));
+                                                                DivC<P2>(two_dx), ring_lo, ring_hi);
     return FS2D_OK;
 }
 
 int stream_cip_nonadv_fused(float *fn, float *fxn, float *fyn, const float *fc, const float *fxc, const float *fyc, const float *pc,
-                            const uint8_t *mask, const fs2d_dom &d, float dt, float dx, float re, float two_dx, cudaStream_t s) {
-    if (is_pow2(dx) && is_pow2(two_dx)) return launch_nonadv_fused<true>(fn, fxn, fyn, fc, fxc, fyc, pc, mask, d, dt, dx, re, two_dx, s);
-    return launch_nonadv_fused<false>(fn, fxn, fyn, fc, fxc, fyc, pc, mask, d, dt, dx, re, two_dx, s);
+                            const uint8_t *mask, const fs2d_dom &d, float dt, float dx, float re, float two_dx, int ring_lo,
+                            int ring_hi, cudaStream_t s) {
+    if (is_pow2(dx) && is_pow2(two_dx))
+        return launch_nonadv_fused<true>(fn, fxn, fyn, fc, fxc, fyc, pc, mask, d, dt, dx, re, two_dx, ring_lo, ring_hi, s);
+    return launch_nonadv_fused<false>(fn, fxn, fyn, fc, fxc, fyc, pc, mask, d, dt, dx, re, two_dx, ring_lo, ring_hi, s);
 }
 
 }  // namespace fs2d

@@ -43,7 +43,7 @@ _SIGNATURES = {
     "fs2d_mac_update": (c_int, [_P, _P, _P, _P, Dom, c_float, c_float, c_float, c_int, _P]),
     "fs2d_cip_nonadv": (c_int, [_P, _P, _P, _P, Dom, c_float, c_float, c_float, _P]),
     "fs2d_cip_nonadv_grad": (c_int, [_P, _P, _P, _P, _P, _P, _P, Dom, c_float, _P]),
-    "fs2d_cip_nonadv_fused": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, Dom, c_float, c_float, c_float, c_float, _P]),
+    "fs2d_cip_nonadv_fused": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, Dom, c_float, c_float, c_float, c_float, c_int, c_int, _P]),
     "fs2d_cip_advect": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, Dom, c_float, c_float, c_float, c_float, _P]),
     "fs2d_set_grad": (c_int, [_P, _P, _P, Dom, c_float, _P]),
     "fs2d_vort_calc": (c_int, [_P, _P, _P, _P, Dom, c_float, _P]),

@@ -113,11 +113,15 @@ int fs2d_cip_nonadv_grad(float *fxn, float *fyn, const float *fxc, const float *
                          const uint8_t *mask, fs2d_dom d, float two_dx, void *stream);
 /* EXPERIMENTAL (not used by default): fs2d_cip_nonadv followed by fs2d_cip_nonadv_grad in ONE pass over HBM (53 instead of
  * 70 B/cell): fn at the four neighbours of a cell is recomputed from fc / pc on a one-cell ring around each tile; wall
- * neighbours keep the value stored in fn.  Same fn, fxn, fyn as the two calls, bit for bit.  Whole-array use only (a row
- * strip would need two fresh halo rows of fc and pc instead of one of fn); falls back to the two kernels when the TMA
- * preconditions (Y % 16 == 0, 16-byte aligned fields) do not hold.  Outputs must not alias inputs. */
+ * neighbours keep the value stored in fn.  Defined as fs2d_cip_nonadv on the rows [ring_lo, ring_hi) followed by
+ * fs2d_cip_nonadv_grad on [r0, r1), bit for bit, where [ring_lo, ring_hi) is [r0, r1) extended by at most one row per side:
+ * fn of those extra rows is recomputed (and stored) instead of being read -- a rank of a row-strip decomposition passes its
+ * owned rows +- 1 and needs two fresh halo rows of fc and pc instead of an exchange of fn.  Falls back to the two kernels when
+ * the TMA preconditions (Y % 16 == 0, 16-byte aligned fields) do not hold.  An empty [r0, r1) is a no-op.  Outputs must not
+ * alias inputs. */
 int fs2d_cip_nonadv_fused(float *fn, float *fxn, float *fyn, const float *fc, const float *fxc, const float *fyc, const float *pc,
-                          const uint8_t *mask, fs2d_dom d, float dt, float dx, float re, float two_dx, void *stream);
+                          const uint8_t *mask, fs2d_dom d, float dt, float dx, float re, float two_dx, int ring_lo, int ring_hi,
+                          void *stream);
 /* CipMacSolver._advection_phase/_cip_advect, fs/solver.py:267-332 (fluid cells);
  * dx2 = (float)(dx*dx), dx3 = (float)(dx*dx*dx) folded in double by the caller */
 int fs2d_cip_advect(float *fn, float *fxn, float *fyn, const float *fc, const float *fxc, const float *fyc,

@@ -149,9 +149,12 @@ class FakeFs2d:
         self._windowed(d, [self.a(fxn, d, 2), self.a(fyn, d, 2)], lambda w, ox, oy: orc.lib().orc_cip_nonadv_grad(
             _p(ox), _p(oy), _p(XC[w]), _p(YC[w]), _p(FC[w]), _p(FN[w]), _p(M[w]), _i(ox.shape[0]), _i(d.Y), _f(two_dx)))
 
-    def fs2d_cip_nonadv_fused(self, fn, fxn, fyn, fc, fxc, fyc, pc, mask, d, dt, dx, re, two_dx, stream) -> None:
-        """by definition the two reference kernels one after the other (include/fs2d.h)"""
-        self.fs2d_cip_nonadv(fn, fc, pc, mask, d, dt, dx, re, stream)
+    def fs2d_cip_nonadv_fused(self, fn, fxn, fyn, fc, fxc, fyc, pc, mask, d, dt, dx, re, two_dx, ring_lo, ring_hi, stream) -> None:
+        """by definition (include/fs2d.h): fs2d_cip_nonadv on [ring_lo, ring_hi), then fs2d_cip_nonadv_grad on [r0, r1);
+        an empty [r0, r1) is a no-op"""
+        if d.r0 == d.r1:
+            return
+        self.fs2d_cip_nonadv(fn, fc, pc, mask, d.replace(r0=ring_lo, r1=ring_hi), dt, dx, re, stream)
         self.fs2d_cip_nonadv_grad(fxn, fyn, fxc, fyc, fc, fn, mask, d, two_dx, stream)
 
     def fs2d_cip_advect(self, fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, dx2, dx3, stream) -> None:

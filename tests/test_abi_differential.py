@@ -75,8 +75,9 @@ class Case:
     def f(self, *shape, scale=1.0):
         return (self.rng.uniform(-1, 1, shape) * scale).astype(np.float32)
 
-    def run(self, name: str, arrays: dict, outs: tuple, build_args) -> None:
-        """arrays: name -> ndarray; build_args(ptrs) -> argument tuple of the entry point"""
+    def run(self, name: str, arrays: dict, outs: tuple, build_args, written: dict | None = None) -> None:
+        """arrays: name -> ndarray; build_args(ptrs) -> argument tuple of the entry point; written: output -> (lo, hi) rows it
+        may write when that is not [r0, r1)"""
         res = []
         for impl in ("emu", "fake"):
             ts = {k: torch.from_numpy(a.copy()) for k, a in arrays.items()}
@@ -91,8 +92,9 @@ class Case:
         tag = f"{name} {self.X}x{self.Y} rows {d.r0}:{d.r1} clamp {d.clo}:{d.chi} dx={self.dx}"
         for k in outs:
             assert_bitexact(f"{tag}: {k}", res[0][k], res[1][k])
+            lo, hi = (written or {}).get(k, (d.r0, d.r1))
             untouched = np.ones(self.X, bool)
-            untouched[d.r0:d.r1] = False
+            untouched[lo:hi] = False
             assert_bitexact(f"{tag}: {k} rows outside the window", res[0][k][untouched], arrays[k][untouched])
 
 
@@ -117,7 +119,11 @@ def test_dense_entry_points_against_the_window_model(libs, seed):
     c.run("fs2d_cip_nonadv_grad", dict(fxn=o2a, fyn=o2b, fxc=fx, fyc=fy, fc=v, fn=o2c, mask=m), ("fxn", "fyn"),
           lambda q: (q["fxn"], q["fyn"], q["fxc"], q["fyc"], q["fc"], q["fn"], q["mask"], d, 2.0 * dx, None))
     c.run("fs2d_cip_nonadv_fused", dict(fn=o2a, fxn=o2b, fyn=o2c, fc=v, fxc=fx, fyc=fy, pc=p, mask=m), ("fn", "fxn", "fyn"),
-          lambda q: (q["fn"], q["fxn"], q["fyn"], q["fc"], q["fxc"], q["fyc"], q["pc"], q["mask"], d, dt, dx, re, 2.0 * dx, None))
+          lambda q: (q["fn"], q["fxn"], q["fyn"], q["fc"], q["fxc"], q["fyc"], q["pc"], q["mask"], d, dt, dx, re, 2.0 * dx, d.r0, d.r1, None))
+    ring = (max(d.r0 - 1, d.clo), min(d.r1 + 1, d.chi + 1))     # what a strip passes: fn recomputed (and stored) one row beyond each side
+    c.run("fs2d_cip_nonadv_fused", dict(fn=o2a, fxn=o2b, fyn=o2c, fc=v, fxc=fx, fyc=fy, pc=p, mask=m), ("fn", "fxn", "fyn"),
+          lambda q: (q["fn"], q["fxn"], q["fyn"], q["fc"], q["fxc"], q["fyc"], q["pc"], q["mask"], d, dt, dx, re, 2.0 * dx, ring[0], ring[1], None),
+          written={"fn": ring})
     c.run("fs2d_cip_advect", dict(fn=o2a, fxn=o2b, fyn=o2c, fc=v, fxc=fx, fyc=fy, mask=m), ("fn", "fxn", "fyn"),
           lambda q: (q["fn"], q["fxn"], q["fyn"], q["fc"], q["fxc"], q["fyc"], q["fc"], q["mask"], d, dt, dx, dx**2, dx**3, None))
     c.run("fs2d_set_grad", dict(fx=o2a, fy=o2b, f=v), ("fx", "fy"), lambda q: (q["fx"], q["fy"], q["f"], d, dx, None))

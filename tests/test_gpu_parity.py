@@ -773,7 +773,7 @@ def _nonadv_fused_check(num, X, Y, mask_override=None):
                     if fused:
                         _lib.call("fs2d_cip_nonadv_fused", s.v.next.ptr(), s.vx.next.ptr(), s.vy.next.ptr(), s.v.current.ptr(),
                                   s.vx.current.ptr(), s.vy.current.ptr(), s.p.current.ptr(), _lib.ptr(bc._bc_mask), bc.dom, s.dt,
-                                  s.dx, s.re, 2.0 * s.dx, _lib.stream())
+                                  s.dx, s.re, 2.0 * s.dx, bc.dom.r0, bc.dom.r1, _lib.stream())
                     else:
                         s._non_advection_phase(s.v.next, s.v.current, s.p.current)
                         s._non_advection_phase_grad(s.vx.next, s.vy.next, s.vx.current, s.vy.current, s.v.current, s.v.next)
