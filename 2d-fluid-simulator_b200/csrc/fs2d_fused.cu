@@ -1068,4 +1068,18 @@ int fs2d_jacobi_fused_part(float *p_out, const float *p_in, const float *src, co
     return FS2D_OK;
 }
 
+int fs2d_jacobi_fused_tail(float *p_out, float *p_in, const float *src, const uint8_t *pcode, fs2d_dom d, int T, int skip_from,
+                           int skip_n, void *stream) {
+    FS2D_REQUIRE(p_out && p_in && src && pcode && p_out != p_in, "null/aliased field pointer");
+    FS2D_REQUIRE(T >= 1 && T <= F_TMAX, "fused iteration count out of range");
+    FS2D_REQUIRE(d.Y % 16 == 0 && ((uintptr_t)p_in % 16 == 0) && ((uintptr_t)p_out % 16 == 0) && ((uintptr_t)src % 16 == 0) &&
+                     ((uintptr_t)pcode % 16 == 0),
+                 "fused Jacobi needs Y % 16 == 0 and 16-byte aligned fields (TMA row pitch / base alignment)");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+    if (int e = fused_pass(p_in, p_out, src, pcode, d, T, (cudaStream_t)stream, skip_from, skip_n, true)) return e;
+    FS2D_LAUNCH_CHECK();
+    return FS2D_OK;
+}
+
 }  // extern "C"

@@ -291,9 +291,22 @@ static int plan_jacobi(int n_sweeps, int fuse_mask, int *out, int cap, int tail_
     return n;
 }
 
+// The schedule of one update under the current tuning: with the experimental tail (fs2d_set_tuning(4, 1), variants >= 5) it
+// ends {..., fused pass that also emits the BC values of its penultimate state, ONE literal iteration} instead of
+// {..., two literal iterations}; see jacobi_fused5_body<.., EMIT>.  *tail = 1 if entry n - 2 is that emitting pass (if the
+// entry before the last one is itself a literal iteration, the usual reasoning applies unchanged).
+static int plan_with_tail(int n_sweeps, int fuse_mask, int *out, int cap, bool *tail) {
+    int n = -1;
+    if (fs2d::g_tail_emit && fs2d::g_fused_variant >= 5 && fuse_mask != 0 && n_sweeps >= 3) n = plan_jacobi(n_sweeps, fuse_mask, out, cap, 1);
+    *tail = n >= 2 && out[n - 2] > 0;
+    if (n < 0) n = plan_jacobi(n_sweeps, fuse_mask, out, cap);
+    return n;
+}
+
 int fs2d_jacobi_plan(int n_sweeps, int fuse_mask, int *sizes, int cap, int *n_entries) {
     FS2D_REQUIRE(n_sweeps >= 0 && fuse_mask >= 0 && sizes && n_entries && cap > 0, "bad plan arguments");
-    const int n = plan_jacobi(n_sweeps, fuse_mask, sizes, cap);
+    bool tail = false;
+    const int n = plan_with_tail(n_sweeps, fuse_mask, sizes, cap, &tail);
     FS2D_REQUIRE(n >= 0, "plan does not fit the output array");
     *n_entries = n;
     return FS2D_OK;
@@ -309,16 +322,8 @@ int fs2d_jacobi_update(float *pa, float *pb, const float *src, const uint8_t *pc
     float *cur = pa, *nxt = pb;
     if (d.r1 == d.r0 || !fused_supported(pa, pb, src, pcode, d)) fuse_mask = 0;
     static thread_local int plan[4200];
-    // Experimental tail (fs2d_set_tuning(4, 1), variant 5): {..., fused pass that also emits the BC values of its
-    // penultimate state, ONE literal iteration} instead of {..., two literal iterations}; see jacobi_fused5_body<.., EMIT>.
-    // If the schedule's entry before the last one is itself a literal iteration the old reasoning applies unchanged.
-    int n = -1;
-    bool tail = fs2d::g_tail_emit && fs2d::g_fused_variant >= 5 && fuse_mask != 0 && n_sweeps >= 3;
-    if (tail) n = plan_jacobi(n_sweeps, fuse_mask, plan, 4200, 1);
-    if (n < 0) {
-        tail = false;
-        n = plan_jacobi(n_sweeps, fuse_mask, plan, 4200);
-    }
+    bool tail = false;
+    const int n = plan_with_tail(n_sweeps, fuse_mask, plan, 4200, &tail);
     FS2D_REQUIRE(n >= 0, "iteration count too large");
     for (int k = 0; k < n; ++k) {
         if (plan[k] > 0) {

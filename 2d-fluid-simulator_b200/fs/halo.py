@@ -169,7 +169,11 @@ def jacobi_update_distributed(jac, p: DoubleBuffer, v_current: Field) -> None:
     else:
         hx.exchange(v_current, min(bc.halo, reach + 1))
         src = jac._source(v_current, dom=ext)
-    for t in plan:
+    # experimental tail (fs2d_set_tuning(4, 1)): the schedule then ends {fused pass, ONE literal iteration} and that pass emits
+    # the BC values of its penultimate state (the default schedule always ends with two literal iterations)
+    tail_at = len(plan) - 2 if len(plan) >= 2 and plan[-2] > 0 else -1
+    for k, t in enumerate(plan):
+        emit = k == tail_at
         if t > 0:
             # Overlap: the pass reads the fresh halo rows only in its first and last TILE ROW, so the tile rows in
             # between run while the SendRecv is in flight.  The interior window starts at a multiple of the tile height
@@ -177,12 +181,12 @@ def jacobi_update_distributed(jac, p: DoubleBuffer, v_current: Field) -> None:
             mid, m = _pass_windows(bc, t)
             if mid is None:
                 hx.exchange(p.current, t)
-                jac._fused(p.next, p.current, src, t)
+                jac._fused(p.next, p.current, src, t, emit=emit)
             else:
                 reqs = hx.start(p.current, t)
-                jac._fused(p.next, p.current, src, t, dom=mid)              # tile rows [1, m): owned rows only
+                jac._fused(p.next, p.current, src, t, dom=mid, emit=emit)              # tile rows [1, m): owned rows only
                 hx.finish(reqs)
-                jac._fused(p.next, p.current, src, t, skip=(1, m - 1))      # tile rows {0} U [m, k) in one launch
+                jac._fused(p.next, p.current, src, t, skip=(1, m - 1), emit=emit)      # tile rows {0} U [m, k) in one launch
         else:
             hx.exchange(p.current, 2)
             bc.set_pressure_boundary_condition(p.current)       # owned rows and the first halo row

@@ -101,11 +101,16 @@ class JacobiPressureUpdater(PressureUpdater):
         _lib.call("fs2d_jacobi_plan", self._n_iter, self.fuse_mask(p), sizes, cap, ctypes.byref(n))
         return list(sizes[:n.value])
 
-    def _fused(self, p_next: Field, p_current: Field, src: Field, t: int, dom=None, skip=None) -> None:
+    def _fused(self, p_next: Field, p_current: Field, src: Field, t: int, dom=None, skip=None, emit: bool = False) -> None:
         """One fused pass; dom: row window (default: the owned rows); skip = (first, n): leave these tile rows of the
-        window's tiling to another launch (fs2d_jacobi_fused_part)."""
+        window's tiling to another launch (fs2d_jacobi_fused_part); emit: the experimental tail pass that also stores the BC
+        values of its penultimate state into the wall cells of p_current (fs2d_jacobi_fused_tail)."""
         bc = self._bc
-        if skip is None:
+        if emit:
+            first, n = skip if skip is not None else (0, 0)
+            _lib.call("fs2d_jacobi_fused_tail", p_next.ptr(), p_current.ptr(), src.ptr(), _lib.ptr(bc._pcode), dom or bc.dom, t,
+                      first, n, _lib.stream())
+        elif skip is None:
             _lib.call("fs2d_jacobi_fused", p_next.ptr(), p_current.ptr(), src.ptr(), _lib.ptr(bc._pcode), dom or bc.dom, t,
                       _lib.stream())
         else:

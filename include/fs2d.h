@@ -179,6 +179,13 @@ int fs2d_jacobi_fused(float *p_out, const float *p_in, const float *src, const u
  * first and last tile rows, which read the fresh halo, in ONE launch through this entry point. */
 int fs2d_jacobi_fused_part(float *p_out, const float *p_in, const float *src, const uint8_t *pcode, fs2d_dom d, int T,
                            int skip_from, int skip_n, void *stream);
+/* EXPERIMENTAL: fs2d_jacobi_fused_part whose pass also stores, into the wall-BC cells of p_in (rows [r0, r1) of the launched
+ * tile rows; those cells are never read), the BC values of the pass's PENULTIMATE state -- what the reference leaves there
+ * (SURVEY T1).  A pass of T iterations ending at iteration n - 1 followed by ONE literal iteration then reproduces both
+ * physical buffers of an n-iteration update.  fs2d_jacobi_plan returns such a schedule (entry n - 2 fused, entry n - 1
+ * literal) when fs2d_set_tuning(4, 1) is active; fused variants >= 5 only. */
+int fs2d_jacobi_fused_tail(float *p_out, float *p_in, const float *src, const uint8_t *pcode, fs2d_dom d, int T, int skip_from,
+                           int skip_n, void *stream);
 /* tile geometry of the fused kernel for T iterations per pass: loaded tile rows x cols, the halo it discards on
  * each side (rows: T; columns: T rounded up to 4 -- TMA box starts must be 16-byte aligned) and the largest T */
 int fs2d_fused_tile(int T, int *rows, int *cols, int *halo_rows, int *halo_cols, int *t_max);

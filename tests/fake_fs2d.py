@@ -236,20 +236,27 @@ class FakeFs2d:
             cur, nxt = nxt, cur
         final_in_b._obj.value = int(cur == pb)
 
-    def _fused_rows(self, p_out, p_in, src, pcode, d, T, row_sets) -> None:
-        PI, PO, S, M = self.a(p_in, d, 1), self.a(p_out, d, 1), self.a(src, d, 2), mask_from_pcode(self.a(pcode, d))
+    def _fused_rows(self, p_out, p_in, src, pcode, d, T, row_sets, emit: bool = False) -> None:
+        PC = self.a(pcode, d)
+        PI, PO, S, M = self.a(p_in, d, 1), self.a(p_out, d, 1), self.a(src, d, 2), mask_from_pcode(PC)
         w = slice(d.clo, d.chi + 1)
         mw = self._c(M[w])
         cur = PI[w].copy()
+        bc_of_penultimate = None
         for _ in range(T):
-            orc.p_bc(cur, mw)
+            orc.p_bc(cur, mw)                 # cur now holds the post-BC values of the state before this iteration
+            bc_of_penultimate = cur.copy()
             nxt = cur.copy()
             self._sweep_window(nxt, cur, S[w], mw, src, d.Y)
             cur = nxt
         relaxed = mw != 1
+        code = PC[w] & 15
+        wall_bc = (code >= 1) & (code <= 8)
         for r0, r1 in row_sets:     # BC cells of p_out are neither read nor written (include/fs2d.h)
             a, b = r0 - d.clo, r1 - d.clo
             PO[r0:r1][relaxed[a:b]] = cur[a:b][relaxed[a:b]]
+            if emit:                # fs2d_jacobi_fused_tail: BC values of the penultimate state into the wall-BC cells of p_in
+                PI[r0:r1][wall_bc[a:b]] = bc_of_penultimate[a:b][wall_bc[a:b]]
 
     def fs2d_jacobi_fused(self, p_out, p_in, src, pcode, d, T, stream) -> None:
         self._fused_rows(p_out, p_in, src, pcode, d, T, [(d.r0, d.r1)])
@@ -261,6 +268,14 @@ class FakeFs2d:
         k = (d.r1 - d.r0 + ti - 1) // ti
         sets = [(d.r0 + q * ti, min(d.r0 + (q + 1) * ti, d.r1)) for q in range(k) if not (skip_from <= q < skip_from + skip_n)]
         self._fused_rows(p_out, p_in, src, pcode, d, T, sets)
+
+    def fs2d_jacobi_fused_tail(self, p_out, p_in, src, pcode, d, T, skip_from, skip_n, stream) -> None:
+        rows, hr = ctypes.c_int(), ctypes.c_int()
+        self.real.fs2d_fused_tile(T, ctypes.byref(rows), None, ctypes.byref(hr), None, None)
+        ti = rows.value - 2 * hr.value
+        k = (d.r1 - d.r0 + ti - 1) // ti
+        sets = [(d.r0 + q * ti, min(d.r0 + (q + 1) * ti, d.r1)) for q in range(k) if not (skip_from <= q < skip_from + skip_n)]
+        self._fused_rows(p_out, p_in, src, pcode, d, T, sets, emit=True)
 
     def fs2d_rbsor_pass(self, pn, pc, src, mask, d, omega, one_minus_omega, parity, stream) -> None:
         PC, S, M = self.a(pc, d, 1), self.a(src, d, 2), self.a(mask, d)

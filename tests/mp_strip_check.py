@@ -101,6 +101,11 @@ def main() -> None:
         dev = torch.device("cuda", local)
         dist.init_process_group("nccl", device_id=dev)
         cases = CASES
+    for item in filter(None, os.environ.get("FS2D_STRIP_TUNING", "").split(",")):   # e.g. "4=1": experimental kernel variants
+        from fs import _lib as _l
+
+        k, v = item.split("=")
+        _l.call("fs2d_set_tuning", int(k), int(v))
     n_ok = 0
     for num, X, Y, scheme, vc, pkw, steps, halo in cases:
         res = Y

@@ -238,7 +238,7 @@ STRIP_CASES = [
     ("cip", 5.0, dict(pressure="jacobi", n_iter=11), 5))]     # walls, inflow and outflow cells on and next to the strip edges
 
 
-def _strip_worker(rank: int, world: int, port: int, q) -> None:
+def _strip_worker(rank: int, world: int, port: int, q, tuning=()) -> None:
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.set_num_threads(1)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -252,6 +252,8 @@ def _strip_worker(rank: int, world: int, port: int, q) -> None:
 
     orc.set_threads(1)
     fake = FakeFs2d(_lib.load()).install_plain()
+    for key, value in tuning:
+        _lib.call("fs2d_set_tuning", key, value)
     failures, info = [], []
     for num, X, Y, scheme, vc, pkw, dye, steps, halo in STRIP_CASES:
         part = Partition(X, rank, world, halo)
@@ -264,7 +266,8 @@ def _strip_worker(rank: int, world: int, port: int, q) -> None:
         for _ in range(steps):
             solver.update()
         hx = exchanger_for(solver._bc)
-        info.append((num, scheme, hx.n_exchanges, sum(1 for c in fake.trace[n0:] if c.startswith("fs2d_jacobi_fused"))))
+        info.append((num, scheme, hx.n_exchanges, sum(1 for c in fake.trace[n0:] if c.startswith("fs2d_jacobi_fused")),
+                     sum(1 for c in fake.trace[n0:] if c == "fs2d_jacobi_fused_tail")))
         ref = None
         if rank == 0:
             ref = orc.OracleSolver(mask, const, dt, dx, re, scheme, vc, _oracle_pressure(pkw), bc_dye=bc_dye)
@@ -301,8 +304,29 @@ def test_strips_equal_single_domain_under_gloo(world):
     for rank, failures, info in res:
         assert not failures, "\n".join(failures[:5])
     info = res[0][2]
-    assert all(n_ex > 0 for _, _, n_ex, _ in info)                 # every case really exchanged halos
-    assert info[4][3] > 0                                           # the 13-iteration case ran fused passes on the strips
+    assert all(i[2] > 0 for i in info)                             # every case really exchanged halos
+    assert info[4][3] > 0 and info[4][4] == 0                       # the 13-iteration case ran fused passes on the strips
+
+
+def test_strips_with_the_emitting_tail_under_gloo():
+    """fs2d_set_tuning(4, 1) on strips: the schedule ends {emitting fused pass, one literal iteration}; every physical
+    buffer -- the wall cells of both pressure buffers included -- still equals the reference's orchestration."""
+    from test_distributed import free_port
+
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=_strip_worker, args=(r, world, port, q, ((4, 1),))) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    for rank, failures, info in res:
+        assert not failures, "\n".join(failures[:5])
+    assert res[0][2][4][4] > 0 and any(i[4] > 0 for i in res[0][2][7:])     # the tail pass really ran (scene and random-mask cases)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
