@@ -239,7 +239,7 @@ def run_ours(a: argparse.Namespace) -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
     assert lib.fs2d_device_ok(), lib.fs2d_last_error().decode()
-    # experimental kernel selection for A/B runs (default: none): FS2D_TUNING="1=8,4=1,5=1,nonadv=1" -> fs2d_set_tuning(key, value)
+    # experimental kernel selection for A/B runs (default: none): FS2D_TUNING="1=8,4=1,5=1,nonadv=1,limitskip=1" -> fs2d_set_tuning(key, value)
     # pairs and CipMacSolver.fused_non_advection; recorded in the JSON line as "tuning"
     tuning = {}
     for item in filter(None, os.environ.get("FS2D_TUNING", "").split(",")):
@@ -249,6 +249,10 @@ def run_ours(a: argparse.Namespace) -> None:
             from fs.solver import CipMacSolver
 
             CipMacSolver.fused_non_advection = bool(int(v))
+        elif k == "limitskip":
+            from fs.pressure_updater import PressureUpdater
+
+            PressureUpdater.limit_skip = bool(int(v))
         else:
             _lib.call("fs2d_set_tuning", int(k), int(v))
 

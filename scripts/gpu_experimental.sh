@@ -42,7 +42,7 @@ for tool in memcheck racecheck synccheck; do
   echo "-- $tool"; FS2D_EXPERIMENTAL=1 timeout 280 compute-sanitizer --tool $tool --print-limit 5 python scripts/sanitize_small.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|^ok|=========.*(Error|hazard|Invalid)" | head -8
 done
 echo "== whole step with the experimental kernels (device-only bench line), default first"
-for t in "" "1=7" "1=8" "1=8,4=1" "1=8,4=1,5=1" "1=8,4=1,5=1,nonadv=1"; do
+for t in "" "1=7" "1=8" "1=8,4=1" "1=8,4=1,5=1" "1=8,4=1,5=1,nonadv=1,limitskip=1"; do
   FS2D_TUNING="$t" timeout 200 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-extra-config 2>/dev/null | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); print('tuning', d.get('tuning'), 'ms/step', round(d['ms_per_step'],3), 'ms/sweep', round(d['roofline']['ms_per_sweep'],5))"
 done | tee gpurun_out/bench_experimental.txt

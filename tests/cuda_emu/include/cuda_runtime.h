@@ -332,5 +332,13 @@ inline int __all_sync(unsigned, int pred) {
     const int g = emu::warp_rendezvous(0, pred);
     return emu::my_warp().pred_and[g];
 }
+inline unsigned __float_as_uint(float f) { unsigned i; memcpy(&i, &f, 4); return i; }
+inline float __uint_as_float(unsigned i) { float f; memcpy(&f, &i, 4); return f; }
+inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+    const int lane = emu::M().cur->lin % 32;
+    const int g = emu::warp_rendezvous((uint32_t)__float_as_int(v), 1);
+    return __int_as_float((int)emu::my_warp().buf[g][lane ^ lane_mask]);
+}
+inline unsigned atomicMax(unsigned *p, unsigned v) { const unsigned o = *p; if (v > o) *p = v; return o; }
 inline int atomicAdd(int *p, int v) { const int o = *p; *p += v; return o; }
 inline unsigned atomicAdd(unsigned *p, unsigned v) { const unsigned o = *p; *p += v; return o; }
