@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out
 echo "== experimental parity tests (GPU)"
-FS2D_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "nonadv_fused or fused_non_advection or marching_vorticity" 2>&1 | tail -8
+FS2D_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "nonadv_fused or fused_non_advection or marching_vorticity or limit_skip" 2>&1 | tail -8
 echo "== kernel bench, random fields"
 timeout 240 python scripts/kernel_bench.py 2>&1 | tee gpurun_out/kernel_bench_experimental.txt | tail -14
 echo "== kernel bench, uniform fields (quiescent-like)"

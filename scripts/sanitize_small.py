@@ -31,6 +31,7 @@ for num, X, Y in ((2, 256, 128), (3, 200, 176)):
         for variant, tail, march, fused in ((6, 0, 0, False), (5, 1, 1, True), (7, 0, 0, False), (8, 1, 1, True)):
             lib.fs2d_set_tuning(1, variant); lib.fs2d_set_tuning(4, tail); lib.fs2d_set_tuning(5, march)
             s.fused_non_advection = fused
+            s.pressure_updater.limit_skip = fused
             s.update(); s.update()
         lib.fs2d_set_tuning(1, 5); lib.fs2d_set_tuning(4, 0); lib.fs2d_set_tuning(5, 0)
         s.fused_non_advection = False
