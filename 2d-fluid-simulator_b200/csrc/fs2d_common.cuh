@@ -33,11 +33,11 @@ void launch_p_bc(float *p, const int32_t *tgt, const int32_t *src0, const int32_
                  int n, cudaStream_t s);
 inline unsigned nblk(int n, int b) { return (unsigned)((n + b - 1) / b); }
 bool is_pow2(float x);
-extern int g_fused_variant;  // fused Jacobi kernel variant (1 smem planes, 3 register tile), fs2d_set_tuning(1, v)
-// one fused pass of T Jacobi iterations p_in -> p_out (fs2d_fused.cu)
+// one fused pass of T Jacobi iterations p_in -> p_out (fs2d_fused.cu); order / n_order: tile list of fs2d_fused_order for
+// exactly this geometry, or nullptr (classified on the fly)
 int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t *pcode, const fs2d_dom &d, int T,
-               cudaStream_t s, int skip_from = 0, int skip_n = 0, bool emit = false);
-extern int g_tail_emit;      // fs2d_set_tuning(4, v), see fs2d_fused.cu
+               cudaStream_t s, int skip_from, int skip_n, bool emit, const int *order, int n_order);
+extern int g_tail_emit;      // fs2d_set_tuning(4, v), see fs2d_pressure.cu
 // TMA-fed streaming versions of the stencil kernels (fs2d_stream.cu); g_stream: fs2d_set_tuning(2, 0/1)
 extern int g_stream, g_stream_cfg;
 bool stream_ok(const fs2d_dom &d, const void *const *ptrs, int n);
@@ -48,13 +48,6 @@ int stream_cip_nonadv(float *fn, const float *fc, const float *pc, const uint8_t
                       float re, bool p2, cudaStream_t s);
 int stream_vort_apply(float *vn, float *w, float *wabs, const float *vc, const uint8_t *mask, const fs2d_dom &d, float dx,
                       float dtw, bool p2, cudaStream_t s);
-int stream_cip_nonadv_fused(float *fn, float *fxn, float *fyn, const float *fc, const float *fxc, const float *fyc, const float *pc,
-                            const uint8_t *mask, const fs2d_dom &d, float dt, float dx, float re, float two_dx, int ring_lo,
-                            int ring_hi, cudaStream_t s);
-// EXPERIMENTAL marching version of VorticityConfinement.apply() (fs2d_vort_march.cu); g_vort_march: fs2d_set_tuning(5, 0/1)
-extern int g_vort_march;
-int vort_march(float *vn, float *w, float *wabs, const float *vc, const uint8_t *mask, const fs2d_dom &d, float dx, float dtw,
-               cudaStream_t s);
 bool fused_supported(const float *pa, const float *pb, const float *src, const uint8_t *pcode, const fs2d_dom &d);
 
 // ---- indexing (clamp-to-edge sample(), fs/differentiation.py:4-9) -----------------------------

@@ -555,27 +555,6 @@ int fs2d_cip_nonadv_grad(float *fxn, float *fyn, const float *fxc, const float *
     return FS2D_OK;
 }
 
-int fs2d_cip_nonadv_fused(float *fn, float *fxn, float *fyn, const float *fc, const float *fxc, const float *fyc, const float *pc,
-                          const uint8_t *mask, fs2d_dom d, float dt, float dx, float re, float two_dx, int ring_lo, int ring_hi,
-                          void *stream) {
-    FS2D_REQUIRE(fn && fxn && fyn && fc && fxc && fyc && pc && mask, "null field pointer");
-    FS2D_REQUIRE(fn != fc && fxn != fxc && fyn != fyc, "the fused non-advection phase cannot run in place");
-    if (int e = check_dom(d)) return e;
-    FS2D_REQUIRE(d.clo <= ring_lo && ring_lo <= d.r0 && d.r0 - ring_lo <= 1 && d.r1 <= ring_hi && ring_hi - d.r1 <= 1 && ring_hi <= d.chi + 1,
-                 "ring rows must be [r0, r1) extended by at most one row per side, inside the clamp window");
-    if (d.r1 == d.r0) return FS2D_OK;
-    const void *ptrs[] = {fn, fxn, fyn, fc, fxc, fyc, pc, mask};
-    if (!stream_ok(d, ptrs, 8)) {   // TMA needs Y % 16 == 0 and 16-byte aligned fields: the two reference kernels instead
-        fs2d_dom ring = d;
-        ring.r0 = ring_lo; ring.r1 = ring_hi;
-        if (int e = fs2d_cip_nonadv(fn, fc, pc, mask, ring, dt, dx, re, stream)) return e;
-        return fs2d_cip_nonadv_grad(fxn, fyn, fxc, fyc, fc, fn, mask, d, two_dx, stream);
-    }
-    if (int e = stream_cip_nonadv_fused(fn, fxn, fyn, fc, fxc, fyc, pc, mask, d, dt, dx, re, two_dx, ring_lo, ring_hi, STREAM)) return e;
-    FS2D_LAUNCH_CHECK();
-    return FS2D_OK;
-}
-
 int fs2d_cip_advect(float *fn, float *fxn, float *fyn, const float *fc, const float *fxc, const float *fyc,
                     const float *v, const uint8_t *mask, fs2d_dom d, float dt, float dx, float dx2, float dx3,
                     void *stream) {
@@ -645,11 +624,6 @@ int fs2d_vort_apply(float *vn, float *w, float *wabs, const float *vc, const uin
             FS2D_LAUNCH_CHECK();
             return FS2D_OK;
         }
-    }
-    if (g_vort_march) {   // experimental marching kernel (fs2d_vort_march.cu), off by default
-        if (int e = vort_march(vn, w, wabs, vc, mask, d, dx, dtw, STREAM)) return e;
-        FS2D_LAUNCH_CHECK();
-        return FS2D_OK;
     }
 #define VP(P2) ++g_launches, k_vort_apply<P2><<<dense_grid_nu(d, VA_ROWS / TY), dense_block(), 0, STREAM>>>(vn, w, wabs, vc, mask, d, DivC<P2>(dx), dtw)
     DISPATCH_P2(is_pow2(dx), VP(true), VP(false));

@@ -251,11 +251,9 @@ extern "C" {
 
 int fs2d_set_tuning(int key, int value) {
     if (key == 0 && (value == 1 || value == 2 || value == 4 || value == 8 || value == 16)) { g_jm_rows = value; return FS2D_OK; }
-    if (key == 1 && (value == 1 || value == 3 || (value >= 5 && value <= 8))) { fs2d::g_fused_variant = value; return FS2D_OK; }
     if (key == 2 && value >= 0 && value <= 2) { fs2d::g_stream = value; return FS2D_OK; }
     if (key == 3 && value >= 0 && value <= 3) { fs2d::g_stream_cfg = value; return FS2D_OK; }
     if (key == 4 && (value == 0 || value == 1)) { fs2d::g_tail_emit = value; return FS2D_OK; }
-    if (key == 5 && (value == 0 || value == 1)) { fs2d::g_vort_march = value; return FS2D_OK; }
     set_error("unknown tuning key %d / value %d", key, value);
     return FS2D_E_BADARG;
 }
@@ -295,11 +293,11 @@ int fs2d_jacobi_sweep(float *pn, const float *pc, const float *src, const uint8_
 
 // Decompose n_sweeps reference iterations into fused passes (size t >= 1, only sizes whose bit is set in
 // fuse_mask) and literal single iterations (size 0), cheapest first by a cost table measured on B200 at
-// 8192^2 cells (scripts/sweep_bench.py, us): the last two iterations are always literal and the
+// 8192^2 cells (scripts/sweep_bench.py, us): the last `tail_literal` iterations are literal and the
 // number of buffer flips (= number of entries) must have the parity of n_sweeps so that the two PHYSICAL
 // buffers end up exactly as in the reference.
 static int plan_jacobi(int n_sweeps, int fuse_mask, int *out, int cap, int tail_literal = 2) {
-    static const float pass_cost[13] = {0, 214, 237, 226, 245, 295, 340, 381, 420, 501, 547, 607, 655};   // variant 5
+    static const float pass_cost[13] = {0, 214, 237, 226, 245, 295, 340, 381, 420, 501, 547, 607, 655};
     const float lit_cost = 195.0f;
     const int n_lit = n_sweeps < tail_literal ? n_sweeps : tail_literal, n_f = n_sweeps - n_lit;
     int n = 0;
@@ -337,13 +335,13 @@ static int plan_jacobi(int n_sweeps, int fuse_mask, int *out, int cap, int tail_
     return n;
 }
 
-// The schedule of one update under the current tuning: with the experimental tail (fs2d_set_tuning(4, 1), variants >= 5) it
-// ends {..., fused pass that also emits the BC values of its penultimate state, ONE literal iteration} instead of
-// {..., two literal iterations}; see jacobi_fused5_body<.., EMIT>.  *tail = 1 if entry n - 2 is that emitting pass (if the
-// entry before the last one is itself a literal iteration, the usual reasoning applies unchanged).
+// The schedule of one update: it ends {..., fused pass that also emits the BC values of its penultimate state, ONE literal
+// iteration} (see jacobi_fused_body<EMIT>; measured 56 us faster per 80-iteration update at 8192^2) -- or, with
+// fs2d_set_tuning(4, 0), {..., two literal iterations}.  *tail = 1 if entry n - 2 is that emitting pass (if the entry
+// before the last one is itself a literal iteration, the usual reasoning applies unchanged).
 static int plan_with_tail(int n_sweeps, int fuse_mask, int *out, int cap, bool *tail) {
     int n = -1;
-    if (fs2d::g_tail_emit && fs2d::g_fused_variant >= 5 && fuse_mask != 0 && n_sweeps >= 3) n = plan_jacobi(n_sweeps, fuse_mask, out, cap, 1);
+    if (fs2d::g_tail_emit && fuse_mask != 0 && n_sweeps >= 3) n = plan_jacobi(n_sweeps, fuse_mask, out, cap, 1);
     *tail = n >= 2 && out[n - 2] > 0;
     if (n < 0) n = plan_jacobi(n_sweeps, fuse_mask, out, cap);
     return n;
@@ -360,10 +358,11 @@ int fs2d_jacobi_plan(int n_sweeps, int fuse_mask, int *sizes, int cap, int *n_en
 
 int fs2d_jacobi_update(float *pa, float *pb, const float *src, const uint8_t *pcode, fs2d_dom d, int n_sweeps,
                        const int32_t *tgt, const int32_t *src0, const int32_t *src1, const uint8_t *kind, float *scratch,
-                       int n_bc, int fuse_mask, int *final_in_b, void *stream) {
+                       int n_bc, int fuse_mask, const int32_t *const *orders, const int *n_orders, int *final_in_b, void *stream) {
     FS2D_REQUIRE(pa && pb && src && pcode && pa != pb, "null/aliased field pointer");
     FS2D_REQUIRE(n_sweeps >= 0 && fuse_mask >= 0, "negative sweep count");
     FS2D_REQUIRE(n_bc == 0 || (tgt && src0 && src1 && kind && scratch), "null BC table");
+    FS2D_REQUIRE(!orders || n_orders, "tile lists without their lengths");
     if (int e = check_dom(d)) return e;
     float *cur = pa, *nxt = pb;
     if (d.r1 == d.r0 || !fused_supported(pa, pb, src, pcode, d)) fuse_mask = 0;
@@ -374,7 +373,9 @@ int fs2d_jacobi_update(float *pa, float *pb, const float *src, const uint8_t *pc
     for (int k = 0; k < n; ++k) {
         if (plan[k] > 0) {
             // fused pass: plan[k] iterations in shared memory (fs2d_fused.cu)
-            if (int e = fused_pass(cur, nxt, src, pcode, d, plan[k], STREAM, 0, 0, tail && k == n - 2)) return e;
+            const int t = plan[k];
+            const int32_t *order = orders ? orders[t] : nullptr;
+            if (int e = fused_pass(cur, nxt, src, pcode, d, t, STREAM, 0, 0, tail && k == n - 2, order, order ? n_orders[t] : 0)) return e;
         } else {
             // literal reference iteration (fs/pressure_updater.py:57-60): in-place sparse BC, then the plain sweep
             launch_p_bc(cur, tgt, src0, src1, kind, scratch, n_bc, STREAM);

@@ -334,185 +334,4 @@ int stream_vort_apply(float *vn, float *w, float *wabs, const float *vc, const u
     return launch_stream(OpVort<false>{vn, w, wabs, dtw, DivC<false>(dx)}, fields, mask, d, s);
 }
 
-// =============================================================================================
-// EXPERIMENTAL (off by default, fs2d_cip_nonadv_fused): _non_advection_phase + _non_advection_phase_grad in ONE pass.
-//
-// fs/solver.py:216-217 runs two kernels: fn = fc + (-grad p + lap fc / Re) dt on the not-wall cells (:229-240), then
-// fxn = fxc + d/dx (fn - fc), fyn = fyc + d/dy (fn - fc) from fn at the four neighbours (:242-261).  Separately they move
-// 21 + 49 = 70 B/cell; fn at a neighbour is a function of fc and p one cell further out, so one kernel that recomputes
-// it on a one-cell ring around its tile moves 8 (fc) + 4 (p) + 16 (fxc, fyc) + 1 (mask) + 24 (fn, fxn, fyn) = 53 B/cell.
-//
-// Per tile (16 x 64 cells, TMA-fed stages like k_stream): phase 1 evaluates fn on the tile + ring (18 x 66 cells; a wall
-// cell keeps the value stored in the fn array -- never written by the reference kernel, SURVEY T1 -- which is read from
-// global memory) into a shared scratch tile and stores the tile's own not-wall cells (and those of the ring rows outside
-// [r0, r1) that the caller allows it to recompute: [ring_lo, ring_hi)); phase 2 forms the two gradients from the scratch tile.  Same per-cell functions and operation order as the two kernels: bit-identical results.
-// Reads outside the clamp window [clo, chi] x [0, Y-1] are clamped by index, so no halo repair is needed.
-// =============================================================================================
-constexpr int NFU_HR = 2;                                   // row halo of the fc / p boxes (ring 1 + its stencil)
-constexpr int NFU_ROWS = ST_TR + 2 * NFU_HR;                // 20
-constexpr int NFU_FC_BYTES = NFU_ROWS * 2 * ST_BC * 4;      // 11520
-constexpr int NFU_PC_BYTES = NFU_ROWS * ST_BC * 4;          // 5760
-constexpr int NFU_FX_BYTES = ST_TR * 2 * ST_TC * 4;         // 8192 (centre only)
-constexpr int NFU_MK_ROWS = ST_TR + 2, NFU_MK_COLS = ST_TC + 32;
-constexpr int NFU_OFF_PC = NFU_FC_BYTES;
-constexpr int NFU_OFF_FX = NFU_OFF_PC + NFU_PC_BYTES;
-constexpr int NFU_OFF_FY = NFU_OFF_FX + NFU_FX_BYTES;
-constexpr int NFU_OFF_MK = NFU_OFF_FY + NFU_FX_BYTES;
-constexpr int NFU_STAGE = ((NFU_OFF_MK + NFU_MK_ROWS * NFU_MK_COLS + 127) / 128) * 128;
-constexpr uint32_t NFU_TX = NFU_FC_BYTES + NFU_PC_BYTES + 2 * NFU_FX_BYTES + NFU_MK_ROWS * NFU_MK_COLS;
-constexpr int NFU_SC_ROWS = ST_TR + 2, NFU_SC_COLS = ST_TC + 2;   // fn scratch: tile + ring
-static_assert(NFU_FC_BYTES % 128 == 0 && NFU_PC_BYTES % 128 == 0 && NFU_FX_BYTES % 128 == 0, "TMA destinations are 128-byte aligned");
-
-struct NfuMaps {
-    CUtensorMap fc, pc, fx, fy, mask;
-};
-// clamped neighbourhood of the cell (r, j) inside the fc / p boxes of a stage (box element (0, 0) = cell (br0, bc0))
-struct NfuAt {
-    int r, j, br0, bc0, clo, chi, ymax;
-    __device__ __forceinline__ int row(int dr) const { return min(max(r + dr, clo), chi) - br0; }
-    __device__ __forceinline__ int col(int dc) const { return min(max(j + dc, 0), ymax) - bc0; }
-    __device__ __forceinline__ float ld1(const float *f, int dr, int dc) const { return f[row(dr) * ST_BC + col(dc)]; }
-    __device__ __forceinline__ float2 ld2(const float *f, int dr, int dc) const {
-        return *reinterpret_cast<const float2 *>(f + row(dr) * (2 * ST_BC) + 2 * col(dc));
-    }
-};
-
-template <bool P2, int STAGES, int MIN_CTAS>
-__global__ void __launch_bounds__(256, MIN_CTAS)
-    k_nonadv_fused(const __grid_constant__ NfuMaps maps, float *__restrict__ fn, float *__restrict__ fxn, float *__restrict__ fyn,
-                   const fs2d_dom d, const StreamGeom g, float dt, float re, DivC<P2> ddx, DivC<P2> ddx2, DivC<P2> d2dx,
-                   int ring_lo, int ring_hi) {
-    extern __shared__ __align__(1024) uint8_t nf_sm[];
-    __shared__ __align__(8) uint64_t full[STAGES];
-    float2 *scratch = reinterpret_cast<float2 *>(nf_sm + (size_t)STAGES * NFU_STAGE);
-    const int tid = threadIdx.x;
-    const int tx = tid % ST_TC, ty = tid / ST_TC;
-
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s) st_mbar_init(&full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int first = blockIdx.x, step = gridDim.x;
-
-#define NFU_ISSUE(tile_, stage_)                                                                          \
-    do {                                                                                                  \
-        const int R0_ = d.r0 + ((tile_) / g.tiles_j) * ST_TR, C0_ = ((tile_) % g.tiles_j) * ST_TC;        \
-        uint8_t *b_ = nf_sm + (size_t)(stage_) * NFU_STAGE;                                               \
-        st_mbar_expect(&full[stage_], NFU_TX);                                                            \
-        st_tma_2d(b_, &maps.fc, 2 * (C0_ - ST_HC), R0_ - NFU_HR, &full[stage_]);                          \
-        st_tma_2d(b_ + NFU_OFF_PC, &maps.pc, C0_ - ST_HC, R0_ - NFU_HR, &full[stage_]);                   \
-        st_tma_2d(b_ + NFU_OFF_FX, &maps.fx, 2 * C0_, R0_, &full[stage_]);                                \
-        st_tma_2d(b_ + NFU_OFF_FY, &maps.fy, 2 * C0_, R0_, &full[stage_]);                                \
-        st_tma_2d(b_ + NFU_OFF_MK, &maps.mask, C0_ - 16, R0_ - 1, &full[stage_]);                         \
-    } while (0)
-
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES - 1; ++s)
-            if (first + s * step < g.n_tiles) NFU_ISSUE(first + s * step, s);
-    }
-    int k = 0;
-    for (int tile = first; tile < g.n_tiles; tile += step, ++k) {
-        const int stage = k % STAGES;
-        if (tid == 0) {   // refill the stage the previous tile has released (all threads passed its closing barrier)
-            const int ahead = tile + (STAGES - 1) * step;
-            if (ahead < g.n_tiles) NFU_ISSUE(ahead, (k + STAGES - 1) % STAGES);
-        }
-        const int R0 = d.r0 + (tile / g.tiles_j) * ST_TR, C0 = (tile % g.tiles_j) * ST_TC;
-        const uint8_t *base = nf_sm + (size_t)stage * NFU_STAGE;
-        const float *s_fc = reinterpret_cast<const float *>(base);
-        const float *s_pc = reinterpret_cast<const float *>(base + NFU_OFF_PC);
-        const float2 *s_fx = reinterpret_cast<const float2 *>(base + NFU_OFF_FX);
-        const float2 *s_fy = reinterpret_cast<const float2 *>(base + NFU_OFF_FY);
-        const uint8_t *s_mk = base + NFU_OFF_MK;
-        st_mbar_wait(&full[stage], (uint32_t)((k / STAGES) & 1));
-
-        // ---- phase 1: fn on the tile and its one-cell ring (cells inside the clamp window only) ---------------------
-        for (int e = tid; e < NFU_SC_ROWS * NFU_SC_COLS; e += 256) {
-            const int lr = e / NFU_SC_COLS, lc = e - lr * NFU_SC_COLS;
-            const int r = R0 - 1 + lr, j = C0 - 1 + lc;
-            if (r < d.clo || r > d.chi || j < 0 || j >= d.Y) continue;   // never read: neighbour reads are clamped
-            const size_t idx = (size_t)r * d.Y + j;
-            float2 val;
-            if (s_mk[lr * NFU_MK_COLS + lc + 15] == 1 || r < ring_lo || r >= ring_hi) {
-                // a wall cell, or a row outside [ring_lo, ring_hi) -- the rows whose fn this call may recompute: the value
-                // stored in fn (never written here), exactly what the separate gradient kernel would read
-                val = reinterpret_cast<const float2 *>(fn)[idx];
-            } else {
-                const NfuAt at{r, j, R0 - NFU_HR, C0 - ST_HC, d.clo, d.chi, d.Y - 1};
-                val = c_cip_nonadv<P2>(l_cip_nonadv(at, s_fc, s_pc), dt, ddx, ddx2, re);
-                // stored by the tile that owns the cell's column: its own rows inside [r0, r1), and the ring rows outside it
-                const bool own_row = lr >= 1 && lr <= ST_TR && r < d.r1;
-                if (lc >= 1 && lc <= ST_TC && (own_row || r < d.r0 || r >= d.r1)) reinterpret_cast<float2 *>(fn)[idx] = val;
-            }
-            scratch[lr * NFU_SC_COLS + lc] = val;
-        }
-        __syncthreads();
-
-        // ---- phase 2: the gradients of (fn - fc) on the tile's not-wall cells ----------------------------------------
-        const int j = C0 + tx;
-        if (j < d.Y) {
-#pragma unroll
-            for (int u = 0; u < ST_TR / 4; ++u) {
-                const int lr = ty + 4 * u, r = R0 + lr;
-                if (r >= d.r1 || s_mk[(lr + 1) * NFU_MK_COLS + tx + 16] == 1) continue;
-                const NfuAt at{r, j, R0 - NFU_HR, C0 - ST_HC, d.clo, d.chi, d.Y - 1};
-                // scratch coordinates of the clamped neighbours (scratch element (0, 0) = cell (R0 - 1, C0 - 1))
-                const int rp = min(r + 1, d.chi) - (R0 - 1), rm = max(r - 1, d.clo) - (R0 - 1), rc = lr + 1;
-                const int cp = min(j + 1, d.Y - 1) - (C0 - 1), cm = max(j - 1, 0) - (C0 - 1), cc = tx + 1;
-                const float2 gx = scratch[rp * NFU_SC_COLS + cc] - at.ld2(s_fc, +1, 0) - scratch[rm * NFU_SC_COLS + cc] + at.ld2(s_fc, -1, 0);
-                const float2 gy = scratch[rc * NFU_SC_COLS + cp] - at.ld2(s_fc, 0, +1) - scratch[rc * NFU_SC_COLS + cm] + at.ld2(s_fc, 0, -1);
-                const size_t idx = (size_t)r * d.Y + j;
-                reinterpret_cast<float2 *>(fxn)[idx] = s_fx[lr * ST_TC + tx] + d2dx(gx);
-                reinterpret_cast<float2 *>(fyn)[idx] = s_fy[lr * ST_TC + tx] + d2dx(gy);
-            }
-        }
-        __syncthreads();   // the stage may be refilled and the scratch tile overwritten
-    }
-#undef NFU_ISSUE
-}
-
-template <bool P2>
-static int launch_nonadv_fused(float *fn, float *fxn, float *fyn, const float *fc, const float *fxc, const float *fyc,
-                               const float *pc, const uint8_t *mask, const fs2d_dom &d, float dt, float dx, float re, float two_dx,
-                               int ring_lo, int ring_hi, cudaStream_t s) {
-    constexpr int STAGES = 2, MIN_CTAS = 2;
-    constexpr int SMEM = STAGES * NFU_STAGE + NFU_SC_ROWS * NFU_SC_COLS * 8;
-    static int n_sm = 0;
-    static bool attr_set = false;
-    if (!n_sm) {
-        int dev = 0;
-        FS2D_CUDA_CHECK(cudaGetDevice(&dev));
-        FS2D_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    }
-    if (!attr_set) {
-        FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_nonadv_fused<P2, STAGES, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        attr_set = true;
-    }
-    NfuMaps maps;
-    if (int e = make_map(&maps.fc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, fc, 2ull * d.Y, d.rows, 2 * ST_BC, NFU_ROWS)) return e;
-    if (int e = make_map(&maps.pc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pc, d.Y, d.rows, ST_BC, NFU_ROWS)) return e;
-    if (int e = make_map(&maps.fx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, fxc, 2ull * d.Y, d.rows, 2 * ST_TC, ST_TR)) return e;
-    if (int e = make_map(&maps.fy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, fyc, 2ull * d.Y, d.rows, 2 * ST_TC, ST_TR)) return e;
-    if (int e = make_map(&maps.mask, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, mask, d.Y, d.rows, NFU_MK_COLS, NFU_MK_ROWS)) return e;
-    StreamGeom g;
-    g.tiles_j = (d.Y + ST_TC - 1) / ST_TC;
-    g.n_tiles = g.tiles_j * ((d.r1 - d.r0 + ST_TR - 1) / ST_TR);
-    const int grid = g.n_tiles < MIN_CTAS * n_sm ? g.n_tiles : MIN_CTAS * n_sm;
-    ++g_launches;
-    k_nonadv_fused<P2, STAGES, MIN_CTAS><<<grid, 256, SMEM, s>>>(maps, fn, fxn, fyn, d, g, dt, re, DivC<P2>(dx), DivC<P2>(dx * dx),
-                                                                DivC<P2>(two_dx), ring_lo, ring_hi);
-    return FS2D_OK;
-}
-
-int stream_cip_nonadv_fused(float *fn, float *fxn, float *fyn, const float *fc, const float *fxc, const float *fyc, const float *pc,
-                            const uint8_t *mask, const fs2d_dom &d, float dt, float dx, float re, float two_dx, int ring_lo,
-                            int ring_hi, cudaStream_t s) {
-    if (is_pow2(dx) && is_pow2(two_dx))
-        return launch_nonadv_fused<true>(fn, fxn, fyn, fc, fxc, fyc, pc, mask, d, dt, dx, re, two_dx, ring_lo, ring_hi, s);
-    return launch_nonadv_fused<false>(fn, fxn, fyn, fc, fxc, fyc, pc, mask, d, dt, dx, re, two_dx, ring_lo, ring_hi, s);
-}
-
 }  // namespace fs2d

@@ -43,7 +43,6 @@ _SIGNATURES = {
     "fs2d_mac_update": (c_int, [_P, _P, _P, _P, Dom, c_float, c_float, c_float, c_int, _P]),
     "fs2d_cip_nonadv": (c_int, [_P, _P, _P, _P, Dom, c_float, c_float, c_float, _P]),
     "fs2d_cip_nonadv_grad": (c_int, [_P, _P, _P, _P, _P, _P, _P, Dom, c_float, _P]),
-    "fs2d_cip_nonadv_fused": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, Dom, c_float, c_float, c_float, c_float, c_int, c_int, _P]),
     "fs2d_cip_advect": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, Dom, c_float, c_float, c_float, c_float, _P]),
     "fs2d_set_grad": (c_int, [_P, _P, _P, Dom, c_float, _P]),
     "fs2d_vort_calc": (c_int, [_P, _P, _P, _P, Dom, c_float, _P]),
@@ -53,11 +52,13 @@ _SIGNATURES = {
     "fs2d_pressure_source_vmax": (c_int, [_P, _P, Dom, c_float, c_float, _P, c_int, _P]),
     "fs2d_limit_if": (c_int, [_P, Dom, c_float, _P, _P]),
     "fs2d_jacobi_sweep": (c_int, [_P, _P, _P, _P, Dom, c_int, _P]),
-    "fs2d_jacobi_update": (c_int, [_P, _P, _P, _P, Dom, c_int, _P, _P, _P, _P, _P, c_int, c_int, POINTER(c_int), _P]),
+    "fs2d_jacobi_update": (c_int, [_P, _P, _P, _P, Dom, c_int, _P, _P, _P, _P, _P, c_int, c_int, POINTER(_P), POINTER(c_int),
+                                   POINTER(c_int), _P]),
+    "fs2d_fused_order": (c_int, [_P, Dom, c_int, c_int, c_int, _P, c_int, POINTER(c_int), _P]),
     "fs2d_jacobi_plan": (c_int, [c_int, c_int, POINTER(c_int), c_int, POINTER(c_int)]),
-    "fs2d_jacobi_fused": (c_int, [_P, _P, _P, _P, Dom, c_int, _P]),
-    "fs2d_jacobi_fused_part": (c_int, [_P, _P, _P, _P, Dom, c_int, c_int, c_int, _P]),
-    "fs2d_jacobi_fused_tail": (c_int, [_P, _P, _P, _P, Dom, c_int, c_int, c_int, _P]),
+    "fs2d_jacobi_fused": (c_int, [_P, _P, _P, _P, Dom, c_int, _P, c_int, _P]),
+    "fs2d_jacobi_fused_part": (c_int, [_P, _P, _P, _P, Dom, c_int, c_int, c_int, _P, c_int, _P]),
+    "fs2d_jacobi_fused_tail": (c_int, [_P, _P, _P, _P, Dom, c_int, c_int, c_int, _P, c_int, _P]),
     "fs2d_fused_tile": (c_int, [c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "fs2d_rbsor_pass": (c_int, [_P, _P, _P, _P, Dom, c_float, c_float, c_int, _P]),
     "fs2d_limit": (c_int, [_P, Dom, c_float, _P]),

@@ -54,6 +54,7 @@ class BoundaryCondition:
         self._pcode = local(_bc_tables.pack_pcode(pcode), _bc_tables.PC_W_NONE)
         self._pcode_global = pcode           # unpacked codes of the whole grid (fused-kernel validity analysis)
         self._fused_ok: dict[int, bool] = {}
+        self._fused_orders: dict[tuple, tuple] = {}
         self._bc_const = local(torch.from_numpy(bc_const).to(self.device))
         # BC targets: owned rows plus the halo rows whose sources are inside the window
         tl, th = max(lo, g0 - max(self.halo - 2, 0)), min(hi, g1 + max(self.halo - 2, 0))
@@ -124,6 +125,27 @@ class BoundaryCondition:
                                                 fresh_below=T if self.partition.has_upper else None))
             self._fused_ok[key] = bool(ok)
         return self._fused_ok[key]
+
+    def fused_order(self, T: int, dom=None, skip: tuple[int, int] | None = None) -> tuple[torch.Tensor, int]:
+        """Tile list of one fused-pass geometry (fs2d_fused_order): (device int32 tensor, entries).  The class of a tile
+        -- open fluid / BC cells or edges / nothing to store -- depends on pcode and the geometry only, so it is built once
+        per (T, row window, skipped tile rows) and handed to every pass of that shape."""
+        import ctypes
+
+        d = dom or self.dom
+        first, n = skip if skip is not None else (0, 0)
+        key = (T, d.r0, d.r1, d.clo, d.chi, first, n)
+        if key not in self._fused_orders:
+            rows, cols, hr, hc, tmax = (ctypes.c_int() for _ in range(5))
+            _lib.call("fs2d_fused_tile", T, ctypes.byref(rows), ctypes.byref(cols), ctypes.byref(hr), ctypes.byref(hc),
+                      ctypes.byref(tmax))
+            ti, tj = rows.value - 2 * hr.value, cols.value - 2 * hc.value
+            cap = max(1, -(-(d.r1 - d.r0) // ti) * -(-d.Y // tj))
+            order = torch.empty(cap, dtype=torch.int32, device=self.device)
+            counts = (ctypes.c_int * 3)()
+            _lib.call("fs2d_fused_order", _lib.ptr(self._pcode), d, T, first, n, _lib.ptr(order), cap, counts, _lib.stream())
+            self._fused_orders[key] = (order, int(counts[0]), int(counts[1]), int(counts[2]))
+        return self._fused_orders[key][:2]
 
     def stale_cells_agree(self, a: Field, b: Field) -> bool:
         """True if the never-written wall cells read by relaxed neighbours hold equal values in both

@@ -223,32 +223,11 @@ def cip_update_distributed(s) -> None:
     bc = s._bc
     hx = exchanger_for(bc)
     v, vx, vy, p = s.v, s.vx, s.vy, s.p
-    if s.fused_non_advection and bc.halo >= 2:
-        # EXPERIMENTAL (off by default): both non-advection kernels in one pass.  fn on the first halo row of each side is
-        # recomputed (and stored) from two fresh halo rows of v and p.  Its WALL cells are never written by any kernel and
-        # are read by the advection phase, so the neighbour's row of v.next still travels -- in the same NCCL
-        # group as p and before the kernel writes its not-wall cells: one exchange instead of two.
-        _velocity_bc(bc, hx, v.current, 2)
-        d = bc.dom
-        lo, hi = max(d.r0 - 1, d.clo), min(d.r1 + 1, d.chi + 1)
-        if d.r1 - d.r0 < 24:
-            hx.finish(hx.start([(p.current, 2), (v.next, 1)]))
-            s._non_advection_fused(lo, hi)
-        else:
-            reqs = hx.start([(p.current, 2), (v.next, 1)])
-            with _rows(bc, d.r0 + 2, d.r1 - 2):     # with its ring rows r0 + 1 and r1 - 2 it reads the rows [r0, r1) only
-                s._non_advection_fused(d.r0 + 1, d.r1 - 1)
-            hx.finish(reqs)
-            with _rows(bc, d.r0, d.r0 + 2):
-                s._non_advection_fused(lo, d.r0 + 3)
-            with _rows(bc, d.r1 - 2, d.r1):
-                s._non_advection_fused(d.r1 - 3, hi)
-    else:
-        _velocity_bc(bc, hx, v.current, 1)
-        # every exchange below is hidden behind the interior rows of the kernel that needs it (_overlapped)
-        _overlapped(bc, hx, [(p.current, 1)], lambda: s._non_advection_phase(v.next, v.current, p.current), 1)
-        _overlapped(bc, hx, [(v.next, 1)],            # fn(i+-1, j) of the grad kernel
-                    lambda: s._non_advection_phase_grad(vx.next, vy.next, vx.current, vy.current, v.current, v.next), 1)
+    _velocity_bc(bc, hx, v.current, 1)
+    # every exchange below is hidden behind the interior rows of the kernel that needs it (_overlapped)
+    _overlapped(bc, hx, [(p.current, 1)], lambda: s._non_advection_phase(v.next, v.current, p.current), 1)
+    _overlapped(bc, hx, [(v.next, 1)],            # fn(i+-1, j) of the grad kernel
+                lambda: s._non_advection_phase_grad(vx.next, vy.next, vx.current, vy.current, v.current, v.next), 1)
     v.swap(); vx.swap(); vy.swap()
     _overlapped(bc, hx, [(vx.current, 1), (vy.current, 1)],   # CIP reads f, fx, fy at the upwind row i_m = i +- 1
                 lambda: s._advection_phase(v.next, vx.next, vy.next, v.current, vx.current, vy.current, v.current), 1)

@@ -111,6 +111,18 @@ class JacobiPressureUpdater(PressureUpdater):
             p.current.dirty = p.next.dirty = False
         return self._agreed_mask
 
+    def _orders(self, mask: int):
+        """Host arrays (indexed by pass size) of the tile lists fs2d_jacobi_update hands to its fused passes."""
+        key = (mask, self._bc.dom.r0, self._bc.dom.r1)
+        if getattr(self, "_orders_key", None) != key:
+            ptrs, counts = (ctypes.c_void_p * 13)(), (ctypes.c_int * 13)()
+            for t in range(1, 13):
+                if (mask >> t) & 1:
+                    order, n = self._bc.fused_order(t)
+                    ptrs[t], counts[t] = _lib.ptr(order), n
+            self._orders_key, self._orders_val = key, (ptrs, counts)
+        return self._orders_val
+
     def plan(self, p: DoubleBuffer) -> list[int]:
         """Schedule of one update: fused pass sizes (> 0) and literal iterations (0), fs2d_jacobi_plan."""
         cap = self._n_iter + 4
@@ -123,16 +135,17 @@ class JacobiPressureUpdater(PressureUpdater):
         window's tiling to another launch (fs2d_jacobi_fused_part); emit: the experimental tail pass that also stores the BC
         values of its penultimate state into the wall cells of p_current (fs2d_jacobi_fused_tail)."""
         bc = self._bc
+        order, n_order = bc.fused_order(t, dom, skip)
         if emit:
             first, n = skip if skip is not None else (0, 0)
             _lib.call("fs2d_jacobi_fused_tail", p_next.ptr(), p_current.ptr(), src.ptr(), _lib.ptr(bc._pcode), dom or bc.dom, t,
-                      first, n, _lib.stream())
+                      first, n, _lib.ptr(order), n_order, _lib.stream())
         elif skip is None:
             _lib.call("fs2d_jacobi_fused", p_next.ptr(), p_current.ptr(), src.ptr(), _lib.ptr(bc._pcode), dom or bc.dom, t,
-                      _lib.stream())
+                      _lib.ptr(order), n_order, _lib.stream())
         else:
             _lib.call("fs2d_jacobi_fused_part", p_next.ptr(), p_current.ptr(), src.ptr(), _lib.ptr(bc._pcode), dom or bc.dom,
-                      t, skip[0], skip[1], _lib.stream())
+                      t, skip[0], skip[1], _lib.ptr(order), n_order, _lib.stream())
 
     def update(self, p: DoubleBuffer, v_current: Field) -> None:
         bc = self._bc
@@ -144,9 +157,11 @@ class JacobiPressureUpdater(PressureUpdater):
         src = self._source(v_current)
         t = bc._p_table
         final_in_b = ctypes.c_int(0)
+        mask = self.fuse_mask(p)
+        orders, n_orders = self._orders(mask)
         _lib.call("fs2d_jacobi_update", p.current.ptr(), p.next.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom,
                   self._n_iter, _lib.ptr(t["tgt"]), _lib.ptr(t["src0"]), _lib.ptr(t["src1"]), _lib.ptr(t["kind"]),
-                  _lib.ptr(bc._scratch), t["n"], self.fuse_mask(p), ctypes.byref(final_in_b), _lib.stream())
+                  _lib.ptr(bc._scratch), t["n"], mask, orders, n_orders, ctypes.byref(final_in_b), _lib.stream())
         if final_in_b.value:
             p.swap()  # n_iter odd: same net effect as the reference's n_iter swaps
 

@@ -153,28 +153,12 @@ class CipMacSolver(Solver):
         bc = self._bc
         _lib.call("fs2d_set_grad", fx.ptr(), fy.ptr(), f.ptr(), bc.dom, self.dx, _lib.stream())
 
-    #: EXPERIMENTAL, off by default: run the two non-advection kernels as ONE pass over HBM (fs2d_cip_nonadv_fused; same
-    #: results bit for bit, 53 instead of 70 B/cell; on strips also one halo exchange fewer).  Verified on the CPU emulation of the kernel
-    #: sources (tests/test_kernels_emulated.py); not yet measured on a B200.
-    fused_non_advection = False
-
     def _update_velocities(self, v: DoubleBuffer, vx: DoubleBuffer, vy: DoubleBuffer, p: DoubleBuffer) -> None:
-        if self.fused_non_advection and self._bc.partition.world == 1:
-            self._non_advection_fused(self._bc.dom.r0, self._bc.dom.r1)
-        else:
-            self._non_advection_phase(v.next, v.current, p.current)
-            self._non_advection_phase_grad(vx.next, vy.next, vx.current, vy.current, v.current, v.next)
+        self._non_advection_phase(v.next, v.current, p.current)
+        self._non_advection_phase_grad(vx.next, vy.next, vx.current, vy.current, v.current, v.next)
         v.swap(); vx.swap(); vy.swap()
         self._advection_phase(v.next, vx.next, vy.next, v.current, vx.current, vy.current, v.current)
         v.swap(); vx.swap(); vy.swap()
-
-    def _non_advection_fused(self, ring_lo: int, ring_hi: int) -> None:
-        """both non-advection kernels in one pass on the rows of bc.dom (fs2d_cip_nonadv_fused); fn of the rows
-        [ring_lo, ring_hi) outside that window is recomputed, of all other rows read as stored"""
-        bc, v, vx, vy, p = self._bc, self.v, self.vx, self.vy, self.p
-        _lib.call("fs2d_cip_nonadv_fused", v.next.ptr(), vx.next.ptr(), vy.next.ptr(), v.current.ptr(), vx.current.ptr(),
-                  vy.current.ptr(), p.current.ptr(), _lib.ptr(bc._bc_mask), bc.dom, self.dt, self.dx, self.re, 2.0 * self.dx,
-                  ring_lo, ring_hi, _lib.stream())
 
     def _non_advection_phase(self, fn: Field, fc: Field, pc: Field) -> None:
         bc = self._bc

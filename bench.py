@@ -56,6 +56,9 @@ def parse() -> argparse.Namespace:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-config", action="store_true", help="skip the BASELINE configs[1] side measurement (N=1)")
     ap.add_argument("--cpu-sample-rows", type=int, default=1024, help="rows of the CPU-baseline sample grid")
+    ap.add_argument("--state", choices=["quiescent", "developed", "both"], default="both",
+                    help="initial state of the device-resident timing: the reference's all-zero start (the headline `value`), "
+                         "seeded non-uniform fields (`developed`), or both (default; the second one as value_developed_state)")
     ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3, 5],
                     help="run a BASELINE.json config on its own grid instead of the headline workload: 2 = bc2 res=2048 Re=1e4 "
                          "80 sweeps, 3 = bc3 res=4096 Re=1e8 vc=10 100 sweeps, 5 = bc5 res=16384 Re=1e6 200 sweeps (rows split over --gpus)")
@@ -78,13 +81,77 @@ def peaks() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def kernel_source_sha256() -> str:
+    """identity of the dominant kernel's source: an ncu capture only describes the code it was taken from"""
+    import hashlib
+
+    h = hashlib.sha256()
+    for name in ("fs2d_fused.cu", "fs2d_common.cuh"):
+        h.update((REPO / "2d-fluid-simulator_b200" / "csrc" / name).read_bytes())
+    return h.hexdigest()
+
+
 def traffic_from_profile():
-    """dram__bytes_read+write per launch of the dominant kernel from the committed ncu capture (profiles/)."""
+    """dram__bytes_read+write per launch of the dominant kernel (and of a whole step) from the committed ncu capture
+    (profiles/dominant_kernel_traffic.json, written by scripts/summarize_profiles.py).  The capture records the hash of the
+    kernel sources it profiled; a capture of other code is refused (None) instead of silently going stale."""
     f = REPO / "profiles" / "dominant_kernel_traffic.json"
     try:
-        return json.loads(f.read_text())
+        t = json.loads(f.read_text())
     except Exception:  # noqa: BLE001
         return None
+    if t.get("source_sha256") != kernel_source_sha256():
+        return {"stale": True, "note": f"{f.name} was captured from other kernel sources ({str(t.get('source_sha256'))[:12]}..., "
+                                        f"now {kernel_source_sha256()[:12]}...): re-run scripts/gpu_ncu_step.sh"}
+    return t
+
+
+def pin_to_gpu_numa(local_rank: int) -> dict:
+    """CPU affinity of this rank = the NUMA node its GPU hangs off, set BEFORE pinned host buffers are allocated (first touch
+    puts them on that node): at N = 8 the host->device streams of the e2e leg otherwise share one root complex."""
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        node = int(Path(f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node").read_text())
+        if node < 0:
+            return {"numa_node": None}
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception as e:  # noqa: BLE001
+        return {"numa_node": None, "error": f"{type(e).__name__}: {e}"[:120]}
+
+
+def developed_like_state(solver, seed: int = 0) -> None:
+    """Non-uniform fields in every buffer (smooth structures of a few dozen cells plus cell-scale noise; both signs of both
+    velocity components): the instruction paths a developed flow takes -- non-zero Laplacians, vorticity gradients and source
+    terms, all four CIP upwind directions -- instead of the exactly uniform regions of a quiescent start (fdiv_z's zero
+    dividends, the confinement NaN rule).  A real developed flow at 8192^2 is out of reach (CFL 0.05: 1e5+ steps)."""
+    import torch
+
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1234 + seed)
+    for name, amp in (("v", 1.0), ("vx", 8.0), ("vy", 8.0), ("p", 0.5)):
+        buf = getattr(solver, name)
+        for f in (buf.current, buf.next):
+            t = f.tensor
+            shape = t.shape if t.dim() == 3 else t.shape + (1,)
+            coarse = torch.rand((1, shape[2], shape[0] // 32 + 2, shape[1] // 32 + 2), device=t.device, generator=g) * 2 - 1
+            smooth = torch.nn.functional.interpolate(coarse, size=(shape[0], shape[1]), mode="bilinear", align_corners=False)[0]
+            smooth = smooth.permute(1, 2, 0).reshape(t.shape)
+            t.copy_(amp * (smooth + 0.05 * (torch.rand(t.shape, device=t.device, generator=g) * 2 - 1)))
+            del coarse, smooth
+            f.dirty = True
+    buf = solver.p                      # the never-written wall cells of the two pressure buffers must agree for fused passes
+    buf.next.tensor.copy_(buf.current.tensor)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -139,27 +206,97 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm / cpu_baseline (the oracle; the only place bench.py executes oracle/)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference(rows: int, cols: int, n_jacobi: int, steps: int, warmup: int) -> dict:
+def taichi_reference(rows: int, cols: int, n_jacobi: int, steps: int, warmup: int, repeats: int):
+    """The reference ITSELF under a real Taichi runtime (`ti.init(arch=ti.cpu)`, /root/reference/main.py:65-66), when both can be
+    imported on this box: taichi, and the reference's `fs` package from baseline/_ref (or $FS2D_REFERENCE_DIR).  Neither exists
+    in the build container nor on the pod's GPU boxes (taichi==1.7.4 has no wheel in /opt/wheelhouse, requires-python >= 3.13;
+    `pip install --target baseline/_ref /root/reference` fails at metadata generation -- DESIGN.md), so this returns None and the
+    oracle port below is timed instead.  When it fires, the line says kind "taichi" and the first step is also compared with the
+    oracle (the shim's lowering choices: fast_math, NaN min/max -- SURVEY T2/T5)."""
+    ref_dir = os.environ.get("FS2D_REFERENCE_DIR") or str(REPO / "baseline" / "_ref")
+    if not (Path(ref_dir) / "fs" / "solver.py").exists():
+        return None
+    try:
+        import taichi as ti
+    except Exception:  # noqa: BLE001
+        return None
+    import numpy as np
+
+    from fs.boundary_condition import build_scene as our_scene
+    from oracle import oracle as orc
+
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "fs" or k.startswith("fs.")}
+    sys.path.insert(0, ref_dir)
+    try:
+        ti.init(arch=ti.cpu)
+        from fs.boundary_condition import BoundaryCondition as RefBC      # the reference's own classes from here on
+        from fs.pressure_updater import JacobiPressureUpdater as RefJacobi
+        from fs.solver import CipMacSolver as RefCip
+        from fs.vorticity_confinement import VorticityConfinement as RefVC
+
+        const, mask = our_scene(SCENE, rows, cols)
+        dt, dx = 0.05 / Y_COLS, 1.0 / Y_COLS
+        bc = RefBC(const, mask)
+        solver = RefCip(bc, RefJacobi(bc, dt, dx, n_jacobi), dt, dx, RE, RefVC(bc, dt, dx, VC))
+        solver.update()
+        ti.sync()
+        check = orc.OracleSolver(mask, const, dt, dx, RE, SCHEME, VC, ("jacobi", n_jacobi))
+        check.update()
+        v_ref, v_orc = solver.v.current.to_numpy(), check.v.current
+        agree = {"max_abs_diff_v_step1": float(np.nanmax(np.abs(v_ref - v_orc))), "bit_identical_v_step1": bool(np.array_equal(v_ref, v_orc, equal_nan=True))}
+        for _ in range(max(warmup, 4)):          # every ti.template() kernel is specialised per field tuple: A/B swaps compile twice
+            solver.update()
+        ti.sync()
+        rates = []
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                solver.update()
+            ti.sync()
+            rates.append(rows * cols * steps / (time.perf_counter() - t0))
+        v = statistics.median(rates)
+        return {"value": v, "unit": "cell-updates/s", "cores": os.cpu_count() or 1, "kind": "taichi",
+                "sample": f"the reference's CipMacSolver + JacobiPressureUpdater({n_jacobi}) under taichi {ti.__version__} arch=cpu on a "
+                          f"{rows}x{cols} grid, median of {repeats} x {steps} steps; vs oracle after step 1: {agree}",
+                "ms_per_step": rows * cols / v * 1e3, "repeat_values": rates}
+    except Exception as e:  # noqa: BLE001
+        print(f"[bench] taichi reference unavailable: {type(e).__name__}: {e}", file=sys.stderr)
+        return None
+    finally:
+        sys.path.remove(ref_dir)
+        for k in [k for k in sys.modules if k == "fs" or k.startswith("fs.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def cpu_reference(rows: int, cols: int, n_jacobi: int, steps: int, warmup: int, repeats: int = 3) -> dict:
+    """The reference's CPU path on `rows x cols` cells of the workload: real Taichi if this box has it (see above), else the
+    C/OpenMP oracle port on ALL host cores.  The team size is set through the OpenMP runtime: torch.distributed.run exports
+    OMP_NUM_THREADS=1 to every rank, which starved this arm at N > 1 in round 1."""
+    r = taichi_reference(rows, cols, n_jacobi, steps, warmup, repeats)
+    if r is not None:
+        return r
     from fs.boundary_condition import build_scene
     from oracle import oracle as orc
 
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = orc.set_threads(os.cpu_count() or 1)
     const, mask = build_scene(SCENE, rows, cols)
     dt, dx = 0.05 / Y_COLS, 1.0 / Y_COLS
     s = orc.OracleSolver(mask, const, dt, dx, RE, SCHEME, VC, ("jacobi", n_jacobi))
     for _ in range(warmup):
         s.update()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        s.update()
-    t = time.perf_counter() - t0
-    cells = rows * cols
-    return {"value": cells * steps / t, "unit": "cell-updates/s", "cores": cores, "kind": "port",
-            "sample": f"CPU oracle (C/OpenMP restatement of the reference's Taichi kernels; Taichi itself is not "
-                      f"installable offline), same scene/scheme/{n_jacobi} sweeps on a {rows}x{cols} grid, "
-                      f"{steps} steps after {warmup} warm-up, {t / steps * 1e3:.0f} ms/step",
-            "ms_per_step": t / steps * 1e3}
+    rates = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            s.update()
+        rates.append(rows * cols * steps / (time.perf_counter() - t0))
+    v = statistics.median(rates)
+    return {"value": v, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+            "sample": f"CPU oracle (C/OpenMP restatement of the reference's Taichi kernels; Taichi itself is not installable "
+                      f"offline), {cores} OpenMP threads, same scene/scheme/{n_jacobi} sweeps on a {rows}x{cols} grid, median of "
+                      f"{repeats} x {steps} steps after {warmup} warm-up, {rows * cols / v * 1e3:.0f} ms/step on that grid",
+            "ms_per_step": rows * cols / v * 1e3, "repeat_values": rates}
 
 
 def run_reference(a: argparse.Namespace) -> None:
@@ -168,11 +305,17 @@ def run_reference(a: argparse.Namespace) -> None:
         return
     rows = min(a.cpu_sample_rows, a.rows_per_gpu * a.gpus)
     r = cpu_reference(rows, a.cols, a.jacobi, a.steps, a.warmup)
+    cfg = workload_config(a, a.gpus)
+    # what was actually timed: a bounded sample of the workload; the value is a per-cell rate, so the full grid's step time is
+    # sample ms/step x (global cells / sample cells)
+    cfg["reference_sample"] = {"rows": rows, "cols": a.cols, "cells": rows * a.cols, "extrapolation": "per cell (cell-updates/s)",
+                               "ms_per_step_on_sample": r["ms_per_step"],
+                               "ms_per_step_extrapolated_to_global_grid": r["ms_per_step"] * (a.rows_per_gpu * a.gpus) / rows}
     line = {"impl": "reference", "metric": "cell-updates/s", "value": r["value"], "unit": "cell-updates/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(a, a.gpus), "gpu_launches": 0,
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "config": cfg, "gpu_launches": 0,
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "repeat_values")},
             "e2e": {"value": r["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -239,17 +382,13 @@ def run_ours(a: argparse.Namespace) -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
     assert lib.fs2d_device_ok(), lib.fs2d_last_error().decode()
-    # experimental kernel selection for A/B runs (default: none): FS2D_TUNING="1=8,4=1,5=1,nonadv=1,limitskip=1" -> fs2d_set_tuning(key, value)
-    # pairs and CipMacSolver.fused_non_advection; recorded in the JSON line as "tuning"
+    # experimental kernel selection for A/B runs (default: none): FS2D_TUNING="4=0,limitskip=1" -> fs2d_set_tuning(key, value) pairs;
+    # recorded in the JSON line as "tuning"
     tuning = {}
     for item in filter(None, os.environ.get("FS2D_TUNING", "").split(",")):
         k, v = item.split("=")
         tuning[k] = int(v)
-        if k == "nonadv":
-            from fs.solver import CipMacSolver
-
-            CipMacSolver.fused_non_advection = bool(int(v))
-        elif k == "limitskip":
+        if k == "limitskip":
             from fs.pressure_updater import PressureUpdater
 
             PressureUpdater.limit_skip = bool(int(v))

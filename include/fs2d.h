@@ -72,17 +72,11 @@ int fs2d_version(void);
 unsigned long long fs2d_launch_count(void);
 /* performance knobs (never change results):
  * key 0 = rows marched per warp by the single-iteration Jacobi sweep {1, 2, 4 (default), 8, 16};
- * key 1 = fused Jacobi kernel variant {1: one column per thread, shared-memory planes (64 x 128 tile); 3: register tile +
- *         warp shuffles (64 x 128 tile); 5: register tile on a 96 x 128 tile (default); 6: EXPERIMENTAL, variant 5 with
- *         pairwise named barriers between neighbouring warps instead of a CTA barrier per iteration; 7 / 8: EXPERIMENTAL,
- *         variants 5 / 6 whose slow tiles resolve the BC source cells of their slow cells once per tile};
  * key 2 = TMA-fed streaming versions of the CIP-path stencil kernels {0: off, 1: CIP advection (default), 2: also the
  *         non-advection phase and the vorticity confinement};
  * key 3 = streaming-kernel shape {stages x CTAs/SM x threads}: {0: 3x2x256, 1: 2x3x256 (default), 2: 3x2x512, 3: 2x2x512}.
- * key 4 = EXPERIMENTAL tail of fs2d_jacobi_update {0: two literal iterations (default); 1: the last fused pass also emits the
- *         BC values of its penultimate state, so ONE literal iteration ends the update (variants 5 and 6)}.
- * key 5 = EXPERIMENTAL fs2d_vort_apply kernel {0: shared-memory tile (default); 1: marching kernel, one curl evaluation per cell,
- *         j-neighbours by warp shuffles, no shared memory}.
+ * key 4 = tail of fs2d_jacobi_update {1 (default): the last fused pass also emits the BC values of its penultimate state, so
+ *         ONE literal iteration ends the update; 0: two literal iterations}.
  * Unknown keys / values return FS2D_E_BADARG and change nothing. */
 int fs2d_set_tuning(int key, int value);
 /* 1 if the library was built for sm_100a and a device of compute capability 10.x is current */
@@ -111,17 +105,6 @@ int fs2d_cip_nonadv(float *fn, const float *fc, const float *pc, const uint8_t *
 /* CipMacSolver._non_advection_phase_grad, fs/solver.py:242-261; two_dx = (float)(2.0*dx) */
 int fs2d_cip_nonadv_grad(float *fxn, float *fyn, const float *fxc, const float *fyc, const float *fc, const float *fn,
                          const uint8_t *mask, fs2d_dom d, float two_dx, void *stream);
-/* EXPERIMENTAL (not used by default): fs2d_cip_nonadv followed by fs2d_cip_nonadv_grad in ONE pass over HBM (53 instead of
- * 70 B/cell): fn at the four neighbours of a cell is recomputed from fc / pc on a one-cell ring around each tile; wall
- * neighbours keep the value stored in fn.  Defined as fs2d_cip_nonadv on the rows [ring_lo, ring_hi) followed by
- * fs2d_cip_nonadv_grad on [r0, r1), bit for bit, where [ring_lo, ring_hi) is [r0, r1) extended by at most one row per side:
- * fn of those extra rows is recomputed (and stored) instead of being read -- a rank of a row-strip decomposition passes its
- * owned rows +- 1 and needs two fresh halo rows of fc and pc instead of an exchange of fn.  Falls back to the two kernels when
- * the TMA preconditions (Y % 16 == 0, 16-byte aligned fields) do not hold.  An empty [r0, r1) is a no-op.  Outputs must not
- * alias inputs. */
-int fs2d_cip_nonadv_fused(float *fn, float *fxn, float *fyn, const float *fc, const float *fxc, const float *fyc, const float *pc,
-                          const uint8_t *mask, fs2d_dom d, float dt, float dx, float re, float two_dx, int ring_lo, int ring_hi,
-                          void *stream);
 /* CipMacSolver._advection_phase/_cip_advect, fs/solver.py:267-332 (fluid cells);
  * dx2 = (float)(dx*dx), dx3 = (float)(dx*dx*dx) folded in double by the caller */
 int fs2d_cip_advect(float *fn, float *fxn, float *fyn, const float *fc, const float *fxc, const float *fyc,
@@ -160,39 +143,54 @@ int fs2d_jacobi_sweep(float *pn, const float *pc, const float *src, const uint8_
 /* n_sweeps of {pressure BC, Jacobi} with ping-pong between pa (current) and pb (next); equal to
  * n_sweeps reference iterations (fs/pressure_updater.py:56-60) INCLUDING the final contents of the
  * BC cells of both buffers.  (tgt, src0, src1, kind, n_bc): table as in fs2d_pressure_bc; scratch:
- * >= n_bc floats.  fuse_mask: bit t set (1 <= t <= 12) allows all but the last two iterations to run as
+ * >= n_bc floats.  fuse_mask: bit t set (1 <= t <= 12) allows all but the last iterations to run as
  * fused passes of t iterations (fs2d_jacobi_fused) -- the caller must have verified that pass size against
- * the preconditions listed there; 0 = literal iterations only.  *final_in_b = 1 if the current buffer after
- * the call is pb (n_sweeps odd). */
+ * the preconditions listed there; 0 = literal iterations only.  orders / n_orders: NULL, or HOST arrays of 13
+ * entries indexed by t holding the tile list of fs2d_fused_order(pcode, d, t, 0, 0, ...) (device pointer) and
+ * its length for every t of fuse_mask (a NULL entry: that pass size classifies its tiles on the fly).
+ * *final_in_b = 1 if the current buffer after the call is pb (n_sweeps odd). */
 int fs2d_jacobi_update(float *pa, float *pb, const float *src, const uint8_t *pcode, fs2d_dom d, int n_sweeps,
                        const int32_t *tgt, const int32_t *src0, const int32_t *src1, const uint8_t *kind, float *scratch,
-                       int n_bc, int fuse_mask, int *final_in_b, void *stream);
+                       int n_bc, int fuse_mask, const int32_t *const *orders, const int *n_orders, int *final_in_b,
+                       void *stream);
 /* The schedule fs2d_jacobi_update uses: sizes[k] > 0 = one fused pass of that many iterations, 0 = one literal
- * iteration {fs2d_pressure_bc, fs2d_jacobi_sweep}; every entry flips the buffers once.  (A multi-rank host runs
- * the same schedule with a halo exchange in front of every entry.) */
+ * iteration {fs2d_pressure_bc, fs2d_jacobi_sweep}; every entry flips the buffers once.  With a fused pass in the
+ * schedule it ends {..., fused pass through fs2d_jacobi_fused_tail, ONE literal iteration} (fs2d_set_tuning(4, 0):
+ * {..., two literal iterations}).  (A multi-rank host runs the same schedule with a halo exchange in front of every
+ * entry.) */
 int fs2d_jacobi_plan(int n_sweeps, int fuse_mask, int *sizes, int cap, int *n_entries);
-/* One fused pass: T reference iterations {BC, sweep} computed in shared memory, p_in -> relaxed cells of
+/* Tile list of one fused pass geometry (rows [r0, r1) of d tiled for T iterations, minus the tile rows
+ * [skip_from, skip_from + skip_n), see fs2d_jacobi_fused_part): classifies every tile from pcode -- open fluid / has BC
+ * cells, global edges or cells outside the grid / nothing to store -- and writes to `order` (DEVICE array of `cap` >=
+ * number-of-tiles ints) the tiles that have work to do, the expensive ones first, as the kernel will deal them to its
+ * persistent CTAs.  counts (HOST array of 3): entries written, how many of them are slow tiles, tiles dropped.  The list
+ * depends on pcode, d, T and the skipped rows only: build it once per mask and geometry (it synchronises the stream). */
+int fs2d_fused_order(const uint8_t *pcode, fs2d_dom d, int T, int skip_from, int skip_n, int32_t *order, int cap, int *counts,
+                     void *stream);
+/* One fused pass: T reference iterations {BC, sweep} computed on chip, p_in -> relaxed cells of
  * p_out (rows [r0, r1)); bit-identical to T calls of fs2d_pressure_bc + fs2d_jacobi_sweep on the relaxed
  * cells.  BC cells of p_in/p_out are neither read nor written (their values are recomputed from pcode).
+ * order / n_order: the tile list of fs2d_fused_order for exactly this (pcode, d, T), or NULL / 0 (the tiles are then
+ * classified on the launch stream before the pass: same results, an extra pass over pcode and an unbalanced order).
  * Preconditions (checked by the host layer, fs/_bc_tables.py): Y % 16 == 0 and 16-byte aligned fields;
  * T <= t_max of fs2d_fused_tile; the mask's dependency reach fits the tile halo (fused_reach_ok); no
  * inflow cell reads a wall-BC cell; never-written wall cells hold equal values in p_in and p_out; in a
  * row strip the halo rows [r0-T, r1+T) of p_in and src are up to date. */
 int fs2d_jacobi_fused(float *p_out, const float *p_in, const float *src, const uint8_t *pcode, fs2d_dom d, int T,
-                      void *stream);
+                      const int32_t *order, int n_order, void *stream);
 /* The same pass restricted to part of its tile rows: the tiling of rows [r0, r1) (tile rows of fs2d_fused_tile rows -
  * 2 * halo_rows output rows, anchored at r0) minus the tile rows [skip_from, skip_from + skip_n).  A multi-rank host
  * runs the interior tile rows (a row window through fs2d_jacobi_fused) while the halo SendRecv is in flight and then the
  * first and last tile rows, which read the fresh halo, in ONE launch through this entry point. */
 int fs2d_jacobi_fused_part(float *p_out, const float *p_in, const float *src, const uint8_t *pcode, fs2d_dom d, int T,
-                           int skip_from, int skip_n, void *stream);
-/* EXPERIMENTAL: fs2d_jacobi_fused_part whose pass also stores, into the wall-BC cells of p_in (rows [r0, r1) of the launched
- * tile rows; those cells are never read), the BC values of the pass's PENULTIMATE state -- what the reference leaves there
+                           int skip_from, int skip_n, const int32_t *order, int n_order, void *stream);
+/* fs2d_jacobi_fused_part whose pass also stores, into the wall-BC cells of p_in (rows [r0, r1) of the launched tile rows;
+ * those cells are never read), the BC values of the pass's PENULTIMATE state -- what the reference leaves there
  * (SURVEY T1).  A pass of T iterations ending at iteration n - 1 followed by ONE literal iteration then reproduces both
- * physical buffers of an n-iteration update.  fs2d_jacobi_plan returns such a schedule (entry n - 2 fused, entry n - 1
- * literal) when fs2d_set_tuning(4, 1) is active; fused variants >= 5 only. */
+ * physical buffers of an n-iteration update; fs2d_jacobi_plan returns such a schedule (entry n - 2 fused, entry n - 1
+ * literal). */
 int fs2d_jacobi_fused_tail(float *p_out, float *p_in, const float *src, const uint8_t *pcode, fs2d_dom d, int T, int skip_from,
-                           int skip_n, void *stream);
+                           int skip_n, const int32_t *order, int n_order, void *stream);
 /* tile geometry of the fused kernel for T iterations per pass: loaded tile rows x cols, the halo it discards on
  * each side (rows: T; columns: T rounded up to 4 -- TMA box starts must be 16-byte aligned) and the largest T */
 int fs2d_fused_tile(int T, int *rows, int *cols, int *halo_rows, int *halo_cols, int *t_max);

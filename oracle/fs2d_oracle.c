@@ -23,6 +23,7 @@
  * Layout: grid X (slow, index i) x Y (fast, index j), row-major; vector fields AoS [i][j][c].
  */
 #include <math.h>
+#include <omp.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -539,4 +540,9 @@ void orc_render(float *rgb, const float *v, const float *p, const float *dye, co
         }
 }
 
-int orc_abi_version(void) { return 3; }
+/* thread control for the timed CPU legs of bench.py: torchrun exports OMP_NUM_THREADS=1 to every rank, so the environment
+ * cannot be trusted; the caller sets the team size explicitly */
+void orc_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int orc_max_threads(void) { return omp_get_max_threads(); }
+
+int orc_abi_version(void) { return 4; }

@@ -171,8 +171,12 @@ def render(v, p, dye, mask, dx, mode: str) -> np.ndarray:
     return rgb
 
 
-def set_threads(n: int) -> None:
+def set_threads(n: int) -> int:
+    """Size of the OpenMP team of the oracle kernels, set through the runtime (an OMP_NUM_THREADS read at load time cannot
+    be trusted: torch.distributed.run exports OMP_NUM_THREADS=1 to every rank).  Returns the team size in effect."""
     os.environ["OMP_NUM_THREADS"] = str(n)
+    lib().orc_set_threads(_i(int(n)))
+    return int(lib().orc_max_threads())
 
 
 # ----------------------------------------------------------------------------- orchestration

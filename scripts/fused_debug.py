@@ -16,6 +16,6 @@ a.tensor.uniform_(-1, 1); b.tensor.copy_(a.tensor); v.tensor.uniform_(-1, 1)
 src = jac._source(v)
 torch.cuda.synchronize()
 print("fused_ok", bc.fused_ok(T), flush=True)
-_lib.call("fs2d_jacobi_fused", b.ptr(), a.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom, T, _lib.stream())
+_lib.call("fs2d_jacobi_fused", b.ptr(), a.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom, T, _lib.ptr(bc.fused_order(T)[0]), bc.fused_order(T)[1], _lib.stream())
 torch.cuda.synchronize()
 print("ran", X, Y, T, float(b.tensor.abs().sum()), flush=True)

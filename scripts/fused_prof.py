@@ -15,5 +15,5 @@ a, b, v = Field((X, Y), 1), Field((X, Y), 1), Field((X, Y), 2)
 a.tensor.uniform_(-1, 1); v.tensor.uniform_(-1, 1); b.tensor.copy_(a.tensor)
 src = jac._source(v)
 for T in [int(x) for x in sys.argv[1:]]:
-    _lib.call("fs2d_jacobi_fused", b.ptr(), a.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom, T, _lib.stream())
+    _lib.call("fs2d_jacobi_fused", b.ptr(), a.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom, T, _lib.ptr(bc.fused_order(T)[0]), bc.fused_order(T)[1], _lib.stream())
 torch.cuda.synchronize()

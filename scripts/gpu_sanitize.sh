@@ -6,4 +6,4 @@ for tool in memcheck racecheck synccheck; do
 done
 echo "== fused tests + sweep (swizzled source reads)"
 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "fused" 2>&1 | tail -2
-FUSED_VARIANT=5 timeout 200 python scripts/sweep_bench.py 2>&1 | grep -E "T= ?(4|6|8|12):|pass_cost"
+timeout 200 python scripts/sweep_bench.py 2>&1 | grep -E "T= ?(4|6|8|12):|pass_cost"

@@ -26,15 +26,10 @@ vc = s.vorticity_confinement
 cases = {
     "cip_nonadv (21 B)": (lambda: s._non_advection_phase(s.v.next, s.v.current, s.p.current), 21),
     "cip_nonadv_grad (49 B)": (lambda: s._non_advection_phase_grad(s.vx.next, s.vy.next, s.vx.current, s.vy.current, s.v.current, s.v.next), 49),
-    "cip_nonadv_fused EXPERIMENTAL (53 B = nonadv + grad in one pass)": (lambda: _lib.call(
-        "fs2d_cip_nonadv_fused", s.v.next.ptr(), s.vx.next.ptr(), s.vy.next.ptr(), s.v.current.ptr(), s.vx.current.ptr(),
-        s.vy.current.ptr(), s.p.current.ptr(), _lib.ptr(bc._bc_mask), bc.dom, s.dt, s.dx, s.re, 2.0 * s.dx, bc.dom.r0, bc.dom.r1, _lib.stream()), 53),
     "cip_advect (49 B)": (lambda: s._advection_phase(s.v.next, s.vx.next, s.vy.next, s.v.current, s.vx.current, s.vy.current, s.v.current), 49),
     "vort_calc (17 B)": (lambda: vc._calc_vorticity(s.v.current), 17),
     "vort_add (25 B)": (lambda: vc._add_vorticity(s.v.next, s.v.current), 25),
     "vort_apply fused (25 B)": (lambda: vc._apply_fused(s.v.next, s.v.current), 25),
-    "vort_apply MARCHING, EXPERIMENTAL (25 B)": (lambda: (_lib.load().fs2d_set_tuning(5, 1), vc._apply_fused(s.v.next, s.v.current),
-                                                          _lib.load().fs2d_set_tuning(5, 0)), 25),
     "p_source (16 B)": (lambda: s.pressure_updater._source(s.v.current), 16),
     "limit (8 B)": (lambda: limit_field(s.v.current, VELOCITY_LIMIT, bc=bc), 8),
 }

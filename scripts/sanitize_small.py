@@ -18,22 +18,12 @@ for num, X, Y in ((2, 256, 128), (3, 200, 176)):
     rng = np.random.default_rng(1)
     for k in ("v", "vx", "vy", "p"):
         getattr(s, k).current.from_numpy(rng.uniform(-1, 1, getattr(s, k).current.tensor.shape).astype(np.float32))
-    for variant in (5, 3, 1):
-        lib.fs2d_set_tuning(1, variant)
-        for stream in (2, 0):
+    for tail in (1, 0):                 # the two tails of the Jacobi update (fs2d_set_tuning(4, .))
+        lib.fs2d_set_tuning(4, tail)
+        for stream in (2, 0, 1):        # streaming-kernel selection; ends on the default
             lib.fs2d_set_tuning(2, stream)
+            s.pressure_updater.limit_skip = bool(tail)
             s.update()
-    # the experimental kernels (off by default): pair-barrier Jacobi variant, emitting tail, marching vorticity kernel,
-    # fused non-advection phase
-    import os
-    if os.environ.get("FS2D_EXPERIMENTAL") == "1":
-        lib.fs2d_set_tuning(2, 1)
-        for variant, tail, march, fused in ((6, 0, 0, False), (5, 1, 1, True), (7, 0, 0, False), (8, 1, 1, True)):
-            lib.fs2d_set_tuning(1, variant); lib.fs2d_set_tuning(4, tail); lib.fs2d_set_tuning(5, march)
-            s.fused_non_advection = fused
-            s.pressure_updater.limit_skip = fused
-            s.update(); s.update()
-        lib.fs2d_set_tuning(1, 5); lib.fs2d_set_tuning(4, 0); lib.fs2d_set_tuning(5, 0)
-        s.fused_non_advection = False
+    lib.fs2d_set_tuning(4, 1)
     torch.cuda.synchronize()
     print("ok", num, X, Y, float(s.p.current.tensor.abs().sum()))

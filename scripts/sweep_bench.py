@@ -30,21 +30,22 @@ for inline in (False,):
         ms = e0.elapsed_time(e1) / 20
         print(f"inline={inline} rows/warp={rows:2d}: {ms*1e3:7.1f} us/sweep  algorithmic {12*X*Y/ms/1e6:7.1f} GB/s  actual~{17*X*Y/ms/1e6:7.1f} GB/s", flush=True)
 
-import os
-variant = int(os.environ.get("FUSED_VARIANT", "3"))
-lib.fs2d_set_tuning(1, variant)
-print(f"fused passes, variant {variant} (T iterations per pass), us per iteration:")
+print("fused passes (T iterations per pass), us per iteration:")
+for T in (1, 4, 8, 12):
+    if bc.fused_ok(T):
+        bc.fused_order(T)
+        print("  tile list T =", T, "(entries, slow, dropped) =", [v[1:] for k, v in bc._fused_orders.items() if k[0] == T][0])
 costs = {}
 for T in range(1, 13):
     if not bc.fused_ok(T):
         print("T", T, "not valid for this mask"); continue
     for _ in range(2):
-        _lib.call("fs2d_jacobi_fused", b.ptr(), a.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom, T, _lib.stream())
+        _lib.call("fs2d_jacobi_fused", b.ptr(), a.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom, T, _lib.ptr(bc.fused_order(T)[0]), bc.fused_order(T)[1], _lib.stream())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(5):
-        _lib.call("fs2d_jacobi_fused", b.ptr(), a.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom, T, _lib.stream())
-        _lib.call("fs2d_jacobi_fused", a.ptr(), b.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom, T, _lib.stream())
+        _lib.call("fs2d_jacobi_fused", b.ptr(), a.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom, T, _lib.ptr(bc.fused_order(T)[0]), bc.fused_order(T)[1], _lib.stream())
+        _lib.call("fs2d_jacobi_fused", a.ptr(), b.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom, T, _lib.ptr(bc.fused_order(T)[0]), bc.fused_order(T)[1], _lib.stream())
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     costs[T] = ms * 1e3

@@ -28,7 +28,7 @@ PTX_HELPERS = {
     "mbar_expect_tx": "emu::mbar_expect_tx(bar, bytes);", "st_mbar_expect": "emu::mbar_expect_tx(bar, bytes);",
     "mbar_wait": "emu::mbar_wait(bar, parity);", "st_mbar_wait": "emu::mbar_wait(bar, parity);",
     "tma_load_2d": "emu::tma_load_2d(dst, map, c0, c1, bar);", "st_tma_2d": "emu::tma_load_2d(dst, map, c0, c1, bar);",
-    "named_bar_sync": "emu::named_barrier(id, count);",
+    "ld_acquire_smem": "return emu::flag_load(p);", "st_release_smem": "emu::flag_store(p, v);",
 }
 
 

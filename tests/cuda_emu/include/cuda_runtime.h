@@ -70,6 +70,10 @@ inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 template <class T>
 inline cudaError_t cudaMalloc(T **p, size_t n) { *p = (T *)calloc(1, n); return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2 };
+inline cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(dst, src, n); return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaGetDriverEntryPoint(const char *name, void **fn, int, cudaDriverEntryPointQueryResult *q);   // cuda.h
 
 // ---- the fiber machine ---------------------------------------------------------------------------------------------
@@ -299,6 +303,16 @@ inline void mbar_wait(uint64_t *bar, uint32_t parity) {       // try_wait.parity
     MBar *b = reinterpret_cast<MBar *>(bar);
     while (b->phase == (uint8_t)parity) yield();
 }
+// progress flags in shared memory (st.release / ld.acquire at CTA scope): a store is progress, a poll is a scheduling point --
+// a polling loop that never sees its value is reported as a deadlock like any other blocked fiber
+inline void flag_store(int *p, int v) {
+    *p = v;
+    ++M().progress;
+}
+inline int flag_load(const int *p) {
+    yield();
+    return *p;
+}
 }  // namespace emu
 
 // ---- device builtins -----------------------------------------------------------------------------------------------
@@ -328,6 +342,7 @@ inline float __shfl_down_sync(unsigned, float v, int delta) {
     const int g = emu::warp_rendezvous((uint32_t)__float_as_int(v), 1);
     return lane + delta < 32 ? __int_as_float((int)emu::my_warp().buf[g][lane + delta]) : v;
 }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_rendezvous(0, 1); }
 inline int __all_sync(unsigned, int pred) {
     const int g = emu::warp_rendezvous(0, pred);
     return emu::my_warp().pred_and[g];

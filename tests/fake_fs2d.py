@@ -149,14 +149,6 @@ class FakeFs2d:
         self._windowed(d, [self.a(fxn, d, 2), self.a(fyn, d, 2)], lambda w, ox, oy: orc.lib().orc_cip_nonadv_grad(
             _p(ox), _p(oy), _p(XC[w]), _p(YC[w]), _p(FC[w]), _p(FN[w]), _p(M[w]), _i(ox.shape[0]), _i(d.Y), _f(two_dx)))
 
-    def fs2d_cip_nonadv_fused(self, fn, fxn, fyn, fc, fxc, fyc, pc, mask, d, dt, dx, re, two_dx, ring_lo, ring_hi, stream) -> None:
-        """by definition (include/fs2d.h): fs2d_cip_nonadv on [ring_lo, ring_hi), then fs2d_cip_nonadv_grad on [r0, r1);
-        an empty [r0, r1) is a no-op"""
-        if d.r0 == d.r1:
-            return
-        self.fs2d_cip_nonadv(fn, fc, pc, mask, d.replace(r0=ring_lo, r1=ring_hi), dt, dx, re, stream)
-        self.fs2d_cip_nonadv_grad(fxn, fyn, fxc, fyc, fc, fn, mask, d, two_dx, stream)
-
     def fs2d_cip_advect(self, fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, dx2, dx3, stream) -> None:
         FC, XC, YC, V, M = self.a(fc, d, 2), self.a(fxc, d, 2), self.a(fyc, d, 2), self.a(v, d, 2), self.a(mask, d)
         self._windowed(d, [self.a(fn, d, 2), self.a(fxn, d, 2), self.a(fyn, d, 2)], lambda w, o, ox, oy: orc.lib().orc_cip_advect(
@@ -248,8 +240,8 @@ class FakeFs2d:
 
         self._windowed(d, [self.a(pn, d, 1)], body)
 
-    def fs2d_jacobi_update(self, pa, pb, src, pcode, d, n_sweeps, tgt, src0, src1, kind, scratch, n_bc, fuse_mask, final_in_b,
-                           stream) -> None:
+    def fs2d_jacobi_update(self, pa, pb, src, pcode, d, n_sweeps, tgt, src0, src1, kind, scratch, n_bc, fuse_mask, orders,
+                           n_orders, final_in_b, stream) -> None:
         cur, nxt = pa, pb
         for _ in range(n_sweeps):   # the literal loop of fs/pressure_updater.py:56-60
             self.fs2d_pressure_bc(cur, tgt, src0, src1, kind, scratch, n_bc, stream)
@@ -279,10 +271,14 @@ class FakeFs2d:
             if emit:                # fs2d_jacobi_fused_tail: BC values of the penultimate state into the wall-BC cells of p_in
                 PI[r0:r1][wall_bc[a:b]] = bc_of_penultimate[a:b][wall_bc[a:b]]
 
-    def fs2d_jacobi_fused(self, p_out, p_in, src, pcode, d, T, stream) -> None:
+    def fs2d_fused_order(self, pcode, d, T, skip_from, skip_n, order, cap, counts, stream) -> None:
+        """the tile list only steers the CUDA kernel's work distribution; the stand-in computes whole row sets"""
+        counts[0], counts[1], counts[2] = 1, 0, 0
+
+    def fs2d_jacobi_fused(self, p_out, p_in, src, pcode, d, T, order, n_order, stream) -> None:
         self._fused_rows(p_out, p_in, src, pcode, d, T, [(d.r0, d.r1)])
 
-    def fs2d_jacobi_fused_part(self, p_out, p_in, src, pcode, d, T, skip_from, skip_n, stream) -> None:
+    def fs2d_jacobi_fused_part(self, p_out, p_in, src, pcode, d, T, skip_from, skip_n, order, n_order, stream) -> None:
         rows, hr = ctypes.c_int(), ctypes.c_int()
         self.real.fs2d_fused_tile(T, ctypes.byref(rows), None, ctypes.byref(hr), None, None)
         ti = rows.value - 2 * hr.value
@@ -290,7 +286,7 @@ class FakeFs2d:
         sets = [(d.r0 + q * ti, min(d.r0 + (q + 1) * ti, d.r1)) for q in range(k) if not (skip_from <= q < skip_from + skip_n)]
         self._fused_rows(p_out, p_in, src, pcode, d, T, sets)
 
-    def fs2d_jacobi_fused_tail(self, p_out, p_in, src, pcode, d, T, skip_from, skip_n, stream) -> None:
+    def fs2d_jacobi_fused_tail(self, p_out, p_in, src, pcode, d, T, skip_from, skip_n, order, n_order, stream) -> None:
         rows, hr = ctypes.c_int(), ctypes.c_int()
         self.real.fs2d_fused_tile(T, ctypes.byref(rows), None, ctypes.byref(hr), None, None)
         ti = rows.value - 2 * hr.value

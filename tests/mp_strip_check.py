@@ -119,8 +119,6 @@ def main() -> None:
         part = Partition(X, rank, world, halo)
         strip = make_solver(BoundaryCondition(const, mask, device=dev, partition=part), dt, dx, re, vc, scheme, **pkw)
         single = make_solver(BoundaryCondition(const, mask, device=dev), dt, dx, re, vc, scheme, **pkw) if rank == 0 else None
-        if os.environ.get("FS2D_FUSED_NONADV") == "1" and scheme == "cip":
-            strip.fused_non_advection = True      # experimental one-pass non-advection phase on the strips; `single` stays default
         rng = np.random.default_rng(1234 + (num if isinstance(num, int) else 50 + int(num[4:])))
         g0, g1 = part.owned()
         p_first = None

@@ -63,7 +63,7 @@ def test_null_pointers_are_rejected_with_valueerror():
     with pytest.raises(ValueError, match="null field pointer"):
         _lib.call("fs2d_pressure_source", _FAKE, None, d, 0.1, 0.1, None)
     with pytest.raises(ValueError, match="null/aliased"):
-        _lib.call("fs2d_jacobi_fused", _FAKE, _FAKE, _FAKE, _FAKE, d, 4, None)
+        _lib.call("fs2d_jacobi_fused", _FAKE, _FAKE, _FAKE, _FAKE, d, 4, None, 0, None)
     with pytest.raises(ValueError, match="in place"):
         _lib.call("fs2d_jacobi_sweep", _FAKE, _FAKE, _FAKE, _FAKE, d, 0, None)
     with pytest.raises(ValueError, match="in place"):
@@ -80,13 +80,13 @@ def test_bad_domains_schemes_and_sizes_are_rejected():
     with pytest.raises(ValueError, match="parity"):
         _lib.call("fs2d_rbsor_pass", _FAKE, _FAKE, _FAKE, _FAKE, _dom(), 1.3, -0.3, 2, None)
     with pytest.raises(ValueError, match="out of range"):
-        _lib.call("fs2d_jacobi_fused", _FAKE, _FAKE + 64, _FAKE, _FAKE, _dom(Y=16, chi=7), 13, None)
+        _lib.call("fs2d_jacobi_fused", _FAKE, _FAKE + 64, _FAKE, _FAKE, _dom(Y=16, chi=7), 13, None, 0, None)
     with pytest.raises(ValueError, match="Y % 16"):
-        _lib.call("fs2d_jacobi_fused", _FAKE, _FAKE + 64, _FAKE, _FAKE, _dom(Y=8), 4, None)
+        _lib.call("fs2d_jacobi_fused", _FAKE, _FAKE + 64, _FAKE, _FAKE, _dom(Y=8), 4, None, 0, None)
     with pytest.raises(ValueError, match="unknown tuning key"):
         _lib.call("fs2d_set_tuning", 99, 0)
     with pytest.raises(ValueError, match="unknown tuning key"):
-        _lib.call("fs2d_set_tuning", 1, 4)       # no such fused-kernel variant
+        _lib.call("fs2d_set_tuning", 1, 4)       # no such key (the fused-kernel variants of round 1 are gone)
 
 
 def test_empty_inputs_are_noops():
@@ -101,7 +101,7 @@ def test_empty_inputs_are_noops():
     _lib.call("fs2d_vort_apply", _FAKE, _FAKE, _FAKE, _FAKE + 64, _FAKE, d, 0.1, 0.1, None)
     _lib.call("fs2d_pressure_source", _FAKE, _FAKE, d, 0.1, 0.1, None)
     _lib.call("fs2d_jacobi_sweep", _FAKE, _FAKE + 64, _FAKE, _FAKE, d, 0, None)
-    _lib.call("fs2d_jacobi_fused", _FAKE, _FAKE + 64, _FAKE, _FAKE, _dom(Y=16, r0=3, r1=3), 4, None)
+    _lib.call("fs2d_jacobi_fused", _FAKE, _FAKE + 64, _FAKE, _FAKE, _dom(Y=16, r0=3, r1=3), 4, None, 0, None)
     _lib.call("fs2d_vel_bc", _FAKE, _FAKE, None, None, None, None, 0, None)
     _lib.call("fs2d_pressure_bc", _FAKE, None, None, None, None, None, 0, None)
     _lib.call("fs2d_dye_bc", _FAKE, _FAKE, None, 0, None)

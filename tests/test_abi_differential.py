@@ -118,12 +118,6 @@ def test_dense_entry_points_against_the_window_model(libs, seed):
           lambda q: (q["fn"], q["fc"], q["pc"], q["mask"], d, dt, dx, re, None))
     c.run("fs2d_cip_nonadv_grad", dict(fxn=o2a, fyn=o2b, fxc=fx, fyc=fy, fc=v, fn=o2c, mask=m), ("fxn", "fyn"),
           lambda q: (q["fxn"], q["fyn"], q["fxc"], q["fyc"], q["fc"], q["fn"], q["mask"], d, 2.0 * dx, None))
-    c.run("fs2d_cip_nonadv_fused", dict(fn=o2a, fxn=o2b, fyn=o2c, fc=v, fxc=fx, fyc=fy, pc=p, mask=m), ("fn", "fxn", "fyn"),
-          lambda q: (q["fn"], q["fxn"], q["fyn"], q["fc"], q["fxc"], q["fyc"], q["pc"], q["mask"], d, dt, dx, re, 2.0 * dx, d.r0, d.r1, None))
-    ring = (max(d.r0 - 1, d.clo), min(d.r1 + 1, d.chi + 1))     # what a strip passes: fn recomputed (and stored) one row beyond each side
-    c.run("fs2d_cip_nonadv_fused", dict(fn=o2a, fxn=o2b, fyn=o2c, fc=v, fxc=fx, fyc=fy, pc=p, mask=m), ("fn", "fxn", "fyn"),
-          lambda q: (q["fn"], q["fxn"], q["fyn"], q["fc"], q["fxc"], q["fyc"], q["pc"], q["mask"], d, dt, dx, re, 2.0 * dx, ring[0], ring[1], None),
-          written={"fn": ring})
     c.run("fs2d_cip_advect", dict(fn=o2a, fxn=o2b, fyn=o2c, fc=v, fxc=fx, fyc=fy, mask=m), ("fn", "fxn", "fyn"),
           lambda q: (q["fn"], q["fxn"], q["fyn"], q["fc"], q["fxc"], q["fyc"], q["fc"], q["mask"], d, dt, dx, dx**2, dx**3, None))
     c.run("fs2d_set_grad", dict(fx=o2a, fy=o2b, f=v), ("fx", "fy"), lambda q: (q["fx"], q["fy"], q["f"], d, dx, None))
@@ -133,12 +127,6 @@ def test_dense_entry_points_against_the_window_model(libs, seed):
           lambda q: (q["vn"], q["vc"], q["w"], q["wabs"], q["mask"], d, dx, dt * 5.0, None))
     c.run("fs2d_vort_apply", dict(vn=o2a, w=o1a, wabs=o1b, vc=v, mask=m), ("vn", "w", "wabs"),
           lambda q: (q["vn"], q["w"], q["wabs"], q["vc"], q["mask"], d, dx, dt * 5.0, None))
-    c.emu.fs2d_set_tuning(5, 1)     # the experimental marching kernel behind the same entry point
-    try:
-        c.run("fs2d_vort_apply", dict(vn=o2a, w=o1a, wabs=o1b, vc=v, mask=m), ("vn", "w", "wabs"),
-              lambda q: (q["vn"], q["w"], q["wabs"], q["vc"], q["mask"], d, dx, dt * 5.0, None))
-    finally:
-        c.emu.fs2d_set_tuning(5, 0)
     c.run("fs2d_limit", dict(v=v * np.float32(14.0)), ("v",), lambda q: (q["v"], d, 10.0, None))
     c.run("fs2d_clamp", dict(f=c.f(X, Y, 3, scale=2.0)), ("f",), lambda q: (q["f"], d, 3, 0.0, 1.0, None))
     c.run("fs2d_dye_nonadv", dict(dn=o3a, dc=dye, mask=m), ("dn",), lambda q: (q["dn"], q["dc"], q["mask"], d, dt, dx, re, None))

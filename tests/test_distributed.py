@@ -163,22 +163,6 @@ def test_strip_check_script_with_emulated_kernels(world):
     assert out.returncode == 0 and f"MP_CHECK OK 8 cases on {world} ranks" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
-def test_strips_with_the_experimental_fused_non_advection_kernel():
-    """CipMacSolver.fused_non_advection on strips (emulated kernels, gloo, world 2): fn on the first halo rows is
-    recomputed from two fresh halo rows of v and p instead of being exchanged; every buffer still equals the default
-    single-domain run bitwise."""
-    sys.path.insert(0, str(REPO / "tests" / "cuda_emu"))
-    import build_emu
-
-    build_emu.build()
-    for world in (2,):      # (world 4 checked by hand; the strip logic itself is covered for world 2-4 by the tests above)
-        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-               "--master-addr", "127.0.0.1", "--master-port", str(free_port()), str(REPO / "tests" / "mp_strip_check.py")]
-        out = subprocess.run(cmd, capture_output=True, text=True, timeout=1200,
-                             env=dict(os.environ, FS2D_FAKE_LIB="emu", FS2D_FUSED_NONADV="1"))
-        assert out.returncode == 0 and f"MP_CHECK OK 8 cases on {world} ranks" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
-
-
 def test_split_windows_cover_the_strip_and_keep_the_interior_off_the_halo():
     """fs.halo.split_windows: the interior window is a whole number of tile rows starting one tile row into the strip,
     and its reads (t rows beyond it) stay inside the owned rows."""

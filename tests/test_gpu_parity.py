@@ -309,17 +309,15 @@ def test_properties_at_res_8192(env):
 FUSED_CASES = [(1, 128, 64), (2, 256, 128), (3, 320, 160), (4, 200, 96), (5, 384, 192), (2, 1000, 512), (3, 2048, 1024)]
 
 
-@pytest.mark.parametrize("variant", [1, 3, 5])
+@pytest.mark.parametrize("listed", [True, False])
 @pytest.mark.parametrize("num,X,Y", FUSED_CASES)
-def test_fused_pass_equals_literal_iterations(env, num, X, Y, variant, t_list=(1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12), need=3):
-    env.fs2d_set_tuning(1, variant)
-    try:
-        _fused_pass_check(num, X, Y, t_list=t_list, need=need)
-    finally:
-        env.fs2d_set_tuning(1, 5)
+def test_fused_pass_equals_literal_iterations(env, num, X, Y, listed, t_list=(1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12), need=3):
+    """listed: the pass walks the precomputed tile list of fs2d_fused_order (what the host layer does); not listed: it
+    classifies its tiles on the fly (order = NULL)"""
+    _fused_pass_check(num, X, Y, t_list=t_list, need=need, listed=listed)
 
 
-def _fused_pass_check(num, X, Y, mask_override=None, t_list=(1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12), need=3):
+def _fused_pass_check(num, X, Y, mask_override=None, t_list=(1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12), need=3, listed=True):
     from fs import _lib
     from fs.boundary_condition import BoundaryCondition, build_scene
     from fs.pressure_updater import JacobiPressureUpdater
@@ -343,7 +341,9 @@ def _fused_pass_check(num, X, Y, mask_override=None, t_list=(1, 2, 3, 4, 5, 6, 7
         for _ in range(T):  # literal iterations
             bc.set_pressure_boundary_condition(a); jac._sweep(b, a, src, inline_bc=False); a, b = b, a
         fin, fout = fld(p0), fld(p0)
-        _lib.call("fs2d_jacobi_fused", fout.ptr(), fin.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom, T, _lib.stream())
+        order, n_order = bc.fused_order(T) if listed else (None, 0)
+        _lib.call("fs2d_jacobi_fused", fout.ptr(), fin.ptr(), src.ptr(), _lib.ptr(bc._pcode), bc.dom, T, _lib.ptr(order), n_order,
+                  _lib.stream())
         got, want = fout.tensor, a.tensor
         same = (got == want) | (got.isnan() & want.isnan())
         bad = relaxed & ~same
@@ -354,9 +354,8 @@ def _fused_pass_check(num, X, Y, mask_override=None, t_list=(1, 2, 3, 4, 5, 6, 7
     return checked
 
 
-@pytest.mark.parametrize("variant", [1, 3, 5])
 @pytest.mark.parametrize("seed", range(4))
-def test_fused_pass_random_obstacles(env, seed, variant, size=(512, 256), t_list=(1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12)):
+def test_fused_pass_random_obstacles(env, seed, size=(512, 256), t_list=(1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12)):
     """Random blocky obstacles (thick enough for the reach rule) scattered over a channel: many tiles mix open-fluid
     warps, wall faces, convex corners and global edges."""
     from fs.boundary_condition import build_scene
@@ -369,11 +368,7 @@ def test_fused_pass_random_obstacles(env, seed, variant, size=(512, 256), t_list
         h, w = rng.integers(5, 40, 2)
         i0, j0 = rng.integers(8, X - 48), rng.integers(8, Y - 48)
         mask[i0:i0 + h, j0:j0 + w] = 1
-    env.fs2d_set_tuning(1, variant)
-    try:
-        _fused_pass_check(1, X, Y, mask_override=mask, t_list=t_list, need=1)
-    finally:
-        env.fs2d_set_tuning(1, 5)
+    _fused_pass_check(1, X, Y, mask_override=mask, t_list=t_list, need=1, listed=seed % 2 == 0)
 
 
 @pytest.mark.parametrize("num,X,Y,n_iter", [(2, 256, 128, 80), (5, 384, 192, 21), (1, 128, 64, 7), (3, 320, 160, 13), (2, 96, 48, 3)])
@@ -655,8 +650,7 @@ def test_stream_kernels_equal_direct_kernels(env, num, X, Y):
                 assert_bitexact(f"{name} bc{num} dx={dxv} dom={dom.r0}:{dom.r1}", a, b)
 
 
-@pytest.mark.parametrize("variant", [3, 5])
-def test_fused_pass_split_into_interior_and_edge_launches(env, variant, X=1000, Y=512):
+def test_fused_pass_split_into_interior_and_edge_launches(env, X=1000, Y=512):
     """fs2d_jacobi_fused on an interior row window + fs2d_jacobi_fused_part on the remaining tile rows == one launch
     (what the multi-rank host does to hide the halo exchange)."""
     from fs import _lib
@@ -665,30 +659,26 @@ def test_fused_pass_split_into_interior_and_edge_launches(env, variant, X=1000, 
     from fs.pressure_updater import JacobiPressureUpdater
     import ctypes
 
-    env.fs2d_set_tuning(1, variant)
-    try:
-        const, mask = build_scene(2, X, Y)
-        bc = BoundaryCondition(const, mask)
-        rng = np.random.default_rng(7)
-        p0 = rng.uniform(-1, 1, mask.shape).astype(np.float32)
-        v = fld(rng.uniform(-1, 1, mask.shape + (2,)).astype(np.float32))
-        jac = JacobiPressureUpdater(bc, 0.05 / Y, 1.0 / Y, 1, fuse=0)
-        src = jac._source(v)
-        for T in (4, 8):
-            assert bc.fused_ok(T)
-            rows, cols, hr, hc, tmax = (ctypes.c_int() for _ in range(5))
-            _lib.call("fs2d_fused_tile", T, ctypes.byref(rows), ctypes.byref(cols), ctypes.byref(hr), ctypes.byref(hc), ctypes.byref(tmax))
-            mid, m = split_windows(bc.dom, rows.value - 2 * hr.value, T)
-            assert mid is not None
-            whole, parts, fin = fld(p0), fld(p0), fld(p0)
-            jac._fused(whole, fin, src, T)
-            jac._fused(parts, fin, src, T, dom=mid)
-            jac._fused(parts, fin, src, T, skip=(1, m - 1))
-            assert torch.equal(whole.tensor, parts.tensor), f"T={T}: split launches differ from the single launch"
-            with pytest.raises((ValueError, RuntimeError)):
-                jac._fused(parts, fin, src, T, skip=(1, 10 ** 6))
-    finally:
-        env.fs2d_set_tuning(1, 5)
+    const, mask = build_scene(2, X, Y)
+    bc = BoundaryCondition(const, mask)
+    rng = np.random.default_rng(7)
+    p0 = rng.uniform(-1, 1, mask.shape).astype(np.float32)
+    v = fld(rng.uniform(-1, 1, mask.shape + (2,)).astype(np.float32))
+    jac = JacobiPressureUpdater(bc, 0.05 / Y, 1.0 / Y, 1, fuse=0)
+    src = jac._source(v)
+    for T in (4, 8):
+        assert bc.fused_ok(T)
+        rows, cols, hr, hc, tmax = (ctypes.c_int() for _ in range(5))
+        _lib.call("fs2d_fused_tile", T, ctypes.byref(rows), ctypes.byref(cols), ctypes.byref(hr), ctypes.byref(hc), ctypes.byref(tmax))
+        mid, m = split_windows(bc.dom, rows.value - 2 * hr.value, T)
+        assert mid is not None
+        whole, parts, fin = fld(p0), fld(p0), fld(p0)
+        jac._fused(whole, fin, src, T)
+        jac._fused(parts, fin, src, T, dom=mid)
+        jac._fused(parts, fin, src, T, skip=(1, m - 1))
+        assert torch.equal(whole.tensor, parts.tensor), f"T={T}: split launches differ from the single launch"
+        with pytest.raises((ValueError, RuntimeError)):
+            jac._fused(parts, fin, src, T, skip=(1, 10 ** 6))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -735,128 +725,53 @@ def test_division_special_cases_match_the_oracle(env):
 
 
 # ------------------------------------------------------------------------------------------------
-# 11. EXPERIMENTAL kernels (off by default).  On a GPU they run only with FS2D_EXPERIMENTAL=1 (not yet measured there);
-#     tests/test_kernels_emulated.py always runs the same bodies on the CPU emulation of the kernel sources.
+# 11. the two tails of fs2d_jacobi_update; tile lists; the limiter skip
 # ------------------------------------------------------------------------------------------------
-import os  # noqa: E402
-
-experimental = pytest.mark.skipif(os.environ.get("FS2D_EXPERIMENTAL") != "1", reason="experimental kernel: set FS2D_EXPERIMENTAL=1")
-
-
-def _nonadv_fused_check(num, X, Y, mask_override=None):
-    """fs2d_cip_nonadv_fused == fs2d_cip_nonadv + fs2d_cip_nonadv_grad, all three output fields, whole grid and a row
-    window with clamp bounds inside the array, power-of-two and general dx; never-written cells keep their values."""
-    from fs import _lib
-    from fs.boundary_condition import BoundaryCondition, build_scene
-    from fs.fluid_simulator import make_solver
-
-    const, mask = build_scene(num, X, Y)
-    if mask_override is not None:
-        mask = mask_override
-    bc = BoundaryCondition(const, mask)
-    rng = np.random.default_rng(X * Y + 1)
-    doms = [bc.dom, bc.dom.replace(r0=5, r1=X - 11, clo=2, chi=X - 3)]
-    for dxv in (1.0 / 128, 0.013):
-        s = make_solver(bc, 0.05 / Y, dxv, 1e3, None, "cip", pressure="jacobi", n_iter=1)
-        init = {k: rng.uniform(-1, 1, getattr(s, k).current.tensor.shape).astype(np.float32) for k in ("v", "vx", "vy", "p")}
-        stale = {k: rng.uniform(-1, 1, getattr(s, k).current.tensor.shape).astype(np.float32) for k in ("v", "vx", "vy")}
-        for dom in doms:
-            out = []
-            for fused in (True, False):
-                for k, a in init.items():
-                    getattr(s, k).current.from_numpy(a)
-                for k, a in stale.items():
-                    getattr(s, k).next.from_numpy(a)
-                old = bc.dom
-                bc.dom = dom
-                try:
-                    if fused:
-                        _lib.call("fs2d_cip_nonadv_fused", s.v.next.ptr(), s.vx.next.ptr(), s.vy.next.ptr(), s.v.current.ptr(),
-                                  s.vx.current.ptr(), s.vy.current.ptr(), s.p.current.ptr(), _lib.ptr(bc._bc_mask), bc.dom, s.dt,
-                                  s.dx, s.re, 2.0 * s.dx, bc.dom.r0, bc.dom.r1, _lib.stream())
-                    else:
-                        s._non_advection_phase(s.v.next, s.v.current, s.p.current)
-                        s._non_advection_phase_grad(s.vx.next, s.vy.next, s.vx.current, s.vy.current, s.v.current, s.v.next)
-                finally:
-                    bc.dom = old
-                out.append((s.v.next.to_numpy(), s.vx.next.to_numpy(), s.vy.next.to_numpy()))
-            for name, a, b in zip(("fn", "fxn", "fyn"), out[0], out[1]):
-                assert_bitexact(f"{name} bc{num} {X}x{Y} dx={dxv} rows {dom.r0}:{dom.r1}", a, b)
-
-
-@pytest.mark.parametrize("num,X,Y", [(2, 256, 128), (3, 200, 176), (5, 333, 208), (1, 64, 48), (4, 97, 80)])
-def test_nonadv_fused_equals_two_kernels(env, num, X, Y):
-    _nonadv_fused_check(num, X, Y)
-
-
-@pytest.mark.parametrize("seed", range(3))
-def test_nonadv_fused_random_masks(env, seed):
-    rng = np.random.default_rng(500 + seed)
-    X, Y = 150 + 16 * seed, 96
-    mask = np.zeros((X, Y), dtype=np.uint8)
-    mask[:, :2] = 1; mask[:, -2:] = 1
-    for _ in range(25):
-        i, j = int(rng.integers(0, X - 6)), int(rng.integers(0, Y - 6))
-        mask[i:i + int(rng.integers(1, 7)), j:j + int(rng.integers(1, 7))] = 1
-    mask[:2, 2:-2] = np.where(rng.random((2, Y - 4)) < 0.8, 2, mask[:2, 2:-2])
-    mask[-2:, 2:-2] = np.where(rng.random((2, Y - 4)) < 0.7, 3, mask[-2:, 2:-2])
-    _nonadv_fused_check(1, X, Y, mask_override=mask)
-
-
-def test_fused_non_advection_trajectory_vs_oracle(env):
-    """CipMacSolver.fused_non_advection = True: a whole trajectory through the experimental kernel vs the oracle."""
-    from fs.boundary_condition import build_scene
-    from oracle import oracle as orc
-
-    X, Y = 160, 80
-    dt, dx, re, vc, pressure = 0.05 / Y, 1.0 / Y, 1e4, 5.0, ("jacobi", 6)
-    const, mask = build_scene(3, X, Y)
-    s = make_fs(mask, const, dt, dx, re, "cip", vc, pressure)
-    s.fused_non_advection = True
-    ref = orc.OracleSolver(mask, const, dt, dx, re, "cip", vc, pressure)
-    for n in range(4):
-        s.update(); ref.update()
-        got = fs_state(s)
-        for k, a in ref.state().items():
-            assert_bitexact(f"step {n} {k}", got[k].to_numpy(), a)
-
-
-@pytest.mark.parametrize("num,X,Y", [(2, 256, 128), (5, 384, 192), (2, 1000, 512), (3, 2048, 1024)])
-def test_pair_barrier_variant_equals_literal_iterations(env, num, X, Y):
-    """fused Jacobi variants 6 (pairwise named barriers between neighbouring warps in open-fluid tiles), 7 (resolved
-    slow-cell table) and 8 (both)"""
-    for variant in (6, 7, 8):
-        test_fused_pass_equals_literal_iterations(env, num, X, Y, variant)
-
-
 @pytest.mark.parametrize("num,X,Y,n_iter", [(2, 256, 128, 80), (5, 384, 192, 21), (1, 128, 64, 7), (3, 320, 160, 13), (2, 96, 48, 3),
                                             (4, 200, 96, 4), (1, 288, 352, 10)])
-def test_emitting_tail_pass_equals_literal_update(env, num, X, Y, n_iter):
-    """fs2d_set_tuning(4, 1): the update ends with {fused pass emitting the BC values of its penultimate state, ONE literal
-    iteration}; both physical buffers -- wall-BC cells included -- must still equal n literal iterations."""
-    env.fs2d_set_tuning(4, 1)
+def test_two_literal_tail_equals_literal_update(env, num, X, Y, n_iter):
+    """fs2d_set_tuning(4, 0): the update ends with two literal iterations instead of the default {fused pass emitting the BC
+    values of its penultimate state, ONE literal iteration}; both physical buffers -- wall-BC cells included -- must equal
+    n literal iterations either way (the default tail is what test_fused_update_equals_literal_update runs)."""
+    env.fs2d_set_tuning(4, 0)
     try:
         test_fused_update_equals_literal_update(env, num, X, Y, n_iter)
     finally:
-        env.fs2d_set_tuning(4, 0)
+        env.fs2d_set_tuning(4, 1)
 
 
-def test_marching_vorticity_kernel(env, kernels_golden, masks_small):
-    """fs2d_set_tuning(5, 1): the marching version of VorticityConfinement.apply() behind fs2d_vort_apply"""
-    env.fs2d_set_tuning(5, 1)
-    try:
-        for num in BCS:
-            test_each_kernel_matches_reference_fixture(env, num, kernels_golden, masks_small)
-        for name in TRAJ:
-            if "novc" not in name:
-                test_trajectory_matches_reference_fixture(env, name, masks_small)
-        for seed in range(6):
-            test_random_mask_trajectory_vs_oracle(env, seed)
-        for cfg in CONFIGS:
-            if cfg[6] is not None:
-                test_config_trajectory_vs_oracle(env, cfg)
-    finally:
-        env.fs2d_set_tuning(5, 0)
+@pytest.mark.parametrize("num,X,Y", [(2, 1000, 512), (5, 768, 384), (3, 640, 320)])
+def test_tile_list_classes(env, num, X, Y):
+    """fs2d_fused_order: every tile of the pass is listed exactly once or dropped; dropped tiles have no relaxed / BC cell in
+    their output region; the slow tiles come first; tiles listed as open fluid contain nothing but plain fluid cells."""
+    from fs.boundary_condition import BoundaryCondition, build_scene
+    import ctypes
+    from fs import _lib
+
+    const, mask = build_scene(num, X, Y)
+    bc = BoundaryCondition(const, mask)
+    pcode = bc._pcode.cpu().numpy()
+    for T in (1, 4, 8, 12):
+        rows, cols, hr, hc, tmax = (ctypes.c_int() for _ in range(5))
+        _lib.call("fs2d_fused_tile", T, ctypes.byref(rows), ctypes.byref(cols), ctypes.byref(hr), ctypes.byref(hc), ctypes.byref(tmax))
+        TI, TJ, HI, HJ = rows.value - 2 * hr.value, cols.value - 2 * hc.value, hr.value, hc.value
+        order, n = bc.fused_order(T)
+        _, n_slow, n_skip = bc._fused_orders[(T, bc.dom.r0, bc.dom.r1, bc.dom.clo, bc.dom.chi, 0, 0)][1:]
+        ent = order.cpu().numpy()[:n]
+        tiles, cls = ent & ((1 << 28) - 1), ent >> 28
+        tiles_i, tiles_j = -(-X // TI), -(-Y // TJ)
+        assert n + n_skip == tiles_i * tiles_j and len(set(tiles.tolist())) == n
+        assert (cls[:n_slow] == 1).all() and (cls[n_slow:] == 0).all()
+        listed = set(tiles.tolist())
+        for t in range(tiles_i * tiles_j):
+            r0, c0 = (t // tiles_j) * TI, (t % tiles_j) * TJ
+            out = pcode[r0:min(r0 + TI, X), c0:min(c0 + TJ, Y)] & 15
+            if t not in listed:
+                assert (out == 9).all(), f"dropped tile {t} has work to do"
+        for t in tiles[cls == 0]:
+            r0, c0 = (t // tiles_j) * TI - HI, (t % tiles_j) * TJ - HJ
+            assert r0 > 0 and c0 > 0 and r0 + rows.value < X and c0 + cols.value < Y
+            assert (pcode[r0:r0 + rows.value, c0:c0 + cols.value] == 0).all()
 
 
 def _limit_skip_check(scale):
@@ -891,6 +806,3 @@ def test_limit_skip_trajectory_vs_oracle(env, scale):
     _limit_skip_check(scale)
 
 
-for _t in (test_limit_skip_trajectory_vs_oracle, test_marching_vorticity_kernel, test_emitting_tail_pass_equals_literal_update, test_nonadv_fused_equals_two_kernels, test_nonadv_fused_random_masks, test_fused_non_advection_trajectory_vs_oracle,
-           test_pair_barrier_variant_equals_literal_iterations):
-    globals()[_t.__name__] = experimental(_t)

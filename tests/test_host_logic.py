@@ -176,14 +176,18 @@ def test_swap_counts_follow_the_reference(monkeypatch):
         assert solver.v.current is v_a and solver.p.current is p_a
 
 
-def test_jacobi_schedule_with_fused_passes_equals_literal_iterations(monkeypatch):
+@pytest.mark.parametrize("tail", [1, 0])
+def test_jacobi_schedule_with_fused_passes_equals_literal_iterations(monkeypatch, tail):
     """jacobi_update_distributed's building blocks on one domain: running the plan entry by entry (fused passes through
-    fs2d_jacobi_fused, split into interior + edge launches, literal iterations in between) == fs2d_jacobi_update."""
+    fs2d_jacobi_fused, split into interior + edge launches, literal iterations in between) == fs2d_jacobi_update.
+    tail 1 (default): the plan ends {emitting fused pass, one literal iteration}; 0: two literal iterations."""
     from fake_fs2d import FakeFs2d
     from fs import _lib
     from fs.halo import split_windows
 
     FakeFs2d(_lib.load()).install(monkeypatch)
+    _lib.load().fs2d_set_tuning(4, tail)
+    monkeypatch.setattr(_lib, "_tail_restore", None, raising=False)
     X, Y, n_iter = 512, 64, 19
     solver, _ = _build(2, X, Y, "cip", None, dict(pressure="jacobi", n_iter=n_iter), False)
     jac, bc = solver.pressure_updater, solver._bc
@@ -193,7 +197,10 @@ def test_jacobi_schedule_with_fused_passes_equals_literal_iterations(monkeypatch
     for f in (solver.p.current, solver.p.next):
         f.from_numpy(p0)
     plan = jac.plan(solver.p)
-    assert sum(t if t else 1 for t in plan) == n_iter and any(t > 0 for t in plan) and plan[-2:] == [0, 0]
+    _lib.load().fs2d_set_tuning(4, 1)     # (the schedule is in hand; leave the library in its default state)
+    assert sum(t if t else 1 for t in plan) == n_iter and any(t > 0 for t in plan)
+    assert plan[-1] == 0 and (plan[-2] > 0) == bool(tail)
+    tail_at = len(plan) - 2 if tail else -1
     jac.update(solver.p, solver.v.current)
     want = {k: _buffers(solver)[k].to_numpy().copy() for k in ("p_cur", "p_nxt")}
     for f in (solver.p.current, solver.p.next):
@@ -204,14 +211,14 @@ def test_jacobi_schedule_with_fused_passes_equals_literal_iterations(monkeypatch
     p = solver.p
     a0 = p.current
     src = jac._source(solver.v.current)
-    for t in plan:
+    for k, t in enumerate(plan):
         if t > 0:
             rows, hr = ctypes.c_int(), ctypes.c_int()
             _lib.load().fs2d_fused_tile(t, ctypes.byref(rows), None, ctypes.byref(hr), None, None)
             mid, m = split_windows(bc.dom, rows.value - 2 * hr.value, t)
             assert mid is not None
-            jac._fused(p.next, p.current, src, t, dom=mid)
-            jac._fused(p.next, p.current, src, t, skip=(1, m - 1))
+            jac._fused(p.next, p.current, src, t, dom=mid, emit=k == tail_at)
+            jac._fused(p.next, p.current, src, t, skip=(1, m - 1), emit=k == tail_at)
         else:
             bc.set_pressure_boundary_condition(p.current)
             jac._sweep(p.next, p.current, src, inline_bc=False)
@@ -310,20 +317,21 @@ def test_strips_equal_single_domain_under_gloo(world):
         assert not failures, "\n".join(failures[:5])
     info = res[0][2]
     assert all(i[2] > 0 for i in info)                             # every case really exchanged halos
-    assert info[4][3] > 0 and info[4][4] == 0                       # the 13-iteration case ran fused passes on the strips
+    assert info[4][3] > 0 and info[4][4] > 0                        # the 13-iteration case ran fused passes on the strips, the last one emitting
 
 
-def test_strips_with_the_emitting_tail_and_limit_skip_under_gloo():
-    """fs2d_set_tuning(4, 1) on strips: the schedule ends {emitting fused pass, one literal iteration}; every physical
-    buffer -- the wall cells of both pressure buffers included -- still equals the reference's orchestration.  Also with
-    PressureUpdater.limit_skip: the three source pre-pass windows of a strip accumulate one maximum, consulted by the limiter."""
+def test_strips_with_the_two_literal_tail_and_limit_skip_under_gloo():
+    """fs2d_set_tuning(4, 0) on strips: the schedule ends with two literal iterations instead of the default {emitting fused
+    pass, one literal iteration}; every physical buffer -- the wall cells of both pressure buffers included -- still equals
+    the reference's orchestration.  Also with PressureUpdater.limit_skip: the three source pre-pass windows of a strip
+    accumulate one maximum, consulted by the limiter."""
     from test_distributed import free_port
 
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = free_port()
-    procs = [ctx.Process(target=_strip_worker, args=(r, world, port, q, ((4, 1), ("limit_skip", 1)))) for r in range(world)]
+    procs = [ctx.Process(target=_strip_worker, args=(r, world, port, q, ((4, 0), ("limit_skip", 1)))) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=600) for _ in range(world))
@@ -332,7 +340,7 @@ def test_strips_with_the_emitting_tail_and_limit_skip_under_gloo():
         assert p.exitcode == 0
     for rank, failures, info in res:
         assert not failures, "\n".join(failures[:5])
-    assert res[0][2][4][4] > 0 and any(i[4] > 0 for i in res[0][2][7:])     # the tail pass really ran (scene and random-mask cases)
+    assert all(i[4] == 0 for i in res[0][2])     # no emitting pass anywhere
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -4,7 +4,7 @@ fixtures and the oracle.
 
 What this covers that nothing else can without a GPU: the kernels' indexing and tiling logic -- clamp windows and row
 windows, interior fast paths, the TMA tile pipeline with clamp repair in shared memory, the fused Jacobi kernels' tile
-scheduler / slow-cell lists / edge-row exchange / shrinking valid region (all three variants), barrier placement (a
+lists / slow-cell lists / edge-row exchange / shrinking valid region, barrier and progress-counter placement (a
 missing __syncthreads deadlocks or corrupts here too), TMA box geometry and alignment rules.
 What it does not cover: anything about the hardware -- memory ordering, async-proxy fences, occupancy, performance.  The
 `-m gpu` tests on a B200 remain the parity gate; this module exists so that kernel logic is exercised on every CPU run.
@@ -71,22 +71,35 @@ def test_emu_jacobi_row_range_invariance_and_literal_equivalence(env):
     G.test_jacobi_row_range_invariance_and_literal_equivalence(env, res=128)
 
 
-_FUSED_EMU_CASES = ([(n, x, y, v) for v in (1, 3, 5) for n, x, y in [(1, 128, 64), (2, 256, 128), (4, 200, 96), (5, 384, 192), (1, 288, 352)]]
-                    + [(n, x, y, v) for v in (6, 7, 8) for n, x, y in [(2, 256, 128), (1, 288, 352)]])   # 6, 7, 8: experimental
+_FUSED_EMU_CASES = [(n, x, y, listed) for listed in (True, False)
+                    for n, x, y in [(1, 128, 64), (2, 256, 128), (4, 200, 96), (5, 384, 192), (1, 288, 352), (1, 300, 480)]]
 
 
-@pytest.mark.parametrize("num,X,Y,variant", _FUSED_EMU_CASES)
-def test_emu_fused_pass_equals_literal_iterations(env, num, X, Y, variant):
-    # (1, 288, 352) is wide and tall enough to contain OPEN-FLUID tiles (no wall, BC cell or grid edge in the tile): the
-    # register-tile kernels' fast path with the early prefetch of the next tile; every tile of the smaller grids is "slow"
+@pytest.mark.parametrize("num,X,Y,listed", _FUSED_EMU_CASES)
+def test_emu_fused_pass_equals_literal_iterations(env, num, X, Y, listed):
+    # (1, 288, 352) and (1, 300, 480) are wide and tall enough to contain OPEN-FLUID tiles (no wall, BC cell or grid edge in
+    # the tile): the autonomous-warp path with per-warp TMA refills and the edge-row exchange under progress counters;
+    # every tile of the smaller grids is "slow" (CTA barriers)
     big = X * Y > 40000
-    G.test_fused_pass_equals_literal_iterations(env, num, X, Y, variant, t_list=(3, 8) if big else (1, 2, 4, 6, 8, 11, 12),
+    G.test_fused_pass_equals_literal_iterations(env, num, X, Y, listed, t_list=(1, 3, 8, 12) if big else (1, 2, 4, 6, 8, 11, 12),
                                                 need=2 if big else 3)
 
 
-@pytest.mark.parametrize("variant", [1, 3, 5, 8])
-def test_emu_fused_pass_random_obstacles(env, variant):
-    G.test_fused_pass_random_obstacles(env, 0, variant, size=(320, 160), t_list=(4, 8))
+@pytest.mark.parametrize("num,X,Y,listed", [(4, 480, 640, True), (4, 480, 640, False), (5, 768, 384, True), (5, 768, 384, False)])
+def test_emu_fused_pass_open_and_skipped_tiles(env, num, X, Y, listed):
+    """bc4 at 480 x 640: mostly open-fluid tiles -- consecutive autonomous tiles per CTA, and (unlisted: spread order) slow tiles
+    in between; bc5 at 768 x 384: its thick slab contains tiles without any relaxed cell, which are dropped / skipped"""
+    G._fused_pass_check(num, X, Y, t_list=(3, 8), need=2, listed=listed)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_emu_fused_pass_random_obstacles(env, seed):
+    G.test_fused_pass_random_obstacles(env, seed, size=(320, 160), t_list=(4, 8))
+
+
+@pytest.mark.parametrize("num,X,Y", [(5, 384, 192), (1, 300, 480)])
+def test_emu_tile_list_classes(env, num, X, Y):
+    G.test_tile_list_classes(env, num, X, Y)
 
 
 @pytest.mark.parametrize("num,X,Y,n_iter", [(1, 128, 64, 7), (3, 320, 160, 13), (2, 96, 48, 3)])
@@ -109,9 +122,8 @@ def test_emu_stream_kernel_shapes(env, cfg):
         env.fs2d_set_tuning(3, 1)
 
 
-@pytest.mark.parametrize("variant", [3, 5, 8])
-def test_emu_fused_pass_split_into_interior_and_edge_launches(env, variant):
-    G.test_fused_pass_split_into_interior_and_edge_launches(env, variant, X=420, Y=160)
+def test_emu_fused_pass_split_into_interior_and_edge_launches(env):
+    G.test_fused_pass_split_into_interior_and_edge_launches(env, X=420, Y=160)
 
 
 @pytest.mark.parametrize("num,res,scheme", [(2, 96, "kk"), (5, 100, "upwind")])
@@ -119,59 +131,22 @@ def test_emu_dye_simulator_vs_oracle(env, num, res, scheme):
     G.test_dye_simulator_vs_oracle(env, num, res, scheme)
 
 
-# ---- experimental kernels (off by default in the product; gated on the GPU until measured there) ---------------------------
-@pytest.mark.parametrize("num,X,Y", [(2, 256, 128), (3, 200, 176), (5, 333, 208), (1, 64, 48), (4, 97, 80)])
-def test_emu_nonadv_fused_equals_two_kernels(env, num, X, Y):
-    G._nonadv_fused_check(num, X, Y)
+# ---- the two tails of the update; the limiter skip ------------------------------------------------------------------------
+@pytest.mark.parametrize("num,X,Y,n_iter", [(1, 128, 64, 7), (3, 320, 160, 13), (2, 96, 48, 3), (4, 200, 96, 4), (1, 288, 352, 6)])
+def test_emu_two_literal_tail_equals_literal_update(env, num, X, Y, n_iter):
+    G.test_two_literal_tail_equals_literal_update(env, num, X, Y, n_iter)
 
 
-@pytest.mark.parametrize("seed", range(3))
-def test_emu_nonadv_fused_random_masks(env, seed):
-    G.test_nonadv_fused_random_masks.__wrapped__(env, seed) if hasattr(G.test_nonadv_fused_random_masks, "__wrapped__") else \
-        G.test_nonadv_fused_random_masks(env, seed)
-
-
-def test_emu_fused_non_advection_trajectory_vs_oracle(env):
-    G.test_fused_non_advection_trajectory_vs_oracle(env)
-
-
-def test_emu_pair_barrier_variant_on_a_wide_open_grid(env):
-    """variant 6 where it differs from variant 5: many OPEN-FLUID tiles (pair barriers instead of CTA barriers), every
-    pass size, against literal iterations"""
-    G.test_fused_pass_equals_literal_iterations(env, 1, 300, 480, 6, t_list=(2, 3, 5, 8, 12), need=5)
-
-
-@pytest.mark.parametrize("num,X,Y,n_iter", [(1, 128, 64, 7), (3, 320, 160, 13), (2, 96, 48, 3), (4, 200, 96, 4)])
-def test_emu_emitting_tail_pass_equals_literal_update(env, num, X, Y, n_iter):
-    G.test_emitting_tail_pass_equals_literal_update.__wrapped__(env, num, X, Y, n_iter) if hasattr(
-        G.test_emitting_tail_pass_equals_literal_update, "__wrapped__") else G.test_emitting_tail_pass_equals_literal_update(env, num, X, Y, n_iter)
-
-
-@pytest.mark.parametrize("variant", [6, 7, 8])
-def test_emu_emitting_tail_with_the_other_experimental_variants(env, variant):
-    env.fs2d_set_tuning(1, variant)
-    try:
-        for num, X, Y, n_iter in ((1, 128, 64, 7), (1, 288, 352, 6), (3, 200, 96, 5)):
-            G.test_emitting_tail_pass_equals_literal_update(env, num, X, Y, n_iter)
-    finally:
-        env.fs2d_set_tuning(1, 5)
-
-
-def test_emu_emitting_tail_trajectory_vs_oracle(env):
-    """whole trajectories with the experimental tail: every physical buffer (p.next's wall cells included) vs the oracle"""
-    env.fs2d_set_tuning(4, 1)
-    try:
-        for seed in (0, 3):
-            G.test_random_mask_trajectory_vs_oracle(env, seed)
-    finally:
-        env.fs2d_set_tuning(4, 0)
+def test_emu_emitting_tail_on_open_tiles(env):
+    """the default (emitting) tail on a grid with open-fluid tiles"""
+    G.test_fused_update_equals_literal_update(env, 1, 288, 352, 6)
 
 
 @pytest.mark.parametrize("seed", range(8))
 def test_emu_fused_pass_fuzz(env, seed):
     """random grid sizes and masks (thick blocks / thin walls / stray inflow and outflow cells): for every pass size the host
     layer declares valid, a fused pass == literal iterations.  (A longer run of the same generator -- 140 masks, 1500 passes,
-    variants 1/3/5/6 -- found no mismatch.)"""
+    round-1 kernels -- found no mismatch.)"""
     import numpy as np
 
     rng = np.random.default_rng(7000 + seed)
@@ -188,29 +163,7 @@ def test_emu_fused_pass_fuzz(env, seed):
     if kind == 2:
         for _ in range(6):
             mask[int(rng.integers(3, X - 3)), int(rng.integers(3, Y - 3))] = int(rng.integers(2, 4))
-    for variant in (3, 5, 8):
-        env.fs2d_set_tuning(1, variant)
-        try:
-            G._fused_pass_check(1, X, Y, mask_override=mask, t_list=(1, 3, 8), need=0)
-        finally:
-            env.fs2d_set_tuning(1, 5)
-
-
-def test_emu_marching_vorticity_kernel(env, kernels_golden, masks_small):
-    """fs2d_set_tuning(5, 1): the experimental marching version of VorticityConfinement.apply() behind the same entry point --
-    reference fixtures (all scenes), trajectories with confinement, random masks, IEEE special cases"""
-    env.fs2d_set_tuning(5, 1)
-    try:
-        for num in G.BCS:
-            G.test_each_kernel_matches_reference_fixture(env, num, kernels_golden, masks_small)
-        for name in G.TRAJ:
-            if "novc" not in name:
-                G.test_trajectory_matches_reference_fixture(env, name, masks_small)
-        for seed in (1, 4):
-            G.test_random_mask_trajectory_vs_oracle(env, seed)
-        G.test_config_trajectory_vs_oracle(env, [c for c in G.CONFIGS if c[0] == "kk_r100"][0])
-    finally:
-        env.fs2d_set_tuning(5, 0)
+    G._fused_pass_check(1, X, Y, mask_override=mask, t_list=(1, 3, 8), need=0, listed=seed % 2 == 0)
 
 
 @pytest.mark.parametrize("scale", [0.5, 40.0])
@@ -222,15 +175,15 @@ def test_emu_limit_skip_trajectory_vs_oracle(env, scale):
 @pytest.mark.skipif(os.environ.get("FS2D_EMU_SCHED") is not None, reason="already inside an adversarial-schedule run")
 @pytest.mark.parametrize("seed", [1])
 def test_emu_synchronisation_under_adversarial_warp_schedules(seed):
-    """The kernels with hand-written synchronisation (fused Jacobi variants incl. the open-fluid fast path and the
-    pair-barrier variant, the TMA streaming kernels, the fused non-advection kernel) once more under the emulator's
+    """The kernels with hand-written synchronisation (the fused Jacobi kernel: autonomous warps with per-warp TMA refills
+    and progress counters in open-fluid tiles, CTA barriers in the others; the TMA streaming kernels) once more under the emulator's
     starvation scheduler (FS2D_EMU_SCHED=<seed>): a victim warp -- the leader half of the time -- only runs when every
     other warp is blocked, so warps drift as far apart as the barriers allow.  Seeded mutants with a missing barrier or
     an early TMA refill pass the round-robin schedule but fail here."""
     import subprocess
 
-    sel = ("288-352 or pair_barrier or stream_kernel_shapes or (nonadv_fused_equals and 256) or random_obstacles or "
-           "(emitting_tail_pass and 128-64) or fused_non_advection_trajectory")
+    sel = ("288-352 or 300-480 or stream_kernel_shapes or random_obstacles or emitting_tail_on_open or "
+           "(two_literal_tail and 128-64) or split_into_interior")
     out = subprocess.run([sys.executable, "-m", "pytest", __file__, "-x", "-q", "-p", "no:cacheprovider", "-k", sel],
                          capture_output=True, text=True, timeout=1200, env=dict(os.environ, FS2D_EMU_SCHED=str(seed)))
     assert out.returncode == 0 and " passed" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
