@@ -27,6 +27,7 @@ void set_error(const char *fmt, ...);
 #define FS2D_LAUNCH_CHECK() FS2D_CUDA_CHECK(cudaGetLastError())
 
 extern unsigned long long g_launches;  // every kernel launch of the library bumps this
+constexpr int FS2D_MAX_DEVICES = 64;   // per-device launch facts (SM count, opt-in shared-memory attributes) are kept per ordinal
 int check_dom(const fs2d_dom &d);
 // in-place sparse pressure BC (gather then scatter); no-op for n <= 0
 void launch_p_bc(float *p, const int32_t *tgt, const int32_t *src0, const int32_t *src1, const uint8_t *kind, float *scratch,

@@ -34,7 +34,6 @@
 #include <map>
 #include <mutex>
 #include <utility>
-#include <vector>
 
 #include "fs2d_common.cuh"
 
@@ -74,18 +73,45 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
-// progress counters of the warps in shared memory: publish with release, poll with acquire (CTA scope)
-__device__ __forceinline__ int ld_acquire_smem(const int *p) {
-    int v;
-    asm volatile("ld.acquire.cta.shared::cta.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+// The iteration loop of the autonomous warps addresses shared memory by 32-bit shared-window addresses computed ONCE
+// (ld/st.shared): through generic pointers the compiler re-derived the window base (S2R SR_CgaCtaId + LEA) and the slot /
+// row offsets in every iteration -- a quarter of the loop's non-arithmetic instructions.
+#ifdef FS2D_EMU
+typedef uintptr_t saddr_t;   // CPU emulation (tests/cuda_emu): a plain pointer
+#else
+typedef uint32_t saddr_t;
+#endif
+__device__ __forceinline__ saddr_t smem_addr(const void *p) { return (saddr_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds4_s(saddr_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_smem(int *p, int v) {
-    asm volatile("st.release.cta.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+__device__ __forceinline__ void sts4_s(saddr_t a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
-__device__ __forceinline__ void flag_wait_ge(const int *p, int v) {
-    while (ld_acquire_smem(p) < v) {
-    }
+// progress counters of the warps in shared memory: publish with release, poll with acquire (CTA scope)
+__device__ __forceinline__ void st_release_s(saddr_t a, int v) {
+    asm volatile("st.release.cta.shared::cta.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+// the smaller of two counters (both neighbours of a warp), one look.  `after`: a value the look must not be scheduled ahead
+// of (the compiler otherwise hoists the loads to right behind the previous shared-memory access, where they are useless)
+__device__ __forceinline__ int flag_peek2(saddr_t a, saddr_t b, float after = 0.0f) {
+    int x, y;
+    asm volatile("ld.acquire.cta.shared::cta.b32 %0, [%1];" : "=r"(x) : "r"(a), "f"(after) : "memory");
+    asm volatile("ld.acquire.cta.shared::cta.b32 %0, [%1];" : "=r"(y) : "r"(b), "f"(after) : "memory");
+    return min(x, y);
+}
+// keeps a loop-invariant value in its register: without it the compiler, short of registers, rebuilds such values from
+// threadIdx / SR_CgaCtaId in every iteration
+template <class T>
+__device__ __forceinline__ T keep_in_register(T v) {
+    asm volatile("" : "+r"(v));
+    return v;
+}
+// wait until both counters have reached v; `seen` = an earlier flag_peek2 of the same counters (they only grow)
+__device__ __forceinline__ void flag_wait2(saddr_t a, saddr_t b, int v, int seen) {
+    while (seen < v) seen = flag_peek2(a, b);
 }
 // generic-proxy accesses of a staging buffer are ordered before the async-proxy (TMA) writes that refill it
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -100,12 +126,15 @@ struct FusedGeom {
 // tile row of the tiling for the launch's `row`-th tile row
 __host__ __device__ __forceinline__ int f_tile_row(const FusedGeom &g, int row) { return row < g.skip_from ? row : row + g.skip_n; }
 
-// entries of a tile list: tile index of the launch (row-major over its tile rows) | class << 28
+// entries of a tile list: tile column | tile row of the launch << 14 | class << 28 (no division in the kernel)
 constexpr int FC_PURE = 0;   // every loaded cell is an open-fluid cell inside the grid, away from BC cells and global edges
 constexpr int FC_SLOW = 1;   // anything else that has work to do
 constexpr int FC_SKIP = 2;   // no cell of the output region is relaxed or takes a BC value: nothing to store
 constexpr int FC_SHIFT = 28;
-constexpr int FC_TILE_MASK = (1 << FC_SHIFT) - 1;
+constexpr int FC_ROW_SHIFT = 14;
+constexpr int FC_COL_MASK = (1 << FC_ROW_SHIFT) - 1;   // also the largest tile row / column count of a launch
+__host__ __device__ __forceinline__ int fc_row(int e) { return (e >> FC_ROW_SHIFT) & FC_COL_MASK; }
+__host__ __device__ __forceinline__ int fc_col(int e) { return e & FC_COL_MASK; }
 
 __device__ __forceinline__ float4 lds4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ void sts4(float *p, float a, float b, float c, float d) {
@@ -151,6 +180,71 @@ __device__ __forceinline__ void jacobi_rows(float (&p)[HK][4], const float (&t2)
             S[2] = A[2] + p[k][3] + p[k][1];
             S[3] = A[3] + rt[k] + p[k][2];
         }
+    }
+}
+
+// The same iteration in two phases, for the autonomous warps of open-fluid tiles: phase A needs no other warp (the rows
+// 1..HK-2 of the block, in place, and the old values of the rows 1 and HK-2, which the rows 0 and HK-1 still need);
+// phase B finishes the rows 0 and HK-1 from the neighbouring warps' edge rows.  A warp publishes its own edge rows, runs
+// phase A -- three quarters of the arithmetic -- and only then looks whether its neighbours have published theirs, so it
+// hardly ever waits and the latency of the look-up is off the critical path.  Same expression and order per cell.
+template <int HK>
+__device__ __forceinline__ void jacobi_rows_shuffles(const float (&p)[HK][4], float (&lf)[HK], float (&rt)[HK]) {
+    constexpr uint32_t FULL = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < HK; ++k) {   // j-neighbours of the block's first / last column, all rows: own data only
+        lf[k] = __shfl_up_sync(FULL, p[k][3], 1);
+        rt[k] = __shfl_down_sync(FULL, p[k][0], 1);
+    }
+}
+template <int HK, class Hook>
+__device__ __forceinline__ void jacobi_rows_inner(float (&p)[HK][4], const float (&t2)[HK][4], const float (&t3)[HK][4],
+                                                  const float (&lf)[HK], const float (&rt)[HK], float (&a1)[4], float (&a6)[4],
+                                                  Hook hook) {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        a1[h] = p[1][h];
+        a6[h] = p[HK - 2][h];
+    }
+    float S[4], A[4];
+    S[0] = p[2][0] + p[0][0] + p[1][1] + lf[1];
+    S[1] = p[2][1] + p[0][1] + p[1][2] + p[1][0];
+    S[2] = p[2][2] + p[0][2] + p[1][3] + p[1][1];
+    S[3] = p[2][3] + p[0][3] + rt[1] + p[1][2];
+#pragma unroll
+    for (int k = 2; k <= HK - 1; ++k) {
+        if (k == HK - 1) hook(p[k - 3][0]);   // (a load whose result is wanted after the last row; issued once row k-3 is done)
+        if (k < HK - 1) {   // last use of the old row k-1
+#pragma unroll
+            for (int h = 0; h < 4; ++h) A[h] = p[k + 1][h] + p[k - 1][h];
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) p[k - 1][h] = 0.25f * S[h] + t2[k - 1][h] - t3[k - 1][h];   // finish row k-1
+        if (k < HK - 1) {
+            S[0] = A[0] + p[k][1] + lf[k];
+            S[1] = A[1] + p[k][2] + p[k][0];
+            S[2] = A[2] + p[k][3] + p[k][1];
+            S[3] = A[3] + rt[k] + p[k][2];
+        }
+    }
+}
+template <int HK>
+__device__ __forceinline__ void jacobi_rows_outer(float (&p)[HK][4], const float (&t2)[HK][4], const float (&t3)[HK][4],
+                                                  const float (&lf)[HK], const float (&rt)[HK], const float (&a1)[4],
+                                                  const float (&a6)[4], const float4 up, const float4 dn) {
+    float S[4], Z[4];
+    S[0] = a1[0] + up.x + p[0][1] + lf[0];
+    S[1] = a1[1] + up.y + p[0][2] + p[0][0];
+    S[2] = a1[2] + up.z + p[0][3] + p[0][1];
+    S[3] = a1[3] + up.w + rt[0] + p[0][2];
+    Z[0] = dn.x + a6[0] + p[HK - 1][1] + lf[HK - 1];
+    Z[1] = dn.y + a6[1] + p[HK - 1][2] + p[HK - 1][0];
+    Z[2] = dn.z + a6[2] + p[HK - 1][3] + p[HK - 1][1];
+    Z[3] = dn.w + a6[3] + rt[HK - 1] + p[HK - 1][2];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        p[0][h] = 0.25f * S[h] + t2[0][h] - t3[0][h];
+        p[HK - 1][h] = 0.25f * Z[h] + t2[HK - 1][h] - t3[HK - 1][h];
     }
 }
 
@@ -204,16 +298,6 @@ __device__ __forceinline__ float f_resolved_value(const float *pl, uint32_t x) {
 constexpr int FS_CAP = VN / 8;   // slow cells per tile the resolved table has room for (behind the slow-cell list): 1536
 static_assert(VN <= (1 << 14), "plane offsets must fit 14 bits");
 
-// next entry of the tile list that has work to do, starting at index i with stride `step`; -1 at the end
-__device__ __forceinline__ int f_next_entry(const int *__restrict__ order, int n_order, int &i, int step) {
-    while (i < n_order) {
-        const int e = __ldg(order + i);
-        if ((e >> FC_SHIFT) != FC_SKIP) return e;
-        i += step;
-    }
-    return -1;
-}
-
 // EMIT (the "tail" pass of fs2d_jacobi_update): besides its output the pass stores, into the wall-BC cells of its INPUT
 // array `emit` (= p_in; those cells are never read, their values are recomputed from pcode), the BC values of its
 // PENULTIMATE state.  The reference leaves exactly these values in the wall cells of the buffer its last sweep writes
@@ -223,7 +307,8 @@ __device__ __forceinline__ int f_next_entry(const int *__restrict__ order, int n
 template <bool EMIT>
 __device__ __forceinline__ void jacobi_fused_body(const CUtensorMap *mp, const CUtensorMap *ms, const CUtensorMap *mc,
                                                   float *__restrict__ p_out, const int *__restrict__ order, int n_order,
-                                                  const fs2d_dom &d, const FusedGeom &g, float *emit) {
+                                                  const int *__restrict__ n_order_dev, const fs2d_dom &d, const FusedGeom &g,
+                                                  float *emit) {
     extern __shared__ __align__(1024) float sm[];
     uint8_t *stg_code = reinterpret_cast<uint8_t *>(sm + VOFF_BYTES);
     uint16_t *slow_list = reinterpret_cast<uint16_t *>(sm + VOFF_LIST);
@@ -243,10 +328,9 @@ __device__ __forceinline__ void jacobi_fused_body(const CUtensorMap *mp, const C
     // one warp's slice (8 rows) of the boxes of tile entry `e`
 #define FS2D_ISSUE(e)                                                                                  \
     do {                                                                                               \
-        const int t_ = (e) & FC_TILE_MASK;                                                             \
         const bool slow_ = ((e) >> FC_SHIFT) != FC_PURE;                                               \
-        const int R0_ = d.r0 + f_tile_row(g, t_ / g.tiles_j) * g.TI - g.T + lr0;                       \
-        const int C0_ = (t_ % g.tiles_j) * g.TJ - g.HJ;                                                \
+        const int R0_ = d.r0 + f_tile_row(g, fc_row(e)) * g.TI - g.T + lr0;                            \
+        const int C0_ = fc_col(e) * g.TJ - g.HJ;                                                       \
         mbar_expect_tx(&full[w], slow_ ? TX_SLOW : TX_PURE);                                           \
         tma_load_2d(sm + VOFF_P0 + lr0 * FSJ, mp, C0_, R0_, &full[w]);                                 \
         tma_load_2d(sm + VOFF_SRC + 2 * lr0 * FSJ, ms, 2 * C0_, R0_, &full[w]);                        \
@@ -258,8 +342,13 @@ __device__ __forceinline__ void jacobi_fused_body(const CUtensorMap *mp, const C
         prog[tid] = 0;
     }
     __syncthreads();
+    if (n_order_dev) n_order = __ldg(n_order_dev);   // list built on the launch stream (k_fused_compact): its length lives on the device
+    // the CTA walks the entries blockIdx.x + k * gridDim.x; an entry is read two tiles before it is processed (one tile
+    // before its loads are issued), so the latency of the list is never exposed
+    const int step = (int)gridDim.x;
     int i = blockIdx.x;
-    int entry = f_next_entry(order, n_order, i, (int)gridDim.x);
+    int entry = i < n_order ? __ldg(order + i) : -1;
+    int entry_next = i + step < n_order ? __ldg(order + i + step) : -1;
     if (issuer && entry >= 0) FS2D_ISSUE(entry);
     uint32_t parity = 0;
     int lv = 0;   // edge-row sets published so far by every warp of this CTA (all warps count alike)
@@ -270,14 +359,18 @@ __device__ __forceinline__ void jacobi_fused_body(const CUtensorMap *mp, const C
     const int x_own = VOFF_EX + (w * 2) * FSJ + c;                                  // this warp's top row; + FSJ: bottom row
     const int x_up = w > 0 ? VOFF_EX + ((w - 1) * 2 + 1) * FSJ + c : x_own;         // bottom row of the warp above
     const int x_dn = w < V_WARPS - 1 ? VOFF_EX + ((w + 1) * 2) * FSJ + c : x_own + FSJ;
+    // the same as shared-window addresses of exchange plane 0 (plane 1: + EX_PLANE_BYTES), and the neighbours' counters (a rim
+    // warp has one neighbour: it looks at that one twice)
+    const saddr_t xa_own = keep_in_register(smem_addr(sm + x_own));   // the others are fixed distances away (x_up, x_dn above)
+    const saddr_t fa_own = keep_in_register(smem_addr(&prog[w]));
+    const bool w_first = w == 0, w_last = w == V_WARPS - 1;
+    constexpr saddr_t EX_PLANE_BYTES = VEX_PLANE * 4, ROW_BYTES = FSJ * 4;
 
     while (entry >= 0) {
-        const int tile = entry & FC_TILE_MASK;
         const bool tile_slow = (entry >> FC_SHIFT) != FC_PURE;
-        int i_next = i + (int)gridDim.x;
-        const int entry_next = f_next_entry(order, n_order, i_next, (int)gridDim.x);
-        const int R0 = d.r0 + f_tile_row(g, tile / g.tiles_j) * g.TI - g.T;   // local-array row of tile row 0
-        const int C0 = (tile % g.tiles_j) * g.TJ - g.HJ;                      // column of tile column 0
+        const int entry_next2 = i + 2 * step < n_order ? __ldg(order + i + 2 * step) : -1;
+        const int R0 = d.r0 + f_tile_row(g, fc_row(entry)) * g.TI - g.T;   // local-array row of tile row 0
+        const int C0 = fc_col(entry) * g.TJ - g.HJ;                          // column of tile column 0
         float p[HK][4], t2[HK][4], t3[HK][4];
 
         if (!tile_slow) {
@@ -306,15 +399,20 @@ __device__ __forceinline__ void jacobi_fused_body(const CUtensorMap *mp, const C
             // still reads: to produce set n + 2 it needs the neighbour's set n + 1, made after the neighbour read set n.
             for (int s = 0; s < g.T; ++s) {
                 const int set = lv + s;
-                float *xw = sm + (set & 1) * VEX_PLANE;
-                sts4(xw + x_own, p[0][0], p[0][1], p[0][2], p[0][3]);
-                sts4(xw + x_own + FSJ, p[HK - 1][0], p[HK - 1][1], p[HK - 1][2], p[HK - 1][3]);
+                const saddr_t xo = xa_own + ((set & 1) ? EX_PLANE_BYTES : 0);
+                sts4_s(xo, p[0][0], p[0][1], p[0][2], p[0][3]);
+                sts4_s(xo + ROW_BYTES, p[HK - 1][0], p[HK - 1][1], p[HK - 1][2], p[HK - 1][3]);
+                float lf[HK], rt[HK], a1[4], a6[4];
+                jacobi_rows_shuffles<HK>(p, lf, rt);   // (the edge-row stores drain meanwhile: the release below does not wait)
                 __syncwarp();
-                if (issuer) st_release_smem(&prog[w], set + 1);
-                if (w > 0) flag_wait_ge(&prog[w - 1], set + 1);
-                if (w < V_WARPS - 1) flag_wait_ge(&prog[w + 1], set + 1);
-                const float4 upv = lds4(xw + x_up), dnv = lds4(xw + x_dn);
-                jacobi_rows<HK, true>(p, t2, t3, FULL, upv, dnv);
+                if (issuer) st_release_s(fa_own, set + 1);
+                const saddr_t fa_up = w_first ? fa_own + 4 : fa_own - 4, fa_dn = w_last ? fa_own - 4 : fa_own + 4;
+                int seen = 0;
+                // rows 1..6 need no other warp; three rows before they are done, take a first look at the neighbours' counters
+                jacobi_rows_inner<HK>(p, t2, t3, lf, rt, a1, a6, [&](float after) { seen = flag_peek2(fa_up, fa_dn, after); });
+                flag_wait2(fa_up, fa_dn, set + 1, seen);
+                const float4 upv = lds4_s(w_first ? xo : xo - ROW_BYTES), dnv = lds4_s(w_last ? xo + ROW_BYTES : xo + 2 * ROW_BYTES);
+                jacobi_rows_outer<HK>(p, t2, t3, lf, rt, a1, a6, upv, dnv);
             }
             lv += g.T;
             // ---- store the inner (TI x TJ) cells that belong to rows [r0, r1) -----------------------------------------
@@ -473,8 +571,9 @@ __device__ __forceinline__ void jacobi_fused_body(const CUtensorMap *mp, const C
             }
         }
         parity ^= 1;
-        i = i_next;
+        i += step;
         entry = entry_next;
+        entry_next = entry_next2;
     }
 #undef FS2D_ISSUE
 }
@@ -482,23 +581,21 @@ __device__ __forceinline__ void jacobi_fused_body(const CUtensorMap *mp, const C
 __global__ void __launch_bounds__(V_THREADS, 1)
     k_jacobi_fused(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_src,
                    const __grid_constant__ CUtensorMap map_code, float *__restrict__ p_out, const int *__restrict__ order,
-                   int n_order, fs2d_dom d, FusedGeom g) {
+                   int n_order, const int *__restrict__ n_order_dev, fs2d_dom d, FusedGeom g) {
     // the descriptors must be addressed in the kernel-parameter space (the TMA unit cannot read a copy that the compiler
     // spilled to local memory): take their addresses here
-    jacobi_fused_body<false>(&map_p, &map_src, &map_code, p_out, order, n_order, d, g, nullptr);
+    jacobi_fused_body<false>(&map_p, &map_src, &map_code, p_out, order, n_order, n_order_dev, d, g, nullptr);
 }
 __global__ void __launch_bounds__(V_THREADS, 1)
     k_jacobi_fused_emit(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_src,
                         const __grid_constant__ CUtensorMap map_code, float *__restrict__ p_out, const int *__restrict__ order,
-                        int n_order, fs2d_dom d, FusedGeom g, float *emit) {
-    jacobi_fused_body<true>(&map_p, &map_src, &map_code, p_out, order, n_order, d, g, emit);
+                        int n_order, const int *__restrict__ n_order_dev, fs2d_dom d, FusedGeom g, float *emit) {
+    jacobi_fused_body<true>(&map_p, &map_src, &map_code, p_out, order, n_order, n_order_dev, d, g, emit);
 }
 
-// Class of every tile of a launch: one CTA of 128 threads per tile, thread = tile column.  out[(t * mul) % n_tiles] =
-// t | class << 28 (mul = 1: identity; the on-the-fly path spreads the tiles with a multiplier coprime to n_tiles so that
-// the tiles a CTA walks, blockIdx.x + k * gridDim.x, are not all in one tile column).
+// Class of every tile of a launch: one CTA of 128 threads per tile, thread = tile column.  out[t] = t | class << 28.
 __global__ void __launch_bounds__(FSJ)
-    k_fused_classify(const uint8_t *__restrict__ pcode, fs2d_dom d, FusedGeom g, int *__restrict__ out, int n_tiles, int mul) {
+    k_fused_classify(const uint8_t *__restrict__ pcode, fs2d_dom d, FusedGeom g, int *__restrict__ out) {
     const int t = blockIdx.x;
     const int R0 = d.r0 + f_tile_row(g, t / g.tiles_j) * g.TI - g.T;
     const int C0 = (t % g.tiles_j) * g.TJ - g.HJ;
@@ -519,7 +616,47 @@ __global__ void __launch_bounds__(FSJ)
     const int all_pure = __syncthreads_and(pure ? 1 : 0), all_skip = __syncthreads_and(skip ? 1 : 0);
     if (tc == 0) {
         const int cls = all_skip ? FC_SKIP : (all_pure ? FC_PURE : FC_SLOW);
-        out[(int)(((long long)t * mul) % n_tiles)] = t | (cls << FC_SHIFT);
+        out[t] = (t % g.tiles_j) | ((t / g.tiles_j) << FC_ROW_SHIFT) | (cls << FC_SHIFT);
+    }
+}
+
+// The tile list of a launch from the classes: the slow tiles first (dealt round-robin to the persistent CTAs, so each gets
+// its share of the expensive ones and the cheap tiles fill the tail), then the open-fluid tiles in natural order (CTAs that
+// run side by side then work on neighbouring tiles, whose halos overlap in L2); tiles with nothing to store are dropped.
+// One CTA; counts = {entries, slow entries, dropped}.
+constexpr int CP_THREADS = 1024;
+__global__ void __launch_bounds__(CP_THREADS) k_fused_compact(const int *__restrict__ cls, int n, int *__restrict__ out, int *counts) {
+    __shared__ int s_slow[CP_THREADS], s_pure[CP_THREADS];
+    const int tid = threadIdx.x;
+    const int chunk = (n + CP_THREADS - 1) / CP_THREADS;
+    const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
+    int n_slow = 0, n_pure = 0;
+    for (int k = lo; k < hi; ++k) {
+        const int c = cls[k] >> FC_SHIFT;
+        n_slow += c == FC_SLOW;
+        n_pure += c == FC_PURE;
+    }
+    s_slow[tid] = n_slow;
+    s_pure[tid] = n_pure;
+    __syncthreads();
+    for (int off = 1; off < CP_THREADS; off <<= 1) {   // inclusive scan
+        const int a = tid >= off ? s_slow[tid - off] : 0, b = tid >= off ? s_pure[tid - off] : 0;
+        __syncthreads();
+        s_slow[tid] += a;
+        s_pure[tid] += b;
+        __syncthreads();
+    }
+    const int tot_slow = s_slow[CP_THREADS - 1], tot_pure = s_pure[CP_THREADS - 1];
+    int o_slow = s_slow[tid] - n_slow, o_pure = tot_slow + s_pure[tid] - n_pure;
+    for (int k = lo; k < hi; ++k) {
+        const int e = cls[k], c = e >> FC_SHIFT;
+        if (c == FC_SLOW) out[o_slow++] = e;
+        else if (c == FC_PURE) out[o_pure++] = e;
+    }
+    if (tid == 0) {
+        counts[0] = tot_slow + tot_pure;
+        counts[1] = tot_slow;
+        counts[2] = n - tot_slow - tot_pure;
     }
 }
 
@@ -613,19 +750,37 @@ static int make_geom(FusedGeom *g, const fs2d_dom &d, int T, int skip_from, int 
     g->skip_n = skip_n;
     g->tiles_i = all_rows - skip_n;
     g->tiles_j = (d.Y + g->TJ - 1) / g->TJ;
-    if ((long long)g->tiles_i * g->tiles_j > FC_TILE_MASK) {
-        set_error("bad argument: more than 2^28 tiles in one fused pass");
+    if (g->tiles_i > FC_COL_MASK || g->tiles_j > FC_COL_MASK) {
+        set_error("bad argument: more than 2^14 tile rows or columns in one fused pass");
         return FS2D_E_BADARG;
     }
     return FS2D_OK;
 }
 
-// a multiplier coprime to n (spreads the natural tile order of the on-the-fly path over the CTAs)
-static int coprime_multiplier(int n) {
-    static const int primes[] = {7919, 104729, 611953, 15485863};
-    for (int p : primes)
-        if (n % p != 0 && p % n != 0) return p % n;
-    return 1;
+// classes -> tile list on stream s: classes into scratch, list into `out` (n_tiles ints), counts into counts_dev (3 ints)
+static int build_order(const uint8_t *pcode, const fs2d_dom &d, const FusedGeom &g, int *cls_tmp, int *out, int *counts_dev,
+                       cudaStream_t s) {
+    const int n_tiles = g.tiles_i * g.tiles_j;
+    g_launches += 2;
+    k_fused_classify<<<n_tiles, FSJ, 0, s>>>(pcode, d, g, cls_tmp);
+    k_fused_compact<<<1, CP_THREADS, 0, s>>>(cls_tmp, n_tiles, out, counts_dev);
+    return FS2D_OK;
+}
+
+// scratch of (device, stream) with room for n_tiles classes + n_tiles entries + 4 counters
+static int get_scratch(int dev, cudaStream_t s, int n_tiles, int **buf) {
+    std::lock_guard<std::mutex> lock(g_fused_mutex);
+    Scratch &sc = g_scratch[std::make_pair(dev, s)];
+    const int need = 2 * n_tiles + 4;
+    if (sc.cap < need) {
+        if (sc.buf) FS2D_CUDA_CHECK(cudaFree(sc.buf));   // (cudaFree waits for the passes still using it)
+        sc.buf = nullptr;
+        sc.cap = 0;
+        FS2D_CUDA_CHECK(cudaMalloc(&sc.buf, sizeof(int) * (size_t)need));
+        sc.cap = need;
+    }
+    *buf = sc.buf;
+    return FS2D_OK;
 }
 
 int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t *pcode, const fs2d_dom &d, int T,
@@ -640,24 +795,14 @@ int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t 
     if (int e = make_map(&mp, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p_in, d.Y, d.rows, FSJ, HK)) return e;
     if (int e = make_map(&ms, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, src, 2ull * d.Y, d.rows, 2 * FSJ, HK)) return e;
     if (int e = make_map(&mc, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, pcode, d.Y, d.rows, FCW, HK)) return e;
-    if (!order) {   // no precomputed tile list (fs2d_fused_order): classify now, on the launch stream
+    const int *n_order_dev = nullptr;
+    if (!order) {   // no precomputed tile list (fs2d_fused_order): build it now, on the launch stream; its length stays on the device
         int *buf = nullptr;
-        {
-            std::lock_guard<std::mutex> lock(g_fused_mutex);
-            Scratch &sc = g_scratch[std::make_pair(dev, s)];
-            if (sc.cap < n_tiles) {
-                if (sc.buf) FS2D_CUDA_CHECK(cudaFree(sc.buf));   // stream-ordered reuse: earlier passes on this stream are done with it first
-                sc.buf = nullptr;
-                sc.cap = 0;
-                FS2D_CUDA_CHECK(cudaMalloc(&sc.buf, sizeof(int) * (size_t)n_tiles));
-                sc.cap = n_tiles;
-            }
-            buf = sc.buf;
-        }
-        ++g_launches;
-        k_fused_classify<<<n_tiles, FSJ, 0, s>>>(pcode, d, g, buf, n_tiles, coprime_multiplier(n_tiles));
-        order = buf;
-        n_order = n_tiles;
+        if (int e = get_scratch(dev, s, n_tiles, &buf)) return e;
+        if (int e = build_order(pcode, d, g, buf, buf + n_tiles, buf + 2 * n_tiles, s)) return e;
+        order = buf + n_tiles;
+        n_order_dev = buf + 2 * n_tiles;
+        n_order = n_tiles;   // upper bound (grid size); the kernel reads the true length
     }
     if (n_order <= 0) return FS2D_OK;
     if (n_order > n_tiles) {
@@ -666,8 +811,8 @@ int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t 
     }
     const int grid = n_order < n_sm ? n_order : n_sm;
     ++g_launches;
-    if (emit) k_jacobi_fused_emit<<<grid, dim3(32, V_WARPS, 1), V_SMEM, s>>>(mp, ms, mc, p_out, order, n_order, d, g, const_cast<float *>(p_in));
-    else k_jacobi_fused<<<grid, dim3(32, V_WARPS, 1), V_SMEM, s>>>(mp, ms, mc, p_out, order, n_order, d, g);
+    if (emit) k_jacobi_fused_emit<<<grid, dim3(32, V_WARPS, 1), V_SMEM, s>>>(mp, ms, mc, p_out, order, n_order, n_order_dev, d, g, const_cast<float *>(p_in));
+    else k_jacobi_fused<<<grid, dim3(32, V_WARPS, 1), V_SMEM, s>>>(mp, ms, mc, p_out, order, n_order, n_order_dev, d, g);
     return FS2D_OK;
 }
 
@@ -710,27 +855,13 @@ int fs2d_fused_order(const uint8_t *pcode, fs2d_dom d, int T, int skip_from, int
     if (n_tiles == 0) return FS2D_OK;
     FS2D_REQUIRE(cap >= n_tiles, "tile-list buffer too small (needs one entry per tile of the pass)");
     cudaStream_t s = (cudaStream_t)stream;
-    ++g_launches;
-    k_fused_classify<<<n_tiles, FSJ, 0, s>>>(pcode, d, g, order, n_tiles, 1);
+    int dev = 0, n_sm = 0, *buf = nullptr;
+    if (int e = device_info(&dev, &n_sm)) return e;
+    if (int e = get_scratch(dev, s, n_tiles, &buf)) return e;
+    if (int e = build_order(pcode, d, g, buf, order, buf + 2 * n_tiles, s)) return e;
     FS2D_LAUNCH_CHECK();
-    std::vector<int> cls((size_t)n_tiles), sorted;
-    FS2D_CUDA_CHECK(cudaMemcpyAsync(cls.data(), order, sizeof(int) * (size_t)n_tiles, cudaMemcpyDeviceToHost, s));
+    FS2D_CUDA_CHECK(cudaMemcpyAsync(counts, buf + 2 * n_tiles, 3 * sizeof(int), cudaMemcpyDeviceToHost, s));
     FS2D_CUDA_CHECK(cudaStreamSynchronize(s));
-    sorted.reserve((size_t)n_tiles);
-    int n_slow = 0, n_skip = 0;
-    for (int e : cls)   // slow tiles first: dealt round-robin to the CTAs, the cheap tiles fill the tail
-        if ((e >> FC_SHIFT) == FC_SLOW) { sorted.push_back(e); ++n_slow; }
-    for (int e : cls) {
-        if ((e >> FC_SHIFT) == FC_PURE) sorted.push_back(e);
-        else if ((e >> FC_SHIFT) == FC_SKIP) ++n_skip;
-    }
-    if (!sorted.empty()) {
-        FS2D_CUDA_CHECK(cudaMemcpyAsync(order, sorted.data(), sizeof(int) * sorted.size(), cudaMemcpyHostToDevice, s));
-        FS2D_CUDA_CHECK(cudaStreamSynchronize(s));
-    }
-    counts[0] = (int)sorted.size();
-    counts[1] = n_slow;
-    counts[2] = n_skip;
     return FS2D_OK;
 }
 

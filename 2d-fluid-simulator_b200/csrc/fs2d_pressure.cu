@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(TX *TY)
     else b_p_source<true>(src, vc, d, dt, dx);
 }
 
-// EXPERIMENTAL (fs2d_pressure_source_vmax / fs2d_limit_if): the same pre-pass that also leaves max |v|^2 over every cell it
+// fs2d_pressure_source_vmax / fs2d_limit_if (PressureUpdater.limit_skip): the same pre-pass that also leaves max |v|^2 over every cell it
 // reads in *vmax (bit pattern of a non-negative float, atomicMax; NaNs are ignored exactly like limit_field ignores them).
 // Its four neighbour loads cover every cell of the rows [r0, r1), v does not change between this pre-pass and limit_field
 // at the end of the step (fs/solver.py:200-202), and sqrtf is monotone: if sqrtf(max) <= limit, limit_field is a no-op and
@@ -74,7 +74,10 @@ __device__ __forceinline__ void b_p_source_vmax(float *__restrict__ src, const f
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && m > 0.0f) atomicMax(vmax, __float_as_uint(m));
+    // one atomic per warp at most, and only while the warp's maximum still beats the recorded one (a stale read only costs an
+    // extra atomic): 2 M same-address atomics per pass serialised in L2 and cost more than the limiter pass they replace
+    if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && __float_as_uint(m) > *reinterpret_cast<volatile unsigned int *>(vmax))
+        atomicMax(vmax, __float_as_uint(m));
 }
 __global__ void __launch_bounds__(TX *TY)
     k_p_source_vmax(float *__restrict__ src, const float *__restrict__ vc, fs2d_dom d, float dt, float dx, unsigned int *vmax) {
@@ -297,8 +300,8 @@ int fs2d_jacobi_sweep(float *pn, const float *pc, const float *src, const uint8_
 // number of buffer flips (= number of entries) must have the parity of n_sweeps so that the two PHYSICAL
 // buffers end up exactly as in the reference.
 static int plan_jacobi(int n_sweeps, int fuse_mask, int *out, int cap, int tail_literal = 2) {
-    static const float pass_cost[13] = {0, 214, 237, 226, 245, 295, 340, 381, 420, 501, 547, 607, 655};
-    const float lit_cost = 195.0f;
+    static const float pass_cost[13] = {0, 170, 179, 182, 202, 247, 277, 314, 360, 428, 470, 527, 567};   // r02, autonomous warps
+    const float lit_cost = 190.0f;
     const int n_lit = n_sweeps < tail_literal ? n_sweeps : tail_literal, n_f = n_sweeps - n_lit;
     int n = 0;
     if (n_f > 0 && (fuse_mask & 0x1FFE) && n_f < 4096) {

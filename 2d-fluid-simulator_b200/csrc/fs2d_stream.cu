@@ -274,18 +274,19 @@ int g_stream_cfg = 1;   // fs2d_set_tuning(3, v): {stages x CTAs/SM x threads}: 
 template <class Op, int ST_STAGES, int MIN_CTAS, int ST_THREADS>
 static int launch_stream_cfg(const Op &op, const float *const *fields, const uint8_t *mask, const fs2d_dom &d, cudaStream_t s) {
     using L = StageLayout<Op>;
-    static int n_sm = 0;
-    static bool attr_set = false;
     constexpr int SMEM = L::STAGE_BYTES * ST_STAGES;
-    if (!n_sm) {
-        int dev = 0;
-        FS2D_CUDA_CHECK(cudaGetDevice(&dev));
-        FS2D_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    }
-    if (!attr_set) {
+    // per DEVICE (a process may drive several): SM count, and the opt-in shared-memory size of this instantiation
+    static int n_sm_of[FS2D_MAX_DEVICES] = {};
+    static bool attr_set_on[FS2D_MAX_DEVICES] = {};
+    int dev = 0;
+    FS2D_CUDA_CHECK(cudaGetDevice(&dev));
+    FS2D_REQUIRE(dev >= 0 && dev < FS2D_MAX_DEVICES, "device ordinal out of range");
+    if (!n_sm_of[dev]) FS2D_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
+    if (!attr_set_on[dev]) {
         FS2D_CUDA_CHECK(cudaFuncSetAttribute(k_stream<Op, ST_STAGES, MIN_CTAS, ST_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        attr_set = true;
+        attr_set_on[dev] = true;
     }
+    const int n_sm = n_sm_of[dev];
     StreamMaps<Op::NF> maps;
     for (int k = 0; k < Op::NF; ++k)
         if (int e = make_map(&maps.f[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, fields[k], (uint64_t)Op::chan(k) * d.Y, d.rows,

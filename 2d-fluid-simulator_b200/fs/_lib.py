@@ -113,6 +113,8 @@ def ptr(t: torch.Tensor | None) -> int | None:
 
 
 def stream() -> int:
+    """The current stream of the CURRENT device.  Fields live on the device that was current when their BoundaryCondition
+    was built (BoundaryCondition refuses any other `device=`), so this is also the stream of the tensors' device."""
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -23,54 +23,95 @@ FLUID, WALL, INFLOW, OUTFLOW = 0, 1, 2, 3
 class BoundaryCondition:
     """bc_const: (X, Y, 2) f32 inflow velocities; bc_mask: (X, Y) u8 cell types (:13, :78-85)."""
 
-    def __init__(self, bc_const: npt.NDArray, bc_mask: npt.NDArray, device=None, partition=None) -> None:
+    #: rows of scene a rank needs beyond its owned rows when it builds only its strip (`row_offset`): the tables and the
+    #: fused-pass validity analysis look at most 2 * 12 + 2 rows past the owned rows (a dependency cone grows by at most two
+    #: rows per iteration, 12 iterations per pass at most)
+    STRIP_MARGIN = 32
+
+    def __init__(self, bc_const: npt.NDArray, bc_mask: npt.NDArray, device=None, partition=None, row_offset: int | None = None) -> None:
+        """row_offset (not in the reference; needs `partition`): the arrays hold only the global rows [row_offset, row_offset +
+        len) of the scene -- at least the rank's owned rows +- STRIP_MARGIN, clipped to the grid (build_scene(..., rows=...),
+        strip_rows()) -- instead of the whole grid; every table comes out identical to a build from the global arrays."""
         bc_const = np.ascontiguousarray(bc_const, dtype=np.float32)
         bc_mask = np.ascontiguousarray(bc_mask, dtype=np.uint8)
         if bc_const.shape[:2] != bc_mask.shape or bc_const.shape[2:] != (2,):
             raise ValueError(f"bc_const {bc_const.shape} / bc_mask {bc_mask.shape} shape mismatch")
         self.device = torch.device(device) if device is not None else default_device()
-        self._global_resolution = (int(bc_mask.shape[0]), int(bc_mask.shape[1]))
+        if self.device.type == "cuda" and self.device.index not in (None, torch.cuda.current_device()):
+            # kernels are launched on the current device's stream (fs/_lib.py:stream): pointers of another device would fault
+            raise ValueError(f"BoundaryCondition(device={self.device}) while cuda:{torch.cuda.current_device()} is current: "
+                             "call torch.cuda.set_device() first (one process per GPU)")
+        XA, Y = int(bc_mask.shape[0]), int(bc_mask.shape[1])      # rows the arrays hold
+        if row_offset is None:
+            A0, X = 0, XA
+        else:
+            if partition is None:
+                raise ValueError("row_offset needs the partition it belongs to")
+            A0, X = int(row_offset), partition.x_global
+        self._global_resolution = (X, Y)
         if partition is None:
             from fs.distributed import Partition
 
-            partition = Partition.single(self._global_resolution[0])
+            partition = Partition.single(X)
+        if partition.x_global != X:
+            raise ValueError(f"partition of {partition.x_global} rows for a scene of {X} rows")
         self.partition = partition
-        X, Y = self._global_resolution
         w0, w1 = partition.window()          # global rows held in the local array (owned + halo)
         g0, g1 = partition.owned()           # global rows this rank updates
+        if row_offset is not None:
+            need = self.strip_rows(partition)
+            if A0 > need[0] or A0 + XA < need[1]:
+                raise ValueError(f"arrays hold the rows [{A0}, {A0 + XA}) but rank {partition.rank} needs {need} (owned rows +- STRIP_MARGIN)")
         self._resolution = (g1 - g0, Y)
         self.halo = partition.halo
+        self._row_offset = A0
 
+        # from here on rows are indexed in ARRAY coordinates (global row - A0); array edges that are not grid edges lie in
+        # the margin, where the clamped neighbour reads of the table builders produce values nobody uses
         gmask = torch.from_numpy(bc_mask).to(self.device)
         pcode = _bc_tables.pressure_codes(gmask)
         lo, hi = max(w0, 0), min(w1, X)      # part of the window that exists globally
 
-        def local(t_global: torch.Tensor, fill=0) -> torch.Tensor:
-            out = torch.full((w1 - w0,) + tuple(t_global.shape[1:]), fill, dtype=t_global.dtype, device=self.device)
-            out[lo - w0:hi - w0] = t_global[lo:hi]
+        def local(t_array: torch.Tensor, fill=0) -> torch.Tensor:
+            out = torch.full((w1 - w0,) + tuple(t_array.shape[1:]), fill, dtype=t_array.dtype, device=self.device)
+            out[lo - w0:hi - w0] = t_array[lo - A0:hi - A0]
             return out.contiguous()
 
         self._bc_mask = local(gmask, WALL)
         self._pcode = local(_bc_tables.pack_pcode(pcode), _bc_tables.PC_W_NONE)
-        self._pcode_global = pcode           # unpacked codes of the whole grid (fused-kernel validity analysis)
+        self._pcode_global = pcode           # unpacked codes of the array's rows (fused-kernel validity analysis)
         self._fused_ok: dict[int, bool] = {}
         self._fused_orders: dict[tuple, tuple] = {}
-        self._bc_const = local(torch.from_numpy(bc_const).to(self.device))
+        self._bc_const = self._upload_rows(bc_const, lo, hi, w0, w1, A0)
         # BC targets: owned rows plus the halo rows whose sources are inside the window
         tl, th = max(lo, g0 - max(self.halo - 2, 0)), min(hi, g1 + max(self.halo - 2, 0))
-        self._vel_table = _bc_tables.velocity_table(gmask, tl, th, w0, w1)
-        self._p_table = _bc_tables.pressure_table(pcode, max(lo, g0 - max(self.halo - 1, 0)),
-                                                  min(hi, g1 + max(self.halo - 1, 0)), w0, w1)
+        self._vel_table = _bc_tables.velocity_table(gmask, tl - A0, th - A0, w0 - A0, w1 - A0)
+        self._p_table = _bc_tables.pressure_table(pcode, max(lo, g0 - max(self.halo - 1, 0)) - A0,
+                                                  min(hi, g1 + max(self.halo - 1, 0)) - A0, w0 - A0, w1 - A0)
         stale = _bc_tables.exposed_stale_cells(pcode)
         if stale.numel():
             si, sj = stale // Y, stale % Y
-            keep = (si >= lo) & (si < hi)
-            stale = (si[keep] - w0) * Y + sj[keep]
+            keep = (si >= lo - A0) & (si < hi - A0)
+            stale = (si[keep] - (w0 - A0)) * Y + sj[keep]
         self._exposed_stale = stale
         n = max(self._vel_table["n"], self._p_table["n"], 1)
         self._scratch = torch.empty(2 * n, dtype=torch.float32, device=self.device)
         self.dom = _lib.Dom(rows=w1 - w0, Y=Y, r0=g0 - w0, r1=g1 - w0, clo=lo - w0, chi=hi - 1 - w0, gi0=w0)
         del gmask
+
+    @classmethod
+    def strip_rows(cls, partition) -> tuple[int, int]:
+        """global rows [a, b) of the scene a rank must hold to build its BoundaryCondition with `row_offset=a`"""
+        g0, g1 = partition.owned()
+        m = max(cls.STRIP_MARGIN, partition.halo + 4)
+        return max(0, g0 - m), min(partition.x_global, g1 + m)
+
+    def _upload_rows(self, host: npt.NDArray, lo: int, hi: int, w0: int, w1: int, A0: int, fill=0) -> torch.Tensor:
+        """local (window-shaped) device copy of a per-cell host array that holds the global rows from A0 on: only the window's
+        rows cross PCIe"""
+        out = torch.full((w1 - w0,) + tuple(host.shape[1:]), fill, dtype=torch.from_numpy(host[:0]).dtype, device=self.device)
+        out[lo - w0:hi - w0] = torch.from_numpy(np.ascontiguousarray(host[lo - A0:hi - A0])).to(self.device)
+        return out.contiguous()
 
     # -- reference API ---------------------------------------------------------------------
     def set_velocity_boundary_condition(self, vc: Field) -> None:
@@ -118,7 +159,7 @@ class BoundaryCondition:
                   ctypes.byref(tmax))
         key = (T, rows.value, cols.value)   # the tile depends on the kernel variant (fs2d_set_tuning)
         if key not in self._fused_ok:
-            g0, g1 = self.partition.owned()
+            g0, g1 = (g - self._row_offset for g in self.partition.owned())      # array coordinates
             ok = (1 <= T <= tmax.value and self._global_resolution[1] % 16 == 0 and self._p_table["feed"]["n"] == 0
                   and (self.partition.world == 1 or self.halo >= T + 1)
                   and _bc_tables.fused_reach_ok(self._pcode_global, T, rows.value, cols.value, hr.value, hc.value, g0, g1,
@@ -159,17 +200,16 @@ class BoundaryCondition:
 class DyeBoundaryCondition(BoundaryCondition):
     """(:88-112) adds the inflow dye colours bc_dye (X, Y, 3) f32 and set_dye_boundary_condition."""
 
-    def __init__(self, bc_const: npt.NDArray, bc_dye: npt.NDArray, bc_mask: npt.NDArray, device=None, partition=None) -> None:
-        super().__init__(bc_const, bc_mask, device=device, partition=partition)
+    def __init__(self, bc_const: npt.NDArray, bc_dye: npt.NDArray, bc_mask: npt.NDArray, device=None, partition=None,
+                 row_offset: int | None = None) -> None:
+        super().__init__(bc_const, bc_mask, device=device, partition=partition, row_offset=row_offset)
         bc_dye = np.ascontiguousarray(bc_dye, dtype=np.float32)
-        if bc_dye.shape != tuple(self._global_resolution) + (3,):
-            raise ValueError(f"bc_dye {bc_dye.shape} does not match the mask {self._global_resolution}")
+        if bc_dye.shape != tuple(np.shape(bc_mask)) + (3,):
+            raise ValueError(f"bc_dye {bc_dye.shape} does not match the mask {np.shape(bc_mask)}")
         X, Y = self._global_resolution
         w0, w1 = self.partition.window()
         lo, hi = max(w0, 0), min(w1, X)
-        loc = torch.zeros((w1 - w0, Y, 3), dtype=torch.float32, device=self.device)
-        loc[lo - w0:hi - w0] = torch.from_numpy(bc_dye[lo:hi]).to(self.device)
-        self._bc_dye = loc.contiguous()
+        self._bc_dye = self._upload_rows(bc_dye, lo, hi, w0, w1, self._row_offset)
         self._dye_tgt = torch.nonzero((self._bc_mask == INFLOW).flatten(), as_tuple=True)[0].to(torch.int32).contiguous()
 
     def set_dye_boundary_condition(self, dye: Field) -> None:
@@ -186,46 +226,71 @@ def create_bc_array(x_resolution: int, y_resolution: int) -> tuple[npt.NDArray, 
             np.zeros((x_resolution, y_resolution, 3), dtype=np.float32))
 
 
-def set_plane(bc, bc_mask, bc_dye, lower_left, upper_right) -> None:
+class _Win:
+    """Row window [a, b) of a scene that is X rows tall: the builders below speak GLOBAL row indices (NumPy slice semantics,
+    negative values included) and this maps them onto arrays that hold only the window's rows.  A rank of a row-strip
+    decomposition builds just its strip (+ a margin) instead of the global grid (21 B/cell of host memory)."""
+
+    def __init__(self, X: int, a: int = 0, b: int | None = None) -> None:
+        self.X, self.a, self.b = int(X), int(a), int(X if b is None else b)
+        if not 0 <= self.a <= self.b <= self.X:
+            raise ValueError(f"row window [{a}, {b}) outside the {X} rows of the scene")
+
+    def rows(self, sl) -> slice:
+        """local slice of the window rows selected by the global int / slice `sl` (empty if they miss the window)"""
+        if isinstance(sl, (int, np.integer)):
+            i = int(sl) % self.X
+            sl = slice(i, i + 1)
+        lo, hi, step = sl.indices(self.X)
+        assert step == 1
+        lo, hi = max(lo, self.a), min(hi, self.b)
+        return slice(lo - self.a, max(hi, lo) - self.a)
+
+
+def set_plane(bc, bc_mask, bc_dye, lower_left, upper_right, win: _Win | None = None) -> None:
     """Axis-aligned wall slab (:157-168); NumPy slice semantics incl. negative corners."""
-    sl = (slice(int(lower_left[0]), int(upper_right[0])), slice(int(lower_left[1]), int(upper_right[1])))
+    win = win or _Win(bc.shape[0])
+    sl = (win.rows(slice(int(lower_left[0]), int(upper_right[0]))), slice(int(lower_left[1]), int(upper_right[1])))
     bc[sl] = 0.0
     bc_mask[sl] = WALL
     if bc_dye is not None:
         bc_dye[sl] = 0.0
 
 
-def set_circle(bc, bc_mask, bc_dye, center, radius: float) -> None:
+def set_circle(bc, bc_mask, bc_dye, center, radius: float, win: _Win | None = None) -> None:
     """Wall disc (:137-154): cell (i, j) is wall iff |(i, j) + 0.5 - center| < radius, scanned over the
     reference's rounded bounding box.  Vectorised; same float64 arithmetic per cell."""
+    win = win or _Win(bc.shape[0])
     c = np.asarray(center, dtype=np.float64)
     lo = np.round(np.maximum(c - radius, 0)).astype(np.int32)
-    u0 = round(min(center[0] + radius, bc.shape[0]))
+    u0 = round(min(center[0] + radius, win.X))
     u1 = round(min(center[1] + radius, bc.shape[1]))
-    if u0 <= lo[0] or u1 <= lo[1]:
+    r0, r1 = max(int(lo[0]), win.a), min(int(u0), win.b)      # the bounding box's rows that fall into the window
+    if r1 <= r0 or u1 <= lo[1]:
         return
-    x = np.arange(lo[0], u0, dtype=np.float64)[:, None] + 0.5 - c[0]
+    x = np.arange(r0, r1, dtype=np.float64)[:, None] + 0.5 - c[0]
     y = np.arange(lo[1], u1, dtype=np.float64)[None, :] + 0.5 - c[1]
     inside = np.sqrt(x * x + y * y) < radius
-    sub = (slice(int(lo[0]), int(u0)), slice(int(lo[1]), int(u1)))
+    sub = (slice(r0 - win.a, r1 - win.a), slice(int(lo[1]), int(u1)))
     bc[sub][inside] = 0.0
     bc_mask[sub][inside] = WALL
     if bc_dye is not None:
         bc_dye[sub][inside] = 0.0
 
 
-def set_obstacle_fromfile(bc, bc_mask, bc_dye, filepath: Path) -> None:
+def set_obstacle_fromfile(bc, bc_mask, bc_dye, filepath: Path, win: _Win | None = None) -> None:
     """Dark pixels of an image become wall (:171-198)."""
     from PIL import Image
 
+    win = win or _Win(bc.shape[0])
     image = Image.open(filepath).convert("L")
-    x_res, y_res = bc.shape[:2]
+    x_res, y_res = win.X, bc.shape[1]
     x_ratio, y_ratio = x_res / image.width, y_res / image.height
     size = (x_res, round(image.height * x_ratio)) if x_ratio < y_ratio else (round(image.width * y_ratio), y_res)
     image = image.resize(size)
     canvas = Image.new(image.mode, (x_res, y_res), 255)
     canvas.paste(image, ((x_res - image.width) // 2, 0))
-    dark = np.flip(np.array(canvas).T, axis=1) < 200
+    dark = (np.flip(np.array(canvas).T, axis=1) < 200)[win.a:win.b]
     bc[dark] = 0.0
     bc_mask[dark] = WALL
     if bc_dye is not None:
@@ -244,122 +309,126 @@ _YEL, _BLU, _RED, _CYA = (np.array(c) for c in ([1.1, 1.1, 0.2], [0.2, 0.2, 1.1]
 _RAMP = [_CYA, _RED, _BLU, _YEL]
 
 
-def _inflow(bc, mask, rows, cols) -> None:
-    bc[rows, cols] = np.array([1.0, 0.0], dtype=np.float32)
-    mask[rows, cols] = INFLOW
+def _inflow(bc, mask, rows, cols, win: _Win) -> None:
+    bc[win.rows(rows), cols] = np.array([1.0, 0.0], dtype=np.float32)
+    mask[win.rows(rows), cols] = INFLOW
 
 
-def _outflow(bc, mask, rows, cols) -> None:
-    bc[rows, cols] = 0.0
-    mask[rows, cols] = OUTFLOW
+def _outflow(bc, mask, rows, cols, win: _Win) -> None:
+    bc[win.rows(rows), cols] = 0.0
+    mask[win.rows(rows), cols] = OUTFLOW
 
 
-def _floor_ceiling(bc, mask, X, Y, dye=None) -> None:
-    set_plane(bc, mask, dye, (0, 0), (X, 2))
-    set_plane(bc, mask, dye, (0, Y - 2), (X, Y))
+def _floor_ceiling(bc, mask, X, Y, dye, win: _Win) -> None:
+    set_plane(bc, mask, dye, (0, 0), (X, 2), win)
+    set_plane(bc, mask, dye, (0, Y - 2), (X, Y), win)
 
 
 ALL = slice(None)
 
 
-def build_scene(num: int, x_res: int, y_res: int, obstacle_image: Path | None = None, with_dye: bool = False):
+def build_scene(num: int, x_res: int, y_res: int, obstacle_image: Path | None = None, with_dye: bool = False,
+                rows: tuple[int, int] | None = None):
     """(bc_const, bc_mask) of scene `num` on an x_res x y_res grid.  `create_boundary_conditionN`
     of the reference is build_scene(N, 2*res, res) (:226, 272, 326, 376, 425, 486); other aspect
-    ratios are used for the weak-scaling grids."""
+    ratios are used for the weak-scaling grids.  rows = (a, b): only the global rows [a, b) of the scene
+    (arrays of b - a rows, identical to the corresponding rows of the full build)."""
     X, Y = int(x_res), int(y_res)
-    bc, mask, dye = create_bc_array(X, Y)
+    win = _Win(X, *(rows or (0, X)))
+    bc, mask, dye = create_bc_array(win.b - win.a, Y)
     if not with_dye:
         dye = None
+    first2 = win.rows(slice(0, 2))     # the two inflow rows, as far as the window holds them
 
-    def two_rows(ramp):  # the same colour ramp on both inflow rows (:239, :339, :393-394, :499)
-        return np.stack((ramp, ramp), axis=0)
+    def plane(lower_left, upper_right) -> None:
+        set_plane(bc, mask, dye, lower_left, upper_right, win)
 
     if num == 1:                                                   # :222-265
-        _inflow(bc, mask, slice(0, 2), ALL)
+        _inflow(bc, mask, slice(0, 2), ALL, win)
         if with_dye:
-            dye[:2, :] = two_rows(create_color_map(_RAMP * 3, Y))
-        _outflow(bc, mask, -1, ALL)
-        _floor_ceiling(bc, mask, X, Y, dye)
-        set_circle(bc, mask, dye, (X // 4, Y // 2), Y // 18)
+            dye[first2, :] = create_color_map(_RAMP * 3, Y)[None]    # the same colour ramp on both inflow rows (:239)
+        _outflow(bc, mask, -1, ALL, win)
+        _floor_ceiling(bc, mask, X, Y, dye, win)
+        set_circle(bc, mask, dye, (X // 4, Y // 2), Y // 18, win)
     elif num == 2:                                                 # :268-319
-        _inflow(bc, mask, slice(0, 2), ALL)
+        _inflow(bc, mask, slice(0, 2), ALL, win)
         if with_dye:
-            dye[:2, :] = np.array([0.2, 0.2, 1.2])
+            dye[first2, :] = np.array([0.2, 0.2, 1.2])
             width = Y // 10
             for i in range(0, Y, width):
-                dye[:2, i:i + width // 2] = np.array([1.2, 1.2, 0.2])
-        set_plane(bc, mask, dye, (0, 0), (2, Y // 3))
-        set_plane(bc, mask, dye, (0, 2 * Y // 3), (2, Y))
-        set_plane(bc, mask, dye, (X - 2, 0), (X, Y))
-        _floor_ceiling(bc, mask, X, Y, dye)
+                dye[first2, i:i + width // 2] = np.array([1.2, 1.2, 0.2])
+        plane((0, 0), (2, Y // 3))
+        plane((0, 2 * Y // 3), (2, Y))
+        plane((X - 2, 0), (X, Y))
+        _floor_ceiling(bc, mask, X, Y, dye, win)
         xp, yp, size = X // 5, Y // 2, Y // 32
-        set_plane(bc, mask, dye, (xp - size, yp), (xp + size, Y))
-        set_plane(bc, mask, dye, (2 * xp - size, 0), (2 * xp + size, yp))
-        set_plane(bc, mask, dye, (3 * xp - size, yp), (3 * xp + size, Y))
-        set_plane(bc, mask, dye, (4 * xp - size, 0), (4 * xp + size, yp))
+        plane((xp - size, yp), (xp + size, Y))
+        plane((2 * xp - size, 0), (2 * xp + size, yp))
+        plane((3 * xp - size, yp), (3 * xp + size, Y))
+        plane((4 * xp - size, 0), (4 * xp + size, yp))
         yq = Y // 3
-        _outflow(bc, mask, slice(-2, None), slice(yq, 2 * yq))
+        _outflow(bc, mask, slice(-2, None), slice(yq, 2 * yq), win)
     elif num == 3:                                                 # :322-369
-        _inflow(bc, mask, slice(0, 2), ALL)
+        _inflow(bc, mask, slice(0, 2), ALL, win)
         if with_dye:
-            dye[:2, :] = two_rows(create_color_map(_RAMP, Y))
-        _outflow(bc, mask, -1, ALL)
-        _floor_ceiling(bc, mask, X, Y, dye)
+            dye[first2, :] = create_color_map(_RAMP, Y)[None]
+        _outflow(bc, mask, -1, ALL, win)
+        _floor_ceiling(bc, mask, X, Y, dye, win)
         np.random.seed(123)  # noqa: NPY002  (legacy RNG on purpose: same stream as the reference)
         points = np.random.uniform(0, X, (100, 2))  # noqa: NPY002
         points = points[points[:, 1] < Y]
         radius = 16 * (Y / 500)
         for p in points:
-            set_circle(bc, mask, dye, p, radius)
+            set_circle(bc, mask, dye, p, radius, win)
     elif num == 4:                                                 # :372-418
-        set_plane(bc, mask, dye, (0, 0), (2, Y))
-        set_plane(bc, mask, dye, (X - 2, 0), (X, Y))
-        _floor_ceiling(bc, mask, X, Y, dye)
+        plane((0, 0), (2, Y))
+        plane((X - 2, 0), (X, Y))
+        _floor_ceiling(bc, mask, X, Y, dye, win)
         if with_dye:
-            ramp = two_rows(create_color_map(_RAMP, Y // 4 - 2))
-            dye[:2, 3 * Y // 4:-2] = ramp
-            dye[:2, 2:Y // 4] = ramp
-        _inflow(bc, mask, slice(0, 2), slice(3 * Y // 4, -2))
-        _inflow(bc, mask, slice(0, 2), slice(2, Y // 4))
-        _outflow(bc, mask, slice(-2, None), slice(3 * Y // 8, 5 * Y // 8))
+            ramp = create_color_map(_RAMP, Y // 4 - 2)[None]
+            dye[first2, 3 * Y // 4:-2] = ramp
+            dye[first2, 2:Y // 4] = ramp
+        _inflow(bc, mask, slice(0, 2), slice(3 * Y // 4, -2), win)
+        _inflow(bc, mask, slice(0, 2), slice(2, Y // 4), win)
+        _outflow(bc, mask, slice(-2, None), slice(3 * Y // 8, 5 * Y // 8), win)
     elif num == 5:                                                 # :421-479
-        _inflow(bc, mask, slice(0, 2), slice(2, Y // 3))
-        _inflow(bc, mask, slice(0, 2), slice(2 * Y // 3, Y - 2))
+        _inflow(bc, mask, slice(0, 2), slice(2, Y // 3), win)
+        _inflow(bc, mask, slice(0, 2), slice(2 * Y // 3, Y - 2), win)
         if with_dye:
-            dye[:2, 2:Y // 3] = np.array([1.2, 0.2, 0.2])
-            dye[:2, 2 * Y // 3:Y - 2] = np.array([0.2, 1.2, 1.2])
-        _outflow(bc, mask, slice(-2, None), ALL)
-        _floor_ceiling(bc, mask, X, Y, dye)
+            dye[first2, 2:Y // 3] = np.array([1.2, 0.2, 0.2])
+            dye[first2, 2 * Y // 3:Y - 2] = np.array([0.2, 1.2, 1.2])
+        _outflow(bc, mask, slice(-2, None), ALL, win)
+        _floor_ceiling(bc, mask, X, Y, dye, win)
         size = X // 64
-        set_plane(bc, mask, dye, (0, Y // 5), (11 * X // 30, 4 * Y // 5))
-        set_plane(bc, mask, dye, (X // 2 - size, 0), (X // 2 + size, 2 * Y // 5))
-        set_plane(bc, mask, dye, (X // 2 - size, 3 * Y // 5), (X // 2 + size, Y))
+        plane((0, Y // 5), (11 * X // 30, 4 * Y // 5))
+        plane((X // 2 - size, 0), (X // 2 + size, 2 * Y // 5))
+        plane((X // 2 - size, 3 * Y // 5), (X // 2 + size, Y))
         yp, half = Y // 6, np.array([Y, Y]) // 25
         for a, b in zip((7, 8, 9, 10, 11), (0, 1, 0, 1, 0), strict=True):
             for i in range(1, 6 + b):
                 p = np.array([a * X // 12, i * yp - b * Y // 12])
-                set_plane(bc, mask, dye, p - half, p + half)
+                plane(p - half, p + half)
     elif num == 6:                                                 # :482-524
-        _inflow(bc, mask, slice(0, 2), ALL)
+        _inflow(bc, mask, slice(0, 2), ALL, win)
         if with_dye:
-            dye[:2, :] = two_rows(create_color_map(_RAMP, Y))
-        _outflow(bc, mask, -1, ALL)
-        _floor_ceiling(bc, mask, X, Y, dye)
+            dye[first2, :] = create_color_map(_RAMP, Y)[None]
+        _outflow(bc, mask, -1, ALL, win)
+        _floor_ceiling(bc, mask, X, Y, dye, win)
         path = obstacle_image or Path(__file__).resolve().parents[1] / "images" / "bc_mask" / "dragon.png"
         if not Path(path).exists():
             raise FileNotFoundError(f"scene 6 needs the reference's obstacle image (images/bc_mask/dragon.png); "
                                     f"not found at {path}")
-        set_obstacle_fromfile(bc, mask, dye, Path(path))
+        set_obstacle_fromfile(bc, mask, dye, Path(path), win)
     else:
         raise NotImplementedError
     return (bc, mask, dye) if with_dye else (bc, mask)
 
 
-def _make(num: int, resolution: int, enable_dye: bool, **kw) -> BoundaryCondition:
+def _make(num: int, resolution: int, enable_dye: bool, obstacle_image=None, **kw) -> BoundaryCondition:
     if enable_dye:
-        bc, mask, dye = build_scene(num, 2 * resolution, resolution, with_dye=True)
+        bc, mask, dye = build_scene(num, 2 * resolution, resolution, obstacle_image=obstacle_image, with_dye=True)
         return DyeBoundaryCondition(bc, dye, mask, **kw)
-    bc, mask = build_scene(num, 2 * resolution, resolution)
+    bc, mask = build_scene(num, 2 * resolution, resolution, obstacle_image=obstacle_image)
     return BoundaryCondition(bc, mask, **kw)
 
 

@@ -37,7 +37,9 @@ class HostPipelinedStepper:
             self.up.wait_event(self._down_done[slot])          # the slot's previous result has left the device
         with torch.cuda.stream(self.up):
             for n in self.state_names:
-                getattr(s, n).current.owned().copy_(host_state[n], non_blocking=True)
+                f = getattr(s, n).current
+                f.owned().copy_(host_state[n], non_blocking=True)
+                f.dirty = True       # written from the host: the Jacobi updater re-checks its fused-pass precondition (stale wall cells)
             up_done = torch.cuda.Event()
             up_done.record()
         self.comp.wait_event(up_done)

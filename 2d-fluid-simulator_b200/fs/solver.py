@@ -62,6 +62,7 @@ def limit_field(field: Field, limit: float, dom=None, bc: BoundaryCondition | No
             dom = _lib.Dom(rows=X + 2 * field.halo, Y=Y, r0=field.halo, r1=field.halo + X, clo=0,
                            chi=X + 2 * field.halo - 1, gi0=0)
     if pressure_updater is not None and getattr(pressure_updater, "_vmax_field", None) is field:
+        pressure_updater._vmax_field = None      # a recorded maximum is valid for exactly one limiter call
         _lib.call("fs2d_limit_if", field.ptr(), dom, limit, _lib.ptr(pressure_updater._vmax), _lib.stream())
     else:
         _lib.call("fs2d_limit", field.ptr(), dom, limit, _lib.stream())

@@ -39,7 +39,13 @@ def main() -> None:
     parser.add_argument("--output", type=str, default=str(Path(__file__).parent.resolve() / "output"))
     parser.add_argument("--jacobi", type=int, default=0, help="use JacobiPressureUpdater with N sweeps/step")
     parser.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
+    parser.add_argument("--obstacle-image", type=str, default=None,
+                        help="-bc 6: path of the reference's images/bc_mask/dragon.png (an asset of the reference, not shipped here)")
     args = parser.parse_args()
+    if args.boundary_condition == 6:
+        default_png = Path(__file__).resolve().parent / "images" / "bc_mask" / "dragon.png"
+        if args.obstacle_image is None and not default_png.exists():
+            parser.error("-bc 6 needs the reference's obstacle image: pass --obstacle-image /path/to/images/bc_mask/dragon.png")
 
     if args.cpu:
         raise SystemExit("-cpu: this build runs on B200 only (hand-written sm_100a kernels, no CPU fallback)")
@@ -57,6 +63,8 @@ def main() -> None:
           f"Scheme: {scheme}\nVorticity confinement: {vor_eps}")
 
     kw = dict(pressure="jacobi", n_iter=args.jacobi) if args.jacobi > 0 else {}
+    if args.obstacle_image is not None:
+        kw["obstacle_image"] = Path(args.obstacle_image)
     cls = FluidSimulator if args.no_dye else DyeFluidSimulator
     fluid_sim = cls.create(n_bc, resolution, dt, dx, re, vor_eps, scheme, **kw)
 
@@ -68,7 +76,7 @@ def main() -> None:
     for step in range(args.steps):
         fluid_sim.step()
         if args.dump_every and (step + 1) % args.dump_every == 0:
-            out.mkdir(exist_ok=True)
+            out.mkdir(parents=True, exist_ok=True)
             np.savez(str(out / f"step_{step + 1:06}.npz"), **fluid_sim.field_to_numpy())
     torch.cuda.synchronize()
     t = time.perf_counter() - t0

@@ -374,6 +374,7 @@ def run_ours(a: argparse.Namespace) -> None:
     if world != a.gpus:
         raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {a.gpus}")
     torch.cuda.set_device(local)
+    numa = pin_to_gpu_numa(local)
     # stdout carries exactly ONE JSON line: whatever libraries print there (NCCL's version banner, ...) goes to stderr
     sys.stdout.flush()
     json_fd = os.dup(1)
@@ -397,11 +398,20 @@ def run_ours(a: argparse.Namespace) -> None:
 
     X, Y = a.rows_per_gpu * world, a.cols
     dt, dx = 0.05 / Y_COLS, 1.0 / Y_COLS
-    const, mask = build_scene(SCENE, X, Y)
     part = Partition(X, rank, world, 0 if world == 1 else 9)   # halo 9: fused Jacobi passes of up to 8 iterations
-    bc = BoundaryCondition(const, mask, partition=part)
+    t_setup = time.perf_counter()
+    if world == 1:
+        const, mask = build_scene(SCENE, X, Y)
+        bc = BoundaryCondition(const, mask, partition=part)
+    else:   # every rank builds (and uploads) only its strip of the scene: O(strip) host and device memory, not O(global grid)
+        a0, a1 = BoundaryCondition.strip_rows(part)
+        const, mask = build_scene(SCENE, X, Y, rows=(a0, a1))
+        bc = BoundaryCondition(const, mask, partition=part, row_offset=a0)
     del const, mask
     solver = make_solver(bc, dt, dx, RE, VC, SCHEME, pressure="jacobi", n_iter=a.jacobi)
+    solver.pressure_updater.plan(solver.p)      # setup work (fused-pass validity analysis, tile lists) happens here, not in the warm-up
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t_setup
     cells_total = X * Y
 
     def barrier():
@@ -422,64 +432,135 @@ def run_ours(a: argparse.Namespace) -> None:
     #     one graph launch per step), eagerly on strips (the NCCL exchanges are issued from the host).
     from fs.fluid_simulator import FluidSimulator
 
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
-    solver.timing_events = None
-    for _ in range(a.warmup):
-        solver.update()
-    barrier()
-    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e_start.record()
-    for k in range(a.steps):
-        solver.timing_events = ev[k]      # the solver records these around pressure_updater.update()
-        solver.update()
-    e_stop.record()
-    barrier()
-    solver.timing_events = None
-    ms_step_eager = max_over_ranks(e_start.elapsed_time(e_stop)) / a.steps
-
-    sim = FluidSimulator(solver)
     use_graph = world == 1 and not a.no_graph
-    if use_graph:
-        sim.enable_cuda_graph()
-    for _ in range(a.warmup):
-        sim.step()
-    barrier()
-    n0 = lib.fs2d_launch_count()
-    t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+
+    def time_device(solver, sample_clocks: bool):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+        solver.timing_events = None
+        for _ in range(a.warmup):
+            solver.update()
+        barrier()
+        e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_start.record()
+        for k in range(a.steps):
+            solver.timing_events = ev[k]      # the solver records these around pressure_updater.update()
+            solver.update()
+        e_stop.record()
+        barrier()
+        solver.timing_events = None
+        ms_eager = max_over_ranks(e_start.elapsed_time(e_stop)) / a.steps
+        sim = FluidSimulator(solver)
+        if use_graph:
+            sim.enable_cuda_graph()
+        for _ in range(a.warmup):
+            sim.step()
+        barrier()
+        n0 = lib.fs2d_launch_count()
+        t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clk = ClockSampler(local) if sample_clocks else None
+        if clk:
+            clk.__enter__()
         t_start.record()
         for k in range(a.steps):
             sim.step()
         t_stop.record()
         barrier()
-    launches = lib.fs2d_launch_count() - n0
-    if use_graph:   # replayed kernels do not pass through the library's counter: count what one eager step launches
-        c0 = lib.fs2d_launch_count()
-        solver.update()
-        torch.cuda.synchronize()
-        launches = (lib.fs2d_launch_count() - c0) * a.steps
-    ms_total = max_over_ranks(t_start.elapsed_time(t_stop))
-    ms_step = ms_total / a.steps
+        if clk:
+            clk.__exit__()
+        launches = lib.fs2d_launch_count() - n0
+        if use_graph:   # replayed kernels do not pass through the library's counter: count what one eager step launches
+            sim._graphs = None
+            c0 = lib.fs2d_launch_count()
+            solver.update()
+            torch.cuda.synchronize()
+            launches = (lib.fs2d_launch_count() - c0) * a.steps
+        ms_total = max_over_ranks(t_start.elapsed_time(t_stop))
+        ms_poisson = max_over_ranks(sum(s.elapsed_time(e) for s, e in ev) / a.steps)
+        return {"ms_total": ms_total, "ms_step": ms_total / a.steps, "ms_step_eager": ms_eager, "ms_poisson": ms_poisson,
+                "launches": int(launches), "clocks": clk.summary() if clk else None}
+
+    developed = None
+    if a.state in ("developed", "both"):
+        developed_like_state(solver)
+        r = time_device(solver, sample_clocks=a.state == "developed")
+        developed = {"value": cells_total * a.steps / (r["ms_total"] * 1e-3), "unit": "cell-updates/s", "ms_per_step": r["ms_step"],
+                     "ms_per_sweep": r["ms_poisson"] / a.jacobi, "ms_non_poisson": r["ms_step_eager"] - r["ms_poisson"],
+                     "finite": bool(torch.isfinite(solver.v.current.tensor).all()),
+                     "what": "same workload started from seeded non-uniform fields (smooth structures + cell-scale noise in v, vx, vy, p): "
+                             "the instruction paths of a developed flow instead of the exactly uniform regions of a quiescent start"}
+        if a.state == "both":      # back to the reference's initial state (all fields zero, fs/double_buffer.py:14-18) for the headline
+            for name in ("v", "vx", "vy", "p"):
+                getattr(solver, name).reset()
+            vcf = solver.vorticity_confinement
+            if vcf is not None:
+                vcf.vorticity.fill(0)
+                vcf.vorticity_abs.fill(0)
+    if a.state != "developed":
+        r = time_device(solver, sample_clocks=True)
+    clocks, launches = r["clocks"], r["launches"]
+    ms_total, ms_step, ms_step_eager, ms_poisson = r["ms_total"], r["ms_step"], r["ms_step_eager"], r["ms_poisson"]
     value = cells_total * a.steps / (ms_total * 1e-3)
-    ms_poisson = max_over_ranks(sum(s.elapsed_time(e) for s, e in ev) / a.steps)
     ms_sweep = ms_poisson / a.jacobi
     try:    # the update's schedule (host-side query): fused pass sizes, 0 = one literal {BC, sweep} iteration
         schedule = solver.pressure_updater.plan(solver.p)
     except Exception:  # noqa: BLE001
         schedule = None
+
+    # the dominant kernel on its own: CUDA events around back-to-back T = 8 passes on this rank's strip (the pass size the
+    # schedule uses most), ping-pong between the two pressure buffers
+    kernel_alone = None
+    jac = solver.pressure_updater
+    t_dom = max(set(t for t in (schedule or []) if t > 0), key=(schedule or []).count, default=0)
+    if t_dom and world == 1:
+        src = jac._src
+        pa, pb = solver.p.current, solver.p.next
+        save = (pa.tensor.clone(), pb.tensor.clone())
+        for _ in range(2):
+            jac._fused(pb, pa, src, t_dom)
+            jac._fused(pa, pb, src, t_dom)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        k0.record()
+        for _ in range(reps):
+            jac._fused(pb, pa, src, t_dom)
+            jac._fused(pa, pb, src, t_dom)
+        k1.record()
+        torch.cuda.synchronize()
+        pa.tensor.copy_(save[0]); pb.tensor.copy_(save[1])
+        del save
+        kernel_alone = {"T": t_dom, "us_per_launch": k0.elapsed_time(k1) * 1e3 / (2 * reps), "launches_timed": 2 * reps}
+
     peak, peak_src = peaks()
-    achieved = ALGO_BYTES_PER_CELL_SWEEP * (a.rows_per_gpu * Y) / (ms_sweep * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_jacobi_fused5 (T Jacobi iterations per pass on a 96x128 register tile; update = fused passes + 2 literal sweeps)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL_SWEEP * a.rows_per_gpu * Y,
-                "ms_per_sweep": ms_sweep, "poisson_share_of_step": ms_poisson / ms_step_eager, "traffic": traffic_from_profile(),
+    cells_gpu = a.rows_per_gpu * Y
+    achieved = ALGO_BYTES_PER_CELL_SWEEP * cells_gpu / (ms_sweep * 1e-3) / 1e9
+    traffic = traffic_from_profile()
+    usable = bool(traffic) and not traffic.get("stale") and not a.config and a.rows_per_gpu == CELLS_PER_GPU_ROWS and Y == 8192
+    roofline = {"bound": "issue/latency" , "kernel": "k_jacobi_fused (T Jacobi iterations per pass on a 96x128 register tile, autonomous warps; update = "
+                                                     "source pre-pass + fused passes + 1 literal sweep)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_algorithmic": achieved / peak,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL_SWEEP * cells_gpu,
+                "ms_per_sweep": ms_sweep, "poisson_share_of_step": ms_poisson / ms_step_eager,
+                "traffic": traffic.get("dram_bytes_per_launch") if usable else None, "traffic_detail": traffic,
                 "update_schedule": schedule,
                 "timed": "CUDA events around pressure_updater.update() inside every timed step (all its launches: source pre-pass, "
-                         "fused passes, 2 literal iterations with their sparse BC kernels) / sweeps per update",
-                "note": "frac > 1 is expected: the fused kernel keeps tiles in registers / shared memory for T iterations, so the DRAM "
-                        "traffic per iteration (see traffic, per fused launch of T=8 iterations) is far below the 12 B/cell "
-                        "algorithmic figure the fraction is defined on",
-                "whole_step_algorithmic_gbs": ALGO_BYTES_PER_CELL_STEP * (a.rows_per_gpu * Y) / (ms_step * 1e-3) / 1e9}
+                         "fused passes, the literal tail with its sparse BC kernels) / sweeps per update",
+                "bound_note": "the 12 B/cell/sweep algorithmic figure stops being a floor under temporal blocking (T iterations per pass over "
+                              "HBM): frac_algorithmic > 1 says how far the kernel is beyond what a one-sweep-per-pass kernel could reach; "
+                              "frac_dram = ACTUAL dram bytes (ncu, traffic) / launch time / peak says how far it is below the HBM roof. "
+                              "It is bounded by instruction issue / latency (12 warps per SM, 156 registers: the register tile holds "
+                              "p, t2, t3 of 12288 cells), see issue_active_pct",
+                "whole_step_algorithmic_gbs": ALGO_BYTES_PER_CELL_STEP * cells_gpu / (ms_step * 1e-3) / 1e9}
+    if kernel_alone:
+        kernel_alone["algorithmic_gbs"] = ALGO_BYTES_PER_CELL_SWEEP * cells_gpu * kernel_alone["T"] / (kernel_alone["us_per_launch"] * 1e-6) / 1e9
+        kernel_alone["frac_algorithmic"] = kernel_alone["algorithmic_gbs"] / peak
+        if usable and traffic.get("iterations_per_launch") == kernel_alone["T"]:
+            kernel_alone["dram_gbs"] = traffic["dram_bytes_per_launch"] / (kernel_alone["us_per_launch"] * 1e-6) / 1e9
+            roofline["frac_dram"] = kernel_alone["dram_gbs"] / peak
+            roofline["issue_active_pct"] = traffic.get("issue_active_pct")
+        roofline["kernel_alone"] = kernel_alone
+    if usable and traffic.get("step_dram_bytes"):
+        roofline["step_dram_gbs"] = traffic["step_dram_bytes"] / (ms_step * 1e-3) / 1e9
+        roofline["step_frac_dram"] = roofline["step_dram_gbs"] / peak
 
     # ---- end-to-end through the public API with host buffers ----------------------------------
     # fs.pipeline.HostPipelinedStepper: every step uploads the state (v, vx, vy, p) from pinned host memory,
@@ -537,8 +618,10 @@ def run_ours(a: argparse.Namespace) -> None:
                 "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, world),
                 "stepping": "cuda-graph replay (1 launch/step)" if use_graph else "eager launches",
-                "ms_per_step_eager": ms_step_eager, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu, "baseline_config_2": extra, "tuning": tuning or None}
+                "ms_per_step_eager": ms_step_eager, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "cpu_baseline": cpu, "baseline_config_2": extra, "value_developed_state": developed, "numa": numa, "setup_s": t_setup,
+                "state": "quiescent start (all fields zero, the reference's initial state)" if a.state != "developed" else "developed-like seeded fields",
+                "tuning": tuning or None}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:

@@ -53,18 +53,34 @@ if rep:
     ni, ti, ri, wi = hd.index("Kernel Name"), hd.index("gpu__time_duration.sum"), hd.index("dram__bytes_read.sum"), hd.index("dram__bytes_write.sum")
     for r in rr[2:]:
         print(f"{r[ni][:36]:36s} {float(r[ti]):9.1f} {rr[1][ti]}  dram rd {float(r[ri]):8.1f} wr {float(r[wi]):8.1f} {rr[1][ri]}")
-    dom = [r for r in rr[2:] if "k_jacobi_fused" in r[ni]]
+    dom = [r for r in rr[2:] if "k_jacobi_fused" in r[ni] and "emit" not in r[ni]]
     if dom:
+        import hashlib
+        from pathlib import Path
+
         r = dom[0]
         scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
         rd, wr = float(r[ri]) * scale[rr[1][ri]], float(r[wi]) * scale[rr[1][wi]]
-        T = 8  # the plan of an 80-iteration update: 6 + 9 x 8 fused iterations (the 3rd fused launch is a T = 8 pass) + 2 literal
+        T = 8  # the plan of an 80-iteration update: mostly T = 8 passes (the 3rd fused launch of a step is one)
         cells = 8192 * 8192
+        # DRAM bytes of a whole step: every kernel's bytes (its one captured launch) x its launches per step (launch list;
+        # one k_limit launch per step).  The fused passes of other sizes are counted with the T = 8 figure.
+        per_kernel = {x[ni].split("(")[0].replace("void ", "").replace("fs2d::", ""): (float(x[ri]) * scale[rr[1][ri]] + float(x[wi]) * scale[rr[1][wi]])
+                      for x in rr[2:]}
+        steps = max(1, agg.get("k_limit", agg.get("k_limit_if", [1]))[0])
+        step_bytes = sum(per_kernel.get(k, 0.0) * n / steps for k, (n, _) in agg.items())
+        h = hashlib.sha256()
+        for name in ("fs2d_fused.cu", "fs2d_common.cuh"):
+            h.update((Path(__file__).resolve().parents[1] / "2d-fluid-simulator_b200" / "csrc" / name).read_bytes())
+        ia = hd.index("smsp__issue_active.avg.pct_of_peak_sustained_active")
         json.dump({"kernel": f"{r[ni].split('(')[0]} (T={T} iterations per launch, 8192x8192 cells)",
                    "dram_bytes_read_per_launch": int(rd), "dram_bytes_write_per_launch": int(wr),
                    "dram_bytes_per_launch": int(rd + wr), "iterations_per_launch": T,
                    "dram_bytes_per_cell_iteration": round((rd + wr) / cells / T, 2),
                    "algorithmic_bytes_per_launch": 12 * cells * T, "launch_duration_us_under_ncu": float(r[ti]),
-                   "source": f"profiles/{tag}_kernels_ncu_full.csv (ncu --set full --clock-control none, one capture)"},
+                   "issue_active_pct": float(r[ia]), "step_dram_bytes": int(step_bytes), "steps_in_launch_list": steps,
+                   "source_sha256": h.hexdigest(),
+                   "source": f"profiles/{tag}_kernels_ncu_full.csv (ncu --set full --clock-control none, one capture; bench.py refuses "
+                             "this file when the kernel sources no longer hash to source_sha256)"},
                   open("profiles/dominant_kernel_traffic.json", "w"))
         print(open("profiles/dominant_kernel_traffic.json").read())

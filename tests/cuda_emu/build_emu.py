@@ -28,7 +28,12 @@ PTX_HELPERS = {
     "mbar_expect_tx": "emu::mbar_expect_tx(bar, bytes);", "st_mbar_expect": "emu::mbar_expect_tx(bar, bytes);",
     "mbar_wait": "emu::mbar_wait(bar, parity);", "st_mbar_wait": "emu::mbar_wait(bar, parity);",
     "tma_load_2d": "emu::tma_load_2d(dst, map, c0, c1, bar);", "st_tma_2d": "emu::tma_load_2d(dst, map, c0, c1, bar);",
-    "ld_acquire_smem": "return emu::flag_load(p);", "st_release_smem": "emu::flag_store(p, v);",
+    "smem_addr": "return (saddr_t)(uintptr_t)p;",
+    "lds4_s": "return *reinterpret_cast<const float4 *>(a);",
+    "sts4_s": "*reinterpret_cast<float4 *>(a) = make_float4(x, y, z, w);",
+    "st_release_s": "emu::flag_store(reinterpret_cast<int *>(a), v);",
+    "flag_peek2": "(void)after; return min(*reinterpret_cast<const int *>(a), *reinterpret_cast<const int *>(b));",
+    "flag_wait2": "emu::flag_wait_ge(reinterpret_cast<const int *>(a), v); emu::flag_wait_ge(reinterpret_cast<const int *>(b), v);",
 }
 
 

@@ -313,6 +313,13 @@ inline int flag_load(const int *p) {
     yield();
     return *p;
 }
+// the polling loop itself: blocked while the counter is below `v`; getting past it is progress (a poll that finds its value
+// at once is not a scheduling point, otherwise a round in which every fiber merely walks through satisfied polls would look
+// like a deadlock)
+inline void flag_wait_ge(const int *p, int v) {
+    while (*p < v) yield();
+    ++M().progress;
+}
 }  // namespace emu
 
 // ---- device builtins -----------------------------------------------------------------------------------------------

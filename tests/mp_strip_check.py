@@ -39,6 +39,16 @@ CASES = [
     ("rand1", 192, 64, "cip", 5.0, dict(pressure="jacobi", n_iter=11), 2, 5),  # thin walls on / next to the strip edges
     ("rand3", 192, 64, "kk", None, dict(pressure="jacobi", n_iter=14), 2, 6),
 ]
+# GPU runs only (seconds on a B200): the BASELINE scenes with their own sweep counts, fused passes of 8 across every strip edge
+GPU_CASES = [
+    (2, 8192, 2048, "cip", 5.0, dict(pressure="jacobi", n_iter=80), 2, 9),     # bc2, 80 sweeps (configs 2 / 4)
+    (5, 4096, 2048, "cip", 5.0, dict(pressure="jacobi", n_iter=200), 2, 9),    # bc5, 200 sweeps (config 5 at res 2048)
+    (3, 4096, 2048, "cip", 10.0, dict(pressure="jacobi", n_iter=100), 1, 9),   # bc3, vc=10, 100 sweeps (config 3 at res 2048)
+]
+# FS2D_STRIP_BIG=1: BASELINE config 5 itself (bc5, res=16384: 32768 x 16384 cells, 200 sweeps), quiescent start, 2 steps; the
+# single-domain run needs 45 GB on rank 0's GPU
+BIG_CASES = [(5, 32768, 16384, "cip", 5.0, dict(pressure="jacobi", n_iter=200), 2, 9)]
+SEED_MAX_CELLS = 1 << 25     # larger grids start quiescent (all fields zero) instead of from seeded random buffers
 
 
 def random_scene(seed: int, X: int, Y: int):
@@ -100,7 +110,9 @@ def main() -> None:
         torch.cuda.set_device(local)
         dev = torch.device("cuda", local)
         dist.init_process_group("nccl", device_id=dev)
-        cases = CASES
+        cases = CASES + GPU_CASES + (BIG_CASES if os.environ.get("FS2D_STRIP_BIG") == "1" else [])
+        if os.environ.get("FS2D_STRIP_ONLY_BIG") == "1":
+            cases = BIG_CASES
     for item in filter(None, os.environ.get("FS2D_STRIP_TUNING", "").split(",")):   # e.g. "4=1": experimental kernel variants
         from fs import _lib as _l
 
@@ -119,10 +131,11 @@ def main() -> None:
         part = Partition(X, rank, world, halo)
         strip = make_solver(BoundaryCondition(const, mask, device=dev, partition=part), dt, dx, re, vc, scheme, **pkw)
         single = make_solver(BoundaryCondition(const, mask, device=dev), dt, dx, re, vc, scheme, **pkw) if rank == 0 else None
+        del const, mask
         rng = np.random.default_rng(1234 + (num if isinstance(num, int) else 50 + int(num[4:])))
         g0, g1 = part.owned()
         p_first = None
-        for k, f in buffers(strip).items():  # same seeded global state on every rank (incl. "next" buffers)
+        for k, f in (buffers(strip).items() if X * Y <= SEED_MAX_CELLS else ()):  # same seeded global state on every rank (incl. "next" buffers)
             shape = (X, Y, 2) if f.n == 2 else (X, Y)
             scale = 0.05 / dx if k[:2] in ("vx", "vy") else (0.5 if k[0] == "v" and k != "vort" else 1.0)
             a = (rng.uniform(-1, 1, shape) * scale).astype(np.float32)
@@ -151,6 +164,12 @@ def main() -> None:
                     raise SystemExit(f"MP_CHECK FAIL case bc{num} {X}x{Y} {scheme} {pkw} buffer {k}: "
                                      f"{int(bad.sum())} values differ, first rows {rows}")
         n_ok += 1
+        if rank == 0:
+            print(f"  case ok: bc{num} {X}x{Y} {scheme} vc={vc} {pkw} steps={steps} halo={halo} on {world} ranks"
+                  f"{'' if X * Y <= SEED_MAX_CELLS else ' (quiescent start)'}", flush=True)
+        del strip, single
+        if dev.type == "cuda":
+            torch.cuda.empty_cache()
         dist.barrier()
     if rank == 0:
         print(f"MP_CHECK OK {n_ok} cases on {world} ranks", flush=True)

@@ -139,3 +139,43 @@ def test_fused_reach_bounds_the_stale_rows_below_a_strip():
                 a[...] = b
         same = np.array_equal(full[:48][mask[:48] != 1], part[:48][mask[:48] != 1], equal_nan=False)
         assert same == expect_strip_ok
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# a rank that builds only its strip of the scene (build_scene(rows=...), BoundaryCondition(row_offset=...)) must end up
+# with exactly the tables of a build from the global arrays
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("num,X,Y,world,halo", [(2, 320, 64, 3, 9), (5, 384, 96, 2, 13), (3, 400, 80, 4, 9), (1, 300, 96, 2, 4),
+                                                (4, 96, 48, 2, 2), (5, 256, 128, 1, 0)])
+def test_strip_built_boundary_condition_equals_global_build(num, X, Y, world, halo):
+    from fs.boundary_condition import BoundaryCondition, DyeBoundaryCondition
+
+    const, mask, dye = build_scene(num, X, Y, with_dye=True)
+    for rank in range(world):
+        part = Partition(X, rank, world, halo)
+        a, b = BoundaryCondition.strip_rows(part)
+        assert 0 <= a <= part.owned()[0] and part.owned()[1] <= b <= X and (b - a < X or world == 1 or X < 200)
+        c_w, m_w, d_w = build_scene(num, X, Y, with_dye=True, rows=(a, b))
+        assert np.array_equal(m_w, mask[a:b]) and np.array_equal(c_w, const[a:b]) and np.array_equal(d_w, dye[a:b])
+        glob = DyeBoundaryCondition(const, dye, mask, device="cpu", partition=part)
+        loc = DyeBoundaryCondition(c_w, d_w, m_w, device="cpu", partition=part, row_offset=a)
+        for name in ("_bc_mask", "_pcode", "_bc_const", "_bc_dye", "_dye_tgt", "_exposed_stale"):
+            assert torch.equal(getattr(glob, name), getattr(loc, name)), f"rank {rank}: {name} differs"
+        for tname in ("_vel_table", "_p_table"):
+            tg, tl = getattr(glob, tname), getattr(loc, tname)
+            for k, v in tg.items():
+                if isinstance(v, torch.Tensor):
+                    assert torch.equal(v, tl[k]), f"rank {rank}: {tname}[{k}] differs"
+                elif isinstance(v, dict):
+                    for kk, vv in v.items():
+                        assert (torch.equal(vv, tl[k][kk]) if isinstance(vv, torch.Tensor) else vv == tl[k][kk]), f"{tname}[{k}][{kk}]"
+                else:
+                    assert v == tl[k], f"rank {rank}: {tname}[{k}] {v} != {tl[k]}"
+        assert [getattr(glob.dom, f) for f, _ in glob.dom._fields_] == [getattr(loc.dom, f) for f, _ in loc.dom._fields_]
+        if Y % 16 == 0:
+            for T in (3, 8) if rank % 2 == 0 else (12,):
+                if world == 1 or halo >= T + 1:
+                    assert glob.fused_ok(T) == loc.fused_ok(T), f"rank {rank}: fused_ok({T}) differs"
+    with pytest.raises(ValueError):     # arrays that do not cover the rows the rank needs
+        part = Partition(X, 0, max(world, 2), max(halo, 2))
+        BoundaryCondition(const[5:], mask[5:], device="cpu", partition=part, row_offset=5)

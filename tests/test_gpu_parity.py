@@ -535,6 +535,28 @@ def test_config3_full_size_step_vs_oracle(env):
         assert_bitexact(f"config3 {k}", got[k].to_numpy(), a)
 
 
+def test_bench_workload_step_vs_oracle(env):
+    """The EXACT workload bench.py times on one GPU -- bc=2 on the 8192 x 8192 shard of BASELINE config 4, CIP, Re=1e5, vc=5,
+    dt=0.05/8192, 80 Jacobi sweeps, quiescent start -- two steps, every physical buffer bit-compared with the oracle
+    (67 M cells: the oracle needs a few seconds per step on the box's host cores)."""
+    from fs.boundary_condition import build_scene
+    from oracle import oracle as orc
+    import os
+
+    orc.set_threads(os.cpu_count() or 1)
+    X = Y = 8192
+    dt, dx, re, vc, pressure = 0.05 / Y, 1.0 / Y, 1e5, 5.0, ("jacobi", 80)
+    const, mask = build_scene(2, X, Y)
+    s = make_fs(mask, const, dt, dx, re, "cip", vc, pressure)
+    ref = orc.OracleSolver(mask, const, dt, dx, re, "cip", vc, pressure)
+    assert any(t > 0 for t in s.pressure_updater.plan(s.p)), "the bench workload must run fused passes"
+    for n in range(2):
+        s.update(); ref.update()
+        got = fs_state(s)
+        for k, a in ref.state().items():
+            assert_bitexact(f"bench workload step {n} {k}", got[k].to_numpy(), a)
+
+
 def test_config5_grid_fused_equals_literal(env):
     """BASELINE config 5's grid on ONE GPU (bc=5 res=16384: 32768 x 16384 = 537 M cells): the fused Jacobi update
     (200 sweeps) equals 200 literal iterations bitwise -- size-independent property, no oracle needed."""
@@ -758,8 +780,8 @@ def test_tile_list_classes(env, num, X, Y):
         order, n = bc.fused_order(T)
         _, n_slow, n_skip = bc._fused_orders[(T, bc.dom.r0, bc.dom.r1, bc.dom.clo, bc.dom.chi, 0, 0)][1:]
         ent = order.cpu().numpy()[:n]
-        tiles, cls = ent & ((1 << 28) - 1), ent >> 28
         tiles_i, tiles_j = -(-X // TI), -(-Y // TJ)
+        tiles, cls = ((ent >> 14) & 0x3FFF) * tiles_j + (ent & 0x3FFF), ent >> 28      # entry = col | row << 14 | class << 28
         assert n + n_skip == tiles_i * tiles_j and len(set(tiles.tolist())) == n
         assert (cls[:n_slow] == 1).all() and (cls[n_slow:] == 0).all()
         listed = set(tiles.tolist())
