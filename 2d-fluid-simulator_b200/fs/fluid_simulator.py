@@ -62,17 +62,19 @@ class FluidSimulator:
         s = self._solver
         return [b for b in (getattr(s, n, None) for n in ("v", "vx", "vy", "p", "dye", "dyex", "dyey")) if b is not None]
 
-    def enable_cuda_graph(self) -> None:
+    def enable_cuda_graph(self, strips: bool = False) -> None:
         """Capture the ~100-200 kernel launches of `solver.update()` into CUDA graphs and replay them in step().
 
         Small grids are launch-bound (a res=512 step is 150 launches of a few microseconds each).  The double
         buffers swap roles inside a step, so a step's kernel arguments repeat with period 1 or 2; one graph is
         captured per phase and step() replays them in turn, mirroring the swaps on the Python side so that
-        `.current` / `.next` stay truthful.  Single-rank only; results are bit-identical (same kernels)."""
+        `.current` / `.next` stay truthful.  Results are bit-identical (same kernels).  On row strips (world > 1) the
+        halo SendRecvs are captured with the kernels (NCCL point-to-point operations are capturable; every rank must call
+        this at the same point, like any collective): opt-in with strips=True."""
         import torch
 
-        if self._solver._bc.partition.world > 1:
-            raise NotImplementedError("CUDA-graph stepping is single-rank (NCCL exchanges are issued from the host)")
+        if self._solver._bc.partition.world > 1 and not strips:
+            raise NotImplementedError("CUDA-graph stepping on row strips is opt-in: enable_cuda_graph(strips=True) on every rank")
         if self._graphs is not None:
             return
         self._solver.update()               # warm-up outside capture: lazy allocations, one-time validity checks

@@ -53,6 +53,7 @@ def parse() -> argparse.Namespace:
     ap.add_argument("--jacobi", type=int, default=N_JACOBI)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
+    ap.add_argument("--graph-strips", action="store_true", help="N > 1: capture the strips' steps (kernels + NCCL SendRecvs) into CUDA graphs too")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-config", action="store_true", help="skip the BASELINE configs[1] side measurement (N=1)")
     ap.add_argument("--cpu-sample-rows", type=int, default=1024, help="rows of the CPU-baseline sample grid")
@@ -432,7 +433,7 @@ def run_ours(a: argparse.Namespace) -> None:
     #     one graph launch per step), eagerly on strips (the NCCL exchanges are issued from the host).
     from fs.fluid_simulator import FluidSimulator
 
-    use_graph = world == 1 and not a.no_graph
+    use_graph = (world == 1 or a.graph_strips) and not a.no_graph
 
     def time_device(solver, sample_clocks: bool):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
@@ -451,7 +452,7 @@ def run_ours(a: argparse.Namespace) -> None:
         ms_eager = max_over_ranks(e_start.elapsed_time(e_stop)) / a.steps
         sim = FluidSimulator(solver)
         if use_graph:
-            sim.enable_cuda_graph()
+            sim.enable_cuda_graph(strips=world > 1)
         for _ in range(a.warmup):
             sim.step()
         barrier()
@@ -550,6 +551,10 @@ def run_ours(a: argparse.Namespace) -> None:
                               "It is bounded by instruction issue / latency (12 warps per SM, 156 registers: the register tile holds "
                               "p, t2, t3 of 12288 cells), see issue_active_pct",
                 "whole_step_algorithmic_gbs": ALGO_BYTES_PER_CELL_STEP * cells_gpu / (ms_step * 1e-3) / 1e9}
+    try:    # tile classes of the fused passes on this rank: {T: [tiles listed, of which slow (BC cells / edges), dropped (nothing to store)]}
+        roofline["tile_lists"] = {str(k[0]): list(v[1:]) for k, v in sorted(bc._fused_orders.items()) if k[5:] == (0, 0) and k[1:3] == (bc.dom.r0, bc.dom.r1)}
+    except Exception:  # noqa: BLE001
+        pass
     if kernel_alone:
         kernel_alone["algorithmic_gbs"] = ALGO_BYTES_PER_CELL_SWEEP * cells_gpu * kernel_alone["T"] / (kernel_alone["us_per_launch"] * 1e-6) / 1e9
         kernel_alone["frac_algorithmic"] = kernel_alone["algorithmic_gbs"] / peak

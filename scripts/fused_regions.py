@@ -70,8 +70,10 @@ tail = find("parity ^= 1;", slow_end)
 end = find("#undef FS2D_ISSUE", tail)
 regions = [
     ("helper: mbarrier wait (TMA arrival)", *fn_range("void mbar_wait")),
-    ("helper: TMA issue (expect_tx + UTMALDG)", find("void mbar_expect_tx("), find("// progress counters of the warps")),
-    ("helper: poll neighbours (flag_wait_ge)", find("int ld_acquire_smem("), find("// generic-proxy accesses")),
+    ("helper: TMA issue (expect_tx + UTMALDG)", find("void mbar_expect_tx("), find("// The iteration loop of the autonomous warps addresses")),
+    ("helper: shared ld/st by address (edge rows)", find("float4 lds4_s("), find("// progress counters of the warps")),
+    ("helper: release store of the counter", find("void st_release_s("), find("// the smaller of two counters")),
+    ("helper: poll neighbours (peek / wait)", find("int flag_peek2("), find("// generic-proxy accesses")),
     ("helper: proxy fence", find("void fence_proxy_async("), find("void fence_proxy_async(") + 1),
     ("open tile: shuffles", *fn_range("void jacobi_rows_shuffles")),
     ("open tile: rows 1..6 (no neighbour needed)", *fn_range("void jacobi_rows_inner")),

@@ -127,9 +127,16 @@ def main() -> None:
     for num, X, Y, scheme, vc, pkw, steps, halo in cases:
         res = Y
         dt, dx, re = 0.05 / res, 1.0 / res, 1e4
-        const, mask = random_scene(int(num[4:]), X, Y) if isinstance(num, str) else build_scene(num, X, Y)
         part = Partition(X, rank, world, halo)
-        strip = make_solver(BoundaryCondition(const, mask, device=dev, partition=part), dt, dx, re, vc, scheme, **pkw)
+        if isinstance(num, str):
+            const, mask = random_scene(int(num[4:]), X, Y)
+            strip = make_solver(BoundaryCondition(const, mask, device=dev, partition=part), dt, dx, re, vc, scheme, **pkw)
+        else:   # the strip is built from ITS rows of the scene only (build_scene(rows=...), row_offset), the single domain from the whole scene
+            a0, a1 = BoundaryCondition.strip_rows(part)
+            c_w, m_w = build_scene(num, X, Y, rows=(a0, a1))
+            strip = make_solver(BoundaryCondition(c_w, m_w, device=dev, partition=part, row_offset=a0), dt, dx, re, vc, scheme, **pkw)
+            del c_w, m_w
+            const, mask = build_scene(num, X, Y) if rank == 0 else (None, None)
         single = make_solver(BoundaryCondition(const, mask, device=dev), dt, dx, re, vc, scheme, **pkw) if rank == 0 else None
         del const, mask
         rng = np.random.default_rng(1234 + (num if isinstance(num, int) else 50 + int(num[4:])))
