@@ -94,43 +94,6 @@ def vorticity_apply_distributed(vc, v: DoubleBuffer) -> None:
     _overlapped(bc, hx, [(v.current, 2)], lambda: vc._apply_fused(v.next, v.current), 2)
 
 
-class _Side:
-    """Edge work of a split kernel on a second stream.  A kernel that needs fresh halo rows is split into the rows that
-    do not read them (launched at once, while the SendRecv is in flight) and the edge rows (launched when the halo has
-    arrived).  Queued behind the interior launch on the SAME stream, the edge launch would only start when the last
-    interior block has finished -- two kernel tails and a launch gap per split kernel.  On a second stream it depends on
-    the halo and on the kernel's inputs only, so its blocks fill the SMs the interior launch frees as it drains.
-
-        side = _Side(bc, tensor)      # forks here: the side stream sees everything enqueued so far
-        <interior launch>             # current stream
-        with side:                    # side stream
-            hx.finish(reqs); <edge launches>
-        # leaving the block joins: the current stream waits for the side stream
-
-    CPU tensors (host-logic tests under gloo): everything runs in program order on the host, `with side` is a no-op."""
-
-    def __init__(self, bc, like: torch.Tensor) -> None:
-        self.cuda = like.is_cuda
-        if self.cuda:
-            self.stream = getattr(bc, "_side_stream", None)
-            if self.stream is None:
-                self.stream = bc._side_stream = torch.cuda.Stream(device=like.device)
-            self.stream.wait_event(torch.cuda.current_stream().record_event())
-
-    def __enter__(self):
-        if self.cuda:
-            self._ctx = torch.cuda.stream(self.stream)
-            self._ctx.__enter__()
-        return self
-
-    def __exit__(self, *exc):
-        if self.cuda:
-            done = self.stream.record_event()
-            self._ctx.__exit__(*exc)
-            torch.cuda.current_stream().wait_event(done)
-        return False
-
-
 @contextmanager
 def _rows(bc, r0: int, r1: int):
     """Temporarily restrict the rows the kernels of `bc` update (they all take bc.dom)."""
@@ -152,16 +115,13 @@ def _overlapped(bc, hx: HaloExchanger, exchanges: list, launch, reach: int) -> N
         launch()
         return
     reqs = hx.start(exchanges)
-    f0 = exchanges[0][0]
-    side = _Side(bc, f0.tensor if isinstance(f0, Field) else f0)
     with _rows(bc, d.r0 + reach, d.r1 - reach):
         launch()
-    with side:
-        hx.finish(reqs)
-        with _rows(bc, d.r0, d.r0 + reach):
-            launch()
-        with _rows(bc, d.r1 - reach, d.r1):
-            launch()
+    hx.finish(reqs)
+    with _rows(bc, d.r0, d.r0 + reach):
+        launch()
+    with _rows(bc, d.r1 - reach, d.r1):
+        launch()
 
 
 def _pass_windows(bc, t: int):
@@ -224,11 +184,9 @@ def jacobi_update_distributed(jac, p: DoubleBuffer, v_current: Field) -> None:
                 jac._fused(p.next, p.current, src, t, emit=emit)
             else:
                 reqs = hx.start(p.current, t)
-                side = _Side(bc, p.current.tensor)
                 jac._fused(p.next, p.current, src, t, dom=mid, emit=emit)              # tile rows [1, m): owned rows only
-                with side:   # the edge tile rows wait for the halo only: their blocks run as the interior launch drains
-                    hx.finish(reqs)
-                    jac._fused(p.next, p.current, src, t, skip=(1, m - 1), emit=emit)  # tile rows {0} U [m, k) in one launch
+                hx.finish(reqs)
+                jac._fused(p.next, p.current, src, t, skip=(1, m - 1), emit=emit)      # tile rows {0} U [m, k) in one launch
         else:
             hx.exchange(p.current, 2)
             bc.set_pressure_boundary_condition(p.current)       # owned rows and the first halo row
