@@ -22,10 +22,26 @@ __global__ void k_dye_bc(float *__restrict__ dye, const float *__restrict__ bc_d
     dye[o + 2] = bc_dye[o + 2];
 }
 
-// fs/solver.py:46-49  clamp_field (all cells, all components)
+// fs/solver.py:46-49  clamp_field (all cells, all components): ti.min(ti.max(f, low), high).  A value that is already inside
+// [low, high] is not written back (same bits either way): after the first step almost every dye value is, so the pass is a
+// read of the field (12 B/cell) instead of a read and a write ("already inside" = the clamped value has the same BITS, so NaN -> low and -0 -> what fmaxf makes of it are still stored).
 __global__ void __launch_bounds__(256) k_clamp(float *__restrict__ f, size_t begin, size_t end, float low, float high) {
     const size_t k = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < end) f[k] = fminf(fmaxf(f[k], low), high);
+    if (k < end) {
+        const float v = f[k], c = fminf(fmaxf(v, low), high);
+        if (__float_as_uint(c) != __float_as_uint(v)) f[k] = c;
+    }
+}
+// the same on 16-byte chunks [begin4, end4) of the array
+__global__ void __launch_bounds__(256) k_clamp4(float4 *__restrict__ f, size_t begin4, size_t end4, float low, float high) {
+    const size_t k = begin4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= end4) return;
+    const float4 v = f[k];
+    const float4 c = make_float4(fminf(fmaxf(v.x, low), high), fminf(fmaxf(v.y, low), high), fminf(fmaxf(v.z, low), high),
+                                 fminf(fmaxf(v.w, low), high));
+    if (__float_as_uint(c.x) != __float_as_uint(v.x) || __float_as_uint(c.y) != __float_as_uint(v.y) ||
+        __float_as_uint(c.z) != __float_as_uint(v.z) || __float_as_uint(c.w) != __float_as_uint(v.w))
+        f[k] = c;
 }
 
 // fs/solver.py:157-161  DyeMacSolver._update_dye: dn = dc - dt * advect(vc, dc)   (fluid cells)
@@ -213,7 +229,10 @@ int fs2d_clamp(float *f, fs2d_dom d, int channels, float low, float high, void *
     if (d.r1 == d.r0) return FS2D_OK;
     const size_t begin = (size_t)d.r0 * d.Y * channels, end = (size_t)d.r1 * d.Y * channels;
     ++g_launches;
-    k_clamp<<<(unsigned)((end - begin + 255) / 256), 256, 0, STREAM>>>(f, begin, end, low, high);
+    if ((uintptr_t)f % 16 == 0 && begin % 4 == 0 && end % 4 == 0)
+        k_clamp4<<<(unsigned)(((end - begin) / 4 + 255) / 256), 256, 0, STREAM>>>(reinterpret_cast<float4 *>(f), begin / 4, end / 4, low, high);
+    else
+        k_clamp<<<(unsigned)((end - begin + 255) / 256), 256, 0, STREAM>>>(f, begin, end, low, high);
     FS2D_LAUNCH_CHECK();
     return FS2D_OK;
 }

@@ -219,6 +219,101 @@ __global__ void __launch_bounds__(TX *TY)
     pn[idx] = one_minus_omega * pc[idx] + omega * pred;
 }
 
+// fs/pressure_updater.py:86-96  BOTH colour passes of one red-black SOR iteration in one pass over HBM:
+//     odd cells:   pn = (1 - w) pc + w predict(pc)          (_update_pressures_odd,  :98-102)
+//     even cells:  pn = (1 - w) pn + w predict(pn)          (_update_pressures_even, :104-108, reads the odd cells just written)
+// A warp owns 120 columns x RB_ROWS rows (lane l: columns J0 + 4l .. 4l+3; lanes 0 and 31 only supply j-neighbours) and
+// marches down the rows: the "odd-updated" row O[q] (odd fluid cells relaxed from pc, every other cell = what pn holds) is
+// formed in registers, and as soon as O[q-2], O[q-1], O[q] exist the even cells of row q-1 are relaxed from them and the
+// row is stored -- only its fluid cells, so never-written cells keep their values.  O of the rows just
+// outside the chunk is recomputed by both neighbours (it depends on pc and on never-written cells of pn only), so chunks
+// are independent.  21 B/cell (pc 4, pn 4 + 4, source 8, mask 1) instead of two passes over all five arrays; same
+// expression and order per cell: bit-identical to the two k_rbsor_pass launches.  Requires Y % 4 == 0, pn != pc.
+constexpr int RB_ROWS = 32, RB_WARPS = 8, RB_COLS = 120;
+__global__ void __launch_bounds__(32 * RB_WARPS)
+    k_rbsor_fused(float *__restrict__ pn, const float *__restrict__ pc, const float *__restrict__ src,
+                  const uint8_t *__restrict__ mask, fs2d_dom d, float omega, float one_minus_omega) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    const int lane = threadIdx.x;
+    const int jc0 = FS2D_COLBLK * RB_COLS - 4 + 4 * lane;
+    const bool in_grid = jc0 >= 0 && jc0 < d.Y;
+    const int jc = in_grid ? jc0 : (jc0 < 0 ? 0 : d.Y - 4);   // lanes outside the grid read a valid address, their values are unused
+    const bool owner = in_grid && lane >= 1 && lane <= 30;
+    const bool left_edge = jc0 == 0, right_edge = jc0 + 4 >= d.Y;
+    const int rb = d.r0 + (FS2D_ROWBLK * RB_WARPS + threadIdx.y) * RB_ROWS;
+    const int re = min(rb + RB_ROWS, d.r1);
+    if (rb >= re) return;   // warp-uniform
+    auto row4 = [&](const float *f, int r) { return __ldg(reinterpret_cast<const float4 *>(f + IX(d, CR(d, r), jc))); };
+    float4 pc_m = row4(pc, rb - 2), pc_0 = row4(pc, rb - 1), pc_p;
+    float Om2[4] = {0, 0, 0, 0}, Om1[4] = {0, 0, 0, 0}, Oq[4];
+    float t2m[4] = {0, 0, 0, 0}, t3m[4] = {0, 0, 0, 0};
+    uint32_t fluid_m = 0;   // bit h: cell h of row q-1 is a fluid cell
+    for (int q = rb - 1; q <= re; ++q) {
+        pc_p = row4(pc, q + 1);
+        const int qc = CR(d, q);   // rows outside the clamp window are formed from a valid row; they are never used (see up / down below)
+        const size_t idx = IX(d, qc, jc);
+        const float4 old = *reinterpret_cast<const float4 *>(pn + idx);   // plain load: pn is written by this kernel
+        const float4 s01 = __ldg(reinterpret_cast<const float4 *>(src + 2 * idx)), s23 = __ldg(reinterpret_cast<const float4 *>(src + 2 * idx) + 1);
+        const uchar4 mk = __ldg(reinterpret_cast<const uchar4 *>(mask + idx));
+        const float t2[4] = {s01.x, s01.z, s23.x, s23.z}, t3[4] = {s01.y, s01.w, s23.y, s23.w};
+        const uint32_t fluid = (uint32_t)(mk.x == 0) | ((uint32_t)(mk.y == 0) << 1) | ((uint32_t)(mk.z == 0) << 2) | ((uint32_t)(mk.w == 0) << 3);
+        // ---- odd cells of row q from pc ----
+        float pl = __shfl_up_sync(FULL, pc_0.w, 1), pr = __shfl_down_sync(FULL, pc_0.x, 1);
+        if (left_edge) pl = pc_0.x;      // sample() clamps to the cell itself
+        if (right_edge) pr = pc_0.w;
+        const float c0[4] = {pc_0.x, pc_0.y, pc_0.z, pc_0.w};
+        const float e0[4] = {pc_p.x, pc_p.y, pc_p.z, pc_p.w}, w0[4] = {pc_m.x, pc_m.y, pc_m.z, pc_m.w};
+        const float q0[4] = {pc_0.y, pc_0.z, pc_0.w, pr}, z0[4] = {pl, pc_0.x, pc_0.y, pc_0.z};
+        const float o4[4] = {old.x, old.y, old.z, old.w};
+        const int par0 = (d.gi0 + qc + jc) & 1;   // parity of the lane's first cell in row q
+        const bool in_window = q >= d.r0 && q < d.r1;   // the odd pass only touches the rows [r0, r1): a row outside them is what pn holds
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const float pred = 0.25f * (e0[h] + w0[h] + q0[h] + z0[h]) + t2[h] - t3[h];
+            const bool odd = ((par0 + h) & 1) == 1;
+            Oq[h] = (in_window && odd && ((fluid >> h) & 1u)) ? one_minus_omega * c0[h] + omega * pred : o4[h];
+        }
+        // ---- even cells of row q-1 from O[q-2], O[q-1], O[q]; store the row ----
+        if (q - 1 >= rb) {
+            const int r = q - 1;
+            float ol = __shfl_up_sync(FULL, Om1[3], 1), orr = __shfl_down_sync(FULL, Om1[0], 1);
+            if (left_edge) ol = Om1[0];
+            if (right_edge) orr = Om1[3];
+            const bool has_up = r - 1 >= d.clo, has_dn = r + 1 <= d.chi;
+            const float qn[4] = {Om1[1], Om1[2], Om1[3], orr}, zn[4] = {ol, Om1[0], Om1[1], Om1[2]};
+            const int par1 = (d.gi0 + r + jc) & 1;
+            float out[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const float pe = has_dn ? Oq[h] : Om1[h], pw = has_up ? Om2[h] : Om1[h];
+                const float pred = 0.25f * (pe + pw + qn[h] + zn[h]) + t2m[h] - t3m[h];
+                const bool even = ((par1 + h) & 1) == 0;
+                out[h] = (even && ((fluid_m >> h) & 1u)) ? one_minus_omega * Om1[h] + omega * pred : Om1[h];
+            }
+            if (owner && fluid_m) {
+                float *dst = pn + IX(d, r, jc);
+                if (fluid_m == 15u) {
+                    *reinterpret_cast<float4 *>(dst) = make_float4(out[0], out[1], out[2], out[3]);
+                } else {
+#pragma unroll
+                    for (int h = 0; h < 4; ++h)
+                        if ((fluid_m >> h) & 1u) dst[h] = out[h];
+                }
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            Om2[h] = Om1[h];
+            Om1[h] = Oq[h];
+            t2m[h] = t2[h];
+            t3m[h] = t3[h];
+        }
+        fluid_m = fluid;
+        pc_m = pc_0;
+        pc_0 = pc_p;
+    }
+}
+
 static void launch_jacobi(float *pn, const float *pc, const float *src, const uint8_t *pcode, const fs2d_dom &d,
                           int inline_bc, cudaStream_t s) {
     const bool vec = (d.Y % 4 == 0) && ((uintptr_t)pn % 16 == 0) && ((uintptr_t)pc % 16 == 0) &&
@@ -257,6 +352,7 @@ int fs2d_set_tuning(int key, int value) {
     if (key == 2 && value >= 0 && value <= 2) { fs2d::g_stream = value; return FS2D_OK; }
     if (key == 3 && value >= 0 && value <= 3) { fs2d::g_stream_cfg = value; return FS2D_OK; }
     if (key == 4 && (value == 0 || value == 1)) { fs2d::g_tail_emit = value; return FS2D_OK; }
+    if (key == 6 && value >= 0 && value <= 64) { fs2d::g_reserve_sms = value; return FS2D_OK; }
     set_error("unknown tuning key %d / value %d", key, value);
     return FS2D_E_BADARG;
 }
@@ -388,6 +484,24 @@ int fs2d_jacobi_update(float *pa, float *pb, const float *src, const uint8_t *pc
     }
     FS2D_LAUNCH_CHECK();
     if (final_in_b) *final_in_b = (cur == pb);
+    return FS2D_OK;
+}
+
+int fs2d_rbsor_iteration(float *pn, const float *pc, const float *src, const uint8_t *mask, fs2d_dom d, float omega,
+                         float one_minus_omega, void *stream) {
+    FS2D_REQUIRE(pn && pc && src && mask && pn != pc, "null/aliased field pointer");
+    if (int e = check_dom(d)) return e;
+    if (d.r1 == d.r0) return FS2D_OK;
+    const bool vec = (d.Y % 4 == 0) && ((uintptr_t)pn % 16 == 0) && ((uintptr_t)pc % 16 == 0) && ((uintptr_t)src % 16 == 0) &&
+                     ((uintptr_t)mask % 4 == 0);
+    if (!vec) {   // the two colour passes of the reference, one kernel each
+        if (int e = fs2d_rbsor_pass(pn, pc, src, mask, d, omega, one_minus_omega, 1, stream)) return e;
+        return fs2d_rbsor_pass(pn, pn, src, mask, d, omega, one_minus_omega, 0, stream);
+    }
+    ++g_launches;
+    const dim3 blk(32, RB_WARPS, 1), grd(nblk(d.Y, RB_COLS), nblk(d.r1 - d.r0, RB_ROWS * RB_WARPS), 1);
+    k_rbsor_fused<<<grd, blk, 0, STREAM>>>(pn, pc, src, mask, d, omega, one_minus_omega);
+    FS2D_LAUNCH_CHECK();
     return FS2D_OK;
 }
 

@@ -61,6 +61,7 @@ _SIGNATURES = {
     "fs2d_jacobi_fused_tail": (c_int, [_P, _P, _P, _P, Dom, c_int, c_int, c_int, _P, c_int, _P]),
     "fs2d_fused_tile": (c_int, [c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "fs2d_rbsor_pass": (c_int, [_P, _P, _P, _P, Dom, c_float, c_float, c_int, _P]),
+    "fs2d_rbsor_iteration": (c_int, [_P, _P, _P, _P, Dom, c_float, c_float, _P]),
     "fs2d_limit": (c_int, [_P, Dom, c_float, _P]),
     "fs2d_render": (c_int, [_P, _P, _P, _P, _P, Dom, c_float, c_int, _P]),
     "fs2d_dye_bc": (c_int, [_P, _P, _P, c_int, _P]),

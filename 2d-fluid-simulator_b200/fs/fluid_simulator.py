@@ -57,6 +57,7 @@ class FluidSimulator:
 
     # -- CUDA-graph stepping (not in the reference): one graph launch per time step -------------------
     _graphs = None
+    _graph_strips = False
 
     def _buffers(self) -> list:
         s = self._solver
@@ -77,8 +78,11 @@ class FluidSimulator:
             raise NotImplementedError("CUDA-graph stepping on row strips is opt-in: enable_cuda_graph(strips=True) on every rank")
         if self._graphs is not None:
             return
+        self._graph_strips = strips
         self._solver.update()               # warm-up outside capture: lazy allocations, one-time validity checks
         torch.cuda.synchronize()
+        for f in (self._solver.p.current, self._solver.p.next):
+            f.dirty = False                 # whatever the pressure updater validates per host write, it has validated now (see _replay)
         start = [id(b.current) for b in self._buffers()]
         graphs = []
         for _ in range(2):                  # period <= 2: every buffer swaps a fixed number of times per step
@@ -102,10 +106,9 @@ class FluidSimulator:
         if any(b.current.dirty or b.next.dirty for b in self._buffers() if b is self._solver.p):
             # a pressure buffer was rewritten from the host (from_numpy / load_state_dict) since the capture: the captured
             # schedule may contain fused passes whose precondition (equal never-written wall cells) no longer holds.
-            # Drop the graphs, run this step eagerly (the updater re-validates), and capture again on the next call.
+            # Drop the graphs and capture again: the warm-up step of the capture IS this step (eager; the updater re-validates).
             self._graphs = None
-            self._solver.update()
-            self.enable_cuda_graph()
+            self.enable_cuda_graph(strips=self._graph_strips)
             return
         g, flips = self._graphs[self._phase]
         g.replay()

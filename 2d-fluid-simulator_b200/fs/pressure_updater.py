@@ -183,8 +183,17 @@ class RedBlackSorPressureUpdater(PressureUpdater):
 
     def _update(self, p_next: Field, p_current: Field, v_current: Field, src: Field | None = None) -> None:
         src = src if src is not None else self._source(v_current)
+        if self.fused_colours and p_next is not p_current:
+            bc, w = self._bc, self._relaxation_factor      # both colour passes in one pass over HBM (fs2d_rbsor_iteration)
+            _lib.call("fs2d_rbsor_iteration", p_next.ptr(), p_current.ptr(), src.ptr(), _lib.ptr(bc._bc_mask), bc.dom, w, 1.0 - w,
+                      _lib.stream())
+            return
         self._pass(p_next, p_current, src, 1)   # _update_pressures_odd  (:98-102)
         self._pass(p_next, p_next, src, 0)      # _update_pressures_even (:104-108), pc = pn
+
+    #: one kernel per iteration instead of one per colour (same results bit for bit); the strips of a multi-rank run keep the
+    #: two passes (fs/halo.py: the neighbour's odd cells are exchanged in between)
+    fused_colours = True
 
     def update(self, p: DoubleBuffer, v_current: Field) -> None:
         if self._bc.partition.world > 1:

@@ -77,6 +77,9 @@ unsigned long long fs2d_launch_count(void);
  * key 3 = streaming-kernel shape {stages x CTAs/SM x threads}: {0: 3x2x256, 1: 2x3x256 (default), 2: 3x2x512, 3: 2x2x512}.
  * key 4 = tail of fs2d_jacobi_update {1 (default): the last fused pass also emits the BC values of its penultimate state, so
  *         ONE literal iteration ends the update; 0: two literal iterations}.
+ * key 6 = SMs the persistent kernels (fused Jacobi, TMA-streamed stencils) leave free {0 (default) .. 64}: a multi-rank host
+ *         sets a few so that the NCCL SendRecv of a halo exchange can run BESIDE the kernel it is meant to overlap (a persistent
+ *         grid otherwise holds every SM until its first CTA exits).
  * Unknown keys / values return FS2D_E_BADARG and change nothing. */
 int fs2d_set_tuning(int key, int value);
 /* 1 if the library was built for sm_100a and a device of compute capability 10.x is current */
@@ -198,6 +201,12 @@ int fs2d_fused_tile(int T, int *rows, int *cols, int *halo_rows, int *halo_cols,
  * colour `parity`, (i_global + j) % 2); pc may alias pn (even pass, :96); src as above */
 int fs2d_rbsor_pass(float *pn, const float *pc, const float *src, const uint8_t *mask, fs2d_dom d, float omega,
                     float one_minus_omega, int parity, void *stream);
+/* RedBlackSorPressureUpdater._update, fs/pressure_updater.py:86-96: the odd pass (pn <- pc) followed by the even pass
+ * (pn <- pn) in ONE pass over HBM, bit-identical to fs2d_rbsor_pass(pn, pc, .., 1) + fs2d_rbsor_pass(pn, pn, .., 0);
+ * pn must not alias pc.  (A rank of a row-strip decomposition keeps the two passes: the neighbour's odd cells travel
+ * in between.) */
+int fs2d_rbsor_iteration(float *pn, const float *pc, const float *src, const uint8_t *mask, fs2d_dom d, float omega,
+                         float one_minus_omega, void *stream);
 /* ---- dye transport (3-channel AoS fields; DyeMacSolver / DyeCipMacSolver, fs/solver.py:110-161, :335-401) ---- */
 /* DyeBoundaryCondition.set_dye_boundary_condition, fs/boundary_condition.py:94-99: dye[tgt] = bc_dye[tgt] for
  * the inflow cells listed in tgt (linear cell indices into the local array) */

@@ -294,6 +294,11 @@ class FakeFs2d:
         sets = [(d.r0 + q * ti, min(d.r0 + (q + 1) * ti, d.r1)) for q in range(k) if not (skip_from <= q < skip_from + skip_n)]
         self._fused_rows(p_out, p_in, src, pcode, d, T, sets, emit=True)
 
+    def fs2d_rbsor_iteration(self, pn, pc, src, mask, d, omega, one_minus_omega, stream) -> None:
+        """by definition (include/fs2d.h): the odd pass pn <- pc, then the even pass pn <- pn"""
+        self.fs2d_rbsor_pass(pn, pc, src, mask, d, omega, one_minus_omega, 1, stream)
+        self.fs2d_rbsor_pass(pn, pn, src, mask, d, omega, one_minus_omega, 0, stream)
+
     def fs2d_rbsor_pass(self, pn, pc, src, mask, d, omega, one_minus_omega, parity, stream) -> None:
         PC, S, M = self.a(pc, d, 1), self.a(src, d, 2), self.a(mask, d)
         dt, dx = self.src_params[src]

@@ -508,11 +508,40 @@ def test_cuda_graph_stepping_is_bitwise_identical(env, scheme, vc, n_iter, dye):
     graph = cls.create(*args, pressure="jacobi", n_iter=n_iter)
     graph.enable_cuda_graph()
     eager.step()                                  # enable_cuda_graph() ran one warm-up step
+    captured = graph._graphs
     for n in range(5):
         eager.step(); graph.step()
         se, sg = eager.state_dict(), graph.state_dict()
         for k in se:
             assert_bitexact(f"step {n} {k}", sg[k], se[k])
+    assert graph._graphs is captured, "the graphs must be replayed, not re-captured, while nobody writes the buffers from the host"
+
+
+def test_cuda_graph_default_path_replays_and_recaptures_after_host_writes(env):
+    """The facade's defaults (RB-SOR x2, dye): step() replays the captured graphs (r02 regression: a never-cleared `dirty` flag
+    made every step drop and re-capture them); a pressure buffer rewritten from the host drops them once, and stepping stays
+    bit-identical to eager stepping."""
+    from fs.fluid_simulator import DyeFluidSimulator
+
+    res = 64
+    args = (3, res, 0.05 / res, 1.0 / res, 1e4, 5.0, "cip")
+    eager, graph = DyeFluidSimulator.create(*args), DyeFluidSimulator.create(*args)
+    graph.enable_cuda_graph()
+    eager.step()
+    captured = graph._graphs
+    for _ in range(3):
+        eager.step(); graph.step()
+    assert graph._graphs is captured
+    rng = np.random.default_rng(5)
+    p_new = rng.uniform(-1, 1, eager.solver.p.current.to_numpy().shape).astype(np.float32)
+    for sim in (eager, graph):
+        sim.solver.p.current.from_numpy(p_new)
+    for n in range(3):
+        eager.step(); graph.step()
+        se, sg = eager.state_dict(), graph.state_dict()
+        for k in se:
+            assert_bitexact(f"after host write, step {n} {k}", sg[k], se[k])
+    assert graph._graphs is not None and graph._graphs is not captured
 
 
 # ------------------------------------------------------------------------------------------------
@@ -828,3 +857,43 @@ def test_limit_skip_trajectory_vs_oracle(env, scale):
     _limit_skip_check(scale)
 
 
+
+
+# ------------------------------------------------------------------------------------------------
+# 12. red-black SOR: both colour passes in one kernel == the two reference passes
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("num,X,Y", [(1, 128, 64), (2, 256, 128), (3, 200, 176), (5, 384, 192), (4, 97, 80), (2, 1000, 512)])
+def test_rbsor_fused_colours_equal_two_passes(env, num, X, Y):
+    """fs2d_rbsor_iteration == fs2d_rbsor_pass(odd, pn <- pc) + fs2d_rbsor_pass(even, pn <- pn): whole grid and row windows with
+    clamp bounds inside the array, random fields in BOTH buffers (stale values of never-written cells must survive), also on
+    masks with fluid cells on the grid's first / last rows."""
+    from fs import _lib
+    from fs.boundary_condition import BoundaryCondition, build_scene
+    from fs.pressure_updater import RedBlackSorPressureUpdater
+
+    const, mask = build_scene(num, X, Y)
+    rng = np.random.default_rng(num * 1000 + X)
+    for variant in range(2):
+        m = mask.copy()
+        if variant == 1:      # fluid cells on the first / last rows and next to the first / last columns: every clamp of sample()
+            m[:2, 2:-2] = np.where(rng.random((2, Y - 4)) < 0.5, 0, m[:2, 2:-2])
+            m[-2:, 2:-2] = np.where(rng.random((2, Y - 4)) < 0.5, 0, m[-2:, 2:-2])
+            m[4:-4, :2] = np.where(rng.random((X - 8, 2)) < 0.5, 0, m[4:-4, :2])
+            m[4:-4, -2:] = np.where(rng.random((X - 8, 2)) < 0.5, 0, m[4:-4, -2:])
+        bc = BoundaryCondition(const, m)
+        sor = RedBlackSorPressureUpdater(bc, 0.05 / Y, 1.0 / Y, 1.3, 1)
+        v = fld(rng.uniform(-1, 1, m.shape + (2,)).astype(np.float32))
+        src = sor._source(v)
+        pc0, pn0 = (rng.uniform(-1, 1, m.shape).astype(np.float32) for _ in range(2))
+        doms = [bc.dom, bc.dom.replace(r0=5, r1=X - 11, clo=2, chi=X - 3), bc.dom.replace(r0=33, r1=34)]
+        for dom in doms:
+            res = []
+            for fused in (True, False):
+                pc, pn = fld(pc0), fld(pn0)
+                if fused:
+                    _lib.call("fs2d_rbsor_iteration", pn.ptr(), pc.ptr(), src.ptr(), _lib.ptr(bc._bc_mask), dom, 1.3, 1.0 - 1.3, _lib.stream())
+                else:
+                    sor._pass(pn, pc, src, 1, dom=dom)
+                    sor._pass(pn, pn, src, 0, dom=dom)
+                res.append(pn.to_numpy())
+            assert_bitexact(f"bc{num} {X}x{Y} variant {variant} rows {dom.r0}:{dom.r1}", res[0], res[1])

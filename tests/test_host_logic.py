@@ -145,7 +145,7 @@ def test_single_domain_host_layer_equals_reference_orchestration(case, monkeypat
     if pkw["pressure"] == "jacobi":
         assert v_part[len(head) + 1:] == ["fs2d_jacobi_update", "fs2d_limit"]
     else:
-        assert v_part[len(head) + 1:] == ["fs2d_pressure_bc", "fs2d_rbsor_pass", "fs2d_rbsor_pass"] * pkw["n_iter"] + ["fs2d_limit"]
+        assert v_part[len(head) + 1:] == ["fs2d_pressure_bc", "fs2d_rbsor_iteration"] * pkw["n_iter"] + ["fs2d_limit"]
     dye_part = step[len(v_part):]
     if not dye:
         assert dye_part == []

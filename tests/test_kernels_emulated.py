@@ -187,3 +187,8 @@ def test_emu_synchronisation_under_adversarial_warp_schedules(seed):
     out = subprocess.run([sys.executable, "-m", "pytest", __file__, "-x", "-q", "-p", "no:cacheprovider", "-k", sel],
                          capture_output=True, text=True, timeout=1200, env=dict(os.environ, FS2D_EMU_SCHED=str(seed)))
     assert out.returncode == 0 and " passed" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("num,X,Y", [(1, 128, 64), (3, 200, 176), (4, 97, 80)])
+def test_emu_rbsor_fused_colours_equal_two_passes(env, num, X, Y):
+    G.test_rbsor_fused_colours_equal_two_passes(env, num, X, Y)
