@@ -132,11 +132,21 @@ __device__ __forceinline__ float2 operator-(float2 a) { return make_float2(-a.x,
 // vorticity gradients are exactly 0 there) made that slow path the common case.  0 / y = +-0 (sign = XOR of the
 // signs) for every y but 0 and NaN, where it is NaN.
 __device__ __forceinline__ float fdiv_z(float x, float y) {
+#ifdef FS2D_FDIV_BRANCHLESS
     const bool z = x == 0.0f;
     const bool ybad = !(fabsf(y) > 0.0f);   // y is 0 or NaN
     const float q = (z ? 1.0f : x) / ((z && ybad) ? 1.0f : y);
     const float sz = __int_as_float((__float_as_int(x) ^ __float_as_int(y)) & (int)0x80000000);
     return z ? (ybad ? __int_as_float(0x7fffffff) : sz) : q;
+#else
+    // a real branch: warps whose dividends are all zero (uniform regions: the whole grid of a quiescent start) skip the
+    // division sequence altogether; in mixed warps the non-zero lanes divide as usual
+    if (x == 0.0f) {
+        const bool ybad = !(fabsf(y) > 0.0f);   // y is 0 or NaN
+        return ybad ? __int_as_float(0x7fffffff) : __int_as_float((__float_as_int(x) ^ __float_as_int(y)) & (int)0x80000000);
+    }
+    return x / y;
+#endif
 }
 __device__ __forceinline__ float2 operator/(float2 a, float s) { return make_float2(fdiv_z(a.x, s), fdiv_z(a.y, s)); }
 __device__ __forceinline__ float2 operator/(float2 a, float2 b) { return make_float2(fdiv_z(a.x, b.x), fdiv_z(a.y, b.y)); }

@@ -435,22 +435,6 @@ __global__ void __launch_bounds__(TX *TY) k_limit(float *__restrict__ v, fs2d_do
     }
 }
 
-// EXPERIMENTAL: limit_field that returns at once when the pressure-source pre-pass (k_p_source_vmax, fs2d_pressure.cu) saw no
-// |v|^2 whose square root exceeds the limit -- then no cell would be modified
-__global__ void __launch_bounds__(TX *TY) k_limit_if(float *__restrict__ v, fs2d_dom d, float limit, const unsigned int *__restrict__ vmax) {
-    if (!(sqrtf(__uint_as_float(__ldg(vmax))) > limit)) return;
-    constexpr int NU = NU_LIMIT;
-    FS2D_ROWS(d, j, r, ok)
-    float2 c[NU];
-#pragma unroll
-    for (int u = 0; u < NU; ++u) c[u] = reinterpret_cast<const float2 *>(v)[IX(d, r[u], j)];
-#pragma unroll
-    for (int u = 0; u < NU; ++u) {
-        const float nrm = sqrtf(c[u].x * c[u].x + c[u].y * c[u].y);
-        if (ok[u] && nrm > limit)
-            reinterpret_cast<float2 *>(v)[IX(d, r[u], j)] = make_float2(limit * (c[u].x / nrm), limit * (c[u].y / nrm));
-    }
-}
 
 }  // namespace fs2d
 
@@ -637,15 +621,6 @@ int fs2d_limit(float *v, fs2d_dom d, float limit, void *stream) {
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
     ++g_launches; k_limit<<<dense_grid_nu(d, NU_LIMIT), dense_block(), 0, STREAM>>>(v, d, limit);
-    FS2D_LAUNCH_CHECK();
-    return FS2D_OK;
-}
-
-int fs2d_limit_if(float *v, fs2d_dom d, float limit, const unsigned int *vmax, void *stream) {
-    FS2D_REQUIRE(v && vmax, "null field pointer");
-    if (int e = check_dom(d)) return e;
-    if (d.r1 == d.r0) return FS2D_OK;
-    ++g_launches; k_limit_if<<<dense_grid_nu(d, NU_LIMIT), dense_block(), 0, STREAM>>>(v, d, limit, vmax);
     FS2D_LAUNCH_CHECK();
     return FS2D_OK;
 }

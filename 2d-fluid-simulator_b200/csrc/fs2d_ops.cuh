@@ -135,12 +135,20 @@ __device__ __forceinline__ VortIn l_vort_add(const A &at, const float *vc, const
 template <bool P2>
 __device__ __forceinline__ float2 c_vort_add(const VortIn &x, DivC<P2> ddx, float dtw) {
     const float gx = ddx(0.5f * (x.aip - x.aim)), gy = ddx(0.5f * (x.ajp - x.ajm));
-    const float n2 = gx * gx + gy * gy;
-    const float nrm = n2 == 0.0f ? n2 : sqrtf(n2);                  // sqrt(+0) = +0 without the zero-operand slow path
-    const float nx = fdiv_z(gx, nrm), ny = fdiv_z(gy, nrm);         // 0/0 = NaN on quiescent cells
-    float fx = ny * x.o, fy = -nx * x.o;
-    fx = fmaxf(fminf(fx, 0.1f), -0.1f);  // NaN -> +0.1 by the fminf/fmaxf rule
-    fy = fmaxf(fminf(fy, 0.1f), -0.1f);
+    float fx, fy;
+    if (gx == 0.0f && gy == 0.0f) {
+        // grad|w| = 0 exactly (every cell of a quiescent or uniform region): n = 0/0 = NaN in both components, NaN * w = NaN,
+        // and the clamp turns NaN into +0.1 by the fminf/fmaxf rule whatever w is -- no sqrt, no divisions
+        fx = fy = 0.1f;
+    } else {
+        const float n2 = gx * gx + gy * gy;
+        const float nrm = n2 == 0.0f ? n2 : sqrtf(n2);                  // sqrt(+0) = +0 without the zero-operand slow path
+        const float nx = fdiv_z(gx, nrm), ny = fdiv_z(gy, nrm);         // x/0 = +-inf when the squares underflowed
+        fx = ny * x.o;
+        fy = -nx * x.o;
+        fx = fmaxf(fminf(fx, 0.1f), -0.1f);  // NaN -> +0.1 by the fminf/fmaxf rule
+        fy = fmaxf(fminf(fy, 0.1f), -0.1f);
+    }
     return make_float2(x.c.x + dtw * fx, x.c.y + dtw * fy);
 }
 

@@ -48,43 +48,6 @@ __global__ void __launch_bounds__(TX *TY)
     else b_p_source<true>(src, vc, d, dt, dx);
 }
 
-// fs2d_pressure_source_vmax / fs2d_limit_if (PressureUpdater.limit_skip): the same pre-pass that also leaves max |v|^2 over every cell it
-// reads in *vmax (bit pattern of a non-negative float, atomicMax; NaNs are ignored exactly like limit_field ignores them).
-// Its four neighbour loads cover every cell of the rows [r0, r1), v does not change between this pre-pass and limit_field
-// at the end of the step (fs/solver.py:200-202), and sqrtf is monotone: if sqrtf(max) <= limit, limit_field is a no-op and
-// its 8 B/cell pass over v can be skipped.
-template <bool CL>
-__device__ __forceinline__ void b_p_source_vmax(float *__restrict__ src, const float *__restrict__ vc, const fs2d_dom &d, float dt,
-                                                float dx, unsigned int *vmax) {
-    const int j0 = FS2D_COLBLK * blockDim.x + threadIdx.x;
-    const bool col_ok = j0 < d.Y;
-    const int j = col_ok ? j0 : d.Y - 1;      // no early exit: the whole warp takes part in the reduction below
-    float m = 0.0f;
-#pragma unroll
-    for (int u = 0; u < NU_P_SOURCE; ++u) {
-        const int rr = d.r0 + (FS2D_ROWBLK * NU_P_SOURCE + u) * blockDim.y + threadIdx.y;
-        const bool ok = rr < d.r1;
-        const int r = ok ? rr : d.r1 - 1;
-        const float2 a = ld2<CL>(vc, d, r + 1, j), b = ld2<CL>(vc, d, r - 1, j), c = ld2<CL>(vc, d, r, j + 1), e = ld2<CL>(vc, d, r, j - 1);
-        m = fmaxf(fmaxf(m, a.x * a.x + a.y * a.y), fmaxf(b.x * b.x + b.y * b.y, fmaxf(c.x * c.x + c.y * c.y, e.x * e.x + e.y * e.y)));
-        const float2 sx = a - b, sy = c - e;
-        const float t2 = (sx.x * sx.x + sy.y * sy.y + (sy.x * sx.y)) / 8.0f;
-        const float t3 = fdiv_z(dx * (sx.x + sy.y), 8.0f * dt);
-        if (ok && col_ok) reinterpret_cast<float2 *>(src)[IX(d, r, j)] = make_float2(t2, t3);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    // one atomic per warp at most, and only while the warp's maximum still beats the recorded one (a stale read only costs an
-    // extra atomic): 2 M same-address atomics per pass serialised in L2 and cost more than the limiter pass they replace
-    if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && __float_as_uint(m) > *reinterpret_cast<volatile unsigned int *>(vmax))
-        atomicMax(vmax, __float_as_uint(m));
-}
-__global__ void __launch_bounds__(TX *TY)
-    k_p_source_vmax(float *__restrict__ src, const float *__restrict__ vc, fs2d_dom d, float dt, float dx, unsigned int *vmax) {
-    if (block_interior(d, TY * NU_P_SOURCE, 1)) b_p_source_vmax<false>(src, vc, d, dt, dx, vmax);
-    else b_p_source_vmax<true>(src, vc, d, dt, dx, vmax);
-}
-
 // ---------------------------------------------------------------------------------------------
 // inline pressure BC: post-BC value of cell (r, j) recomputed from the pre-BC field and pcode
 // (fs/boundary_condition.py:41-65); r, j already clamped
@@ -363,18 +326,6 @@ int fs2d_pressure_source(float *src, const float *vc, fs2d_dom d, float dt, floa
     if (d.r1 == d.r0) return FS2D_OK;
     ++g_launches;
     k_p_source<<<dense_grid_nu(d, NU_P_SOURCE), dense_block(), 0, STREAM>>>(src, vc, d, dt, dx);
-    FS2D_LAUNCH_CHECK();
-    return FS2D_OK;
-}
-
-int fs2d_pressure_source_vmax(float *src, const float *vc, fs2d_dom d, float dt, float dx, unsigned int *vmax, int reset,
-                              void *stream) {
-    FS2D_REQUIRE(src && vc && vmax, "null field pointer");
-    if (int e = check_dom(d)) return e;
-    if (reset) FS2D_CUDA_CHECK(cudaMemsetAsync(vmax, 0, sizeof(unsigned int), STREAM));
-    if (d.r1 == d.r0) return FS2D_OK;
-    ++g_launches;
-    k_p_source_vmax<<<dense_grid_nu(d, NU_P_SOURCE), dense_block(), 0, STREAM>>>(src, vc, d, dt, dx, vmax);
     FS2D_LAUNCH_CHECK();
     return FS2D_OK;
 }

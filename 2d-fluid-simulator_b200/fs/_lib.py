@@ -49,8 +49,6 @@ _SIGNATURES = {
     "fs2d_vort_add": (c_int, [_P, _P, _P, _P, _P, Dom, c_float, c_float, _P]),
     "fs2d_vort_apply": (c_int, [_P, _P, _P, _P, _P, Dom, c_float, c_float, _P]),
     "fs2d_pressure_source": (c_int, [_P, _P, Dom, c_float, c_float, _P]),
-    "fs2d_pressure_source_vmax": (c_int, [_P, _P, Dom, c_float, c_float, _P, c_int, _P]),
-    "fs2d_limit_if": (c_int, [_P, Dom, c_float, _P, _P]),
     "fs2d_jacobi_sweep": (c_int, [_P, _P, _P, _P, Dom, c_int, _P]),
     "fs2d_jacobi_update": (c_int, [_P, _P, _P, _P, Dom, c_int, _P, _P, _P, _P, _P, c_int, c_int, POINTER(_P), POINTER(c_int),
                                    POINTER(c_int), _P]),

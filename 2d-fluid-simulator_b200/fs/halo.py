@@ -175,8 +175,8 @@ def jacobi_update_distributed(jac, p: DoubleBuffer, v_current: Field) -> None:
         reqs = hx.start(v_current, min(bc.halo, reach + 1))
         jac._source(v_current, dom=d.replace(r0=d.r0 + 1, r1=d.r1 - 1))
         hx.finish(reqs)
-        jac._source(v_current, dom=ext.replace(r1=d.r0 + 1), first=False)
-        src = jac._source(v_current, dom=ext.replace(r0=d.r1 - 1), first=False)
+        jac._source(v_current, dom=ext.replace(r1=d.r0 + 1))
+        src = jac._source(v_current, dom=ext.replace(r0=d.r1 - 1))
     else:
         hx.exchange(v_current, min(bc.halo, reach + 1))
         src = jac._source(v_current, dom=ext)
@@ -249,7 +249,7 @@ def cip_update_distributed(s) -> None:
     s._pressure_update()
     from fs.solver import VELOCITY_LIMIT, limit_field
 
-    limit_field(v.current, VELOCITY_LIMIT, bc=bc, pressure_updater=s.pressure_updater)
+    limit_field(v.current, VELOCITY_LIMIT, bc=bc)
 
 
 def mac_update_distributed(s) -> None:
@@ -266,7 +266,7 @@ def mac_update_distributed(s) -> None:
     s._pressure_update()
     from fs.solver import VELOCITY_LIMIT, limit_field
 
-    limit_field(s.v.current, VELOCITY_LIMIT, bc=bc, pressure_updater=s.pressure_updater)
+    limit_field(s.v.current, VELOCITY_LIMIT, bc=bc)
 
 
 def dye_update_distributed(s) -> None:

@@ -28,12 +28,6 @@ class PressureUpdater(metaclass=ABCMeta):
     def update(self, p: DoubleBuffer, v_current: Field) -> None:
         pass
 
-    #: EXPERIMENTAL, off by default: the source pre-pass also records max |v|^2, and the solver's limit_field at the end of the
-    #: step (fs/solver.py:202) skips its pass over v when no cell can exceed the limit (fs2d_pressure_source_vmax / fs2d_limit_if)
-    limit_skip = False
-    _vmax = None            # 1-element device tensor: bits of max |v|^2 seen by the pre-passes of the current update
-    _vmax_field = None      # the velocity Field those pre-passes scanned
-
     def _source(self, v_current: Field, dom=None, first: bool = True) -> Field:
         """(t2, t3) velocity terms of predict_p (:23-38), one float2 per cell; v is constant during an
         update (:56-60) so this runs once per update instead of once per sweep.  first=False: a further row window of the
@@ -41,18 +35,7 @@ class PressureUpdater(metaclass=ABCMeta):
         bc = self._bc
         if self._src is None:
             self._src = Field(bc.get_resolution(), 2, bc.device, bc.halo)
-        if self.limit_skip:
-            import torch
-
-            if self._vmax is None:
-                self._vmax = torch.zeros(1, dtype=torch.int32, device=bc.device)
-            _lib.call("fs2d_pressure_source_vmax", self._src.ptr(), v_current.ptr(), dom or bc.dom, self.dt, self.dx,
-                      _lib.ptr(self._vmax), int(first), _lib.stream())
-            self._vmax_field = v_current
-        else:
-            self._vmax_field = None
-            _lib.call("fs2d_pressure_source", self._src.ptr(), v_current.ptr(), dom or bc.dom, self.dt, self.dx,
-                      _lib.stream())
+        _lib.call("fs2d_pressure_source", self._src.ptr(), v_current.ptr(), dom or bc.dom, self.dt, self.dx, _lib.stream())
         return self._src
 
 

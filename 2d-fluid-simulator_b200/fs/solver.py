@@ -51,9 +51,8 @@ class Solver(metaclass=ABCMeta):
             ev[1].record()
 
 
-def limit_field(field: Field, limit: float, dom=None, bc: BoundaryCondition | None = None, pressure_updater=None) -> None:
-    """:38-43 -- rescale |v| > limit to limit (all cells, in place).  pressure_updater: if its source pre-pass of this step
-    recorded max |v|^2 of this very field (experimental PressureUpdater.limit_skip), the pass is skipped when it is a no-op."""
+def limit_field(field: Field, limit: float, dom=None, bc: BoundaryCondition | None = None) -> None:
+    """:38-43 -- rescale |v| > limit to limit (all cells, in place)."""
     if dom is None:
         if bc is not None:
             dom = bc.dom
@@ -61,11 +60,7 @@ def limit_field(field: Field, limit: float, dom=None, bc: BoundaryCondition | No
             X, Y = field.resolution
             dom = _lib.Dom(rows=X + 2 * field.halo, Y=Y, r0=field.halo, r1=field.halo + X, clo=0,
                            chi=X + 2 * field.halo - 1, gi0=0)
-    if pressure_updater is not None and getattr(pressure_updater, "_vmax_field", None) is field:
-        pressure_updater._vmax_field = None      # a recorded maximum is valid for exactly one limiter call
-        _lib.call("fs2d_limit_if", field.ptr(), dom, limit, _lib.ptr(pressure_updater._vmax), _lib.stream())
-    else:
-        _lib.call("fs2d_limit", field.ptr(), dom, limit, _lib.stream())
+    _lib.call("fs2d_limit", field.ptr(), dom, limit, _lib.stream())
 
 
 def clamp_field(field: Field, low: float, high: float, bc: BoundaryCondition | None = None) -> None:
@@ -107,7 +102,7 @@ class MacSolver(Solver):
             self.vorticity_confinement.apply(self.v)
             self.v.swap()
         self._pressure_update()
-        limit_field(self.v.current, VELOCITY_LIMIT, bc=self._bc, pressure_updater=self.pressure_updater)
+        limit_field(self.v.current, VELOCITY_LIMIT, bc=self._bc)
 
     def get_fields(self) -> tuple[Field, Field]:
         return self.v.current, self.p.current
@@ -145,7 +140,7 @@ class CipMacSolver(Solver):
             self.vorticity_confinement.apply(self.v)
             self.v.swap()
         self._pressure_update()
-        limit_field(self.v.current, VELOCITY_LIMIT, bc=self._bc, pressure_updater=self.pressure_updater)
+        limit_field(self.v.current, VELOCITY_LIMIT, bc=self._bc)
 
     def get_fields(self) -> tuple[Field, Field]:
         return self.v.current, self.p.current

@@ -384,18 +384,13 @@ def run_ours(a: argparse.Namespace) -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
     assert lib.fs2d_device_ok(), lib.fs2d_last_error().decode()
-    # experimental kernel selection for A/B runs (default: none): FS2D_TUNING="4=0,limitskip=1" -> fs2d_set_tuning(key, value) pairs;
+    # experimental kernel selection for A/B runs (default: none): FS2D_TUNING="4=0,6=4" -> fs2d_set_tuning(key, value) pairs;
     # recorded in the JSON line as "tuning"
     tuning = {}
     for item in filter(None, os.environ.get("FS2D_TUNING", "").split(",")):
         k, v = item.split("=")
         tuning[k] = int(v)
-        if k == "limitskip":
-            from fs.pressure_updater import PressureUpdater
-
-            PressureUpdater.limit_skip = bool(int(v))
-        else:
-            _lib.call("fs2d_set_tuning", int(k), int(v))
+        _lib.call("fs2d_set_tuning", int(k), int(v))
 
     X, Y = a.rows_per_gpu * world, a.cols
     dt, dx = 0.05 / Y_COLS, 1.0 / Y_COLS

@@ -130,13 +130,6 @@ int fs2d_vort_apply(float *vn, float *w, float *wabs, const float *vc, const uin
  * sx = v(i+1,j) - v(i-1,j), sy = v(i,j+1) - v(i,j-1).  v is constant during one pressure update, so the
  * host computes this once per update; sweeps then evaluate the literal (t1 + t2) - t3. */
 int fs2d_pressure_source(float *src, const float *vc, fs2d_dom d, float dt, float dx, void *stream);
-/* EXPERIMENTAL pair: fs2d_pressure_source that also accumulates max |v|^2 (fl(x*x + y*y), NaNs ignored) over every cell it
- * reads -- a superset of the rows [r0, r1) -- into *vmax (the bits of a non-negative float; reset != 0 zeroes it first), and
- * limit_field that returns at once when sqrtf(*vmax) <= limit, i.e. when it would modify no cell.  The caller guarantees
- * that v was not modified in between and that the limited rows were all covered (fs/solver.py:200-202: they are). */
-int fs2d_pressure_source_vmax(float *src, const float *vc, fs2d_dom d, float dt, float dx, unsigned int *vmax, int reset,
-                              void *stream);
-int fs2d_limit_if(float *v, fs2d_dom d, float limit, const unsigned int *vmax, void *stream);
 /* JacobiPressureUpdater._update, fs/pressure_updater.py:62-66 (not-wall cells), src from
  * fs2d_pressure_source.  inline_bc != 0: neighbour pressures are the post-BC values of `pc`
  * recomputed from `pcode` (pc itself is not modified) == set_pressure_boundary_condition(pc)

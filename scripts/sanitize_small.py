@@ -22,7 +22,6 @@ for num, X, Y in ((2, 256, 128), (3, 200, 176)):
         lib.fs2d_set_tuning(4, tail)
         for stream in (2, 0, 1):        # streaming-kernel selection; ends on the default
             lib.fs2d_set_tuning(2, stream)
-            s.pressure_updater.limit_skip = bool(tail)
             s.update()
     lib.fs2d_set_tuning(4, 1)
     torch.cuda.synchronize()

@@ -61,14 +61,21 @@ if rep:
         r = dom[0]
         scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
         rd, wr = float(r[ri]) * scale[rr[1][ri]], float(r[wi]) * scale[rr[1][wi]]
-        T = 8  # the plan of an 80-iteration update: mostly T = 8 passes (the 3rd fused launch of a step is one)
+        T = int(__import__("os").environ.get("FUSED_T", "7"))  # iterations of the captured launch: the 3rd fused launch of a step; the
+        # schedule of the bench's 80-iteration update is [7 x 9, 8, 8 (emitting), literal] (bench line: roofline.update_schedule)
         cells = 8192 * 8192
         # DRAM bytes of a whole step: every kernel's bytes (its one captured launch) x its launches per step (launch list;
         # one k_limit launch per step).  The fused passes of other sizes are counted with the T = 8 figure.
         per_kernel = {x[ni].split("(")[0].replace("void ", "").replace("fs2d::", ""): (float(x[ri]) * scale[rr[1][ri]] + float(x[wi]) * scale[rr[1][wi]])
                       for x in rr[2:]}
-        steps = max(1, agg.get("k_limit", agg.get("k_limit_if", [1]))[0])
-        step_bytes = sum(per_kernel.get(k, 0.0) * n / steps for k, (n, _) in agg.items())
+        # one step = the launches between the first and the second k_limit of the list (an eager step; later parts of the run
+        # contain the bench's stand-alone timing of the fused kernel)
+        names = [r[ki].split("(")[0].replace("void ", "").replace("fs2d::", "") for r in data if len(r) > mi]
+        lim = [i for i, n in enumerate(names) if n.startswith("k_limit")]
+        one_step = names[lim[0] + 1:lim[1] + 1] if len(lim) >= 2 else names
+        steps = 1
+        step_counts = collections.Counter(one_step)
+        step_bytes = sum(per_kernel.get(k, 0.0) * n for k, n in step_counts.items())
         h = hashlib.sha256()
         for name in ("fs2d_fused.cu", "fs2d_common.cuh"):
             h.update((Path(__file__).resolve().parents[1] / "2d-fluid-simulator_b200" / "csrc" / name).read_bytes())
@@ -78,7 +85,7 @@ if rep:
                    "dram_bytes_per_launch": int(rd + wr), "iterations_per_launch": T,
                    "dram_bytes_per_cell_iteration": round((rd + wr) / cells / T, 2),
                    "algorithmic_bytes_per_launch": 12 * cells * T, "launch_duration_us_under_ncu": float(r[ti]),
-                   "issue_active_pct": float(r[ia]), "step_dram_bytes": int(step_bytes), "steps_in_launch_list": steps,
+                   "issue_active_pct": float(r[ia]), "step_dram_bytes": int(step_bytes), "step_launches": dict(step_counts),
                    "source_sha256": h.hexdigest(),
                    "source": f"profiles/{tag}_kernels_ncu_full.csv (ncu --set full --clock-control none, one capture; bench.py refuses "
                              "this file when the kernel sources no longer hash to source_sha256)"},

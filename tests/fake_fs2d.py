@@ -203,27 +203,6 @@ class FakeFs2d:
         S[lo:hi] = V[lo:hi]
         self.src_params[src] = (dt, dx)
 
-    def fs2d_pressure_source_vmax(self, src, vc, d, dt, dx, vmax, reset, stream) -> None:
-        """model: the plain pre-pass + max |v|^2 (fp32 x*x + y*y, NaNs ignored) over the rows the real kernel reads"""
-        self.fs2d_pressure_source(src, vc, d, dt, dx, stream)
-        VM = self.a(vmax).view(np.uint32)
-        if reset:
-            VM[0] = 0
-        if d.r0 == d.r1:
-            return
-        V = self.a(vc, d, 2)
-        lo, hi = max(d.r0 - 1, d.clo), min(d.r1 + 1, d.chi + 1)
-        with np.errstate(all="ignore"):
-            sq = (V[lo:hi, :, 0] * V[lo:hi, :, 0] + V[lo:hi, :, 1] * V[lo:hi, :, 1]).astype(np.float32)
-        m = np.nanmax(sq) if np.isfinite(sq).any() or np.isinf(sq).any() else np.float32(0.0)
-        if not np.isnan(m):
-            VM[0] = max(int(VM[0]), int(np.float32(m).view(np.uint32)))
-
-    def fs2d_limit_if(self, v, d, limit, vmax, stream) -> None:
-        m = self.a(vmax).view(np.uint32)[:1].view(np.float32)[0]
-        if np.sqrt(np.float32(m)) > np.float32(limit):
-            self.fs2d_limit(v, d, limit, stream)
-
     def _sweep_window(self, pn_w, pc_w, src_w, mask_w, src_ptr, Y) -> None:
         dt, dx = self.src_params[src_ptr]
         orc.lib().orc_jacobi_sweep(_p(pn_w), _p(self._c(pc_w)), _p(self._c(src_w)), _p(self._c(mask_w)), _i(pn_w.shape[0]), _i(Y),

@@ -117,12 +117,7 @@ def main() -> None:
         from fs import _lib as _l
 
         k, v = item.split("=")
-        if k == "limitskip":
-            from fs.pressure_updater import PressureUpdater
-
-            PressureUpdater.limit_skip = bool(int(v))
-        else:
-            _l.call("fs2d_set_tuning", int(k), int(v))
+        _l.call("fs2d_set_tuning", int(k), int(v))
     n_ok = 0
     for num, X, Y, scheme, vc, pkw, steps, halo in cases:
         res = Y

@@ -164,27 +164,6 @@ def test_pressure_entry_points_against_the_window_model(libs, seed):
         untouched = np.ones(X, bool)
         untouched[d.r0:d.r1] = False
         assert_bitexact("rows outside the window", res[0][untouched], pn[untouched])
-    # experimental pair: the pre-pass that records max |v|^2, and the limiter that consults it
-    for vscale in (1.0, 30.0):
-        res = []
-        for impl in ("emu", "fake"):
-            vv = v * np.float32(vscale)
-            vv[d.r0 if d.r0 < d.r1 else 0, 3, 0] = np.nan
-            ts = {k: torch.from_numpy(a.copy()) for k, a in dict(src=np.zeros((X, Y, 2), np.float32), vc=vv, vmax=np.full(1, 77, np.int32)).items()}
-            q = {k: c.fake.ptr(t) for k, t in ts.items()}
-            for name, args in (("fs2d_pressure_source_vmax", (q["src"], q["vc"], d, dt, dx, q["vmax"], 1, None)),
-                               ("fs2d_limit_if", (q["vc"], d, 10.0, q["vmax"], None))):
-                if impl == "emu":
-                    assert getattr(c.emu, name)(*args) == 0, c.emu.fs2d_last_error().decode()
-                else:
-                    c.fake.call(name, *args)
-            res.append((ts["vmax"].numpy().copy(), ts["vc"].numpy().copy()))
-        assert res[0][0][0] == res[1][0][0], f"max |v|^2 bits: kernel {res[0][0][0]:#x} vs model {res[1][0][0]:#x} (rows {d.r0}:{d.r1})"
-        assert_bitexact(f"limit_if vscale {vscale} rows {d.r0}:{d.r1}", res[0][1], res[1][1])
-        # and the conditional limiter equals the unconditional one whenever the recorded maximum covers the limited rows
-        plain = torch.from_numpy((v * np.float32(vscale)).copy()); plain[d.r0 if d.r0 < d.r1 else 0, 3, 0] = float("nan")
-        assert c.emu.fs2d_limit(c.fake.ptr(plain), d, 10.0, None) == 0
-        assert_bitexact("limit_if == limit", res[0][1], plain.numpy())
     for parity in (1, 0):
         res = []
         for impl in ("emu", "fake"):
@@ -199,4 +178,16 @@ def test_pressure_entry_points_against_the_window_model(libs, seed):
                     c.fake.call(name, *args)
             res.append(ts["pn"].numpy())
         assert_bitexact(f"rbsor parity {parity} {X}x{Y} rows {d.r0}:{d.r1} gi0 {d.gi0}", res[0], res[1])
+    res = []     # both colours in one kernel (fs2d_rbsor_iteration) vs the model's two passes
+    for impl in ("emu", "fake"):
+        ts = {k: torch.from_numpy(a.copy()) for k, a in dict(pn=pn, pc=p, src=np.zeros((X, Y, 2), np.float32), vc=v, mask=m).items()}
+        q = {k: c.fake.ptr(t) for k, t in ts.items()}
+        for name, args in (("fs2d_pressure_source", (q["src"], q["vc"], d, dt, dx, None)),
+                           ("fs2d_rbsor_iteration", (q["pn"], q["pc"], q["src"], q["mask"], d, 1.3, 1.0 - 1.3, None))):
+            if impl == "emu":
+                assert getattr(c.emu, name)(*args) == 0, c.emu.fs2d_last_error().decode()
+            else:
+                c.fake.call(name, *args)
+        res.append(ts["pn"].numpy())
+    assert_bitexact(f"rbsor iteration {X}x{Y} rows {d.r0}:{d.r1} gi0 {d.gi0}", res[0], res[1])
     del wide

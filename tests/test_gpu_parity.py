@@ -776,7 +776,7 @@ def test_division_special_cases_match_the_oracle(env):
 
 
 # ------------------------------------------------------------------------------------------------
-# 11. the two tails of fs2d_jacobi_update; tile lists; the limiter skip
+# 11. the two tails of fs2d_jacobi_update; tile lists
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("num,X,Y,n_iter", [(2, 256, 128, 80), (5, 384, 192, 21), (1, 128, 64, 7), (3, 320, 160, 13), (2, 96, 48, 3),
                                             (4, 200, 96, 4), (1, 288, 352, 10)])
@@ -823,40 +823,6 @@ def test_tile_list_classes(env, num, X, Y):
             r0, c0 = (t // tiles_j) * TI - HI, (t % tiles_j) * TJ - HJ
             assert r0 > 0 and c0 > 0 and r0 + rows.value < X and c0 + cols.value < Y
             assert (pcode[r0:r0 + rows.value, c0:c0 + cols.value] == 0).all()
-
-
-def _limit_skip_check(scale):
-    """PressureUpdater.limit_skip: the source pre-pass records max |v|^2 and limit_field skips its pass when nothing can exceed
-    the limit.  scale 0.5: the limiter never fires (skipped every step); 40: it fires (many cells beyond |v| = 10)."""
-    from fs.boundary_condition import build_scene
-    from oracle import oracle as orc
-
-    X, Y = 96, 48
-    dt, dx, re, vc, pressure = 0.05 / Y, 1.0 / Y, 1e4, 5.0, ("jacobi", 3)
-    const, mask = build_scene(2, X, Y)
-    for scheme in ("cip", "upwind"):
-        s = make_fs(mask, const, dt, dx, re, scheme, vc, pressure)
-        s.pressure_updater.limit_skip = True
-        ref = orc.OracleSolver(mask, const, dt, dx, re, scheme, vc, pressure)
-        rng = np.random.default_rng(9)
-        init = {k: (rng.uniform(-1, 1, a.shape) * (scale if k.startswith("v_") else 0.3)).astype(np.float32) for k, a in ref.state().items()}
-        init["v_cur"][5, 7] = np.nan                     # a NaN cell must neither be limited nor hide the others
-        ref.load_state(init)
-        load_fs_state(s, init)
-        for n in range(3):
-            s.update(); ref.update()
-            got = fs_state(s)
-            for k, a in ref.state().items():
-                assert_bitexact(f"{scheme} scale {scale} step {n} {k}", got[k].to_numpy(), a)
-        m = float(s.pressure_updater._vmax.view(torch.float32)[0])
-        assert (np.sqrt(np.float32(m)) > 10.0) == (scale > 1.0) or scheme == "upwind"   # the recorded maximum decides
-
-
-@pytest.mark.parametrize("scale", [0.5, 40.0])
-def test_limit_skip_trajectory_vs_oracle(env, scale):
-    _limit_skip_check(scale)
-
-
 
 
 # ------------------------------------------------------------------------------------------------

@@ -260,12 +260,7 @@ def _strip_worker(rank: int, world: int, port: int, q, tuning=()) -> None:
     orc.set_threads(1)
     fake = FakeFs2d(_lib.load()).install_plain()
     for key, value in tuning:
-        if key == "limit_skip":
-            from fs.pressure_updater import PressureUpdater
-
-            PressureUpdater.limit_skip = bool(value)
-        else:
-            _lib.call("fs2d_set_tuning", key, value)
+        _lib.call("fs2d_set_tuning", key, value)
     failures, info = [], []
     for num, X, Y, scheme, vc, pkw, dye, steps, halo in STRIP_CASES:
         part = Partition(X, rank, world, halo)
@@ -320,18 +315,17 @@ def test_strips_equal_single_domain_under_gloo(world):
     assert info[4][3] > 0 and info[4][4] > 0                        # the 13-iteration case ran fused passes on the strips, the last one emitting
 
 
-def test_strips_with_the_two_literal_tail_and_limit_skip_under_gloo():
+def test_strips_with_the_two_literal_tail_under_gloo():
     """fs2d_set_tuning(4, 0) on strips: the schedule ends with two literal iterations instead of the default {emitting fused
     pass, one literal iteration}; every physical buffer -- the wall cells of both pressure buffers included -- still equals
-    the reference's orchestration.  Also with PressureUpdater.limit_skip: the three source pre-pass windows of a strip
-    accumulate one maximum, consulted by the limiter."""
+    the reference's orchestration."""
     from test_distributed import free_port
 
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = free_port()
-    procs = [ctx.Process(target=_strip_worker, args=(r, world, port, q, ((4, 0), ("limit_skip", 1)))) for r in range(world)]
+    procs = [ctx.Process(target=_strip_worker, args=(r, world, port, q, ((4, 0),))) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=600) for _ in range(world))

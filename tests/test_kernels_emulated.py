@@ -131,7 +131,7 @@ def test_emu_dye_simulator_vs_oracle(env, num, res, scheme):
     G.test_dye_simulator_vs_oracle(env, num, res, scheme)
 
 
-# ---- the two tails of the update; the limiter skip ------------------------------------------------------------------------
+# ---- the two tails of the update ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("num,X,Y,n_iter", [(1, 128, 64, 7), (3, 320, 160, 13), (2, 96, 48, 3), (4, 200, 96, 4), (1, 288, 352, 6)])
 def test_emu_two_literal_tail_equals_literal_update(env, num, X, Y, n_iter):
     G.test_two_literal_tail_equals_literal_update(env, num, X, Y, n_iter)
@@ -164,11 +164,6 @@ def test_emu_fused_pass_fuzz(env, seed):
         for _ in range(6):
             mask[int(rng.integers(3, X - 3)), int(rng.integers(3, Y - 3))] = int(rng.integers(2, 4))
     G._fused_pass_check(1, X, Y, mask_override=mask, t_list=(1, 3, 8), need=0, listed=seed % 2 == 0)
-
-
-@pytest.mark.parametrize("scale", [0.5, 40.0])
-def test_emu_limit_skip_trajectory_vs_oracle(env, scale):
-    G._limit_skip_check(scale)
 
 
 # ---- adversarial schedules ---------------------------------------------------------------------------------------------------
