@@ -39,10 +39,6 @@ bool is_pow2(float x);
 int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t *pcode, const fs2d_dom &d, int T,
                cudaStream_t s, int skip_from, int skip_n, bool emit, const int *order, int n_order);
 extern int g_tail_emit;      // fs2d_set_tuning(4, v), see fs2d_pressure.cu
-// fs2d_set_tuning(6, n): SMs the PERSISTENT kernels (fused Jacobi, TMA-streamed stencils) leave unoccupied.  A persistent
-// grid fills every SM for the whole launch, so a kernel of another stream -- the NCCL SendRecv of a row-strip halo exchange
-// that is supposed to overlap it -- only gets an SM when the first CTA exits, i.e. after the launch.  Multi-rank hosts set a few.
-extern int g_reserve_sms;
 // TMA-fed streaming versions of the stencil kernels (fs2d_stream.cu); g_stream: fs2d_set_tuning(2, 0/1)
 extern int g_stream, g_stream_cfg;
 bool stream_ok(const fs2d_dom &d, const void *const *ptrs, int n);

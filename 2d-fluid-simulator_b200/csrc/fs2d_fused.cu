@@ -809,15 +809,13 @@ int fused_pass(const float *p_in, float *p_out, const float *src, const uint8_t 
         set_error("bad argument: tile list of %d entries for a pass of %d tiles", n_order, n_tiles);
         return FS2D_E_BADARG;
     }
-    const int sms = n_sm - g_reserve_sms > 0 ? n_sm - g_reserve_sms : 1;
-    const int grid = n_order < sms ? n_order : sms;
+    const int grid = n_order < n_sm ? n_order : n_sm;
     ++g_launches;
     if (emit) k_jacobi_fused_emit<<<grid, dim3(32, V_WARPS, 1), V_SMEM, s>>>(mp, ms, mc, p_out, order, n_order, n_order_dev, d, g, const_cast<float *>(p_in));
     else k_jacobi_fused<<<grid, dim3(32, V_WARPS, 1), V_SMEM, s>>>(mp, ms, mc, p_out, order, n_order, n_order_dev, d, g);
     return FS2D_OK;
 }
 
-int g_reserve_sms = 0;   // fs2d_set_tuning(6, n), see fs2d_common.cuh
 int g_tail_emit = 1;   // fs2d_set_tuning(4, v): 0 = end fs2d_jacobi_update with two literal iterations instead of {emitting pass, one}
 
 }  // namespace fs2d

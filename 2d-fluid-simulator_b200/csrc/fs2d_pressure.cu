@@ -315,7 +315,6 @@ int fs2d_set_tuning(int key, int value) {
     if (key == 2 && value >= 0 && value <= 2) { fs2d::g_stream = value; return FS2D_OK; }
     if (key == 3 && value >= 0 && value <= 3) { fs2d::g_stream_cfg = value; return FS2D_OK; }
     if (key == 4 && (value == 0 || value == 1)) { fs2d::g_tail_emit = value; return FS2D_OK; }
-    if (key == 6 && value >= 0 && value <= 64) { fs2d::g_reserve_sms = value; return FS2D_OK; }
     set_error("unknown tuning key %d / value %d", key, value);
     return FS2D_E_BADARG;
 }

@@ -296,8 +296,7 @@ static int launch_stream_cfg(const Op &op, const float *const *fields, const uin
     StreamGeom g;
     g.tiles_j = (d.Y + ST_TC - 1) / ST_TC;
     g.n_tiles = g.tiles_j * ((d.r1 - d.r0 + ST_TR - 1) / ST_TR);
-    const int sms = n_sm - g_reserve_sms > 0 ? n_sm - g_reserve_sms : 1;   // (fs2d_set_tuning(6, n): room for a concurrent NCCL kernel)
-    const int grid = g.n_tiles < MIN_CTAS * sms ? g.n_tiles : MIN_CTAS * sms;
+    const int grid = g.n_tiles < MIN_CTAS * n_sm ? g.n_tiles : MIN_CTAS * n_sm;
     ++g_launches;
     k_stream<Op, ST_STAGES, MIN_CTAS, ST_THREADS><<<grid, ST_THREADS, SMEM, s>>>(maps, op, d, g);
     return FS2D_OK;

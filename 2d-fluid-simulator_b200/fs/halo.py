@@ -63,22 +63,11 @@ class HaloExchanger:
         self.finish(self.start(field, width))
 
 
-#: SMs the persistent kernels leave free on a rank of a multi-rank run, so that NCCL's SendRecv kernel runs beside the kernel
-#: that hides it instead of after it (fs2d_set_tuning(6, n); measured on 2 x B200).  FS2D_RESERVE_SMS overrides.
-RESERVE_SMS = 4
-
-
 def exchanger_for(bc) -> HaloExchanger:
     """The (single) exchanger of a BoundaryCondition; kept on the object so its lifetime follows the partition."""
     hx = getattr(bc, "_halo_exchanger", None)
     if hx is None:
         hx = bc._halo_exchanger = HaloExchanger(bc.partition)
-        if bc.partition.world > 1:
-            import os
-
-            from fs import _lib
-
-            _lib.call("fs2d_set_tuning", 6, int(os.environ.get("FS2D_RESERVE_SMS", RESERVE_SMS)))
     return hx
 
 

@@ -384,7 +384,7 @@ def run_ours(a: argparse.Namespace) -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
     assert lib.fs2d_device_ok(), lib.fs2d_last_error().decode()
-    # experimental kernel selection for A/B runs (default: none): FS2D_TUNING="4=0,6=4" -> fs2d_set_tuning(key, value) pairs;
+    # experimental kernel selection for A/B runs (default: none): FS2D_TUNING="4=0,2=2" -> fs2d_set_tuning(key, value) pairs;
     # recorded in the JSON line as "tuning"
     tuning = {}
     for item in filter(None, os.environ.get("FS2D_TUNING", "").split(",")):

@@ -77,9 +77,6 @@ unsigned long long fs2d_launch_count(void);
  * key 3 = streaming-kernel shape {stages x CTAs/SM x threads}: {0: 3x2x256, 1: 2x3x256 (default), 2: 3x2x512, 3: 2x2x512}.
  * key 4 = tail of fs2d_jacobi_update {1 (default): the last fused pass also emits the BC values of its penultimate state, so
  *         ONE literal iteration ends the update; 0: two literal iterations}.
- * key 6 = SMs the persistent kernels (fused Jacobi, TMA-streamed stencils) leave free {0 (default) .. 64}: a multi-rank host
- *         sets a few so that the NCCL SendRecv of a halo exchange can run BESIDE the kernel it is meant to overlap (a persistent
- *         grid otherwise holds every SM until its first CTA exits).
  * Unknown keys / values return FS2D_E_BADARG and change nothing. */
 int fs2d_set_tuning(int key, int value);
 /* 1 if the library was built for sm_100a and a device of compute capability 10.x is current */
