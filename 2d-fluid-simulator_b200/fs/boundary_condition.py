@@ -27,6 +27,8 @@ class BoundaryCondition:
     #: fused-pass validity analysis look at most 2 * 12 + 2 rows past the owned rows (a dependency cone grows by at most two
     #: rows per iteration, 12 iterations per pass at most)
     STRIP_MARGIN = 32
+    #: halo rows on which the in-place boundary conditions are applied (and v is exchanged for them)
+    BC_HALO = 9
 
     def __init__(self, bc_const: npt.NDArray, bc_mask: npt.NDArray, device=None, partition=None, row_offset: int | None = None) -> None:
         """row_offset (not in the reference; needs `partition`): the arrays hold only the global rows [row_offset, row_offset +
@@ -83,11 +85,14 @@ class BoundaryCondition:
         self._fused_ok: dict[int, bool] = {}
         self._fused_orders: dict[tuple, tuple] = {}
         self._bc_const = self._upload_rows(bc_const, lo, hi, w0, w1, A0)
-        # BC targets: owned rows plus the halo rows whose sources are inside the window
-        tl, th = max(lo, g0 - max(self.halo - 2, 0)), min(hi, g1 + max(self.halo - 2, 0))
+        # BC targets: owned rows plus the halo rows whose sources are inside the window -- of the first BC_HALO halo rows: the
+        # stencil kernels read the post-BC fields at most a few rows beyond the owned ones, however deep the halo is (deep
+        # halos only serve the fused Jacobi passes, fs/halo.py)
+        self.bc_halo = min(self.halo, self.BC_HALO)
+        tl, th = max(lo, g0 - max(self.bc_halo - 2, 0)), min(hi, g1 + max(self.bc_halo - 2, 0))
         self._vel_table = _bc_tables.velocity_table(gmask, tl - A0, th - A0, w0 - A0, w1 - A0)
-        self._p_table = _bc_tables.pressure_table(pcode, max(lo, g0 - max(self.halo - 1, 0)) - A0,
-                                                  min(hi, g1 + max(self.halo - 1, 0)) - A0, w0 - A0, w1 - A0)
+        self._p_table = _bc_tables.pressure_table(pcode, max(lo, g0 - max(self.bc_halo - 1, 0)) - A0,
+                                                  min(hi, g1 + max(self.bc_halo - 1, 0)) - A0, w0 - A0, w1 - A0)
         stale = _bc_tables.exposed_stale_cells(pcode)
         if stale.numel():
             si, sj = stale // Y, stale % Y
@@ -103,7 +108,7 @@ class BoundaryCondition:
     def strip_rows(cls, partition) -> tuple[int, int]:
         """global rows [a, b) of the scene a rank must hold to build its BoundaryCondition with `row_offset=a`"""
         g0, g1 = partition.owned()
-        m = max(cls.STRIP_MARGIN, partition.halo + 4)
+        m = max(cls.STRIP_MARGIN, partition.halo + 28)   # deep halos: windows extended by up to halo - 1 rows, cones 2 * 12 + 2 beyond
         return max(0, g0 - m), min(partition.x_global, g1 + m)
 
     def _upload_rows(self, host: npt.NDArray, lo: int, hi: int, w0: int, w1: int, A0: int, fill=0) -> torch.Tensor:
@@ -150,20 +155,26 @@ class BoundaryCondition:
                 torch.from_numpy(np.ascontiguousarray(bc_mask, dtype=np.uint8)).to(dev))
 
     # -- helpers for the other operators -----------------------------------------------------
-    def fused_ok(self, T: int) -> bool:
-        """May fs2d_jacobi_fused run T iterations per pass on this mask?  (static analysis, cached)"""
+    def fused_ok(self, T: int, ext: int = 0) -> bool:
+        """May fs2d_jacobi_fused run T iterations per pass on this mask?  (static analysis, cached)
+        ext (row strips): the pass updates the owned rows extended by `ext` rows on each side that has a neighbour -- a
+        strip that exchanges the halos of several passes at once recomputes the rows the later passes of the group read
+        (fs/halo.py: deep halos); its tiling is anchored at the extended window, so it is validated separately."""
         import ctypes
 
         rows, cols, hr, hc, tmax = (ctypes.c_int() for _ in range(5))
         _lib.call("fs2d_fused_tile", T, ctypes.byref(rows), ctypes.byref(cols), ctypes.byref(hr), ctypes.byref(hc),
                   ctypes.byref(tmax))
-        key = (T, rows.value, cols.value)   # the tile depends on the kernel variant (fs2d_set_tuning)
+        key = (T, rows.value, cols.value, ext)   # the tile depends on the kernel (fs2d_fused_tile)
         if key not in self._fused_ok:
-            g0, g1 = (g - self._row_offset for g in self.partition.owned())      # array coordinates
+            X = self._global_resolution[0]
+            g0, g1 = self.partition.owned()
+            e0, e1 = max(g0 - ext, 0), min(g1 + ext, X)            # the extended window, clipped to the grid
+            below = T if e1 < X else None                           # rows beyond e1 + T hold stale data (there is a neighbour below)
             ok = (1 <= T <= tmax.value and self._global_resolution[1] % 16 == 0 and self._p_table["feed"]["n"] == 0
-                  and (self.partition.world == 1 or self.halo >= T + 1)
-                  and _bc_tables.fused_reach_ok(self._pcode_global, T, rows.value, cols.value, hr.value, hc.value, g0, g1,
-                                                fresh_below=T if self.partition.has_upper else None))
+                  and (self.partition.world == 1 or self.halo >= T + ext + 1)
+                  and _bc_tables.fused_reach_ok(self._pcode_global, T, rows.value, cols.value, hr.value, hc.value,
+                                                e0 - self._row_offset, e1 - self._row_offset, fresh_below=below))
             self._fused_ok[key] = bool(ok)
         return self._fused_ok[key]
 

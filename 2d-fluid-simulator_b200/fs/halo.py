@@ -157,7 +157,8 @@ def jacobi_update_distributed(jac, p: DoubleBuffer, v_current: Field) -> None:
     bc = jac._bc
     hx = exchanger_for(bc)
     plan = jac.plan(p)
-    reach = max([t for t in plan if t > 0], default=0)
+    groups = jacobi_groups(jac, p, plan)
+    reach = max([sum(t for _, t in g) for g in groups], default=0)   # rows beyond the owned ones on which a pass of the update runs
     # source terms also on the halo rows a pass reads; the rows that need no halo row of v run during the exchange
     d, ext = bc.dom, _extended(bc, reach)
     if d.r1 - d.r0 >= 16:
@@ -169,29 +170,91 @@ def jacobi_update_distributed(jac, p: DoubleBuffer, v_current: Field) -> None:
     else:
         hx.exchange(v_current, min(bc.halo, reach + 1))
         src = jac._source(v_current, dom=ext)
-    # experimental tail (fs2d_set_tuning(4, 1)): the schedule then ends {fused pass, ONE literal iteration} and that pass emits
-    # the BC values of its penultimate state (the default schedule always ends with two literal iterations)
+    # the schedule ends {fused pass that emits the BC values of its penultimate state, ONE literal iteration} (or, with
+    # fs2d_set_tuning(4, 0), two literal iterations)
     tail_at = len(plan) - 2 if len(plan) >= 2 and plan[-2] > 0 else -1
-    for k, t in enumerate(plan):
-        emit = k == tail_at
-        if t > 0:
-            # Overlap: the pass reads the fresh halo rows only in its first and last TILE ROW, so the tile rows in
-            # between run while the SendRecv is in flight.  The interior window starts at a multiple of the tile height
-            # from r0, so both launches use exactly the tiles of a single launch (the validated tiling, fused_reach_ok).
-            mid, m = _pass_windows(bc, t)
-            if mid is None:
-                hx.exchange(p.current, t)
-                jac._fused(p.next, p.current, src, t, emit=emit)
-            else:
-                reqs = hx.start(p.current, t)
-                jac._fused(p.next, p.current, src, t, dom=mid, emit=emit)              # tile rows [1, m): owned rows only
-                hx.finish(reqs)
-                jac._fused(p.next, p.current, src, t, skip=(1, m - 1), emit=emit)      # tile rows {0} U [m, k) in one launch
-        else:
+    for group in groups:
+        k0, t0 = group[0]
+        if t0 == 0:      # literal iteration
             hx.exchange(p.current, 2)
             bc.set_pressure_boundary_condition(p.current)       # owned rows and the first halo row
             jac._sweep(p.next, p.current, src, inline_bc=False)
-        p.swap()
+            p.swap()
+        elif len(group) == 1:
+            # Overlap: the pass reads the fresh halo rows only in its first and last TILE ROW, so the tile rows in
+            # between run while the SendRecv is in flight.  The interior window starts at a multiple of the tile height
+            # from r0, so both launches use exactly the tiles of a single launch (the validated tiling, fused_reach_ok).
+            emit = k0 == tail_at
+            mid, m = _pass_windows(bc, t0)
+            if mid is None:
+                hx.exchange(p.current, t0)
+                jac._fused(p.next, p.current, src, t0, emit=emit)
+            else:
+                reqs = hx.start(p.current, t0)
+                jac._fused(p.next, p.current, src, t0, dom=mid, emit=emit)             # tile rows [1, m): owned rows only
+                hx.finish(reqs)
+                jac._fused(p.next, p.current, src, t0, skip=(1, m - 1), emit=emit)     # tile rows {0} U [m, k) in one launch
+            p.swap()
+        else:
+            # Deep halo: ONE exchange for the whole group of passes.  Pass i recomputes, beyond its owned rows, the rows the
+            # later passes of the group read (sum of their sizes: a few dozen rows of 8192), so none of them needs an
+            # exchange or a split launch.  Both buffers travel: the passes ping-pong between them and read the never-written
+            # wall cells of either in rows that only an exchange fills.
+            total = sum(t for _, t in group)
+            hx.finish(hx.start([(p.current, total), (p.next, total)]))
+            ext = total
+            for k, t in group:
+                ext -= t
+                jac._fused(p.next, p.current, src, t, dom=_extended(bc, ext) if ext else None, emit=k == tail_at)
+                p.swap()
+
+
+def jacobi_groups(jac, p: DoubleBuffer, plan: list[int]) -> list[list[tuple[int, int]]]:
+    """The plan's entries grouped into exchanges: [(index, size), ...] per group.  Consecutive fused passes share ONE halo
+    exchange as long as the sum of their sizes fits the halo (halo >= sum + 1) and every pass is valid on its extended
+    window on EVERY rank (BoundaryCondition.fused_ok(T, ext); agreed once per plan with a MIN all-reduce, setup time)."""
+    bc = jac._bc
+    key = (tuple(plan), bc.halo)
+    cache = jac.__dict__.setdefault("_group_cache", {})
+    if key in cache:
+        return cache[key]
+
+    def build(max_group: int) -> list[list[tuple[int, int]]]:
+        groups, cur = [], []
+        for k, t in enumerate(plan):
+            if t == 0:
+                if cur:
+                    groups.append(cur)
+                    cur = []
+                groups.append([(k, 0)])
+            elif cur and len(cur) < max_group and sum(x for _, x in cur) + t <= bc.halo - 1:
+                cur.append((k, t))
+            else:
+                if cur:
+                    groups.append(cur)
+                cur = [(k, t)]
+        if cur:
+            groups.append(cur)
+        return groups
+
+    groups = build(MAX_PASSES_PER_EXCHANGE)
+    ok = True
+    for g in groups:
+        ext = sum(t for _, t in g)
+        for _, t in g:
+            ext -= t
+            if len(g) > 1 and t > 0 and not bc.fused_ok(t, ext):
+                ok = False
+    if bc.partition.world > 1 and dist.is_initialized():
+        flag = torch.tensor([int(ok)], dtype=torch.int32, device=p.current.tensor.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = bool(int(flag.item()))
+    cache[key] = groups if ok else build(1)
+    return cache[key]
+
+
+#: fused passes that may share one halo exchange (deep halo); 1 = one exchange per pass (round 1)
+MAX_PASSES_PER_EXCHANGE = 4
 
 
 def rbsor_update_distributed(sor, p: DoubleBuffer, v_current: Field) -> None:
@@ -212,9 +275,9 @@ def rbsor_update_distributed(sor, p: DoubleBuffer, v_current: Field) -> None:
 
 def _velocity_bc(bc, hx: HaloExchanger, v: Field, reach: int) -> None:
     """set_velocity_boundary_condition on a strip; afterwards v is post-BC on the owned rows +-reach."""
-    hx.exchange(v, bc.halo)                       # sources lie up to 2 rows away from a target
-    bc.set_velocity_boundary_condition(v)         # targets: owned rows +- (halo - 2)
-    if bc.halo - 2 < reach:
+    hx.exchange(v, bc.bc_halo)                    # sources lie up to 2 rows away from a target
+    bc.set_velocity_boundary_condition(v)         # targets: owned rows +- (bc_halo - 2)
+    if bc.bc_halo - 2 < reach:
         hx.exchange(v, reach)
 
 

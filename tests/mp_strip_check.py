@@ -36,18 +36,21 @@ CASES = [
     (5, 384, 192, "cip", 5.0, dict(pressure="jacobi", n_iter=21), 3, 6),       # odd count, passes of <= 5
     (3, 640, 320, "upwind", None, dict(pressure="jacobi", n_iter=30), 2, 9),
     (2, 640, 64, "cip", 5.0, dict(pressure="jacobi", n_iter=13), 2, 9),       # tall narrow strips: fused passes split into interior + edge launches
+    (2, 640, 64, "cip", 5.0, dict(pressure="jacobi", n_iter=30), 2, 20),      # deep halo: several fused passes per exchange
+    (5, 576, 64, "cip", 5.0, dict(pressure="jacobi", n_iter=23), 2, 24),      # the same with an odd count on bc5
     ("rand1", 192, 64, "cip", 5.0, dict(pressure="jacobi", n_iter=11), 2, 5),  # thin walls on / next to the strip edges
     ("rand3", 192, 64, "kk", None, dict(pressure="jacobi", n_iter=14), 2, 6),
 ]
 # GPU runs only (seconds on a B200): the BASELINE scenes with their own sweep counts, fused passes of 8 across every strip edge
 GPU_CASES = [
     (2, 8192, 2048, "cip", 5.0, dict(pressure="jacobi", n_iter=80), 2, 9),     # bc2, 80 sweeps (configs 2 / 4)
+    (2, 8192, 2048, "cip", 5.0, dict(pressure="jacobi", n_iter=80), 2, 33),    # the same with deep halos (4 passes per exchange): the bench's setting
     (5, 4096, 2048, "cip", 5.0, dict(pressure="jacobi", n_iter=200), 2, 9),    # bc5, 200 sweeps (config 5 at res 2048)
     (3, 4096, 2048, "cip", 10.0, dict(pressure="jacobi", n_iter=100), 1, 9),   # bc3, vc=10, 100 sweeps (config 3 at res 2048)
 ]
 # FS2D_STRIP_BIG=1: BASELINE config 5 itself (bc5, res=16384: 32768 x 16384 cells, 200 sweeps), quiescent start, 2 steps; the
 # single-domain run needs 45 GB on rank 0's GPU
-BIG_CASES = [(5, 32768, 16384, "cip", 5.0, dict(pressure="jacobi", n_iter=200), 2, 9)]
+BIG_CASES = [(5, 32768, 16384, "cip", 5.0, dict(pressure="jacobi", n_iter=200), 2, 33)]
 SEED_MAX_CELLS = 1 << 25     # larger grids start quiescent (all fields zero) instead of from seeded random buffers
 
 

@@ -238,6 +238,7 @@ STRIP_CASES = [
     (5, 96, 32, "kk", 5.0, dict(pressure="rbsor", n_iter=2), False, 3, 2),
     (1, 96, 32, "upwind", None, dict(pressure="jacobi", n_iter=3), False, 3, 4),
     (2, 640, 64, "cip", 5.0, dict(pressure="jacobi", n_iter=13), False, 2, 9),     # fused passes across the strip edges, overlap windows
+    (2, 640, 64, "cip", 5.0, dict(pressure="jacobi", n_iter=30), False, 2, 20),    # deep halo: several fused passes share one exchange
     (1, 96, 32, "cip", 5.0, dict(pressure="rbsor", n_iter=2), True, 2, 2),         # dye (CIP) on strips
     (4, 96, 32, "upwind", 5.0, dict(pressure="jacobi", n_iter=2), True, 2, 2),     # dye (upwind) on strips
 ] + [(f"rand{seed}", 60, 48, scheme, vc, pkw, False, 2, halo) for seed in range(4) for scheme, vc, pkw, halo in (
