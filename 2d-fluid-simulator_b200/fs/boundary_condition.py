@@ -29,6 +29,8 @@ class BoundaryCondition:
     STRIP_MARGIN = 32
     #: halo rows on which the in-place boundary conditions are applied (and v is exchanged for them)
     BC_HALO = 9
+    #: scenes with fewer cells than this build their tables on the host
+    HOST_TABLES_BELOW = 1 << 21
 
     def __init__(self, bc_const: npt.NDArray, bc_mask: npt.NDArray, device=None, partition=None, row_offset: int | None = None) -> None:
         """row_offset (not in the reference; needs `partition`): the arrays hold only the global rows [row_offset, row_offset +
@@ -69,15 +71,19 @@ class BoundaryCondition:
         self._row_offset = A0
 
         # from here on rows are indexed in ARRAY coordinates (global row - A0); array edges that are not grid edges lie in
-        # the margin, where the clamped neighbour reads of the table builders produce values nobody uses
-        gmask = torch.from_numpy(bc_mask).to(self.device)
+        # the margin, where the clamped neighbour reads of the table builders produce values nobody uses.
+        # The tables are torch code (fs/_bc_tables.py): hundreds of small element-wise kernels.  Small grids build them on
+        # the HOST and upload the results (a 128 x 64 scene issued > 900 library-less launches before its first fs2d kernel);
+        # large grids build them on the device (seconds instead of minutes at 8192^2).
+        build_dev = self.device if XA * Y >= self.HOST_TABLES_BELOW else torch.device("cpu")
+        gmask = torch.from_numpy(bc_mask).to(build_dev)
         pcode = _bc_tables.pressure_codes(gmask)
         lo, hi = max(w0, 0), min(w1, X)      # part of the window that exists globally
 
         def local(t_array: torch.Tensor, fill=0) -> torch.Tensor:
-            out = torch.full((w1 - w0,) + tuple(t_array.shape[1:]), fill, dtype=t_array.dtype, device=self.device)
+            out = torch.full((w1 - w0,) + tuple(t_array.shape[1:]), fill, dtype=t_array.dtype, device=build_dev)
             out[lo - w0:hi - w0] = t_array[lo - A0:hi - A0]
-            return out.contiguous()
+            return out.contiguous().to(self.device)
 
         self._bc_mask = local(gmask, WALL)
         self._pcode = local(_bc_tables.pack_pcode(pcode), _bc_tables.PC_W_NONE)
@@ -90,15 +96,19 @@ class BoundaryCondition:
         # halos only serve the fused Jacobi passes, fs/halo.py)
         self.bc_halo = min(self.halo, self.BC_HALO)
         tl, th = max(lo, g0 - max(self.bc_halo - 2, 0)), min(hi, g1 + max(self.bc_halo - 2, 0))
-        self._vel_table = _bc_tables.velocity_table(gmask, tl - A0, th - A0, w0 - A0, w1 - A0)
-        self._p_table = _bc_tables.pressure_table(pcode, max(lo, g0 - max(self.bc_halo - 1, 0)) - A0,
-                                                  min(hi, g1 + max(self.bc_halo - 1, 0)) - A0, w0 - A0, w1 - A0)
+        def to_dev(table: dict) -> dict:
+            return {k: (v.to(self.device) if isinstance(v, torch.Tensor) else to_dev(v) if isinstance(v, dict) else v)
+                    for k, v in table.items()}
+
+        self._vel_table = to_dev(_bc_tables.velocity_table(gmask, tl - A0, th - A0, w0 - A0, w1 - A0))
+        self._p_table = to_dev(_bc_tables.pressure_table(pcode, max(lo, g0 - max(self.bc_halo - 1, 0)) - A0,
+                                                         min(hi, g1 + max(self.bc_halo - 1, 0)) - A0, w0 - A0, w1 - A0))
         stale = _bc_tables.exposed_stale_cells(pcode)
         if stale.numel():
             si, sj = stale // Y, stale % Y
             keep = (si >= lo - A0) & (si < hi - A0)
             stale = (si[keep] - (w0 - A0)) * Y + sj[keep]
-        self._exposed_stale = stale
+        self._exposed_stale = stale.to(self.device)
         n = max(self._vel_table["n"], self._p_table["n"], 1)
         self._scratch = torch.empty(2 * n, dtype=torch.float32, device=self.device)
         self.dom = _lib.Dom(rows=w1 - w0, Y=Y, r0=g0 - w0, r1=g1 - w0, clo=lo - w0, chi=hi - 1 - w0, gi0=w0)
