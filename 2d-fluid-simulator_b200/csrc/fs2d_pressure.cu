@@ -346,7 +346,7 @@ int fs2d_jacobi_sweep(float *pn, const float *pc, const float *src, const uint8_
 // number of buffer flips (= number of entries) must have the parity of n_sweeps so that the two PHYSICAL
 // buffers end up exactly as in the reference.
 static int plan_jacobi(int n_sweeps, int fuse_mask, int *out, int cap, int tail_literal = 2) {
-    static const float pass_cost[13] = {0, 170, 179, 182, 202, 247, 277, 314, 360, 428, 470, 527, 567};   // r02, autonomous warps
+    static const float pass_cost[13] = {0, 166, 178, 184, 184, 223, 248, 283, 323, 379, 411, 463, 496};   // r02 (profiles/r02_fused_sweep_bench_v3.txt)
     const float lit_cost = 190.0f;
     const int n_lit = n_sweeps < tail_literal ? n_sweeps : tail_literal, n_f = n_sweeps - n_lit;
     int n = 0;

@@ -11,7 +11,8 @@ from fs.boundary_condition import BoundaryCondition, build_scene
 from fs.fluid_simulator import make_solver
 
 lib = _lib.load()
-for num, X, Y in ((2, 256, 128), (3, 200, 176)):
+# (1, 300, 480) has open-fluid tiles: the autonomous-warp path of the fused Jacobi kernel (per-warp TMA refills, progress counters)
+for num, X, Y in ((2, 256, 128), (3, 200, 176), (1, 300, 480)):
     const, mask = build_scene(num, X, Y)
     bc = BoundaryCondition(const, mask)
     s = make_solver(bc, 0.05 / Y, 1.0 / 128, 1e3, 5.0, "cip", pressure="jacobi", n_iter=12)
@@ -26,3 +27,11 @@ for num, X, Y in ((2, 256, 128), (3, 200, 176)):
     lib.fs2d_set_tuning(4, 1)
     torch.cuda.synchronize()
     print("ok", num, X, Y, float(s.p.current.tensor.abs().sum()))
+
+# the path main.py runs by default: RB-SOR (both colours in one kernel), dye, clamp
+from fs.fluid_simulator import DyeFluidSimulator
+sim = DyeFluidSimulator.create(2, 96, 0.05 / 96, 1.0 / 96, 1e4, 5.0, "cip")
+for _ in range(3):
+    sim.step()
+torch.cuda.synchronize()
+print("ok default path", float(sim.solver.p.current.tensor.abs().sum()))
