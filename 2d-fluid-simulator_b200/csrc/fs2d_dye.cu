@@ -7,9 +7,13 @@
 
 namespace fs2d {
 
-template <int C>
+// CL = true: clamp-to-edge like sample(); CL = false: the caller guarantees that the access lies inside the clamp window
+// (block_interior), so the neighbour is a plain offset -- the per-load min/max and 64-bit index arithmetic was a third of
+// the dye kernels' instructions
+template <int C, bool CL = true>
 __device__ __forceinline__ float ldc(const float *f, const fs2d_dom &d, int r, int j, int c) {
-    return __ldg(f + (size_t)C * IX(d, CR(d, r), CJ(d, j)) + c);
+    if (CL) return __ldg(f + (size_t)C * IX(d, CR(d, r), CJ(d, j)) + c);
+    return __ldg(f + (ptrdiff_t)C * ((ptrdiff_t)r * d.Y + j) + c);
 }
 
 // fs/boundary_condition.py:94-99  set_dye_boundary_condition: dye = bc_dye on inflow cells (sparse list)
@@ -88,47 +92,61 @@ __global__ void __launch_bounds__(TX *TY)
 }
 
 // fs/solver.py:378-383  _non_advection_phase_dye: dn = dc + diffusion(dc) * dt   (not-wall cells)
-template <bool P2, int C>
-__global__ void __launch_bounds__(TX *TY)
-    k_dye_nonadv(float *__restrict__ dn, const float *__restrict__ dc, const uint8_t *__restrict__ mask, fs2d_dom d,
-                 float dt, DivC<P2> ddx2, float re) {
+template <bool P2, int C, bool CL>
+__device__ __forceinline__ void b_dye_nonadv(float *__restrict__ dn, const float *__restrict__ dc, const uint8_t *__restrict__ mask,
+                                             const fs2d_dom &d, float dt, DivC<P2> ddx2, float re) {
     FS2D_CELL(d, r, j)
     const size_t idx = IX(d, r, j);
     if (mask[idx] == 1) return;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         const float cc = __ldg(dc + C * idx + c);
-        const float d2x = ddx2(ldc<C>(dc, d, r + 1, j, c) - 2.0f * cc + ldc<C>(dc, d, r - 1, j, c));
-        const float d2y = ddx2(ldc<C>(dc, d, r, j + 1, c) - 2.0f * cc + ldc<C>(dc, d, r, j - 1, c));
+        const float d2x = ddx2(ldc<C, CL>(dc, d, r + 1, j, c) - 2.0f * cc + ldc<C, CL>(dc, d, r - 1, j, c));
+        const float d2y = ddx2(ldc<C, CL>(dc, d, r, j + 1, c) - 2.0f * cc + ldc<C, CL>(dc, d, r, j - 1, c));
         dn[C * idx + c] = cc + fdiv_z(d2x + d2y, re) * dt;
     }
 }
-
-// fs/solver.py:242-261  _non_advection_phase_grad on C channels
 template <bool P2, int C>
 __global__ void __launch_bounds__(TX *TY)
-    k_nonadv_grad_n(float *__restrict__ fxn, float *__restrict__ fyn, const float *__restrict__ fxc,
-                    const float *__restrict__ fyc, const float *__restrict__ fc, const float *__restrict__ fn,
-                    const uint8_t *__restrict__ mask, fs2d_dom d, DivC<P2> d2dx) {
+    k_dye_nonadv(float *__restrict__ dn, const float *__restrict__ dc, const uint8_t *__restrict__ mask, fs2d_dom d,
+                 float dt, DivC<P2> ddx2, float re) {
+    if (block_interior(d, TY, 1)) b_dye_nonadv<P2, C, false>(dn, dc, mask, d, dt, ddx2, re);
+    else b_dye_nonadv<P2, C, true>(dn, dc, mask, d, dt, ddx2, re);
+}
+
+// fs/solver.py:242-261  _non_advection_phase_grad on C channels
+template <bool P2, int C, bool CL>
+__device__ __forceinline__ void b_nonadv_grad_n(float *__restrict__ fxn, float *__restrict__ fyn, const float *__restrict__ fxc,
+                                                const float *__restrict__ fyc, const float *__restrict__ fc,
+                                                const float *__restrict__ fn, const uint8_t *__restrict__ mask, const fs2d_dom &d,
+                                                DivC<P2> d2dx) {
     FS2D_CELL(d, r, j)
     const size_t idx = IX(d, r, j);
     if (mask[idx] == 1) return;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        const float gx = ldc<C>(fn, d, r + 1, j, c) - ldc<C>(fc, d, r + 1, j, c) - ldc<C>(fn, d, r - 1, j, c) + ldc<C>(fc, d, r - 1, j, c);
-        const float gy = ldc<C>(fn, d, r, j + 1, c) - ldc<C>(fc, d, r, j + 1, c) - ldc<C>(fn, d, r, j - 1, c) + ldc<C>(fc, d, r, j - 1, c);
+        const float gx = ldc<C, CL>(fn, d, r + 1, j, c) - ldc<C, CL>(fc, d, r + 1, j, c) - ldc<C, CL>(fn, d, r - 1, j, c) + ldc<C, CL>(fc, d, r - 1, j, c);
+        const float gy = ldc<C, CL>(fn, d, r, j + 1, c) - ldc<C, CL>(fc, d, r, j + 1, c) - ldc<C, CL>(fn, d, r, j - 1, c) + ldc<C, CL>(fc, d, r, j - 1, c);
         fxn[C * idx + c] = __ldg(fxc + C * idx + c) + d2dx(gx);
         fyn[C * idx + c] = __ldg(fyc + C * idx + c) + d2dx(gy);
     }
 }
-
-// fs/solver.py:267-332  _advection_phase/_cip_advect on C channels, advecting velocity v (float2)
 template <bool P2, int C>
 __global__ void __launch_bounds__(TX *TY)
-    k_cip_advect_n(float *__restrict__ fn, float *__restrict__ fxn, float *__restrict__ fyn,
-                   const float *__restrict__ fc, const float *__restrict__ fxc, const float *__restrict__ fyc,
-                   const float *__restrict__ v, const uint8_t *__restrict__ mask, fs2d_dom d, float dt, float dx,
-                   DivC<P2> ddx, float dx2, float dx3) {
+    k_nonadv_grad_n(float *__restrict__ fxn, float *__restrict__ fyn, const float *__restrict__ fxc,
+                    const float *__restrict__ fyc, const float *__restrict__ fc, const float *__restrict__ fn,
+                    const uint8_t *__restrict__ mask, fs2d_dom d, DivC<P2> d2dx) {
+    if (block_interior(d, TY, 1)) b_nonadv_grad_n<P2, C, false>(fxn, fyn, fxc, fyc, fc, fn, mask, d, d2dx);
+    else b_nonadv_grad_n<P2, C, true>(fxn, fyn, fxc, fyc, fc, fn, mask, d, d2dx);
+}
+
+// fs/solver.py:267-332  _advection_phase/_cip_advect on C channels, advecting velocity v (float2)
+template <bool P2, int C, bool CL>
+__device__ __forceinline__ void b_cip_advect_n(float *__restrict__ fn, float *__restrict__ fxn, float *__restrict__ fyn,
+                                               const float *__restrict__ fc, const float *__restrict__ fxc,
+                                               const float *__restrict__ fyc, const float *__restrict__ v,
+                                               const uint8_t *__restrict__ mask, const fs2d_dom &d, float dt, float dx,
+                                               DivC<P2> ddx, float dx2, float dx3) {
     FS2D_CELL(d, r, j)
     const size_t idx = IX(d, r, j);
     if (mask[idx] != 0) return;
@@ -137,13 +155,13 @@ __global__ void __launch_bounds__(TX *TY)
     const int r_m = r - (int)i_s, j_m = j - (int)j_s;
     const DivC<P2> disd(i_s * dx3), djsd(j_s * dx3), ddx2(dx2), disdx(i_s * dx);
     const float Xd = -vel.x * dt, Yd = -vel.y * dt;
-    const float2 dxv = ddx(0.5f * (ld2(v, d, r + 1, j) - ld2(v, d, r - 1, j)));
-    const float2 dyv = ddx(0.5f * (ld2(v, d, r, j + 1) - ld2(v, d, r, j - 1)));
+    const float2 dxv = ddx(0.5f * (ld2<CL>(v, d, r + 1, j) - ld2<CL>(v, d, r - 1, j)));
+    const float2 dyv = ddx(0.5f * (ld2<CL>(v, d, r, j + 1) - ld2<CL>(v, d, r, j - 1)));
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        const float f00 = ldc<C>(fc, d, r, j, c), f0m = ldc<C>(fc, d, r, j_m, c), fm0 = ldc<C>(fc, d, r_m, j, c), fmm = ldc<C>(fc, d, r_m, j_m, c);
-        const float x00 = ldc<C>(fxc, d, r, j, c), x0m = ldc<C>(fxc, d, r, j_m, c), xm0 = ldc<C>(fxc, d, r_m, j, c);
-        const float y00 = ldc<C>(fyc, d, r, j, c), y0m = ldc<C>(fyc, d, r, j_m, c), ym0 = ldc<C>(fyc, d, r_m, j, c);
+        const float f00 = ldc<C, CL>(fc, d, r, j, c), f0m = ldc<C, CL>(fc, d, r, j_m, c), fm0 = ldc<C, CL>(fc, d, r_m, j, c), fmm = ldc<C, CL>(fc, d, r_m, j_m, c);
+        const float x00 = ldc<C, CL>(fxc, d, r, j, c), x0m = ldc<C, CL>(fxc, d, r, j_m, c), xm0 = ldc<C, CL>(fxc, d, r_m, j, c);
+        const float y00 = ldc<C, CL>(fyc, d, r, j, c), y0m = ldc<C, CL>(fyc, d, r, j_m, c), ym0 = ldc<C, CL>(fyc, d, r_m, j, c);
         const float tmp1 = f00 - f0m - fm0 + fmm;
         const float tmp2 = fm0 - f00;
         const float tmp3 = f0m - f00;
@@ -160,6 +178,15 @@ __global__ void __launch_bounds__(TX *TY)
         fxn[C * idx + c] = Fx - dt * (Fx * dxv.x + Fy * dxv.y) / 2.0f;
         fyn[C * idx + c] = Fy - dt * (Fx * dyv.x + Fy * dyv.y) / 2.0f;
     }
+}
+template <bool P2, int C>
+__global__ void __launch_bounds__(TX *TY)
+    k_cip_advect_n(float *__restrict__ fn, float *__restrict__ fxn, float *__restrict__ fyn,
+                   const float *__restrict__ fc, const float *__restrict__ fxc, const float *__restrict__ fyc,
+                   const float *__restrict__ v, const uint8_t *__restrict__ mask, fs2d_dom d, float dt, float dx,
+                   DivC<P2> ddx, float dx2, float dx3) {
+    if (block_interior(d, TY, 1)) b_cip_advect_n<P2, C, false>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, ddx, dx2, dx3);
+    else b_cip_advect_n<P2, C, true>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, ddx, dx2, dx3);
 }
 
 // fs/solver.py:207-211  _set_grad on C channels

@@ -434,9 +434,10 @@ def test_dye_trajectory_matches_reference_fixture(env, name):
             assert_bitexact(f"{name} step {n} {k}", f.to_numpy(), g[f"s{n}_{k}"])
 
 
-@pytest.mark.parametrize("num,res,scheme", [(1, 128, "cip"), (2, 96, "kk"), (5, 100, "upwind")])
+@pytest.mark.parametrize("num,res,scheme", [(1, 128, "cip"), (2, 96, "kk"), (5, 100, "upwind"), (2, 320, "cip"), (3, 256, "cip")])
 def test_dye_simulator_vs_oracle(env, num, res, scheme):
-    """DyeFluidSimulator.create (main.py's default object graph) for a few steps vs the oracle."""
+    """DyeFluidSimulator.create (main.py's default object graph) for a few steps vs the oracle.  res >= 256: grids wide enough
+    for blocks that lie wholly inside the clamp window (the kernels' interior fast paths) and for RB-SOR chunks of 32 rows."""
     from fs.boundary_condition import build_scene
     from fs.fluid_simulator import DyeFluidSimulator
     from oracle import oracle as orc
@@ -445,13 +446,17 @@ def test_dye_simulator_vs_oracle(env, num, res, scheme):
     sim = DyeFluidSimulator.create(num, res, dt, dx, re, vc, scheme)
     const, mask, dye = build_scene(num, 2 * res, res, with_dye=True)
     ref = orc.OracleSolver(mask, const, dt, dx, re, scheme, vc, ("rbsor", 1.3, 2), bc_dye=dye)
-    for _ in range(6):
+    for _ in range(6 if res < 200 else 3):
         sim.step(); ref.update()
     out = sim.field_to_numpy()
     assert set(out) == {"v", "p", "dye"} and out["dye"].shape == (2 * res, res, 3)
     assert_bitexact("v", out["v"], ref.v.current); assert_bitexact("p", out["p"], ref.p.current)
     assert_bitexact("dye", out["dye"], ref.dye.current)
     assert float(out["dye"].max()) > 0.5   # dye actually entered the domain
+    if res >= 200:      # every physical buffer, dye derivative fields included
+        got = dye_state(sim.solver)
+        for k, a in ref.state().items():
+            assert_bitexact(f"bc{num} res {res} {k}", got[k].to_numpy(), a)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -126,7 +126,7 @@ def test_emu_fused_pass_split_into_interior_and_edge_launches(env):
     G.test_fused_pass_split_into_interior_and_edge_launches(env, X=420, Y=160)
 
 
-@pytest.mark.parametrize("num,res,scheme", [(2, 96, "kk"), (5, 100, "upwind")])
+@pytest.mark.parametrize("num,res,scheme", [(2, 96, "kk"), (5, 100, "upwind"), (2, 256, "cip")])
 def test_emu_dye_simulator_vs_oracle(env, num, res, scheme):
     G.test_dye_simulator_vs_oracle(env, num, res, scheme)
 
