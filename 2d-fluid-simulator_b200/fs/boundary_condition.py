@@ -445,6 +445,17 @@ def build_scene(num: int, x_res: int, y_res: int, obstacle_image: Path | None = 
     return (bc, mask, dye) if with_dye else (bc, mask)
 
 
+def scene_row_activity(num: int, x_res: int, y_res: int, chunk: int = 2048) -> npt.NDArray:
+    """Fraction of not-wall cells in every row of scene `num`, built chunk by chunk (O(chunk) memory): the weight that
+    fs.distributed.balanced_bounds turns into strips of equal work."""
+    out = np.empty(int(x_res), dtype=np.float64)
+    for a in range(0, int(x_res), chunk):
+        b = min(a + chunk, int(x_res))
+        _, mask = build_scene(num, x_res, y_res, rows=(a, b))
+        out[a:b] = (mask != WALL).mean(axis=1)
+    return out
+
+
 def _make(num: int, resolution: int, enable_dye: bool, obstacle_image=None, **kw) -> BoundaryCondition:
     if enable_dye:
         bc, mask, dye = build_scene(num, 2 * resolution, resolution, obstacle_image=obstacle_image, with_dye=True)

@@ -53,6 +53,8 @@ def parse() -> argparse.Namespace:
     ap.add_argument("--jacobi", type=int, default=N_JACOBI)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
+    ap.add_argument("--balance-strips", action="store_true", help="N > 1: strips of equal work (walls cost less) instead of equal rows; default for --config 5")
+    ap.add_argument("--equal-strips", action="store_true", help="--config 5: equal rows per strip")
     ap.add_argument("--graph-strips", action="store_true", help="N > 1: capture the strips' steps (kernels + NCCL SendRecvs) into CUDA graphs too")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-config", action="store_true", help="skip the BASELINE configs[1] side measurement (N=1)")
@@ -394,8 +396,16 @@ def run_ours(a: argparse.Namespace) -> None:
 
     X, Y = a.rows_per_gpu * world, a.cols
     dt, dx = 0.05 / Y_COLS, 1.0 / Y_COLS
-    part = Partition(X, rank, world, 0 if world == 1 else 33)  # halo 33: four fused Jacobi passes of up to 8 iterations per exchange
     t_setup = time.perf_counter()
+    bounds = None
+    if world > 1 and (a.balance_strips or (a.config == 5 and not a.equal_strips)):
+        # strips of equal WORK instead of equal rows: the fused Jacobi passes skip tiles inside walls, the other kernels stream
+        # every cell; weights from the per-kernel times of the single-GPU step (non-Poisson 2.0 ms, 45 us per sweep at 8192^2)
+        from fs.boundary_condition import scene_row_activity
+        from fs.distributed import balanced_bounds
+
+        bounds = balanced_bounds(2.0 + 0.045 * a.jacobi * scene_row_activity(SCENE, X, Y), world, min_rows=64)
+    part = Partition(X, rank, world, 0 if world == 1 else 33, bounds)  # halo 33: four fused Jacobi passes of up to 8 iterations per exchange
     if world == 1:
         const, mask = build_scene(SCENE, X, Y)
         bc = BoundaryCondition(const, mask, partition=part)
@@ -619,7 +629,7 @@ def run_ours(a: argparse.Namespace) -> None:
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, world),
                 "stepping": "cuda-graph replay (1 launch/step)" if use_graph else "eager launches",
                 "ms_per_step_eager": ms_step_eager, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu, "baseline_config_2": extra, "value_developed_state": developed, "numa": numa, "setup_s": t_setup,
+                "cpu_baseline": cpu, "baseline_config_2": extra, "value_developed_state": developed, "numa": numa, "setup_s": t_setup, "strip_bounds": list(bounds) if bounds else None,
                 "state": "quiescent start (all fields zero, the reference's initial state)" if a.state != "developed" else "developed-like seeded fields",
                 "tuning": tuning or None}
         sys.stdout.flush()

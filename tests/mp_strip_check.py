@@ -122,10 +122,20 @@ def main() -> None:
         k, v = item.split("=")
         _l.call("fs2d_set_tuning", int(k), int(v))
     n_ok = 0
-    for num, X, Y, scheme, vc, pkw, steps, halo in cases:
+    # cases tall enough run a second time on strips of UNEQUAL height (Partition.bounds: what bench.py --config 5 uses to balance
+    # the work of scenes with unevenly distributed walls)
+    runs = [(c, False) for c in cases] + [(c, True) for c in cases if not isinstance(c[0], str) and c[1] >= 512 and c[1] // world >= 2 * c[7] + 16
+                                           and c[1] * c[2] <= SEED_MAX_CELLS]
+    for (num, X, Y, scheme, vc, pkw, steps, halo), skewed in runs:
         res = Y
         dt, dx, re = 0.05 / res, 1.0 / res, 1e4
-        part = Partition(X, rank, world, halo)
+        bounds = None
+        if skewed:   # strip k ends at X * ((k + 1) / world) ** 1.6, never thinner than the halo
+            bounds = [0]
+            for k in range(1, world):
+                bounds.append(min(max(int(X * (k / world) ** 1.6), bounds[-1] + halo + 8), X - (world - k) * (halo + 8)))
+            bounds.append(X)
+        part = Partition(X, rank, world, halo, tuple(bounds) if bounds else None)
         if isinstance(num, str):
             const, mask = random_scene(int(num[4:]), X, Y)
             strip = make_solver(BoundaryCondition(const, mask, device=dev, partition=part), dt, dx, re, vc, scheme, **pkw)
@@ -170,7 +180,7 @@ def main() -> None:
                                      f"{int(bad.sum())} values differ, first rows {rows}")
         n_ok += 1
         if rank == 0:
-            print(f"  case ok: bc{num} {X}x{Y} {scheme} vc={vc} {pkw} steps={steps} halo={halo} on {world} ranks"
+            print(f"  case ok: bc{num} {X}x{Y} {scheme} vc={vc} {pkw} steps={steps} halo={halo} on {world} ranks{' strips ' + str(bounds) if bounds else ''}"
                   f"{'' if X * Y <= SEED_MAX_CELLS else ' (quiescent start)'}", flush=True)
         del strip, single
         if dev.type == "cuda":
