@@ -445,14 +445,33 @@ def build_scene(num: int, x_res: int, y_res: int, obstacle_image: Path | None = 
     return (bc, mask, dye) if with_dye else (bc, mask)
 
 
-def scene_row_activity(num: int, x_res: int, y_res: int, chunk: int = 2048) -> npt.NDArray:
-    """Fraction of not-wall cells in every row of scene `num`, built chunk by chunk (O(chunk) memory): the weight that
-    fs.distributed.balanced_bounds turns into strips of equal work."""
-    out = np.empty(int(x_res), dtype=np.float64)
-    for a in range(0, int(x_res), chunk):
-        b = min(a + chunk, int(x_res))
-        _, mask = build_scene(num, x_res, y_res, rows=(a, b))
-        out[a:b] = (mask != WALL).mean(axis=1)
+def scene_row_cost(num: int, x_res: int, y_res: int, n_sweeps: int, tile=(80, 112, 8, 8), tile_rows_per_chunk: int = 32) -> npt.NDArray:
+    """Estimated cost (microseconds on a B200) of one time step per ROW of scene `num` with n_sweeps fused Jacobi iterations:
+    the weight fs.distributed.balanced_bounds turns into strips of equal work.  The stencil kernels stream every cell
+    (2.0 ms per 67 M cells); the fused Jacobi passes work by tiles of `tile` = (output rows, output columns, row halo, column
+    halo): a tile inside a wall is skipped, an open-fluid tile costs one unit, a tile with BC cells about 2.2 (5.3 ns per unit
+    and sweep: 323 us for the 7590 units of a T = 8 pass at bc2 8192^2, profiles/r02_*).  Built chunk by chunk (O(chunk)
+    memory), identical on every rank."""
+    X, Y = int(x_res), int(y_res)
+    ti, tj, hi, hj = tile
+    out = np.empty(X, dtype=np.float64)
+    step = ti * tile_rows_per_chunk
+    for a in range(0, X, step):
+        b = min(a + step, X)
+        lo, hi_row = max(a - hi, 0), min(b + hi, X)
+        _, m = build_scene(num, X, Y, rows=(lo, hi_row))
+        wall, fluid = (m == WALL), (m == FLUID)
+        for r in range(a, b, ti):
+            r0, r1 = max(r - hi, lo) - lo, min(r + ti + hi, hi_row) - lo       # loaded rows of this tile row, chunk coordinates
+            units = 0.0
+            for c in range(0, Y, tj):
+                c0, c1 = max(c - hj, 0), min(c + tj + hj, Y)
+                if wall[r0:r1, c0:c1].all():
+                    continue                                   # nothing to relax: the pass drops the tile
+                inside = r - hi >= 0 and r + ti + hi <= X and c - hj >= 0 and c + tj + hj <= Y
+                units += 1.0 if inside and fluid[r0:r1, c0:c1].all() else 2.2
+            rows = min(r + ti, b) - r
+            out[r:r + rows] = (5.3e-3 * n_sweeps * units + 2.98e-5 * ti * Y) / ti
     return out
 
 

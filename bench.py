@@ -399,12 +399,12 @@ def run_ours(a: argparse.Namespace) -> None:
     t_setup = time.perf_counter()
     bounds = None
     if world > 1 and (a.balance_strips or (a.config == 5 and not a.equal_strips)):
-        # strips of equal WORK instead of equal rows: the fused Jacobi passes skip tiles inside walls, the other kernels stream
-        # every cell; weights from the per-kernel times of the single-GPU step (non-Poisson 2.0 ms, 45 us per sweep at 8192^2)
-        from fs.boundary_condition import scene_row_activity
+        # strips of equal WORK instead of equal rows: the fused Jacobi passes skip tiles inside walls and pay double for tiles
+        # with BC cells, the other kernels stream every cell (fs.boundary_condition.scene_row_cost)
+        from fs.boundary_condition import scene_row_cost
         from fs.distributed import balanced_bounds
 
-        bounds = balanced_bounds(2.0 + 0.045 * a.jacobi * scene_row_activity(SCENE, X, Y), world, min_rows=64)
+        bounds = balanced_bounds(scene_row_cost(SCENE, X, Y, a.jacobi), world, min_rows=128)
     part = Partition(X, rank, world, 0 if world == 1 else 33, bounds)  # halo 33: four fused Jacobi passes of up to 8 iterations per exchange
     if world == 1:
         const, mask = build_scene(SCENE, X, Y)

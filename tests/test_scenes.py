@@ -59,3 +59,27 @@ def test_non_2to1_scene_has_same_structure():
     assert mask.shape == (96, 32)
     assert (mask[:2, 32 // 3: 2 * 32 // 3] == 2).all() and (mask[-2:, 32 // 3: 2 * (32 // 3)] == 3).all()
     assert (mask[:, :2] == 1).all() and (mask[:, -2:] == 1).all()
+
+
+def test_balanced_strips_follow_the_cost_model():
+    """fs.boundary_condition.scene_row_cost + fs.distributed.balanced_bounds: strips of (nearly) equal estimated work, every
+    row assigned exactly once, and bc5 -- a third of it wall -- gets taller strips where its slab is."""
+    import numpy as np
+
+    from fs.boundary_condition import scene_row_cost
+    from fs.distributed import Partition, balanced_bounds
+
+    X, Y = 4096, 2048
+    w = scene_row_cost(5, X, Y, 200)
+    assert w.shape == (X,) and (w > 0).all()
+    for world in (2, 4, 8):
+        b = balanced_bounds(w, world, min_rows=64)
+        assert b[0] == 0 and b[-1] == X and all(b[k + 1] - b[k] >= 64 for k in range(world))
+        loads = [w[b[k]:b[k + 1]].sum() for k in range(world)]
+        equal = [w[k * X // world:(k + 1) * X // world].sum() for k in range(world)]
+        assert max(loads) <= max(equal) + 1e-9 and max(loads) / (sum(loads) / world) < 1.12
+        parts = [Partition(X, r, world, 9, b) for r in range(world)]
+        assert [p.owned() for p in parts] == [(b[k], b[k + 1]) for k in range(world)]
+    assert np.diff(balanced_bounds(w, 8, 64))[0] > X // 8          # the slab rows (0 .. 11 X / 30) are cheap: the first strip is taller
+    with __import__("pytest").raises(ValueError):
+        Partition(X, 0, 2, 9, (0, 5, X))                            # a strip thinner than the halo
