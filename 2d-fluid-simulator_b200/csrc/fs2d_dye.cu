@@ -2,9 +2,10 @@
 // 3-channel AoS fields (fs/solver.py:110-161, :335-401).  Kernels here are generic in the channel count C
 // (scalar loads per component, same per-component operation order as the float2 kernels in
 // fs2d_kernels.cu), instantiated for C = 3.  Dye is off the benchmark path (`-no_dye`) but on the path main.py runs by
-// default.  The three kernels of the CIP path (non-advection, its gradient update, CIP advection) run ONE CHANNEL OF ONE
-// CELL PER THREAD, threads ordered like the floats of the AoS row (FS2D_CELL_CH): every load and store of a warp is then
-// 128 contiguous bytes, where a thread that owns a whole cell reads 12-byte strided words three times over.
+// default.  One cell (all C channels) per thread.  Measured and dropped in round 2: one CHANNEL of one cell per thread, threads
+// ordered like the floats of the AoS row so that every warp access is 128 contiguous bytes -- bit-identical and 1.5-2.5x
+// SLOWER (CIP advection 750 -> 1098 us, gradient update 416 -> 682, non-advection 230 -> 570 us at 8192 x 4096): the kernels
+// are bound by instruction issue, and the per-thread index / mask / velocity work is then paid per float instead of per cell.
 #include "fs2d_common.cuh"
 
 namespace fs2d {
@@ -16,27 +17,6 @@ template <int C, bool CL = true>
 __device__ __forceinline__ float ldc(const float *f, const fs2d_dom &d, int r, int j, int c) {
     if (CL) return __ldg(f + (size_t)C * IX(d, CR(d, r), CJ(d, j)) + c);
     return __ldg(f + (ptrdiff_t)C * ((ptrdiff_t)r * d.Y + j) + c);
-}
-
-// One channel of one cell per thread: a block is (C * CH_COLS, CH_ROWS) threads covering CH_COLS columns of CH_ROWS rows;
-// threadIdx.x runs over the C * CH_COLS floats of the block's piece of an AoS row.
-constexpr int CH_COLS = 64;
-constexpr int CH_ROWS = 2;
-template <int C>
-inline dim3 ch_block() { return dim3(C * CH_COLS, CH_ROWS, 1); }
-inline dim3 ch_grid(const fs2d_dom &d) {
-    return dim3((unsigned)((d.Y + CH_COLS - 1) / CH_COLS), (unsigned)((d.r1 - d.r0 + CH_ROWS - 1) / CH_ROWS), 1);
-}
-#define FS2D_CELL_CH(C, d, r, j, c)                                \
-    const int c = (int)threadIdx.x % (C);                          \
-    const int j = FS2D_COLBLK * CH_COLS + (int)threadIdx.x / (C);  \
-    const int r = (d).r0 + FS2D_ROWBLK * CH_ROWS + threadIdx.y;    \
-    if (j >= (d).Y || r >= (d).r1) return;
-// block_interior for these blocks (CH_COLS columns, whatever blockDim.x is)
-__device__ __forceinline__ bool ch_block_interior(const fs2d_dom &d, int halo) {
-    const int rb = d.r0 + FS2D_ROWBLK * CH_ROWS, jb = FS2D_COLBLK * CH_COLS;
-    return rb - halo >= d.clo && rb + CH_ROWS - 1 + halo <= d.chi && rb + CH_ROWS <= d.r1 && jb - halo >= 0 &&
-           jb + CH_COLS - 1 + halo <= d.Y - 1;
 }
 
 // fs/boundary_condition.py:94-99  set_dye_boundary_condition: dye = bc_dye on inflow cells (sparse list)
@@ -118,19 +98,22 @@ __global__ void __launch_bounds__(TX *TY)
 template <bool P2, int C, bool CL>
 __device__ __forceinline__ void b_dye_nonadv(float *__restrict__ dn, const float *__restrict__ dc, const uint8_t *__restrict__ mask,
                                              const fs2d_dom &d, float dt, DivC<P2> ddx2, float re) {
-    FS2D_CELL_CH(C, d, r, j, c)
+    FS2D_CELL(d, r, j)
     const size_t idx = IX(d, r, j);
     if (mask[idx] == 1) return;
-    const float cc = __ldg(dc + C * idx + c);
-    const float d2x = ddx2(ldc<C, CL>(dc, d, r + 1, j, c) - 2.0f * cc + ldc<C, CL>(dc, d, r - 1, j, c));
-    const float d2y = ddx2(ldc<C, CL>(dc, d, r, j + 1, c) - 2.0f * cc + ldc<C, CL>(dc, d, r, j - 1, c));
-    dn[C * idx + c] = cc + fdiv_z(d2x + d2y, re) * dt;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const float cc = __ldg(dc + C * idx + c);
+        const float d2x = ddx2(ldc<C, CL>(dc, d, r + 1, j, c) - 2.0f * cc + ldc<C, CL>(dc, d, r - 1, j, c));
+        const float d2y = ddx2(ldc<C, CL>(dc, d, r, j + 1, c) - 2.0f * cc + ldc<C, CL>(dc, d, r, j - 1, c));
+        dn[C * idx + c] = cc + fdiv_z(d2x + d2y, re) * dt;
+    }
 }
 template <bool P2, int C>
-__global__ void __launch_bounds__(C *CH_COLS *CH_ROWS)
+__global__ void __launch_bounds__(TX *TY)
     k_dye_nonadv(float *__restrict__ dn, const float *__restrict__ dc, const uint8_t *__restrict__ mask, fs2d_dom d,
                  float dt, DivC<P2> ddx2, float re) {
-    if (ch_block_interior(d, 1)) b_dye_nonadv<P2, C, false>(dn, dc, mask, d, dt, ddx2, re);
+    if (block_interior(d, TY, 1)) b_dye_nonadv<P2, C, false>(dn, dc, mask, d, dt, ddx2, re);
     else b_dye_nonadv<P2, C, true>(dn, dc, mask, d, dt, ddx2, re);
 }
 
@@ -140,20 +123,23 @@ __device__ __forceinline__ void b_nonadv_grad_n(float *__restrict__ fxn, float *
                                                 const float *__restrict__ fyc, const float *__restrict__ fc,
                                                 const float *__restrict__ fn, const uint8_t *__restrict__ mask, const fs2d_dom &d,
                                                 DivC<P2> d2dx) {
-    FS2D_CELL_CH(C, d, r, j, c)
+    FS2D_CELL(d, r, j)
     const size_t idx = IX(d, r, j);
     if (mask[idx] == 1) return;
-    const float gx = ldc<C, CL>(fn, d, r + 1, j, c) - ldc<C, CL>(fc, d, r + 1, j, c) - ldc<C, CL>(fn, d, r - 1, j, c) + ldc<C, CL>(fc, d, r - 1, j, c);
-    const float gy = ldc<C, CL>(fn, d, r, j + 1, c) - ldc<C, CL>(fc, d, r, j + 1, c) - ldc<C, CL>(fn, d, r, j - 1, c) + ldc<C, CL>(fc, d, r, j - 1, c);
-    fxn[C * idx + c] = __ldg(fxc + C * idx + c) + d2dx(gx);
-    fyn[C * idx + c] = __ldg(fyc + C * idx + c) + d2dx(gy);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const float gx = ldc<C, CL>(fn, d, r + 1, j, c) - ldc<C, CL>(fc, d, r + 1, j, c) - ldc<C, CL>(fn, d, r - 1, j, c) + ldc<C, CL>(fc, d, r - 1, j, c);
+        const float gy = ldc<C, CL>(fn, d, r, j + 1, c) - ldc<C, CL>(fc, d, r, j + 1, c) - ldc<C, CL>(fn, d, r, j - 1, c) + ldc<C, CL>(fc, d, r, j - 1, c);
+        fxn[C * idx + c] = __ldg(fxc + C * idx + c) + d2dx(gx);
+        fyn[C * idx + c] = __ldg(fyc + C * idx + c) + d2dx(gy);
+    }
 }
 template <bool P2, int C>
-__global__ void __launch_bounds__(C *CH_COLS *CH_ROWS)
+__global__ void __launch_bounds__(TX *TY)
     k_nonadv_grad_n(float *__restrict__ fxn, float *__restrict__ fyn, const float *__restrict__ fxc,
                     const float *__restrict__ fyc, const float *__restrict__ fc, const float *__restrict__ fn,
                     const uint8_t *__restrict__ mask, fs2d_dom d, DivC<P2> d2dx) {
-    if (ch_block_interior(d, 1)) b_nonadv_grad_n<P2, C, false>(fxn, fyn, fxc, fyc, fc, fn, mask, d, d2dx);
+    if (block_interior(d, TY, 1)) b_nonadv_grad_n<P2, C, false>(fxn, fyn, fxc, fyc, fc, fn, mask, d, d2dx);
     else b_nonadv_grad_n<P2, C, true>(fxn, fyn, fxc, fyc, fc, fn, mask, d, d2dx);
 }
 
@@ -164,7 +150,7 @@ __device__ __forceinline__ void b_cip_advect_n(float *__restrict__ fn, float *__
                                                const float *__restrict__ fyc, const float *__restrict__ v,
                                                const uint8_t *__restrict__ mask, const fs2d_dom &d, float dt, float dx,
                                                DivC<P2> ddx, DivC<P2> ddx2, DivC<P2> ddx3) {
-    FS2D_CELL_CH(C, d, r, j, c)
+    FS2D_CELL(d, r, j)
     const size_t idx = IX(d, r, j);
     if (mask[idx] != 0) return;
     const float2 vel = __ldg(reinterpret_cast<const float2 *>(v) + idx);
@@ -175,7 +161,8 @@ __device__ __forceinline__ void b_cip_advect_n(float *__restrict__ fn, float *__
     const float Xd = -vel.x * dt, Yd = -vel.y * dt;
     const float2 dxv = ddx(0.5f * (ld2<CL>(v, d, r + 1, j) - ld2<CL>(v, d, r - 1, j)));
     const float2 dyv = ddx(0.5f * (ld2<CL>(v, d, r, j + 1) - ld2<CL>(v, d, r, j - 1)));
-    {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
         const float f00 = ldc<C, CL>(fc, d, r, j, c), f0m = ldc<C, CL>(fc, d, r, j_m, c), fm0 = ldc<C, CL>(fc, d, r_m, j, c), fmm = ldc<C, CL>(fc, d, r_m, j_m, c);
         const float x00 = ldc<C, CL>(fxc, d, r, j, c), x0m = ldc<C, CL>(fxc, d, r, j_m, c), xm0 = ldc<C, CL>(fxc, d, r_m, j, c);
         const float y00 = ldc<C, CL>(fyc, d, r, j, c), y0m = ldc<C, CL>(fyc, d, r, j_m, c), ym0 = ldc<C, CL>(fyc, d, r_m, j, c);
@@ -197,12 +184,12 @@ __device__ __forceinline__ void b_cip_advect_n(float *__restrict__ fn, float *__
     }
 }
 template <bool P2, int C>
-__global__ void __launch_bounds__(C *CH_COLS *CH_ROWS)
+__global__ void __launch_bounds__(TX *TY)
     k_cip_advect_n(float *__restrict__ fn, float *__restrict__ fxn, float *__restrict__ fyn,
                    const float *__restrict__ fc, const float *__restrict__ fxc, const float *__restrict__ fyc,
                    const float *__restrict__ v, const uint8_t *__restrict__ mask, fs2d_dom d, float dt, float dx,
                    DivC<P2> ddx, DivC<P2> ddx2, DivC<P2> ddx3) {
-    if (ch_block_interior(d, 1)) b_cip_advect_n<P2, C, false>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, ddx, ddx2, ddx3);
+    if (block_interior(d, TY, 1)) b_cip_advect_n<P2, C, false>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, ddx, ddx2, ddx3);
     else b_cip_advect_n<P2, C, true>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, ddx, ddx2, ddx3);
 }
 
@@ -300,7 +287,7 @@ int fs2d_dye_nonadv(float *dn, const float *dc, const uint8_t *mask, fs2d_dom d,
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
     const float dx2 = dx * dx;
-#define DN(P2) k_dye_nonadv<P2, 3><<<ch_grid(d), ch_block<3>(), 0, STREAM>>>(dn, dc, mask, d, dt, DivC<P2>(dx2), re)
+#define DN(P2) k_dye_nonadv<P2, 3><<<dense_grid(d), dense_block(), 0, STREAM>>>(dn, dc, mask, d, dt, DivC<P2>(dx2), re)
     P2_DISPATCH(is_pow2(dx), DN(true), DN(false));
 #undef DN
     FS2D_LAUNCH_CHECK();
@@ -312,7 +299,7 @@ int fs2d_dye_nonadv_grad(float *fxn, float *fyn, const float *fxc, const float *
     FS2D_REQUIRE(fxn && fyn && fxc && fyc && fc && fn && mask, "null field pointer");
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
-#define NG(P2) k_nonadv_grad_n<P2, 3><<<ch_grid(d), ch_block<3>(), 0, STREAM>>>(fxn, fyn, fxc, fyc, fc, fn, mask, d, DivC<P2>(two_dx))
+#define NG(P2) k_nonadv_grad_n<P2, 3><<<dense_grid(d), dense_block(), 0, STREAM>>>(fxn, fyn, fxc, fyc, fc, fn, mask, d, DivC<P2>(two_dx))
     P2_DISPATCH(is_pow2(two_dx), NG(true), NG(false));
 #undef NG
     FS2D_LAUNCH_CHECK();
@@ -326,7 +313,7 @@ int fs2d_dye_cip_advect(float *fn, float *fxn, float *fyn, const float *fc, cons
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
     const bool p2 = is_pow2(dx) && is_pow2(dx2) && is_pow2(dx3);
-#define CA(P2) k_cip_advect_n<P2, 3><<<ch_grid(d), ch_block<3>(), 0, STREAM>>>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, DivC<P2>(dx), DivC<P2>(dx2), DivC<P2>(dx3))
+#define CA(P2) k_cip_advect_n<P2, 3><<<dense_grid(d), dense_block(), 0, STREAM>>>(fn, fxn, fyn, fc, fxc, fyc, v, mask, d, dt, dx, DivC<P2>(dx), DivC<P2>(dx2), DivC<P2>(dx3))
     P2_DISPATCH(p2, CA(true), CA(false));
 #undef CA
     FS2D_LAUNCH_CHECK();
