@@ -350,6 +350,16 @@ inline float __shfl_down_sync(unsigned, float v, int delta) {
     return lane + delta < 32 ? __int_as_float((int)emu::my_warp().buf[g][lane + delta]) : v;
 }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_rendezvous(0, 1); }
+inline int __shfl_up_sync(unsigned, int v, int delta) {
+    const int lane = emu::M().cur->lin % 32;
+    const int g = emu::warp_rendezvous((uint32_t)v, 1);
+    return lane - delta >= 0 ? (int)emu::my_warp().buf[g][lane - delta] : v;
+}
+inline int __shfl_sync(unsigned, int v, int src) {
+    const int g = emu::warp_rendezvous((uint32_t)v, 1);
+    return (int)emu::my_warp().buf[g][src & 31];
+}
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __all_sync(unsigned, int pred) {
     const int g = emu::warp_rendezvous(0, pred);
     return emu::my_warp().pred_and[g];
