@@ -184,7 +184,7 @@ __device__ __forceinline__ void b_cip_advect_n(float *__restrict__ fn, float *__
     }
 }
 template <bool P2, int C>
-__global__ void __launch_bounds__(TX *TY)
+__global__ void __launch_bounds__(TX *TY, 5)
     k_cip_advect_n(float *__restrict__ fn, float *__restrict__ fxn, float *__restrict__ fyn,
                    const float *__restrict__ fc, const float *__restrict__ fxc, const float *__restrict__ fyc,
                    const float *__restrict__ v, const uint8_t *__restrict__ mask, fs2d_dom d, float dt, float dx,
