@@ -194,7 +194,10 @@ __global__ void __launch_bounds__(TX *TY)
 // are independent.  21 B/cell (pc 4, pn 4 + 4, source 8, mask 1) instead of two passes over all five arrays; same
 // expression and order per cell: bit-identical to the two k_rbsor_pass launches.  Requires Y % 4 == 0, pn != pc.
 constexpr int RB_ROWS = 32, RB_WARPS = 8, RB_COLS = 120;
-__global__ void __launch_bounds__(32 * RB_WARPS)
+// 3 resident blocks (80 registers instead of 94, 20 bytes spilled): 164 -> 154 us per iteration at 8192 x 4096; 4 blocks
+// (64 registers, 120 bytes spilled): 188 us; 5 blocks: 304 us.  The kernel stays bound by its registers (three pc rows, three
+// O rows and the source of the previous row live across the march): occupancy 37 %, 0.64 of the HBM peak on its 21 B/cell.
+__global__ void __launch_bounds__(32 * RB_WARPS, 3)
     k_rbsor_fused(float *__restrict__ pn, const float *__restrict__ pc, const float *__restrict__ src,
                   const uint8_t *__restrict__ mask, fs2d_dom d, float omega, float one_minus_omega) {
     constexpr uint32_t FULL = 0xffffffffu;
