@@ -57,10 +57,13 @@ def test_tma_kernels_use_tma_and_mbarriers(sass):
 
 
 def test_hot_kernels_do_not_spill(sass):
-    hot = ["k_jacobi_fused", "k_jacobi_fused_emit", "k_jacobi_march<false, 4>", "k_p_source", "k_cip_nonadv<true>",
+    hot = ["k_jacobi_fused", "k_jacobi_fused_emit", "k_jacobi_march<false, 4>", "k_cip_nonadv<true>",
            "k_cip_nonadv_grad<true>", "k_stream<OpAdvect<true>, 2, 3, 256>", "k_vort_apply<true>", "k_limit"]
     for name in hot:
         _, u = sass[name]
         assert u.get("LOCAL", 0) == 0 and u.get("STACK", 0) == 0, f"{name}: spills ({u})"
+    # k_p_source is held to 40 registers (6 resident blocks per SM) at the price of two spilled words: measured 213 -> 196 us
+    _, u = sass["k_p_source"]
+    assert u["REG"] <= 40 and u.get("STACK", 0) <= 16, f"k_p_source: {u}"
     # the 96 x 128 register tile needs <= 168 registers to keep 384 threads (12 warps) resident on one SM
     assert sass["k_jacobi_fused"][1]["REG"] <= 168
