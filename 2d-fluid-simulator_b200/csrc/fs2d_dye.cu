@@ -100,13 +100,14 @@ __device__ __forceinline__ void b_dye_nonadv(float *__restrict__ dn, const float
                                              const fs2d_dom &d, float dt, DivC<P2> ddx2, float re) {
     FS2D_CELL(d, r, j)
     const size_t idx = IX(d, r, j);
-    if (mask[idx] == 1) return;
+    const uint8_t m = __ldg(mask + idx);   // consulted at the stores: the field loads do not wait for it
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         const float cc = __ldg(dc + C * idx + c);
         const float d2x = ddx2(ldc<C, CL>(dc, d, r + 1, j, c) - 2.0f * cc + ldc<C, CL>(dc, d, r - 1, j, c));
         const float d2y = ddx2(ldc<C, CL>(dc, d, r, j + 1, c) - 2.0f * cc + ldc<C, CL>(dc, d, r, j - 1, c));
-        dn[C * idx + c] = cc + fdiv_z(d2x + d2y, re) * dt;
+        const float out = cc + fdiv_z(d2x + d2y, re) * dt;
+        if (m != 1) dn[C * idx + c] = out;
     }
 }
 template <bool P2, int C>
@@ -125,13 +126,16 @@ __device__ __forceinline__ void b_nonadv_grad_n(float *__restrict__ fxn, float *
                                                 DivC<P2> d2dx) {
     FS2D_CELL(d, r, j)
     const size_t idx = IX(d, r, j);
-    if (mask[idx] == 1) return;
+    const uint8_t m = __ldg(mask + idx);   // consulted at the stores: the field loads do not wait for it
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         const float gx = ldc<C, CL>(fn, d, r + 1, j, c) - ldc<C, CL>(fc, d, r + 1, j, c) - ldc<C, CL>(fn, d, r - 1, j, c) + ldc<C, CL>(fc, d, r - 1, j, c);
         const float gy = ldc<C, CL>(fn, d, r, j + 1, c) - ldc<C, CL>(fc, d, r, j + 1, c) - ldc<C, CL>(fn, d, r, j - 1, c) + ldc<C, CL>(fc, d, r, j - 1, c);
-        fxn[C * idx + c] = __ldg(fxc + C * idx + c) + d2dx(gx);
-        fyn[C * idx + c] = __ldg(fyc + C * idx + c) + d2dx(gy);
+        const float ox = __ldg(fxc + C * idx + c) + d2dx(gx), oy = __ldg(fyc + C * idx + c) + d2dx(gy);
+        if (m != 1) {
+            fxn[C * idx + c] = ox;
+            fyn[C * idx + c] = oy;
+        }
     }
 }
 template <bool P2, int C>
@@ -152,7 +156,7 @@ __device__ __forceinline__ void b_cip_advect_n(float *__restrict__ fn, float *__
                                                DivC<P2> ddx, DivC<P2> ddx2, DivC<P2> ddx3) {
     FS2D_CELL(d, r, j)
     const size_t idx = IX(d, r, j);
-    if (mask[idx] != 0) return;
+    const uint8_t m = __ldg(mask + idx);   // consulted at the stores: the velocity load (which every other load waits for) does not wait for it
     const float2 vel = __ldg(reinterpret_cast<const float2 *>(v) + idx);
     const float i_s = sign1(vel.x), j_s = sign1(vel.y);
     const int r_m = r - (int)i_s, j_m = j - (int)j_s;
@@ -176,11 +180,14 @@ __device__ __forceinline__ void b_cip_advect_n(float *__restrict__ fn, float *__
         const float e = ddx2(3.0f * tmp2 + i_s * (xm0 + 2.0f * x00) * dx);
         const float f = ddx2(3.0f * tmp3 + j_s * (y0m + 2.0f * y00) * dx);
         const float g = disdx(-(ym0 - y00) + cc * dx2);
-        fn[C * idx + c] = ((a * Xd + cc * Yd + e) * Xd + g * Yd + x00) * Xd + ((b * Yd + dd * Xd + f) * Yd + y00) * Yd + f00;
+        const float F = ((a * Xd + cc * Yd + e) * Xd + g * Yd + x00) * Xd + ((b * Yd + dd * Xd + f) * Yd + y00) * Yd + f00;
         const float Fx = (3.0f * a * Xd + 2.0f * cc * Yd + 2.0f * e) * Xd + (dd * Yd + g) * Yd + x00;
         const float Fy = (3.0f * b * Yd + 2.0f * dd * Xd + 2.0f * f) * Yd + (cc * Xd + g) * Xd + y00;
-        fxn[C * idx + c] = Fx - dt * (Fx * dxv.x + Fy * dxv.y) / 2.0f;
-        fyn[C * idx + c] = Fy - dt * (Fx * dyv.x + Fy * dyv.y) / 2.0f;
+        if (m == 0) {
+            fn[C * idx + c] = F;
+            fxn[C * idx + c] = Fx - dt * (Fx * dxv.x + Fy * dxv.y) / 2.0f;
+            fyn[C * idx + c] = Fy - dt * (Fx * dyv.x + Fy * dyv.y) / 2.0f;
+        }
     }
 }
 template <bool P2, int C>
