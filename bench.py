@@ -105,7 +105,7 @@ def traffic_from_profile():
         return None
     if t.get("source_sha256") != kernel_source_sha256():
         return {"stale": True, "note": f"{f.name} was captured from other kernel sources ({str(t.get('source_sha256'))[:12]}..., "
-                                        f"now {kernel_source_sha256()[:12]}...): re-run scripts/gpu_ncu_step.sh"}
+                                        f"now {kernel_source_sha256()[:12]}...): re-run scripts/gpu_evidence.sh and scripts/summarize_profiles.py"}
     return t
 
 

@@ -1,5 +1,5 @@
 #!/bin/bash
-# gpurun --timeout 1800 -- 'bash scripts/gpu_final1.sh'
+# gpurun --timeout 1800 -- 'bash scripts/gpu_evidence.sh'
 # One B200, everything the round's single-GPU evidence consists of: the -m gpu suite, smoke, the bench line and the reference
 # arm, BASELINE configs 2 / 3 / 5 on their own grids, the default main.py path, sanitizers, and the ncu captures.
 set -u

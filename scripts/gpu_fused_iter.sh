@@ -1,5 +1,5 @@
 #!/bin/bash
-# gpurun --timeout 900 -- 'bash scripts/gpu_fused3.sh'   (fused kernel iteration: parity, pass timings, step)
+# gpurun --timeout 900 -- 'bash scripts/gpu_fused_iter.sh'   (fused kernel iteration: parity, pass timings, step)
 set -u
 mkdir -p gpurun_out
 echo "== fused parity tests"
