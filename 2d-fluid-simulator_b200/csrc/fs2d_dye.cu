@@ -118,6 +118,76 @@ __global__ void __launch_bounds__(TX *TY)
     else b_dye_nonadv<P2, C, true>(dn, dc, mask, d, dt, ddx2, re);
 }
 
+// The same on FOUR CELLS PER THREAD (3 channels x 4 cells = 12 consecutive floats of the AoS row = three 16-byte words): a warp
+// covers 128 columns of one row, the rows above / below are three 128-bit loads each, the j-neighbours of the quad's end cells
+// come from the adjacent lanes by shuffle (the warp's first / last lane loads them, or takes its own cell on a grid edge, as
+// sample() clamps).  9 LDG.128 + 6 SHFL per 4 cells instead of 60 scalar loads: the one-cell kernel is bound by instruction
+// issue.  Same expression and order per value.  Requires Y % 4 == 0 and 16-byte aligned fields.
+constexpr int DN4_WARPS = 8;
+int g_dye_vec = 1;   // fs2d_set_tuning(5, v): 0 = always the one-cell-per-thread non-advection kernel
+template <bool P2>
+__global__ void __launch_bounds__(32 * DN4_WARPS)
+    k_dye_nonadv4(float *__restrict__ dn, const float *__restrict__ dc, const uint8_t *__restrict__ mask, fs2d_dom d, float dt,
+                  DivC<P2> ddx2, float re) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    const int lane = threadIdx.x;
+    const int r = d.r0 + FS2D_ROWBLK * DN4_WARPS + threadIdx.y;
+    if (r >= d.r1) return;   // warp-uniform
+    const int j0 = FS2D_COLBLK * 128 + 4 * lane;
+    const bool active = j0 < d.Y;
+    const int jc = active ? j0 : d.Y - 4;   // lanes past the grid read a valid quad (their values feed no active lane's result)
+    auto quad = [&](int row, float (&v)[12]) {
+        const float4 *q = reinterpret_cast<const float4 *>(dc + 3 * IX(d, row, jc));
+        const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
+    };
+    float C[12], U[12], D[12], L[3], R[3];
+    quad(r, C);
+    quad(CR(d, r + 1), U);
+    quad(CR(d, r - 1), D);
+    const uchar4 mk = __ldg(reinterpret_cast<const uchar4 *>(mask + IX(d, r, jc)));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        L[c] = __shfl_up_sync(FULL, C[9 + c], 1);
+        R[c] = __shfl_down_sync(FULL, C[c], 1);
+    }
+    if (lane == 0) {   // cell j0 - 1: outside the warp's span, or the cell itself on the grid's first column
+#pragma unroll
+        for (int c = 0; c < 3; ++c) L[c] = j0 == 0 ? C[c] : __ldg(dc + 3 * IX(d, r, j0 - 1) + c);
+    }
+    if (lane == 31 || j0 + 4 >= d.Y) {   // cell j0 + 4
+#pragma unroll
+        for (int c = 0; c < 3; ++c) R[c] = j0 + 4 >= d.Y ? C[9 + c] : __ldg(dc + 3 * IX(d, r, j0 + 4) + c);
+    }
+    if (!active) return;
+    float out[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) {
+        const float cc = C[e];
+        const float jp = e < 9 ? C[e + 3] : R[e - 9], jm = e >= 3 ? C[e - 3] : L[e];
+        const float d2x = ddx2(U[e] - 2.0f * cc + D[e]);
+        const float d2y = ddx2(jp - 2.0f * cc + jm);
+        out[e] = cc + fdiv_z(d2x + d2y, re) * dt;
+    }
+    float *dst = dn + 3 * IX(d, r, j0);
+    if (mk.x != 1 && mk.y != 1 && mk.z != 1 && mk.w != 1) {
+        float4 *q = reinterpret_cast<float4 *>(dst);
+        q[0] = make_float4(out[0], out[1], out[2], out[3]);
+        q[1] = make_float4(out[4], out[5], out[6], out[7]);
+        q[2] = make_float4(out[8], out[9], out[10], out[11]);
+    } else {
+        const uint8_t m[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (m[q] != 1) {
+                dst[3 * q] = out[3 * q];
+                dst[3 * q + 1] = out[3 * q + 1];
+                dst[3 * q + 2] = out[3 * q + 2];
+            }
+    }
+}
+
 // fs/solver.py:242-261  _non_advection_phase_grad on C channels
 template <bool P2, int C, bool CL>
 __device__ __forceinline__ void b_nonadv_grad_n(float *__restrict__ fxn, float *__restrict__ fyn, const float *__restrict__ fxc,
@@ -294,7 +364,13 @@ int fs2d_dye_nonadv(float *dn, const float *dc, const uint8_t *mask, fs2d_dom d,
     if (int e = check_dom(d)) return e;
     if (d.r1 == d.r0) return FS2D_OK;
     const float dx2 = dx * dx;
-#define DN(P2) k_dye_nonadv<P2, 3><<<dense_grid(d), dense_block(), 0, STREAM>>>(dn, dc, mask, d, dt, DivC<P2>(dx2), re)
+    const bool vec = g_dye_vec && d.Y % 4 == 0 && (uintptr_t)dn % 16 == 0 && (uintptr_t)dc % 16 == 0 && (uintptr_t)mask % 4 == 0;
+    const dim3 g4((unsigned)((d.Y + 127) / 128), (unsigned)((d.r1 - d.r0 + DN4_WARPS - 1) / DN4_WARPS), 1), b4(32, DN4_WARPS, 1);
+#define DN(P2)                                                                                                 \
+    do {                                                                                                       \
+        if (vec) k_dye_nonadv4<P2><<<g4, b4, 0, STREAM>>>(dn, dc, mask, d, dt, DivC<P2>(dx2), re);               \
+        else k_dye_nonadv<P2, 3><<<dense_grid(d), dense_block(), 0, STREAM>>>(dn, dc, mask, d, dt, DivC<P2>(dx2), re); \
+    } while (0)
     P2_DISPATCH(is_pow2(dx), DN(true), DN(false));
 #undef DN
     FS2D_LAUNCH_CHECK();

@@ -77,6 +77,8 @@ unsigned long long fs2d_launch_count(void);
  * key 3 = streaming-kernel shape {stages x CTAs/SM x threads}: {0: 3x2x256, 1: 2x3x256 (default), 2: 3x2x512, 3: 2x2x512}.
  * key 4 = tail of fs2d_jacobi_update {1 (default): the last fused pass also emits the BC values of its penultimate state, so
  *         ONE literal iteration ends the update; 0: two literal iterations}.
+ * key 5 = dye non-advection phase {1 (default): four cells per thread with 128-bit accesses when Y % 4 == 0 and the fields are
+ *         16-byte aligned; 0: always one cell per thread}.
  * Unknown keys / values return FS2D_E_BADARG and change nothing. */
 int fs2d_set_tuning(int key, int value);
 /* 1 if the library was built for sm_100a and a device of compute capability 10.x is current */

@@ -459,8 +459,9 @@ def test_dye_simulator_vs_oracle(env, num, res, scheme):
             assert_bitexact(f"bc{num} res {res} {k}", got[k].to_numpy(), a)
 
 
+@pytest.mark.parametrize("vec", [1, 0])
 @pytest.mark.parametrize("num,res,dx", [(2, 160, 1.0 / 160), (3, 136, 1.0 / 128)])
-def test_dye_step_from_random_state_vs_oracle(env, num, res, dx):
+def test_dye_step_from_random_state_vs_oracle(env, num, res, dx, vec):
     """The default object graph stepped from a RANDOM state (velocities of both signs in every cell, non-zero dye and dye
     derivatives everywhere): the dye kernels' interior blocks see real data -- a fresh scene has dye only next to the inflow,
     which is edge-block territory.  dx: a non-power-of-two spacing (IEEE divisions) and a power of two (exact reciprocals)."""
@@ -472,6 +473,14 @@ def test_dye_step_from_random_state_vs_oracle(env, num, res, dx):
     sim = DyeFluidSimulator.create(num, res, dt, dx, re, vc, "cip")
     const, mask, dye = build_scene(num, 2 * res, res, with_dye=True)
     ref = orc.OracleSolver(mask, const, dt, dx, re, "cip", vc, ("rbsor", 1.3, 2), bc_dye=dye)
+    assert env.fs2d_set_tuning(5, vec) == 0      # dye non-advection: four cells per thread (default) / one cell per thread
+    try:
+        _dye_random_steps(sim, ref, num, res)
+    finally:
+        env.fs2d_set_tuning(5, 1)
+
+
+def _dye_random_steps(sim, ref, num, res):
     rng = np.random.default_rng(res)
     st = {}
     for k, a in ref.state().items():
