@@ -216,6 +216,77 @@ __global__ void __launch_bounds__(TX *TY)
     else b_cip_nonadv<P2, true>(fn, fc, pc, mask, d, dt, ddx, ddx2, re);
 }
 
+// The same on FOUR CELLS PER THREAD: a warp covers 128 columns of one row; the rows r-1, r, r+1 of v are two 128-bit loads
+// each and those of p one, the j-neighbours of the quad's end cells come from the adjacent lanes by shuffle (the warp's first /
+// last lane loads them, or takes its own cell on a grid edge, as sample() clamps).  9 LDG.128 + 6 SHFL per 4 cells instead of
+// 40 loads: the one-cell kernel spends its issue slots on loads and their addresses.  Per-cell arithmetic: c_cip_nonadv, the
+// very function the other paths call.  Requires Y % 4 == 0 and 16-byte aligned fields (fs2d_set_tuning(6, 0): never used).
+constexpr int NA4_WARPS = 8;
+int g_nonadv_vec = 1;
+template <bool P2>
+__global__ void __launch_bounds__(32 * NA4_WARPS)
+    k_cip_nonadv4(float *__restrict__ fn, const float *__restrict__ fc, const float *__restrict__ pc,
+                  const uint8_t *__restrict__ mask, fs2d_dom d, float dt, DivC<P2> ddx, DivC<P2> ddx2, float re) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    const int lane = threadIdx.x;
+    const int r = d.r0 + FS2D_ROWBLK * NA4_WARPS + threadIdx.y;
+    if (r >= d.r1) return;   // warp-uniform
+    const int j0 = FS2D_COLBLK * 128 + 4 * lane;
+    const bool active = j0 < d.Y;
+    const int jc = active ? j0 : d.Y - 4;   // lanes past the grid read a valid quad (their values feed no active lane's result)
+    auto vquad = [&](int row, float2 (&v)[4]) {
+        const float4 *q = reinterpret_cast<const float4 *>(fc + 2 * IX(d, row, jc));
+        const float4 a = __ldg(q), b = __ldg(q + 1);
+        v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w); v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
+    };
+    auto pquad = [&](int row, float (&v)[4]) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(pc + IX(d, row, jc)));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    };
+    float2 C[4], U[4], D[4];
+    float pC[4], pU[4], pD[4];
+    const int ru = CR(d, r + 1), rd = CR(d, r - 1);
+    vquad(r, C); vquad(ru, U); vquad(rd, D);
+    pquad(r, pC); pquad(ru, pU); pquad(rd, pD);
+    const uchar4 mk = __ldg(reinterpret_cast<const uchar4 *>(mask + IX(d, r, jc)));
+    float2 L, R;
+    L.x = __shfl_up_sync(FULL, C[3].x, 1); L.y = __shfl_up_sync(FULL, C[3].y, 1);
+    R.x = __shfl_down_sync(FULL, C[0].x, 1); R.y = __shfl_down_sync(FULL, C[0].y, 1);
+    float pL = __shfl_up_sync(FULL, pC[3], 1), pR = __shfl_down_sync(FULL, pC[0], 1);
+    if (lane == 0) {   // cell j0 - 1: outside the warp's span, or the cell itself on the grid's first column
+        if (j0 == 0) { L = C[0]; pL = pC[0]; }
+        else { L = __ldg(reinterpret_cast<const float2 *>(fc) + IX(d, r, j0 - 1)); pL = __ldg(pc + IX(d, r, j0 - 1)); }
+    }
+    if (lane == 31 || j0 + 4 >= d.Y) {   // cell j0 + 4
+        if (j0 + 4 >= d.Y) { R = C[3]; pR = pC[3]; }
+        else { R = __ldg(reinterpret_cast<const float2 *>(fc) + IX(d, r, j0 + 4)); pR = __ldg(pc + IX(d, r, j0 + 4)); }
+    }
+    if (!active) return;
+    float2 out[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        NonadvIn x;
+        x.c = C[q]; x.ip = U[q]; x.im = D[q];
+        x.jp = q < 3 ? C[q < 3 ? q + 1 : 3] : R;
+        x.jm = q > 0 ? C[q > 0 ? q - 1 : 0] : L;
+        x.pip = pU[q]; x.pim = pD[q];
+        x.pjp = q < 3 ? pC[q < 3 ? q + 1 : 3] : pR;
+        x.pjm = q > 0 ? pC[q > 0 ? q - 1 : 0] : pL;
+        out[q] = c_cip_nonadv<P2>(x, dt, ddx, ddx2, re);
+    }
+    float *dst = fn + 2 * IX(d, r, j0);
+    if (mk.x != 1 && mk.y != 1 && mk.z != 1 && mk.w != 1) {
+        float4 *q = reinterpret_cast<float4 *>(dst);
+        q[0] = make_float4(out[0].x, out[0].y, out[1].x, out[1].y);
+        q[1] = make_float4(out[2].x, out[2].y, out[3].x, out[3].y);
+    } else {
+        const uint8_t m[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (m[q] != 1) reinterpret_cast<float2 *>(dst)[q] = out[q];
+    }
+}
+
 // fs/solver.py:242-261  _non_advection_phase_grad (raw indexing -> clamp)
 template <bool P2, bool CL>
 __device__ __forceinline__ void b_cip_nonadv_grad(float *__restrict__ fxn, float *__restrict__ fyn, const float *__restrict__ fxc,
@@ -527,6 +598,15 @@ int fs2d_cip_nonadv(float *fn, const float *fc, const float *pc, const uint8_t *
         }
     }
     const float dx2 = dx * dx;
+    if (g_nonadv_vec && d.Y % 4 == 0 && (uintptr_t)fn % 16 == 0 && (uintptr_t)fc % 16 == 0 && (uintptr_t)pc % 16 == 0 &&
+        (uintptr_t)mask % 4 == 0) {
+        const dim3 g4((unsigned)((d.Y + 127) / 128), (unsigned)((d.r1 - d.r0 + NA4_WARPS - 1) / NA4_WARPS), 1), b4(32, NA4_WARPS, 1);
+#define NA4(P2) ++g_launches, k_cip_nonadv4<P2><<<g4, b4, 0, STREAM>>>(fn, fc, pc, mask, d, dt, DivC<P2>(dx), DivC<P2>(dx2), re)
+        DISPATCH_P2(is_pow2(dx), NA4(true), NA4(false));
+#undef NA4
+        FS2D_LAUNCH_CHECK();
+        return FS2D_OK;
+    }
 #define NA(P2) ++g_launches, k_cip_nonadv<P2><<<dense_grid_nu(d, NU_CIP_NONADV), dense_block(), 0, STREAM>>>(fn, fc, pc, mask, d, dt, DivC<P2>(dx), DivC<P2>(dx2), re)
     DISPATCH_P2(is_pow2(dx), NA(true), NA(false));
 #undef NA

@@ -312,7 +312,7 @@ static void launch_jacobi(float *pn, const float *pc, const float *src, const ui
 using namespace fs2d;
 #define STREAM ((cudaStream_t)stream)
 
-namespace fs2d { extern int g_dye_vec; }   // fs2d_dye.cu
+namespace fs2d { extern int g_dye_vec, g_nonadv_vec; }   // fs2d_dye.cu, fs2d_kernels.cu
 extern "C" {
 
 int fs2d_set_tuning(int key, int value) {
@@ -321,6 +321,7 @@ int fs2d_set_tuning(int key, int value) {
     if (key == 3 && value >= 0 && value <= 3) { fs2d::g_stream_cfg = value; return FS2D_OK; }
     if (key == 4 && (value == 0 || value == 1)) { fs2d::g_tail_emit = value; return FS2D_OK; }
     if (key == 5 && (value == 0 || value == 1)) { fs2d::g_dye_vec = value; return FS2D_OK; }
+    if (key == 6 && (value == 0 || value == 1)) { fs2d::g_nonadv_vec = value; return FS2D_OK; }
     set_error("unknown tuning key %d / value %d", key, value);
     return FS2D_E_BADARG;
 }

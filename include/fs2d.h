@@ -79,6 +79,7 @@ unsigned long long fs2d_launch_count(void);
  *         ONE literal iteration ends the update; 0: two literal iterations}.
  * key 5 = dye non-advection phase {1 (default): four cells per thread with 128-bit accesses when Y % 4 == 0 and the fields are
  *         16-byte aligned; 0: always one cell per thread}.
+ * key 6 = CIP non-advection phase of the velocity, the same choice {1 (default): four cells per thread; 0: one cell per thread}.
  * Unknown keys / values return FS2D_E_BADARG and change nothing. */
 int fs2d_set_tuning(int key, int value);
 /* 1 if the library was built for sm_100a and a device of compute capability 10.x is current */

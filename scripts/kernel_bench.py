@@ -21,6 +21,7 @@ for f in (s.v, s.vx, s.vy, s.p):
         f.current.tensor.fill_(0.25 if f is s.v else 0.0); f.next.tensor.zero_()
 from fs import _lib
 _lib.load().fs2d_set_tuning(3, int(os.environ.get("STREAM_CFG", "0")))
+_lib.load().fs2d_set_tuning(6, int(os.environ.get("NONADV_VEC", "1")))   # 0: the one-cell-per-thread cip_nonadv kernel
 print("fields:", MODE, "stream cfg", os.environ.get("STREAM_CFG", "0"))
 vc = s.vorticity_confinement
 cases = {

@@ -745,6 +745,39 @@ def test_stream_kernels_equal_direct_kernels(env, num, X, Y):
                 assert_bitexact(f"{name} bc{num} dx={dxv} dom={dom.r0}:{dom.r1}", a, b)
 
 
+@pytest.mark.parametrize("num,X,Y", [(1, 64, 8), (2, 256, 128), (3, 200, 132), (5, 333, 260)])
+def test_vectorised_nonadv_equals_one_cell_kernel(env, num, X, Y):
+    """cip_nonadv on four cells per thread (128-bit accesses, j-neighbours by shuffle; the default when Y % 4 == 0) vs the
+    one-cell-per-thread kernel (fs2d_set_tuning(6, 0)): widths of two lanes, one full warp, a warp plus one lane, two warps
+    plus one lane; whole grid and a row window with clamp bounds inside the array; both division instantiations."""
+    from fs.boundary_condition import BoundaryCondition, build_scene
+    from fs.fluid_simulator import make_solver
+
+    const, mask = build_scene(num, X, Y)
+    bc = BoundaryCondition(const, mask)
+    rng = np.random.default_rng(X + Y)
+    doms = [bc.dom, bc.dom.replace(r0=7, r1=X - 9, clo=3, chi=X - 4)]
+    for dxv in (1.0 / 128, 0.01):
+        s = make_solver(bc, 0.05 / 128, dxv, 1e3, 5.0, "cip", pressure="jacobi", n_iter=1)
+        init = {k: rng.uniform(-1, 1, getattr(s, k).current.tensor.shape).astype(np.float32) for k in ("v", "p")}
+        for dom in doms:
+            out = []
+            for vec in (1, 0):
+                assert env.fs2d_set_tuning(6, vec) == 0
+                old = bc.dom
+                try:
+                    s.v.current.from_numpy(init["v"]); s.v.next.from_numpy(init["v"][::-1].copy()); s.p.current.from_numpy(init["p"])
+                    bc.dom = dom
+                    s._non_advection_phase(s.v.next, s.v.current, s.p.current)
+                    out.append(s.v.next.to_numpy())
+                finally:
+                    bc.dom = old
+                    env.fs2d_set_tuning(6, 1)
+            assert_bitexact(f"nonadv bc{num} {X}x{Y} dx={dxv} dom={dom.r0}:{dom.r1}", out[0], out[1])
+            if (np.asarray(mask)[dom.r0:dom.r1] != 1).any():
+                assert not np.array_equal(out[0], init["v"][::-1])      # it did write
+
+
 def test_fused_pass_split_into_interior_and_edge_launches(env, X=1000, Y=512):
     """fs2d_jacobi_fused on an interior row window + fs2d_jacobi_fused_part on the remaining tile rows == one launch
     (what the multi-rank host does to hide the halo exchange)."""

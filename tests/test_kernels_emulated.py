@@ -52,6 +52,7 @@ test_emu_each_kernel_matches_reference_fixture = G.test_each_kernel_matches_refe
 test_emu_trajectory_matches_reference_fixture = G.test_trajectory_matches_reference_fixture
 test_emu_dye_trajectory_matches_reference_fixture = G.test_dye_trajectory_matches_reference_fixture
 test_emu_dye_step_from_random_state_vs_oracle = G.test_dye_step_from_random_state_vs_oracle
+test_emu_vectorised_nonadv_equals_one_cell_kernel = G.test_vectorised_nonadv_equals_one_cell_kernel
 test_emu_render_matches_reference_fixture = G.test_render_matches_reference_fixture
 test_emu_state_dict_roundtrip_resumes_bitwise = G.test_state_dict_roundtrip_resumes_bitwise
 test_emu_random_mask_trajectory_vs_oracle = G.test_random_mask_trajectory_vs_oracle
