@@ -57,7 +57,7 @@ def test_tma_kernels_use_tma_and_mbarriers(sass):
 
 
 def test_hot_kernels_do_not_spill(sass):
-    hot = ["k_jacobi_fused", "k_jacobi_fused_emit", "k_jacobi_march<false, 4>", "k_cip_nonadv<true>",
+    hot = ["k_jacobi_fused", "k_jacobi_fused_emit", "k_jacobi_march<false, 4>", "k_cip_nonadv<true>", "k_cip_nonadv4<true>",
            "k_cip_nonadv_grad<true>", "k_stream<OpAdvect<true>, 2, 3, 256>", "k_vort_apply<true>", "k_limit"]
     for name in hot:
         _, u = sass[name]
